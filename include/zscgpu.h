@@ -1,0 +1,168 @@
+/* zscgpu.h — the C-ABI of the B200 DEFLATE engine.
+ *
+ * This is the thin layer the host C code (zsc_b200/csrc/host/*.c, the zsc_pub.h surface) calls;
+ * it is also what a foreign-language binding (ctypes / cgo / JNI) would bind for batched,
+ * device-resident work.  Plain pointers and sizes only; no CUDA or torch types.
+ *
+ * Memory model ("no dynamic allocation after init", reference README.md:37-44 and the
+ * work-buffer carve-up at reference src/deflate.c:332-375): zscgpu_init() allocates every device
+ * arena and every pinned control block once; no later call allocates or frees anything.
+ *
+ *   raw  arena : uncompressed bytes (deflate input / inflate output)
+ *   comp arena : compressed bytes   (deflate output / inflate input)
+ *   sym  arena : LZ77 symbol scratch, 4 B per input byte of the largest deflate batch
+ *
+ * What each entry point replaces in the reference:
+ *   zscgpu_deflate_batch   the section loop of zsc_compress_gzip2 (src/zsc_compress.c:121-140) and
+ *                          everything below it: deflate() -> deflate_fast / deflate_slow /
+ *                          deflate_rle / deflate_huff / deflate_stored (src/deflate.c:1694-2245),
+ *                          longest_match (:1400), fill_window (:1532), _tr_flush_block and the
+ *                          Huffman stage (src/trees.c:426-993), zlib header/trailer
+ *                          (src/deflate.c:1029-1057, :1284-1285)
+ *   zscgpu_inflate_batch   the loop of zsc_uncompress_gzip2 (src/zsc_uncompr.c:103-127): inflate()
+ *                          (src/inflate.c:704-1404), inflate_table (src/inftrees.c:60),
+ *                          inflate_fast (src/inffast.c:76), inflateSync (src/inflate.c:1547)
+ *   zscgpu_adler32 / zscgpu_crc32   adler32_z (src/adler32.c:56), crc32_z (src/crc32.c:502)
+ *
+ * All functions return 0 on success or a negative zscgpu_status; stream-level results use the
+ * reference's ZlibReturn values (Z_OK 0, Z_DATA_ERROR -3, Z_BUF_ERROR -5 ...).
+ */
+#ifndef ZSCGPU_H
+#define ZSCGPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct zscgpu_engine zscgpu_engine;
+
+typedef enum {
+    ZSCGPU_OK = 0,
+    ZSCGPU_ERR_NO_DEVICE = -101,   /* no CUDA device / wrong architecture: there is NO CPU fallback */
+    ZSCGPU_ERR_CUDA = -102,        /* a CUDA runtime call failed; see zscgpu_last_error() */
+    ZSCGPU_ERR_CAPACITY = -103,    /* batch exceeds the arenas fixed at init */
+    ZSCGPU_ERR_ARG = -104
+} zscgpu_status;
+
+typedef struct {
+    int32_t  device;            /* CUDA device ordinal */
+    uint64_t raw_bytes;         /* capacity of the raw arena */
+    uint64_t comp_bytes;        /* capacity of the comp arena */
+    uint64_t deflate_batch_max; /* largest number of input bytes one zscgpu_deflate_batch may take */
+    uint32_t max_streams;       /* largest number of streams per batch */
+    uint32_t max_chunks;        /* largest number of chunks (sections and their sub-chunks) per batch */
+} zscgpu_config;
+
+/* One stream of a batch.  Offsets are byte offsets into the arenas. */
+typedef struct {
+    uint64_t raw_off;   /* deflate: input,  inflate: output */
+    uint32_t raw_len;   /* deflate: input length, inflate: output capacity */
+    uint32_t comp_len;  /* deflate: output capacity, inflate: input length */
+    uint64_t comp_off;  /* deflate: output, inflate: input */
+} zscgpu_stream;
+
+/* Per-stream results. */
+typedef struct {
+    int32_t  ret;       /* ZlibReturn of this stream */
+    uint32_t produced;  /* bytes written (deflate: compressed, inflate: uncompressed) */
+    uint32_t consumed;  /* bytes consumed of the input */
+    uint32_t check;     /* adler32 (zlib) or crc32 (gzip) of the uncompressed data */
+} zscgpu_result;
+
+/* Parameters of a deflate batch; same meaning and validation as zsc_compress2's arguments. */
+typedef struct {
+    uint32_t max_block_len;  /* section size; a full-flush marker follows every section but the last */
+    int32_t  level;          /* -1, 0..9 */
+    int32_t  strategy;       /* ZlibStrategy */
+    int32_t  wrap;           /* 0 raw deflate, 1 zlib (2-byte header + adler32), 2 gzip body: raw deflate,
+                                header/trailer added by the host layer, crc32 reported in result.check */
+    int32_t  window_bits;    /* 9..15 (0 = 15): largest match distance is 1 << window_bits */
+    int32_t  reserved;
+} zscgpu_deflate_params;
+
+void zscgpu_default_config(zscgpu_config *cfg);
+int  zscgpu_init(const zscgpu_config *cfg, zscgpu_engine **out);
+void zscgpu_destroy(zscgpu_engine *e);
+const char *zscgpu_last_error(const zscgpu_engine *e);   /* e may be NULL: last init error */
+const char *zscgpu_build_info(void);                     /* e.g. "sm_100a cuda 12.9" */
+
+/* Process-wide default engine used by the zsc_pub.h entry points.  zscgpu_global_init() is the
+ * explicit "init" of the no-allocation-after-init model; if the application never calls it, the
+ * first zsc_* call initialises an engine with zscgpu_default_config(). */
+int  zscgpu_global_init(const zscgpu_config *cfg);
+zscgpu_engine *zscgpu_global(void);
+void zscgpu_global_shutdown(void);
+
+/* Arena access (device pointers, for callers that produce or consume data on the GPU). */
+void    *zscgpu_raw_ptr(zscgpu_engine *e);
+void    *zscgpu_comp_ptr(zscgpu_engine *e);
+uint64_t zscgpu_raw_capacity(const zscgpu_engine *e);
+uint64_t zscgpu_comp_capacity(const zscgpu_engine *e);
+void    *zscgpu_cuda_stream(zscgpu_engine *e);   /* the cudaStream_t every kernel is launched on */
+
+/* Host <-> arena copies on the engine's stream; *_async returns after enqueueing. `which`: 0 raw, 1 comp. */
+int zscgpu_upload(zscgpu_engine *e, int which, uint64_t off, const void *host, uint64_t n);
+int zscgpu_download(zscgpu_engine *e, int which, void *host, uint64_t off, uint64_t n);
+int zscgpu_upload_async(zscgpu_engine *e, int which, uint64_t off, const void *host, uint64_t n);
+int zscgpu_download_async(zscgpu_engine *e, int which, void *host, uint64_t off, uint64_t n);
+int zscgpu_sync(zscgpu_engine *e);
+/* Device-to-device replicate inside an arena (bench: build config 4's 16x replicated streams). */
+int zscgpu_copy_within(zscgpu_engine *e, int which, uint64_t dst_off, uint64_t src_off, uint64_t n);
+
+/* Pinned host memory from the engine's fixed pool is not provided; callers may pin their own. */
+int zscgpu_host_register(void *p, uint64_t n);
+int zscgpu_host_unregister(void *p);
+
+/* Batched codec calls: inputs and outputs are resident in the arenas.  Blocking: results are valid
+ * on return.  n streams; res has n entries. */
+int zscgpu_deflate_batch(zscgpu_engine *e, const zscgpu_stream *streams, uint32_t n,
+                         const zscgpu_deflate_params *p, zscgpu_result *res);
+int zscgpu_inflate_batch(zscgpu_engine *e, const zscgpu_stream *streams, uint32_t n,
+                         int32_t wrap, zscgpu_result *res);
+
+/* Split calls used by the benchmark to time with CUDA events: enqueue only / fetch results. */
+int zscgpu_deflate_enqueue(zscgpu_engine *e, const zscgpu_stream *streams, uint32_t n,
+                           const zscgpu_deflate_params *p);
+int zscgpu_inflate_enqueue(zscgpu_engine *e, const zscgpu_stream *streams, uint32_t n, int32_t wrap);
+int zscgpu_fetch_results(zscgpu_engine *e, uint32_t n, zscgpu_result *res);
+/* Re-launch the kernels of the last enqueue without rebuilding descriptors (bench inner loop). */
+int zscgpu_relaunch(zscgpu_engine *e);
+uint32_t zscgpu_last_launch_count(const zscgpu_engine *e);
+
+/* One-shot calls on HOST buffers (what zsc_compress / zsc_uncompress / adler32 / crc32 use): copy in,
+ * run a batch of one stream at offset 0 of the arenas, copy out.  comp_skip leaves room at the start
+ * of dest for a wrapper the caller writes itself (gzip header). kind: 0 adler32, 1 crc32. */
+int zscgpu_compress_host(zscgpu_engine *e, uint8_t *dest, uint32_t dest_cap, const uint8_t *src,
+                         uint32_t src_len, const zscgpu_deflate_params *p, uint32_t comp_skip,
+                         zscgpu_result *res);
+int zscgpu_uncompress_host(zscgpu_engine *e, uint8_t *dest, uint32_t dest_cap, const uint8_t *src,
+                           uint32_t src_len, int32_t wrap, zscgpu_result *res);
+int zscgpu_checksum_host(zscgpu_engine *e, int kind, uint32_t init, const uint8_t *buf, uint64_t len,
+                         uint32_t *out);
+
+/* Checksums over raw-arena bytes [off, off+len): value continues from `init` (adler: 1, crc: 0 to start). */
+int zscgpu_adler32(zscgpu_engine *e, uint64_t off, uint64_t len, uint32_t init, uint32_t *out);
+int zscgpu_crc32(zscgpu_engine *e, uint64_t off, uint64_t len, uint32_t init, uint32_t *out);
+int zscgpu_adler32_enqueue(zscgpu_engine *e, uint64_t off, uint64_t len);
+int zscgpu_crc32_enqueue(zscgpu_engine *e, uint64_t off, uint64_t len);
+
+/* Event timing on the engine's stream (so a C or ctypes caller can time kernels on the launching
+ * stream without a CUDA binding of its own).  Slots 0..15. */
+int zscgpu_event_record(zscgpu_engine *e, int slot);
+int zscgpu_event_elapsed_ms(zscgpu_engine *e, int slot_start, int slot_stop, float *ms);
+
+/* Debug / test hooks: LZ77 symbols of chunk `chunk` of the last deflate batch. */
+int zscgpu_debug_fetch_symbols(zscgpu_engine *e, uint32_t chunk, uint32_t *out, uint32_t cap,
+                               uint32_t *nsym);
+
+/* Host-side checksum combination (the reference removed adler32_combine / crc32_combine,
+ * src/adler32.c:142-143, src/crc32.c:636-637; these follow from the definitions). */
+uint32_t zscgpu_adler32_combine(uint32_t adler1, uint32_t adler2, uint64_t len2);
+uint32_t zscgpu_crc32_combine(uint32_t crc1, uint32_t crc2, uint64_t len2);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,101 @@
+"""Test-side access to the checkers: oracle/_ref (the unmodified reference, compiled by oracle/Makefile),
+oracle/libzsc_oracle.so (our CPU restatement) and tests/libzsc_cpuharness.so (host build of product logic)."""
+import ctypes as C
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_PATH = os.path.join(ROOT, "oracle", "_ref", "libzsc_ref.so")
+ORACLE_PATH = os.path.join(ROOT, "oracle", "libzsc_oracle.so")
+HARNESS_PATH = os.path.join(ROOT, "tests", "libzsc_cpuharness.so")
+
+import sys
+sys.path.insert(0, ROOT)
+from zsc_b200.capi import Zsc, _declare_zsc, u8p, u32p  # noqa: E402
+
+
+def have_ref():
+    return os.path.exists(REF_PATH)
+
+
+_ref = None
+
+
+def ref():
+    """Zsc wrapper over the reference's own code."""
+    global _ref
+    if _ref is None:
+        L = C.CDLL(REF_PATH, mode=C.RTLD_LOCAL)
+        _declare_zsc(L)
+        L.refprobe_sizeof_deflate_state.restype = C.c_uint32
+        L.refprobe_sizeof_inflate_state.restype = C.c_uint32
+        _ref = Zsc(L)
+    return _ref
+
+
+_har = None
+
+
+def harness():
+    global _har
+    if _har is None:
+        L = C.CDLL(HARNESS_PATH, mode=C.RTLD_LOCAL)
+        L.h_inflate.argtypes = [u8p, C.c_uint32, u8p, C.c_uint32, C.c_int, u32p]
+        L.h_deflate_model.argtypes = [u8p, C.c_uint32, C.c_uint32, C.POINTER(C.c_int32), u8p, C.c_uint32, u32p, C.c_uint32, u32p]
+        L.h_deflate_model.restype = C.c_uint32
+        _har = L
+    return _har
+
+
+def h_inflate(comp, cap, wrap=1):
+    comp = np.ascontiguousarray(comp, dtype=np.uint8)
+    padded = np.zeros(len(comp) + 16, dtype=np.uint8)
+    padded[:len(comp)] = comp
+    out = np.zeros(max(cap, 1), dtype=np.uint8)
+    res = (C.c_uint32 * 7)()
+    harness().h_inflate(padded.ctypes.data_as(u8p), len(comp), out.ctypes.data_as(u8p), cap, wrap, res)
+    ret = C.c_int32(res[0]).value
+    return ret, out[:res[2]].copy(), dict(reason=res[1], produced=res[2], consumed=res[3], data_errors=res[4],
+                                          stored_check=res[5], have_check=res[6])
+
+
+# level -> [mode, chain, nice, lazy, min_len, max_dist, force_type, wrap, zhdr]; must mirror zs_lz_params (engine.cu)
+def lz_params(level, strategy=0, wrap=1, wbits=15):
+    if level == -1:
+        level = 6
+    chain = [0, 0, 1, 3, 7, 15, 127, 255, 1023, 4095][level]
+    nice = [0, 258, 258, 258, 32, 64, 128, 128, 258, 258][level]
+    lazy = [0, 0, 1, 1, 1, 1, 1, 1, 1, 1][level]
+    mode, min_len, force = 0, 3, -1
+    if strategy == 2:
+        mode = 2
+    elif strategy == 3:
+        mode, lazy = 1, 0
+    elif strategy == 1:
+        min_len = 6
+    elif strategy == 4:
+        force = 1
+    if level == 0:
+        mode, force = 2, 0
+    lf = 0 if (strategy >= 2 or level < 2) else (1 if level < 6 else (2 if level == 6 else 3))
+    hdr = ((8 + ((wbits - 8) << 4)) << 8) | (lf << 6)
+    hdr += 31 - (hdr % 31)
+    zhdr = (hdr >> 8) | ((hdr & 0xFF) << 8)
+    return [mode, chain, nice, lazy, min_len, 1 << wbits, force, wrap, zhdr]
+
+
+def model_deflate(src, max_block_len, level, strategy=0, wrap=1, wbits=15):
+    """Bit-exact CPU prediction of what the GPU deflate path must emit (stream at a 16-byte aligned offset)."""
+    src = np.ascontiguousarray(src, dtype=np.uint8)
+    n = len(src)
+    padded = np.zeros(n + 64, dtype=np.uint8)
+    padded[:n] = src
+    cap = n + n // 4 + 4096
+    out = np.zeros(cap, dtype=np.uint8)
+    syms = np.zeros(max(n, 1), dtype=np.uint32)
+    nsym = C.c_uint32(0)
+    p = (C.c_int32 * 9)(*lz_params(level, strategy, wrap, wbits))
+    sz = harness().h_deflate_model(padded.ctypes.data_as(u8p), n, max_block_len, p, out.ctypes.data_as(u8p), cap,
+                                   syms.ctypes.data_as(u32p), len(syms), C.byref(nsym))
+    return out[:sz].copy(), syms[:nsym.value].copy()

@@ -1,0 +1,370 @@
+/* deflate_huff.cu — block histogram + code construction, output-offset scan, bit packing (sm_100a).
+ *
+ * The GPU form of the reference's Huffman stage (src/trees.c): _tr_tally (include/zsc/deflate.h:338-354)
+ * becomes a per-block histogram over the symbol words the LZ kernel wrote; build_tree / gen_codes /
+ * send_all_trees become zh_build_block (huff_build.h); compress_block + send_bits + flush_pending
+ * (src/trees.c:948-993, :292-304, src/deflate.c:927) become a kernel in which every thread packs a run
+ * of 32 symbols at a bit offset that comes from a prefix sum, into a shared-memory image of the
+ * block that is then written to its final position in one coalesced pass.  Block, section and
+ * stream offsets come from one scan (zk_elem algebra) — nothing is compacted after the fact.
+ */
+#include "common.cuh"
+
+/* ======================= K2: histogram + codes ======================= */
+#define ZB_THREADS 128
+
+struct ZbSmem {
+    uint32_t lfreq[ZB_THREADS / 32][ZH_LCODES_PAD];
+    uint32_t dfreq[ZB_THREADS / 32][ZH_DCODES_PAD];
+    zh_scratch scratch;
+    zh_block blk;
+};
+
+__global__ void __launch_bounds__(ZB_THREADS)
+zs_block_kernel(const ZsChunk *__restrict__ chunks, const uint32_t *__restrict__ blk_chunk,
+                const uint32_t *__restrict__ sym, const uint32_t *__restrict__ chunk_nsym,
+                const uint32_t *__restrict__ blk_in_start, zh_block *__restrict__ blocks, ZsLzParams P)
+{
+    __shared__ ZbSmem S;
+    const uint32_t b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5;
+    const uint32_t c = blk_chunk[b];
+    const ZsChunk cd = chunks[c];
+    const uint32_t k = b - cd.blk_base;
+    const uint32_t nsym = chunk_nsym[c];
+    uint32_t nblk = (nsym + ZS_BLOCK_SYMS - 1) / ZS_BLOCK_SYMS;
+    if (nblk == 0) nblk = 1;
+    if (k >= nblk) { if (tid == 0) { blocks[b].type = ZH_UNUSED; blocks[b].flags = 0; } return; }
+    const uint32_t cnt = min(ZS_BLOCK_SYMS, nsym - k * ZS_BLOCK_SYMS);
+    const uint32_t *bs = sym + cd.sym_off + (uint64_t)k * ZS_BLOCK_SYMS;
+
+    for (uint32_t i = tid; i < (ZB_THREADS / 32) * ZH_LCODES_PAD; i += ZB_THREADS) (&S.lfreq[0][0])[i] = 0;
+    for (uint32_t i = tid; i < (ZB_THREADS / 32) * ZH_DCODES_PAD; i += ZB_THREADS) (&S.dfreq[0][0])[i] = 0;
+    __syncthreads();
+    for (uint32_t i = tid; i < cnt; i += ZB_THREADS) {
+        uint32_t s = bs[i];
+        if (s & ZS_MATCH) {
+            atomicAdd(&S.lfreq[warp][257 + zs_len_code((s >> 16) & 0xFF)], 1u);
+            atomicAdd(&S.dfreq[warp][zs_dist_code(s & 0x7FFF)], 1u);
+        } else {
+            atomicAdd(&S.lfreq[warp][s & 0xFF], 1u);
+        }
+    }
+    __syncthreads();
+    for (uint32_t i = tid; i < ZH_LCODES_PAD; i += ZB_THREADS) {
+        uint32_t v = 0;
+        for (int w = 0; w < ZB_THREADS / 32; w++) v += S.lfreq[w][i];
+        S.lfreq[0][i] = v + (i == 256 ? 1u : 0u);
+    }
+    if (tid < ZH_DCODES_PAD) {
+        uint32_t v = 0;
+        for (int w = 0; w < ZB_THREADS / 32; w++) v += S.dfreq[w][tid];
+        S.dfreq[0][tid] = v;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t in_start = blk_in_start[b];
+        uint32_t in_end = (k + 1 < nblk) ? blk_in_start[b + 1] : cd.len;
+        uint32_t flags = 0;
+        if (k == 0 && (cd.flags & ZC_FIRST_OF_STREAM)) flags |= ZB_FIRST_OF_STREAM;
+        if (k == nblk - 1 && (cd.flags & ZC_LAST_OF_SECTION)) flags |= ZB_LAST_OF_SECTION;
+        if (k == nblk - 1 && (cd.flags & ZC_LAST_OF_STREAM)) flags |= ZB_LAST_OF_STREAM;
+        zh_build_block(S.lfreq[0], S.dfreq[0], in_end - in_start, (flags & ZB_LAST_OF_STREAM) ? 1 : 0,
+                       P.force_type, &S.blk, &S.scratch);
+        S.blk.nsym = cnt;
+        S.blk.in_start = in_start;
+        S.blk.flags = flags;
+        S.blk.pad0 = 0;
+        S.blk.bitoff = 0;
+        S.blk.sym_off = cd.sym_off + (uint64_t)k * ZS_BLOCK_SYMS;
+    }
+    __syncthreads();
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(&S.blk);
+    uint32_t *dst = reinterpret_cast<uint32_t *>(&blocks[b]);
+    for (uint32_t i = tid; i < sizeof(zh_block) / 4; i += ZB_THREADS) dst[i] = src[i];
+}
+
+/* ======================= K2b: offsets, one CTA per stream ======================= */
+#define ZO_THREADS 256
+
+__global__ void __launch_bounds__(ZO_THREADS)
+zs_offset_kernel(const ZsStream *__restrict__ streams, const ZsChunk *__restrict__ chunks,
+                 const uint32_t *__restrict__ blk_chunk, zh_block *__restrict__ blocks,
+                 const ZsAdlerAcc *__restrict__ adler_acc, uint32_t *__restrict__ comp32,
+                 int32_t *__restrict__ res_ret, uint32_t *__restrict__ res_produced,
+                 uint32_t *__restrict__ res_check, ZsLzParams P)
+{
+    __shared__ zk_elem part[ZO_THREADS];
+    __shared__ uint64_t s_end;
+    __shared__ int s_fail;
+    const uint32_t sidx = blockIdx.x, tid = threadIdx.x;
+    const ZsStream st = streams[sidx];
+    const uint32_t per = (st.blk_count + ZO_THREADS - 1) / ZO_THREADS;
+    const uint32_t lo = min(st.blk_count, tid * per), hi = min(st.blk_count, lo + per);
+    zk_elem acc = zk_ident();
+    for (uint32_t i = lo; i < hi; i++) {
+        const zh_block *bp = &blocks[st.blk_first + i];
+        acc = zk_compose(acc, zk_elem_of_block(bp->type, bp->body_bits, bp->in_len, bp->flags, P.wrap));
+    }
+    part[tid] = acc;
+    __syncthreads();
+    if (tid == 0) {
+        zk_elem run = zk_ident();
+        for (int i = 0; i < ZO_THREADS; i++) { zk_elem t = part[i]; part[i] = run; run = zk_compose(run, t); }
+        uint64_t x0 = st.comp_off * 8ull;
+        uint64_t xe = zk_apply(run, x0);
+        uint64_t bytes = (xe - x0 + 7) >> 3;
+        int fail = bytes > st.comp_cap;
+        s_end = xe; s_fail = fail;
+        res_ret[sidx] = fail ? -5 /* Z_BUF_ERROR */ : 0;
+        res_produced[sidx] = fail ? 0u : (uint32_t)bytes;
+        uint32_t a = (uint32_t)(adler_acc[sidx].s1 % ZS_ADLER_BASE), bsum = (uint32_t)(adler_acc[sidx].s2 % ZS_ADLER_BASE);
+        /* adler32 of the stream = (1 + sum bytes, len + weighted sum) mod 65521 */
+        a = (a + 1) % ZS_ADLER_BASE;
+        bsum = (uint32_t)((bsum + (uint64_t)st.raw_len) % ZS_ADLER_BASE);
+        res_check[sidx] = (bsum << 16) | a;
+        if (!fail && (xe & 31)) comp32[xe >> 5] = 0;
+    }
+    __syncthreads();
+    const uint64_t x0 = st.comp_off * 8ull;
+    const int fail = s_fail;
+    uint64_t x = zk_apply(part[tid], x0);
+    for (uint32_t i = lo; i < hi; i++) {
+        zh_block *bp = &blocks[st.blk_first + i];
+        uint32_t type = bp->type;
+        if (type == ZH_UNUSED) continue;
+        bp->bitoff = x;
+        if (fail) bp->flags |= ZB_STREAM_FAILED; else comp32[x >> 5] = 0;
+        x = zk_apply(zk_elem_of_block(type, bp->body_bits, bp->in_len, bp->flags, P.wrap), x);
+    }
+}
+
+/* ======================= K3: bit packing, one CTA per block ======================= */
+#define ZE_THREADS 256
+#define ZE_RUN 32                                   /* symbols per thread */
+#define ZE_STAGE_WORDS 12480                        /* 16 + 3072 + 8192*48 + 15 + 47 bits, rounded up */
+
+struct ZeSmem {
+    uint32_t stage[ZE_STAGE_WORDS];
+    uint32_t lcode[ZH_LCODES_PAD];
+    uint32_t dcode[ZH_DCODES_PAD];
+    uint32_t lenmap[256];       /* (len code bits | extra << codelen) | nbits << 24 */
+    uint32_t wsum[ZE_THREADS / 32];
+    uint32_t total_bits;
+};
+
+static_assert(ZS_BLOCK_SYMS == ZE_THREADS * ZE_RUN, "one run of ZE_RUN symbols per thread");
+
+__device__ __forceinline__ void ze_or_bits(uint32_t *stage, uint32_t pos, uint64_t v, uint32_t n)
+{
+    /* n <= 33 bits at local bit position pos, shared-memory atomics (used at piece boundaries) */
+    if (n == 0) return;
+    uint32_t w = pos >> 5, sh = pos & 31;
+    unsigned long long t = (unsigned long long)v << sh;        /* n + sh <= 64 */
+    atomicOr(&stage[w], (uint32_t)t);
+    if (sh + n > 32) atomicOr(&stage[w + 1], (uint32_t)(t >> 32));
+}
+
+/* code bits of one symbol, split in two parts of <= 20 and <= 28 bits */
+__device__ __forceinline__ void ze_sym_bits(const ZeSmem &S, uint32_t s, uint32_t &v0, uint32_t &n0, uint32_t &v1, uint32_t &n1)
+{
+    if (s & ZS_MATCH) {
+        uint32_t lm = S.lenmap[(s >> 16) & 0xFF];
+        v0 = lm & 0xFFFFFFu; n0 = lm >> 24;
+        uint32_t d = s & 0x7FFF;
+        uint32_t dc, eb, ev;
+        if (d < 4) { dc = d; eb = 0; ev = 0; }
+        else { uint32_t n = 31u - (uint32_t)__clz((int)d); dc = (n << 1) | ((d >> (n - 1)) & 1u); eb = n - 1; ev = d & ((1u << eb) - 1u); }
+        uint32_t e = S.dcode[dc];
+        uint32_t cl = e >> 16;
+        v1 = (e & 0xFFFFu) | (ev << cl); n1 = cl + eb;
+    } else {
+        uint32_t e = S.lcode[s & 0xFF];
+        v0 = e & 0xFFFFu; n0 = e >> 16; v1 = 0; n1 = 0;
+    }
+}
+
+/* write one byte of the comp arena; words shared with neighbouring blocks go through atomics */
+__device__ __forceinline__ void ze_put_byte(uint8_t *comp, uint64_t pos, uint32_t v, uint64_t w_first, uint64_t w_last)
+{
+    uint64_t w = pos >> 2;
+    if (w == w_first || w == w_last) atomicOr(reinterpret_cast<uint32_t *>(comp) + w, v << (8 * (uint32_t)(pos & 3)));
+    else comp[pos] = (uint8_t)v;
+}
+
+__global__ void __launch_bounds__(ZE_THREADS)
+zs_encode_kernel(const zh_block *__restrict__ blocks, const uint32_t *__restrict__ blk_chunk,
+                 const ZsChunk *__restrict__ chunks, const uint32_t *__restrict__ sym,
+                 const uint8_t *__restrict__ raw, uint8_t *__restrict__ comp,
+                 const uint32_t *__restrict__ res_check, ZsLzParams P)
+{
+    extern __shared__ __align__(16) unsigned char ze_smem_raw[];
+    ZeSmem &S = *reinterpret_cast<ZeSmem *>(ze_smem_raw);
+    const uint32_t b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const zh_block *bp = &blocks[b];
+    const uint32_t type = bp->type, flags = bp->flags;
+    if (type == ZH_UNUSED || (flags & ZB_STREAM_FAILED)) return;
+    const ZsChunk cd = chunks[blk_chunk[b]];
+    const uint64_t x = bp->bitoff;
+    const zk_elem el = zk_elem_of_block(type, bp->body_bits, bp->in_len, flags, P.wrap);
+    const uint64_t xe = zk_apply(el, x);
+    const uint64_t w_first = x >> 5, w_last = (xe & 31) ? (xe >> 5) : ~0ull;
+    const uint32_t hdr_bits = bp->hdr_bits;
+    const uint32_t pre_bits = ((flags & ZB_FIRST_OF_STREAM) && P.wrap == 1) ? 16u : 0u;
+    uint32_t *comp32 = reinterpret_cast<uint32_t *>(comp);
+
+    /* suffix value: full-flush marker (00 00 FF FF) or big-endian adler32 */
+    uint32_t suf_bits = 0, suf_val = 0, suf_pre = 0;
+    if (flags & ZB_LAST_OF_STREAM) { if (P.wrap == 1) { suf_bits = 32; suf_val = __byte_perm(res_check[cd.stream], 0, 0x0123); } }
+    else if (flags & ZB_LAST_OF_SECTION) { suf_pre = 3; suf_bits = 32; suf_val = 0xFFFF0000u; }
+
+    if (type == ZH_STORED) {
+        /* [stream header][3-bit block header][pad][LEN][NLEN][bytes][suffix]: byte-granular writes */
+        const uint32_t in_len = bp->in_len;
+        const uint64_t hb = x + pre_bits;                 /* bit position of the block header */
+        const uint64_t d0 = (zk_up8(hb + 3) >> 3);        /* byte position of LEN */
+        if (tid == 0) {
+            /* leading bits: zlib header (if any) + 3 header bits, then zero pad */
+            uint64_t v = (pre_bits ? (uint64_t)(uint32_t)P.zhdr : 0ull) | ((uint64_t)(bp->hdr[0] & 7u) << pre_bits);
+            uint32_t sh = (uint32_t)(x & 7);
+            v <<= sh;
+            for (uint64_t p = x >> 3; p < d0; p++) { ze_put_byte(comp, p, (uint32_t)(v & 0xFF), w_first, w_last); v >>= 8; }
+            ze_put_byte(comp, d0, in_len & 0xFF, w_first, w_last);
+            ze_put_byte(comp, d0 + 1, (in_len >> 8) & 0xFF, w_first, w_last);
+            ze_put_byte(comp, d0 + 2, (~in_len) & 0xFF, w_first, w_last);
+            ze_put_byte(comp, d0 + 3, ((~in_len) >> 8) & 0xFF, w_first, w_last);
+            uint64_t p = d0 + 4 + in_len;
+            if (suf_pre) { ze_put_byte(comp, p, 0, w_first, w_last); p++; }
+            for (uint32_t i = 0; i < suf_bits / 8; i++) ze_put_byte(comp, p + i, (suf_val >> (8 * i)) & 0xFF, w_first, w_last);
+        }
+        const uint8_t *src = raw + cd.raw_off + bp->in_start;
+        for (uint32_t i = tid; i < in_len; i += ZE_THREADS) ze_put_byte(comp, d0 + 4 + i, src[i], w_first, w_last);
+        return;
+    }
+
+    /* ---- compressed block: build the bit image in shared memory ---- */
+    const uint32_t lbase = (uint32_t)(x & 31);            /* local bit position of the element start */
+    const uint32_t nsym = bp->nsym;
+    for (uint32_t i = tid; i < ZH_LCODES_PAD; i += ZE_THREADS) S.lcode[i] = bp->lcode[i];
+    if (tid < ZH_DCODES_PAD) S.dcode[tid] = bp->dcode[tid];
+    const uint32_t total_words = (uint32_t)(((xe - (x & ~31ull)) + 31) >> 5);
+    for (uint32_t i = tid; i < total_words + 1 && i < ZE_STAGE_WORDS; i += ZE_THREADS) S.stage[i] = 0;
+    __syncthreads();
+    {
+        /* length symbol -> packed code + extra bits */
+        uint32_t lc = tid;                                 /* ZE_THREADS == 256 */
+        int c = zs_len_code(lc);
+        uint32_t e = S.lcode[257 + c];
+        uint32_t cl = e >> 16;
+        uint32_t eb = (uint32_t)zh_extra_lbits(c);
+        uint32_t ev = eb ? (lc & ((1u << eb) - 1u)) : 0u;
+        S.lenmap[lc] = ((e & 0xFFFFu) | (ev << cl)) | ((cl + eb) << 24);
+    }
+    /* stream header + block header bits */
+    if (tid == 0 && pre_bits) ze_or_bits(S.stage, lbase, (uint32_t)P.zhdr, 16);
+    {
+        const uint32_t hpos = lbase + pre_bits;
+        const uint32_t hwords = (hdr_bits + 31) >> 5;
+        for (uint32_t i = tid; i < hwords; i += ZE_THREADS) {
+            uint32_t nb = min(32u, hdr_bits - i * 32);
+            uint32_t v = bp->hdr[i];
+            if (nb < 32) v &= (1u << nb) - 1u;
+            ze_or_bits(S.stage, hpos + i * 32, v, nb);
+        }
+    }
+    __syncthreads();
+
+    /* ---- pass 1: bits per thread run ---- */
+    uint32_t sy[ZE_RUN];
+    const uint32_t *bs = sym + bp->sym_off;
+    const uint32_t s0 = tid * ZE_RUN;
+#pragma unroll
+    for (int i = 0; i < ZE_RUN / 4; i++) {
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (s0 + i * 4 < nsym) v = __ldg(reinterpret_cast<const uint4 *>(bs + s0) + i);
+        sy[i * 4 + 0] = v.x; sy[i * 4 + 1] = v.y; sy[i * 4 + 2] = v.z; sy[i * 4 + 3] = v.w;
+    }
+    uint32_t mybits = 0;
+#pragma unroll
+    for (int i = 0; i < ZE_RUN; i++) {
+        if (s0 + i < nsym) { uint32_t v0, n0, v1, n1; ze_sym_bits(S, sy[i], v0, n0, v1, n1); mybits += n0 + n1; }
+    }
+    uint32_t inc = mybits;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, o); if ((int)lane >= o) inc += t; }
+    if (lane == 31) S.wsum[warp] = inc;
+    __syncthreads();
+    uint32_t wbase = 0;
+    for (uint32_t w = 0; w < warp; w++) wbase += S.wsum[w];
+    if (tid == ZE_THREADS - 1) S.total_bits = wbase + inc;
+    const uint32_t sympos = lbase + pre_bits + hdr_bits;
+    uint32_t pos = sympos + wbase + inc - mybits;
+
+    /* ---- pass 2: pack the run; only its first and last words can be shared with neighbours ---- */
+    if (mybits) {
+        uint32_t w = pos >> 5;
+        uint32_t fill = pos & 31;
+        unsigned long long acc = 0;
+        bool first = true;
+#pragma unroll
+        for (int i = 0; i < ZE_RUN; i++) {
+            if (s0 + i < nsym) {
+                uint32_t v0, n0, v1, n1;
+                ze_sym_bits(S, sy[i], v0, n0, v1, n1);
+                acc |= (unsigned long long)v0 << fill; fill += n0;
+                if (fill >= 32) {
+                    if (first) { atomicOr(&S.stage[w], (uint32_t)acc); first = false; } else S.stage[w] = (uint32_t)acc;
+                    w++; acc >>= 32; fill -= 32;
+                }
+                if (n1) {
+                    acc |= (unsigned long long)v1 << fill; fill += n1;
+                    if (fill >= 32) {
+                        if (first) { atomicOr(&S.stage[w], (uint32_t)acc); first = false; } else S.stage[w] = (uint32_t)acc;
+                        w++; acc >>= 32; fill -= 32;
+                    }
+                }
+            }
+        }
+        if (fill) atomicOr(&S.stage[w], (uint32_t)acc);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        /* end-of-block, then the suffix */
+        uint32_t p = sympos + S.total_bits;
+        uint32_t e = S.lcode[256];
+        ze_or_bits(S.stage, p, e & 0xFFFFu, e >> 16);
+        p += e >> 16;
+        if (flags & (ZB_LAST_OF_STREAM | ZB_LAST_OF_SECTION)) {
+            /* positions are relative to a word boundary, so byte alignment is preserved */
+            p += suf_pre;
+            p = (p + 7) & ~7u;
+            ze_or_bits(S.stage, p, suf_val, suf_bits);
+        }
+    }
+    __syncthreads();
+    /* ---- flush: interior words are owned by this block; boundary words are OR-ed ---- */
+    for (uint32_t i = tid; i < total_words; i += ZE_THREADS) {
+        uint64_t w = w_first + i;
+        uint32_t v = S.stage[i];
+        if (w == w_first || w == w_last) atomicOr(&comp32[w], v);
+        else comp32[w] = v;
+    }
+}
+
+extern "C" size_t zs_encode_smem_bytes(void) { return sizeof(ZeSmem); }
+
+extern "C" cudaError_t zs_huff_launch(cudaStream_t st, uint32_t nblk_slots, uint32_t nstreams,
+                                      const ZsChunk *chunks, const uint32_t *blk_chunk,
+                                      const ZsStream *streams, const uint32_t *sym,
+                                      const uint32_t *chunk_nsym, const uint32_t *blk_in_start,
+                                      zh_block *blocks, const ZsAdlerAcc *adler_acc,
+                                      const uint8_t *raw, uint8_t *comp, int32_t *res_ret,
+                                      uint32_t *res_produced, uint32_t *res_check, ZsLzParams P)
+{
+    if (nblk_slots == 0 || nstreams == 0) return cudaSuccess;
+    zs_block_kernel<<<nblk_slots, ZB_THREADS, 0, st>>>(chunks, blk_chunk, sym, chunk_nsym, blk_in_start, blocks, P);
+    zs_offset_kernel<<<nstreams, ZO_THREADS, 0, st>>>(streams, chunks, blk_chunk, blocks, adler_acc,
+                                                      reinterpret_cast<uint32_t *>(comp), res_ret, res_produced, res_check, P);
+    cudaFuncSetAttribute(zs_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ZeSmem));
+    zs_encode_kernel<<<nblk_slots, ZE_THREADS, sizeof(ZeSmem), st>>>(blocks, blk_chunk, chunks, sym, raw, comp, res_check, P);
+    return cudaGetLastError();
+}

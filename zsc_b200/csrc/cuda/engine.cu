@@ -1,0 +1,594 @@
+/* engine.cu — the C-ABI of the engine (include/zscgpu.h): arenas, descriptors, kernel sequencing.
+ *
+ * Everything is allocated in zscgpu_init(); later calls only fill pinned descriptor blocks, copy
+ * them to their device twins and launch kernels on the engine's one CUDA stream.
+ */
+#include <mutex>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include "common.cuh"
+#include "zscgpu.h"
+
+/* kernel launchers (deflate_lz.cu, deflate_huff.cu, checksum.cu, inflate.cu) */
+extern "C" cudaError_t zs_lz_launch(cudaStream_t, int, uint32_t, const uint8_t *, const ZsChunk *, uint32_t *, uint32_t *, uint32_t *, ZsLzParams);
+extern "C" cudaError_t zs_huff_launch(cudaStream_t, uint32_t, uint32_t, const ZsChunk *, const uint32_t *, const ZsStream *, const uint32_t *,
+                                      const uint32_t *, const uint32_t *, zh_block *, const ZsAdlerAcc *, const uint8_t *, uint8_t *,
+                                      int32_t *, uint32_t *, uint32_t *, ZsLzParams);
+extern "C" cudaError_t zs_adler_chunks_launch(cudaStream_t, uint32_t, const uint8_t *, const ZsChunk *, const ZsStream *, ZsAdlerAcc *);
+extern "C" cudaError_t zs_adler_flat_launch(cudaStream_t, const uint8_t *, uint64_t, ZsAdlerAcc *, int);
+extern "C" cudaError_t zs_crc_init_launch(cudaStream_t);
+extern "C" cudaError_t zs_crc_flat_launch(cudaStream_t, const uint8_t *, uint64_t, uint32_t, uint32_t *, int);
+extern "C" cudaError_t zs_inflate_launch(cudaStream_t, uint32_t, const ZsStream *, const uint8_t *, uint8_t *, int32_t,
+                                         int32_t *, uint32_t *, uint32_t *, uint32_t *, uint32_t *, ZsAdlerAcc *, uint32_t);
+
+#define ZS_NEVENTS 16
+
+struct zscgpu_engine {
+    zscgpu_config cfg;
+    int sms;
+    cudaStream_t stream;
+    uint8_t *d_raw, *d_comp;
+    uint32_t *d_sym;
+    uint64_t sym_cap;                 /* symbols */
+    uint32_t blk_cap;                 /* block slots */
+    /* descriptors: pinned host + device twins */
+    ZsChunk *h_chunks, *d_chunks;
+    ZsStream *h_streams, *d_streams;
+    uint32_t *h_blk_chunk, *d_blk_chunk;
+    uint32_t *d_chunk_nsym, *d_blk_in_start;
+    zh_block *d_blocks;
+    ZsAdlerAcc *d_adler;              /* per stream; slot max_streams is the flat-checksum slot */
+    uint32_t *d_crc;                  /* [2] */
+    uint32_t *d_aux;                  /* inflate: [2 * max_streams] trailer check + flags */
+    uint32_t last_max_raw;
+    int32_t *d_ret, *h_ret;
+    uint32_t *d_produced, *h_produced, *d_consumed, *h_consumed, *d_check, *h_check;
+    cudaEvent_t ev[ZS_NEVENTS];
+    /* last enqueue, for zscgpu_relaunch */
+    int last_kind;                    /* 0 none, 1 deflate, 2 inflate */
+    uint32_t last_nstreams, last_nchunks, last_nblk;
+    int last_chain;
+    int32_t last_wrap;
+    ZsLzParams last_lz;
+    uint32_t launches;
+    std::mutex mu;
+    char err[512];
+};
+
+static char g_init_err[512];
+static zscgpu_engine *g_engine;
+static std::mutex g_mu;
+
+static int zs_fail(zscgpu_engine *e, cudaError_t ce, const char *what, int line)
+{
+    char *dst = e ? e->err : g_init_err;
+    snprintf(dst, 512, "CUDA error %d (%s) at engine.cu:%d: %s", (int)ce, cudaGetErrorString(ce), line, what);
+    return ZSCGPU_ERR_CUDA;
+}
+
+extern "C" const char *zscgpu_last_error(const zscgpu_engine *e) { return e ? e->err : g_init_err; }
+extern "C" const char *zscgpu_build_info(void) { return "zsc-b200 engine: sm_100a, CUDA " ZS_STR(CUDART_VERSION); }
+
+extern "C" void zscgpu_default_config(zscgpu_config *cfg)
+{
+    memset(cfg, 0, sizeof(*cfg));
+    cfg->device = 0;
+    cfg->raw_bytes = (1ull << 30) + (64ull << 20);
+    cfg->comp_bytes = (1ull << 30) + (192ull << 20);
+    cfg->deflate_batch_max = (1ull << 30) + (64ull << 20);
+    cfg->max_streams = 1u << 16;
+    cfg->max_chunks = 1u << 18;
+}
+
+template <typename T> static cudaError_t zs_pinned(T **p, size_t n) { return cudaHostAlloc((void **)p, n * sizeof(T), cudaHostAllocDefault); }
+template <typename T> static cudaError_t zs_dev(T **p, size_t n) { return cudaMalloc((void **)p, n * sizeof(T)); }
+
+extern "C" int zscgpu_init(const zscgpu_config *cfg_in, zscgpu_engine **out)
+{
+    zscgpu_engine *e = nullptr;
+    if (!out) return ZSCGPU_ERR_ARG;
+    *out = nullptr;
+    zscgpu_config cfg;
+    if (cfg_in) cfg = *cfg_in; else zscgpu_default_config(&cfg);
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev <= cfg.device) {
+        snprintf(g_init_err, sizeof(g_init_err), "no CUDA device %d (%s): the zsc-b200 engine has no CPU fallback",
+                 cfg.device, ce != cudaSuccess ? cudaGetErrorString(ce) : "device count too small");
+        return ZSCGPU_ERR_NO_DEVICE;
+    }
+    cudaDeviceProp prop;
+    ZS_CUDA_CHECK(cudaGetDeviceProperties(&prop, cfg.device));
+    if (prop.major != 10) {
+        snprintf(g_init_err, sizeof(g_init_err), "device %d is sm_%d%d; this library carries sm_100a code only",
+                 cfg.device, prop.major, prop.minor);
+        return ZSCGPU_ERR_NO_DEVICE;
+    }
+    ZS_CUDA_CHECK(cudaSetDevice(cfg.device));
+    e = new zscgpu_engine();
+    e->cfg = cfg;
+    e->sms = prop.multiProcessorCount;
+    e->err[0] = 0;
+    e->last_kind = 0;
+    e->launches = 0;
+    ZS_CUDA_CHECK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    /* arenas, padded so that vector loads and word-granular stores at the ends stay inside */
+    ZS_CUDA_CHECK(zs_dev(&e->d_raw, cfg.raw_bytes + 4096));
+    ZS_CUDA_CHECK(zs_dev(&e->d_comp, cfg.comp_bytes + 4096));
+    e->sym_cap = cfg.deflate_batch_max + 4ull * cfg.max_chunks + 64;
+    ZS_CUDA_CHECK(zs_dev(&e->d_sym, e->sym_cap));
+    e->blk_cap = (uint32_t)(cfg.deflate_batch_max / ZS_BLOCK_SYMS) + cfg.max_chunks + 1;
+    ZS_CUDA_CHECK(zs_pinned(&e->h_chunks, cfg.max_chunks));
+    ZS_CUDA_CHECK(zs_dev(&e->d_chunks, cfg.max_chunks));
+    ZS_CUDA_CHECK(zs_pinned(&e->h_streams, cfg.max_streams));
+    ZS_CUDA_CHECK(zs_dev(&e->d_streams, cfg.max_streams));
+    ZS_CUDA_CHECK(zs_pinned(&e->h_blk_chunk, e->blk_cap));
+    ZS_CUDA_CHECK(zs_dev(&e->d_blk_chunk, e->blk_cap));
+    ZS_CUDA_CHECK(zs_dev(&e->d_chunk_nsym, cfg.max_chunks));
+    ZS_CUDA_CHECK(zs_dev(&e->d_blk_in_start, e->blk_cap + 1));
+    ZS_CUDA_CHECK(zs_dev(&e->d_blocks, e->blk_cap));
+    ZS_CUDA_CHECK(zs_dev(&e->d_adler, cfg.max_streams + 1));
+    ZS_CUDA_CHECK(zs_dev(&e->d_crc, 4));
+    ZS_CUDA_CHECK(zs_dev(&e->d_aux, 2ull * cfg.max_streams));
+    ZS_CUDA_CHECK(zs_dev(&e->d_ret, cfg.max_streams));
+    ZS_CUDA_CHECK(zs_dev(&e->d_produced, cfg.max_streams));
+    ZS_CUDA_CHECK(zs_dev(&e->d_consumed, cfg.max_streams));
+    ZS_CUDA_CHECK(zs_dev(&e->d_check, cfg.max_streams));
+    ZS_CUDA_CHECK(zs_pinned(&e->h_ret, cfg.max_streams));
+    ZS_CUDA_CHECK(zs_pinned(&e->h_produced, cfg.max_streams));
+    ZS_CUDA_CHECK(zs_pinned(&e->h_consumed, cfg.max_streams));
+    ZS_CUDA_CHECK(zs_pinned(&e->h_check, cfg.max_streams + 4));
+    for (int i = 0; i < ZS_NEVENTS; i++) ZS_CUDA_CHECK(cudaEventCreate(&e->ev[i]));
+    ZS_CUDA_CHECK(zs_crc_init_launch(e->stream));
+    ZS_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    *out = e;
+    return ZSCGPU_OK;
+}
+
+extern "C" void zscgpu_destroy(zscgpu_engine *e)
+{
+    if (!e) return;
+    cudaStreamSynchronize(e->stream);
+    cudaFree(e->d_raw); cudaFree(e->d_comp); cudaFree(e->d_sym);
+    cudaFreeHost(e->h_chunks); cudaFree(e->d_chunks);
+    cudaFreeHost(e->h_streams); cudaFree(e->d_streams);
+    cudaFreeHost(e->h_blk_chunk); cudaFree(e->d_blk_chunk);
+    cudaFree(e->d_chunk_nsym); cudaFree(e->d_blk_in_start); cudaFree(e->d_blocks);
+    cudaFree(e->d_adler); cudaFree(e->d_crc); cudaFree(e->d_aux);
+    cudaFree(e->d_ret); cudaFree(e->d_produced); cudaFree(e->d_consumed); cudaFree(e->d_check);
+    cudaFreeHost(e->h_ret); cudaFreeHost(e->h_produced); cudaFreeHost(e->h_consumed); cudaFreeHost(e->h_check);
+    for (int i = 0; i < ZS_NEVENTS; i++) cudaEventDestroy(e->ev[i]);
+    cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+extern "C" int zscgpu_global_init(const zscgpu_config *cfg)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_engine) return ZSCGPU_OK;
+    return zscgpu_init(cfg, &g_engine);
+}
+extern "C" zscgpu_engine *zscgpu_global(void)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g_engine) (void)zscgpu_init(nullptr, &g_engine);
+    return g_engine;
+}
+extern "C" void zscgpu_global_shutdown(void)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    zscgpu_destroy(g_engine);
+    g_engine = nullptr;
+}
+
+extern "C" void *zscgpu_raw_ptr(zscgpu_engine *e) { return e->d_raw; }
+extern "C" void *zscgpu_comp_ptr(zscgpu_engine *e) { return e->d_comp; }
+extern "C" uint64_t zscgpu_raw_capacity(const zscgpu_engine *e) { return e->cfg.raw_bytes; }
+extern "C" uint64_t zscgpu_comp_capacity(const zscgpu_engine *e) { return e->cfg.comp_bytes; }
+extern "C" void *zscgpu_cuda_stream(zscgpu_engine *e) { return (void *)e->stream; }
+
+static int zs_arena(zscgpu_engine *e, int which, uint64_t off, uint64_t n, uint8_t **p)
+{
+    uint64_t cap = which ? e->cfg.comp_bytes : e->cfg.raw_bytes;
+    if (off > cap || n > cap - off) { snprintf(e->err, sizeof(e->err), "arena range out of bounds"); return ZSCGPU_ERR_CAPACITY; }
+    *p = (which ? e->d_comp : e->d_raw) + off;
+    return ZSCGPU_OK;
+}
+extern "C" int zscgpu_upload_async(zscgpu_engine *e, int which, uint64_t off, const void *host, uint64_t n)
+{
+    uint8_t *p; int r = zs_arena(e, which, off, n, &p); if (r) return r;
+    if (n) ZS_CUDA_CHECK(cudaMemcpyAsync(p, host, n, cudaMemcpyHostToDevice, e->stream));
+    return ZSCGPU_OK;
+}
+extern "C" int zscgpu_download_async(zscgpu_engine *e, int which, void *host, uint64_t off, uint64_t n)
+{
+    uint8_t *p; int r = zs_arena(e, which, off, n, &p); if (r) return r;
+    if (n) ZS_CUDA_CHECK(cudaMemcpyAsync(host, p, n, cudaMemcpyDeviceToHost, e->stream));
+    return ZSCGPU_OK;
+}
+extern "C" int zscgpu_sync(zscgpu_engine *e) { ZS_CUDA_CHECK(cudaStreamSynchronize(e->stream)); return ZSCGPU_OK; }
+extern "C" int zscgpu_upload(zscgpu_engine *e, int which, uint64_t off, const void *host, uint64_t n)
+{
+    int r = zscgpu_upload_async(e, which, off, host, n); if (r) return r;
+    return zscgpu_sync(e);
+}
+extern "C" int zscgpu_download(zscgpu_engine *e, int which, void *host, uint64_t off, uint64_t n)
+{
+    int r = zscgpu_download_async(e, which, host, off, n); if (r) return r;
+    return zscgpu_sync(e);
+}
+extern "C" int zscgpu_copy_within(zscgpu_engine *e, int which, uint64_t dst_off, uint64_t src_off, uint64_t n)
+{
+    uint8_t *d, *s;
+    int r = zs_arena(e, which, dst_off, n, &d); if (r) return r;
+    r = zs_arena(e, which, src_off, n, &s); if (r) return r;
+    if (n) ZS_CUDA_CHECK(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToDevice, e->stream));
+    return ZSCGPU_OK;
+}
+extern "C" int zscgpu_host_register(void *p, uint64_t n)
+{
+    cudaError_t ce = cudaHostRegister(p, n, cudaHostRegisterDefault);
+    return ce == cudaSuccess ? ZSCGPU_OK : ZSCGPU_ERR_CUDA;
+}
+extern "C" int zscgpu_host_unregister(void *p) { return cudaHostUnregister(p) == cudaSuccess ? ZSCGPU_OK : ZSCGPU_ERR_CUDA; }
+
+extern "C" int zscgpu_event_record(zscgpu_engine *e, int slot)
+{
+    if (slot < 0 || slot >= ZS_NEVENTS) return ZSCGPU_ERR_ARG;
+    ZS_CUDA_CHECK(cudaEventRecord(e->ev[slot], e->stream));
+    return ZSCGPU_OK;
+}
+extern "C" int zscgpu_event_elapsed_ms(zscgpu_engine *e, int a, int b, float *ms)
+{
+    if (a < 0 || a >= ZS_NEVENTS || b < 0 || b >= ZS_NEVENTS) return ZSCGPU_ERR_ARG;
+    ZS_CUDA_CHECK(cudaEventSynchronize(e->ev[b]));
+    ZS_CUDA_CHECK(cudaEventElapsedTime(ms, e->ev[a], e->ev[b]));
+    return ZSCGPU_OK;
+}
+
+/* ----------------------------- deflate ----------------------------- */
+
+/* level/strategy -> search parameters.  The reference's configuration_table (src/deflate.c:146-158)
+ * tunes a serial hash-chain search; these are the equivalents for the group-parallel search,
+ * chosen so the ratio stays within 2 % of the reference at the same level (tests/test_ratio.py). */
+static int zs_lz_params(const zscgpu_deflate_params *p, ZsLzParams *L, int *chain_kernel)
+{
+    int level = p->level == -1 ? 6 : p->level;
+    if (level < 0 || level > 9 || p->strategy < 0 || p->strategy > 4 || p->wrap < 0 || p->wrap > 2) return -1;
+    memset(L, 0, sizeof(*L));
+    L->mode = 0; L->min_len = 3; L->force_type = -1; L->wrap = p->wrap;
+    static const int chain_tab[10] = {0, 0, 1, 3, 7, 15, 127, 255, 1023, 4095};
+    static const int nice_tab[10] = {0, 258, 258, 258, 32, 64, 128, 128, 258, 258};
+    static const int lazy_tab[10] = {0, 0, 1, 1, 1, 1, 1, 1, 1, 1};
+    L->chain = chain_tab[level]; L->nice = nice_tab[level]; L->lazy = lazy_tab[level];
+    if (p->strategy == 2 /* Z_HUFFMAN_ONLY */) L->mode = 2;
+    else if (p->strategy == 3 /* Z_RLE */) { L->mode = 1; L->lazy = 0; }
+    else if (p->strategy == 1 /* Z_FILTERED */) L->min_len = 6;
+    else if (p->strategy == 4 /* Z_FIXED */) L->force_type = ZH_STATIC;
+    if (level == 0) { L->mode = 2; L->force_type = ZH_STORED; }
+    *chain_kernel = (L->mode == 0 && L->chain > 0) ? 1 : 0;
+    int wbits = p->window_bits ? p->window_bits : 15;
+    if (wbits < 9 || wbits > 15) return -1;
+    L->max_dist = 1 << wbits;
+    /* zlib header (RFC 1950): CMF = method 8 + window size; FLG carries the level class
+       (same values as reference src/deflate.c:1029-1049) */
+    int lf = (p->strategy >= 2 || level < 2) ? 0 : (level < 6 ? 1 : (level == 6 ? 2 : 3));
+    uint32_t hdr = ((8u + ((uint32_t)(wbits - 8) << 4)) << 8) | ((uint32_t)lf << 6);
+    hdr += 31 - (hdr % 31);
+    L->zhdr = (int32_t)((hdr >> 8) | ((hdr & 0xFF) << 8));
+    return 0;
+}
+
+static int zs_build_deflate_desc(zscgpu_engine *e, const zscgpu_stream *streams, uint32_t n, uint32_t mbl,
+                                 uint32_t *nchunks_out, uint32_t *nblk_out)
+{
+    uint64_t sym = 0, total = 0;
+    uint32_t nc = 0, nb = 0;
+    for (uint32_t s = 0; s < n; s++) {
+        const zscgpu_stream *z = &streams[s];
+        if (z->raw_off > e->cfg.raw_bytes || z->raw_len > e->cfg.raw_bytes - z->raw_off ||
+            z->comp_off > e->cfg.comp_bytes || z->comp_len > e->cfg.comp_bytes - z->comp_off) {
+            snprintf(e->err, sizeof(e->err), "stream %u lies outside the arenas", s);
+            return ZSCGPU_ERR_CAPACITY;
+        }
+        ZsStream *S = &e->h_streams[s];
+        S->raw_off = z->raw_off; S->comp_off = z->comp_off; S->raw_len = z->raw_len; S->comp_cap = z->comp_len;
+        S->blk_first = nb; S->chunk_first = nc;
+        total += z->raw_len;
+        uint32_t pos = 0;
+        do {
+            uint32_t sec = z->raw_len - pos < mbl ? z->raw_len - pos : mbl;
+            uint32_t nsub = sec ? (sec + ZS_CHUNK_MAX - 1) / ZS_CHUNK_MAX : 1;
+            for (uint32_t j = 0; j < nsub; j++) {
+                if (nc >= e->cfg.max_chunks) { snprintf(e->err, sizeof(e->err), "batch needs more than max_chunks=%u chunks", e->cfg.max_chunks); return ZSCGPU_ERR_CAPACITY; }
+                uint32_t coff = j * ZS_CHUNK_MAX;
+                uint32_t clen = sec - coff < ZS_CHUNK_MAX ? sec - coff : ZS_CHUNK_MAX;
+                ZsChunk *C = &e->h_chunks[nc];
+                C->raw_off = z->raw_off + pos + coff;
+                C->sym_off = sym;
+                C->len = clen;
+                C->dict_len = coff < ZS_WINDOW ? coff : ZS_WINDOW;
+                C->blk_base = nb;
+                C->blk_cap = clen ? (clen + ZS_BLOCK_SYMS - 1) / ZS_BLOCK_SYMS : 1;
+                C->stream = s;
+                C->flags = 0;
+                if (pos == 0 && j == 0) C->flags |= ZC_FIRST_OF_STREAM;
+                if (j == nsub - 1) {
+                    C->flags |= ZC_LAST_OF_SECTION;
+                    if (pos + sec >= z->raw_len) C->flags |= ZC_LAST_OF_STREAM;
+                }
+                if ((uint64_t)nb + C->blk_cap > e->blk_cap) { snprintf(e->err, sizeof(e->err), "batch needs too many block slots"); return ZSCGPU_ERR_CAPACITY; }
+                for (uint32_t k = 0; k < C->blk_cap; k++) e->h_blk_chunk[nb + k] = nc;
+                nb += C->blk_cap;
+                sym += ((uint64_t)clen + 3) & ~3ull;
+                if (clen == 0) sym += 4;
+                nc++;
+            }
+            pos += sec;
+        } while (pos < z->raw_len);
+        S->blk_count = nb - S->blk_first; S->chunk_count = nc - S->chunk_first;
+    }
+    if (total > e->cfg.deflate_batch_max || sym > e->sym_cap) {
+        snprintf(e->err, sizeof(e->err), "deflate batch of %llu bytes exceeds deflate_batch_max=%llu",
+                 (unsigned long long)total, (unsigned long long)e->cfg.deflate_batch_max);
+        return ZSCGPU_ERR_CAPACITY;
+    }
+    *nchunks_out = nc; *nblk_out = nb;
+    return ZSCGPU_OK;
+}
+
+static int zs_deflate_launch_all(zscgpu_engine *e)
+{
+    const uint32_t n = e->last_nstreams, nc = e->last_nchunks, nb = e->last_nblk;
+    ZS_CUDA_CHECK(cudaMemsetAsync(e->d_adler, 0, sizeof(ZsAdlerAcc) * n, e->stream));
+    ZS_CUDA_CHECK(zs_adler_chunks_launch(e->stream, nc, e->d_raw, e->d_chunks, e->d_streams, e->d_adler));
+    ZS_CUDA_CHECK(zs_lz_launch(e->stream, e->last_chain, nc, e->d_raw, e->d_chunks, e->d_sym, e->d_chunk_nsym, e->d_blk_in_start, e->last_lz));
+    ZS_CUDA_CHECK(zs_huff_launch(e->stream, nb, n, e->d_chunks, e->d_blk_chunk, e->d_streams, e->d_sym, e->d_chunk_nsym,
+                                 e->d_blk_in_start, e->d_blocks, e->d_adler, e->d_raw, e->d_comp, e->d_ret, e->d_produced, e->d_check, e->last_lz));
+    ZS_CUDA_CHECK(cudaMemcpyAsync(e->h_ret, e->d_ret, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, e->stream));
+    ZS_CUDA_CHECK(cudaMemcpyAsync(e->h_produced, e->d_produced, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, e->stream));
+    ZS_CUDA_CHECK(cudaMemcpyAsync(e->h_check, e->d_check, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, e->stream));
+    e->launches = 5;   /* adler, lz, block, offset, encode */
+    return ZSCGPU_OK;
+}
+
+extern "C" int zscgpu_deflate_enqueue(zscgpu_engine *e, const zscgpu_stream *streams, uint32_t n, const zscgpu_deflate_params *p)
+{
+    std::lock_guard<std::mutex> lk(e->mu);
+    if (!streams || !p || n == 0 || n > e->cfg.max_streams || p->max_block_len == 0) { snprintf(e->err, sizeof(e->err), "bad deflate batch arguments"); return ZSCGPU_ERR_ARG; }
+    ZsLzParams L; int chain;
+    if (zs_lz_params(p, &L, &chain)) { snprintf(e->err, sizeof(e->err), "bad level/strategy/wrap"); return ZSCGPU_ERR_ARG; }
+    uint32_t nc = 0, nb = 0;
+    int r = zs_build_deflate_desc(e, streams, n, p->max_block_len, &nc, &nb);
+    if (r) return r;
+    ZS_CUDA_CHECK(cudaMemcpyAsync(e->d_chunks, e->h_chunks, sizeof(ZsChunk) * nc, cudaMemcpyHostToDevice, e->stream));
+    ZS_CUDA_CHECK(cudaMemcpyAsync(e->d_streams, e->h_streams, sizeof(ZsStream) * n, cudaMemcpyHostToDevice, e->stream));
+    ZS_CUDA_CHECK(cudaMemcpyAsync(e->d_blk_chunk, e->h_blk_chunk, sizeof(uint32_t) * nb, cudaMemcpyHostToDevice, e->stream));
+    e->last_kind = 1; e->last_nstreams = n; e->last_nchunks = nc; e->last_nblk = nb; e->last_chain = chain; e->last_lz = L;
+    return zs_deflate_launch_all(e);
+}
+
+static int zs_inflate_launch_all(zscgpu_engine *e)
+{
+    const uint32_t n = e->last_nstreams;
+    ZS_CUDA_CHECK(zs_inflate_launch(e->stream, n, e->d_streams, e->d_comp, e->d_raw, e->last_wrap, e->d_ret, e->d_produced, e->d_consumed, e->d_check,
+                                    e->d_aux, e->d_adler, e->last_max_raw));
+    ZS_CUDA_CHECK(cudaMemcpyAsync(e->h_ret, e->d_ret, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, e->stream));
+    ZS_CUDA_CHECK(cudaMemcpyAsync(e->h_produced, e->d_produced, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, e->stream));
+    ZS_CUDA_CHECK(cudaMemcpyAsync(e->h_consumed, e->d_consumed, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, e->stream));
+    ZS_CUDA_CHECK(cudaMemcpyAsync(e->h_check, e->d_check, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, e->stream));
+    e->launches = 3;   /* inflate, output adler, check */
+    return ZSCGPU_OK;
+}
+
+extern "C" int zscgpu_inflate_enqueue(zscgpu_engine *e, const zscgpu_stream *streams, uint32_t n, int32_t wrap)
+{
+    std::lock_guard<std::mutex> lk(e->mu);
+    if (!streams || n == 0 || n > e->cfg.max_streams || (wrap & 0xFF) > 1 || wrap < 0) { snprintf(e->err, sizeof(e->err), "bad inflate batch arguments"); return ZSCGPU_ERR_ARG; }
+    uint32_t max_raw = 0;
+    for (uint32_t s = 0; s < n; s++) {
+        const zscgpu_stream *z = &streams[s];
+        if (z->raw_off > e->cfg.raw_bytes || z->raw_len > e->cfg.raw_bytes - z->raw_off ||
+            z->comp_off > e->cfg.comp_bytes || z->comp_len > e->cfg.comp_bytes - z->comp_off) {
+            snprintf(e->err, sizeof(e->err), "stream %u lies outside the arenas", s);
+            return ZSCGPU_ERR_CAPACITY;
+        }
+        ZsStream *S = &e->h_streams[s];
+        memset(S, 0, sizeof(*S));
+        S->raw_off = z->raw_off; S->comp_off = z->comp_off; S->raw_len = z->raw_len; S->comp_cap = z->comp_len;
+        if (z->raw_len > max_raw) max_raw = z->raw_len;
+    }
+    ZS_CUDA_CHECK(cudaMemcpyAsync(e->d_streams, e->h_streams, sizeof(ZsStream) * n, cudaMemcpyHostToDevice, e->stream));
+    e->last_max_raw = max_raw;
+    e->last_kind = 2; e->last_nstreams = n; e->last_wrap = wrap;
+    return zs_inflate_launch_all(e);
+}
+
+extern "C" int zscgpu_relaunch(zscgpu_engine *e)
+{
+    std::lock_guard<std::mutex> lk(e->mu);
+    if (e->last_kind == 1) return zs_deflate_launch_all(e);
+    if (e->last_kind == 2) return zs_inflate_launch_all(e);
+    return ZSCGPU_ERR_ARG;
+}
+extern "C" uint32_t zscgpu_last_launch_count(const zscgpu_engine *e) { return e->launches; }
+
+extern "C" int zscgpu_fetch_results(zscgpu_engine *e, uint32_t n, zscgpu_result *res)
+{
+    std::lock_guard<std::mutex> lk(e->mu);
+    if (n != e->last_nstreams || !res) return ZSCGPU_ERR_ARG;
+    ZS_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    for (uint32_t i = 0; i < n; i++) {
+        res[i].ret = e->h_ret[i];
+        res[i].produced = e->h_produced[i];
+        res[i].consumed = e->last_kind == 2 ? e->h_consumed[i] : e->h_streams[i].raw_len;
+        res[i].check = e->h_check[i];
+    }
+    return ZSCGPU_OK;
+}
+
+extern "C" int zscgpu_deflate_batch(zscgpu_engine *e, const zscgpu_stream *streams, uint32_t n, const zscgpu_deflate_params *p, zscgpu_result *res)
+{
+    int r = zscgpu_deflate_enqueue(e, streams, n, p);
+    if (r) return r;
+    return zscgpu_fetch_results(e, n, res);
+}
+extern "C" int zscgpu_inflate_batch(zscgpu_engine *e, const zscgpu_stream *streams, uint32_t n, int32_t wrap, zscgpu_result *res)
+{
+    int r = zscgpu_inflate_enqueue(e, streams, n, wrap);
+    if (r) return r;
+    return zscgpu_fetch_results(e, n, res);
+}
+
+/* ----------------------------- one-shot host-buffer calls ----------------------------- */
+/* The zsc_pub.h entry points land here: copy in, run the batch of one stream, copy out.  `call_mu`
+ * serialises whole calls because they all use offset 0 of the arenas. */
+static std::mutex g_call_mu;
+
+extern "C" int zscgpu_compress_host(zscgpu_engine *e, uint8_t *dest, uint32_t dest_cap, const uint8_t *src, uint32_t src_len,
+                                    const zscgpu_deflate_params *p, uint32_t comp_skip, zscgpu_result *res)
+{
+    std::lock_guard<std::mutex> lk(g_call_mu);
+    if ((uint64_t)src_len > e->cfg.raw_bytes || (uint64_t)src_len > e->cfg.deflate_batch_max) {
+        snprintf(e->err, sizeof(e->err), "source of %u bytes exceeds the engine's arenas (raw %llu B)", src_len, (unsigned long long)e->cfg.raw_bytes);
+        return ZSCGPU_ERR_CAPACITY;
+    }
+    int r = zscgpu_upload_async(e, 0, 0, src, src_len); if (r) return r;
+    zscgpu_stream st;
+    st.raw_off = 0; st.raw_len = src_len; st.comp_off = comp_skip;
+    uint64_t cap = dest_cap > comp_skip ? dest_cap - comp_skip : 0;
+    if (cap > e->cfg.comp_bytes - comp_skip) cap = e->cfg.comp_bytes - comp_skip;
+    st.comp_len = (uint32_t)cap;
+    r = zscgpu_deflate_enqueue(e, &st, 1, p); if (r) return r;
+    if (p->wrap == 2) { r = zscgpu_crc32_enqueue(e, 0, src_len); if (r) return r; }
+    r = zscgpu_fetch_results(e, 1, res); if (r) return r;
+    if (p->wrap == 2) {
+        uint32_t h[2];
+        ZS_CUDA_CHECK(cudaMemcpyAsync(h, e->d_crc, 8, cudaMemcpyDeviceToHost, e->stream));
+        ZS_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+        res->check = h[1];
+    }
+    if (res->ret == 0 && res->produced) return zscgpu_download(e, 1, dest + comp_skip, comp_skip, res->produced);
+    return ZSCGPU_OK;
+}
+
+extern "C" int zscgpu_uncompress_host(zscgpu_engine *e, uint8_t *dest, uint32_t dest_cap, const uint8_t *src, uint32_t src_len,
+                                      int32_t wrap, zscgpu_result *res)
+{
+    std::lock_guard<std::mutex> lk(g_call_mu);
+    if ((uint64_t)src_len > e->cfg.comp_bytes) {
+        snprintf(e->err, sizeof(e->err), "source of %u bytes exceeds the comp arena (%llu B)", src_len, (unsigned long long)e->cfg.comp_bytes);
+        return ZSCGPU_ERR_CAPACITY;
+    }
+    int r = zscgpu_upload_async(e, 1, 0, src, src_len); if (r) return r;
+    zscgpu_stream st;
+    st.raw_off = 0; st.comp_off = 0; st.comp_len = src_len;
+    st.raw_len = (uint64_t)dest_cap > e->cfg.raw_bytes ? (uint32_t)e->cfg.raw_bytes : dest_cap;
+    r = zscgpu_inflate_batch(e, &st, 1, wrap, res); if (r) return r;
+    if (res->produced) return zscgpu_download(e, 0, dest, 0, res->produced);
+    return ZSCGPU_OK;
+}
+
+extern "C" int zscgpu_checksum_host(zscgpu_engine *e, int kind, uint32_t init, const uint8_t *buf, uint64_t len, uint32_t *out)
+{
+    std::lock_guard<std::mutex> lk(g_call_mu);
+    uint32_t v = init;
+    uint64_t done = 0;
+    do {
+        uint64_t n = len - done < e->cfg.raw_bytes ? len - done : e->cfg.raw_bytes;
+        int r = zscgpu_upload_async(e, 0, 0, buf + done, n); if (r) return r;
+        r = kind ? zscgpu_crc32(e, 0, n, v, &v) : zscgpu_adler32(e, 0, n, v, &v); if (r) return r;
+        done += n;
+    } while (done < len);
+    *out = v;
+    return ZSCGPU_OK;
+}
+
+/* ----------------------------- checksums ----------------------------- */
+extern "C" int zscgpu_adler32_enqueue(zscgpu_engine *e, uint64_t off, uint64_t len)
+{
+    uint8_t *p; int r = zs_arena(e, 0, off, len, &p); if (r) return r;
+    ZsAdlerAcc *acc = e->d_adler + e->cfg.max_streams;
+    ZS_CUDA_CHECK(cudaMemsetAsync(acc, 0, sizeof(ZsAdlerAcc), e->stream));
+    if (len) ZS_CUDA_CHECK(zs_adler_flat_launch(e->stream, p, len, acc, e->sms));
+    e->launches = 1;
+    return ZSCGPU_OK;
+}
+extern "C" int zscgpu_adler32(zscgpu_engine *e, uint64_t off, uint64_t len, uint32_t init, uint32_t *out)
+{
+    std::lock_guard<std::mutex> lk(e->mu);
+    int r = zscgpu_adler32_enqueue(e, off, len); if (r) return r;
+    ZsAdlerAcc h;
+    ZS_CUDA_CHECK(cudaMemcpyAsync(&h, e->d_adler + e->cfg.max_streams, sizeof(h), cudaMemcpyDeviceToHost, e->stream));
+    ZS_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    /* fold the running value in: a = a0 + S1, b = b0 + len * a0 + S2  (a0 = 1, b0 = 0 for a fresh sum) */
+    uint64_t a0 = init & 0xFFFF, b0 = (init >> 16) & 0xFFFF;
+    uint64_t a = (a0 + h.s1 % ZS_ADLER_BASE) % ZS_ADLER_BASE;
+    uint64_t b = (b0 + (len % ZS_ADLER_BASE) * a0 + h.s2 % ZS_ADLER_BASE) % ZS_ADLER_BASE;
+    *out = (uint32_t)((b << 16) | a);
+    return ZSCGPU_OK;
+}
+extern "C" int zscgpu_crc32_enqueue(zscgpu_engine *e, uint64_t off, uint64_t len)
+{
+    uint8_t *p; int r = zs_arena(e, 0, off, len, &p); if (r) return r;
+    ZS_CUDA_CHECK(cudaMemsetAsync(e->d_crc, 0, 8, e->stream));
+    ZS_CUDA_CHECK(zs_crc_flat_launch(e->stream, p, len, 0, e->d_crc, e->sms));
+    e->launches = 2;
+    return ZSCGPU_OK;
+}
+extern "C" int zscgpu_crc32(zscgpu_engine *e, uint64_t off, uint64_t len, uint32_t init, uint32_t *out)
+{
+    std::lock_guard<std::mutex> lk(e->mu);
+    uint8_t *p; int r = zs_arena(e, 0, off, len, &p); if (r) return r;
+    ZS_CUDA_CHECK(cudaMemsetAsync(e->d_crc, 0, 8, e->stream));
+    ZS_CUDA_CHECK(zs_crc_flat_launch(e->stream, p, len, init, e->d_crc, e->sms));
+    uint32_t h[2];
+    ZS_CUDA_CHECK(cudaMemcpyAsync(h, e->d_crc, 8, cudaMemcpyDeviceToHost, e->stream));
+    ZS_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    *out = h[1];
+    return ZSCGPU_OK;
+}
+
+/* ----------------------------- debug ----------------------------- */
+extern "C" int zscgpu_debug_fetch_symbols(zscgpu_engine *e, uint32_t chunk, uint32_t *out, uint32_t cap, uint32_t *nsym)
+{
+    std::lock_guard<std::mutex> lk(e->mu);
+    if (e->last_kind != 1 || chunk >= e->last_nchunks) return ZSCGPU_ERR_ARG;
+    ZS_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    uint32_t n = 0;
+    ZS_CUDA_CHECK(cudaMemcpy(&n, e->d_chunk_nsym + chunk, 4, cudaMemcpyDeviceToHost));
+    *nsym = n;
+    if (n > cap) n = cap;
+    if (n) ZS_CUDA_CHECK(cudaMemcpy(out, e->d_sym + e->h_chunks[chunk].sym_off, 4ull * n, cudaMemcpyDeviceToHost));
+    return ZSCGPU_OK;
+}
+
+/* ----------------------------- host-side combination ----------------------------- */
+extern "C" uint32_t zscgpu_adler32_combine(uint32_t adler1, uint32_t adler2, uint64_t len2)
+{
+    /* a = a1 + a2 - 1;  b = b1 + b2 + len2 * (a1 - 1)   (mod 65521) */
+    const uint64_t B = ZS_ADLER_BASE;
+    uint64_t a1 = adler1 & 0xFFFF, b1 = adler1 >> 16, a2 = adler2 & 0xFFFF, b2 = adler2 >> 16;
+    uint64_t a = (a1 + a2 + B - 1) % B;
+    uint64_t b = (b1 + b2 + (len2 % B) * ((a1 + B - 1) % B)) % B;
+    return (uint32_t)((b << 16) | a);
+}
+static uint32_t zs_h_multmodp(uint32_t a, uint32_t b)
+{
+    uint32_t m = 1u << 31, p = 0;
+    for (;;) {
+        if (a & m) { p ^= b; if ((a & (m - 1)) == 0) break; }
+        m >>= 1;
+        b = (b & 1) ? (b >> 1) ^ 0xEDB88320u : b >> 1;
+    }
+    return p;
+}
+extern "C" uint32_t zscgpu_crc32_combine(uint32_t crc1, uint32_t crc2, uint64_t len2)
+{
+    /* crc(A||B) = crc(A) * x^(8 len2) + crc(B) over GF(2)[x]/P: the pre/post inversions cancel */
+    uint32_t x2n = 1u << 30, p = 1u << 31;
+    uint64_t n = len2 * 8;
+    while (n) { if (n & 1) p = zs_h_multmodp(x2n, p); x2n = zs_h_multmodp(x2n, x2n); n >>= 1; }
+    return zs_h_multmodp(p, crc1) ^ crc2;
+}

@@ -1,0 +1,65 @@
+/* inflate.cu — batched inflate: one thread per stream, decode tables in shared memory (sm_100a).
+ *
+ * GPU form of zsc_uncompress's hot loop (reference src/zsc_uncompr.c:103-127 -> inflate /
+ * inflate_fast / inflate_table).  Streams are independent, so the batch is spread one stream per
+ * thread; the 32 threads of a warp keep their 32 sets of tables (1856 B each, inflate_core.h) in
+ * shared memory and decode in lockstep, which works well because reference-compressed streams end
+ * their blocks on the same symbol count.  The data check (adler32 of the output against the
+ * trailer, reference src/inflate.c:1322-1342) is a second, HBM-streaming pass over the output.
+ */
+#include "common.cuh"
+#include "inflate_core.h"
+
+#define ZI_THREADS 32
+
+__global__ void __launch_bounds__(ZI_THREADS)
+zs_inflate_kernel(uint32_t n, const ZsStream *__restrict__ streams, const uint8_t *__restrict__ comp,
+                  uint8_t *__restrict__ raw, int32_t wrap, int32_t *__restrict__ ret,
+                  uint32_t *__restrict__ produced, uint32_t *__restrict__ consumed,
+                  uint32_t *__restrict__ aux /* [2n]: stored check, flags */)
+{
+    extern __shared__ __align__(16) unsigned char zi_smem_raw[];
+    zi_tables *T = reinterpret_cast<zi_tables *>(zi_smem_raw) + threadIdx.x;
+    const uint32_t s = blockIdx.x * ZI_THREADS + threadIdx.x;
+    if (s >= n) return;
+    const ZsStream st = streams[s];
+    zi_result res;
+    zi_inflate(comp + st.comp_off, st.comp_cap, raw + st.raw_off, st.raw_len, wrap, T, &res);
+    ret[s] = res.ret;
+    produced[s] = res.produced;
+    consumed[s] = res.consumed;
+    aux[2 * s] = res.stored_check;
+    aux[2 * s + 1] = res.have_check | (res.data_errors ? 2u : 0u);
+}
+
+__global__ void zs_inflate_check_kernel(uint32_t n, const ZsAdlerAcc *__restrict__ acc, const uint32_t *__restrict__ produced,
+                                        const uint32_t *__restrict__ aux, int32_t wrap, int32_t *__restrict__ ret,
+                                        uint32_t *__restrict__ check)
+{
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    uint32_t a = (uint32_t)((acc[s].s1 + 1) % ZS_ADLER_BASE);
+    uint32_t b = (uint32_t)((acc[s].s2 + produced[s]) % ZS_ADLER_BASE);
+    uint32_t v = (b << 16) | a;
+    check[s] = v;
+    if ((wrap & 0xFF) == 1 && ret[s] == 0 && (aux[2 * s + 1] & 1u) && aux[2 * s] != v) ret[s] = -3;   /* incorrect data check */
+}
+
+extern "C" cudaError_t zs_adler_streams_launch(cudaStream_t st, uint32_t n, uint32_t max_len, const uint8_t *raw,
+                                               const ZsStream *streams, const uint32_t *produced, ZsAdlerAcc *acc);
+
+extern "C" cudaError_t zs_inflate_launch(cudaStream_t st, uint32_t n, const ZsStream *streams, const uint8_t *comp,
+                                         uint8_t *raw, int32_t wrap, int32_t *ret, uint32_t *produced,
+                                         uint32_t *consumed, uint32_t *check, uint32_t *aux, ZsAdlerAcc *acc,
+                                         uint32_t max_raw_len)
+{
+    if (n == 0) return cudaSuccess;
+    const size_t smem = sizeof(zi_tables) * ZI_THREADS;
+    cudaFuncSetAttribute(zs_inflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    zs_inflate_kernel<<<(n + ZI_THREADS - 1) / ZI_THREADS, ZI_THREADS, smem, st>>>(n, streams, comp, raw, wrap, ret, produced, consumed, aux);
+    cudaMemsetAsync(acc, 0, sizeof(ZsAdlerAcc) * n, st);
+    cudaError_t ce = zs_adler_streams_launch(st, n, max_raw_len, raw, streams, produced, acc);
+    if (ce != cudaSuccess) return ce;
+    zs_inflate_check_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, acc, produced, aux, wrap, ret, check);
+    return cudaGetLastError();
+}

@@ -1,0 +1,398 @@
+/* inflate_core.h — one DEFLATE/zlib stream decoded by one thread (host + device).
+ *
+ * Covers what zsc_uncompress needs of the reference's inflate (src/inflate.c:704-1404: zlib header
+ * :740-785, block types :975-1009, stored :1010-1049, dynamic header :1050-1178, data check
+ * :1322-1342), inflate_table (src/inftrees.c:60-358), inflate_fast (src/inffast.c:76-314) and the
+ * corruption recovery of zsc_uncompress_gzip2 (src/zsc_uncompr.c:103-127 with inflateSync,
+ * src/inflate.c:1523-1604) — for the case zsc_uncompress always has: all input and all output
+ * present, so there is no resumable state machine and no sliding window (matches are copied
+ * straight out of the output buffer, as the reference itself does on that path, src/inflate.c:1380).
+ *
+ * The decode tables are NOT the reference's op/bits/val two-level tables: each alphabet gets one
+ * direct-lookup table of 16-bit entries (9 / 6 index bits) plus the canonical-code arrays
+ * (symbols sorted by length, per-length counts) that resolve the rare longer codes by
+ * first-code comparison.  That keeps a stream's tables under 2 KiB so that 32 streams fit in one
+ * warp's shared memory.
+ *
+ * Error behaviour follows the reference: any malformed header, code set, code, distance or
+ * data check yields Z_DATA_ERROR (-3); running out of output room or input yields Z_BUF_ERROR (-5).
+ * The functions are `__host__ __device__` so tests/ can run the GPU's exact decode logic on the
+ * CPU against the reference's known-answer vectors.
+ */
+#ifndef ZSC_INFLATE_CORE_H
+#define ZSC_INFLATE_CORE_H
+
+#include <stdint.h>
+
+#ifdef __CUDACC__
+#define ZID __host__ __device__
+#else
+#define ZID
+#endif
+
+#define ZI_LBITS 9
+#define ZI_DBITS 6
+
+#define ZI_OK 0
+#define ZI_NEED_DICT 2
+#define ZI_DATA_ERROR (-3)
+#define ZI_BUF_ERROR (-5)
+
+/* fine-grained reason, mirrors the reference's strm->msg strings (src/inflate.c, src/inffast.c) */
+enum {
+    ZI_E_NONE = 0, ZI_E_HEADER_CHECK, ZI_E_METHOD, ZI_E_WINDOW, ZI_E_BLOCK_TYPE, ZI_E_STORED_LEN,
+    ZI_E_TOO_MANY_SYMS, ZI_E_CODELEN_SET, ZI_E_BITLEN_REPEAT, ZI_E_NO_EOB, ZI_E_LITLEN_SET,
+    ZI_E_DIST_SET, ZI_E_LITLEN_CODE, ZI_E_DIST_CODE, ZI_E_DIST_TOO_FAR, ZI_E_DATA_CHECK,
+    ZI_E_INPUT_END, ZI_E_OUTPUT_FULL, ZI_E_NEED_DICT
+};
+
+typedef struct {
+    uint16_t lit[1 << ZI_LBITS];     /* sym | len << 9 ; 0 = code longer than ZI_LBITS */
+    uint16_t dist[1 << ZI_DBITS];    /* sym | len << 5 ; 0 = longer */
+    uint16_t lsorted[288];
+    uint16_t dsorted[32];
+    uint16_t lcount[16];
+    uint16_t dcount[16];
+} zi_tables;
+
+typedef struct {
+    const uint8_t *in;      /* stream start */
+    uint32_t in_len;
+    uint32_t ip;            /* next input byte to load */
+    uint64_t hold;
+    uint32_t bits;
+    uint8_t *out;
+    uint32_t out_cap;
+    uint32_t op;
+} zi_io;
+
+typedef struct {
+    int32_t ret;            /* ZI_OK / ZI_DATA_ERROR / ZI_BUF_ERROR / ZI_NEED_DICT */
+    int32_t reason;         /* first ZI_E_* seen */
+    uint32_t produced;
+    uint32_t consumed;
+    uint32_t data_errors;   /* corrupted sections skipped */
+    uint32_t stored_check;  /* adler32 from the trailer */
+    uint32_t have_check;    /* trailer was reached */
+} zi_result;
+
+ZID static inline void zi_refill(zi_io *io)
+{
+#ifdef __CUDA_ARCH__
+    /* 4-byte aligned loads once the cursor is aligned; the arenas are padded, and bits past in_len
+       are never consumed (zi_overrun is checked before anything derived from them is used) */
+    if (io->bits <= 32) {
+        const uint8_t *p = io->in + io->ip;
+        while ((((uintptr_t)p) & 3) != 0 && io->bits <= 56) { io->hold |= (uint64_t)(*p++) << io->bits; io->bits += 8; io->ip++; }
+        if (io->bits <= 32) {
+            io->hold |= (uint64_t)(*reinterpret_cast<const uint32_t *>(p)) << io->bits;
+            io->bits += 32; io->ip += 4;
+        }
+    }
+#else
+    while (io->bits <= 56) {
+        uint8_t b = io->ip < io->in_len ? io->in[io->ip] : 0;
+        io->hold |= (uint64_t)b << io->bits; io->bits += 8; io->ip++;
+    }
+#endif
+}
+/* true when more bits were consumed than the input holds */
+ZID static inline int zi_overrun(const zi_io *io) { return (uint64_t)io->ip * 8 - io->bits > (uint64_t)io->in_len * 8; }
+ZID static inline uint32_t zi_peek(const zi_io *io, int n) { return (uint32_t)io->hold & ((1u << n) - 1u); }
+ZID static inline void zi_drop(zi_io *io, int n) { io->hold >>= n; io->bits -= (uint32_t)n; }
+ZID static inline uint32_t zi_take(zi_io *io, int n) { uint32_t v = zi_peek(io, n); zi_drop(io, n); return v; }
+ZID static inline uint32_t zi_take32(zi_io *io) { uint32_t v = (uint32_t)io->hold; zi_drop(io, 32); return v; }
+ZID static inline uint32_t zi_consumed_bytes(const zi_io *io) { return (uint32_t)(((uint64_t)io->ip * 8 - io->bits + 7) >> 3); }
+
+ZID static inline uint32_t zi_rev(uint32_t v, int n)
+{
+#ifdef __CUDA_ARCH__
+    return __brev(v) >> (32 - n);
+#endif
+    uint32_t r = 0;
+    for (int i = 0; i < n; i++) { r = (r << 1) | (v & 1); v >>= 1; }
+    return r;
+}
+
+/* Build one alphabet's tables from code lengths. kind 0: code-length/literal alphabets must be
+ * complete; an incomplete set is tolerated only when its longest code is 1 bit and kind != 0
+ * (same rule as the reference, src/inftrees.c:168-177).  Returns 0 or -1. */
+ZID static inline int zi_build(const uint8_t *lens, int n, int tbits, uint16_t *table, uint16_t *sorted,
+                               uint16_t *count, int shift, int allow_incomplete)
+{
+    uint16_t offs[16];
+    for (int i = 0; i < 16; i++) count[i] = 0;
+    for (int i = 0; i < n; i++) count[lens[i]]++;
+    for (int i = 0; i < (1 << tbits); i++) table[i] = 0;
+    int maxl = 15;
+    while (maxl > 0 && count[maxl] == 0) maxl--;
+    if (maxl == 0) { count[0] = 0; return allow_incomplete ? 0 : -1; }   /* no codes: any use is an error */
+    int left = 1;
+    for (int l = 1; l <= 15; l++) { left <<= 1; left -= count[l]; if (left < 0) return -1; }
+    if (left > 0 && (!allow_incomplete || maxl != 1)) return -1;
+    offs[1] = 0;
+    for (int l = 1; l < 15; l++) offs[l + 1] = (uint16_t)(offs[l] + count[l]);
+    for (int i = 0; i < n; i++) if (lens[i]) sorted[offs[lens[i]]++] = (uint16_t)i;
+    count[0] = 0;
+    /* direct table: canonical codes in (length, symbol) order */
+    uint32_t code = 0; int k = 0;
+    for (int l = 1; l <= maxl && l <= tbits; l++) {
+        for (int c = 0; c < count[l]; c++, k++, code++) {
+            uint32_t r = zi_rev(code, l);
+            uint16_t e = (uint16_t)(sorted[k] | (l << shift));
+            for (uint32_t j = r; j < (1u << tbits); j += (1u << l)) table[j] = e;
+        }
+        code <<= 1;
+    }
+    return 0;
+}
+
+/* Decode one symbol. Returns the symbol or -1 (invalid code). */
+ZID static inline int zi_decode(zi_io *io, const uint16_t *table, int tbits, const uint16_t *sorted,
+                                const uint16_t *count, int shift)
+{
+    uint32_t e = table[zi_peek(io, tbits)];
+    if (e) { zi_drop(io, (int)(e >> shift)); return (int)(e & ((1u << shift) - 1u)); }
+    /* longer than tbits: canonical first-code walk over the bit-reversed prefix */
+    uint32_t v = zi_rev(zi_peek(io, 15), 15);
+    uint32_t first = 0, index = 0;
+    for (int l = 1; l <= 15; l++) {
+        uint32_t c = count[l];
+        uint32_t code = v >> (15 - l);
+        if (l > tbits && code - first < c) { zi_drop(io, l); return (int)sorted[index + (code - first)]; }
+        index += c; first = (first + c) << 1;
+    }
+    return -1;
+}
+
+ZID static inline int zi_fail(zi_result *r, int ret, int reason)
+{
+    if (r->reason == ZI_E_NONE) r->reason = reason;
+    r->ret = ret;
+    return ret;
+}
+
+/* Decode deflate blocks until the final block ends (returns ZI_OK) or an error. `lens` is a scratch
+ * area of >= 320 bytes that may alias T->lit (it is dead before the tables are filled). */
+ZID static inline int zi_blocks(zi_io *io, zi_tables *T, zi_result *res, uint32_t win_size)
+{
+    const uint8_t order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+    for (;;) {
+        zi_refill(io);
+        uint32_t last = zi_take(io, 1), type = zi_take(io, 2);
+        if (zi_overrun(io)) return zi_fail(res, ZI_BUF_ERROR, ZI_E_INPUT_END);
+        if (type == 3) return zi_fail(res, ZI_DATA_ERROR, ZI_E_BLOCK_TYPE);
+        if (type == 0) {
+            zi_drop(io, (int)(io->bits & 7));
+            zi_refill(io);
+            uint32_t v = zi_take32(io);
+            if (zi_overrun(io)) return zi_fail(res, ZI_BUF_ERROR, ZI_E_INPUT_END);
+            uint32_t len = v & 0xFFFF;
+            if (len != ((v >> 16) ^ 0xFFFF)) return zi_fail(res, ZI_DATA_ERROR, ZI_E_STORED_LEN);
+            /* rewind the bit buffer to a byte cursor */
+            uint32_t pos = io->ip - (io->bits >> 3);
+            io->hold = 0; io->bits = 0; io->ip = pos;
+            uint32_t n = len;
+            int short_in = 0, short_out = 0;
+            if (n > io->in_len - (pos < io->in_len ? pos : io->in_len)) { n = io->in_len - (pos < io->in_len ? pos : io->in_len); short_in = 1; }
+            if (n > io->out_cap - io->op) { n = io->out_cap - io->op; short_out = 1; short_in = 0; }
+            for (uint32_t i = 0; i < n; i++) io->out[io->op + i] = io->in[pos + i];
+            io->op += n; io->ip = pos + n;
+            if (short_out) return zi_fail(res, ZI_BUF_ERROR, ZI_E_OUTPUT_FULL);
+            if (short_in) return zi_fail(res, ZI_BUF_ERROR, ZI_E_INPUT_END);
+        } else {
+            if (type == 1) {
+                /* fixed code (RFC 1951 3.2.6): 32 five-bit distance codes (30 and 31 are invalid when
+                   used, src/inflate.c:122-206), literal/length lengths 8/9/7/8 in closed form */
+                uint8_t tmp[32];
+                for (int i = 0; i < 32; i++) tmp[i] = 5;
+                (void)zi_build(tmp, 32, ZI_DBITS, T->dist, T->dsorted, T->dcount, 5, 1);
+                for (int i = 0; i < 16; i++) T->lcount[i] = 0;
+                T->lcount[7] = 24; T->lcount[8] = 152; T->lcount[9] = 112;
+                int k = 0;
+                for (int i = 256; i < 280; i++) T->lsorted[k++] = (uint16_t)i;
+                for (int i = 0; i < 144; i++) T->lsorted[k++] = (uint16_t)i;
+                for (int i = 280; i < 288; i++) T->lsorted[k++] = (uint16_t)i;
+                for (int i = 144; i < 256; i++) T->lsorted[k++] = (uint16_t)i;
+                for (int i = 0; i < (1 << ZI_LBITS); i++) T->lit[i] = 0;
+                uint32_t code = 0; k = 0;
+                for (int l = 7; l <= 9; l++) {
+                    for (int c = 0; c < T->lcount[l]; c++, k++, code++) {
+                        uint32_t r = zi_rev(code, l);
+                        uint16_t e = (uint16_t)(T->lsorted[k] | (l << 9));
+                        for (uint32_t j = r; j < (1u << ZI_LBITS); j += (1u << l)) T->lit[j] = e;
+                    }
+                    code <<= 1;
+                }
+            } else {
+                zi_refill(io);
+                uint32_t nlen = zi_take(io, 5) + 257, ndist = zi_take(io, 5) + 1, ncode = zi_take(io, 4) + 4;
+                if (zi_overrun(io)) return zi_fail(res, ZI_BUF_ERROR, ZI_E_INPUT_END);
+                if (nlen > 286 || ndist > 30) return zi_fail(res, ZI_DATA_ERROR, ZI_E_TOO_MANY_SYMS);
+                uint8_t cl[19];
+                for (int i = 0; i < 19; i++) cl[i] = 0;
+                for (uint32_t i = 0; i < ncode; i++) { zi_refill(io); cl[order[i]] = (uint8_t)zi_take(io, 3); }
+                if (zi_overrun(io)) return zi_fail(res, ZI_BUF_ERROR, ZI_E_INPUT_END);
+                /* code-length code: a 7-bit direct table (128 entries) laid over dist[64] and the first
+                   64 entries of lsorted, both dead until this header has been parsed */
+                uint16_t *cltab = T->dist;
+                uint16_t clsorted[19], clcount[16];
+                if (zi_build(cl, 19, 7, cltab, clsorted, clcount, 5, 0)) return zi_fail(res, ZI_DATA_ERROR, ZI_E_CODELEN_SET);
+                uint8_t *lens = (uint8_t *)T->lit;
+                uint32_t i = 0, total = nlen + ndist;
+                while (i < total) {
+                    zi_refill(io);
+                    int s = zi_decode(io, cltab, 7, clsorted, clcount, 5);
+                    if (s < 0) return zi_fail(res, zi_overrun(io) ? ZI_BUF_ERROR : ZI_DATA_ERROR, zi_overrun(io) ? ZI_E_INPUT_END : ZI_E_CODELEN_SET);
+                    if (s < 16) lens[i++] = (uint8_t)s;
+                    else {
+                        uint32_t rep, val = 0;
+                        if (s == 16) {
+                            if (i == 0) return zi_fail(res, ZI_DATA_ERROR, ZI_E_BITLEN_REPEAT);
+                            val = lens[i - 1]; rep = 3 + zi_take(io, 2);
+                        } else if (s == 17) rep = 3 + zi_take(io, 3);
+                        else rep = 11 + zi_take(io, 7);
+                        if (i + rep > total) return zi_fail(res, ZI_DATA_ERROR, ZI_E_BITLEN_REPEAT);
+                        while (rep--) lens[i++] = (uint8_t)val;
+                    }
+                    if (zi_overrun(io)) return zi_fail(res, ZI_BUF_ERROR, ZI_E_INPUT_END);
+                }
+                if (lens[256] == 0) return zi_fail(res, ZI_DATA_ERROR, ZI_E_NO_EOB);
+                /* distance tables first (they overwrite the code-length table), from the tail of lens */
+                if (zi_build(lens + nlen, (int)ndist, ZI_DBITS, T->dist, T->dsorted, T->dcount, 5, 1))
+                    return zi_fail(res, ZI_DATA_ERROR, ZI_E_DIST_SET);
+                /* literal/length: sorted + counts while lens is alive, then the table over it */
+                {
+                    uint16_t offs[16];
+                    for (int k = 0; k < 16; k++) T->lcount[k] = 0;
+                    for (uint32_t k = 0; k < nlen; k++) T->lcount[lens[k]]++;
+                    T->lcount[0] = 0;
+                    int left = 1, maxl = 15;
+                    for (int l = 1; l <= 15; l++) { left <<= 1; left -= T->lcount[l]; if (left < 0) return zi_fail(res, ZI_DATA_ERROR, ZI_E_LITLEN_SET); }
+                    while (maxl > 0 && T->lcount[maxl] == 0) maxl--;
+                    if (left > 0 && maxl != 1) return zi_fail(res, ZI_DATA_ERROR, ZI_E_LITLEN_SET);
+                    offs[1] = 0;
+                    for (int l = 1; l < 15; l++) offs[l + 1] = (uint16_t)(offs[l] + T->lcount[l]);
+                    for (uint32_t k = 0; k < nlen; k++) if (lens[k]) T->lsorted[offs[lens[k]]++] = (uint16_t)k;
+                    for (int k = 0; k < (1 << ZI_LBITS); k++) T->lit[k] = 0;
+                    uint32_t code = 0; int k = 0;
+                    for (int l = 1; l <= maxl && l <= ZI_LBITS; l++) {
+                        for (int c = 0; c < T->lcount[l]; c++, k++, code++) {
+                            uint32_t r = zi_rev(code, l);
+                            uint16_t e = (uint16_t)(T->lsorted[k] | (l << 9));
+                            for (uint32_t j = r; j < (1u << ZI_LBITS); j += (1u << l)) T->lit[j] = e;
+                        }
+                        code <<= 1;
+                    }
+                }
+            }
+            /* ---- symbol loop ---- */
+            for (;;) {
+                zi_refill(io);
+                int s = zi_decode(io, T->lit, ZI_LBITS, T->lsorted, T->lcount, 9);
+                if (zi_overrun(io)) return zi_fail(res, ZI_BUF_ERROR, ZI_E_INPUT_END);
+                if (s < 0) return zi_fail(res, ZI_DATA_ERROR, ZI_E_LITLEN_CODE);
+                if (s < 256) {
+                    if (io->op >= io->out_cap) return zi_fail(res, ZI_BUF_ERROR, ZI_E_OUTPUT_FULL);
+                    io->out[io->op++] = (uint8_t)s;
+                    continue;
+                }
+                if (s == 256) break;
+                if (s > 285) return zi_fail(res, ZI_DATA_ERROR, ZI_E_LITLEN_CODE);
+                uint32_t c = (uint32_t)s - 257, len;
+                if (c < 8) len = 3 + c;
+                else if (c == 28) len = 258;
+                else { uint32_t eb = (c - 4) >> 2; len = 3 + ((4 + (c & 3)) << eb) + zi_take(io, (int)eb); }
+                zi_refill(io);
+                int d = zi_decode(io, T->dist, ZI_DBITS, T->dsorted, T->dcount, 5);
+                if (d < 0 || d > 29) return zi_fail(res, zi_overrun(io) ? ZI_BUF_ERROR : ZI_DATA_ERROR, zi_overrun(io) ? ZI_E_INPUT_END : ZI_E_DIST_CODE);
+                uint32_t dist;
+                if (d < 4) dist = 1 + (uint32_t)d;
+                else { uint32_t eb = ((uint32_t)d - 2) >> 1; dist = 1 + ((2 + ((uint32_t)d & 1)) << eb) + zi_take(io, (int)eb); }
+                if (zi_overrun(io)) return zi_fail(res, ZI_BUF_ERROR, ZI_E_INPUT_END);
+                if (dist > io->op || dist > win_size) return zi_fail(res, ZI_DATA_ERROR, ZI_E_DIST_TOO_FAR);
+                uint32_t room = io->out_cap - io->op;
+                uint32_t n = len < room ? len : room;
+                uint8_t *q = io->out + io->op;
+                const uint8_t *f = q - dist;
+                for (uint32_t i = 0; i < n; i++) q[i] = f[i];
+                io->op += n;
+                if (n < len) return zi_fail(res, ZI_BUF_ERROR, ZI_E_OUTPUT_FULL);
+            }
+        }
+        if (last) return ZI_OK;
+    }
+}
+
+/* Scan for the next full-flush marker 00 00 FF FF at or after byte `from`; returns the position just
+ * after it or in_len when none (the reference's syncsearch, src/inflate.c:1523-1545). */
+ZID static inline uint32_t zi_sync(const uint8_t *in, uint32_t in_len, uint32_t from)
+{
+    uint32_t got = 0;     /* how much of 00 00 FF FF has been seen */
+    for (uint32_t p = from; p < in_len; p++) {
+        uint32_t b = in[p];
+        if (b == (got < 2 ? 0u : 0xFFu)) got++;
+        else if (b) got = 0;
+        else got = 4 - got;          /* a zero where FF was due: the zero run restarts */
+        if (got == 4) return p + 1;
+    }
+    return in_len;
+}
+
+/* Whole stream: wrapper (wrap 1 = zlib, 0 = raw), blocks, trailer, corruption recovery.
+ * The adler32 of the output is verified by the caller (a separate HBM-streaming pass on the GPU);
+ * res->stored_check/have_check report the trailer. */
+ZID static inline void zi_inflate(const uint8_t *in, uint32_t in_len, uint8_t *out, uint32_t out_cap,
+                                  int wrap, zi_tables *T, zi_result *res)
+{
+    zi_io io;
+    io.in = in; io.in_len = in_len; io.ip = 0; io.hold = 0; io.bits = 0;
+    io.out = out; io.out_cap = out_cap; io.op = 0;
+    res->ret = ZI_OK; res->reason = ZI_E_NONE; res->produced = 0; res->consumed = 0;
+    res->data_errors = 0; res->stored_check = 0; res->have_check = 0;
+    /* wrap: low byte 0 raw / 1 zlib; bits 8..15 = largest window_bits the caller accepts (0 = 15) */
+    const uint32_t maxw = ((wrap >> 8) & 0xFF) ? (uint32_t)((wrap >> 8) & 0xFF) : 15u;
+    wrap &= 0xFF;
+    uint32_t win = 1u << maxw;
+    int r = ZI_OK;
+    if (wrap == 1) {
+        zi_refill(&io);
+        uint32_t h = zi_take(&io, 16);
+        if (zi_overrun(&io)) r = zi_fail(res, ZI_BUF_ERROR, ZI_E_INPUT_END);
+        else if ((((h & 0xFF) << 8) | (h >> 8)) % 31) r = zi_fail(res, ZI_DATA_ERROR, ZI_E_HEADER_CHECK);
+        else if ((h & 0xF) != 8) r = zi_fail(res, ZI_DATA_ERROR, ZI_E_METHOD);
+        else if (((h >> 4) & 0xF) + 8 > maxw) r = zi_fail(res, ZI_DATA_ERROR, ZI_E_WINDOW);
+        else if (h & 0x2000) r = zi_fail(res, ZI_NEED_DICT, ZI_E_NEED_DICT);
+        else win = 1u << (((h >> 4) & 0xF) + 8);
+    }
+    for (;;) {
+        if (r == ZI_OK) r = zi_blocks(&io, T, res, win);
+        if (r != ZI_DATA_ERROR) break;
+        /* corrupted section: skip to the next full-flush point and keep appending output */
+        res->data_errors++;
+        uint32_t pos = io.ip - (io.bits >> 3);
+        if (pos > in_len) pos = in_len;
+        uint32_t nx = zi_sync(in, in_len, pos);
+        if (nx >= in_len) { io.hold = 0; io.bits = 0; io.ip = in_len; break; }
+        io.hold = 0; io.bits = 0; io.ip = nx;
+        r = ZI_OK;
+    }
+    if (r == ZI_OK) {
+        zi_drop(&io, (int)(io.bits & 7));
+        if (wrap == 1) {
+            zi_refill(&io);
+            uint32_t t = zi_take32(&io);
+            if (zi_overrun(&io)) r = zi_fail(res, ZI_BUF_ERROR, ZI_E_INPUT_END);
+            else {
+                res->stored_check = ((t & 0xFF) << 24) | ((t & 0xFF00) << 8) | ((t >> 8) & 0xFF00) | (t >> 24);
+                res->have_check = 1;
+            }
+        }
+    }
+    res->produced = io.op;
+    uint32_t c = zi_consumed_bytes(&io);
+    res->consumed = c > in_len ? in_len : c;
+    if (res->data_errors) res->ret = ZI_DATA_ERROR; else res->ret = r;
+}
+
+#endif
