@@ -1,0 +1,312 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the zsc-b200 engine (BASELINE.json configs[1]).
+
+Workload (per GPU): 1 GiB synthetic mixed text/binary (tools/datagen.c, seed 1 + rank), compressed
+as ONE zsc_compress-shaped stream at level 1 with max_block_len = 256 KiB (4096 independently
+decodable sections).  A "step" is one full pass of the deflate path over that buffer.
+
+  value      input GB/s, inputs resident in HBM, CUDA events on the engine's stream, max over ranks
+  e2e        the same pass through the host-buffer C-ABI call behind zsc_compress
+             (zscgpu_compress_host: H2D of the 1 GiB, all kernels, D2H of the compressed stream)
+  roofline   the LZ77 kernel (dominant): (N + C) algorithmic bytes / its event-timed duration
+             against the measured HBM copy bandwidth in MEASURED_PEAKS.json
+  cpu_baseline  the reference's own zsc_compress2 (oracle/_ref, compiled from /root/reference) on the
+             host cores, bounded sample of the same workload
+
+`--impl reference` times only the reference arm.  Launch with torchrun for --gpus > 1 (one rank per
+GPU, independent 1 GiB per rank: the path shards with no collective, scaling is "weak").
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+
+GIB = 1 << 30
+SECTION = 262144
+LEVEL = 1
+METRIC = "deflate_level1_input_GBps"
+WORKLOAD = "configs[1]: 1 GiB synthetic mixed text/binary per GPU, zlib level 1, max_block_len 256 KiB (4096 sections), one stream"
+
+
+def env_int(k, d):
+    try:
+        return int(os.environ.get(k, d))
+    except ValueError:
+        return d
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks/throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, gpu):
+        super().__init__(daemon=True)
+        self.gpu = gpu
+        self.rows = []
+        self.stop_flag = False
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm, mx, reasons = [], 0.0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = max(mx, float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic():
+    """DRAM bytes per launch of the LZ kernel from the committed `ncu --set full` capture, if any."""
+    p = os.path.join(ROOT, "profiles", "lz_kernel_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get("dram_bytes_per_launch_1GiB")
+        except Exception:
+            return None
+    return None
+
+
+def reference_arm(nbytes_per_job, jobs, threads, level=LEVEL, data=None):
+    """Time the reference's zsc_compress2 over `jobs` independent slices on `threads` host threads."""
+    from refimpl import REF_PATH
+    from zsc_b200 import datagen
+    L = C.CDLL(REF_PATH, mode=C.RTLD_LOCAL)
+    u64p, u32p, i32p = C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.POINTER(C.c_int32)
+    L.refprobe_batch.argtypes = [C.c_int, C.c_int, C.c_uint32, C.c_void_p, u64p, u32p, C.c_void_p, u64p, u32p, u32p, i32p,
+                                 C.c_uint32, C.c_int32, C.c_int32]
+    total = nbytes_per_job * jobs
+    if data is None:
+        data = datagen.mixed(total, seed=1)
+    cap = nbytes_per_job + nbytes_per_job // 8 + 4096
+    dst = np.empty(cap * jobs, dtype=np.uint8)
+    so = (C.c_uint64 * jobs)(*[i * nbytes_per_job for i in range(jobs)])
+    sl = (C.c_uint32 * jobs)(*[nbytes_per_job] * jobs)
+    do = (C.c_uint64 * jobs)(*[i * cap for i in range(jobs)])
+    dc = (C.c_uint32 * jobs)(*[cap] * jobs)
+    dl = (C.c_uint32 * jobs)()
+    rt = (C.c_int32 * jobs)()
+
+    def once():
+        t = time.perf_counter()
+        L.refprobe_batch(0, threads, jobs, data.ctypes.data, so, sl, dst.ctypes.data, do, dc, dl, rt, SECTION, level, 0)
+        dt = time.perf_counter() - t
+        assert all(r == 0 for r in rt), "reference zsc_compress2 failed"
+        return dt, sum(dl)
+    return once, total
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    threads = cores
+    job = 4 << 20
+    jobs = max(threads, min(256, (threads * 16 << 20) // job))
+    once, total = reference_arm(job, jobs, threads)
+    for _ in range(min(args.warmup, 1)):
+        once()
+    ts = []
+    for _ in range(args.steps):
+        dt, csz = once()
+        ts.append(dt)
+    t = sum(ts) / len(ts)
+    v = total / 1e9 / t
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(v, 4), "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(t * 1e3, 3), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "level": LEVEL, "max_block_len": SECTION,
+                   "note": "reference zsc_compress2 (unmodified, oracle/_ref) on host cores; each step = bounded sample"},
+        "cpu_baseline": {"value": round(v, 4), "unit": "GB/s", "cores": threads, "kind": "reference",
+                         "sample": f"{jobs} independent {job >> 20} MiB slices of the workload ({total >> 20} MiB), one pthread per core"},
+        "e2e": {"value": round(v, 4), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "ratio": round(total / csz, 4),
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_gpu(args, rank, world, local_rank):
+    from zsc_b200 import Engine, datagen, DeflateParams, Result
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist_mod
+        torch.cuda.set_device(local_rank)
+        dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist = dist_mod
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    def allmax(v):
+        if dist is None:
+            return v
+        import torch
+        t = torch.tensor([v], dtype=torch.float64, device=f"cuda:{local_rank}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    n = GIB
+    E = Engine(raw_bytes=n + (1 << 20), comp_bytes=n + (n >> 3) + (1 << 20), deflate_batch_max=n + (1 << 20),
+               max_streams=16, max_chunks=8192, device=local_rank)
+    data = datagen.mixed(n, seed=1 + rank)
+    cap = n + (n >> 3)
+    dest = np.empty(cap, dtype=np.uint8)
+    E.L.zscgpu_host_register(data.ctypes.data, data.nbytes)
+    E.L.zscgpu_host_register(dest.ctypes.data, dest.nbytes)
+    E.upload(0, 0, data)
+    st = Engine.make_streams([0], [n], [0], [cap])
+
+    # ---- warm-up (also the parity spot-check of this very run) ----
+    E.deflate_enqueue(st, SECTION, LEVEL)
+    res = E.fetch(1)
+    assert res[0].ret == 0, f"deflate failed: {res[0].ret}"
+    csize = res[0].produced
+    for _ in range(max(args.warmup - 1, 0)):
+        E.relaunch()
+    E.sync()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    # ---- timed: device-resident ----
+    barrier(); E.sync()
+    t_wall0 = time.perf_counter()
+    step_ms, lz_ms, parts = [], [], []
+    for _ in range(args.steps):
+        E.event(0); E.relaunch(); E.event(1); E.sync()
+        step_ms.append(E.elapsed_ms(0, 1))
+        lz_ms.append(E.elapsed_ms(9, 10))
+        parts.append([E.elapsed_ms(8 + i, 9 + i) for i in range(5)])
+    E.sync(); barrier()
+    t_wall = time.perf_counter() - t_wall0
+    total_ms = allmax(sum(step_ms))
+    # ---- timed: end to end through the host-buffer call ----
+    e2e_steps = max(1, min(args.steps, 3))
+    p = DeflateParams(SECTION, LEVEL, 0, 1, 15, 0)
+    r1 = Result()
+    E.L.zscgpu_compress_host(E.h, dest.ctypes.data, cap, data.ctypes.data, n, C.byref(p), 0, C.byref(r1))   # warm
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        rc = E.L.zscgpu_compress_host(E.h, dest.ctypes.data, cap, data.ctypes.data, n, C.byref(p), 0, C.byref(r1))
+        assert rc == 0 and r1.ret == 0
+    barrier()
+    e2e_s = allmax((time.perf_counter() - t0) / e2e_steps)
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    # ---- parity spot-check on this run's output: reference inflate of a prefix of sections ----
+    parity = "unchecked"
+    try:
+        from refimpl import have_ref, ref
+        import zlib
+        d = zlib.decompressobj()
+        back = d.decompress(dest[:r1.produced].tobytes(), 8 << 20)
+        parity = "first 8 MiB inflate bit-exact (python zlib)" if np.frombuffer(back, np.uint8).tobytes() == data[:len(back)].tobytes() else "MISMATCH"
+    except Exception as ex:  # pragma: no cover
+        parity = f"check failed: {ex!r}"
+
+    if rank != 0:
+        return
+    ms_per_step = total_ms / args.steps
+    value = world * n / 1e9 / (ms_per_step / 1e3)
+    peak, peak_src = measured_peak()
+    lz = sum(lz_ms) / len(lz_ms)
+    alg_bytes = n + csize
+    achieved = alg_bytes / 1e9 / (lz / 1e3)
+    pk = [sum(p_[i] for p_ in parts) / len(parts) for i in range(5)]
+    line = {
+        "metric": METRIC, "value": round(value, 3), "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "level": LEVEL, "max_block_len": SECTION, "bytes_per_gpu": n,
+                   "compressed_bytes": int(csize), "ratio": round(n / csize, 4),
+                   "l2": "inputs (1 GiB) and symbol scratch (1.3 GiB) far exceed the 126 MB L2; no flush needed",
+                   "parity": parity, "wall_s_timed_region": round(t_wall, 3)},
+        "roofline": {"bound": "hbm", "kernel": "zs_lz_kernel<false>", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
+                     "frac": round(achieved / peak, 5), "traffic": ncu_traffic(), "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": int(alg_bytes), "kernel_ms": round(lz, 3),
+                     "kernel_share_of_step": round(lz / ms_per_step, 4),
+                     "stage_ms": {"adler32": round(pk[0], 3), "lz77": round(pk[1], 3), "block_codes": round(pk[2], 3),
+                                  "offsets": round(pk[3], 3), "bitpack": round(pk[4], 3)}},
+        "e2e": {"value": round(world * n / 1e9 / e2e_s, 3), "unit": "GB/s", "h2d_bytes_per_step": n,
+                "d2h_bytes_per_step": int(r1.produced), "api": "zscgpu_compress_host (the call behind zsc_compress), pinned host buffers"},
+        "gpu_launches": int(args.steps * 5 + e2e_steps * 5),
+        "clocks": sampler.summary(),
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            cores = os.cpu_count() or 1
+            job = 4 << 20
+            jobs = max(cores, min(256, (cores * 16 << 20) // job))
+            once, total = reference_arm(job, jobs, cores, data=data[:job * jobs] if job * jobs <= n else None)
+            dt, csz = once()
+            line["cpu_baseline"] = {"value": round(total / 1e9 / dt, 4), "unit": "GB/s", "cores": cores, "kind": "reference",
+                                    "sample": f"first {total >> 20} MiB of the workload as {jobs} independent {job >> 20} MiB zsc_compress2 calls, one pthread per core",
+                                    "ratio": round(total / csz, 4)}
+        except Exception as ex:
+            line["cpu_baseline"] = {"value": None, "unit": "GB/s", "cores": 0, "kind": "reference", "sample": f"unavailable: {ex!r}"}
+    print(json.dumps(line), flush=True)
+    E.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="zsc_b200", choices=["zsc_b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if args.warmup < 3 and args.impl != "reference":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_gpu(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -79,7 +79,11 @@ typedef struct {
     int32_t  wrap;           /* 0 raw deflate, 1 zlib (2-byte header + adler32), 2 gzip body: raw deflate,
                                 header/trailer added by the host layer, crc32 reported in result.check */
     int32_t  window_bits;    /* 9..15 (0 = 15): largest match distance is 1 << window_bits */
-    int32_t  reserved;
+    int32_t  part;           /* 0 whole streams.  For one logical stream sharded over several engines
+                                (GPUs): bit 0 = not the first part (no stream header), bit 1 = not the last
+                                part (the last section ends with a full-flush marker, no final block and no
+                                trailer).  Parts concatenate byte-wise; result.check is the part's own
+                                adler32, to be folded with zscgpu_adler32_combine. */
 } zscgpu_deflate_params;
 
 void zscgpu_default_config(zscgpu_config *cfg);
@@ -149,7 +153,9 @@ int zscgpu_adler32_enqueue(zscgpu_engine *e, uint64_t off, uint64_t len);
 int zscgpu_crc32_enqueue(zscgpu_engine *e, uint64_t off, uint64_t len);
 
 /* Event timing on the engine's stream (so a C or ctypes caller can time kernels on the launching
- * stream without a CUDA binding of its own).  Slots 0..15. */
+ * stream without a CUDA binding of its own).  Slots 0..7 are the caller's.  Slots 8..13 are recorded
+ * by every deflate launch: 8 start, 9 after adler32, 10 after the LZ77 kernel, 11 after block
+ * histogram + code construction, 12 after the offset scan, 13 after bit packing. */
 int zscgpu_event_record(zscgpu_engine *e, int slot);
 int zscgpu_event_elapsed_ms(zscgpu_engine *e, int slot_start, int slot_stop, float *ms);
 

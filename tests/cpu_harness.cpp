@@ -133,7 +133,9 @@ static void encode_block(BitW &bw, const zh_block &B, const uint32_t *sy, const 
     if ((B.flags & ZB_FIRST_OF_STREAM) && wrap == 1) bw.put(zhdr, 16);
     if (B.type == ZH_STORED) {
         bw.put(B.hdr[0] & 7, 3); bw.align();
-        bw.put(B.in_len & 0xFFFF, 16); bw.put((~B.in_len) & 0xFFFF, 16);
+        bw.put(B.stored_total & 0xFFFF, 16); bw.put((~B.stored_total) & 0xFFFF, 16);
+        for (uint32_t i = 0; i < B.in_len; i++) bw.put(in_bytes[i], 8);
+    } else if (B.type == ZH_STORED_CONT) {
         for (uint32_t i = 0; i < B.in_len; i++) bw.put(in_bytes[i], 8);
     } else {
         for (uint32_t i = 0; i < B.hdr_bits; i++) bw.put((B.hdr[i >> 5] >> (i & 31)) & 1, 1);
@@ -200,6 +202,7 @@ uint32_t h_deflate_model(const uint8_t *src, uint32_t n, uint32_t max_block_len,
             lz_chunk(src + (cstart - dict) - a, a, dict, clen, P, sym, bstart, BS);
             uint32_t nblk = (uint32_t)((sym.size() + BS - 1) / BS);
             if (nblk == 0) nblk = 1;
+            std::vector<zh_block> blks(nblk);
             for (uint32_t k = 0; k < nblk; k++) {
                 uint32_t cnt = (uint32_t)sym.size() - k * BS < BS ? (uint32_t)sym.size() - k * BS : BS;
                 uint32_t lf[ZH_LCODES_PAD] = {0}, df[ZH_DCODES_PAD] = {0};
@@ -213,11 +216,26 @@ uint32_t h_deflate_model(const uint8_t *src, uint32_t n, uint32_t max_block_len,
                 uint32_t flags = 0;
                 if (pos == 0 && j == 0 && k == 0) flags |= ZB_FIRST_OF_STREAM;
                 if (j == nsub - 1 && k == nblk - 1) { flags |= ZB_LAST_OF_SECTION; if (pos + sec >= n) flags |= ZB_LAST_OF_STREAM; }
-                static zh_block B;
+                zh_block &B = blks[k];
                 zh_build_block(lf, df, in_end - in_start, (flags & ZB_LAST_OF_STREAM) ? 1 : 0, force, &B, &scratch);
-                B.nsym = cnt; B.flags = flags; B.in_start = in_start;
-                encode_block(bw, B, sym.data() + k * BS, src + cstart + in_start, wrap, zhdr, adler);
+                B.nsym = cnt; B.flags = flags; B.in_start = in_start; B.stored_total = in_end - in_start;
             }
+            // merge runs of stored blocks (mirrors zs_offset_kernel)
+            {
+                int head = -1; uint32_t total = 0;
+                for (uint32_t k = 0; k < nblk; k++) {
+                    zh_block &B = blks[k];
+                    if (B.type == ZH_STORED) {
+                        if (head >= 0 && total + B.in_len <= 65535u) {
+                            B.type = ZH_STORED_CONT; total += B.in_len; blks[head].stored_total = total;
+                            if (B.flags & ZB_LAST_OF_STREAM) blks[head].hdr[0] |= 1u;
+                        } else { head = (int)k; total = B.in_len; }
+                    } else head = -1;
+                    if (B.flags & (ZB_LAST_OF_SECTION | ZB_LAST_OF_STREAM)) head = -1;
+                }
+            }
+            for (uint32_t k = 0; k < nblk; k++)
+                encode_block(bw, blks[k], sym.data() + k * BS, src + cstart + blks[k].in_start, wrap, zhdr, adler);
             for (size_t i = 0; i < sym.size() && total_sym < sym_cap; i++) sym_out[total_sym++] = sym[i];
         }
         pos += sec;

@@ -34,6 +34,20 @@ def ref():
     return _ref
 
 
+_ora = None
+
+
+def oracle():
+    """Zsc wrapper over the CPU restatement oracle/zsc_oracle.c (uncompress, checksums, size checks)."""
+    global _ora
+    if _ora is None:
+        L = C.CDLL(ORACLE_PATH, mode=C.RTLD_LOCAL)
+        _declare_zsc(L, strict=False)
+        L.ora_inflate_raw.argtypes = [u8p, C.c_uint32, u8p, C.c_uint32, u32p, C.POINTER(C.c_char_p)]
+        _ora = Zsc(L)
+    return _ora
+
+
 _har = None
 
 

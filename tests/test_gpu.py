@@ -1,0 +1,360 @@
+"""GPU parity tests (`-m gpu`, run on a B200).  Every call goes through the C-ABI library
+(libzsc_b200.so): the zsc_pub.h entry points on host buffers and the batched zscgpu_* entry points on
+device-resident buffers.  The checker is the oracle: the reference's own code (oracle/_ref, prebuilt in the
+snapshot) when present, else the CPU restatement; plus the committed golden fixtures.  /root/reference is
+never read here."""
+import ctypes as C
+import json
+import os
+import zlib
+
+import numpy as np
+import pytest
+
+import refimpl
+from zsc_b200 import Engine, capi, datagen, shard
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load(name):
+    return json.load(open(os.path.join(G, name)))
+
+
+def vec_bytes(x):
+    return bytes(int(t, 16) for t in x["hex"].split()) if "kind" in x else bytes.fromhex(x["hex"])
+
+
+def gpu_deflate(E, x, mbl, level, strategy=0, wrap=1, cap=None, wbits=15, part=0):
+    E.upload(0, 0, x) if len(x) else None
+    cap = cap if cap is not None else len(x) + len(x) // 8 + 4096
+    st = Engine.make_streams([0], [len(x)], [0], [cap])
+    r = E.deflate(st, mbl, level, strategy, wrap, wbits, part)[0]
+    return r, E.download(1, 0, r.produced)
+
+
+# ------------------------------------------------------------------ deflate
+CASES = [("mixed", lambda: datagen.fill(1 << 20, 1, datagen.MIXED)),
+         ("telemetry", lambda: datagen.fill(1 << 20, 1000, datagen.TELEMETRY, piece=262144)),
+         ("text", lambda: datagen.fill(300001, 4, datagen.TEXT)),
+         ("random", lambda: datagen.fill(200000, 5, datagen.RANDOM)),
+         ("zeros", lambda: np.zeros(700000, np.uint8)),
+         ("ff", lambda: np.full(70001, 255, np.uint8)),
+         ("empty", lambda: np.zeros(0, np.uint8)),
+         ("one", lambda: np.frombuffer(b"Z", np.uint8)),
+         ("two", lambda: np.frombuffer(b"ab", np.uint8)),
+         ("short_rep", lambda: np.frombuffer(b"abcabcabcabcabcabc", np.uint8))]
+
+
+@pytest.mark.parametrize("name,make", CASES)
+@pytest.mark.parametrize("level,strategy", [(1, 0), (6, 0), (9, 0), (0, 0), (3, 0), (6, 1), (6, 2), (6, 3), (6, 4)])
+def test_deflate_bit_exact_with_model_and_inflates_through_checker(engine, checker, name, make, level, strategy):
+    x = make()
+    if level == 9 and len(x) > 400000:
+        x = x[:400000]
+    for mbl in (262144, 100000):
+        r, comp = gpu_deflate(engine, x, mbl, level, strategy)
+        assert r.ret == 0 and r.check == zlib.adler32(x.tobytes())
+        model, _ = refimpl.model_deflate(x, mbl, level, strategy)
+        assert np.array_equal(comp, model), f"GPU stream differs from its bit-exact prediction ({name}, L{level}, s{strategy})"
+        rr, out, used = checker.uncompress(comp, len(x) + 1)
+        assert rr == 0 and used == len(comp) and np.array_equal(out, x)
+        assert len(comp) <= capi.zsc().max_output_size(len(x), mbl, level)[1]
+
+
+@pytest.mark.parametrize("level", [1, 6, 9])
+def test_deflate_ratio_within_two_percent_of_reference(engine, level):
+    if not refimpl.have_ref():
+        pytest.skip("oracle/_ref not present")
+    R = refimpl.ref()
+    n = (4 << 20) if level < 9 else (1 << 20)
+    for kind, seed, piece in ((datagen.MIXED, 1, 1 << 20), (datagen.TELEMETRY, 1000, 262144)):
+        x = datagen.fill(n, seed, kind, piece=piece)
+        r, comp = gpu_deflate(engine, x, 262144, level)
+        rc, refc = R.compress(x, 262144, level)
+        assert r.ret == 0 and rc == 0
+        assert len(comp) <= 1.02 * len(refc), (kind, level, len(comp), len(refc))   # tolerance stated by north_star: <= 2 %
+
+
+def test_deflate_sections_are_independently_decodable(engine):
+    """every max_block_len section starts right after a full-flush marker and decodes on its own with a fresh
+    raw inflater (the property zsc_pub.h:24-29 documents and zsc_uncompress's recovery relies on)"""
+    x = datagen.fill(1 << 20, 2, datagen.MIXED)
+    mbl = 100000
+    r, comp = gpu_deflate(engine, x, mbl, 6)
+    b = comp.tobytes()
+    starts, p = [2], b.find(b"\x00\x00\xff\xff")
+    while p >= 0:
+        starts.append(p + 4)
+        p = b.find(b"\x00\x00\xff\xff", p + 1)
+    k, nsec = 0, -(-len(x) // mbl)
+    for s in starts:
+        if k == nsec:
+            break
+        want = x[k * mbl:(k + 1) * mbl].tobytes()
+        try:
+            got = zlib.decompressobj(-15).decompress(b[s:], len(want))
+        except zlib.error:
+            continue
+        if got == want:
+            k += 1
+    assert k == nsec
+
+
+def test_deflate_window_bits_and_raw(engine, checker):
+    x = datagen.fill(300000, 6, datagen.MIXED)
+    for wbits in (9, 12, 15):
+        r, comp = gpu_deflate(engine, x, 100000, 6, wbits=wbits)
+        assert r.ret == 0
+        rr, out, used = checker.uncompress(comp, len(x), window_bits=wbits)
+        assert rr == 0 and np.array_equal(out, x)
+        assert (comp[0] >> 4) + 8 == wbits
+    r, comp = gpu_deflate(engine, x, 100000, 6, wrap=0)
+    assert np.array_equal(np.frombuffer(zlib.decompress(comp.tobytes(), -15), np.uint8), x)
+
+
+def test_deflate_output_too_small_is_buf_error(engine):
+    x = datagen.fill(100000, 8, datagen.MIXED)
+    r, comp = gpu_deflate(engine, x, 100000, 6, cap=42)
+    assert r.ret == capi.Z_BUF_ERROR and r.produced == 0
+
+
+def test_deflate_batch_of_independent_buffers_matches_single_calls(engine, checker):
+    """config 3 shape: many independent buffers, one stream each, ragged lengths"""
+    n = 48
+    lens = [262144 - 977 * i for i in range(n)]
+    x = datagen.telemetry_buffers(n, 262144, seed=1000)
+    engine.upload(0, 0, x)
+    st = Engine.make_streams([i * 262144 for i in range(n)], lens, [i * 300000 for i in range(n)], [300000] * n)
+    res = engine.deflate(st, 262144, 6)
+    for i in (0, 1, 17, n - 1):
+        comp = engine.download(1, i * 300000, res[i].produced)
+        src = x[i * 262144:i * 262144 + lens[i]]
+        rr, out, used = checker.uncompress(comp, lens[i])
+        assert res[i].ret == 0 and rr == 0 and used == len(comp) and np.array_equal(out, src)
+        r1, c1 = gpu_deflate(engine, src, 262144, 6)
+        assert np.array_equal(c1, comp)
+        engine.upload(0, 0, x)
+
+
+def test_deflate_large_section_is_sub_chunked_with_dictionary(engine, checker):
+    """max_block_len >= source_len: one section, several chunks primed with the preceding 32 KiB"""
+    x = datagen.fill(3 << 20, 12, datagen.MIXED)
+    r, comp = gpu_deflate(engine, x, 1 << 30, 6)
+    r2, comp2 = gpu_deflate(engine, x, 262144, 6)
+    rr, out, used = checker.uncompress(comp, len(x))
+    assert r.ret == 0 and rr == 0 and np.array_equal(out, x)
+    assert comp.tobytes().count(b"\x00\x00\xff\xff") <= 2          # no markers inside the single section
+    assert len(comp) <= len(comp2)                                   # dictionaries recover the cross-chunk matches
+
+
+# ------------------------------------------------------------------ inflate
+def test_inflate_reference_streams_fixture_through_zsc_pub():
+    Z = capi.zsc()
+    g = load("ref_streams.json")
+    inputs = {k: np.frombuffer(bytes.fromhex(v["hex"]), dtype=np.uint8) for k, v in g["inputs"].items()}
+    for s in g["streams"]:
+        x = inputs[s["input"]]
+        comp = np.frombuffer(bytes.fromhex(s["hex"]), dtype=np.uint8)
+        r, out, used = Z.uncompress(comp, len(x) + 16, window_bits=s["window_bits"])
+        assert r == 0 and used == len(comp) and np.array_equal(out, x), s["input"]
+
+
+@pytest.mark.parametrize("fixture", ["infcover_vectors.json", "bad_headers.json"])
+def test_inflate_known_answer_vectors_through_zsc_pub(fixture):
+    """reference test/infcover.c / test/zlib_gtest.cpp:1815-1918 vectors: same return code, same output"""
+    Z = capi.zsc()
+    for x in load(fixture):
+        ref = x["ref"]
+        r, out, used = Z.uncompress(np.frombuffer(vec_bytes(x), np.uint8), 70000, window_bits=x["window_bits"])
+        assert r == ref["ret"], (x["what"], r, ref["ret"])
+        assert len(out) == ref["produced"], x["what"]
+        if ref["out_hex"] is not None:
+            assert out.tobytes().hex() == ref["out_hex"]
+        if x["window_bits"] in (15, -15):
+            assert used == ref["consumed"], x["what"]
+
+
+def test_inflate_batch_of_reference_streams(engine, checker):
+    if not refimpl.have_ref():
+        pytest.skip("oracle/_ref not present")
+    R = refimpl.ref()
+    srcs, comps = [], []
+    for i in range(40):
+        n = 262144 - 1013 * i
+        x = datagen.fill(n, 50 + i, datagen.MIXED if i % 2 else datagen.TELEMETRY, piece=1 << 20)
+        rc, c = R.compress(x, 262144 if i % 3 else 50000, (1, 6, 9)[i % 3])
+        srcs.append(x); comps.append(c)
+    coff, roff, desc = 0, 0, []
+    for x, c in zip(srcs, comps):
+        engine.upload(1, coff, c)
+        desc.append((roff, len(x), coff, len(c)))
+        coff += len(c) + 3; roff += len(x) + 5        # deliberately unaligned packing
+    st = Engine.make_streams(*zip(*desc))
+    res = engine.inflate(st, 1)
+    for x, d, r in zip(srcs, desc, res):
+        out = engine.download(0, d[0], r.produced)
+        assert r.ret == 0 and r.consumed == d[3] and r.check == zlib.adler32(x.tobytes())
+        assert np.array_equal(out, x)
+
+
+def test_inflate_corruption_recovery_matches_checker(checker):
+    """flip one byte (reference test/zlib_gtest.cpp:696-699): same code, same recovered bytes as the checker"""
+    Z = capi.zsc()
+    rng = np.random.default_rng(11)
+    x = datagen.fill(600000, 77, datagen.MIXED)
+    for level, mbl in ((6, 100000), (1, 50000)):
+        rc, comp = Z.compress(x, mbl, level)
+        assert rc == 0
+        for _ in range(12):
+            bad = comp.copy()
+            pos = int(rng.integers(2, len(bad)))
+            bad[pos] ^= 1 << int(rng.integers(0, 8))
+            r, out, used = Z.uncompress(bad, len(x))
+            rr, out2, used2 = checker.uncompress(bad, len(x))
+            assert r == rr and len(out) == len(out2) and np.array_equal(out, out2), (level, pos, r, rr, len(out), len(out2))
+            assert used == used2
+
+
+def test_inflate_output_and_input_limits(checker):
+    Z = capi.zsc()
+    x = datagen.fill(200000, 78, datagen.MIXED)
+    rc, comp = Z.compress(x, 100000, 6)
+    for cap in (0, 42, len(x) - 1, len(x)):
+        r, out, used = Z.uncompress(comp, cap)
+        rr, out2, used2 = checker.uncompress(comp, cap)
+        assert r == rr and np.array_equal(out, out2), cap           # Z_BUF_ERROR with the buffer filled, as the reference
+    r, out, used = Z.uncompress(comp[:len(comp) // 3], len(x))
+    rr, out2, used2 = checker.uncompress(comp[:len(comp) // 3], len(x))
+    assert r == rr == capi.Z_BUF_ERROR and np.array_equal(out, out2)
+
+
+# ------------------------------------------------------------------ zsc_pub round trips and gzip
+@pytest.mark.parametrize("level", [0, 1, 6, 9])
+def test_zsc_pub_round_trip_both_directions(checker, level):
+    Z = capi.zsc()
+    for x in (datagen.fill(500000, 90, datagen.MIXED), datagen.fill(152089, 91, datagen.TEXT)):
+        r, comp = Z.compress(x, 100000, level)
+        assert r == 0
+        rr, out, used = checker.uncompress(comp, len(x))
+        assert rr == 0 and used == len(comp) and np.array_equal(out, x)
+        if refimpl.have_ref():
+            rc, refc = checker.compress(x, 100000, level)
+            r2, out2, used2 = Z.uncompress(refc, len(x))
+            assert r2 == 0 and used2 == len(refc) and np.array_equal(out2, x)
+        r3, out3, used3 = Z.uncompress(comp, len(x))
+        assert r3 == 0 and np.array_equal(out3, x)
+
+
+def test_zsc_pub_gzip_wrapper(checker):
+    Z = capi.zsc()
+    x = datagen.fill(300000, 92, datagen.MIXED)
+    r, comp = Z.compress(x, 100000, 6, window_bits=31)
+    assert r == 0 and comp[0] == 31 and comp[1] == 139
+    import gzip
+    assert gzip.decompress(comp.tobytes()) == x.tobytes()
+    rr, out, used = checker.uncompress(comp, len(x), window_bits=31)
+    assert rr == 0 and used == len(comp) and np.array_equal(out, x)
+    r2, out2, used2 = Z.uncompress(comp, len(x), window_bits=31)
+    assert r2 == 0 and used2 == len(comp) and np.array_equal(out2, x)
+    r3, out3, used3 = Z.uncompress(comp, len(x), window_bits=47)      # auto-detect
+    assert r3 == 0 and np.array_equal(out3, x)
+    name = (C.c_uint8 * 6)(*b"Hello\0")
+    gz = capi.GzHeader()
+    gz.name = C.cast(name, capi.u8p); gz.time = 1234; gz.os = 3; gz.hcrc = 1
+    r4, comp4 = Z.compress(x, 100000, 6, window_bits=31, gz=gz)
+    assert r4 == 0 and gzip.decompress(comp4.tobytes()) == x.tobytes() and b"Hello\0" in comp4[:20].tobytes()
+    if refimpl.have_ref():
+        rc, refc = checker.compress(x, 100000, 6, window_bits=31, gz=gz)
+        assert len(comp4) <= 1.02 * len(refc)
+
+
+def test_zsc_pub_error_codes(checker):
+    """reference test/zlib_gtest.cpp:1499-1505,1588-1595: 42-byte destinations are Z_BUF_ERROR"""
+    Z = capi.zsc()
+    x = datagen.fill(100000, 93, datagen.MIXED)
+    assert Z.compress(x, 100000, 6, dest_cap=42)[0] == capi.Z_BUF_ERROR
+    r, comp = Z.compress(x, 100000, 6)
+    assert Z.uncompress(comp, 42)[0] == capi.Z_BUF_ERROR
+
+
+# ------------------------------------------------------------------ checksums
+def test_checksums_bit_exact(engine, checker):
+    x = datagen.fill(8 << 20, 5, datagen.RANDOM)
+    engine.upload(0, 0, x)
+    for off, n in ((0, 0), (0, 1), (0, 15), (1, 16), (3, 5552), (7, 65521), (0, 1 << 20), (5, (8 << 20) - 5), (0, 8 << 20)):
+        b = x[off:off + n]
+        assert engine.adler32(off, n) == checker.adler32(b) == zlib.adler32(b.tobytes())
+        assert engine.crc32(off, n) == checker.crc32(b) == zlib.crc32(b.tobytes())
+    for fill in (0x00, 0xFF):                                    # worst case for the deferred modulo
+        y = np.full((3 << 20) + 13, fill, np.uint8)
+        engine.upload(0, 0, y)
+        assert engine.adler32(0, len(y)) == zlib.adler32(y.tobytes())
+        assert engine.crc32(0, len(y)) == zlib.crc32(y.tobytes())
+    # running values and combination across 8 shards
+    engine.upload(0, 0, x)
+    cuts = [i * (len(x) // 8) + (i % 3) for i in range(8)] + [len(x)]
+    a, c = 1, 0
+    for lo, hi in zip(cuts[:-1], cuts[1:]):
+        a = shard.adler32_combine(a, engine.adler32(lo, hi - lo), hi - lo)
+        c = shard.crc32_combine(c, engine.crc32(lo, hi - lo), hi - lo)
+    assert a == zlib.adler32(x.tobytes()) and c == zlib.crc32(x.tobytes())
+    assert engine.adler32(100, 5000, init=zlib.adler32(x[:100].tobytes())) == zlib.adler32(x[:5100].tobytes())
+    assert engine.crc32(100, 5000, init=zlib.crc32(x[:100].tobytes())) == zlib.crc32(x[:5100].tobytes())
+    Z = capi.zsc()
+    assert Z.adler32(x[:100001]) == zlib.adler32(x[:100001].tobytes()) and Z.crc32(x[:100001]) == zlib.crc32(x[:100001].tobytes())
+
+
+# ------------------------------------------------------------------ sharded stream (two engines' worth of parts on one GPU)
+def test_sharded_stream_parts_stitch_into_one_valid_stream(engine, checker):
+    x = datagen.fill(900000, 13, datagen.MIXED)
+    mbl, level, world = 100000, 6, 2
+    nsec = -(-len(x) // mbl)
+    parts, adlers, lens = [], [], []
+    for rank, (lo, hi) in enumerate(shard.partition(nsec, world)):
+        b0, b1 = shard.byte_range(lo, hi, mbl, len(x))
+        r, comp = gpu_deflate(engine, x[b0:b1], mbl, level, wrap=0, part=(0 if rank == world - 1 else 2))
+        assert r.ret == 0
+        parts.append(comp.tobytes()); adlers.append(r.check); lens.append(b1 - b0)
+    stream = np.frombuffer(shard.stitch(parts, adlers, lens, level), np.uint8)
+    rr, out, used = checker.uncompress(stream, len(x))
+    assert rr == 0 and used == len(stream) and np.array_equal(out, x)
+    r1, whole = gpu_deflate(engine, x, mbl, level)
+    assert np.array_equal(whole, stream)                               # identical to the single-engine stream
+
+
+# ------------------------------------------------------------------ full BASELINE size, size-independent properties
+def test_full_size_round_trip_1GiB_level1():
+    """configs[1] at full size: deflate L1 -> GPU inflate round trip, checksum of the round trip equals the
+    checksum of the input, every section decodes; a strided sample of sections also goes through the checker."""
+    n = 1 << 30
+    E = Engine(raw_bytes=n + (1 << 20), comp_bytes=n + (n >> 3), deflate_batch_max=n + (1 << 20), max_streams=8192, max_chunks=8192)
+    try:
+        x = datagen.mixed(n, seed=1)
+        E.upload(0, 0, x)
+        a_in = E.adler32(0, n)
+        assert a_in == zlib.adler32(x.tobytes())
+        st = Engine.make_streams([0], [n], [0], [n + (n >> 3)])
+        r = E.deflate(st, 262144, 1)[0]
+        assert r.ret == 0 and r.check == a_in
+        comp_size = r.produced
+        assert comp_size <= capi.zsc().max_output_size(n, 262144, 1)[1]
+        # the compressed stream inflates on the GPU to the same bytes
+        E.L.zscgpu_copy_within(E.h, 0, 0, 0, 0)
+        zero = np.zeros(1 << 20, np.uint8)
+        for off in range(0, 64 << 20, 1 << 20):
+            E.upload(0, off, zero)                                      # scrub part of the raw arena
+        st2 = Engine.make_streams([0], [n], [0], [comp_size])
+        r2 = E.inflate(st2, 1)[0]
+        assert r2.ret == 0 and r2.produced == n and r2.consumed == comp_size and r2.check == a_in
+        assert E.adler32(0, n) == a_in
+        back = E.download(0, 0, n)
+        assert np.array_equal(back, x)
+        # a prefix of the stream through the checker's own inflate (bounded: 16 sections)
+        comp = E.download(1, 0, comp_size)
+        d = zlib.decompressobj()
+        head = d.decompress(comp.tobytes(), 16 * 262144)
+        assert head == x[:len(head)].tobytes()
+    finally:
+        E.close()

@@ -34,7 +34,7 @@ class Result(C.Structure):
 
 class DeflateParams(C.Structure):
     _fields_ = [("max_block_len", C.c_uint32), ("level", C.c_int32), ("strategy", C.c_int32),
-                ("wrap", C.c_int32), ("window_bits", C.c_int32), ("reserved", C.c_int32)]
+                ("wrap", C.c_int32), ("window_bits", C.c_int32), ("part", C.c_int32)]
 
 
 class GzHeader(C.Structure):
@@ -68,10 +68,31 @@ ZSC_SYMBOLS = [
 ]
 
 
-def _declare_zsc(L):
-    """argtypes/restype of the zsc_pub.h surface on a loaded library (ours or the reference's)."""
+class _Tolerant:
+    """attribute proxy that ignores symbols a checker library does not export"""
+
+    def __init__(self, L):
+        object.__setattr__(self, "_L", L)
+
+    def __getattr__(self, name):
+        try:
+            return getattr(self._L, name)
+        except AttributeError:
+            return _Missing()
+
+
+class _Missing:
+    def __setattr__(self, k, v):
+        pass
+
+
+def _declare_zsc(L, strict=True):
+    """argtypes/restype of the zsc_pub.h surface on a loaded library (ours, the reference's, the oracle's)."""
     I, U = C.c_int32, C.c_uint32
     gz = C.POINTER(GzHeader)
+    real = L
+    if not strict:
+        L = _Tolerant(L)
     L.zsc_compress_get_min_work_buf_size.argtypes = [u32p]
     L.zsc_compress_get_min_work_buf_size2.argtypes = [I, I, u32p]
     L.zsc_compress_get_max_output_size.argtypes = [U, U, I, u32p]
@@ -96,7 +117,7 @@ def _declare_zsc(L):
     L.crc32_z.argtypes = [U, u8p, C.c_size_t]; L.crc32_z.restype = U
     L.zError.argtypes = [I]; L.zError.restype = C.c_char_p
     L.zlibVersion.argtypes = []; L.zlibVersion.restype = C.c_char_p
-    return L
+    return real
 
 
 _lib = None
@@ -286,8 +307,8 @@ class Engine:
             arr[i].comp_off, arr[i].comp_len = int(comp_offs[i]), int(comp_lens[i])
         return arr
 
-    def deflate(self, streams, max_block_len, level, strategy=0, wrap=1, window_bits=15):
-        p = DeflateParams(max_block_len, level, strategy, wrap, window_bits, 0)
+    def deflate(self, streams, max_block_len, level, strategy=0, wrap=1, window_bits=15, part=0):
+        p = DeflateParams(max_block_len, level, strategy, wrap, window_bits, part)
         res = (Result * len(streams))()
         self._ck(self.L.zscgpu_deflate_batch(self.h, streams, len(streams), C.byref(p), res))
         return res

@@ -73,7 +73,7 @@ zs_block_kernel(const ZsChunk *__restrict__ chunks, const uint32_t *__restrict__
         S.blk.nsym = cnt;
         S.blk.in_start = in_start;
         S.blk.flags = flags;
-        S.blk.pad0 = 0;
+        S.blk.stored_total = in_end - in_start;
         S.blk.bitoff = 0;
         S.blk.sym_off = cd.sym_off + (uint64_t)k * ZS_BLOCK_SYMS;
     }
@@ -98,6 +98,28 @@ zs_offset_kernel(const ZsStream *__restrict__ streams, const ZsChunk *__restrict
     __shared__ int s_fail;
     const uint32_t sidx = blockIdx.x, tid = threadIdx.x;
     const ZsStream st = streams[sidx];
+    /* Merge runs of adjacent stored blocks of a chunk into one stored block of <= 65535 bytes: the
+       first keeps the header with the run's length, the others become payload-only continuations.
+       Keeps incompressible data at 5 bytes per 64 KiB, inside the reference's output bound. */
+    for (uint32_t c = st.chunk_first + tid; c < st.chunk_first + st.chunk_count; c += ZO_THREADS) {
+        const uint32_t base = chunks[c].blk_base, capn = chunks[c].blk_cap;
+        uint32_t head = 0xFFFFFFFFu, total = 0;
+        for (uint32_t k = 0; k < capn; k++) {
+            zh_block *bp = &blocks[base + k];
+            const uint32_t type = bp->type;
+            if (type == ZH_UNUSED) break;
+            if (type == ZH_STORED) {
+                if (head != 0xFFFFFFFFu && total + bp->in_len <= 65535u) {
+                    bp->type = ZH_STORED_CONT;
+                    total += bp->in_len;
+                    blocks[head].stored_total = total;
+                    if (bp->flags & ZB_LAST_OF_STREAM) blocks[head].hdr[0] |= 1u;
+                } else { head = base + k; total = bp->in_len; }
+            } else head = 0xFFFFFFFFu;
+            if (bp->flags & (ZB_LAST_OF_SECTION | ZB_LAST_OF_STREAM)) head = 0xFFFFFFFFu;
+        }
+    }
+    __syncthreads();
     const uint32_t per = (st.blk_count + ZO_THREADS - 1) / ZO_THREADS;
     const uint32_t lo = min(st.blk_count, tid * per), hi = min(st.blk_count, lo + per);
     zk_elem acc = zk_ident();
@@ -217,27 +239,31 @@ zs_encode_kernel(const zh_block *__restrict__ blocks, const uint32_t *__restrict
     if (flags & ZB_LAST_OF_STREAM) { if (P.wrap == 1) { suf_bits = 32; suf_val = __byte_perm(res_check[cd.stream], 0, 0x0123); } }
     else if (flags & ZB_LAST_OF_SECTION) { suf_pre = 3; suf_bits = 32; suf_val = 0xFFFF0000u; }
 
-    if (type == ZH_STORED) {
-        /* [stream header][3-bit block header][pad][LEN][NLEN][bytes][suffix]: byte-granular writes */
+    if (type == ZH_STORED || type == ZH_STORED_CONT) {
+        /* [stream header][3-bit block header][pad][LEN][NLEN][bytes][suffix]: byte-granular writes.
+           A continuation of a merged run is payload (+ suffix) only and starts byte aligned. */
         const uint32_t in_len = bp->in_len;
+        const uint32_t run_len = bp->stored_total;
         const uint64_t hb = x + pre_bits;                 /* bit position of the block header */
-        const uint64_t d0 = (zk_up8(hb + 3) >> 3);        /* byte position of LEN */
+        const uint64_t d0 = type == ZH_STORED ? (zk_up8(hb + 3) >> 3) + 4 : (x >> 3);   /* first payload byte */
         if (tid == 0) {
-            /* leading bits: zlib header (if any) + 3 header bits, then zero pad */
-            uint64_t v = (pre_bits ? (uint64_t)(uint32_t)P.zhdr : 0ull) | ((uint64_t)(bp->hdr[0] & 7u) << pre_bits);
-            uint32_t sh = (uint32_t)(x & 7);
-            v <<= sh;
-            for (uint64_t p = x >> 3; p < d0; p++) { ze_put_byte(comp, p, (uint32_t)(v & 0xFF), w_first, w_last); v >>= 8; }
-            ze_put_byte(comp, d0, in_len & 0xFF, w_first, w_last);
-            ze_put_byte(comp, d0 + 1, (in_len >> 8) & 0xFF, w_first, w_last);
-            ze_put_byte(comp, d0 + 2, (~in_len) & 0xFF, w_first, w_last);
-            ze_put_byte(comp, d0 + 3, ((~in_len) >> 8) & 0xFF, w_first, w_last);
-            uint64_t p = d0 + 4 + in_len;
+            if (type == ZH_STORED) {
+                /* leading bits: zlib header (if any) + 3 header bits, then zero pad */
+                uint64_t v = (pre_bits ? (uint64_t)(uint32_t)P.zhdr : 0ull) | ((uint64_t)(bp->hdr[0] & 7u) << pre_bits);
+                uint32_t sh = (uint32_t)(x & 7);
+                v <<= sh;
+                for (uint64_t p = x >> 3; p < d0 - 4; p++) { ze_put_byte(comp, p, (uint32_t)(v & 0xFF), w_first, w_last); v >>= 8; }
+                ze_put_byte(comp, d0 - 4, run_len & 0xFF, w_first, w_last);
+                ze_put_byte(comp, d0 - 3, (run_len >> 8) & 0xFF, w_first, w_last);
+                ze_put_byte(comp, d0 - 2, (~run_len) & 0xFF, w_first, w_last);
+                ze_put_byte(comp, d0 - 1, ((~run_len) >> 8) & 0xFF, w_first, w_last);
+            }
+            uint64_t p = d0 + in_len;
             if (suf_pre) { ze_put_byte(comp, p, 0, w_first, w_last); p++; }
             for (uint32_t i = 0; i < suf_bits / 8; i++) ze_put_byte(comp, p + i, (suf_val >> (8 * i)) & 0xFF, w_first, w_last);
         }
         const uint8_t *src = raw + cd.raw_off + bp->in_start;
-        for (uint32_t i = tid; i < in_len; i += ZE_THREADS) ze_put_byte(comp, d0 + 4 + i, src[i], w_first, w_last);
+        for (uint32_t i = tid; i < in_len; i += ZE_THREADS) ze_put_byte(comp, d0 + i, src[i], w_first, w_last);
         return;
     }
 
@@ -358,12 +384,15 @@ extern "C" cudaError_t zs_huff_launch(cudaStream_t st, uint32_t nblk_slots, uint
                                       const uint32_t *chunk_nsym, const uint32_t *blk_in_start,
                                       zh_block *blocks, const ZsAdlerAcc *adler_acc,
                                       const uint8_t *raw, uint8_t *comp, int32_t *res_ret,
-                                      uint32_t *res_produced, uint32_t *res_check, ZsLzParams P)
+                                      uint32_t *res_produced, uint32_t *res_check, ZsLzParams P,
+                                      cudaEvent_t ev_after_block, cudaEvent_t ev_after_offset)
 {
     if (nblk_slots == 0 || nstreams == 0) return cudaSuccess;
     zs_block_kernel<<<nblk_slots, ZB_THREADS, 0, st>>>(chunks, blk_chunk, sym, chunk_nsym, blk_in_start, blocks, P);
+    if (ev_after_block) cudaEventRecord(ev_after_block, st);
     zs_offset_kernel<<<nstreams, ZO_THREADS, 0, st>>>(streams, chunks, blk_chunk, blocks, adler_acc,
                                                       reinterpret_cast<uint32_t *>(comp), res_ret, res_produced, res_check, P);
+    if (ev_after_offset) cudaEventRecord(ev_after_offset, st);
     cudaFuncSetAttribute(zs_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ZeSmem));
     zs_encode_kernel<<<nblk_slots, ZE_THREADS, sizeof(ZeSmem), st>>>(blocks, blk_chunk, chunks, sym, raw, comp, res_check, P);
     return cudaGetLastError();

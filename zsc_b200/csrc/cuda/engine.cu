@@ -14,7 +14,7 @@
 extern "C" cudaError_t zs_lz_launch(cudaStream_t, int, uint32_t, const uint8_t *, const ZsChunk *, uint32_t *, uint32_t *, uint32_t *, ZsLzParams);
 extern "C" cudaError_t zs_huff_launch(cudaStream_t, uint32_t, uint32_t, const ZsChunk *, const uint32_t *, const ZsStream *, const uint32_t *,
                                       const uint32_t *, const uint32_t *, zh_block *, const ZsAdlerAcc *, const uint8_t *, uint8_t *,
-                                      int32_t *, uint32_t *, uint32_t *, ZsLzParams);
+                                      int32_t *, uint32_t *, uint32_t *, ZsLzParams, cudaEvent_t, cudaEvent_t);
 extern "C" cudaError_t zs_adler_chunks_launch(cudaStream_t, uint32_t, const uint8_t *, const ZsChunk *, const ZsStream *, ZsAdlerAcc *);
 extern "C" cudaError_t zs_adler_flat_launch(cudaStream_t, const uint8_t *, uint64_t, ZsAdlerAcc *, int);
 extern "C" cudaError_t zs_crc_init_launch(cudaStream_t);
@@ -280,7 +280,7 @@ static int zs_lz_params(const zscgpu_deflate_params *p, ZsLzParams *L, int *chai
     return 0;
 }
 
-static int zs_build_deflate_desc(zscgpu_engine *e, const zscgpu_stream *streams, uint32_t n, uint32_t mbl,
+static int zs_build_deflate_desc(zscgpu_engine *e, const zscgpu_stream *streams, uint32_t n, uint32_t mbl, int part,
                                  uint32_t *nchunks_out, uint32_t *nblk_out)
 {
     uint64_t sym = 0, total = 0;
@@ -313,10 +313,10 @@ static int zs_build_deflate_desc(zscgpu_engine *e, const zscgpu_stream *streams,
                 C->blk_cap = clen ? (clen + ZS_BLOCK_SYMS - 1) / ZS_BLOCK_SYMS : 1;
                 C->stream = s;
                 C->flags = 0;
-                if (pos == 0 && j == 0) C->flags |= ZC_FIRST_OF_STREAM;
+                if (pos == 0 && j == 0 && !(part & 1)) C->flags |= ZC_FIRST_OF_STREAM;
                 if (j == nsub - 1) {
                     C->flags |= ZC_LAST_OF_SECTION;
-                    if (pos + sec >= z->raw_len) C->flags |= ZC_LAST_OF_STREAM;
+                    if (pos + sec >= z->raw_len && !(part & 2)) C->flags |= ZC_LAST_OF_STREAM;
                 }
                 if ((uint64_t)nb + C->blk_cap > e->blk_cap) { snprintf(e->err, sizeof(e->err), "batch needs too many block slots"); return ZSCGPU_ERR_CAPACITY; }
                 for (uint32_t k = 0; k < C->blk_cap; k++) e->h_blk_chunk[nb + k] = nc;
@@ -341,11 +341,17 @@ static int zs_build_deflate_desc(zscgpu_engine *e, const zscgpu_stream *streams,
 static int zs_deflate_launch_all(zscgpu_engine *e)
 {
     const uint32_t n = e->last_nstreams, nc = e->last_nchunks, nb = e->last_nblk;
+    /* event slots 8..13 bracket the kernels of the last deflate launch (see zscgpu.h) */
     ZS_CUDA_CHECK(cudaMemsetAsync(e->d_adler, 0, sizeof(ZsAdlerAcc) * n, e->stream));
+    ZS_CUDA_CHECK(cudaEventRecord(e->ev[8], e->stream));
     ZS_CUDA_CHECK(zs_adler_chunks_launch(e->stream, nc, e->d_raw, e->d_chunks, e->d_streams, e->d_adler));
+    ZS_CUDA_CHECK(cudaEventRecord(e->ev[9], e->stream));
     ZS_CUDA_CHECK(zs_lz_launch(e->stream, e->last_chain, nc, e->d_raw, e->d_chunks, e->d_sym, e->d_chunk_nsym, e->d_blk_in_start, e->last_lz));
+    ZS_CUDA_CHECK(cudaEventRecord(e->ev[10], e->stream));
     ZS_CUDA_CHECK(zs_huff_launch(e->stream, nb, n, e->d_chunks, e->d_blk_chunk, e->d_streams, e->d_sym, e->d_chunk_nsym,
-                                 e->d_blk_in_start, e->d_blocks, e->d_adler, e->d_raw, e->d_comp, e->d_ret, e->d_produced, e->d_check, e->last_lz));
+                                 e->d_blk_in_start, e->d_blocks, e->d_adler, e->d_raw, e->d_comp, e->d_ret, e->d_produced, e->d_check, e->last_lz,
+                                 e->ev[11], e->ev[12]));
+    ZS_CUDA_CHECK(cudaEventRecord(e->ev[13], e->stream));
     ZS_CUDA_CHECK(cudaMemcpyAsync(e->h_ret, e->d_ret, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, e->stream));
     ZS_CUDA_CHECK(cudaMemcpyAsync(e->h_produced, e->d_produced, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, e->stream));
     ZS_CUDA_CHECK(cudaMemcpyAsync(e->h_check, e->d_check, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, e->stream));
@@ -360,7 +366,7 @@ extern "C" int zscgpu_deflate_enqueue(zscgpu_engine *e, const zscgpu_stream *str
     ZsLzParams L; int chain;
     if (zs_lz_params(p, &L, &chain)) { snprintf(e->err, sizeof(e->err), "bad level/strategy/wrap"); return ZSCGPU_ERR_ARG; }
     uint32_t nc = 0, nb = 0;
-    int r = zs_build_deflate_desc(e, streams, n, p->max_block_len, &nc, &nb);
+    int r = zs_build_deflate_desc(e, streams, n, p->max_block_len, p->part, &nc, &nb);
     if (r) return r;
     ZS_CUDA_CHECK(cudaMemcpyAsync(e->d_chunks, e->h_chunks, sizeof(ZsChunk) * nc, cudaMemcpyHostToDevice, e->stream));
     ZS_CUDA_CHECK(cudaMemcpyAsync(e->d_streams, e->h_streams, sizeof(ZsStream) * n, cudaMemcpyHostToDevice, e->stream));

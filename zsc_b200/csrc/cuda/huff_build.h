@@ -28,7 +28,7 @@
 #define ZH_BLCODES 19
 #define ZH_HDR_WORDS 96            /* 3072 bits: > worst-case dynamic header (see zh_build_block) */
 
-enum { ZH_STORED = 0, ZH_STATIC = 1, ZH_DYNAMIC = 2, ZH_UNUSED = 3 };
+enum { ZH_STORED = 0, ZH_STATIC = 1, ZH_DYNAMIC = 2, ZH_UNUSED = 3, ZH_STORED_CONT = 4 };
 
 /* Per-block result consumed by the encode kernel. code entries: (bit-reversed code) | len << 16. */
 typedef struct {
@@ -39,7 +39,7 @@ typedef struct {
     uint32_t in_start;                /* input offset (chunk-relative) where this block starts */
     uint32_t in_len;                  /* input bytes the block covers */
     uint32_t flags;                   /* ZB_* */
-    uint32_t pad0;
+    uint32_t stored_total;            /* head of a merged stored run: bytes of the whole run (its LEN field) */
     uint64_t bitoff;                  /* absolute bit offset in the comp arena (offset pass) */
     uint64_t sym_off;                 /* offset of the first symbol in the sym arena */
     uint32_t hdr[ZH_HDR_WORDS];
@@ -244,8 +244,8 @@ ZHD static inline void zh_build_block(const uint32_t *lfreq, const uint32_t *dfr
     if (static_lenb <= opt_lenb) opt_lenb = static_lenb;
     int type;
     if (force == ZH_STORED) type = ZH_STORED;
+    else if ((uint64_t)in_len + 4 <= opt_lenb && in_len <= 65535u) type = ZH_STORED;   /* also under Z_FIXED */
     else if (force == ZH_STATIC) type = ZH_STATIC;
-    else if ((uint64_t)in_len + 4 <= opt_lenb && in_len <= 65535u) type = ZH_STORED;
     else if (static_lenb == opt_lenb || hdr > 32u * ZH_HDR_WORDS - 64u) type = ZH_STATIC;
     else type = ZH_DYNAMIC;
 
@@ -345,6 +345,7 @@ ZHD static inline zk_elem zk_elem_of_block(uint32_t type, uint32_t body_bits, ui
     if ((flags & ZB_FIRST_OF_STREAM) && wrap == 1) e.a = 16;
     zk_elem body = zk_ident();
     if (type == ZH_STORED) { body.a = 3; body.b = 32 + 8ull * in_len; body.al = 1; }
+    else if (type == ZH_STORED_CONT) body.a = 8ull * in_len;      /* payload only, already byte aligned */
     else body.a = body_bits;
     e = zk_compose(e, body);
     if (flags & ZB_LAST_OF_STREAM) {

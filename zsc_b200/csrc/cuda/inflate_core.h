@@ -74,6 +74,7 @@ typedef struct {
     uint32_t data_errors;   /* corrupted sections skipped */
     uint32_t stored_check;  /* adler32 from the trailer */
     uint32_t have_check;    /* trailer was reached */
+    int32_t last_reason;    /* ZI_E_* of the most recent failure */
 } zi_result;
 
 ZID static inline void zi_refill(zi_io *io)
@@ -168,6 +169,7 @@ ZID static inline int zi_decode(zi_io *io, const uint16_t *table, int tbits, con
 ZID static inline int zi_fail(zi_result *r, int ret, int reason)
 {
     if (r->reason == ZI_E_NONE) r->reason = reason;
+    r->last_reason = reason;
     r->ret = ret;
     return ret;
 }
@@ -325,7 +327,7 @@ ZID static inline int zi_blocks(zi_io *io, zi_tables *T, zi_result *res, uint32_
 }
 
 /* Scan for the next full-flush marker 00 00 FF FF at or after byte `from`; returns the position just
- * after it or in_len when none (the reference's syncsearch, src/inflate.c:1523-1545). */
+ * after it, or in_len + 1 when there is none (the reference's syncsearch, src/inflate.c:1523-1545). */
 ZID static inline uint32_t zi_sync(const uint8_t *in, uint32_t in_len, uint32_t from)
 {
     uint32_t got = 0;     /* how much of 00 00 FF FF has been seen */
@@ -336,12 +338,20 @@ ZID static inline uint32_t zi_sync(const uint8_t *in, uint32_t in_len, uint32_t 
         else got = 4 - got;          /* a zero where FF was due: the zero run restarts */
         if (got == 4) return p + 1;
     }
-    return in_len;
+    return in_len + 1;
 }
 
 /* Whole stream: wrapper (wrap 1 = zlib, 0 = raw), blocks, trailer, corruption recovery.
  * The adler32 of the output is verified by the caller (a separate HBM-streaming pass on the GPU);
- * res->stored_check/have_check report the trailer. */
+ * res->stored_check/have_check report the trailer.
+ *
+ * Recovery mirrors zsc_uncompress's loop (src/zsc_uncompr.c:103-127) around inflateSync
+ * (src/inflate.c:1547-1604): after a data error the search for 00 00 FF FF starts at the first
+ * byte the decoder has not pulled (`held` bytes earlier for the two fields the reference still
+ * holds un-dropped in its accumulator when it reports the error: the 16-bit zlib header and the
+ * 32-bit stored-block LEN/NLEN).  No bytes left and nothing held -> Z_BUF_ERROR; no marker ->
+ * Z_DATA_ERROR with all input consumed; marker -> decoding continues behind it and output keeps
+ * appending; a stream that needed any recovery ends as Z_DATA_ERROR. */
 ZID static inline void zi_inflate(const uint8_t *in, uint32_t in_len, uint8_t *out, uint32_t out_cap,
                                   int wrap, zi_tables *T, zi_result *res)
 {
@@ -349,50 +359,62 @@ ZID static inline void zi_inflate(const uint8_t *in, uint32_t in_len, uint8_t *o
     io.in = in; io.in_len = in_len; io.ip = 0; io.hold = 0; io.bits = 0;
     io.out = out; io.out_cap = out_cap; io.op = 0;
     res->ret = ZI_OK; res->reason = ZI_E_NONE; res->produced = 0; res->consumed = 0;
-    res->data_errors = 0; res->stored_check = 0; res->have_check = 0;
+    res->data_errors = 0; res->stored_check = 0; res->have_check = 0; res->last_reason = ZI_E_NONE;
     /* wrap: low byte 0 raw / 1 zlib; bits 8..15 = largest window_bits the caller accepts (0 = 15) */
     const uint32_t maxw = ((wrap >> 8) & 0xFF) ? (uint32_t)((wrap >> 8) & 0xFF) : 15u;
     wrap &= 0xFF;
     uint32_t win = 1u << maxw;
-    int r = ZI_OK;
+    uint32_t held = 0;
+    int r = ZI_OK, terminal = 0;
     if (wrap == 1) {
         zi_refill(&io);
         uint32_t h = zi_take(&io, 16);
+        held = 2;
         if (zi_overrun(&io)) r = zi_fail(res, ZI_BUF_ERROR, ZI_E_INPUT_END);
         else if ((((h & 0xFF) << 8) | (h >> 8)) % 31) r = zi_fail(res, ZI_DATA_ERROR, ZI_E_HEADER_CHECK);
         else if ((h & 0xF) != 8) r = zi_fail(res, ZI_DATA_ERROR, ZI_E_METHOD);
         else if (((h >> 4) & 0xF) + 8 > maxw) r = zi_fail(res, ZI_DATA_ERROR, ZI_E_WINDOW);
         else if (h & 0x2000) r = zi_fail(res, ZI_NEED_DICT, ZI_E_NEED_DICT);
-        else win = 1u << (((h >> 4) & 0xF) + 8);
+        else { win = 1u << (((h >> 4) & 0xF) + 8); held = 0; }
     }
     for (;;) {
-        if (r == ZI_OK) r = zi_blocks(&io, T, res, win);
+        if (r == ZI_OK) { r = zi_blocks(&io, T, res, win); held = (r == ZI_DATA_ERROR && res->last_reason == ZI_E_STORED_LEN) ? 4u : 0u; }
+        if (r == ZI_OK) {
+            /* final block done: byte-align, then the 4-byte data check of a zlib stream */
+            zi_drop(&io, (int)(io.bits & 7));
+            if (wrap == 1) {
+                zi_refill(&io);
+                uint32_t t = zi_take32(&io);
+                if (zi_overrun(&io)) r = zi_fail(res, ZI_BUF_ERROR, ZI_E_INPUT_END);
+                else if (res->data_errors) {
+                    /* the reference's running check restarted at the flush point it resynchronised to, so it
+                       cannot match the whole-stream trailer: it reports a data error with those 4 bytes held */
+                    r = zi_fail(res, ZI_DATA_ERROR, ZI_E_DATA_CHECK); held = 4;
+                } else {
+                    res->stored_check = ((t & 0xFF) << 24) | ((t & 0xFF00) << 8) | ((t >> 8) & 0xFF00) | (t >> 24);
+                    res->have_check = 1;
+                }
+            }
+        }
         if (r != ZI_DATA_ERROR) break;
-        /* corrupted section: skip to the next full-flush point and keep appending output */
         res->data_errors++;
         uint32_t pos = io.ip - (io.bits >> 3);
         if (pos > in_len) pos = in_len;
-        uint32_t nx = zi_sync(in, in_len, pos);
-        if (nx >= in_len) { io.hold = 0; io.bits = 0; io.ip = in_len; break; }
-        io.hold = 0; io.bits = 0; io.ip = nx;
+        io.hold = 0; io.bits = 0;
+        if (held == 0 && pos >= in_len) { io.ip = in_len; terminal = ZI_BUF_ERROR; break; }
+        uint32_t nx = zi_sync(in, in_len, pos - held);
+        held = 0;
+        if (nx > in_len) { io.ip = in_len; terminal = ZI_DATA_ERROR; break; }
+        io.ip = nx;
         r = ZI_OK;
-    }
-    if (r == ZI_OK) {
-        zi_drop(&io, (int)(io.bits & 7));
-        if (wrap == 1) {
-            zi_refill(&io);
-            uint32_t t = zi_take32(&io);
-            if (zi_overrun(&io)) r = zi_fail(res, ZI_BUF_ERROR, ZI_E_INPUT_END);
-            else {
-                res->stored_check = ((t & 0xFF) << 24) | ((t & 0xFF00) << 8) | ((t >> 8) & 0xFF00) | (t >> 24);
-                res->have_check = 1;
-            }
-        }
     }
     res->produced = io.op;
     uint32_t c = zi_consumed_bytes(&io);
     res->consumed = c > in_len ? in_len : c;
-    if (res->data_errors) res->ret = ZI_DATA_ERROR; else res->ret = r;
+    if (terminal) res->ret = terminal;
+    else if (r == ZI_OK && res->data_errors) res->ret = ZI_DATA_ERROR;
+    else res->ret = r;
+    if (r == ZI_NEED_DICT) res->consumed = 0;      /* the reference returns before updating total_in (src/inflate.c:970-973) */
 }
 
 #endif
