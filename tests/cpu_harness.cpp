@@ -246,6 +246,13 @@ uint32_t h_deflate_model(const uint8_t *src, uint32_t n, uint32_t max_block_len,
     return (uint32_t)bw.out.size();
 }
 
+// code lengths for a frequency table (property tests: Kraft equality, length limit)
+int h_lengths(const uint32_t *freq, int n, int maxbits, uint8_t *len)
+{
+    static zh_scratch s;
+    return zh_lengths(freq, n, maxbits, len, &s);
+}
+
 // the zk_elem offset algebra, for property tests
 void h_zk_apply_seq(const uint32_t *types, const uint32_t *body_bits, const uint32_t *in_len, const uint32_t *flags,
                     uint32_t n, int wrap, uint64_t x0, uint64_t *offs, uint64_t *end_by_scan)

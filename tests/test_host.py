@@ -262,3 +262,34 @@ def test_partition_covers_all_sections_contiguously():
             assert parts[0][0] == 0 and parts[-1][1] == n
             assert all(parts[i][1] == parts[i + 1][0] for i in range(w - 1))
             assert max(h - l for l, h in parts) - min(h - l for l, h in parts) <= 1
+
+
+def test_code_lengths_are_complete_and_length_limited():
+    """zh_lengths: Kraft sum exactly 1 (the reference's inflate rejects anything else, src/inftrees.c:168-177),
+    never longer than the limit, every used symbol coded — including Fibonacci-like tables that overflow 15 / 7 bits."""
+    L = refimpl.harness()
+    L.h_lengths.argtypes = [refimpl.u32p, C.c_int, C.c_int, refimpl.u8p]
+    rng = np.random.default_rng(0)
+    for trial in range(3000):
+        n, mb = ((19, 7), (30, 15), (286, 15))[trial % 3]
+        k = int(rng.integers(0, n + 1))
+        f = np.zeros(n, np.uint32)
+        idx = rng.choice(n, k, replace=False)
+        mode = trial % 4
+        if mode == 0:
+            f[idx] = rng.integers(1, 5, k)
+        elif mode == 1:
+            f[idx] = (2 ** rng.integers(0, 13, k)).astype(np.uint32)
+        elif mode == 2:
+            f[idx] = rng.integers(1, 8192, k)
+        else:
+            a, b = 1, 1
+            for i in idx[:40]:
+                f[i] = min(a, 8000)
+                a, b = b, a + b
+        ln = np.zeros(n, np.uint8)
+        L.h_lengths(f.ctypes.data_as(refimpl.u32p), n, mb, ln.ctypes.data_as(refimpl.u8p))
+        used = ln[ln > 0].astype(np.int64)
+        assert len(used) >= 2 and used.max() <= mb
+        assert int(np.sum(1 << (mb - used))) == 1 << mb, (trial, n, mb)
+        assert all(ln[i] > 0 for i in range(n) if f[i] > 0)

@@ -133,15 +133,19 @@ ZHD static inline int zh_lengths(const uint32_t *freq_in, int n, int maxbits, ui
         bl_count[d]++;
     }
     if (overflow > 0) {
-        /* Restore the Kraft sum on the length histogram: move one leaf down from the deepest
-         * non-full level, make a clipped leaf its sibling (same repair idea as the reference's
-         * gen_bitlen overflow loop, src/trees.c:474-507), then hand lengths out by frequency. */
-        do {
+        /* Clipping over-subscribes the code by `excess` units of 2^-maxbits.  Each step below moves
+         * one leaf down from the deepest level that still has room and makes a clipped leaf its
+         * sibling, which removes exactly one unit (the repair idea of the reference's gen_bitlen
+         * overflow loop, src/trees.c:474-507, restated on the Kraft sum); then lengths are handed
+         * out by frequency, longest to rarest. */
+        int64_t excess = -((int64_t)1 << maxbits);
+        for (int l = 1; l <= maxbits; l++) excess += (int64_t)bl_count[l] << (maxbits - l);
+        while (excess > 0) {
             int bits = maxbits - 1;
             while (bl_count[bits] == 0) bits--;
             bl_count[bits]--; bl_count[bits + 1] += 2; bl_count[maxbits]--;
-            overflow -= 2;
-        } while (overflow > 0);
+            excess--;
+        }
         int i = 0;
         for (int bits = maxbits; bits >= 1; bits--)
             for (uint32_t k = 0; k < bl_count[bits]; k++) { s->depth[i] = (uint8_t)bits; i++; }

@@ -324,11 +324,13 @@ ZlibReturn zsc_compress(U8 *dest, U32 *dest_len, const U8 *source, U32 source_le
  * src/inflate.c:786-954).  Returns the header length, 0 when truncated, U32_MAX when malformed. */
 ZSC_PRIVATE U32 zsc_gzip_header(const U8 *s, U32 n, gz_header *gh)
 {
-    if (n < 10) return 0;
+    if (n < 2) return 0;
     if (s[0] != 31 || s[1] != 139) return U32_MAX;
-    if (s[2] != 8) return U32_MAX;
-    U32 flg = s[3];
+    if (n < 4) return 0;
+    if (s[2] != 8) return U32_MAX;                /* the reference checks method and flags as soon as it */
+    U32 flg = s[3];                               /* has pulled them (src/inflate.c:786-801) */
     if (flg & 0xe0) return U32_MAX;
+    if (n < 10) return 0;
     if (gh != Z_NULL) {
         gh->text = (I32)(flg & 1);
         gh->time = (U32)s[4] | ((U32)s[5] << 8) | ((U32)s[6] << 16) | ((U32)s[7] << 24);
@@ -442,15 +444,21 @@ ZlibReturn zsc_uncompress_gzip2(U8 *dest, U32 *dest_len, const U8 *source, U32 *
         *source_len = hl + res.consumed;
         if (res.ret == Z_OK) {
             const U8 *t = source + hl + res.consumed;
-            if (source_len_in - (hl + res.consumed) < 8) res.ret = Z_BUF_ERROR;
+            /* CHECK then LENGTH, each as soon as its four bytes are there (src/inflate.c:1322-1354) */
+            U32 left = source_len_in - (hl + res.consumed);
+            if (left < 4) { res.ret = Z_BUF_ERROR; *source_len = source_len_in; }
             else {
                 U32 crc = 0;
-                rc = zscgpu_checksum_host(e, 1, 0, dest, res.produced, &crc);
+                rc = res.produced ? zscgpu_checksum_host(e, 1, 0, dest, res.produced, &crc) : 0;
                 U32 want = (U32)t[0] | ((U32)t[1] << 8) | ((U32)t[2] << 16) | ((U32)t[3] << 24);
-                U32 isize = (U32)t[4] | ((U32)t[5] << 8) | ((U32)t[6] << 16) | ((U32)t[7] << 24);
                 if (rc != 0) return Z_MEM_ERROR;
-                if (crc != want || isize != res.produced) res.ret = Z_DATA_ERROR;
-                else *source_len += 8;
+                if (crc != want) { res.ret = Z_DATA_ERROR; *source_len = source_len_in; }
+                else if (left < 8) { res.ret = Z_BUF_ERROR; *source_len = source_len_in; }
+                else {
+                    U32 isize = (U32)t[4] | ((U32)t[5] << 8) | ((U32)t[6] << 16) | ((U32)t[7] << 24);
+                    if (isize != res.produced) { res.ret = Z_DATA_ERROR; *source_len = source_len_in; }
+                    else *source_len += 8;
+                }
             }
         }
     }
