@@ -24,6 +24,8 @@ int h_inflate(const uint8_t *in, uint32_t in_len, uint8_t *out, uint32_t out_cap
 // ---------------------------------------------------------------- LZ77 model (mirrors deflate_lz.cu)
 struct LzP { int mode, chain, nice, lazy, min_len, max_dist; };
 static const uint32_t TILE = 2048, WINDOW = 32768, NOHASH = 0xFFFF;
+static int g_near = 1;   /* lanes looked at below the current one (deflate_lz.cu looks at the previous lane only) */
+extern "C" void h_set_near(int n) { g_near = n; }
 
 static inline uint32_t ld32(const uint8_t *p, uint32_t q, uint32_t q_end)
 {
@@ -55,9 +57,10 @@ static void lz_chunk(const uint8_t *data, uint32_t a, uint32_t dict_len, uint32_
                     uint32_t q = t0 + g * 32 + l;
                     d[l] = 0;
                     if (h[l] == NOHASH) continue;
-                    int below = -1;
-                    for (int j = (int)l - 1; j >= 0; j--) if (h[j] == h[l]) { below = j; break; }
-                    d[l] = below >= 0 ? l - (uint32_t)below : ((q - head[h[l]]) & 0xFFFF);
+                    /* candidates come from the table as it stood before this group of 32 positions,
+                       unless one of the ZL_NEAR preceding lanes has the same hash */
+                    d[l] = (q - head[h[l]]) & 0xFFFF;
+                    for (int j = 1; j <= g_near && j <= (int)l; j++) if (h[l - j] == h[l]) { d[l] = (uint32_t)j; break; }
                 }
                 for (uint32_t l = 0; l < 32; l++) {
                     uint32_t q = t0 + g * 32 + l;
@@ -88,7 +91,7 @@ static void lz_chunk(const uint8_t *data, uint32_t a, uint32_t dict_len, uint32_
                         }
                         if (P.chain == 0 || budget-- <= 0) break;
                         uint32_t c = q - d;
-                        if (c + WINDOW < t0 + TILE) break;
+                        if (c + WINDOW < t0 + 2 * TILE) break;     /* the hasher runs one tile ahead */
                         uint32_t step = prevd[c & (WINDOW - 1)];
                         if (step == 0) break;
                         d += step;

@@ -4,52 +4,61 @@
  * deflate_fast / deflate_slow / deflate_rle / deflate_huff (reference src/deflate.c:1400-2245) for a
  * whole batch of independent chunks.  The algorithm is re-designed for a GPU rather than ported:
  *
- *   - the chunk streams through a 64 KiB shared-memory ring (32 KiB history + tile + lookahead);
- *   - a tile of ZL_TILE positions is handled in barrier-separated phases:
- *       B  every position gets its 3-byte hash (all threads)
- *       C  one warp walks the tile 32 positions at a time: head-table lookup, __match_any_sync to
- *          find same-hash peers inside the group, head/chain update  -> first candidate per position
- *       D  every position compares against its candidate(s) (all threads; chain walk for the
- *          deeper levels) -> best (length, distance) per position
- *       E  the parse (greedy or one-step lazy) is a pure function next(p) of the per-position
- *          results, so it is resolved with pointer doubling inside each 32-position group
- *          (warp shuffles), one short serial hop per group, and ballot/popc compaction;
+ *   - the chunk streams through a 64 KiB shared-memory ring (32 KiB history + tiles in flight);
+ *   - work advances in tiles of ZL_TILE positions through a two-stage, warp-specialised pipeline:
+ *       hasher warp (warp 0), one tile ahead: walks the tile 32 positions at a time; every lane reads
+ *          the head table for its 3-byte hash (-> candidate distance), the highest lane of each hash
+ *          then claims the slot (shuffle + store + read-back, no __match_any_sync: that instruction
+ *          costs ~15 cycles per distinct value), chain links are recorded for the deeper levels;
+ *       16 worker warps: stage the next tiles into the ring and hash them (A/B), compare every
+ *          position with its candidate(s) (D), and resolve the parse (E): greedy / one-step-lazy
+ *          parsing is a pure function next(p) of the per-position results, so it is resolved with
+ *          pointer doubling inside each 32-position group (warp shuffles), composed per 128-position
+ *          block, one short serial hop per block, then ballot/popc compaction;
  *   - symbols go to the sym arena as 32-bit words (see ZS_MATCH in huff_build.h); the block
  *     histogram, code construction and bit packing are separate kernels (deflate_huff.cu).
  *
  * Candidate positions are always verified byte-for-byte, so stale or aliased head-table entries
- * can cost ratio but never correctness.
+ * can cost ratio but never correctness.  Every step is deterministic: tests/cpu_harness.cpp holds
+ * a scalar model that predicts the symbol stream bit for bit.
  */
 #include "common.cuh"
 
-#define ZL_THREADS 512
-#define ZL_WARPS (ZL_THREADS / 32)
+#define ZL_WORKER_WARPS 16
+#define ZL_WORKERS (ZL_WORKER_WARPS * 32)          /* 512 worker threads */
+#define ZL_THREADS (ZL_WORKERS + 32)               /* + the hasher warp */
 #define ZL_TILE 2048
 #define ZL_GROUPS (ZL_TILE / 32)
-#define ZL_GPW (ZL_GROUPS / ZL_WARPS)      /* groups per warp */
+#define ZL_GPW (ZL_GROUPS / ZL_WORKER_WARPS)       /* consecutive groups per worker warp (one block) */
+#define ZL_BLOCK (ZL_GPW * 32)                     /* 128 positions */
 #define ZL_RING 65536u
 #define ZL_RING_MASK 0xFFFFu
-#define ZL_LOOKAHEAD 272u                  /* >= 258 + 3, multiple of 16 */
+#define ZL_LOOKAHEAD 272u                          /* >= 258 + 3, multiple of 16 */
 #define ZL_HASH_BITS 15
 #define ZL_NOHASH 0xFFFFu
+#define ZL_NONE 0xFFFFu
 
 struct ZlSmem {
     uint32_t ring32[ZL_RING / 4];
     uint16_t head[1 << ZL_HASH_BITS];
-    uint16_t t_hash[ZL_TILE];
-    uint16_t t_dist[ZL_TILE];
-    uint16_t t_len[ZL_TILE + 32];
-    uint16_t t_exit[ZL_TILE];
-    uint16_t g_entry[ZL_GROUPS];
+    uint16_t t_hash[2][ZL_TILE];      /* double buffered: written by workers, read by the hasher */
+    uint16_t t_cand[2][ZL_TILE];      /* double buffered: written by the hasher, read by workers */
+    uint16_t t_dist[ZL_TILE];         /* best distance per position */
+    uint16_t t_len[ZL_TILE + 32];     /* best length per position (+ zero sentinel) */
+    uint16_t t_exit[ZL_TILE];         /* first parse start beyond the position's group */
+    uint16_t t_bexit[ZL_TILE];        /* first parse start beyond the position's 128-block */
+    uint16_t b_entry[ZL_WORKER_WARPS];
     uint32_t g_cnt[ZL_GROUPS];
     uint32_t g_off[ZL_GROUPS];
-    uint32_t carry;       /* absolute q of the next parse start */
-    uint32_t nsym;        /* symbols emitted so far */
+    uint32_t carry;                   /* absolute q of the next parse start */
+    uint32_t nsym;                    /* symbols emitted so far */
 };
 struct ZlSmemChain {
     ZlSmem s;
-    uint16_t prevd[ZS_WINDOW];   /* distance from a position to the previous one with the same hash */
+    uint16_t prevd[ZS_WINDOW];        /* distance from a position to the previous one with the same hash */
 };
+
+__device__ __forceinline__ void zl_bar_workers() { asm volatile("bar.sync 1, %0;" ::"n"(ZL_WORKERS) : "memory"); }
 
 __device__ __forceinline__ uint32_t zl_ld32(const uint32_t *ring32, uint32_t q)
 {
@@ -78,6 +87,66 @@ __device__ __forceinline__ uint32_t zl_match_len(const uint32_t *ring32, uint32_
     return l < maxl ? l : maxl;
 }
 
+/* workers: copy input bytes [from, to) into the ring (16-byte vectors; bytes for the ragged end) */
+__device__ __forceinline__ uint32_t zl_load(uint32_t *ring32, const uint8_t *gbase, uint32_t loaded, uint32_t need, uint32_t q_end, uint32_t wtid)
+{
+    uint8_t *ring8 = (uint8_t *)ring32;
+    if (need <= loaded) return loaded;
+    uint32_t full_end = need & ~15u;
+    for (uint32_t q = loaded + wtid * 16; q < full_end; q += ZL_WORKERS * 16) {
+        uint4 v = __ldg(reinterpret_cast<const uint4 *>(gbase + q));
+        *reinterpret_cast<uint4 *>(&ring8[q & ZL_RING_MASK]) = v;
+    }
+    uint32_t tail0 = max(loaded, full_end);
+    for (uint32_t q = tail0 + wtid; q < need; q += ZL_WORKERS) ring8[q & ZL_RING_MASK] = __ldg(gbase + q);
+    /* zero a few bytes past the very end so 4-byte compares read defined data */
+    if (need == q_end && wtid < 8) ring8[(q_end + wtid) & ZL_RING_MASK] = 0;
+    return (need == q_end) ? need : full_end;
+}
+
+/* workers: 3-byte hashes of one tile */
+__device__ __forceinline__ void zl_hash_tile(const uint32_t *ring32, uint16_t *t_hash, uint32_t t0, uint32_t q_dict, uint32_t q_end, uint32_t wtid)
+{
+    for (uint32_t i = wtid; i < ZL_TILE; i += ZL_WORKERS) {
+        uint32_t q = t0 + i, h = ZL_NOHASH;
+        if (q >= q_dict && q + 3 <= q_end) h = zl_hash(zl_ld32(ring32, q));
+        t_hash[i] = (uint16_t)h;
+    }
+}
+
+/* hasher warp: head-table pass over one tile, groups of 32 positions in order.
+ * Candidate of a position = 1 if the previous lane has the same hash (runs), else the head-table entry as it
+ * stood before the group.  Afterwards the highest lane of every hash holds the slot. */
+template <bool CHAIN>
+__device__ __forceinline__ void zl_hasher_tile(ZlSmem &S, uint16_t *prevd, const uint16_t *t_hash, uint16_t *t_cand, uint32_t t0, uint32_t lane)
+{
+#pragma unroll 2
+    for (uint32_t g = 0; g < ZL_GROUPS; g++) {
+        const uint32_t i = g * 32 + lane, q = t0 + i;
+        const uint32_t h = t_hash[i];
+        const bool valid = (h != ZL_NOHASH);
+        const uint32_t old = S.head[valid ? h : 0];
+        const uint32_t hp = __shfl_up_sync(0xFFFFFFFFu, h, 1), hn = __shfl_down_sync(0xFFFFFFFFu, h, 1);
+        uint32_t d = (q - old) & 0xFFFFu;
+        if (lane > 0 && hp == h) d = 1;
+        const bool writer = valid && !(lane < 31 && hn == h);     /* the next lane will claim the slot instead */
+        if (writer) S.head[h] = (uint16_t)q;
+        __syncwarp();
+        /* read back: a lower lane of this group may have won the store race; the higher one re-claims */
+        for (;;) {
+            uint32_t w = writer ? S.head[h] : q;
+            uint32_t back = (q - w) & 0xFFFFu;
+            bool lose = writer && back != 0 && back < 32;
+            if (!__any_sync(0xFFFFFFFFu, lose)) break;
+            if (lose) S.head[h] = (uint16_t)q;
+            __syncwarp();
+        }
+        if (!valid) d = 0;
+        t_cand[i] = (uint16_t)d;
+        if (CHAIN && valid) prevd[q & (ZS_WINDOW - 1)] = (uint16_t)d;
+    }
+}
+
 template <bool CHAIN>
 __global__ void __launch_bounds__(ZL_THREADS, 1)
 zs_lz_kernel(const uint8_t *__restrict__ raw, const ZsChunk *__restrict__ chunks,
@@ -89,195 +158,186 @@ zs_lz_kernel(const uint8_t *__restrict__ raw, const ZsChunk *__restrict__ chunks
     uint16_t *prevd = CHAIN ? reinterpret_cast<ZlSmemChain *>(zl_smem_raw)->prevd : nullptr;
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool is_hasher = (warp == 0);
+    const uint32_t wtid = tid - 32, ww = warp - 1;                 /* worker thread / warp index */
     const ZsChunk cd = chunks[blockIdx.x];
     const uint64_t src_addr = (uint64_t)(raw + cd.raw_off) - cd.dict_len;
     const uint32_t a = (uint32_t)(src_addr & 15);
     const uint8_t *gbase = (const uint8_t *)(src_addr - a);       /* q = 0 */
     const uint32_t q_dict = a, q_start = a + cd.dict_len, q_end = q_start + cd.len;
     uint32_t *out_sym = sym + cd.sym_off;
+    const bool hashing = (P.mode == 0);
 
     for (uint32_t i = tid; i < (1u << ZL_HASH_BITS) / 2; i += ZL_THREADS) ((uint32_t *)S.head)[i] = 0;
     if (CHAIN) for (uint32_t i = tid; i < ZS_WINDOW / 2; i += ZL_THREADS) ((uint32_t *)prevd)[i] = 0;
     for (uint32_t i = tid; i < ZL_TILE + 32; i += ZL_THREADS) S.t_len[i] = 0;
     if (tid == 0) { S.carry = q_start; S.nsym = 0; if (cd.len == 0) blk_in_start[cd.blk_base] = 0; }
+
+    /* tiles are [t_first + k * ZL_TILE, ...); with hashing the dictionary is walked too */
+    const uint32_t t_first = hashing ? 0 : (q_start / ZL_TILE) * ZL_TILE;
+    const uint32_t ntiles = q_end > t_first ? (q_end - t_first + ZL_TILE - 1) / ZL_TILE : 0;
+    uint32_t loaded = hashing ? 0 : ((t_first > ZS_WINDOW ? t_first - ZS_WINDOW : 0) & ~15u);
+
+    /* ---- prologue: stage tiles 0 and 1, hash them, head-table pass of tile 0 ---- */
+    if (!is_hasher) loaded = zl_load(S.ring32, gbase, loaded, min(q_end, t_first + 2 * ZL_TILE + ZL_LOOKAHEAD), q_end, wtid);
     __syncthreads();
-
-    uint32_t loaded = 0;   /* ring holds q in [0, loaded) (uniform across the CTA) */
-    const uint32_t t_first = (P.mode == 0) ? 0 : (q_start / ZL_TILE) * ZL_TILE;
-
-    for (uint32_t t0 = t_first; t0 < q_end; t0 += ZL_TILE) {
-        /* ---- A: stream input into the ring (16-byte vectors; bytes for the ragged end) ---- */
-        {
-            uint32_t need = min(q_end, t0 + ZL_TILE + ZL_LOOKAHEAD);
-            if (loaded < t0 && P.mode != 0) loaded = (t0 > ZS_WINDOW ? t0 - ZS_WINDOW : 0) & ~15u;
-            uint32_t full_end = need & ~15u;             /* vectors entirely inside the data */
-            for (uint32_t q = loaded + tid * 16; q < full_end; q += ZL_THREADS * 16) {
-                uint4 v = __ldg(reinterpret_cast<const uint4 *>(gbase + q));
-                *reinterpret_cast<uint4 *>(&((uint8_t *)S.ring32)[q & ZL_RING_MASK]) = v;
-            }
-            uint32_t tail0 = max(loaded, full_end);
-            for (uint32_t q = tail0 + tid; q < need; q += ZL_THREADS)
-                ((uint8_t *)S.ring32)[q & ZL_RING_MASK] = __ldg(gbase + q);
-            /* zero a few bytes past the very end so 4-byte compares read defined data */
-            if (need == q_end && tid < 8) ((uint8_t *)S.ring32)[(q_end + tid) & ZL_RING_MASK] = 0;
-            loaded = (need == q_end) ? need : full_end;
-        }
-        __syncthreads();
-
-        if (P.mode == 0) {
-            /* ---- B: hashes ---- */
-            for (uint32_t i = tid; i < ZL_TILE; i += ZL_THREADS) {
-                uint32_t q = t0 + i;
-                uint32_t h = ZL_NOHASH;
-                if (q >= q_dict && q + 3 <= q_end) h = zl_hash(zl_ld32(S.ring32, q));
-                S.t_hash[i] = (uint16_t)h;
-            }
-            __syncthreads();
-            /* ---- C: head-table pass, one warp, groups in order ---- */
-            if (warp == 0) {
-                const uint32_t lt = zs_lanemask_lt(), gt = zs_lanemask_gt();
-#pragma unroll 4
-                for (uint32_t g = 0; g < ZL_GROUPS; g++) {
-                    uint32_t i = g * 32 + lane, q = t0 + i;
-                    uint32_t h = S.t_hash[i];
-                    bool valid = (h != ZL_NOHASH);
-                    uint32_t peers = __match_any_sync(0xFFFFFFFFu, h);
-                    uint32_t d = 0;
-                    if (valid) {
-                        uint32_t old = S.head[h];
-                        uint32_t below = peers & lt;
-                        d = below ? (lane - (31u - (uint32_t)__clz((int)below))) : ((q - old) & 0xFFFFu);
-                        if (!(peers & gt)) S.head[h] = (uint16_t)q;
-                        if (CHAIN) prevd[q & (ZS_WINDOW - 1)] = (uint16_t)d;
-                    }
-                    S.t_dist[i] = (uint16_t)d;
-                    __syncwarp();
-                }
-            }
-            __syncthreads();
-        }
-        if (t0 + ZL_TILE <= q_start) continue;      /* dictionary-only tile */
-
-        /* ---- D: match lengths ---- */
-        if (P.mode != 2) {
-            for (uint32_t i = tid; i < ZL_TILE; i += ZL_THREADS) {
-                uint32_t q = t0 + i;
-                uint32_t best = 0, bestd = 0;
-                if (q >= q_start && q + 3 <= q_end) {
-                    uint32_t maxl = min(ZS_MAX_MATCH, q_end - q);
-                    uint32_t maxd = min((uint32_t)P.max_dist, q - q_dict);
-                    if (P.mode == 1) {
-                        if (maxd >= 1) { best = zl_match_len(S.ring32, q, 1, maxl); bestd = 1; }
-                    } else {
-                        uint32_t d = S.t_dist[i];
-                        int budget = P.chain;
-                        while (d != 0 && d <= maxd) {
-                            /* cheap reject: the byte that would extend the best match must agree */
-                            if (best < 3 || zl_ld8(S.ring32, q + best) == zl_ld8(S.ring32, q + best - d)) {
-                                uint32_t l = zl_match_len(S.ring32, q, d, maxl);
-                                if (l > best) { best = l; bestd = d; if (l >= (uint32_t)P.nice || l >= maxl) break; }
-                            }
-                            if (!CHAIN || budget-- <= 0) break;
-                            uint32_t c = q - d;
-                            if (c + ZS_WINDOW < t0 + ZL_TILE) break;     /* its link was recycled */
-                            uint32_t step = prevd[c & (ZS_WINDOW - 1)];
-                            if (step == 0) break;
-                            d += step;
-                        }
-                    }
-                    if (best < (uint32_t)P.min_len || (best == 3 && bestd > ZS_TOO_FAR)) { best = 0; bestd = 0; }
-                }
-                S.t_len[i] = (uint16_t)best;
-                S.t_dist[i] = (uint16_t)bestd;
-            }
-        } else {
-            for (uint32_t i = tid; i < ZL_TILE; i += ZL_THREADS) { S.t_len[i] = 0; S.t_dist[i] = 0; }
-        }
-        __syncthreads();
-
-        /* ---- E1: per-group exit function by pointer doubling ---- */
-        uint32_t jn[ZL_GPW];
-#pragma unroll
-        for (int k = 0; k < ZL_GPW; k++) {
-            uint32_t g = warp + k * ZL_WARPS, i = g * 32 + lane;
-            uint32_t L = S.t_len[i];
-            bool take = L >= 3;
-            if (take && P.lazy && S.t_len[i + 1] > L) take = false;
-            uint32_t n = take ? L : 1u;
-            jn[k] = n;
-            uint32_t j = lane + n;
-#pragma unroll
-            for (int r = 0; r < 5; r++) {
-                uint32_t jj = __shfl_sync(0xFFFFFFFFu, j, j & 31);
-                if (j < 32) j = jj;
-            }
-            S.t_exit[i] = (uint16_t)(g * 32 + j);
-        }
-        __syncthreads();
-        /* ---- E2: hop from group to group ---- */
-        if (tid == 0) {
-            uint32_t s = S.carry - t0;
-            for (uint32_t g = 0; g < ZL_GROUPS; g++) {
-                uint32_t e = 0xFFFFu;
-                if (s < (g + 1) * 32) { e = s; s = S.t_exit[s]; }
-                S.g_entry[g] = (uint16_t)e;
-            }
-            S.carry = t0 + s;
-        }
-        __syncthreads();
-        /* ---- E3: mark parse starts, count ---- */
-        uint32_t vmask[ZL_GPW], val[ZL_GPW];
-#pragma unroll
-        for (int k = 0; k < ZL_GPW; k++) {
-            uint32_t g = warp + k * ZL_WARPS, i = g * 32 + lane, q = t0 + i;
-            uint32_t e = S.g_entry[g];
-            uint32_t marks = (e != 0xFFFFu) ? (1u << (e - g * 32)) : 0u;
-            uint32_t n = jn[k];
-            uint32_t j = lane + n;
-#pragma unroll
-            for (int r = 0; r < 5; r++) {
-                uint32_t contrib = (((marks >> lane) & 1u) && j < 32) ? (1u << j) : 0u;
-                marks |= __reduce_or_sync(0xFFFFFFFFu, contrib);
-                uint32_t jj = __shfl_sync(0xFFFFFFFFu, j, j & 31);
-                if (j < 32) j = jj;
-            }
-            bool v = ((marks >> lane) & 1u) && q >= q_start && q < q_end;
-            vmask[k] = __ballot_sync(0xFFFFFFFFu, v);
-            val[k] = (n >= 3) ? zs_match(n, S.t_dist[i]) : zl_ld8(S.ring32, q);
-            if (lane == 0) S.g_cnt[g] = __popc(vmask[k]);
-        }
-        __syncthreads();
-        /* ---- scan of group counts (warp 0) ---- */
-        if (warp == 0) {
-            uint32_t c0 = S.g_cnt[lane * 2], c1 = S.g_cnt[lane * 2 + 1];
-            uint32_t s = c0 + c1, inc = s;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, o); if ((int)lane >= o) inc += t; }
-            uint32_t base = S.nsym + inc - s;
-            S.g_off[lane * 2] = base; S.g_off[lane * 2 + 1] = base + c0;
-            __syncwarp();
-            if (lane == 31) S.nsym = S.nsym + inc;
-        }
-        __syncthreads();
-        /* ---- write symbols ---- */
-#pragma unroll
-        for (int k = 0; k < ZL_GPW; k++) {
-            uint32_t g = warp + k * ZL_WARPS, q = t0 + g * 32 + lane;
-            if ((vmask[k] >> lane) & 1u) {
-                uint32_t idx = S.g_off[g] + __popc(vmask[k] & zs_lanemask_lt());
-                out_sym[idx] = val[k];
-                if ((idx & (ZS_BLOCK_SYMS - 1)) == 0) blk_in_start[cd.blk_base + idx / ZS_BLOCK_SYMS] = q - q_start;
-            }
-        }
-        /* the next tile's phase A only touches ring bytes older than the window; phases B..E are
-           separated from this tile's reads by the barrier after A */
+    if (!is_hasher && hashing) {
+        zl_hash_tile(S.ring32, S.t_hash[0], t_first, q_dict, q_end, wtid);
+        if (ntiles > 1) zl_hash_tile(S.ring32, S.t_hash[1], t_first + ZL_TILE, q_dict, q_end, wtid);
     }
     __syncthreads();
+    if (is_hasher && hashing && ntiles > 0) zl_hasher_tile<CHAIN>(S, prevd, S.t_hash[0], S.t_cand[0], t_first, lane);
+    __syncthreads();
+
+    for (uint32_t k = 0; k < ntiles; k++) {
+        const uint32_t t0 = t_first + k * ZL_TILE;
+        if (is_hasher) {
+            /* one tile ahead of the workers */
+            if (hashing && k + 1 < ntiles)
+                zl_hasher_tile<CHAIN>(S, prevd, S.t_hash[(k + 1) & 1], S.t_cand[(k + 1) & 1], t0 + ZL_TILE, lane);
+        } else {
+            /* ---- A: stage tile k+2 (only ring bytes older than the window of tile k are replaced) ---- */
+            loaded = zl_load(S.ring32, gbase, loaded, min(q_end, t0 + 3 * ZL_TILE + ZL_LOOKAHEAD), q_end, wtid);
+            const bool live = (t0 + ZL_TILE > q_start);           /* not a dictionary-only tile */
+            if (live) {
+                /* ---- D: match lengths ---- */
+                const uint16_t *cand = S.t_cand[k & 1];
+                if (P.mode != 2) {
+                    for (uint32_t i = wtid; i < ZL_TILE; i += ZL_WORKERS) {
+                        uint32_t q = t0 + i;
+                        uint32_t best = 0, bestd = 0;
+                        if (q >= q_start && q + 3 <= q_end) {
+                            uint32_t maxl = min(ZS_MAX_MATCH, q_end - q);
+                            uint32_t maxd = min((uint32_t)P.max_dist, q - q_dict);
+                            if (P.mode == 1) {
+                                if (maxd >= 1) { best = zl_match_len(S.ring32, q, 1, maxl); bestd = 1; }
+                            } else {
+                                uint32_t d = cand[i];
+                                int budget = P.chain;
+                                while (d != 0 && d <= maxd) {
+                                    /* cheap reject: the byte that would extend the best match must agree */
+                                    if (best < 3 || zl_ld8(S.ring32, q + best) == zl_ld8(S.ring32, q + best - d)) {
+                                        uint32_t l = zl_match_len(S.ring32, q, d, maxl);
+                                        if (l > best) { best = l; bestd = d; if (l >= (uint32_t)P.nice || l >= maxl) break; }
+                                    }
+                                    if (!CHAIN || budget-- <= 0) break;
+                                    uint32_t c = q - d;
+                                    /* links of positions the hasher may be recycling right now are off limits */
+                                    if (c + ZS_WINDOW < t0 + 2 * ZL_TILE) break;
+                                    uint32_t step = prevd[c & (ZS_WINDOW - 1)];
+                                    if (step == 0) break;
+                                    d += step;
+                                }
+                            }
+                            if (best < (uint32_t)P.min_len || (best == 3 && bestd > ZS_TOO_FAR)) { best = 0; bestd = 0; }
+                        }
+                        S.t_len[i] = (uint16_t)best;
+                        S.t_dist[i] = (uint16_t)bestd;
+                    }
+                } else {
+                    for (uint32_t i = wtid; i < ZL_TILE; i += ZL_WORKERS) { S.t_len[i] = 0; S.t_dist[i] = 0; }
+                }
+                zl_bar_workers();
+
+                /* ---- E1: exit function per group (pointer doubling), composed per 128-block ---- */
+                uint32_t jn[ZL_GPW];
+                const uint32_t b0 = ww * ZL_BLOCK;                 /* this warp's block, tile relative */
+#pragma unroll
+                for (int g = 0; g < ZL_GPW; g++) {
+                    uint32_t i = b0 + g * 32 + lane;
+                    uint32_t L = S.t_len[i];
+                    bool take = L >= 3;
+                    if (take && P.lazy && S.t_len[i + 1] > L) take = false;
+                    uint32_t n = take ? L : 1u;
+                    jn[g] = n;
+                    uint32_t j = lane + n;
+#pragma unroll
+                    for (int r = 0; r < 5; r++) {
+                        uint32_t jj = __shfl_sync(0xFFFFFFFFu, j, j & 31);
+                        if (j < 32) j = jj;
+                    }
+                    S.t_exit[i] = (uint16_t)(b0 + g * 32 + j);
+                }
+                __syncwarp();
+#pragma unroll
+                for (int g = 0; g < ZL_GPW; g++) {
+                    uint32_t i = b0 + g * 32 + lane;
+                    uint32_t e = S.t_exit[i];
+#pragma unroll
+                    for (int hop = g + 1; hop < ZL_GPW; hop++) if (e < b0 + ZL_BLOCK) e = S.t_exit[e];
+                    S.t_bexit[i] = (uint16_t)e;
+                }
+                zl_bar_workers();
+                /* ---- E2: hop from block to block ---- */
+                if (wtid == 0) {
+                    uint32_t s = S.carry - t0;
+#pragma unroll 4
+                    for (uint32_t b = 0; b < ZL_WORKER_WARPS; b++) {
+                        uint32_t e = ZL_NONE;
+                        if (s < (b + 1) * ZL_BLOCK) { e = s; s = S.t_bexit[s]; }
+                        S.b_entry[b] = (uint16_t)e;
+                    }
+                    S.carry = t0 + s;
+                }
+                zl_bar_workers();
+                /* ---- E3: mark parse starts, count ---- */
+                uint32_t vmask[ZL_GPW], val[ZL_GPW];
+                uint32_t s_in = S.b_entry[ww];
+#pragma unroll
+                for (int g = 0; g < ZL_GPW; g++) {
+                    uint32_t i = b0 + g * 32 + lane, q = t0 + i;
+                    uint32_t marks = 0;
+                    if (s_in != ZL_NONE && s_in < b0 + (g + 1) * 32) { marks = 1u << (s_in - (b0 + g * 32)); s_in = S.t_exit[s_in]; }
+                    uint32_t n = jn[g];
+                    uint32_t j = lane + n;
+#pragma unroll
+                    for (int r = 0; r < 5; r++) {
+                        uint32_t contrib = (((marks >> lane) & 1u) && j < 32) ? (1u << j) : 0u;
+                        marks |= __reduce_or_sync(0xFFFFFFFFu, contrib);
+                        uint32_t jj = __shfl_sync(0xFFFFFFFFu, j, j & 31);
+                        if (j < 32) j = jj;
+                    }
+                    bool v = ((marks >> lane) & 1u) && q >= q_start && q < q_end;
+                    vmask[g] = __ballot_sync(0xFFFFFFFFu, v);
+                    val[g] = (n >= 3) ? zs_match(n, S.t_dist[i]) : zl_ld8(S.ring32, q);
+                    if (lane == 0) S.g_cnt[ww * ZL_GPW + g] = __popc(vmask[g]);
+                }
+                zl_bar_workers();
+                /* ---- scan of group counts (worker warp 0) ---- */
+                if (ww == 0) {
+                    uint32_t c0 = S.g_cnt[lane * 2], c1 = S.g_cnt[lane * 2 + 1];
+                    uint32_t s = c0 + c1, inc = s;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, o); if ((int)lane >= o) inc += t; }
+                    uint32_t base = S.nsym + inc - s;
+                    S.g_off[lane * 2] = base; S.g_off[lane * 2 + 1] = base + c0;
+                    __syncwarp();
+                    if (lane == 31) S.nsym = S.nsym + inc;
+                }
+                zl_bar_workers();
+                /* ---- write symbols ---- */
+#pragma unroll
+                for (int g = 0; g < ZL_GPW; g++) {
+                    uint32_t q = t0 + b0 + g * 32 + lane;
+                    if ((vmask[g] >> lane) & 1u) {
+                        uint32_t idx = S.g_off[ww * ZL_GPW + g] + __popc(vmask[g] & zs_lanemask_lt());
+                        out_sym[idx] = val[g];
+                        if ((idx & (ZS_BLOCK_SYMS - 1)) == 0) blk_in_start[cd.blk_base + idx / ZS_BLOCK_SYMS] = q - q_start;
+                    }
+                }
+            } else {
+                zl_bar_workers();       /* ring bytes staged above must be visible before hashing them */
+            }
+            /* ---- B: hashes of tile k+2 (its bytes were staged in A; every path above passed a worker barrier) ---- */
+            if (hashing && k + 2 < ntiles) zl_hash_tile(S.ring32, S.t_hash[k & 1], t0 + 2 * ZL_TILE, q_dict, q_end, wtid);
+        }
+        __syncthreads();
+    }
     if (tid == 0) chunk_nsym[blockIdx.x] = S.nsym;
 }
 
 static_assert(ZL_GROUPS == 64, "group-count scan assumes 64 groups per tile");
-static_assert(ZL_GPW * ZL_WARPS == ZL_GROUPS, "groups must divide evenly over the warps");
+static_assert(ZL_GPW * ZL_WORKER_WARPS == ZL_GROUPS, "groups must divide evenly over the worker warps");
 
 extern "C" size_t zs_lz_smem_bytes(int chain) { return chain ? sizeof(ZlSmemChain) : sizeof(ZlSmem); }
 
