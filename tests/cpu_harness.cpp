@@ -33,7 +33,11 @@ static inline uint32_t ld32(const uint8_t *p, uint32_t q, uint32_t q_end)
     for (int k = 0; k < 4; k++) v |= (uint32_t)(q + k < q_end ? p[q + k] : 0) << (8 * k);
     return v;
 }
-static inline uint32_t hash3(uint32_t v) { return ((v & 0xFFFFFFu) * 2654435761u) >> 17; }
+static inline uint32_t hash3(uint32_t v)
+{
+    uint32_t h = ((v & 0xFFFFFFu) * 2654435761u) >> 17;
+    return h == 0x7FFF ? 0x7FFE : h;       /* 0x7FFF | flag would collide with the no-hash sentinel */
+}
 
 // data: pointer such that data[q] is the byte at position q (q = 0 is the 16-byte aligned base)
 static void lz_chunk(const uint8_t *data, uint32_t a, uint32_t dict_len, uint32_t len, const LzP &P, std::vector<uint32_t> &sym,
@@ -66,9 +70,10 @@ static void lz_chunk(const uint8_t *data, uint32_t a, uint32_t dict_len, uint32_
                     uint32_t q = t0 + g * 32 + l;
                     t_dist[g * 32 + l] = (uint16_t)d[l];
                     if (h[l] == NOHASH) continue;
-                    bool above = false;
-                    for (uint32_t j = l + 1; j < 32; j++) if (h[j] == h[l]) above = true;
-                    if (!above) head[h[l]] = (uint16_t)q;
+                    /* the lowest lane of each hash claims the slot */
+                    bool below = false;
+                    for (uint32_t j = 0; j < l; j++) if (h[j] == h[l]) below = true;
+                    if (!below) head[h[l]] = (uint16_t)q;
                     prevd[q & (WINDOW - 1)] = (uint16_t)d[l];
                 }
             }

@@ -61,6 +61,23 @@ zs_block_kernel(const ZsChunk *__restrict__ chunks, const uint32_t *__restrict__
         S.dfreq[0][tid] = v;
     }
     __syncthreads();
+    /* literal/length keys: collected by one thread, rank-sorted by all (keys are unique) */
+    __shared__ int s_m, s_maxl;
+    if (tid == 0) s_m = zh_lengths_prepare(S.lfreq[0], ZH_LCODES, &S.scratch, &s_maxl);
+    __syncthreads();
+    {
+        const int m = s_m;
+        uint32_t *sorted = S.scratch.w + ZH_LCODES_PAD;          /* free until the merge starts */
+        for (int i = (int)tid; i < m; i += ZB_THREADS) {
+            const uint32_t key = S.scratch.key[i];
+            int rank = 0;
+            for (int j = 0; j < m; j++) rank += (S.scratch.key[j] < key) ? 1 : 0;
+            sorted[rank] = key;
+        }
+        __syncthreads();
+        for (int i = (int)tid; i < m; i += ZB_THREADS) S.scratch.key[i] = sorted[i];
+    }
+    __syncthreads();
     if (tid == 0) {
         uint32_t in_start = blk_in_start[b];
         uint32_t in_end = (k + 1 < nblk) ? blk_in_start[b + 1] : cd.len;
@@ -69,7 +86,7 @@ zs_block_kernel(const ZsChunk *__restrict__ chunks, const uint32_t *__restrict__
         if (k == nblk - 1 && (cd.flags & ZC_LAST_OF_SECTION)) flags |= ZB_LAST_OF_SECTION;
         if (k == nblk - 1 && (cd.flags & ZC_LAST_OF_STREAM)) flags |= ZB_LAST_OF_STREAM;
         zh_build_block(S.lfreq[0], S.dfreq[0], in_end - in_start, (flags & ZB_LAST_OF_STREAM) ? 1 : 0,
-                       P.force_type, &S.blk, &S.scratch);
+                       P.force_type, &S.blk, &S.scratch, s_m, s_maxl);
         S.blk.nsym = cnt;
         S.blk.in_start = in_start;
         S.blk.flags = flags;

@@ -36,6 +36,7 @@
 #define ZL_LOOKAHEAD 272u                          /* >= 258 + 3, multiple of 16 */
 #define ZL_HASH_BITS 15
 #define ZL_NOHASH 0xFFFFu
+#define ZL_SAMEPREV 0x8000u                      /* t_hash flag: the previous position of the group has the same hash */
 #define ZL_NONE 0xFFFFu
 
 struct ZlSmem {
@@ -72,7 +73,8 @@ __device__ __forceinline__ uint32_t zl_ld8(const uint32_t *ring32, uint32_t q)
 }
 __device__ __forceinline__ uint32_t zl_hash(uint32_t v)
 {
-    return ((v & 0xFFFFFFu) * 2654435761u) >> (32 - ZL_HASH_BITS);
+    uint32_t h = ((v & 0xFFFFFFu) * 2654435761u) >> (32 - ZL_HASH_BITS);
+    return h == 0x7FFFu ? 0x7FFEu : h;          /* 0x7FFF | ZL_SAMEPREV would collide with ZL_NOHASH */
 }
 
 /* length of the common prefix of the strings at q and q - d, at most maxl */
@@ -85,6 +87,43 @@ __device__ __forceinline__ uint32_t zl_match_len(const uint32_t *ring32, uint32_
         l += 4;
     }
     return l < maxl ? l : maxl;
+}
+
+/* common prefix of the strings at q and q - d, looking at 16 bytes only (branch-free: 0..16) */
+__device__ __forceinline__ uint32_t zl_match16(const uint32_t *ring32, uint32_t q, uint32_t d)
+{
+    const uint32_t qb = q - d;
+    const uint32_t ia = (q >> 2) & (ZL_RING / 4 - 1), ib = (qb >> 2) & (ZL_RING / 4 - 1);
+    const uint32_t sa = (q & 3) * 8, sb = (qb & 3) * 8;
+    uint32_t a[5], b[5];
+#pragma unroll
+    for (int k = 0; k < 5; k++) { a[k] = ring32[(ia + k) & (ZL_RING / 4 - 1)]; b[k] = ring32[(ib + k) & (ZL_RING / 4 - 1)]; }
+    uint32_t len = 16;
+#pragma unroll
+    for (int k = 3; k >= 0; k--) {
+        const uint32_t x = __funnelshift_r(a[k], a[k + 1], sa) ^ __funnelshift_r(b[k], b[k + 1], sb);
+        if (x) len = 4 * k + ((uint32_t)(__ffs((int)x) - 1) >> 3);
+    }
+    return len;
+}
+
+/* same, eight bytes per step (three aligned words per side, two funnel shifts) */
+__device__ __forceinline__ uint32_t zl_match_ext(const uint32_t *ring32, uint32_t q, uint32_t d, uint32_t limit)
+{
+    uint32_t l = 0;
+    while (l < limit) {
+        const uint32_t qa = q + l, qb = qa - d;
+        const uint32_t ia = (qa >> 2) & (ZL_RING / 4 - 1), ib = (qb >> 2) & (ZL_RING / 4 - 1);
+        const uint32_t a0 = ring32[ia], a1 = ring32[(ia + 1) & (ZL_RING / 4 - 1)], a2 = ring32[(ia + 2) & (ZL_RING / 4 - 1)];
+        const uint32_t b0 = ring32[ib], b1 = ring32[(ib + 1) & (ZL_RING / 4 - 1)], b2 = ring32[(ib + 2) & (ZL_RING / 4 - 1)];
+        const uint32_t sa = (qa & 3) * 8, sb = (qb & 3) * 8;
+        const uint32_t x0 = __funnelshift_r(a0, a1, sa) ^ __funnelshift_r(b0, b1, sb);
+        const uint32_t x1 = __funnelshift_r(a1, a2, sa) ^ __funnelshift_r(b1, b2, sb);
+        if (x0) { l += (uint32_t)(__ffs((int)x0) - 1) >> 3; break; }
+        if (x1) { l += 4 + ((uint32_t)(__ffs((int)x1) - 1) >> 3); break; }
+        l += 8;
+    }
+    return l < limit ? l : limit;
 }
 
 /* workers: copy input bytes [from, to) into the ring (16-byte vectors; bytes for the ragged end) */
@@ -104,46 +143,54 @@ __device__ __forceinline__ uint32_t zl_load(uint32_t *ring32, const uint8_t *gba
     return (need == q_end) ? need : full_end;
 }
 
-/* workers: 3-byte hashes of one tile */
+/* workers: 3-byte hashes of one tile, 15 bits + ZL_SAMEPREV (positions i, i + 512, ... : a warp covers one group) */
 __device__ __forceinline__ void zl_hash_tile(const uint32_t *ring32, uint16_t *t_hash, uint32_t t0, uint32_t q_dict, uint32_t q_end, uint32_t wtid)
 {
+    const uint32_t lane = wtid & 31;
     for (uint32_t i = wtid; i < ZL_TILE; i += ZL_WORKERS) {
         uint32_t q = t0 + i, h = ZL_NOHASH;
         if (q >= q_dict && q + 3 <= q_end) h = zl_hash(zl_ld32(ring32, q));
+        const uint32_t hp = __shfl_up_sync(0xFFFFFFFFu, h, 1);
+        if (lane > 0 && hp == h && h != ZL_NOHASH) h |= ZL_SAMEPREV;
         t_hash[i] = (uint16_t)h;
     }
 }
 
 /* hasher warp: head-table pass over one tile, groups of 32 positions in order.
  * Candidate of a position = 1 if the previous lane has the same hash (runs), else the head-table entry as it
- * stood before the group.  Afterwards the highest lane of every hash holds the slot. */
+ * stood before the group.  Afterwards the lowest lane of every hash holds the slot (lanes flagged
+ * ZL_SAMEPREV never write; among the others the store race is settled by reading back). */
 template <bool CHAIN>
 __device__ __forceinline__ void zl_hasher_tile(ZlSmem &S, uint16_t *prevd, const uint16_t *t_hash, uint16_t *t_cand, uint32_t t0, uint32_t lane)
 {
-#pragma unroll 2
+    /* The loop is a chain of shared-memory round trips (claim -> read back); the next group's hash is
+       prefetched and the lookup result is consumed only after the read-back has been issued. */
+    uint32_t h_next = t_hash[lane];
     for (uint32_t g = 0; g < ZL_GROUPS; g++) {
         const uint32_t i = g * 32 + lane, q = t0 + i;
-        const uint32_t h = t_hash[i];
-        const bool valid = (h != ZL_NOHASH);
-        const uint32_t old = S.head[valid ? h : 0];
-        const uint32_t hp = __shfl_up_sync(0xFFFFFFFFu, h, 1), hn = __shfl_down_sync(0xFFFFFFFFu, h, 1);
-        uint32_t d = (q - old) & 0xFFFFu;
-        if (lane > 0 && hp == h) d = 1;
-        const bool writer = valid && !(lane < 31 && hn == h);     /* the next lane will claim the slot instead */
-        if (writer) S.head[h] = (uint16_t)q;
+        const uint32_t h16 = h_next;
+        if (g + 1 < ZL_GROUPS) h_next = t_hash[i + 32];
+        const bool valid = (h16 != ZL_NOHASH);
+        const bool same = valid && (h16 & ZL_SAMEPREV);
+        const bool writer = valid && !same;
+        const uint32_t hs = valid ? (h16 & 0x7FFFu) : 0;
+        const uint32_t old = S.head[hs];                           /* lookup: table as it stood before the group */
+        if (writer) S.head[hs] = (uint16_t)q;                      /* claim */
         __syncwarp();
-        /* read back: a lower lane of this group may have won the store race; the higher one re-claims */
-        for (;;) {
-            uint32_t w = writer ? S.head[h] : q;
-            uint32_t back = (q - w) & 0xFFFFu;
-            bool lose = writer && back != 0 && back < 32;
-            if (!__any_sync(0xFFFFFFFFu, lose)) break;
-            if (lose) S.head[h] = (uint16_t)q;
-            __syncwarp();
-        }
+        uint32_t w = S.head[hs];                                   /* read back */
+        uint32_t d = same ? 1u : ((q - old) & 0xFFFFu);
         if (!valid) d = 0;
         t_cand[i] = (uint16_t)d;
         if (CHAIN && valid) prevd[q & (ZS_WINDOW - 1)] = (uint16_t)d;
+        /* a higher lane of this group may have won the store race; the lower one re-claims */
+        for (;;) {
+            uint32_t fwd = (w - q) & 0xFFFFu;
+            bool lose = writer && fwd != 0 && fwd < 32;
+            if (!__any_sync(0xFFFFFFFFu, lose)) break;
+            if (lose) S.head[hs] = (uint16_t)q;
+            __syncwarp();
+            w = S.head[hs];
+        }
     }
 }
 
@@ -202,7 +249,45 @@ zs_lz_kernel(const uint8_t *__restrict__ raw, const ZsChunk *__restrict__ chunks
             if (live) {
                 /* ---- D: match lengths ---- */
                 const uint16_t *cand = S.t_cand[k & 1];
-                if (P.mode != 2) {
+                if (P.mode != 2 && !CHAIN) {
+                    /* One candidate per position.  First every lane compares 16 bytes (no divergence); that
+                       settles all short matches.  Lanes that matched all 16 are long matches, and neighbouring
+                       long lanes with the same distance are inside the same match: only the first lane of
+                       such a run extends the comparison, the others subtract their offset from its extent.
+                       Results are exactly the per-position match lengths. */
+                    const uint32_t le = zs_lanemask_lt() | (1u << lane), gt = zs_lanemask_gt();
+                    for (uint32_t i = wtid; i < ZL_TILE; i += ZL_WORKERS) {
+                        const uint32_t q = t0 + i;
+                        uint32_t d = 0, limit = 0;
+                        if (q >= q_start && q + 3 <= q_end) {
+                            d = (P.mode == 1) ? 1u : (uint32_t)cand[i];
+                            if (d > min((uint32_t)P.max_dist, q - q_dict)) d = 0;
+                            limit = q_end - q;
+                        }
+                        uint32_t best = 0;
+                        if (d) best = zl_match16(S.ring32, q, d);
+                        const bool lng = d != 0 && best == 16 && limit > 16;
+                        const uint32_t lm = __ballot_sync(0xFFFFFFFFu, lng);
+                        if (lm) {
+                            const uint32_t dprev = __shfl_up_sync(0xFFFFFFFFu, d, 1);
+                            const bool prev_l = lane > 0 && ((lm >> (lane - 1)) & 1u);
+                            const bool head = lng && (!prev_l || d != dprev);
+                            const uint32_t hm = __ballot_sync(0xFFFFFFFFu, head);
+                            const uint32_t hl = 31u - (uint32_t)__clz((int)(hm & le));
+                            const uint32_t stop = (hm | ~lm) & gt;
+                            const uint32_t nexth = stop ? (uint32_t)__ffs((int)stop) - 1u : 32u;
+                            uint32_t ext = 0;
+                            if (head) ext = 16u + zl_match_ext(S.ring32, q + 16, d, min(limit, ZS_MAX_MATCH + (nexth - lane - 1u)) - 16u);
+                            const uint32_t e = __shfl_sync(0xFFFFFFFFu, ext, hl & 31u);
+                            if (lng) best = e - (lane - hl);
+                        }
+                        best = min(best, min(limit, ZS_MAX_MATCH));
+                        uint32_t bestd = d;
+                        if (best < (uint32_t)P.min_len || (best == 3 && bestd > ZS_TOO_FAR)) { best = 0; bestd = 0; }
+                        S.t_len[i] = (uint16_t)best;
+                        S.t_dist[i] = (uint16_t)bestd;
+                    }
+                } else if (P.mode != 2) {
                     for (uint32_t i = wtid; i < ZL_TILE; i += ZL_WORKERS) {
                         uint32_t q = t0 + i;
                         uint32_t best = 0, bestd = 0;

@@ -73,19 +73,24 @@ ZHD static inline int zh_extra_dbits(int c) { return c < 4 ? 0 : ((c - 2) >> 1);
 
 ZHD static inline uint32_t zh_bitrev(uint32_t v, int n)
 {
+#ifdef __CUDA_ARCH__
+    return n ? (__brev(v) >> (32 - n)) : 0u;
+#else
     uint32_t r = 0;
     for (int i = 0; i < n; i++) { r = (r << 1) | (v & 1); v >>= 1; }
     return r;
+#endif
 }
 
-/* Code lengths for freq[0..n), limited to maxbits. At least two symbols end up with a code, as the
- * reference guarantees for its trees (src/trees.c:595-610), so that the decoder always sees a
- * complete code.  Returns the largest symbol index with a non-zero length. */
-ZHD static inline int zh_lengths(const uint32_t *freq_in, int n, int maxbits, uint8_t *len, zh_scratch *s)
+/* Code lengths for freq[0..n), limited to maxbits, in three stages so that the block kernel can run the
+ * sort on all its threads: prepare (keys = (freq << 9) | symbol of the used symbols; at least two symbols
+ * end up with a code, as the reference guarantees for its trees, src/trees.c:595-610, so that the decoder
+ * always sees a complete code), sort ascending, finish (two-queue merge, depths, length limit). */
+ZHD static inline int zh_lengths_prepare(const uint32_t *freq_in, int n, zh_scratch *s, int *max_code_out)
 {
     uint32_t *freq = s->tmpfreq;
     int m = 0, max_code = -1;
-    for (int i = 0; i < n; i++) { freq[i] = freq_in[i]; len[i] = 0; if (freq[i]) { m++; max_code = i; } }
+    for (int i = 0; i < n; i++) { freq[i] = freq_in[i]; if (freq[i]) { m++; max_code = i; } }
     while (m < 2) {
         int node = (max_code < 2) ? ++max_code : 0;
         if (freq[node] == 0) { freq[node] = 1; m++; }
@@ -96,16 +101,27 @@ ZHD static inline int zh_lengths(const uint32_t *freq_in, int n, int maxbits, ui
     }
     m = 0;
     for (int i = 0; i < n; i++) if (freq[i]) s->key[m++] = (freq[i] << 9) | (uint32_t)i;
-    /* shell sort, ascending by (freq, symbol) */
+    *max_code_out = max_code;
+    return m;
+}
+
+ZHD static inline void zh_sort_keys(uint32_t *key, int m)
+{
+    /* shell sort, ascending by (freq, symbol); keys are unique */
     const int gaps[6] = {132, 57, 23, 10, 4, 1};
     for (int gi = 0; gi < 6; gi++) {
         int gap = gaps[gi];
         for (int i = gap; i < m; i++) {
-            uint32_t v = s->key[i]; int j = i;
-            while (j >= gap && s->key[j - gap] > v) { s->key[j] = s->key[j - gap]; j -= gap; }
-            s->key[j] = v;
+            uint32_t v = key[i]; int j = i;
+            while (j >= gap && key[j - gap] > v) { key[j] = key[j - gap]; j -= gap; }
+            key[j] = v;
         }
     }
+}
+
+ZHD static inline void zh_lengths_finish(int m, int n, int maxbits, uint8_t *len, zh_scratch *s)
+{
+    for (int i = 0; i < n; i++) len[i] = 0;
     /* two-queue merge: leaves [0,m), internal nodes [m, 2m-1) in creation (= weight) order */
     for (int i = 0; i < m; i++) s->w[i] = s->key[i] >> 9;
     int a = 0, b = m, e = m;
@@ -151,6 +167,15 @@ ZHD static inline int zh_lengths(const uint32_t *freq_in, int n, int maxbits, ui
             for (uint32_t k = 0; k < bl_count[bits]; k++) { s->depth[i] = (uint8_t)bits; i++; }
     }
     for (int i = 0; i < m; i++) len[s->key[i] & 0x1FF] = s->depth[i];
+}
+
+/* all three stages; returns the largest symbol index with a non-zero length */
+ZHD static inline int zh_lengths(const uint32_t *freq_in, int n, int maxbits, uint8_t *len, zh_scratch *s)
+{
+    int max_code;
+    int m = zh_lengths_prepare(freq_in, n, s, &max_code);
+    zh_sort_keys(s->key, m);
+    zh_lengths_finish(m, n, maxbits, len, s);
     return max_code;
 }
 
@@ -207,10 +232,15 @@ ZHD static inline int zh_rle(const uint8_t *len, int n, uint16_t *tok, int nt, u
  *   force: -1 none, ZH_STATIC to force fixed codes (Z_FIXED), ZH_STORED to force stored (level 0)
  */
 ZHD static inline void zh_build_block(const uint32_t *lfreq, const uint32_t *dfreq, uint32_t in_len,
-                                      int final_block, int force, zh_block *out, zh_scratch *s)
+                                      int final_block, int force, zh_block *out, zh_scratch *s,
+                                      int lit_m = -1, int lit_max_code = -1)
 {
     const int bl_order[ZH_BLCODES] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
-    int max_l = zh_lengths(lfreq, ZH_LCODES, 15, s->llen, s);
+    /* lit_m >= 0: s->key already holds the sorted literal/length keys (the block kernel sorts them with all
+       its threads); otherwise all stages run here */
+    int max_l;
+    if (lit_m >= 0) { zh_lengths_finish(lit_m, ZH_LCODES, 15, s->llen, s); max_l = lit_max_code; }
+    else max_l = zh_lengths(lfreq, ZH_LCODES, 15, s->llen, s);
     int max_d = zh_lengths(dfreq, ZH_DCODES, 15, s->dlen, s);
     if (max_l < 256) max_l = 256;
     uint64_t dyn = 0, fix = 0;
@@ -300,19 +330,27 @@ ZHD static inline void zh_build_block(const uint32_t *lfreq, const uint32_t *dfr
 #define ZS_MATCH 0x80000000u
 ZHD static inline uint32_t zs_match(uint32_t len, uint32_t dist) { return ZS_MATCH | ((len - 3) << 16) | (dist - 1); }
 
+ZHD static inline int zh_msb(uint32_t v)     /* position of the highest set bit, v != 0 */
+{
+#ifdef __CUDA_ARCH__
+    return 31 - __clz((int)v);
+#else
+    int n = 31;
+    while (!((v >> n) & 1)) n--;
+    return n;
+#endif
+}
 ZHD static inline int zs_len_code(uint32_t lc /* len - 3 */)
 {
     if (lc < 8) return (int)lc;
     if (lc == 255) return 28;
-    int n = 31;
-    while (!((lc >> n) & 1)) n--;        /* msb position, >= 3 */
+    int n = zh_msb(lc);                  /* msb position, >= 3 */
     return ((n - 1) << 2) | (int)((lc >> (n - 2)) & 3);
 }
 ZHD static inline int zs_dist_code(uint32_t d /* dist - 1 */)
 {
     if (d < 4) return (int)d;
-    int n = 31;
-    while (!((d >> n) & 1)) n--;
+    int n = zh_msb(d);
     return (n << 1) | (int)((d >> (n - 1)) & 1);
 }
 
