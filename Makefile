@@ -7,7 +7,7 @@ NVCC ?= nvcc
 CC ?= gcc
 CXX ?= g++
 ARCH = -gencode arch=compute_100a,code=sm_100a
-NVFLAGS = $(ARCH) -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Iinclude -Izsc_b200/csrc/cuda
+NVFLAGS = $(ARCH) -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Iinclude -Izsc_b200/csrc/cuda $(EXTRA_NVFLAGS)
 CFLAGS = -std=gnu11 -O2 -fPIC -Wall -Wextra -Iinclude
 
 CU = deflate_lz deflate_huff checksum inflate engine
