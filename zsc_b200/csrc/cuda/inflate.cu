@@ -21,15 +21,23 @@ zs_inflate_kernel(uint32_t n, const ZsStream *__restrict__ streams, const uint8_
     extern __shared__ __align__(16) unsigned char zi_smem_raw[];
     zi_tables *T = reinterpret_cast<zi_tables *>(zi_smem_raw) + threadIdx.x;
     const uint32_t s = blockIdx.x * ZI_THREADS + threadIdx.x;
+    zi_mach m;
+    if (s < n) {
+        const ZsStream st = streams[s];
+        zi_m_init(&m, comp + st.comp_off, st.comp_cap, raw + st.raw_off, st.raw_len, wrap, T);
+    } else {
+        m.state = ZM_DONE;
+    }
+    /* lockstep: every lane advances its own stream by one bounded step, then the warp re-converges */
+    while (__any_sync(0xFFFFFFFFu, m.state != ZM_DONE)) {
+        if (m.state != ZM_DONE) zi_step(&m);
+    }
     if (s >= n) return;
-    const ZsStream st = streams[s];
-    zi_result res;
-    zi_inflate(comp + st.comp_off, st.comp_cap, raw + st.raw_off, st.raw_len, wrap, T, &res);
-    ret[s] = res.ret;
-    produced[s] = res.produced;
-    consumed[s] = res.consumed;
-    aux[2 * s] = res.stored_check;
-    aux[2 * s + 1] = res.have_check | (res.data_errors ? 2u : 0u);
+    ret[s] = m.res.ret;
+    produced[s] = m.res.produced;
+    consumed[s] = m.res.consumed;
+    aux[2 * s] = m.res.stored_check;
+    aux[2 * s + 1] = m.res.have_check | (m.res.data_errors ? 2u : 0u);
 }
 
 __global__ void zs_inflate_check_kernel(uint32_t n, const ZsAdlerAcc *__restrict__ acc, const uint32_t *__restrict__ produced,

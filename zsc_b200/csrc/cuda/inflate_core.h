@@ -86,7 +86,7 @@ ZID static inline void zi_refill(zi_io *io)
         const uint8_t *p = io->in + io->ip;
         while ((((uintptr_t)p) & 3) != 0 && io->bits <= 56) { io->hold |= (uint64_t)(*p++) << io->bits; io->bits += 8; io->ip++; }
         if (io->bits <= 32) {
-            io->hold |= (uint64_t)(*reinterpret_cast<const uint32_t *>(p)) << io->bits;
+            io->hold |= (uint64_t)__ldg(reinterpret_cast<const uint32_t *>(p)) << io->bits;
             io->bits += 32; io->ip += 4;
         }
     }
@@ -104,6 +104,42 @@ ZID static inline void zi_drop(zi_io *io, int n) { io->hold >>= n; io->bits -= (
 ZID static inline uint32_t zi_take(zi_io *io, int n) { uint32_t v = zi_peek(io, n); zi_drop(io, n); return v; }
 ZID static inline uint32_t zi_take32(zi_io *io) { uint32_t v = (uint32_t)io->hold; zi_drop(io, 32); return v; }
 ZID static inline uint32_t zi_consumed_bytes(const zi_io *io) { return (uint32_t)(((uint64_t)io->ip * 8 - io->bits + 7) >> 3); }
+
+/* n bytes from a region that does not overlap the destination (stored blocks): eight loads in flight */
+ZID static inline void zi_copy_fwd(uint8_t *dst, const uint8_t *src, uint32_t n)
+{
+    uint32_t i = 0;
+    for (; i + 8 <= n; i += 8) {
+        uint8_t b0 = src[i], b1 = src[i + 1], b2 = src[i + 2], b3 = src[i + 3], b4 = src[i + 4], b5 = src[i + 5], b6 = src[i + 6], b7 = src[i + 7];
+        dst[i] = b0; dst[i + 1] = b1; dst[i + 2] = b2; dst[i + 3] = b3; dst[i + 4] = b4; dst[i + 5] = b5; dst[i + 6] = b6; dst[i + 7] = b7;
+    }
+    for (; i < n; i++) dst[i] = src[i];
+}
+
+/* LZ77 copy of n bytes from `dist` back (may overlap forwards, as in the reference's inffast.c:259-272).
+ * The loads of a step never depend on its stores: with dist >= 8 a step reads bytes written by earlier
+ * steps only; shorter distances replicate the dist-byte pattern, read once. */
+ZID static inline void zi_copy_match(uint8_t *q, uint32_t dist, uint32_t n)
+{
+    const uint8_t *f = q - dist;
+    if (dist >= 8) {
+        uint32_t i = 0;
+        for (; i + 8 <= n; i += 8) {
+            uint8_t b0 = f[i], b1 = f[i + 1], b2 = f[i + 2], b3 = f[i + 3], b4 = f[i + 4], b5 = f[i + 5], b6 = f[i + 6], b7 = f[i + 7];
+            q[i] = b0; q[i + 1] = b1; q[i + 2] = b2; q[i + 3] = b3; q[i + 4] = b4; q[i + 5] = b5; q[i + 6] = b6; q[i + 7] = b7;
+        }
+        uint8_t t[8];
+        const uint32_t r = n - i;
+        for (uint32_t k = 0; k < 8; k++) if (k < r) t[k] = f[i + k];
+        for (uint32_t k = 0; k < 8; k++) if (k < r) q[i + k] = t[k];
+    } else {
+        uint64_t pat = 0;                       /* the dist-byte pattern in a register */
+        for (uint32_t k = 0; k < 8; k++) if (k < dist) pat |= (uint64_t)f[k] << (8 * k);
+        uint32_t sh = 0;
+        const uint32_t wrap = 8 * dist;
+        for (uint32_t i = 0; i < n; i++) { q[i] = (uint8_t)(pat >> sh); sh += 8; if (sh == wrap) sh = 0; }
+    }
+}
 
 ZID static inline uint32_t zi_rev(uint32_t v, int n)
 {
@@ -174,35 +210,30 @@ ZID static inline int zi_fail(zi_result *r, int ret, int reason)
     return ret;
 }
 
-/* Decode deflate blocks until the final block ends (returns ZI_OK) or an error. `lens` is a scratch
- * area of >= 320 bytes that may alias T->lit (it is dead before the tables are filled). */
-ZID static inline int zi_blocks(zi_io *io, zi_tables *T, zi_result *res, uint32_t win_size)
+/* Block header: BFINAL / BTYPE, then either the stored-block length (cursor left on the first payload
+ * byte) or the decode tables of a fixed / dynamic block.  Returns ZI_OK or the failure code. */
+ZID static inline int zi_block_head(zi_io *io, zi_tables *T, zi_result *res, uint32_t *last_out, uint32_t *type_out, uint32_t *stored_len)
 {
     const uint8_t order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
-    for (;;) {
+    zi_refill(io);
+    uint32_t last = zi_take(io, 1), type = zi_take(io, 2);
+    *last_out = last; *type_out = type;
+    if (zi_overrun(io)) return zi_fail(res, ZI_BUF_ERROR, ZI_E_INPUT_END);
+    if (type == 3) return zi_fail(res, ZI_DATA_ERROR, ZI_E_BLOCK_TYPE);
+    if (type == 0) {
+        zi_drop(io, (int)(io->bits & 7));
         zi_refill(io);
-        uint32_t last = zi_take(io, 1), type = zi_take(io, 2);
+        uint32_t v = zi_take32(io);
         if (zi_overrun(io)) return zi_fail(res, ZI_BUF_ERROR, ZI_E_INPUT_END);
-        if (type == 3) return zi_fail(res, ZI_DATA_ERROR, ZI_E_BLOCK_TYPE);
-        if (type == 0) {
-            zi_drop(io, (int)(io->bits & 7));
-            zi_refill(io);
-            uint32_t v = zi_take32(io);
-            if (zi_overrun(io)) return zi_fail(res, ZI_BUF_ERROR, ZI_E_INPUT_END);
-            uint32_t len = v & 0xFFFF;
-            if (len != ((v >> 16) ^ 0xFFFF)) return zi_fail(res, ZI_DATA_ERROR, ZI_E_STORED_LEN);
-            /* rewind the bit buffer to a byte cursor */
-            uint32_t pos = io->ip - (io->bits >> 3);
-            io->hold = 0; io->bits = 0; io->ip = pos;
-            uint32_t n = len;
-            int short_in = 0, short_out = 0;
-            if (n > io->in_len - (pos < io->in_len ? pos : io->in_len)) { n = io->in_len - (pos < io->in_len ? pos : io->in_len); short_in = 1; }
-            if (n > io->out_cap - io->op) { n = io->out_cap - io->op; short_out = 1; short_in = 0; }
-            for (uint32_t i = 0; i < n; i++) io->out[io->op + i] = io->in[pos + i];
-            io->op += n; io->ip = pos + n;
-            if (short_out) return zi_fail(res, ZI_BUF_ERROR, ZI_E_OUTPUT_FULL);
-            if (short_in) return zi_fail(res, ZI_BUF_ERROR, ZI_E_INPUT_END);
-        } else {
+        uint32_t len = v & 0xFFFF;
+        if (len != ((v >> 16) ^ 0xFFFF)) return zi_fail(res, ZI_DATA_ERROR, ZI_E_STORED_LEN);
+        /* rewind the bit buffer to a byte cursor */
+        uint32_t pos = io->ip - (io->bits >> 3);
+        io->hold = 0; io->bits = 0; io->ip = pos;
+        *stored_len = len;
+        return ZI_OK;
+    }
+    {
             if (type == 1) {
                 /* fixed code (RFC 1951 3.2.6): 32 five-bit distance codes (30 and 31 are invalid when
                    used, src/inflate.c:122-206), literal/length lengths 8/9/7/8 in closed form */
@@ -288,42 +319,8 @@ ZID static inline int zi_blocks(zi_io *io, zi_tables *T, zi_result *res, uint32_
                     }
                 }
             }
-            /* ---- symbol loop ---- */
-            for (;;) {
-                zi_refill(io);
-                int s = zi_decode(io, T->lit, ZI_LBITS, T->lsorted, T->lcount, 9);
-                if (zi_overrun(io)) return zi_fail(res, ZI_BUF_ERROR, ZI_E_INPUT_END);
-                if (s < 0) return zi_fail(res, ZI_DATA_ERROR, ZI_E_LITLEN_CODE);
-                if (s < 256) {
-                    if (io->op >= io->out_cap) return zi_fail(res, ZI_BUF_ERROR, ZI_E_OUTPUT_FULL);
-                    io->out[io->op++] = (uint8_t)s;
-                    continue;
-                }
-                if (s == 256) break;
-                if (s > 285) return zi_fail(res, ZI_DATA_ERROR, ZI_E_LITLEN_CODE);
-                uint32_t c = (uint32_t)s - 257, len;
-                if (c < 8) len = 3 + c;
-                else if (c == 28) len = 258;
-                else { uint32_t eb = (c - 4) >> 2; len = 3 + ((4 + (c & 3)) << eb) + zi_take(io, (int)eb); }
-                zi_refill(io);
-                int d = zi_decode(io, T->dist, ZI_DBITS, T->dsorted, T->dcount, 5);
-                if (d < 0 || d > 29) return zi_fail(res, zi_overrun(io) ? ZI_BUF_ERROR : ZI_DATA_ERROR, zi_overrun(io) ? ZI_E_INPUT_END : ZI_E_DIST_CODE);
-                uint32_t dist;
-                if (d < 4) dist = 1 + (uint32_t)d;
-                else { uint32_t eb = ((uint32_t)d - 2) >> 1; dist = 1 + ((2 + ((uint32_t)d & 1)) << eb) + zi_take(io, (int)eb); }
-                if (zi_overrun(io)) return zi_fail(res, ZI_BUF_ERROR, ZI_E_INPUT_END);
-                if (dist > io->op || dist > win_size) return zi_fail(res, ZI_DATA_ERROR, ZI_E_DIST_TOO_FAR);
-                uint32_t room = io->out_cap - io->op;
-                uint32_t n = len < room ? len : room;
-                uint8_t *q = io->out + io->op;
-                const uint8_t *f = q - dist;
-                for (uint32_t i = 0; i < n; i++) q[i] = f[i];
-                io->op += n;
-                if (n < len) return zi_fail(res, ZI_BUF_ERROR, ZI_E_OUTPUT_FULL);
-            }
-        }
-        if (last) return ZI_OK;
     }
+    return ZI_OK;
 }
 
 /* Scan for the next full-flush marker 00 00 FF FF at or after byte `from`; returns the position just
@@ -341,80 +338,188 @@ ZID static inline uint32_t zi_sync(const uint8_t *in, uint32_t in_len, uint32_t 
     return in_len + 1;
 }
 
-/* Whole stream: wrapper (wrap 1 = zlib, 0 = raw), blocks, trailer, corruption recovery.
- * The adler32 of the output is verified by the caller (a separate HBM-streaming pass on the GPU);
- * res->stored_check/have_check report the trailer.
+/* ---- the decoder as a state machine -------------------------------------------------------------
+ * One call of zi_step() advances one stream by a bounded amount of work: a header, up to two symbols, or
+ * up to 16 copied bytes.  On the GPU the 32 streams of a warp call it in lockstep, so lanes re-converge
+ * after every step instead of each running its own nest of loops (thread-per-stream decoding is only
+ * viable that way); on the host zi_inflate() simply loops over it.  Both run exactly this code.
  *
  * Recovery mirrors zsc_uncompress's loop (src/zsc_uncompr.c:103-127) around inflateSync
  * (src/inflate.c:1547-1604): after a data error the search for 00 00 FF FF starts at the first
- * byte the decoder has not pulled (`held` bytes earlier for the two fields the reference still
- * holds un-dropped in its accumulator when it reports the error: the 16-bit zlib header and the
- * 32-bit stored-block LEN/NLEN).  No bytes left and nothing held -> Z_BUF_ERROR; no marker ->
+ * byte the decoder has not pulled (`held` bytes earlier for the fields the reference still holds
+ * un-dropped in its accumulator when it reports the error: the 16-bit zlib header, the 32-bit stored-block
+ * LEN/NLEN, the 32-bit check value).  No bytes left and nothing held -> Z_BUF_ERROR; no marker ->
  * Z_DATA_ERROR with all input consumed; marker -> decoding continues behind it and output keeps
  * appending; a stream that needed any recovery ends as Z_DATA_ERROR. */
+enum { ZM_HEAD = 0, ZM_BLOCK, ZM_SYM, ZM_COPY, ZM_STORED, ZM_TRAIL, ZM_RECOVER, ZM_DONE };
+
+typedef struct {
+    zi_io io;
+    zi_result res;
+    zi_tables *T;
+    int32_t state, wrap;
+    uint32_t last, rem, dist, win, maxw, held;
+} zi_mach;
+
+ZID static inline void zi_m_init(zi_mach *m, const uint8_t *in, uint32_t in_len, uint8_t *out, uint32_t out_cap, int wrap, zi_tables *T)
+{
+    m->io.in = in; m->io.in_len = in_len; m->io.ip = 0; m->io.hold = 0; m->io.bits = 0;
+    m->io.out = out; m->io.out_cap = out_cap; m->io.op = 0;
+    m->res.ret = ZI_OK; m->res.reason = ZI_E_NONE; m->res.produced = 0; m->res.consumed = 0;
+    m->res.data_errors = 0; m->res.stored_check = 0; m->res.have_check = 0; m->res.last_reason = ZI_E_NONE;
+    /* wrap: low byte 0 raw / 1 zlib; bits 8..15 = largest window_bits the caller accepts (0 = 15) */
+    m->maxw = ((wrap >> 8) & 0xFF) ? (uint32_t)((wrap >> 8) & 0xFF) : 15u;
+    m->wrap = wrap & 0xFF;
+    m->win = 1u << m->maxw;
+    m->T = T; m->last = 0; m->rem = 0; m->dist = 0; m->held = 0;
+    m->state = m->wrap == 1 ? ZM_HEAD : ZM_BLOCK;
+}
+
+ZID static inline void zi_m_finish(zi_mach *m, int ret)
+{
+    zi_io *io = &m->io;
+    m->res.produced = io->op;
+    uint32_t c = zi_consumed_bytes(io);
+    m->res.consumed = c > io->in_len ? io->in_len : c;
+    if (ret == ZI_OK && m->res.data_errors) ret = ZI_DATA_ERROR;
+    if (ret == ZI_NEED_DICT) m->res.consumed = 0;     /* the reference returns before updating total_in (src/inflate.c:970-973) */
+    m->res.ret = ret;
+    m->state = ZM_DONE;
+}
+
+/* a failure code from a step: data errors go to recovery, everything else ends the stream */
+ZID static inline void zi_m_fail(zi_mach *m, int r, uint32_t held)
+{
+    if (r == ZI_DATA_ERROR) { m->held = held; m->state = ZM_RECOVER; }
+    else zi_m_finish(m, r);
+}
+
+ZID static inline void zi_step(zi_mach *m)
+{
+    zi_io *io = &m->io;
+    zi_result *res = &m->res;
+    zi_tables *T = m->T;
+    if (m->state == ZM_SYM) {
+        /* up to two symbols: most are literals, and two keep the lanes of a warp busy between copies */
+        for (int rep = 0; rep < 2 && m->state == ZM_SYM; rep++) {
+            zi_refill(io);
+            int s = zi_decode(io, T->lit, ZI_LBITS, T->lsorted, T->lcount, 9);
+            if (zi_overrun(io)) { zi_m_fail(m, zi_fail(res, ZI_BUF_ERROR, ZI_E_INPUT_END), 0); break; }
+            if (s < 0) { zi_m_fail(m, zi_fail(res, ZI_DATA_ERROR, ZI_E_LITLEN_CODE), 0); break; }
+            if (s < 256) {
+                if (io->op >= io->out_cap) { zi_m_fail(m, zi_fail(res, ZI_BUF_ERROR, ZI_E_OUTPUT_FULL), 0); break; }
+                io->out[io->op++] = (uint8_t)s;
+                continue;
+            }
+            if (s == 256) { m->state = m->last ? ZM_TRAIL : ZM_BLOCK; break; }
+            if (s > 285) { zi_m_fail(m, zi_fail(res, ZI_DATA_ERROR, ZI_E_LITLEN_CODE), 0); break; }
+            uint32_t c = (uint32_t)s - 257, len;
+            if (c < 8) len = 3 + c;
+            else if (c == 28) len = 258;
+            else { uint32_t eb = (c - 4) >> 2; len = 3 + ((4 + (c & 3)) << eb) + zi_take(io, (int)eb); }
+            zi_refill(io);
+            int d = zi_decode(io, T->dist, ZI_DBITS, T->dsorted, T->dcount, 5);
+            if (d < 0 || d > 29) {
+                int ov = zi_overrun(io);
+                zi_m_fail(m, zi_fail(res, ov ? ZI_BUF_ERROR : ZI_DATA_ERROR, ov ? ZI_E_INPUT_END : ZI_E_DIST_CODE), 0);
+                break;
+            }
+            uint32_t dist;
+            if (d < 4) dist = 1 + (uint32_t)d;
+            else { uint32_t eb = ((uint32_t)d - 2) >> 1; dist = 1 + ((2 + ((uint32_t)d & 1)) << eb) + zi_take(io, (int)eb); }
+            if (zi_overrun(io)) { zi_m_fail(m, zi_fail(res, ZI_BUF_ERROR, ZI_E_INPUT_END), 0); break; }
+            if (dist > io->op || dist > m->win) { zi_m_fail(m, zi_fail(res, ZI_DATA_ERROR, ZI_E_DIST_TOO_FAR), 0); break; }
+            m->rem = len; m->dist = dist; m->state = ZM_COPY;
+        }
+    }
+    if (m->state == ZM_COPY) {
+        uint32_t room = io->out_cap - io->op;
+        uint32_t n = m->rem < 16 ? m->rem : 16;
+        if (n > room) n = room;
+        zi_copy_match(io->out + io->op, m->dist, n);
+        io->op += n; m->rem -= n;
+        if (m->rem == 0) m->state = ZM_SYM;
+        else if (n == 0 || io->op >= io->out_cap) zi_m_fail(m, zi_fail(res, ZI_BUF_ERROR, ZI_E_OUTPUT_FULL), 0);
+        return;
+    }
+    if (m->state == ZM_STORED) {
+        uint32_t pos = io->ip;
+        uint32_t avail = pos < io->in_len ? io->in_len - pos : 0, room = io->out_cap - io->op;
+        uint32_t n = m->rem < 16 ? m->rem : 16;
+        if (n > avail) n = avail;
+        if (n > room) n = room;
+        zi_copy_fwd(io->out + io->op, io->in + pos, n);
+        io->op += n; io->ip = pos + n; m->rem -= n;
+        if (m->rem == 0) m->state = m->last ? ZM_TRAIL : ZM_BLOCK;
+        else if (n == 0) zi_m_fail(m, zi_fail(res, ZI_BUF_ERROR, room == 0 ? ZI_E_OUTPUT_FULL : ZI_E_INPUT_END), 0);
+        return;
+    }
+    if (m->state == ZM_HEAD) {
+        zi_refill(io);
+        uint32_t h = zi_take(io, 16);
+        int r = ZI_OK;
+        if (zi_overrun(io)) r = zi_fail(res, ZI_BUF_ERROR, ZI_E_INPUT_END);
+        else if ((((h & 0xFF) << 8) | (h >> 8)) % 31) r = zi_fail(res, ZI_DATA_ERROR, ZI_E_HEADER_CHECK);
+        else if ((h & 0xF) != 8) r = zi_fail(res, ZI_DATA_ERROR, ZI_E_METHOD);
+        else if (((h >> 4) & 0xF) + 8 > m->maxw) r = zi_fail(res, ZI_DATA_ERROR, ZI_E_WINDOW);
+        else if (h & 0x2000) r = zi_fail(res, ZI_NEED_DICT, ZI_E_NEED_DICT);
+        if (r == ZI_OK) { m->win = 1u << (((h >> 4) & 0xF) + 8); m->state = ZM_BLOCK; }
+        else zi_m_fail(m, r, 2);
+        return;
+    }
+    if (m->state == ZM_BLOCK) {
+        uint32_t type = 0, slen = 0;
+        int r = zi_block_head(io, T, res, &m->last, &type, &slen);
+        if (r != ZI_OK) { zi_m_fail(m, r, (r == ZI_DATA_ERROR && res->last_reason == ZI_E_STORED_LEN) ? 4u : 0u); return; }
+        if (type == 0) { m->rem = slen; m->state = slen ? ZM_STORED : (m->last ? ZM_TRAIL : ZM_BLOCK); }
+        else m->state = ZM_SYM;
+        return;
+    }
+    if (m->state == ZM_TRAIL) {
+        /* final block done: byte-align, then the 4-byte data check of a zlib stream */
+        zi_drop(io, (int)(io->bits & 7));
+        if (m->wrap == 1) {
+            zi_refill(io);
+            uint32_t t = zi_take32(io);
+            if (zi_overrun(io)) { zi_m_finish(m, zi_fail(res, ZI_BUF_ERROR, ZI_E_INPUT_END)); return; }
+            if (res->data_errors) {
+                /* the reference's running check restarted at the flush point it resynchronised to, so it
+                   cannot match the whole-stream trailer: it reports a data error with those 4 bytes held */
+                zi_m_fail(m, zi_fail(res, ZI_DATA_ERROR, ZI_E_DATA_CHECK), 4);
+                return;
+            }
+            res->stored_check = ((t & 0xFF) << 24) | ((t & 0xFF00) << 8) | ((t >> 8) & 0xFF00) | (t >> 24);
+            res->have_check = 1;
+        }
+        zi_m_finish(m, ZI_OK);
+        return;
+    }
+    if (m->state == ZM_RECOVER) {
+        res->data_errors++;
+        uint32_t pos = io->ip - (io->bits >> 3);
+        if (pos > io->in_len) pos = io->in_len;
+        io->hold = 0; io->bits = 0;
+        uint32_t held = m->held;
+        m->held = 0;
+        if (held == 0 && pos >= io->in_len) { io->ip = io->in_len; zi_m_finish(m, ZI_BUF_ERROR); return; }
+        uint32_t nx = zi_sync(io->in, io->in_len, pos - held);
+        if (nx > io->in_len) { io->ip = io->in_len; zi_m_finish(m, ZI_DATA_ERROR); return; }
+        io->ip = nx;
+        m->state = ZM_BLOCK;
+        return;
+    }
+}
+
+/* Whole stream on one thread: wrapper (wrap 1 = zlib, 0 = raw), blocks, trailer, corruption recovery.
+ * The adler32 of the output is verified by the caller (a separate HBM-streaming pass on the GPU);
+ * res->stored_check/have_check report the trailer. */
 ZID static inline void zi_inflate(const uint8_t *in, uint32_t in_len, uint8_t *out, uint32_t out_cap,
                                   int wrap, zi_tables *T, zi_result *res)
 {
-    zi_io io;
-    io.in = in; io.in_len = in_len; io.ip = 0; io.hold = 0; io.bits = 0;
-    io.out = out; io.out_cap = out_cap; io.op = 0;
-    res->ret = ZI_OK; res->reason = ZI_E_NONE; res->produced = 0; res->consumed = 0;
-    res->data_errors = 0; res->stored_check = 0; res->have_check = 0; res->last_reason = ZI_E_NONE;
-    /* wrap: low byte 0 raw / 1 zlib; bits 8..15 = largest window_bits the caller accepts (0 = 15) */
-    const uint32_t maxw = ((wrap >> 8) & 0xFF) ? (uint32_t)((wrap >> 8) & 0xFF) : 15u;
-    wrap &= 0xFF;
-    uint32_t win = 1u << maxw;
-    uint32_t held = 0;
-    int r = ZI_OK, terminal = 0;
-    if (wrap == 1) {
-        zi_refill(&io);
-        uint32_t h = zi_take(&io, 16);
-        held = 2;
-        if (zi_overrun(&io)) r = zi_fail(res, ZI_BUF_ERROR, ZI_E_INPUT_END);
-        else if ((((h & 0xFF) << 8) | (h >> 8)) % 31) r = zi_fail(res, ZI_DATA_ERROR, ZI_E_HEADER_CHECK);
-        else if ((h & 0xF) != 8) r = zi_fail(res, ZI_DATA_ERROR, ZI_E_METHOD);
-        else if (((h >> 4) & 0xF) + 8 > maxw) r = zi_fail(res, ZI_DATA_ERROR, ZI_E_WINDOW);
-        else if (h & 0x2000) r = zi_fail(res, ZI_NEED_DICT, ZI_E_NEED_DICT);
-        else { win = 1u << (((h >> 4) & 0xF) + 8); held = 0; }
-    }
-    for (;;) {
-        if (r == ZI_OK) { r = zi_blocks(&io, T, res, win); held = (r == ZI_DATA_ERROR && res->last_reason == ZI_E_STORED_LEN) ? 4u : 0u; }
-        if (r == ZI_OK) {
-            /* final block done: byte-align, then the 4-byte data check of a zlib stream */
-            zi_drop(&io, (int)(io.bits & 7));
-            if (wrap == 1) {
-                zi_refill(&io);
-                uint32_t t = zi_take32(&io);
-                if (zi_overrun(&io)) r = zi_fail(res, ZI_BUF_ERROR, ZI_E_INPUT_END);
-                else if (res->data_errors) {
-                    /* the reference's running check restarted at the flush point it resynchronised to, so it
-                       cannot match the whole-stream trailer: it reports a data error with those 4 bytes held */
-                    r = zi_fail(res, ZI_DATA_ERROR, ZI_E_DATA_CHECK); held = 4;
-                } else {
-                    res->stored_check = ((t & 0xFF) << 24) | ((t & 0xFF00) << 8) | ((t >> 8) & 0xFF00) | (t >> 24);
-                    res->have_check = 1;
-                }
-            }
-        }
-        if (r != ZI_DATA_ERROR) break;
-        res->data_errors++;
-        uint32_t pos = io.ip - (io.bits >> 3);
-        if (pos > in_len) pos = in_len;
-        io.hold = 0; io.bits = 0;
-        if (held == 0 && pos >= in_len) { io.ip = in_len; terminal = ZI_BUF_ERROR; break; }
-        uint32_t nx = zi_sync(in, in_len, pos - held);
-        held = 0;
-        if (nx > in_len) { io.ip = in_len; terminal = ZI_DATA_ERROR; break; }
-        io.ip = nx;
-        r = ZI_OK;
-    }
-    res->produced = io.op;
-    uint32_t c = zi_consumed_bytes(&io);
-    res->consumed = c > in_len ? in_len : c;
-    if (terminal) res->ret = terminal;
-    else if (r == ZI_OK && res->data_errors) res->ret = ZI_DATA_ERROR;
-    else res->ret = r;
-    if (r == ZI_NEED_DICT) res->consumed = 0;      /* the reference returns before updating total_in (src/inflate.c:970-973) */
+    zi_mach m;
+    zi_m_init(&m, in, in_len, out, out_cap, wrap, T);
+    while (m.state != ZM_DONE) zi_step(&m);
+    *res = m.res;
 }
 
 #endif
