@@ -25,9 +25,9 @@
 #include <stdint.h>
 
 #ifdef __CUDACC__
-#define ZID __host__ __device__
+#define ZID static __host__ __device__ __forceinline__
 #else
-#define ZID
+#define ZID static inline
 #endif
 
 #define ZI_LBITS 9
@@ -77,7 +77,7 @@ typedef struct {
     int32_t last_reason;    /* ZI_E_* of the most recent failure */
 } zi_result;
 
-ZID static inline void zi_refill(zi_io *io)
+ZID void zi_refill(zi_io *io)
 {
 #ifdef __CUDA_ARCH__
     /* 4-byte aligned loads once the cursor is aligned; the arenas are padded, and bits past in_len
@@ -98,15 +98,15 @@ ZID static inline void zi_refill(zi_io *io)
 #endif
 }
 /* true when more bits were consumed than the input holds */
-ZID static inline int zi_overrun(const zi_io *io) { return (uint64_t)io->ip * 8 - io->bits > (uint64_t)io->in_len * 8; }
-ZID static inline uint32_t zi_peek(const zi_io *io, int n) { return (uint32_t)io->hold & ((1u << n) - 1u); }
-ZID static inline void zi_drop(zi_io *io, int n) { io->hold >>= n; io->bits -= (uint32_t)n; }
-ZID static inline uint32_t zi_take(zi_io *io, int n) { uint32_t v = zi_peek(io, n); zi_drop(io, n); return v; }
-ZID static inline uint32_t zi_take32(zi_io *io) { uint32_t v = (uint32_t)io->hold; zi_drop(io, 32); return v; }
-ZID static inline uint32_t zi_consumed_bytes(const zi_io *io) { return (uint32_t)(((uint64_t)io->ip * 8 - io->bits + 7) >> 3); }
+ZID int zi_overrun(const zi_io *io) { return (uint64_t)io->ip * 8 - io->bits > (uint64_t)io->in_len * 8; }
+ZID uint32_t zi_peek(const zi_io *io, int n) { return (uint32_t)io->hold & ((1u << n) - 1u); }
+ZID void zi_drop(zi_io *io, int n) { io->hold >>= n; io->bits -= (uint32_t)n; }
+ZID uint32_t zi_take(zi_io *io, int n) { uint32_t v = zi_peek(io, n); zi_drop(io, n); return v; }
+ZID uint32_t zi_take32(zi_io *io) { uint32_t v = (uint32_t)io->hold; zi_drop(io, 32); return v; }
+ZID uint32_t zi_consumed_bytes(const zi_io *io) { return (uint32_t)(((uint64_t)io->ip * 8 - io->bits + 7) >> 3); }
 
 /* n bytes from a region that does not overlap the destination (stored blocks): eight loads in flight */
-ZID static inline void zi_copy_fwd(uint8_t *dst, const uint8_t *src, uint32_t n)
+ZID void zi_copy_fwd(uint8_t *dst, const uint8_t *src, uint32_t n)
 {
     uint32_t i = 0;
     for (; i + 8 <= n; i += 8) {
@@ -119,7 +119,7 @@ ZID static inline void zi_copy_fwd(uint8_t *dst, const uint8_t *src, uint32_t n)
 /* LZ77 copy of n bytes from `dist` back (may overlap forwards, as in the reference's inffast.c:259-272).
  * The loads of a step never depend on its stores: with dist >= 8 a step reads bytes written by earlier
  * steps only; shorter distances replicate the dist-byte pattern, read once. */
-ZID static inline void zi_copy_match(uint8_t *q, uint32_t dist, uint32_t n)
+ZID void zi_copy_match(uint8_t *q, uint32_t dist, uint32_t n)
 {
     const uint8_t *f = q - dist;
     if (dist >= 8) {
@@ -141,7 +141,7 @@ ZID static inline void zi_copy_match(uint8_t *q, uint32_t dist, uint32_t n)
     }
 }
 
-ZID static inline uint32_t zi_rev(uint32_t v, int n)
+ZID uint32_t zi_rev(uint32_t v, int n)
 {
 #ifdef __CUDA_ARCH__
     return __brev(v) >> (32 - n);
@@ -154,7 +154,7 @@ ZID static inline uint32_t zi_rev(uint32_t v, int n)
 /* Build one alphabet's tables from code lengths. kind 0: code-length/literal alphabets must be
  * complete; an incomplete set is tolerated only when its longest code is 1 bit and kind != 0
  * (same rule as the reference, src/inftrees.c:168-177).  Returns 0 or -1. */
-ZID static inline int zi_build(const uint8_t *lens, int n, int tbits, uint16_t *table, uint16_t *sorted,
+ZID int zi_build(const uint8_t *lens, int n, int tbits, uint16_t *table, uint16_t *sorted,
                                uint16_t *count, int shift, int allow_incomplete)
 {
     uint16_t offs[16];
@@ -185,7 +185,7 @@ ZID static inline int zi_build(const uint8_t *lens, int n, int tbits, uint16_t *
 }
 
 /* Decode one symbol. Returns the symbol or -1 (invalid code). */
-ZID static inline int zi_decode(zi_io *io, const uint16_t *table, int tbits, const uint16_t *sorted,
+ZID int zi_decode(zi_io *io, const uint16_t *table, int tbits, const uint16_t *sorted,
                                 const uint16_t *count, int shift)
 {
     uint32_t e = table[zi_peek(io, tbits)];
@@ -202,7 +202,7 @@ ZID static inline int zi_decode(zi_io *io, const uint16_t *table, int tbits, con
     return -1;
 }
 
-ZID static inline int zi_fail(zi_result *r, int ret, int reason)
+ZID int zi_fail(zi_result *r, int ret, int reason)
 {
     if (r->reason == ZI_E_NONE) r->reason = reason;
     r->last_reason = reason;
@@ -212,7 +212,7 @@ ZID static inline int zi_fail(zi_result *r, int ret, int reason)
 
 /* Block header: BFINAL / BTYPE, then either the stored-block length (cursor left on the first payload
  * byte) or the decode tables of a fixed / dynamic block.  Returns ZI_OK or the failure code. */
-ZID static inline int zi_block_head(zi_io *io, zi_tables *T, zi_result *res, uint32_t *last_out, uint32_t *type_out, uint32_t *stored_len)
+ZID int zi_block_head(zi_io *io, zi_tables *T, zi_result *res, uint32_t *last_out, uint32_t *type_out, uint32_t *stored_len)
 {
     const uint8_t order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
     zi_refill(io);
@@ -325,7 +325,7 @@ ZID static inline int zi_block_head(zi_io *io, zi_tables *T, zi_result *res, uin
 
 /* Scan for the next full-flush marker 00 00 FF FF at or after byte `from`; returns the position just
  * after it, or in_len + 1 when there is none (the reference's syncsearch, src/inflate.c:1523-1545). */
-ZID static inline uint32_t zi_sync(const uint8_t *in, uint32_t in_len, uint32_t from)
+ZID uint32_t zi_sync(const uint8_t *in, uint32_t in_len, uint32_t from)
 {
     uint32_t got = 0;     /* how much of 00 00 FF FF has been seen */
     for (uint32_t p = from; p < in_len; p++) {
@@ -361,7 +361,7 @@ typedef struct {
     uint32_t last, rem, dist, win, maxw, held;
 } zi_mach;
 
-ZID static inline void zi_m_init(zi_mach *m, const uint8_t *in, uint32_t in_len, uint8_t *out, uint32_t out_cap, int wrap, zi_tables *T)
+ZID void zi_m_init(zi_mach *m, const uint8_t *in, uint32_t in_len, uint8_t *out, uint32_t out_cap, int wrap, zi_tables *T)
 {
     m->io.in = in; m->io.in_len = in_len; m->io.ip = 0; m->io.hold = 0; m->io.bits = 0;
     m->io.out = out; m->io.out_cap = out_cap; m->io.op = 0;
@@ -375,7 +375,7 @@ ZID static inline void zi_m_init(zi_mach *m, const uint8_t *in, uint32_t in_len,
     m->state = m->wrap == 1 ? ZM_HEAD : ZM_BLOCK;
 }
 
-ZID static inline void zi_m_finish(zi_mach *m, int ret)
+ZID void zi_m_finish(zi_mach *m, int ret)
 {
     zi_io *io = &m->io;
     m->res.produced = io->op;
@@ -388,13 +388,13 @@ ZID static inline void zi_m_finish(zi_mach *m, int ret)
 }
 
 /* a failure code from a step: data errors go to recovery, everything else ends the stream */
-ZID static inline void zi_m_fail(zi_mach *m, int r, uint32_t held)
+ZID void zi_m_fail(zi_mach *m, int r, uint32_t held)
 {
     if (r == ZI_DATA_ERROR) { m->held = held; m->state = ZM_RECOVER; }
     else zi_m_finish(m, r);
 }
 
-ZID static inline void zi_step(zi_mach *m)
+ZID void zi_step(zi_mach *m)
 {
     zi_io *io = &m->io;
     zi_result *res = &m->res;
@@ -513,7 +513,7 @@ ZID static inline void zi_step(zi_mach *m)
 /* Whole stream on one thread: wrapper (wrap 1 = zlib, 0 = raw), blocks, trailer, corruption recovery.
  * The adler32 of the output is verified by the caller (a separate HBM-streaming pass on the GPU);
  * res->stored_check/have_check report the trailer. */
-ZID static inline void zi_inflate(const uint8_t *in, uint32_t in_len, uint8_t *out, uint32_t out_cap,
+ZID void zi_inflate(const uint8_t *in, uint32_t in_len, uint8_t *out, uint32_t out_cap,
                                   int wrap, zi_tables *T, zi_result *res)
 {
     zi_mach m;
