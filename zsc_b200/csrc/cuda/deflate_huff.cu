@@ -12,21 +12,33 @@
 
 /* ======================= K2: histogram + codes ======================= */
 #define ZB_THREADS 128
+#define ZB_WARPS (ZB_THREADS / 32)
 
 struct ZbSmem {
-    uint32_t lfreq[ZB_THREADS / 32][ZH_LCODES_PAD];
-    uint32_t dfreq[ZB_THREADS / 32][ZH_DCODES_PAD];
-    zh_scratch scratch;
+    uint32_t lfreq[ZB_WARPS][ZH_LCODES_PAD];
+    uint32_t dfreq[ZB_WARPS][ZH_DCODES_PAD];
+    zh_scratch sc;          /* literal/length tree, then code-length tree, tokens, lengths */
+    zh_scratch sc2;         /* distance tree (built by one thread while the literal tree is in progress) */
     zh_block blk;
+    uint32_t bl_count[16];
+    uint32_t cnt_l[16], cnt_d[16], next_l[16], next_d[16];
+    uint32_t red[2][ZB_WARPS];
+    uint32_t scan[ZB_WARPS];
+    zh_decision D;
+    int m, max_l, max_d, overflow;
 };
 
+/* The serial recipe of zh_build_block (huff_build.h) spread over the CTA: key collection, sort, leaf depths,
+ * costs, canonical codes and the header bit string run on all threads; only the two-queue merge, the RLE
+ * tokenisation and the 19-symbol code-length tree stay on one thread.  Results are identical to the serial
+ * form (tests compare the GPU stream with the host model bit for bit). */
 __global__ void __launch_bounds__(ZB_THREADS)
 zs_block_kernel(const ZsChunk *__restrict__ chunks, const uint32_t *__restrict__ blk_chunk,
                 const uint32_t *__restrict__ sym, const uint32_t *__restrict__ chunk_nsym,
                 const uint32_t *__restrict__ blk_in_start, zh_block *__restrict__ blocks, ZsLzParams P)
 {
     __shared__ ZbSmem S;
-    const uint32_t b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5;
+    const uint32_t b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t c = blk_chunk[b];
     const ZsChunk cd = chunks[c];
     const uint32_t k = b - cd.blk_base;
@@ -37,8 +49,11 @@ zs_block_kernel(const ZsChunk *__restrict__ chunks, const uint32_t *__restrict__
     const uint32_t cnt = min(ZS_BLOCK_SYMS, nsym - k * ZS_BLOCK_SYMS);
     const uint32_t *bs = sym + cd.sym_off + (uint64_t)k * ZS_BLOCK_SYMS;
 
-    for (uint32_t i = tid; i < (ZB_THREADS / 32) * ZH_LCODES_PAD; i += ZB_THREADS) (&S.lfreq[0][0])[i] = 0;
-    for (uint32_t i = tid; i < (ZB_THREADS / 32) * ZH_DCODES_PAD; i += ZB_THREADS) (&S.dfreq[0][0])[i] = 0;
+    /* ---- histogram ---- */
+    for (uint32_t i = tid; i < ZB_WARPS * ZH_LCODES_PAD; i += ZB_THREADS) (&S.lfreq[0][0])[i] = 0;
+    for (uint32_t i = tid; i < ZB_WARPS * ZH_DCODES_PAD; i += ZB_THREADS) (&S.dfreq[0][0])[i] = 0;
+    if (tid < 16) { S.bl_count[tid] = 0; S.cnt_l[tid] = 0; S.cnt_d[tid] = 0; }
+    if (tid == 0) { S.m = 0; S.max_l = 0; S.overflow = 0; }
     __syncthreads();
     for (uint32_t i = tid; i < cnt; i += ZB_THREADS) {
         uint32_t s = bs[i];
@@ -52,41 +67,165 @@ zs_block_kernel(const ZsChunk *__restrict__ chunks, const uint32_t *__restrict__
     __syncthreads();
     for (uint32_t i = tid; i < ZH_LCODES_PAD; i += ZB_THREADS) {
         uint32_t v = 0;
-        for (int w = 0; w < ZB_THREADS / 32; w++) v += S.lfreq[w][i];
-        S.lfreq[0][i] = v + (i == 256 ? 1u : 0u);
+        for (int w = 0; w < ZB_WARPS; w++) v += S.lfreq[w][i];
+        v += (i == 256 ? 1u : 0u);
+        S.lfreq[0][i] = v;
+        S.sc.llen[i] = 0;
+        /* ---- literal/length keys (any order: they are sorted next) ---- */
+        if (v && i < ZH_LCODES) { int slot = atomicAdd(&S.m, 1); S.sc.key[slot] = (v << 9) | i; atomicMax(&S.max_l, (int)i); }
     }
     if (tid < ZH_DCODES_PAD) {
         uint32_t v = 0;
-        for (int w = 0; w < ZB_THREADS / 32; w++) v += S.dfreq[w][tid];
+        for (int w = 0; w < ZB_WARPS; w++) v += S.dfreq[w][tid];
         S.dfreq[0][tid] = v;
     }
     __syncthreads();
-    /* literal/length keys: collected by one thread, rank-sorted by all (keys are unique) */
-    __shared__ int s_m, s_maxl;
-    if (tid == 0) s_m = zh_lengths_prepare(S.lfreq[0], ZH_LCODES, &S.scratch, &s_maxl);
-    __syncthreads();
+    /* fewer than two used symbols (an empty block): the serial routine adds the dummy symbols */
+    if (S.m < 2) { if (tid == 0) S.m = zh_lengths_prepare(S.lfreq[0], ZH_LCODES, &S.sc, &S.max_l); __syncthreads(); }
+    const int m = S.m;
+    /* ---- rank sort of the keys (unique) on all threads; the distance tree meanwhile on one thread ---- */
     {
-        const int m = s_m;
-        uint32_t *sorted = S.scratch.w + ZH_LCODES_PAD;          /* free until the merge starts */
+        uint32_t *sorted = S.sc.w + ZH_LCODES_PAD;          /* free until the merge starts */
         for (int i = (int)tid; i < m; i += ZB_THREADS) {
-            const uint32_t key = S.scratch.key[i];
+            const uint32_t key = S.sc.key[i];
             int rank = 0;
-            for (int j = 0; j < m; j++) rank += (S.scratch.key[j] < key) ? 1 : 0;
+            for (int j = 0; j < m; j++) rank += (S.sc.key[j] < key) ? 1 : 0;
             sorted[rank] = key;
         }
         __syncthreads();
-        for (int i = (int)tid; i < m; i += ZB_THREADS) S.scratch.key[i] = sorted[i];
+        for (int i = (int)tid; i < m; i += ZB_THREADS) S.sc.key[i] = sorted[i];
     }
     __syncthreads();
+    /* ---- merges: literal tree on thread 0, the whole distance tree on thread 32 ---- */
+    if (tid == 0) (void)zh_merge(m, &S.sc);
+    if (tid == 32) S.max_d = zh_lengths(S.dfreq[0], ZH_DCODES, 15, S.sc.dlen, &S.sc2);
+    __syncthreads();
+    /* ---- leaf depths in parallel, clipped to 15 ---- */
+    {
+        const uint32_t root = 2u * (uint32_t)m - 2u;
+        for (int i = (int)tid; i < m; i += ZB_THREADS) {
+            uint32_t d = 1, p = S.sc.parent[i];
+            while (p != root) { p = S.sc.parent[p]; d++; }
+            if (d > 15) { d = 15; atomicAdd(&S.overflow, 1); }
+            S.sc.depth[i] = (uint8_t)d;
+            atomicAdd(&S.bl_count[d], 1u);
+        }
+    }
+    __syncthreads();
+    if (S.overflow > 0) { if (tid == 0) zh_repair(15, S.bl_count, &S.sc); __syncthreads(); }
+    for (int i = (int)tid; i < m; i += ZB_THREADS) S.sc.llen[S.sc.key[i] & 0x1FF] = S.sc.depth[i];
+    __syncthreads();
+    /* ---- symbol costs under the dynamic and the fixed code ---- */
+    {
+        uint32_t dyn = 0, fix = 0;
+        for (uint32_t i = tid; i < ZH_LCODES; i += ZB_THREADS) {
+            uint32_t f = S.lfreq[0][i];
+            if (f) {
+                uint32_t ex = i >= 257 ? (uint32_t)zh_extra_lbits((int)i - 257) : 0u;
+                uint32_t fl = i < 144 ? 8u : i < 256 ? 9u : i < 280 ? 7u : 8u;
+                dyn += f * (S.sc.llen[i] + ex); fix += f * (fl + ex);
+            }
+        }
+        if (tid < ZH_DCODES) {
+            uint32_t f = S.dfreq[0][tid];
+            if (f) { uint32_t ex = (uint32_t)zh_extra_dbits((int)tid); dyn += f * (S.sc.dlen[tid] + ex); fix += f * (5u + ex); }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { dyn += __shfl_down_sync(0xFFFFFFFFu, dyn, o); fix += __shfl_down_sync(0xFFFFFFFFu, fix, o); }
+        if (lane == 0) { S.red[0][warp] = dyn; S.red[1][warp] = fix; }
+    }
+    __syncthreads();
+    const uint32_t in_start = blk_in_start[b];
+    const uint32_t in_end = (k + 1 < nblk) ? blk_in_start[b + 1] : cd.len;
+    uint32_t flags = 0;
+    if (k == 0 && (cd.flags & ZC_FIRST_OF_STREAM)) flags |= ZB_FIRST_OF_STREAM;
+    if (k == nblk - 1 && (cd.flags & ZC_LAST_OF_SECTION)) flags |= ZB_LAST_OF_SECTION;
+    if (k == nblk - 1 && (cd.flags & ZC_LAST_OF_STREAM)) flags |= ZB_LAST_OF_STREAM;
+    const uint32_t final_block = (flags & ZB_LAST_OF_STREAM) ? 1u : 0u;
+    /* ---- tokens, code-length tree, header size, block type: one thread ---- */
     if (tid == 0) {
-        uint32_t in_start = blk_in_start[b];
-        uint32_t in_end = (k + 1 < nblk) ? blk_in_start[b + 1] : cd.len;
-        uint32_t flags = 0;
-        if (k == 0 && (cd.flags & ZC_FIRST_OF_STREAM)) flags |= ZB_FIRST_OF_STREAM;
-        if (k == nblk - 1 && (cd.flags & ZC_LAST_OF_SECTION)) flags |= ZB_LAST_OF_SECTION;
-        if (k == nblk - 1 && (cd.flags & ZC_LAST_OF_STREAM)) flags |= ZB_LAST_OF_STREAM;
-        zh_build_block(S.lfreq[0], S.dfreq[0], in_end - in_start, (flags & ZB_LAST_OF_STREAM) ? 1 : 0,
-                       P.force_type, &S.blk, &S.scratch, s_m, s_maxl);
+        uint64_t dyn = 0, fix = 0;
+        for (int w = 0; w < ZB_WARPS; w++) { dyn += S.red[0][w]; fix += S.red[1][w]; }
+        zh_decide(S.max_l, S.max_d, dyn, fix, in_end - in_start, P.force_type, &S.sc, &S.D);
+        zh_codes(S.sc.bllen, ZH_BLCODES, S.sc.blcode);
+    }
+    for (uint32_t i = tid; i < ZH_HDR_WORDS; i += ZB_THREADS) S.blk.hdr[i] = 0;
+    __syncthreads();
+    const int type = S.D.type, nl = S.D.nl, nd = S.D.nd, nbl = S.D.nbl, nt = S.D.nt;
+    if (type != ZH_STORED) {
+        /* ---- final code lengths, their histogram ---- */
+        for (uint32_t i = tid; i < ZH_LCODES_PAD; i += ZB_THREADS) {
+            uint32_t l = type == ZH_STATIC ? (i < 144 ? 8u : i < 256 ? 9u : i < 280 ? 7u : 8u) : ((int)i < nl ? S.sc.llen[i] : 0u);
+            S.sc.llen[i] = (uint8_t)l;
+            if (l) atomicAdd(&S.cnt_l[l], 1u);
+        }
+        if (tid < ZH_DCODES_PAD) {
+            uint32_t l = type == ZH_STATIC ? 5u : ((int)tid < nd ? S.sc.dlen[tid] : 0u);
+            S.sc.dlen[tid] = (uint8_t)l;
+            if (l) atomicAdd(&S.cnt_d[l], 1u);
+        }
+        __syncthreads();
+        if (tid == 0 || tid == 32) {
+            const uint32_t *cn = tid == 0 ? S.cnt_l : S.cnt_d;
+            uint32_t *nx = tid == 0 ? S.next_l : S.next_d;
+            uint32_t code = 0, prev = 0;
+            for (int bits = 1; bits <= 15; bits++) { code = (code + prev) << 1; nx[bits] = code; prev = cn[bits]; }
+        }
+        __syncthreads();
+        /* ---- canonical codes: next_code[len] + rank among the earlier symbols of the same length ---- */
+        for (uint32_t i = tid; i < ZH_LCODES_PAD; i += ZB_THREADS) {
+            const uint32_t l = S.sc.llen[i];
+            uint32_t rank = 0;
+            for (uint32_t j = 0; j < i; j++) rank += (S.sc.llen[j] == l) ? 1u : 0u;
+            S.blk.lcode[i] = l ? (zh_bitrev(S.next_l[l] + rank, (int)l) | (l << 16)) : 0u;
+        }
+        if (tid < ZH_DCODES_PAD) {
+            const uint32_t l = S.sc.dlen[tid];
+            uint32_t rank = 0;
+            for (uint32_t j = 0; j < tid; j++) rank += (S.sc.dlen[j] == l) ? 1u : 0u;
+            S.blk.dcode[tid] = l ? (zh_bitrev(S.next_d[l] + rank, (int)l) | (l << 16)) : 0u;
+        }
+    }
+    /* ---- header bit string ---- */
+    if (type == ZH_DYNAMIC) {
+        const uint32_t base = 3 + 5 + 5 + 4 + 3 * (uint32_t)nbl;
+        if (tid == 0) {
+            const int bl_order[ZH_BLCODES] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+            zh_bitw bw; bw.w = S.blk.hdr; bw.nbits = 0;
+            zh_put(&bw, final_block | (2u << 1), 3);
+            zh_put(&bw, (uint32_t)(nl - 257), 5);
+            zh_put(&bw, (uint32_t)(nd - 1), 5);
+            zh_put(&bw, (uint32_t)(nbl - 4), 4);
+            for (int i = 0; i < nbl; i++) zh_put(&bw, S.sc.bllen[bl_order[i]], 3);
+        }
+        /* tokens: every thread owns a contiguous run, offsets from a block-wide prefix sum */
+        const int per = (nt + ZB_THREADS - 1) / ZB_THREADS;
+        const int t0 = min(nt, (int)tid * per), t1 = min(nt, t0 + per);
+        uint32_t mine = 0;
+        for (int t = t0; t < t1; t++) { uint32_t nb; (void)zh_tok_bits(S.sc.tok[t], S.sc.blcode, &nb); mine += nb; }
+        uint32_t inc = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xFFFFFFFFu, inc, o); if ((int)lane >= o) inc += v; }
+        if (lane == 31) S.scan[warp] = inc;
+        __syncthreads();                                   /* also orders thread 0's zh_put before the atomics */
+        uint32_t pos = base + inc - mine;
+        for (uint32_t w = 0; w < warp; w++) pos += S.scan[w];
+        for (int t = t0; t < t1; t++) {
+            uint32_t nb, v = zh_tok_bits(S.sc.tok[t], S.sc.blcode, &nb);
+            const uint32_t wi = pos >> 5, sh = pos & 31;
+            atomicOr(&S.blk.hdr[wi], v << sh);
+            if (sh + nb > 32) atomicOr(&S.blk.hdr[wi + 1], v >> (32 - sh));
+            pos += nb;
+        }
+        if (tid == ZB_THREADS - 1) { S.blk.hdr_bits = pos; S.blk.body_bits = (uint32_t)S.D.dyn; }
+    } else if (tid == 0) {
+        S.blk.hdr[0] = final_block | ((type == ZH_STATIC ? 1u : 0u) << 1);
+        S.blk.hdr_bits = 3;
+        S.blk.body_bits = type == ZH_STATIC ? (uint32_t)S.D.fix : 0u;
+    }
+    if (tid == 0) {
+        S.blk.type = (uint32_t)type;
+        S.blk.in_len = in_end - in_start;
         S.blk.nsym = cnt;
         S.blk.in_start = in_start;
         S.blk.flags = flags;

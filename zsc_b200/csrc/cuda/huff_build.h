@@ -119,10 +119,10 @@ ZHD static inline void zh_sort_keys(uint32_t *key, int m)
     }
 }
 
-ZHD static inline void zh_lengths_finish(int m, int n, int maxbits, uint8_t *len, zh_scratch *s)
+/* two-queue merge over the sorted keys: leaves [0,m), internal nodes [m, 2m-1) in creation (= weight)
+ * order; fills s->w and s->parent, returns the node count (root = count - 1) */
+ZHD static inline int zh_merge(int m, zh_scratch *s)
 {
-    for (int i = 0; i < n; i++) len[i] = 0;
-    /* two-queue merge: leaves [0,m), internal nodes [m, 2m-1) in creation (= weight) order */
     for (int i = 0; i < m; i++) s->w[i] = s->key[i] >> 9;
     int a = 0, b = m, e = m;
     while ((m - a) + (e - b) > 1) {
@@ -133,6 +133,33 @@ ZHD static inline void zh_lengths_finish(int m, int n, int maxbits, uint8_t *len
         s->parent[x0] = (uint16_t)e; s->parent[x1] = (uint16_t)e;
         e++;
     }
+    return e;
+}
+
+/* Clipping leaf depths to maxbits over-subscribes the code by `excess` units of 2^-maxbits.  Each step
+ * below moves one leaf down from the deepest level that still has room and makes a clipped leaf its
+ * sibling, which removes exactly one unit (the repair idea of the reference's gen_bitlen overflow loop,
+ * src/trees.c:474-507, restated on the Kraft sum); then lengths are handed out by frequency, longest to
+ * rarest (s->depth[i] of the i-th sorted key). */
+ZHD static inline void zh_repair(int maxbits, uint32_t *bl_count, zh_scratch *s)
+{
+    int64_t excess = -((int64_t)1 << maxbits);
+    for (int l = 1; l <= maxbits; l++) excess += (int64_t)bl_count[l] << (maxbits - l);
+    while (excess > 0) {
+        int bits = maxbits - 1;
+        while (bl_count[bits] == 0) bits--;
+        bl_count[bits]--; bl_count[bits + 1] += 2; bl_count[maxbits]--;
+        excess--;
+    }
+    int i = 0;
+    for (int bits = maxbits; bits >= 1; bits--)
+        for (uint32_t k = 0; k < bl_count[bits]; k++) { s->depth[i] = (uint8_t)bits; i++; }
+}
+
+ZHD static inline void zh_lengths_finish(int m, int n, int maxbits, uint8_t *len, zh_scratch *s)
+{
+    for (int i = 0; i < n; i++) len[i] = 0;
+    int e = zh_merge(m, s);
     /* depths, root first; leaf depth clipped to maxbits with the clipped count recorded */
     uint32_t bl_count[16];
     for (int i = 0; i < 16; i++) bl_count[i] = 0;
@@ -148,24 +175,7 @@ ZHD static inline void zh_lengths_finish(int m, int n, int maxbits, uint8_t *len
         s->depth[i] = (uint8_t)d;
         bl_count[d]++;
     }
-    if (overflow > 0) {
-        /* Clipping over-subscribes the code by `excess` units of 2^-maxbits.  Each step below moves
-         * one leaf down from the deepest level that still has room and makes a clipped leaf its
-         * sibling, which removes exactly one unit (the repair idea of the reference's gen_bitlen
-         * overflow loop, src/trees.c:474-507, restated on the Kraft sum); then lengths are handed
-         * out by frequency, longest to rarest. */
-        int64_t excess = -((int64_t)1 << maxbits);
-        for (int l = 1; l <= maxbits; l++) excess += (int64_t)bl_count[l] << (maxbits - l);
-        while (excess > 0) {
-            int bits = maxbits - 1;
-            while (bl_count[bits] == 0) bits--;
-            bl_count[bits]--; bl_count[bits + 1] += 2; bl_count[maxbits]--;
-            excess--;
-        }
-        int i = 0;
-        for (int bits = maxbits; bits >= 1; bits--)
-            for (uint32_t k = 0; k < bl_count[bits]; k++) { s->depth[i] = (uint8_t)bits; i++; }
-    }
+    if (overflow > 0) zh_repair(maxbits, bl_count, s);
     for (int i = 0; i < m; i++) len[s->key[i] & 0x1FF] = s->depth[i];
 }
 
@@ -226,23 +236,62 @@ ZHD static inline int zh_rle(const uint8_t *len, int n, uint16_t *tok, int nt, u
     return nt;
 }
 
-/* Decide the block type and render its header and code tables.
+typedef struct { int type, nl, nd, nbl, nt; uint32_t hdr_bits_est; uint64_t dyn, fix; } zh_decision;
+
+/* From the code lengths and the symbol costs: RLE tokens, the code-length code, the dynamic header size and
+ * the stored / static / dynamic decision (same rule as the reference, src/trees.c:902-934, on byte-rounded
+ * sizes).  dyn_sym / fix_sym = bits of all symbols incl. end-of-block under the dynamic / fixed codes. */
+ZHD static inline void zh_decide(int max_l, int max_d, uint64_t dyn_sym, uint64_t fix_sym, uint32_t in_len, int force,
+                                 zh_scratch *s, zh_decision *D)
+{
+    const int bl_order[ZH_BLCODES] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+    if (max_l < 256) max_l = 256;
+    int nl = max_l + 1, nd = max_d + 1;
+    for (int i = 0; i <= ZH_BLCODES; i++) s->blfreq[i] = 0;
+    int nt = zh_rle(s->llen, nl, s->tok, 0, s->blfreq);
+    nt = zh_rle(s->dlen, nd, s->tok, nt, s->blfreq);
+    (void)zh_lengths(s->blfreq, ZH_BLCODES, 7, s->bllen, s);
+    int nbl = ZH_BLCODES;
+    while (nbl > 4 && s->bllen[bl_order[nbl - 1]] == 0) nbl--;
+    uint32_t hdr = 3 + 5 + 5 + 4 + 3 * (uint32_t)nbl;
+    for (int i = 0; i < nt; i++) {
+        int sym = s->tok[i] & 0xFF;
+        hdr += s->bllen[sym] + (sym == 16 ? 2 : sym == 17 ? 3 : sym == 18 ? 7 : 0);
+    }
+    uint64_t dyn = dyn_sym + hdr, fix = fix_sym + 3;
+    uint64_t opt_lenb = (dyn + 7) >> 3, static_lenb = (fix + 7) >> 3;
+    if (static_lenb <= opt_lenb) opt_lenb = static_lenb;
+    int type;
+    if (force == ZH_STORED) type = ZH_STORED;
+    else if ((uint64_t)in_len + 4 <= opt_lenb && in_len <= 65535u) type = ZH_STORED;   /* also under Z_FIXED */
+    else if (force == ZH_STATIC) type = ZH_STATIC;
+    else if (static_lenb == opt_lenb || hdr > 32u * ZH_HDR_WORDS - 64u) type = ZH_STATIC;
+    else type = ZH_DYNAMIC;
+    D->type = type; D->nl = nl; D->nd = nd; D->nbl = nbl; D->nt = nt; D->hdr_bits_est = hdr; D->dyn = dyn; D->fix = fix;
+}
+
+/* bits of one RLE token under the code-length code: (value, count) */
+ZHD static inline uint32_t zh_tok_bits(uint16_t tok, const uint32_t *blcode, uint32_t *nbits)
+{
+    int sym = tok & 0xFF, ex = tok >> 8;
+    uint32_t cl = blcode[sym] >> 16, v = blcode[sym] & 0xFFFF;
+    int eb = sym == 16 ? 2 : sym == 17 ? 3 : sym == 18 ? 7 : 0;
+    *nbits = cl + (uint32_t)eb;
+    return v | ((uint32_t)ex << cl);
+}
+
+/* Decide the block type and render its header and code tables (serial form; the block kernel runs the same
+ * steps spread over its threads and must produce identical results).
  *   lfreq[286] (with lfreq[256] already counting the end-of-block), dfreq[30]
  *   in_len: input bytes the block covers (stored-block cost), final_block: BFINAL
  *   force: -1 none, ZH_STATIC to force fixed codes (Z_FIXED), ZH_STORED to force stored (level 0)
  */
 ZHD static inline void zh_build_block(const uint32_t *lfreq, const uint32_t *dfreq, uint32_t in_len,
-                                      int final_block, int force, zh_block *out, zh_scratch *s,
-                                      int lit_m = -1, int lit_max_code = -1)
+                                      int final_block, int force, zh_block *out, zh_scratch *s)
 {
     const int bl_order[ZH_BLCODES] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
-    /* lit_m >= 0: s->key already holds the sorted literal/length keys (the block kernel sorts them with all
-       its threads); otherwise all stages run here */
-    int max_l;
-    if (lit_m >= 0) { zh_lengths_finish(lit_m, ZH_LCODES, 15, s->llen, s); max_l = lit_max_code; }
-    else max_l = zh_lengths(lfreq, ZH_LCODES, 15, s->llen, s);
+    int max_l = zh_lengths(lfreq, ZH_LCODES, 15, s->llen, s);
     int max_d = zh_lengths(dfreq, ZH_DCODES, 15, s->dlen, s);
-    if (max_l < 256) max_l = 256;
     uint64_t dyn = 0, fix = 0;
     for (int i = 0; i < ZH_LCODES; i++) {
         uint32_t f = lfreq[i];
@@ -259,33 +308,13 @@ ZHD static inline void zh_build_block(const uint32_t *lfreq, const uint32_t *dfr
         dyn += (uint64_t)f * (uint32_t)(s->dlen[i] + ex);
         fix += (uint64_t)f * (uint32_t)(5 + ex);
     }
-    int nl = max_l + 1, nd = max_d + 1;
-    for (int i = 0; i <= ZH_BLCODES; i++) s->blfreq[i] = 0;
-    int nt = zh_rle(s->llen, nl, s->tok, 0, s->blfreq);
-    nt = zh_rle(s->dlen, nd, s->tok, nt, s->blfreq);
-    (void)zh_lengths(s->blfreq, ZH_BLCODES, 7, s->bllen, s);
-    int nbl = ZH_BLCODES;
-    while (nbl > 4 && s->bllen[bl_order[nbl - 1]] == 0) nbl--;
-    uint32_t hdr = 3 + 5 + 5 + 4 + 3 * (uint32_t)nbl;
-    for (int i = 0; i < nt; i++) {
-        int sym = s->tok[i] & 0xFF;
-        hdr += s->bllen[sym] + (sym == 16 ? 2 : sym == 17 ? 3 : sym == 18 ? 7 : 0);
-    }
-    dyn += hdr;
-    fix += 3;
-    /* same decision rule as the reference (src/trees.c:902-934), on byte-rounded sizes */
-    uint64_t opt_lenb = (dyn + 7) >> 3, static_lenb = (fix + 7) >> 3;
-    if (static_lenb <= opt_lenb) opt_lenb = static_lenb;
-    int type;
-    if (force == ZH_STORED) type = ZH_STORED;
-    else if ((uint64_t)in_len + 4 <= opt_lenb && in_len <= 65535u) type = ZH_STORED;   /* also under Z_FIXED */
-    else if (force == ZH_STATIC) type = ZH_STATIC;
-    else if (static_lenb == opt_lenb || hdr > 32u * ZH_HDR_WORDS - 64u) type = ZH_STATIC;
-    else type = ZH_DYNAMIC;
+    zh_decision D;
+    zh_decide(max_l, max_d, dyn, fix, in_len, force, s, &D);
+    const int type = D.type, nl = D.nl, nd = D.nd, nbl = D.nbl, nt = D.nt;
 
     out->type = (uint32_t)type;
     out->in_len = in_len;
-    for (int i = 0; i < 8; i++) out->hdr[i] = 0;
+    for (int i = 0; i < ZH_HDR_WORDS; i++) out->hdr[i] = 0;
     zh_bitw bw; bw.w = out->hdr; bw.nbits = 0;
     if (type == ZH_STORED) {
         zh_put(&bw, (uint32_t)(final_block ? 1 : 0), 3);
@@ -300,7 +329,7 @@ ZHD static inline void zh_build_block(const uint32_t *lfreq, const uint32_t *dfr
         zh_codes(s->dlen, ZH_DCODES_PAD, out->dcode);
         zh_put(&bw, (uint32_t)(final_block ? 1 : 0) | (1u << 1), 3);
         out->hdr_bits = 3;
-        out->body_bits = (uint32_t)fix;
+        out->body_bits = (uint32_t)D.fix;
         return;
     }
     for (int i = nl; i < ZH_LCODES_PAD; i++) s->llen[i] = 0;
@@ -308,21 +337,17 @@ ZHD static inline void zh_build_block(const uint32_t *lfreq, const uint32_t *dfr
     zh_codes(s->llen, ZH_LCODES_PAD, out->lcode);
     zh_codes(s->dlen, ZH_DCODES_PAD, out->dcode);
     zh_codes(s->bllen, ZH_BLCODES, s->blcode);
-    for (int i = 0; i < ZH_HDR_WORDS; i++) out->hdr[i] = 0;
     zh_put(&bw, (uint32_t)(final_block ? 1 : 0) | (2u << 1), 3);
     zh_put(&bw, (uint32_t)(nl - 257), 5);
     zh_put(&bw, (uint32_t)(nd - 1), 5);
     zh_put(&bw, (uint32_t)(nbl - 4), 4);
     for (int i = 0; i < nbl; i++) zh_put(&bw, s->bllen[bl_order[i]], 3);
     for (int i = 0; i < nt; i++) {
-        int sym = s->tok[i] & 0xFF, ex = s->tok[i] >> 8;
-        zh_put(&bw, s->blcode[sym] & 0xFFFF, (int)(s->blcode[sym] >> 16));
-        if (sym == 16) zh_put(&bw, (uint32_t)ex, 2);
-        else if (sym == 17) zh_put(&bw, (uint32_t)ex, 3);
-        else if (sym == 18) zh_put(&bw, (uint32_t)ex, 7);
+        uint32_t nb, v = zh_tok_bits(s->tok[i], s->blcode, &nb);
+        zh_put(&bw, v, (int)nb);
     }
     out->hdr_bits = bw.nbits;
-    out->body_bits = (uint32_t)dyn;
+    out->body_bits = (uint32_t)D.dyn;
 }
 
 /* ---- symbol format shared by the LZ77 kernel, the histogram and the encoder ----
