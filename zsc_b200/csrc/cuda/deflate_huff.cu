@@ -24,6 +24,7 @@ struct ZbSmem {
     uint32_t cnt_l[16], cnt_d[16], next_l[16], next_d[16];
     uint32_t red[2][ZB_WARPS];
     uint32_t scan[ZB_WARPS];
+    uint32_t ccnt[9][16];
     zh_decision D;
     int m, max_l, max_d, overflow;
 };
@@ -142,16 +143,118 @@ zs_block_kernel(const ZsChunk *__restrict__ chunks, const uint32_t *__restrict__
     if (k == nblk - 1 && (cd.flags & ZC_LAST_OF_SECTION)) flags |= ZB_LAST_OF_SECTION;
     if (k == nblk - 1 && (cd.flags & ZC_LAST_OF_STREAM)) flags |= ZB_LAST_OF_STREAM;
     const uint32_t final_block = (flags & ZB_LAST_OF_STREAM) ? 1u : 0u;
-    /* ---- tokens, code-length tree, header size, block type: one thread ---- */
+    /* ---- RLE of the code lengths into code-length-alphabet tokens, in parallel (same tokens as zh_rle):
+            runs of equal lengths -> tokens per run -> prefix sums -> every run writes its own tokens ---- */
+    const int nl = max(S.max_l, 256) + 1, nd = S.max_d + 1, nseq = nl + nd;
+    uint16_t *run_start = S.sc2.parent;                 /* the distance tree's scratch is free now */
+    uint8_t *run_val = S.sc2.depth;
+    uint16_t *run_tok = reinterpret_cast<uint16_t *>(S.sc2.w);
+    if (tid <= ZH_BLCODES) S.sc.blfreq[tid] = 0;
+    {
+        const int i0 = (int)tid * 3;
+        uint32_t v[3]; bool st[3]; int nst = 0;
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            const int i = i0 + j;
+            v[j] = 0; st[j] = false;
+            if (i < nseq) {
+                v[j] = i < nl ? S.sc.llen[i] : S.sc.dlen[i - nl];
+                const uint32_t pv = (i == 0 || i == nl) ? 0xFFFFu : (i - 1 < nl ? S.sc.llen[i - 1] : S.sc.dlen[i - 1 - nl]);
+                st[j] = (pv != v[j]);
+                nst += st[j] ? 1 : 0;
+            }
+        }
+        uint32_t inc = (uint32_t)nst;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, o); if ((int)lane >= o) inc += t; }
+        if (lane == 31) S.scan[warp] = inc;
+        __syncthreads();
+        uint32_t r = inc - (uint32_t)nst;
+        for (uint32_t w = 0; w < warp; w++) r += S.scan[w];
+        uint32_t nruns = 0;
+        for (uint32_t w = 0; w < ZB_WARPS; w++) nruns += S.scan[w];
+#pragma unroll
+        for (int j = 0; j < 3; j++) if (st[j]) { run_start[r] = (uint16_t)(i0 + j); run_val[r] = (uint8_t)v[j]; r++; }
+        if (tid == 0) run_start[nruns] = (uint16_t)nseq;
+        __syncthreads();
+        /* tokens per run (the runs this thread found), then their offsets */
+        uint32_t r0 = r - (uint32_t)nst, ntk = 0;
+        for (uint32_t q = r0; q < r0 + (uint32_t)nst; q++) {
+            uint32_t run = (uint32_t)run_start[q + 1] - run_start[q];
+            if (run_val[q] == 0) { uint32_t rem = run % 138; ntk += run / 138 + (rem >= 3 ? 1u : rem); }
+            else { run--; uint32_t rem = run % 6; ntk += 1 + run / 6 + (rem >= 3 ? 1u : rem); }
+        }
+        __syncthreads();                                 /* S.scan is reused */
+        inc = ntk;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, o); if ((int)lane >= o) inc += t; }
+        if (lane == 31) S.scan[warp] = inc;
+        __syncthreads();
+        uint32_t t = inc - ntk;
+        for (uint32_t w = 0; w < warp; w++) t += S.scan[w];
+        uint32_t total = 0;
+        for (uint32_t w = 0; w < ZB_WARPS; w++) total += S.scan[w];
+        if (tid == 0) S.D.nt = (int)total;
+        for (uint32_t q = r0; q < r0 + (uint32_t)nst; q++) {
+            uint32_t run = (uint32_t)run_start[q + 1] - run_start[q];
+            const uint32_t val = run_val[q];
+            if (val == 0) {
+                while (run >= 11) { uint32_t rr = run > 138 ? 138 : run; S.sc.tok[t++] = (uint16_t)(18 | ((rr - 11) << 8)); atomicAdd(&S.sc.blfreq[18], 1u); run -= rr; }
+                if (run >= 3) { S.sc.tok[t++] = (uint16_t)(17 | ((run - 3) << 8)); atomicAdd(&S.sc.blfreq[17], 1u); run = 0; }
+                if (run) { atomicAdd(&S.sc.blfreq[0], run); while (run-- > 0) S.sc.tok[t++] = 0; }
+            } else {
+                S.sc.tok[t++] = (uint16_t)val; run--;
+                uint32_t lits = 1;
+                while (run >= 3) { uint32_t rr = run > 6 ? 6 : run; S.sc.tok[t++] = (uint16_t)(16 | ((rr - 3) << 8)); atomicAdd(&S.sc.blfreq[16], 1u); run -= rr; }
+                lits += run;
+                while (run-- > 0) S.sc.tok[t++] = (uint16_t)val;
+                atomicAdd(&S.sc.blfreq[val], lits);
+            }
+        }
+        (void)run_tok;
+    }
+    __syncthreads();
+    /* ---- code-length tree (19 symbols) on one thread, header size on all, decision ---- */
     if (tid == 0) {
-        uint64_t dyn = 0, fix = 0;
-        for (int w = 0; w < ZB_WARPS; w++) { dyn += S.red[0][w]; fix += S.red[1][w]; }
-        zh_decide(S.max_l, S.max_d, dyn, fix, in_end - in_start, P.force_type, &S.sc, &S.D);
+        const int bl_order[ZH_BLCODES] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+        (void)zh_lengths(S.sc.blfreq, ZH_BLCODES, 7, S.sc.bllen, &S.sc);
+        int nbl = ZH_BLCODES;
+        while (nbl > 4 && S.sc.bllen[bl_order[nbl - 1]] == 0) nbl--;
+        S.D.nbl = nbl; S.D.nl = nl; S.D.nd = nd;
         zh_codes(S.sc.bllen, ZH_BLCODES, S.sc.blcode);
+    }
+    __syncthreads();
+    {
+        const int nt_all = S.D.nt;
+        uint32_t hb = 0;
+        for (int t = (int)tid; t < nt_all; t += ZB_THREADS) { uint32_t nb; (void)zh_tok_bits(S.sc.tok[t], S.sc.blcode, &nb); hb += nb; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) hb += __shfl_down_sync(0xFFFFFFFFu, hb, o);
+        __syncthreads();
+        if (lane == 0) S.scan[warp] = hb;
+        __syncthreads();
+        if (tid == 0) {
+            uint64_t dyn = 0, fix = 0;
+            for (int w = 0; w < ZB_WARPS; w++) { dyn += S.red[0][w]; fix += S.red[1][w]; }
+            uint32_t hdr = 3 + 5 + 5 + 4 + 3 * (uint32_t)S.D.nbl;
+            for (int w = 0; w < ZB_WARPS; w++) hdr += S.scan[w];
+            /* same decision rule as zh_decide (reference src/trees.c:902-934) */
+            dyn += hdr; fix += 3;
+            const uint32_t in_len = in_end - in_start;
+            uint64_t opt_lenb = (dyn + 7) >> 3, static_lenb = (fix + 7) >> 3;
+            if (static_lenb <= opt_lenb) opt_lenb = static_lenb;
+            int type;
+            if (P.force_type == ZH_STORED) type = ZH_STORED;
+            else if ((uint64_t)in_len + 4 <= opt_lenb && in_len <= 65535u) type = ZH_STORED;
+            else if (P.force_type == ZH_STATIC) type = ZH_STATIC;
+            else if (static_lenb == opt_lenb || hdr > 32u * ZH_HDR_WORDS - 64u) type = ZH_STATIC;
+            else type = ZH_DYNAMIC;
+            S.D.type = type; S.D.hdr_bits_est = hdr; S.D.dyn = dyn; S.D.fix = fix;
+        }
     }
     for (uint32_t i = tid; i < ZH_HDR_WORDS; i += ZB_THREADS) S.blk.hdr[i] = 0;
     __syncthreads();
-    const int type = S.D.type, nl = S.D.nl, nd = S.D.nd, nbl = S.D.nbl, nt = S.D.nt;
+    const int type = S.D.type, nbl = S.D.nbl, nt = S.D.nt;
     if (type != ZH_STORED) {
         /* ---- final code lengths, their histogram ---- */
         for (uint32_t i = tid; i < ZH_LCODES_PAD; i += ZB_THREADS) {
@@ -172,12 +275,31 @@ zs_block_kernel(const ZsChunk *__restrict__ chunks, const uint32_t *__restrict__
             for (int bits = 1; bits <= 15; bits++) { code = (code + prev) << 1; nx[bits] = code; prev = cn[bits]; }
         }
         __syncthreads();
-        /* ---- canonical codes: next_code[len] + rank among the earlier symbols of the same length ---- */
-        for (uint32_t i = tid; i < ZH_LCODES_PAD; i += ZB_THREADS) {
-            const uint32_t l = S.sc.llen[i];
-            uint32_t rank = 0;
-            for (uint32_t j = 0; j < i; j++) rank += (S.sc.llen[j] == l) ? 1u : 0u;
-            S.blk.lcode[i] = l ? (zh_bitrev(S.next_l[l] + rank, (int)l) | (l << 16)) : 0u;
+        /* ---- canonical codes: next_code[len] + rank among the earlier symbols of the same length.
+                Ranks come from ballots inside each chunk of 32 symbols plus per-length chunk prefixes ---- */
+        uint32_t myrank[3] = {0, 0, 0};
+#pragma unroll
+        for (int q = 0; q < 3; q++) {
+            const uint32_t ch = warp + (uint32_t)q * ZB_WARPS;
+            if (ch < 9) {
+                const uint32_t l = S.sc.llen[ch * 32 + lane];
+                for (uint32_t bits = 1; bits <= 15; bits++) {
+                    const uint32_t mm = __ballot_sync(0xFFFFFFFFu, l == bits);
+                    if (l == bits) myrank[q] = __popc(mm & zs_lanemask_lt());
+                    if (lane == bits) S.ccnt[ch][bits] = __popc(mm);
+                }
+            }
+        }
+        __syncthreads();
+        if (tid >= 1 && tid <= 15) { uint32_t run = 0; for (int ch = 0; ch < 9; ch++) { uint32_t t = S.ccnt[ch][tid]; S.ccnt[ch][tid] = run; run += t; } }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 3; q++) {
+            const uint32_t ch = warp + (uint32_t)q * ZB_WARPS;
+            if (ch < 9) {
+                const uint32_t i = ch * 32 + lane, l = S.sc.llen[i];
+                S.blk.lcode[i] = l ? (zh_bitrev(S.next_l[l] + S.ccnt[ch][l] + myrank[q], (int)l) | (l << 16)) : 0u;
+            }
         }
         if (tid < ZH_DCODES_PAD) {
             const uint32_t l = S.sc.dlen[tid];

@@ -33,6 +33,7 @@
 #define ZL_BLOCK (ZL_GPW * 32)                     /* 128 positions */
 #define ZL_RING 65536u
 #define ZL_RING_MASK 0xFFFFu
+#define ZL_MIRROR 32u                               /* bytes of the ring start repeated after its end */
 #define ZL_LOOKAHEAD 272u                          /* >= 258 + 3, multiple of 16 */
 #define ZL_HASH_BITS 15
 #define ZL_NOHASH 0xFFFFu
@@ -40,7 +41,7 @@
 #define ZL_NONE 0xFFFFu
 
 struct ZlSmem {
-    uint32_t ring32[ZL_RING / 4];
+    uint32_t ring32[ZL_RING / 4 + ZL_MIRROR / 4];   /* + a mirror of the first bytes: multi-word reads never wrap */
     uint16_t head[1 << ZL_HASH_BITS];
     uint16_t t_hash[2][ZL_TILE];      /* double buffered: written by workers, read by the hasher */
     uint16_t t_cand[2][ZL_TILE];      /* double buffered: written by the hasher, read by workers */
@@ -64,7 +65,7 @@ __device__ __forceinline__ void zl_bar_workers() { asm volatile("bar.sync 1, %0;
 __device__ __forceinline__ uint32_t zl_ld32(const uint32_t *ring32, uint32_t q)
 {
     uint32_t i = (q >> 2) & (ZL_RING / 4 - 1);
-    uint32_t w0 = ring32[i], w1 = ring32[(i + 1) & (ZL_RING / 4 - 1)];
+    uint32_t w0 = ring32[i], w1 = ring32[i + 1];
     return __funnelshift_r(w0, w1, (q & 3) * 8);
 }
 __device__ __forceinline__ uint32_t zl_ld8(const uint32_t *ring32, uint32_t q)
@@ -97,7 +98,7 @@ __device__ __forceinline__ uint32_t zl_match16(const uint32_t *ring32, uint32_t 
     const uint32_t sa = (q & 3) * 8, sb = (qb & 3) * 8;
     uint32_t a[5], b[5];
 #pragma unroll
-    for (int k = 0; k < 5; k++) { a[k] = ring32[(ia + k) & (ZL_RING / 4 - 1)]; b[k] = ring32[(ib + k) & (ZL_RING / 4 - 1)]; }
+    for (int k = 0; k < 5; k++) { a[k] = ring32[ia + k]; b[k] = ring32[ib + k]; }
     uint32_t len = 16;
 #pragma unroll
     for (int k = 3; k >= 0; k--) {
@@ -114,8 +115,8 @@ __device__ __forceinline__ uint32_t zl_match_ext(const uint32_t *ring32, uint32_
     while (l < limit) {
         const uint32_t qa = q + l, qb = qa - d;
         const uint32_t ia = (qa >> 2) & (ZL_RING / 4 - 1), ib = (qb >> 2) & (ZL_RING / 4 - 1);
-        const uint32_t a0 = ring32[ia], a1 = ring32[(ia + 1) & (ZL_RING / 4 - 1)], a2 = ring32[(ia + 2) & (ZL_RING / 4 - 1)];
-        const uint32_t b0 = ring32[ib], b1 = ring32[(ib + 1) & (ZL_RING / 4 - 1)], b2 = ring32[(ib + 2) & (ZL_RING / 4 - 1)];
+        const uint32_t a0 = ring32[ia], a1 = ring32[ia + 1], a2 = ring32[ia + 2];
+        const uint32_t b0 = ring32[ib], b1 = ring32[ib + 1], b2 = ring32[ib + 2];
         const uint32_t sa = (qa & 3) * 8, sb = (qb & 3) * 8;
         const uint32_t x0 = __funnelshift_r(a0, a1, sa) ^ __funnelshift_r(b0, b1, sb);
         const uint32_t x1 = __funnelshift_r(a1, a2, sa) ^ __funnelshift_r(b1, b2, sb);
@@ -134,12 +135,23 @@ __device__ __forceinline__ uint32_t zl_load(uint32_t *ring32, const uint8_t *gba
     uint32_t full_end = need & ~15u;
     for (uint32_t q = loaded + wtid * 16; q < full_end; q += ZL_WORKERS * 16) {
         uint4 v = __ldg(reinterpret_cast<const uint4 *>(gbase + q));
-        *reinterpret_cast<uint4 *>(&ring8[q & ZL_RING_MASK]) = v;
+        const uint32_t r = q & ZL_RING_MASK;
+        *reinterpret_cast<uint4 *>(&ring8[r]) = v;
+        if (r < ZL_MIRROR) *reinterpret_cast<uint4 *>(&ring8[ZL_RING + r]) = v;
     }
     uint32_t tail0 = max(loaded, full_end);
-    for (uint32_t q = tail0 + wtid; q < need; q += ZL_WORKERS) ring8[q & ZL_RING_MASK] = __ldg(gbase + q);
+    for (uint32_t q = tail0 + wtid; q < need; q += ZL_WORKERS) {
+        const uint32_t r = q & ZL_RING_MASK;
+        const uint8_t v = __ldg(gbase + q);
+        ring8[r] = v;
+        if (r < ZL_MIRROR) ring8[ZL_RING + r] = v;
+    }
     /* zero a few bytes past the very end so 4-byte compares read defined data */
-    if (need == q_end && wtid < 8) ring8[(q_end + wtid) & ZL_RING_MASK] = 0;
+    if (need == q_end && wtid < 8) {
+        const uint32_t r = (q_end + wtid) & ZL_RING_MASK;
+        ring8[r] = 0;
+        if (r < ZL_MIRROR) ring8[ZL_RING + r] = 0;
+    }
     return (need == q_end) ? need : full_end;
 }
 
@@ -178,10 +190,14 @@ __device__ __forceinline__ void zl_hasher_tile(ZlSmem &S, uint16_t *prevd, const
         if (writer) S.head[hs] = (uint16_t)q;                      /* claim */
         __syncwarp();
         uint32_t w = S.head[hs];                                   /* read back */
-        uint32_t d = same ? 1u : ((q - old) & 0xFFFFu);
-        if (!valid) d = 0;
-        t_cand[i] = (uint16_t)d;
-        if (CHAIN && valid) prevd[q & (ZS_WINDOW - 1)] = (uint16_t)d;
+        if (CHAIN) {
+            uint32_t d = same ? 1u : ((q - old) & 0xFFFFu);
+            if (!valid) d = 0;
+            t_cand[i] = (uint16_t)d;
+            if (valid) prevd[q & (ZS_WINDOW - 1)] = (uint16_t)d;
+        } else {
+            t_cand[i] = (uint16_t)old;                             /* the workers turn it into a distance */
+        }
         /* a higher lane of this group may have won the store race; the lower one re-claims */
         for (;;) {
             uint32_t fwd = (w - q) & 0xFFFFu;
@@ -260,7 +276,11 @@ zs_lz_kernel(const uint8_t *__restrict__ raw, const ZsChunk *__restrict__ chunks
                         const uint32_t q = t0 + i;
                         uint32_t d = 0, limit = 0;
                         if (q >= q_start && q + 3 <= q_end) {
-                            d = (P.mode == 1) ? 1u : (uint32_t)cand[i];
+                            if (P.mode == 1) d = 1u;
+                            else {
+                                const uint32_t h16 = S.t_hash[k & 1][i];
+                                d = (h16 == ZL_NOHASH) ? 0u : ((h16 & ZL_SAMEPREV) ? 1u : ((q - (uint32_t)cand[i]) & 0xFFFFu));
+                            }
                             if (d > min((uint32_t)P.max_dist, q - q_dict)) d = 0;
                             limit = q_end - q;
                         }
