@@ -37,7 +37,7 @@
 #define ZL_LOOKAHEAD 272u                          /* >= 258 + 3, multiple of 16 */
 #define ZL_HASH_BITS 15
 #define ZL_NOHASH 0xFFFFu
-#define ZL_SAMEPREV 0x8000u                      /* t_hash flag: the previous position of the group has the same hash */
+#define ZL_NOTFIRST 0x8000u                      /* t_hash flag: a lower lane of the group has the same hash */
 #define ZL_NONE 0xFFFFu
 
 struct ZlSmem {
@@ -75,7 +75,7 @@ __device__ __forceinline__ uint32_t zl_ld8(const uint32_t *ring32, uint32_t q)
 __device__ __forceinline__ uint32_t zl_hash(uint32_t v)
 {
     uint32_t h = ((v & 0xFFFFFFu) * 2654435761u) >> (32 - ZL_HASH_BITS);
-    return h == 0x7FFFu ? 0x7FFEu : h;          /* 0x7FFF | ZL_SAMEPREV would collide with ZL_NOHASH */
+    return h == 0x7FFFu ? 0x7FFEu : h;          /* 0x7FFF | ZL_NOTFIRST would collide with ZL_NOHASH */
 }
 
 /* length of the common prefix of the strings at q and q - d, at most maxl */
@@ -155,58 +155,69 @@ __device__ __forceinline__ uint32_t zl_load(uint32_t *ring32, const uint8_t *gba
     return (need == q_end) ? need : full_end;
 }
 
-/* workers: 3-byte hashes of one tile, 15 bits + ZL_SAMEPREV (positions i, i + 512, ... : a warp covers one group) */
-__device__ __forceinline__ void zl_hash_tile(const uint32_t *ring32, uint16_t *t_hash, uint32_t t0, uint32_t q_dict, uint32_t q_end, uint32_t wtid)
+/* workers: 3-byte hashes of one tile (positions i, i + 512, ...: a warp covers one group of 32), 15 bits +
+ * ZL_NOTFIRST when a lower lane of the group has the same hash.  Finding those duplicates here, on 16 warps
+ * and off the hasher's serial walk, lets the hasher store without any conflict handling.  The search is a
+ * slot-claiming loop in a 256-entry per-warp scratch: lanes store (rest of hash, lane) at slot hash & 255 and
+ * read back; equal hashes meet in one slot and settle on their lowest lane, lanes that lost the slot to a
+ * different hash go round again.  Exact and independent of which colliding store the hardware keeps. */
+__device__ __forceinline__ void zl_hash_tile(const uint32_t *ring32, uint16_t *t_hash, uint16_t *scratch, uint32_t t0, uint32_t q_dict, uint32_t q_end, uint32_t wtid)
 {
     const uint32_t lane = wtid & 31;
+    uint16_t *sc = scratch + (wtid >> 5) * 256;
     for (uint32_t i = wtid; i < ZL_TILE; i += ZL_WORKERS) {
         uint32_t q = t0 + i, h = ZL_NOHASH;
         if (q >= q_dict && q + 3 <= q_end) h = zl_hash(zl_ld32(ring32, q));
+        const bool valid = (h != ZL_NOHASH);
         const uint32_t hp = __shfl_up_sync(0xFFFFFFFFu, h, 1);
-        if (lane > 0 && hp == h && h != ZL_NOHASH) h |= ZL_SAMEPREV;
-        t_hash[i] = (uint16_t)h;
+        bool notfirst = valid && lane > 0 && hp == h;          /* runs: decided by the neighbour alone */
+        bool un = valid && !notfirst;
+        const uint32_t slot = h & 255u, tag = ((h >> 8) << 5) | lane;
+        while (__any_sync(0xFFFFFFFFu, un)) {
+            if (un) sc[slot] = (uint16_t)tag;
+            __syncwarp();
+            uint32_t r;
+            for (;;) {
+                r = un ? (uint32_t)sc[slot] : tag;
+                const bool higher_won = un && (r >> 5) == (tag >> 5) && (r & 31u) > lane;
+                if (!__any_sync(0xFFFFFFFFu, higher_won)) break;
+                if (higher_won) sc[slot] = (uint16_t)tag;
+                __syncwarp();
+            }
+            if (un && (r >> 5) == (tag >> 5)) { notfirst = (r & 31u) != lane; un = false; }
+            __syncwarp();
+        }
+        t_hash[i] = (uint16_t)(h | ((valid && notfirst) ? ZL_NOTFIRST : 0u));
     }
 }
 
 /* hasher warp: head-table pass over one tile, groups of 32 positions in order.
  * Candidate of a position = 1 if the previous lane has the same hash (runs), else the head-table entry as it
- * stood before the group.  Afterwards the lowest lane of every hash holds the slot (lanes flagged
- * ZL_SAMEPREV never write; among the others the store race is settled by reading back). */
+ * stood before the group; afterwards the lowest lane of every hash holds the slot.  The workers have flagged
+ * every other lane ZL_NOTFIRST, so the stores of a group never collide and the walk is a plain in-order
+ * stream of shared-memory loads and stores with nothing to wait for. */
 template <bool CHAIN>
 __device__ __forceinline__ void zl_hasher_tile(ZlSmem &S, uint16_t *prevd, const uint16_t *t_hash, uint16_t *t_cand, uint32_t t0, uint32_t lane)
 {
-    /* The loop is a chain of shared-memory round trips (claim -> read back); the next group's hash is
-       prefetched and the lookup result is consumed only after the read-back has been issued. */
-    uint32_t h_next = t_hash[lane];
+#pragma unroll 4
     for (uint32_t g = 0; g < ZL_GROUPS; g++) {
         const uint32_t i = g * 32 + lane, q = t0 + i;
-        const uint32_t h16 = h_next;
-        if (g + 1 < ZL_GROUPS) h_next = t_hash[i + 32];
+        const uint32_t h16 = t_hash[i];
         const bool valid = (h16 != ZL_NOHASH);
-        const bool same = valid && (h16 & ZL_SAMEPREV);
-        const bool writer = valid && !same;
         const uint32_t hs = valid ? (h16 & 0x7FFFu) : 0;
-        const uint32_t old = S.head[hs];                           /* lookup: table as it stood before the group */
-        if (writer) S.head[hs] = (uint16_t)q;                      /* claim */
-        __syncwarp();
-        uint32_t w = S.head[hs];                                   /* read back */
+        const uint32_t old = S.head[hs];                                    /* table as it stood before the group */
+        if (valid && !(h16 & ZL_NOTFIRST)) S.head[hs] = (uint16_t)q;        /* the first lane of each hash claims it */
         if (CHAIN) {
+            const uint32_t hp = __shfl_up_sync(0xFFFFFFFFu, h16, 1);
+            const bool same = valid && lane > 0 && hp != ZL_NOHASH && ((hp ^ h16) & 0x7FFFu) == 0;
             uint32_t d = same ? 1u : ((q - old) & 0xFFFFu);
             if (!valid) d = 0;
             t_cand[i] = (uint16_t)d;
             if (valid) prevd[q & (ZS_WINDOW - 1)] = (uint16_t)d;
         } else {
-            t_cand[i] = (uint16_t)old;                             /* the workers turn it into a distance */
+            t_cand[i] = (uint16_t)old;                                      /* the workers turn it into a distance */
         }
-        /* a higher lane of this group may have won the store race; the lower one re-claims */
-        for (;;) {
-            uint32_t fwd = (w - q) & 0xFFFFu;
-            bool lose = writer && fwd != 0 && fwd < 32;
-            if (!__any_sync(0xFFFFFFFFu, lose)) break;
-            if (lose) S.head[hs] = (uint16_t)q;
-            __syncwarp();
-            w = S.head[hs];
-        }
+        __syncwarp();
     }
 }
 
@@ -245,8 +256,8 @@ zs_lz_kernel(const uint8_t *__restrict__ raw, const ZsChunk *__restrict__ chunks
     if (!is_hasher) loaded = zl_load(S.ring32, gbase, loaded, min(q_end, t_first + 2 * ZL_TILE + ZL_LOOKAHEAD), q_end, wtid);
     __syncthreads();
     if (!is_hasher && hashing) {
-        zl_hash_tile(S.ring32, S.t_hash[0], t_first, q_dict, q_end, wtid);
-        if (ntiles > 1) zl_hash_tile(S.ring32, S.t_hash[1], t_first + ZL_TILE, q_dict, q_end, wtid);
+        zl_hash_tile(S.ring32, S.t_hash[0], S.t_exit, t_first, q_dict, q_end, wtid);
+        if (ntiles > 1) zl_hash_tile(S.ring32, S.t_hash[1], S.t_exit, t_first + ZL_TILE, q_dict, q_end, wtid);
     }
     __syncthreads();
     if (is_hasher && hashing && ntiles > 0) zl_hasher_tile<CHAIN>(S, prevd, S.t_hash[0], S.t_cand[0], t_first, lane);
@@ -275,11 +286,14 @@ zs_lz_kernel(const uint8_t *__restrict__ raw, const ZsChunk *__restrict__ chunks
                     for (uint32_t i = wtid; i < ZL_TILE; i += ZL_WORKERS) {
                         const uint32_t q = t0 + i;
                         uint32_t d = 0, limit = 0;
+                        const uint32_t h16 = hashing ? (uint32_t)S.t_hash[k & 1][i] : ZL_NOHASH;
+                        const uint32_t hp16 = __shfl_up_sync(0xFFFFFFFFu, h16, 1);
                         if (q >= q_start && q + 3 <= q_end) {
                             if (P.mode == 1) d = 1u;
                             else {
-                                const uint32_t h16 = S.t_hash[k & 1][i];
-                                d = (h16 == ZL_NOHASH) ? 0u : ((h16 & ZL_SAMEPREV) ? 1u : ((q - (uint32_t)cand[i]) & 0xFFFFu));
+                                /* same hash as the previous lane: a run, candidate distance 1; else the table entry */
+                                const bool same = lane > 0 && hp16 != ZL_NOHASH && ((hp16 ^ h16) & 0x7FFFu) == 0;
+                                d = (h16 == ZL_NOHASH) ? 0u : (same ? 1u : ((q - (uint32_t)cand[i]) & 0xFFFFu));
                             }
                             if (d > min((uint32_t)P.max_dist, q - q_dict)) d = 0;
                             limit = q_end - q;
@@ -434,7 +448,7 @@ zs_lz_kernel(const uint8_t *__restrict__ raw, const ZsChunk *__restrict__ chunks
                 zl_bar_workers();       /* ring bytes staged above must be visible before hashing them */
             }
             /* ---- B: hashes of tile k+2 (its bytes were staged in A; every path above passed a worker barrier) ---- */
-            if (hashing && k + 2 < ntiles) zl_hash_tile(S.ring32, S.t_hash[k & 1], t0 + 2 * ZL_TILE, q_dict, q_end, wtid);
+            if (hashing && k + 2 < ntiles) zl_hash_tile(S.ring32, S.t_hash[k & 1], S.t_exit, t0 + 2 * ZL_TILE, q_dict, q_end, wtid);
         }
         __syncthreads();
     }
