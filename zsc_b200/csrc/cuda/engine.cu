@@ -20,7 +20,7 @@ extern "C" cudaError_t zs_adler_flat_launch(cudaStream_t, const uint8_t *, uint6
 extern "C" cudaError_t zs_crc_init_launch(cudaStream_t);
 extern "C" cudaError_t zs_crc_flat_launch(cudaStream_t, const uint8_t *, uint64_t, uint32_t, uint32_t *, int);
 extern "C" cudaError_t zs_inflate_launch(cudaStream_t, uint32_t, const ZsStream *, const uint8_t *, uint8_t *, int32_t,
-                                         int32_t *, uint32_t *, uint32_t *, uint32_t *, uint32_t *, ZsAdlerAcc *, uint32_t);
+                                         int32_t *, uint32_t *, uint32_t *, uint32_t *, uint32_t *, ZsAdlerAcc *, uint32_t, void *, unsigned long long);
 
 #define ZS_NEVENTS 16
 
@@ -41,6 +41,7 @@ struct zscgpu_engine {
     ZsAdlerAcc *d_adler;              /* per stream; slot max_streams is the flat-checksum slot */
     uint32_t *d_crc;                  /* [2] */
     uint32_t *d_aux;                  /* inflate: [2 * max_streams] trailer check + flags */
+    uint8_t *d_icold;                 /* inflate: 640 B per stream, canonical-code arrays of the rare long codes */
     uint32_t last_max_raw;
     int32_t *d_ret, *h_ret;
     uint32_t *d_produced, *h_produced, *d_consumed, *h_consumed, *d_check, *h_check;
@@ -131,6 +132,7 @@ extern "C" int zscgpu_init(const zscgpu_config *cfg_in, zscgpu_engine **out)
     ZS_CUDA_CHECK(zs_dev(&e->d_adler, cfg.max_streams + 1));
     ZS_CUDA_CHECK(zs_dev(&e->d_crc, 4));
     ZS_CUDA_CHECK(zs_dev(&e->d_aux, 2ull * cfg.max_streams));
+    ZS_CUDA_CHECK(zs_dev(&e->d_icold, (640ull + 1280ull) * cfg.max_streams + 4096));   /* cold arrays, then decode tables */
     ZS_CUDA_CHECK(zs_dev(&e->d_ret, cfg.max_streams));
     ZS_CUDA_CHECK(zs_dev(&e->d_produced, cfg.max_streams));
     ZS_CUDA_CHECK(zs_dev(&e->d_consumed, cfg.max_streams));
@@ -155,7 +157,7 @@ extern "C" void zscgpu_destroy(zscgpu_engine *e)
     cudaFreeHost(e->h_streams); cudaFree(e->d_streams);
     cudaFreeHost(e->h_blk_chunk); cudaFree(e->d_blk_chunk);
     cudaFree(e->d_chunk_nsym); cudaFree(e->d_blk_in_start); cudaFree(e->d_blocks);
-    cudaFree(e->d_adler); cudaFree(e->d_crc); cudaFree(e->d_aux);
+    cudaFree(e->d_adler); cudaFree(e->d_crc); cudaFree(e->d_aux); cudaFree(e->d_icold);
     cudaFree(e->d_ret); cudaFree(e->d_produced); cudaFree(e->d_consumed); cudaFree(e->d_check);
     cudaFreeHost(e->h_ret); cudaFreeHost(e->h_produced); cudaFreeHost(e->h_consumed); cudaFreeHost(e->h_check);
     for (int i = 0; i < ZS_NEVENTS; i++) cudaEventDestroy(e->ev[i]);
@@ -379,7 +381,7 @@ static int zs_inflate_launch_all(zscgpu_engine *e)
 {
     const uint32_t n = e->last_nstreams;
     ZS_CUDA_CHECK(zs_inflate_launch(e->stream, n, e->d_streams, e->d_comp, e->d_raw, e->last_wrap, e->d_ret, e->d_produced, e->d_consumed, e->d_check,
-                                    e->d_aux, e->d_adler, e->last_max_raw));
+                                    e->d_aux, e->d_adler, e->last_max_raw, e->d_icold, 640ull * e->cfg.max_streams));
     ZS_CUDA_CHECK(cudaMemcpyAsync(e->h_ret, e->d_ret, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, e->stream));
     ZS_CUDA_CHECK(cudaMemcpyAsync(e->h_produced, e->d_produced, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, e->stream));
     ZS_CUDA_CHECK(cudaMemcpyAsync(e->h_consumed, e->d_consumed, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, e->stream));

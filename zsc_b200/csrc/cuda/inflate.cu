@@ -16,15 +16,21 @@ __global__ void __launch_bounds__(ZI_THREADS)
 zs_inflate_kernel(uint32_t n, const ZsStream *__restrict__ streams, const uint8_t *__restrict__ comp,
                   uint8_t *__restrict__ raw, int32_t wrap, int32_t *__restrict__ ret,
                   uint32_t *__restrict__ produced, uint32_t *__restrict__ consumed,
-                  uint32_t *__restrict__ aux /* [2n]: stored check, flags */)
+                  uint32_t *__restrict__ aux /* [2n]: stored check, flags */, zi_aux *__restrict__ cold, zi_tables *__restrict__ tabs)
 {
+    const uint32_t s = blockIdx.x * ZI_THREADS + threadIdx.x;
+#ifdef ZI_TABLES_IN_SMEM
     extern __shared__ __align__(16) unsigned char zi_smem_raw[];
     zi_tables *T = reinterpret_cast<zi_tables *>(zi_smem_raw) + threadIdx.x;
-    const uint32_t s = blockIdx.x * ZI_THREADS + threadIdx.x;
+#else
+    /* decode tables live in global memory (they stay L2 / L1 resident): without a shared-memory footprint the
+       SM holds ~20 warps = 640 streams, and it is that parallelism, not table latency, that sets throughput */
+    zi_tables *T = tabs + (s < n ? s : 0);
+#endif
     zi_mach m;
     if (s < n) {
         const ZsStream st = streams[s];
-        zi_m_init(&m, comp + st.comp_off, st.comp_cap, raw + st.raw_off, st.raw_len, wrap, T);
+        zi_m_init(&m, comp + st.comp_off, st.comp_cap, raw + st.raw_off, st.raw_len, wrap, T, cold + s);
     } else {
         m.state = ZM_DONE;
     }
@@ -59,12 +65,16 @@ extern "C" cudaError_t zs_adler_streams_launch(cudaStream_t st, uint32_t n, uint
 extern "C" cudaError_t zs_inflate_launch(cudaStream_t st, uint32_t n, const ZsStream *streams, const uint8_t *comp,
                                          uint8_t *raw, int32_t wrap, int32_t *ret, uint32_t *produced,
                                          uint32_t *consumed, uint32_t *check, uint32_t *aux, ZsAdlerAcc *acc,
-                                         uint32_t max_raw_len)
+                                         uint32_t max_raw_len, void *cold, unsigned long long tabs_off)
 {
     if (n == 0) return cudaSuccess;
+#ifdef ZI_TABLES_IN_SMEM
     const size_t smem = sizeof(zi_tables) * ZI_THREADS;
     cudaFuncSetAttribute(zs_inflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    zs_inflate_kernel<<<(n + ZI_THREADS - 1) / ZI_THREADS, ZI_THREADS, smem, st>>>(n, streams, comp, raw, wrap, ret, produced, consumed, aux);
+#else
+    const size_t smem = 0;
+#endif
+    zs_inflate_kernel<<<(n + ZI_THREADS - 1) / ZI_THREADS, ZI_THREADS, smem, st>>>(n, streams, comp, raw, wrap, ret, produced, consumed, aux, reinterpret_cast<zi_aux *>(cold), reinterpret_cast<zi_tables *>(reinterpret_cast<uint8_t *>(cold) + (size_t)tabs_off));
     cudaMemsetAsync(acc, 0, sizeof(ZsAdlerAcc) * n, st);
     cudaError_t ce = zs_adler_streams_launch(st, n, max_raw_len, raw, streams, produced, acc);
     if (ce != cudaSuccess) return ce;

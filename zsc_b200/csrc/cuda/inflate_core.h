@@ -46,14 +46,18 @@ enum {
     ZI_E_INPUT_END, ZI_E_OUTPUT_FULL, ZI_E_NEED_DICT
 };
 
-typedef struct {
+typedef struct {                     /* hot: shared memory on the GPU, 1216 bytes per stream */
     uint16_t lit[1 << ZI_LBITS];     /* sym | len << 9 ; 0 = code longer than ZI_LBITS */
     uint16_t dist[1 << ZI_DBITS];    /* sym | len << 5 ; 0 = longer */
-    uint16_t lsorted[288];
-    uint16_t dsorted[32];
     uint16_t lcount[16];
     uint16_t dcount[16];
 } zi_tables;
+
+typedef struct {                     /* cold: only the rare codes longer than the direct tables read these
+                                        (global memory on the GPU) */
+    uint16_t lsorted[288];
+    uint16_t dsorted[32];
+} zi_aux;
 
 typedef struct {
     const uint8_t *in;      /* stream start */
@@ -64,6 +68,8 @@ typedef struct {
     uint8_t *out;
     uint32_t out_cap;
     uint32_t op;
+    uint32_t pre;           /* device: the input word at [ip, ip + 4), loaded one refill ahead */
+    uint32_t pv;            /* pre is valid */
 } zi_io;
 
 typedef struct {
@@ -83,11 +89,19 @@ ZID void zi_refill(zi_io *io)
     /* 4-byte aligned loads once the cursor is aligned; the arenas are padded, and bits past in_len
        are never consumed (zi_overrun is checked before anything derived from them is used) */
     if (io->bits <= 32) {
-        const uint8_t *p = io->in + io->ip;
-        while ((((uintptr_t)p) & 3) != 0 && io->bits <= 56) { io->hold |= (uint64_t)(*p++) << io->bits; io->bits += 8; io->ip++; }
-        if (io->bits <= 32) {
-            io->hold |= (uint64_t)__ldg(reinterpret_cast<const uint32_t *>(p)) << io->bits;
+        if (io->pv) {
+            /* the word was requested one refill ago; ask for the next one now */
+            io->hold |= (uint64_t)io->pre << io->bits;
             io->bits += 32; io->ip += 4;
+            io->pre = __ldg(reinterpret_cast<const uint32_t *>(io->in + io->ip));
+        } else {
+            const uint8_t *p = io->in + io->ip;
+            while ((((uintptr_t)p) & 3) != 0 && io->bits <= 56) { io->hold |= (uint64_t)(*p++) << io->bits; io->bits += 8; io->ip++; }
+            if (io->bits <= 32) {
+                io->hold |= (uint64_t)__ldg(reinterpret_cast<const uint32_t *>(p)) << io->bits;
+                io->bits += 32; io->ip += 4; p += 4;
+            }
+            if ((((uintptr_t)p) & 3) == 0) { io->pre = __ldg(reinterpret_cast<const uint32_t *>(p)); io->pv = 1; }
         }
     }
 #else
@@ -103,6 +117,8 @@ ZID uint32_t zi_peek(const zi_io *io, int n) { return (uint32_t)io->hold & ((1u 
 ZID void zi_drop(zi_io *io, int n) { io->hold >>= n; io->bits -= (uint32_t)n; }
 ZID uint32_t zi_take(zi_io *io, int n) { uint32_t v = zi_peek(io, n); zi_drop(io, n); return v; }
 ZID uint32_t zi_take32(zi_io *io) { uint32_t v = (uint32_t)io->hold; zi_drop(io, 32); return v; }
+/* move the cursor to byte `pos`, discarding buffered bits */
+ZID void zi_seek(zi_io *io, uint32_t pos) { io->hold = 0; io->bits = 0; io->ip = pos; io->pv = 0; }
 ZID uint32_t zi_consumed_bytes(const zi_io *io) { return (uint32_t)(((uint64_t)io->ip * 8 - io->bits + 7) >> 3); }
 
 /* n bytes from a region that does not overlap the destination (stored blocks): eight loads in flight */
@@ -212,7 +228,7 @@ ZID int zi_fail(zi_result *r, int ret, int reason)
 
 /* Block header: BFINAL / BTYPE, then either the stored-block length (cursor left on the first payload
  * byte) or the decode tables of a fixed / dynamic block.  Returns ZI_OK or the failure code. */
-ZID int zi_block_head(zi_io *io, zi_tables *T, zi_result *res, uint32_t *last_out, uint32_t *type_out, uint32_t *stored_len)
+ZID int zi_block_head(zi_io *io, zi_tables *T, zi_aux *X, zi_result *res, uint32_t *last_out, uint32_t *type_out, uint32_t *stored_len)
 {
     const uint8_t order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
     zi_refill(io);
@@ -228,8 +244,7 @@ ZID int zi_block_head(zi_io *io, zi_tables *T, zi_result *res, uint32_t *last_ou
         uint32_t len = v & 0xFFFF;
         if (len != ((v >> 16) ^ 0xFFFF)) return zi_fail(res, ZI_DATA_ERROR, ZI_E_STORED_LEN);
         /* rewind the bit buffer to a byte cursor */
-        uint32_t pos = io->ip - (io->bits >> 3);
-        io->hold = 0; io->bits = 0; io->ip = pos;
+        zi_seek(io, io->ip - (io->bits >> 3));
         *stored_len = len;
         return ZI_OK;
     }
@@ -239,20 +254,20 @@ ZID int zi_block_head(zi_io *io, zi_tables *T, zi_result *res, uint32_t *last_ou
                    used, src/inflate.c:122-206), literal/length lengths 8/9/7/8 in closed form */
                 uint8_t tmp[32];
                 for (int i = 0; i < 32; i++) tmp[i] = 5;
-                (void)zi_build(tmp, 32, ZI_DBITS, T->dist, T->dsorted, T->dcount, 5, 1);
+                (void)zi_build(tmp, 32, ZI_DBITS, T->dist, X->dsorted, T->dcount, 5, 1);
                 for (int i = 0; i < 16; i++) T->lcount[i] = 0;
                 T->lcount[7] = 24; T->lcount[8] = 152; T->lcount[9] = 112;
                 int k = 0;
-                for (int i = 256; i < 280; i++) T->lsorted[k++] = (uint16_t)i;
-                for (int i = 0; i < 144; i++) T->lsorted[k++] = (uint16_t)i;
-                for (int i = 280; i < 288; i++) T->lsorted[k++] = (uint16_t)i;
-                for (int i = 144; i < 256; i++) T->lsorted[k++] = (uint16_t)i;
+                for (int i = 256; i < 280; i++) X->lsorted[k++] = (uint16_t)i;
+                for (int i = 0; i < 144; i++) X->lsorted[k++] = (uint16_t)i;
+                for (int i = 280; i < 288; i++) X->lsorted[k++] = (uint16_t)i;
+                for (int i = 144; i < 256; i++) X->lsorted[k++] = (uint16_t)i;
                 for (int i = 0; i < (1 << ZI_LBITS); i++) T->lit[i] = 0;
                 uint32_t code = 0; k = 0;
                 for (int l = 7; l <= 9; l++) {
                     for (int c = 0; c < T->lcount[l]; c++, k++, code++) {
                         uint32_t r = zi_rev(code, l);
-                        uint16_t e = (uint16_t)(T->lsorted[k] | (l << 9));
+                        uint16_t e = (uint16_t)(X->lsorted[k] | (l << 9));
                         for (uint32_t j = r; j < (1u << ZI_LBITS); j += (1u << l)) T->lit[j] = e;
                     }
                     code <<= 1;
@@ -266,9 +281,9 @@ ZID int zi_block_head(zi_io *io, zi_tables *T, zi_result *res, uint32_t *last_ou
                 for (int i = 0; i < 19; i++) cl[i] = 0;
                 for (uint32_t i = 0; i < ncode; i++) { zi_refill(io); cl[order[i]] = (uint8_t)zi_take(io, 3); }
                 if (zi_overrun(io)) return zi_fail(res, ZI_BUF_ERROR, ZI_E_INPUT_END);
-                /* code-length code: a 7-bit direct table (128 entries) laid over dist[64] and the first
-                   64 entries of lsorted, both dead until this header has been parsed */
-                uint16_t *cltab = T->dist;
+                /* code-length code: a 7-bit direct table (128 entries) in the upper half of the literal
+                   table, which is dead until this header has been parsed (lens uses its first 320 bytes) */
+                uint16_t *cltab = T->lit + 256;
                 uint16_t clsorted[19], clcount[16];
                 if (zi_build(cl, 19, 7, cltab, clsorted, clcount, 5, 0)) return zi_fail(res, ZI_DATA_ERROR, ZI_E_CODELEN_SET);
                 uint8_t *lens = (uint8_t *)T->lit;
@@ -292,7 +307,7 @@ ZID int zi_block_head(zi_io *io, zi_tables *T, zi_result *res, uint32_t *last_ou
                 }
                 if (lens[256] == 0) return zi_fail(res, ZI_DATA_ERROR, ZI_E_NO_EOB);
                 /* distance tables first (they overwrite the code-length table), from the tail of lens */
-                if (zi_build(lens + nlen, (int)ndist, ZI_DBITS, T->dist, T->dsorted, T->dcount, 5, 1))
+                if (zi_build(lens + nlen, (int)ndist, ZI_DBITS, T->dist, X->dsorted, T->dcount, 5, 1))
                     return zi_fail(res, ZI_DATA_ERROR, ZI_E_DIST_SET);
                 /* literal/length: sorted + counts while lens is alive, then the table over it */
                 {
@@ -306,13 +321,13 @@ ZID int zi_block_head(zi_io *io, zi_tables *T, zi_result *res, uint32_t *last_ou
                     if (left > 0 && maxl != 1) return zi_fail(res, ZI_DATA_ERROR, ZI_E_LITLEN_SET);
                     offs[1] = 0;
                     for (int l = 1; l < 15; l++) offs[l + 1] = (uint16_t)(offs[l] + T->lcount[l]);
-                    for (uint32_t k = 0; k < nlen; k++) if (lens[k]) T->lsorted[offs[lens[k]]++] = (uint16_t)k;
+                    for (uint32_t k = 0; k < nlen; k++) if (lens[k]) X->lsorted[offs[lens[k]]++] = (uint16_t)k;
                     for (int k = 0; k < (1 << ZI_LBITS); k++) T->lit[k] = 0;
                     uint32_t code = 0; int k = 0;
                     for (int l = 1; l <= maxl && l <= ZI_LBITS; l++) {
                         for (int c = 0; c < T->lcount[l]; c++, k++, code++) {
                             uint32_t r = zi_rev(code, l);
-                            uint16_t e = (uint16_t)(T->lsorted[k] | (l << 9));
+                            uint16_t e = (uint16_t)(X->lsorted[k] | (l << 9));
                             for (uint32_t j = r; j < (1u << ZI_LBITS); j += (1u << l)) T->lit[j] = e;
                         }
                         code <<= 1;
@@ -357,21 +372,22 @@ typedef struct {
     zi_io io;
     zi_result res;
     zi_tables *T;
+    zi_aux *X;
     int32_t state, wrap;
     uint32_t last, rem, dist, win, maxw, held;
 } zi_mach;
 
-ZID void zi_m_init(zi_mach *m, const uint8_t *in, uint32_t in_len, uint8_t *out, uint32_t out_cap, int wrap, zi_tables *T)
+ZID void zi_m_init(zi_mach *m, const uint8_t *in, uint32_t in_len, uint8_t *out, uint32_t out_cap, int wrap, zi_tables *T, zi_aux *X)
 {
     m->io.in = in; m->io.in_len = in_len; m->io.ip = 0; m->io.hold = 0; m->io.bits = 0;
-    m->io.out = out; m->io.out_cap = out_cap; m->io.op = 0;
+    m->io.out = out; m->io.out_cap = out_cap; m->io.op = 0; m->io.pre = 0; m->io.pv = 0;
     m->res.ret = ZI_OK; m->res.reason = ZI_E_NONE; m->res.produced = 0; m->res.consumed = 0;
     m->res.data_errors = 0; m->res.stored_check = 0; m->res.have_check = 0; m->res.last_reason = ZI_E_NONE;
     /* wrap: low byte 0 raw / 1 zlib; bits 8..15 = largest window_bits the caller accepts (0 = 15) */
     m->maxw = ((wrap >> 8) & 0xFF) ? (uint32_t)((wrap >> 8) & 0xFF) : 15u;
     m->wrap = wrap & 0xFF;
     m->win = 1u << m->maxw;
-    m->T = T; m->last = 0; m->rem = 0; m->dist = 0; m->held = 0;
+    m->T = T; m->X = X; m->last = 0; m->rem = 0; m->dist = 0; m->held = 0;
     m->state = m->wrap == 1 ? ZM_HEAD : ZM_BLOCK;
 }
 
@@ -399,11 +415,12 @@ ZID void zi_step(zi_mach *m)
     zi_io *io = &m->io;
     zi_result *res = &m->res;
     zi_tables *T = m->T;
+    zi_aux *X = m->X;
     if (m->state == ZM_SYM) {
         /* up to two symbols: most are literals, and two keep the lanes of a warp busy between copies */
         for (int rep = 0; rep < 2 && m->state == ZM_SYM; rep++) {
             zi_refill(io);
-            int s = zi_decode(io, T->lit, ZI_LBITS, T->lsorted, T->lcount, 9);
+            int s = zi_decode(io, T->lit, ZI_LBITS, X->lsorted, T->lcount, 9);
             if (zi_overrun(io)) { zi_m_fail(m, zi_fail(res, ZI_BUF_ERROR, ZI_E_INPUT_END), 0); break; }
             if (s < 0) { zi_m_fail(m, zi_fail(res, ZI_DATA_ERROR, ZI_E_LITLEN_CODE), 0); break; }
             if (s < 256) {
@@ -418,7 +435,7 @@ ZID void zi_step(zi_mach *m)
             else if (c == 28) len = 258;
             else { uint32_t eb = (c - 4) >> 2; len = 3 + ((4 + (c & 3)) << eb) + zi_take(io, (int)eb); }
             zi_refill(io);
-            int d = zi_decode(io, T->dist, ZI_DBITS, T->dsorted, T->dcount, 5);
+            int d = zi_decode(io, T->dist, ZI_DBITS, X->dsorted, T->dcount, 5);
             if (d < 0 || d > 29) {
                 int ov = zi_overrun(io);
                 zi_m_fail(m, zi_fail(res, ov ? ZI_BUF_ERROR : ZI_DATA_ERROR, ov ? ZI_E_INPUT_END : ZI_E_DIST_CODE), 0);
@@ -449,7 +466,7 @@ ZID void zi_step(zi_mach *m)
         if (n > avail) n = avail;
         if (n > room) n = room;
         zi_copy_fwd(io->out + io->op, io->in + pos, n);
-        io->op += n; io->ip = pos + n; m->rem -= n;
+        io->op += n; io->ip = pos + n; io->pv = 0; m->rem -= n;
         if (m->rem == 0) m->state = m->last ? ZM_TRAIL : ZM_BLOCK;
         else if (n == 0) zi_m_fail(m, zi_fail(res, ZI_BUF_ERROR, room == 0 ? ZI_E_OUTPUT_FULL : ZI_E_INPUT_END), 0);
         return;
@@ -469,7 +486,7 @@ ZID void zi_step(zi_mach *m)
     }
     if (m->state == ZM_BLOCK) {
         uint32_t type = 0, slen = 0;
-        int r = zi_block_head(io, T, res, &m->last, &type, &slen);
+        int r = zi_block_head(io, T, X, res, &m->last, &type, &slen);
         if (r != ZI_OK) { zi_m_fail(m, r, (r == ZI_DATA_ERROR && res->last_reason == ZI_E_STORED_LEN) ? 4u : 0u); return; }
         if (type == 0) { m->rem = slen; m->state = slen ? ZM_STORED : (m->last ? ZM_TRAIL : ZM_BLOCK); }
         else m->state = ZM_SYM;
@@ -498,13 +515,12 @@ ZID void zi_step(zi_mach *m)
         res->data_errors++;
         uint32_t pos = io->ip - (io->bits >> 3);
         if (pos > io->in_len) pos = io->in_len;
-        io->hold = 0; io->bits = 0;
         uint32_t held = m->held;
         m->held = 0;
-        if (held == 0 && pos >= io->in_len) { io->ip = io->in_len; zi_m_finish(m, ZI_BUF_ERROR); return; }
+        if (held == 0 && pos >= io->in_len) { zi_seek(io, io->in_len); zi_m_finish(m, ZI_BUF_ERROR); return; }
         uint32_t nx = zi_sync(io->in, io->in_len, pos - held);
-        if (nx > io->in_len) { io->ip = io->in_len; zi_m_finish(m, ZI_DATA_ERROR); return; }
-        io->ip = nx;
+        if (nx > io->in_len) { zi_seek(io, io->in_len); zi_m_finish(m, ZI_DATA_ERROR); return; }
+        zi_seek(io, nx);
         m->state = ZM_BLOCK;
         return;
     }
@@ -517,7 +533,8 @@ ZID void zi_inflate(const uint8_t *in, uint32_t in_len, uint8_t *out, uint32_t o
                                   int wrap, zi_tables *T, zi_result *res)
 {
     zi_mach m;
-    zi_m_init(&m, in, in_len, out, out_cap, wrap, T);
+    zi_aux X;
+    zi_m_init(&m, in, in_len, out, out_cap, wrap, T, &X);
     while (m.state != ZM_DONE) zi_step(&m);
     *res = m.res;
 }
