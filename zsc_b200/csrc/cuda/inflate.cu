@@ -27,10 +27,13 @@ zs_inflate_kernel(uint32_t n, const ZsStream *__restrict__ streams, const uint8_
        SM holds ~20 warps = 640 streams, and it is that parallelism, not table latency, that sets throughput */
     zi_tables *T = tabs + (s < n ? s : 0);
 #endif
+    /* first-level tables (codes of <= 7 bits, distance table): 384 B per stream in shared memory */
+    __shared__ zi_fast fast[ZI_THREADS];
+    zi_fast *F = &fast[threadIdx.x];
     zi_mach m;
     if (s < n) {
         const ZsStream st = streams[s];
-        zi_m_init(&m, comp + st.comp_off, st.comp_cap, raw + st.raw_off, st.raw_len, wrap, T, cold + s);
+        zi_m_init(&m, comp + st.comp_off, st.comp_cap, raw + st.raw_off, st.raw_len, wrap, T, cold + s, F);
     } else {
         m.state = ZM_DONE;
     }

@@ -53,6 +53,11 @@ typedef struct {                     /* hot: shared memory on the GPU, 1216 byte
     uint16_t dcount[16];
 } zi_tables;
 
+typedef struct {                     /* first-level tables: shared memory on the GPU, 384 bytes per stream */
+    uint16_t lit7[128];              /* literal/length codes of <= 7 bits, indexed by 7 bits; 0 = look further */
+    uint16_t dist6[64];              /* copy of zi_tables.dist */
+} zi_fast;
+
 typedef struct {                     /* cold: only the rare codes longer than the direct tables read these
                                         (global memory on the GPU) */
     uint16_t lsorted[288];
@@ -228,7 +233,7 @@ ZID int zi_fail(zi_result *r, int ret, int reason)
 
 /* Block header: BFINAL / BTYPE, then either the stored-block length (cursor left on the first payload
  * byte) or the decode tables of a fixed / dynamic block.  Returns ZI_OK or the failure code. */
-ZID int zi_block_head(zi_io *io, zi_tables *T, zi_aux *X, zi_result *res, uint32_t *last_out, uint32_t *type_out, uint32_t *stored_len)
+ZID int zi_block_head(zi_io *io, zi_tables *T, zi_aux *X, zi_fast *F, zi_result *res, uint32_t *last_out, uint32_t *type_out, uint32_t *stored_len)
 {
     const uint8_t order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
     zi_refill(io);
@@ -335,6 +340,9 @@ ZID int zi_block_head(zi_io *io, zi_tables *T, zi_aux *X, zi_result *res, uint32
                 }
             }
     }
+    /* first-level copies of the short codes */
+    for (int i = 0; i < 128; i++) { uint16_t e = T->lit[i]; F->lit7[i] = (e && (e >> 9) <= 7) ? e : (uint16_t)0; }
+    for (int i = 0; i < 64; i++) F->dist6[i] = T->dist[i];
     return ZI_OK;
 }
 
@@ -373,11 +381,12 @@ typedef struct {
     zi_result res;
     zi_tables *T;
     zi_aux *X;
+    zi_fast *F;
     int32_t state, wrap;
     uint32_t last, rem, dist, win, maxw, held;
 } zi_mach;
 
-ZID void zi_m_init(zi_mach *m, const uint8_t *in, uint32_t in_len, uint8_t *out, uint32_t out_cap, int wrap, zi_tables *T, zi_aux *X)
+ZID void zi_m_init(zi_mach *m, const uint8_t *in, uint32_t in_len, uint8_t *out, uint32_t out_cap, int wrap, zi_tables *T, zi_aux *X, zi_fast *F)
 {
     m->io.in = in; m->io.in_len = in_len; m->io.ip = 0; m->io.hold = 0; m->io.bits = 0;
     m->io.out = out; m->io.out_cap = out_cap; m->io.op = 0; m->io.pre = 0; m->io.pv = 0;
@@ -387,7 +396,7 @@ ZID void zi_m_init(zi_mach *m, const uint8_t *in, uint32_t in_len, uint8_t *out,
     m->maxw = ((wrap >> 8) & 0xFF) ? (uint32_t)((wrap >> 8) & 0xFF) : 15u;
     m->wrap = wrap & 0xFF;
     m->win = 1u << m->maxw;
-    m->T = T; m->X = X; m->last = 0; m->rem = 0; m->dist = 0; m->held = 0;
+    m->T = T; m->X = X; m->F = F; m->last = 0; m->rem = 0; m->dist = 0; m->held = 0;
     m->state = m->wrap == 1 ? ZM_HEAD : ZM_BLOCK;
 }
 
@@ -416,11 +425,17 @@ ZID void zi_step(zi_mach *m)
     zi_result *res = &m->res;
     zi_tables *T = m->T;
     zi_aux *X = m->X;
+    zi_fast *F = m->F;
     if (m->state == ZM_SYM) {
         /* up to two symbols: most are literals, and two keep the lanes of a warp busy between copies */
         for (int rep = 0; rep < 2 && m->state == ZM_SYM; rep++) {
             zi_refill(io);
-            int s = zi_decode(io, T->lit, ZI_LBITS, X->lsorted, T->lcount, 9);
+            int s;
+            {
+                const uint32_t e7 = F->lit7[zi_peek(io, 7)];
+                if (e7) { zi_drop(io, (int)(e7 >> 9)); s = (int)(e7 & 511u); }
+                else s = zi_decode(io, T->lit, ZI_LBITS, X->lsorted, T->lcount, 9);
+            }
             if (zi_overrun(io)) { zi_m_fail(m, zi_fail(res, ZI_BUF_ERROR, ZI_E_INPUT_END), 0); break; }
             if (s < 0) { zi_m_fail(m, zi_fail(res, ZI_DATA_ERROR, ZI_E_LITLEN_CODE), 0); break; }
             if (s < 256) {
@@ -435,7 +450,12 @@ ZID void zi_step(zi_mach *m)
             else if (c == 28) len = 258;
             else { uint32_t eb = (c - 4) >> 2; len = 3 + ((4 + (c & 3)) << eb) + zi_take(io, (int)eb); }
             zi_refill(io);
-            int d = zi_decode(io, T->dist, ZI_DBITS, X->dsorted, T->dcount, 5);
+            int d;
+            {
+                const uint32_t e6 = F->dist6[zi_peek(io, ZI_DBITS)];
+                if (e6) { zi_drop(io, (int)(e6 >> 5)); d = (int)(e6 & 31u); }
+                else d = zi_decode(io, T->dist, ZI_DBITS, X->dsorted, T->dcount, 5);
+            }
             if (d < 0 || d > 29) {
                 int ov = zi_overrun(io);
                 zi_m_fail(m, zi_fail(res, ov ? ZI_BUF_ERROR : ZI_DATA_ERROR, ov ? ZI_E_INPUT_END : ZI_E_DIST_CODE), 0);
@@ -486,7 +506,7 @@ ZID void zi_step(zi_mach *m)
     }
     if (m->state == ZM_BLOCK) {
         uint32_t type = 0, slen = 0;
-        int r = zi_block_head(io, T, X, res, &m->last, &type, &slen);
+        int r = zi_block_head(io, T, X, F, res, &m->last, &type, &slen);
         if (r != ZI_OK) { zi_m_fail(m, r, (r == ZI_DATA_ERROR && res->last_reason == ZI_E_STORED_LEN) ? 4u : 0u); return; }
         if (type == 0) { m->rem = slen; m->state = slen ? ZM_STORED : (m->last ? ZM_TRAIL : ZM_BLOCK); }
         else m->state = ZM_SYM;
@@ -534,7 +554,8 @@ ZID void zi_inflate(const uint8_t *in, uint32_t in_len, uint8_t *out, uint32_t o
 {
     zi_mach m;
     zi_aux X;
-    zi_m_init(&m, in, in_len, out, out_cap, wrap, T, &X);
+    zi_fast F;
+    zi_m_init(&m, in, in_len, out, out_cap, wrap, T, &X, &F);
     while (m.state != ZM_DONE) zi_step(&m);
     *res = m.res;
 }
