@@ -358,3 +358,27 @@ def test_full_size_round_trip_1GiB_level1():
         assert head == x[:len(head)].tobytes()
     finally:
         E.close()
+
+
+def test_host_call_in_waves_equals_single_shot(checker):
+    """zsc_compress on a large host buffer runs in overlapped waves of sections; the stream must be byte-identical
+    to the single-batch stream, inflate through the checker, and carry the right adler32 / crc32"""
+    n = 160 << 20
+    x = datagen.mixed(n, seed=3)
+    Z = capi.zsc()
+    r, comp = Z.compress(x, 262144, 1)
+    assert r == 0
+    E = Engine(raw_bytes=n + (1 << 20), comp_bytes=n + (n >> 3) + (1 << 20), deflate_batch_max=n + (1 << 20), max_streams=16, max_chunks=4096)
+    try:
+        r1, single = gpu_deflate(E, x, 262144, 1)
+        assert r1.ret == 0 and np.array_equal(single, comp)
+    finally:
+        E.close()
+    assert int.from_bytes(comp[-4:].tobytes(), "big") == zlib.adler32(x.tobytes())
+    d = zlib.decompressobj()
+    assert d.decompress(comp.tobytes(), 8 << 20) == x[:8 << 20].tobytes()
+    r2, back, used = Z.uncompress(comp, n)
+    assert r2 == 0 and used == len(comp) and np.array_equal(back, x)
+    rg, gz = Z.compress(x, 262144, 1, window_bits=31)
+    assert rg == 0 and int.from_bytes(gz[-8:-4].tobytes(), "little") == zlib.crc32(x.tobytes())
+    assert int.from_bytes(gz[-4:].tobytes(), "little") == n

@@ -23,6 +23,7 @@ extern "C" cudaError_t zs_inflate_launch(cudaStream_t, uint32_t, const ZsStream 
                                          int32_t *, uint32_t *, uint32_t *, uint32_t *, uint32_t *, ZsAdlerAcc *, uint32_t, void *, unsigned long long);
 
 #define ZS_NEVENTS 16
+#define ZS_MAX_WAVES 64
 
 struct zscgpu_engine {
     zscgpu_config cfg;
@@ -46,6 +47,8 @@ struct zscgpu_engine {
     int32_t *d_ret, *h_ret;
     uint32_t *d_produced, *h_produced, *d_consumed, *h_consumed, *d_check, *h_check;
     cudaEvent_t ev[ZS_NEVENTS];
+    cudaStream_t copy_stream, d2h_stream;   /* host-buffer calls: uploads / downloads overlap the kernels */
+    cudaEvent_t ev_wave[ZS_MAX_WAVES];
     /* last enqueue, for zscgpu_relaunch */
     int last_kind;                    /* 0 none, 1 deflate, 2 inflate */
     uint32_t last_nstreams, last_nchunks, last_nblk;
@@ -82,7 +85,7 @@ extern "C" void zscgpu_default_config(zscgpu_config *cfg)
     cfg->max_chunks = 1u << 18;
 }
 
-template <typename T> static cudaError_t zs_pinned(T **p, size_t n) { return cudaHostAlloc((void **)p, n * sizeof(T), cudaHostAllocDefault); }
+template <typename T> static cudaError_t zs_pinned(T **p, size_t n) { return cudaHostAlloc((void **)p, n * sizeof(T), cudaHostAllocMapped); }
 template <typename T> static cudaError_t zs_dev(T **p, size_t n) { return cudaMalloc((void **)p, n * sizeof(T)); }
 
 extern "C" int zscgpu_init(const zscgpu_config *cfg_in, zscgpu_engine **out)
@@ -142,6 +145,9 @@ extern "C" int zscgpu_init(const zscgpu_config *cfg_in, zscgpu_engine **out)
     ZS_CUDA_CHECK(zs_pinned(&e->h_consumed, cfg.max_streams));
     ZS_CUDA_CHECK(zs_pinned(&e->h_check, cfg.max_streams + 4));
     for (int i = 0; i < ZS_NEVENTS; i++) ZS_CUDA_CHECK(cudaEventCreate(&e->ev[i]));
+    ZS_CUDA_CHECK(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+    ZS_CUDA_CHECK(cudaStreamCreateWithFlags(&e->d2h_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < ZS_MAX_WAVES; i++) ZS_CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_wave[i], cudaEventDisableTiming));
     ZS_CUDA_CHECK(zs_crc_init_launch(e->stream));
     ZS_CUDA_CHECK(cudaStreamSynchronize(e->stream));
     *out = e;
@@ -161,6 +167,8 @@ extern "C" void zscgpu_destroy(zscgpu_engine *e)
     cudaFree(e->d_ret); cudaFree(e->d_produced); cudaFree(e->d_consumed); cudaFree(e->d_check);
     cudaFreeHost(e->h_ret); cudaFreeHost(e->h_produced); cudaFreeHost(e->h_consumed); cudaFreeHost(e->h_check);
     for (int i = 0; i < ZS_NEVENTS; i++) cudaEventDestroy(e->ev[i]);
+    for (int i = 0; i < ZS_MAX_WAVES; i++) cudaEventDestroy(e->ev_wave[i]);
+    cudaStreamDestroy(e->copy_stream); cudaStreamDestroy(e->d2h_stream);
     cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -340,6 +348,34 @@ static int zs_build_deflate_desc(zscgpu_engine *e, const zscgpu_stream *streams,
     return ZSCGPU_OK;
 }
 
+/* Descriptors travel to the device through a small kernel that reads the pinned host arrays directly: a
+ * cudaMemcpyAsync would share the host-to-device copy engine with the bulk upload of the next wave of a
+ * host-buffer call and wait behind it (measured: the kernels of wave w started when upload w+1 ended). */
+struct ZsDescFetch { const uint32_t *src[3]; uint32_t *dst[3]; uint32_t words[3]; };
+__global__ void __launch_bounds__(256) zs_desc_fetch_kernel(ZsDescFetch d)
+{
+    for (int k = 0; k < 3; k++)
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < d.words[k]; i += gridDim.x * blockDim.x)
+            d.dst[k][i] = d.src[k][i];
+}
+static cudaError_t zs_desc_fetch(zscgpu_engine *e, uint32_t n, uint32_t nc, uint32_t nb)
+{
+    ZsDescFetch d;
+    d.src[0] = (const uint32_t *)e->h_chunks;    d.dst[0] = (uint32_t *)e->d_chunks;    d.words[0] = (uint32_t)(sizeof(ZsChunk) / 4 * nc);
+    d.src[1] = (const uint32_t *)e->h_streams;   d.dst[1] = (uint32_t *)e->d_streams;   d.words[1] = (uint32_t)(sizeof(ZsStream) / 4 * n);
+    d.src[2] = (const uint32_t *)e->h_blk_chunk; d.dst[2] = (uint32_t *)e->d_blk_chunk; d.words[2] = nb;
+    for (int k = 0; k < 3; k++) {
+        void *dp = nullptr;
+        cudaError_t ce = cudaHostGetDevicePointer(&dp, (void *)d.src[k], 0);
+        if (ce != cudaSuccess) return ce;
+        d.src[k] = (const uint32_t *)dp;
+    }
+    uint32_t total = d.words[0] + d.words[1] + d.words[2];
+    uint32_t grid = (total + 255) / 256; if (grid > 148) grid = 148; if (grid == 0) grid = 1;
+    zs_desc_fetch_kernel<<<grid, 256, 0, e->stream>>>(d);
+    return cudaGetLastError();
+}
+
 static int zs_deflate_launch_all(zscgpu_engine *e)
 {
     const uint32_t n = e->last_nstreams, nc = e->last_nchunks, nb = e->last_nblk;
@@ -370,9 +406,8 @@ extern "C" int zscgpu_deflate_enqueue(zscgpu_engine *e, const zscgpu_stream *str
     uint32_t nc = 0, nb = 0;
     int r = zs_build_deflate_desc(e, streams, n, p->max_block_len, p->part, &nc, &nb);
     if (r) return r;
-    ZS_CUDA_CHECK(cudaMemcpyAsync(e->d_chunks, e->h_chunks, sizeof(ZsChunk) * nc, cudaMemcpyHostToDevice, e->stream));
-    ZS_CUDA_CHECK(cudaMemcpyAsync(e->d_streams, e->h_streams, sizeof(ZsStream) * n, cudaMemcpyHostToDevice, e->stream));
-    ZS_CUDA_CHECK(cudaMemcpyAsync(e->d_blk_chunk, e->h_blk_chunk, sizeof(uint32_t) * nb, cudaMemcpyHostToDevice, e->stream));
+    static_assert(sizeof(ZsChunk) % 4 == 0 && sizeof(ZsStream) % 4 == 0, "descriptor structs are copied as words");
+    ZS_CUDA_CHECK(zs_desc_fetch(e, n, nc, nb));
     e->last_kind = 1; e->last_nstreams = n; e->last_nchunks = nc; e->last_nblk = nb; e->last_chain = chain; e->last_lz = L;
     return zs_deflate_launch_all(e);
 }
@@ -407,7 +442,7 @@ extern "C" int zscgpu_inflate_enqueue(zscgpu_engine *e, const zscgpu_stream *str
         S->raw_off = z->raw_off; S->comp_off = z->comp_off; S->raw_len = z->raw_len; S->comp_cap = z->comp_len;
         if (z->raw_len > max_raw) max_raw = z->raw_len;
     }
-    ZS_CUDA_CHECK(cudaMemcpyAsync(e->d_streams, e->h_streams, sizeof(ZsStream) * n, cudaMemcpyHostToDevice, e->stream));
+    ZS_CUDA_CHECK(zs_desc_fetch(e, n, 0, 0));
     e->last_max_raw = max_raw;
     e->last_kind = 2; e->last_nstreams = n; e->last_wrap = wrap;
     return zs_inflate_launch_all(e);
@@ -454,6 +489,72 @@ extern "C" int zscgpu_inflate_batch(zscgpu_engine *e, const zscgpu_stream *strea
  * serialises whole calls because they all use offset 0 of the arenas. */
 static std::mutex g_call_mu;
 
+/* Large host buffers are processed in waves of whole sections: the upload of wave w+1 (copy engine), the
+ * kernels of wave w and the download of wave w-1 (second copy engine) overlap.  Every wave is deflated as a
+ * raw part (zscgpu_deflate_params.part); the parts concatenate byte-wise, the host writes the 2-byte zlib
+ * header and folds the per-part adler32 / crc32 into the trailer value. */
+static int zs_compress_host_waves(zscgpu_engine *e, uint8_t *dest, uint32_t dest_cap, const uint8_t *src, uint32_t src_len,
+                                  const zscgpu_deflate_params *p, uint32_t comp_skip, zscgpu_result *res, uint64_t W, uint32_t nw)
+{
+    ZsLzParams L; int chain;
+    if (zs_lz_params(p, &L, &chain)) { snprintf(e->err, sizeof(e->err), "bad level/strategy/wrap"); return ZSCGPU_ERR_ARG; }
+    auto room = [](uint64_t len) -> uint64_t { return (len + (len >> 3) + 4096 + 63) & ~63ull; };   /* comp arena room of a wave */
+    uint64_t comp_off = 0;
+    /* uploads run one wave ahead of the kernels on their own stream */
+    auto upload = [&](uint32_t w) -> cudaError_t {
+        const uint64_t off = (uint64_t)w * W, len = (src_len - off < W) ? src_len - off : W;
+        cudaError_t ce = cudaMemcpyAsync(e->d_raw + off, src + off, len, cudaMemcpyHostToDevice, e->copy_stream);
+        if (ce != cudaSuccess) return ce;
+        return cudaEventRecord(e->ev_wave[w], e->copy_stream);
+    };
+    ZS_CUDA_CHECK(upload(0));
+    zscgpu_deflate_params pp = *p;
+    pp.wrap = 0;
+    uint64_t out_pos = comp_skip + (p->wrap == 1 ? 2u : 0u);
+    uint32_t check = (p->wrap == 2) ? 0u : 1u;
+    res->ret = 0; res->produced = 0; res->consumed = src_len; res->check = 0;
+    int rc = ZSCGPU_OK;
+    for (uint32_t w = 0; w < nw && rc == ZSCGPU_OK; w++) {
+        const uint64_t off = (uint64_t)w * W, len = (src_len - off < W) ? src_len - off : W;
+        ZS_CUDA_CHECK(cudaStreamWaitEvent(e->stream, e->ev_wave[w], 0));
+        zscgpu_stream st;
+        st.raw_off = off; st.raw_len = (uint32_t)len; st.comp_off = comp_off; st.comp_len = (uint32_t)room(len);
+        comp_off += room(len);
+        pp.part = (w > 0 ? 1 : 0) | (w + 1 < nw ? 2 : 0);
+        zscgpu_result r1;
+        rc = zscgpu_deflate_enqueue(e, &st, 1, &pp); if (rc) break;
+        if (w + 1 < nw) ZS_CUDA_CHECK(upload(w + 1));
+        uint32_t crc_part = 0;
+        if (p->wrap == 2) {
+            rc = zscgpu_crc32_enqueue(e, off, len); if (rc) break;
+            uint32_t h[2];
+            ZS_CUDA_CHECK(cudaMemcpyAsync(h, e->d_crc, 8, cudaMemcpyDeviceToHost, e->stream));
+            rc = zscgpu_fetch_results(e, 1, &r1); if (rc) break;
+            crc_part = h[1];
+        } else {
+            rc = zscgpu_fetch_results(e, 1, &r1); if (rc) break;
+        }
+        if (r1.ret != 0) { res->ret = r1.ret; break; }
+        if (out_pos + r1.produced + (p->wrap == 1 ? 4u : 0u) > dest_cap) { res->ret = -5; break; }
+        ZS_CUDA_CHECK(cudaMemcpyAsync(dest + out_pos, e->d_comp + st.comp_off, r1.produced, cudaMemcpyDeviceToHost, e->d2h_stream));
+        out_pos += r1.produced;
+        check = (p->wrap == 2) ? zscgpu_crc32_combine(check, crc_part, len) : zscgpu_adler32_combine(check, r1.check, len);
+    }
+    ZS_CUDA_CHECK(cudaStreamSynchronize(e->d2h_stream));
+    ZS_CUDA_CHECK(cudaStreamSynchronize(e->copy_stream));
+    if (rc) return rc;
+    if (res->ret != 0) { res->produced = 0; return ZSCGPU_OK; }
+    if (p->wrap == 1) {
+        dest[comp_skip] = (uint8_t)(L.zhdr & 0xFF); dest[comp_skip + 1] = (uint8_t)((L.zhdr >> 8) & 0xFF);
+        dest[out_pos] = (uint8_t)(check >> 24); dest[out_pos + 1] = (uint8_t)(check >> 16);
+        dest[out_pos + 2] = (uint8_t)(check >> 8); dest[out_pos + 3] = (uint8_t)check;
+        out_pos += 4;
+    }
+    res->produced = (uint32_t)(out_pos - comp_skip);
+    res->check = check;
+    return ZSCGPU_OK;
+}
+
 extern "C" int zscgpu_compress_host(zscgpu_engine *e, uint8_t *dest, uint32_t dest_cap, const uint8_t *src, uint32_t src_len,
                                     const zscgpu_deflate_params *p, uint32_t comp_skip, zscgpu_result *res)
 {
@@ -461,6 +562,20 @@ extern "C" int zscgpu_compress_host(zscgpu_engine *e, uint8_t *dest, uint32_t de
     if ((uint64_t)src_len > e->cfg.raw_bytes || (uint64_t)src_len > e->cfg.deflate_batch_max) {
         snprintf(e->err, sizeof(e->err), "source of %u bytes exceeds the engine's arenas (raw %llu B)", src_len, (unsigned long long)e->cfg.raw_bytes);
         return ZSCGPU_ERR_CAPACITY;
+    }
+    /* waves of whole sections when the buffer is large enough to make overlap pay: at least 64 MiB each and,
+       since the LZ kernel runs one chunk per SM at a time, a chunk count that is a multiple of 2 x SMs */
+    if (p->max_block_len != 0 && src_len >= (128u << 20)) {
+        const uint64_t mbl = p->max_block_len;
+        const uint64_t cps = (mbl + ZS_CHUNK_MAX - 1) / ZS_CHUNK_MAX;                 /* chunks per section */
+        const uint64_t round_secs = (2ull * (uint64_t)e->sms + cps - 1) / cps;          /* sections in two rounds of chunks */
+        const uint64_t k = ((64ull << 20) + round_secs * mbl - 1) / (round_secs * mbl);
+        uint64_t W = k * round_secs * mbl;
+        uint64_t nw = ((uint64_t)src_len + W - 1) / W;
+        if (nw > ZS_MAX_WAVES) { W = (((uint64_t)src_len + ZS_MAX_WAVES - 1) / ZS_MAX_WAVES + p->max_block_len - 1) / p->max_block_len * p->max_block_len; nw = ((uint64_t)src_len + W - 1) / W; }
+        const uint64_t need = (uint64_t)src_len + ((uint64_t)src_len >> 3) + nw * (4096 + 64 + 8);
+        if (nw >= 2 && need <= e->cfg.comp_bytes && dest_cap > comp_skip)
+            return zs_compress_host_waves(e, dest, dest_cap, src, src_len, p, comp_skip, res, W, (uint32_t)nw);
     }
     int r = zscgpu_upload_async(e, 0, 0, src, src_len); if (r) return r;
     zscgpu_stream st;
