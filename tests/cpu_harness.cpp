@@ -26,6 +26,7 @@ struct LzP { int mode, chain, nice, lazy, min_len, max_dist; };
 static const uint32_t TILE = 2048, WINDOW = 32768, NOHASH = 0xFFFF;
 static int g_near = 1;   /* lanes looked at below the current one (deflate_lz.cu looks at the previous lane only) */
 extern "C" void h_set_near(int n) { g_near = n; }
+static int g_hash_bits = 15;   /* 14 for the single-candidate kernel, 15 for the chain kernel (deflate_lz.cu ZlK) */
 
 static inline uint32_t ld32(const uint8_t *p, uint32_t q, uint32_t q_end)
 {
@@ -35,7 +36,7 @@ static inline uint32_t ld32(const uint8_t *p, uint32_t q, uint32_t q_end)
 }
 static inline uint32_t hash3(uint32_t v)
 {
-    uint32_t h = ((v & 0xFFFFFFu) * 2654435761u) >> 17;
+    uint32_t h = ((v & 0xFFFFFFu) * 2654435761u) >> (32 - g_hash_bits);
     return h == 0x7FFF ? 0x7FFE : h;       /* 0x7FFF | flag would collide with the no-hash sentinel */
 }
 
@@ -44,6 +45,7 @@ static void lz_chunk(const uint8_t *data, uint32_t a, uint32_t dict_len, uint32_
                      std::vector<uint32_t> &blk_start, uint32_t block_syms)
 {
     const uint32_t q_dict = a, q_start = a + dict_len, q_end = q_start + len;
+    g_hash_bits = (P.mode == 0 && P.chain > 0) ? 15 : 14;
     std::vector<uint16_t> head(32768, 0), prevd(WINDOW, 0);
     std::vector<uint16_t> t_dist(TILE), t_len(TILE + 32, 0);
     uint32_t carry = q_start;

@@ -75,6 +75,9 @@ def h_inflate(comp, cap, wrap=1):
 
 
 # level -> [mode, chain, nice, lazy, min_len, max_dist, force_type, wrap, zhdr]; must mirror zs_lz_params (engine.cu)
+FAST_MAX_DIST = 32768 - 3 * 2048 - 272
+
+
 def lz_params(level, strategy=0, wrap=1, wbits=15):
     if level == -1:
         level = 6
@@ -96,7 +99,10 @@ def lz_params(level, strategy=0, wrap=1, wbits=15):
     hdr = ((8 + ((wbits - 8) << 4)) << 8) | (lf << 6)
     hdr += 31 - (hdr % 31)
     zhdr = (hdr >> 8) | ((hdr & 0xFF) << 8)
-    return [mode, chain, nice, lazy, min_len, 1 << wbits, force, wrap, zhdr]
+    max_dist = 1 << wbits
+    if not (mode == 0 and chain > 0):
+        max_dist = min(max_dist, FAST_MAX_DIST)     # single-candidate kernel: 32 KiB ring (deflate_lz.cu ZL_FAST_MAX_DIST)
+    return [mode, chain, nice, lazy, min_len, max_dist, force, wrap, zhdr]
 
 
 def model_deflate(src, max_block_len, level, strategy=0, wrap=1, wbits=15):

@@ -31,18 +31,25 @@
 #define ZL_GROUPS (ZL_TILE / 32)
 #define ZL_GPW (ZL_GROUPS / ZL_WORKER_WARPS)       /* consecutive groups per worker warp (one block) */
 #define ZL_BLOCK (ZL_GPW * 32)                     /* 128 positions */
-#define ZL_RING 65536u
-#define ZL_RING_MASK 0xFFFFu
+/* Two layouts.  The chain kernel (levels 2..9) keeps a 64 KiB ring, a 15-bit head table and the 32 Ki link
+ * array: one CTA per SM.  The single-candidate kernel (level 1, Z_RLE, Z_HUFFMAN_ONLY) uses a 32 KiB ring and a
+ * 14-bit head table so that two CTAs share an SM (2 x 97 KB of shared memory, 56 registers): the second CTA's
+ * warps fill the issue slots the first leaves empty at its barriers and shared-memory round trips.  A 32 KiB
+ * ring holds the three staged tiles plus the window, which bounds match distances to ZL_FAST_MAX_DIST. */
+template <bool CHAIN> struct ZlK {
+    static constexpr uint32_t RING = CHAIN ? 65536u : 32768u;
+    static constexpr uint32_t HASH_BITS = CHAIN ? 15u : 14u;
+};
 #define ZL_MIRROR 32u                               /* bytes of the ring start repeated after its end */
 #define ZL_LOOKAHEAD 272u                          /* >= 258 + 3, multiple of 16 */
-#define ZL_HASH_BITS 15
+#define ZL_FAST_MAX_DIST (32768u - 3u * ZL_TILE - ZL_LOOKAHEAD)   /* 26352: see zs_lz_fast_max_dist() */
 #define ZL_NOHASH 0xFFFFu
 #define ZL_NOTFIRST 0x8000u                      /* t_hash flag: a lower lane of the group has the same hash */
 #define ZL_NONE 0xFFFFu
 
-struct ZlSmem {
-    uint32_t ring32[ZL_RING / 4 + ZL_MIRROR / 4];   /* + a mirror of the first bytes: multi-word reads never wrap */
-    uint16_t head[1 << ZL_HASH_BITS];
+template <bool CHAIN> struct ZlSmem {
+    uint32_t ring32[ZlK<CHAIN>::RING / 4 + ZL_MIRROR / 4];   /* + a mirror of the first bytes: multi-word reads never wrap */
+    uint16_t head[1u << ZlK<CHAIN>::HASH_BITS];
     uint16_t t_hash[2][ZL_TILE];      /* double buffered: written by workers, read by the hasher */
     uint16_t t_cand[2][ZL_TILE];      /* double buffered: written by the hasher, read by workers */
     uint16_t t_dist[ZL_TILE];         /* best distance per position */
@@ -54,36 +61,33 @@ struct ZlSmem {
     uint32_t g_off[ZL_GROUPS];
     uint32_t carry;                   /* absolute q of the next parse start */
     uint32_t nsym;                    /* symbols emitted so far */
-};
-struct ZlSmemChain {
-    ZlSmem s;
-    uint16_t prevd[ZS_WINDOW];        /* distance from a position to the previous one with the same hash */
+    uint16_t prevd[CHAIN ? ZS_WINDOW : 2];   /* chain kernel: distance from a position to the previous one with the same hash */
 };
 
 __device__ __forceinline__ void zl_bar_workers() { asm volatile("bar.sync 1, %0;" ::"n"(ZL_WORKERS) : "memory"); }
 
-__device__ __forceinline__ uint32_t zl_ld32(const uint32_t *ring32, uint32_t q)
+template <uint32_t RING> __device__ __forceinline__ uint32_t zl_ld32(const uint32_t *ring32, uint32_t q)
 {
-    uint32_t i = (q >> 2) & (ZL_RING / 4 - 1);
+    uint32_t i = (q >> 2) & (RING / 4 - 1);
     uint32_t w0 = ring32[i], w1 = ring32[i + 1];
     return __funnelshift_r(w0, w1, (q & 3) * 8);
 }
-__device__ __forceinline__ uint32_t zl_ld8(const uint32_t *ring32, uint32_t q)
+template <uint32_t RING> __device__ __forceinline__ uint32_t zl_ld8(const uint32_t *ring32, uint32_t q)
 {
-    return ((const uint8_t *)ring32)[q & ZL_RING_MASK];
+    return ((const uint8_t *)ring32)[q & (RING - 1)];
 }
-__device__ __forceinline__ uint32_t zl_hash(uint32_t v)
+template <uint32_t HASH_BITS> __device__ __forceinline__ uint32_t zl_hash(uint32_t v)
 {
-    uint32_t h = ((v & 0xFFFFFFu) * 2654435761u) >> (32 - ZL_HASH_BITS);
+    uint32_t h = ((v & 0xFFFFFFu) * 2654435761u) >> (32 - HASH_BITS);
     return h == 0x7FFFu ? 0x7FFEu : h;          /* 0x7FFF | ZL_NOTFIRST would collide with ZL_NOHASH */
 }
 
 /* length of the common prefix of the strings at q and q - d, at most maxl */
-__device__ __forceinline__ uint32_t zl_match_len(const uint32_t *ring32, uint32_t q, uint32_t d, uint32_t maxl)
+template <uint32_t RING> __device__ __forceinline__ uint32_t zl_match_len(const uint32_t *ring32, uint32_t q, uint32_t d, uint32_t maxl)
 {
     uint32_t l = 0;
     while (l < maxl) {
-        uint32_t x = zl_ld32(ring32, q + l) ^ zl_ld32(ring32, q + l - d);
+        uint32_t x = zl_ld32<RING>(ring32, q + l) ^ zl_ld32<RING>(ring32, q + l - d);
         if (x) { l += (uint32_t)(__ffs((int)x) - 1) >> 3; break; }
         l += 4;
     }
@@ -91,10 +95,10 @@ __device__ __forceinline__ uint32_t zl_match_len(const uint32_t *ring32, uint32_
 }
 
 /* common prefix of the strings at q and q - d, looking at 16 bytes only (branch-free: 0..16) */
-__device__ __forceinline__ uint32_t zl_match16(const uint32_t *ring32, uint32_t q, uint32_t d)
+template <uint32_t RING> __device__ __forceinline__ uint32_t zl_match16(const uint32_t *ring32, uint32_t q, uint32_t d)
 {
     const uint32_t qb = q - d;
-    const uint32_t ia = (q >> 2) & (ZL_RING / 4 - 1), ib = (qb >> 2) & (ZL_RING / 4 - 1);
+    const uint32_t ia = (q >> 2) & (RING / 4 - 1), ib = (qb >> 2) & (RING / 4 - 1);
     const uint32_t sa = (q & 3) * 8, sb = (qb & 3) * 8;
     uint32_t a[5], b[5];
 #pragma unroll
@@ -109,12 +113,12 @@ __device__ __forceinline__ uint32_t zl_match16(const uint32_t *ring32, uint32_t 
 }
 
 /* same, eight bytes per step (three aligned words per side, two funnel shifts) */
-__device__ __forceinline__ uint32_t zl_match_ext(const uint32_t *ring32, uint32_t q, uint32_t d, uint32_t limit)
+template <uint32_t RING> __device__ __forceinline__ uint32_t zl_match_ext(const uint32_t *ring32, uint32_t q, uint32_t d, uint32_t limit)
 {
     uint32_t l = 0;
     while (l < limit) {
         const uint32_t qa = q + l, qb = qa - d;
-        const uint32_t ia = (qa >> 2) & (ZL_RING / 4 - 1), ib = (qb >> 2) & (ZL_RING / 4 - 1);
+        const uint32_t ia = (qa >> 2) & (RING / 4 - 1), ib = (qb >> 2) & (RING / 4 - 1);
         const uint32_t a0 = ring32[ia], a1 = ring32[ia + 1], a2 = ring32[ia + 2];
         const uint32_t b0 = ring32[ib], b1 = ring32[ib + 1], b2 = ring32[ib + 2];
         const uint32_t sa = (qa & 3) * 8, sb = (qb & 3) * 8;
@@ -128,29 +132,29 @@ __device__ __forceinline__ uint32_t zl_match_ext(const uint32_t *ring32, uint32_
 }
 
 /* workers: copy input bytes [from, to) into the ring (16-byte vectors; bytes for the ragged end) */
-__device__ __forceinline__ uint32_t zl_load(uint32_t *ring32, const uint8_t *gbase, uint32_t loaded, uint32_t need, uint32_t q_end, uint32_t wtid)
+template <uint32_t RING> __device__ __forceinline__ uint32_t zl_load(uint32_t *ring32, const uint8_t *gbase, uint32_t loaded, uint32_t need, uint32_t q_end, uint32_t wtid)
 {
     uint8_t *ring8 = (uint8_t *)ring32;
     if (need <= loaded) return loaded;
     uint32_t full_end = need & ~15u;
     for (uint32_t q = loaded + wtid * 16; q < full_end; q += ZL_WORKERS * 16) {
         uint4 v = __ldg(reinterpret_cast<const uint4 *>(gbase + q));
-        const uint32_t r = q & ZL_RING_MASK;
+        const uint32_t r = q & (RING - 1);
         *reinterpret_cast<uint4 *>(&ring8[r]) = v;
-        if (r < ZL_MIRROR) *reinterpret_cast<uint4 *>(&ring8[ZL_RING + r]) = v;
+        if (r < ZL_MIRROR) *reinterpret_cast<uint4 *>(&ring8[RING + r]) = v;
     }
     uint32_t tail0 = max(loaded, full_end);
     for (uint32_t q = tail0 + wtid; q < need; q += ZL_WORKERS) {
-        const uint32_t r = q & ZL_RING_MASK;
+        const uint32_t r = q & (RING - 1);
         const uint8_t v = __ldg(gbase + q);
         ring8[r] = v;
-        if (r < ZL_MIRROR) ring8[ZL_RING + r] = v;
+        if (r < ZL_MIRROR) ring8[RING + r] = v;
     }
     /* zero a few bytes past the very end so 4-byte compares read defined data */
     if (need == q_end && wtid < 8) {
-        const uint32_t r = (q_end + wtid) & ZL_RING_MASK;
+        const uint32_t r = (q_end + wtid) & (RING - 1);
         ring8[r] = 0;
-        if (r < ZL_MIRROR) ring8[ZL_RING + r] = 0;
+        if (r < ZL_MIRROR) ring8[RING + r] = 0;
     }
     return (need == q_end) ? need : full_end;
 }
@@ -161,13 +165,13 @@ __device__ __forceinline__ uint32_t zl_load(uint32_t *ring32, const uint8_t *gba
  * slot-claiming loop in a 256-entry per-warp scratch: lanes store (rest of hash, lane) at slot hash & 255 and
  * read back; equal hashes meet in one slot and settle on their lowest lane, lanes that lost the slot to a
  * different hash go round again.  Exact and independent of which colliding store the hardware keeps. */
-__device__ __forceinline__ void zl_hash_tile(const uint32_t *ring32, uint16_t *t_hash, uint16_t *scratch, uint32_t t0, uint32_t q_dict, uint32_t q_end, uint32_t wtid)
+template <uint32_t RING, uint32_t HASH_BITS> __device__ __forceinline__ void zl_hash_tile(const uint32_t *ring32, uint16_t *t_hash, uint16_t *scratch, uint32_t t0, uint32_t q_dict, uint32_t q_end, uint32_t wtid)
 {
     const uint32_t lane = wtid & 31;
     uint16_t *sc = scratch + (wtid >> 5) * 256;
     for (uint32_t i = wtid; i < ZL_TILE; i += ZL_WORKERS) {
         uint32_t q = t0 + i, h = ZL_NOHASH;
-        if (q >= q_dict && q + 3 <= q_end) h = zl_hash(zl_ld32(ring32, q));
+        if (q >= q_dict && q + 3 <= q_end) h = zl_hash<HASH_BITS>(zl_ld32<RING>(ring32, q));
         const bool valid = (h != ZL_NOHASH);
         const uint32_t hp = __shfl_up_sync(0xFFFFFFFFu, h, 1);
         bool notfirst = valid && lane > 0 && hp == h;          /* runs: decided by the neighbour alone */
@@ -197,7 +201,7 @@ __device__ __forceinline__ void zl_hash_tile(const uint32_t *ring32, uint16_t *t
  * every other lane ZL_NOTFIRST, so the stores of a group never collide and the walk is a plain in-order
  * stream of shared-memory loads and stores with nothing to wait for. */
 template <bool CHAIN>
-__device__ __forceinline__ void zl_hasher_tile(ZlSmem &S, uint16_t *prevd, const uint16_t *t_hash, uint16_t *t_cand, uint32_t t0, uint32_t lane)
+__device__ __forceinline__ void zl_hasher_tile(ZlSmem<CHAIN> &S, uint16_t *prevd, const uint16_t *t_hash, uint16_t *t_cand, uint32_t t0, uint32_t lane)
 {
 #pragma unroll 4
     for (uint32_t g = 0; g < ZL_GROUPS; g++) {
@@ -222,14 +226,15 @@ __device__ __forceinline__ void zl_hasher_tile(ZlSmem &S, uint16_t *prevd, const
 }
 
 template <bool CHAIN>
-__global__ void __launch_bounds__(ZL_THREADS, 1)
+__global__ void __launch_bounds__(ZL_THREADS, CHAIN ? 1 : 2)
 zs_lz_kernel(const uint8_t *__restrict__ raw, const ZsChunk *__restrict__ chunks,
              uint32_t *__restrict__ sym, uint32_t *__restrict__ chunk_nsym,
              uint32_t *__restrict__ blk_in_start, ZsLzParams P)
 {
     extern __shared__ __align__(16) unsigned char zl_smem_raw[];
-    ZlSmem &S = *reinterpret_cast<ZlSmem *>(zl_smem_raw);
-    uint16_t *prevd = CHAIN ? reinterpret_cast<ZlSmemChain *>(zl_smem_raw)->prevd : nullptr;
+    ZlSmem<CHAIN> &S = *reinterpret_cast<ZlSmem<CHAIN> *>(zl_smem_raw);
+    uint16_t *prevd = S.prevd;
+    constexpr uint32_t RING = ZlK<CHAIN>::RING, HASH_BITS = ZlK<CHAIN>::HASH_BITS;
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool is_hasher = (warp == 0);
@@ -242,7 +247,7 @@ zs_lz_kernel(const uint8_t *__restrict__ raw, const ZsChunk *__restrict__ chunks
     uint32_t *out_sym = sym + cd.sym_off;
     const bool hashing = (P.mode == 0);
 
-    for (uint32_t i = tid; i < (1u << ZL_HASH_BITS) / 2; i += ZL_THREADS) ((uint32_t *)S.head)[i] = 0;
+    for (uint32_t i = tid; i < (1u << HASH_BITS) / 2; i += ZL_THREADS) ((uint32_t *)S.head)[i] = 0;
     if (CHAIN) for (uint32_t i = tid; i < ZS_WINDOW / 2; i += ZL_THREADS) ((uint32_t *)prevd)[i] = 0;
     for (uint32_t i = tid; i < ZL_TILE + 32; i += ZL_THREADS) S.t_len[i] = 0;
     if (tid == 0) { S.carry = q_start; S.nsym = 0; if (cd.len == 0) blk_in_start[cd.blk_base] = 0; }
@@ -253,11 +258,11 @@ zs_lz_kernel(const uint8_t *__restrict__ raw, const ZsChunk *__restrict__ chunks
     uint32_t loaded = hashing ? 0 : ((t_first > ZS_WINDOW ? t_first - ZS_WINDOW : 0) & ~15u);
 
     /* ---- prologue: stage tiles 0 and 1, hash them, head-table pass of tile 0 ---- */
-    if (!is_hasher) loaded = zl_load(S.ring32, gbase, loaded, min(q_end, t_first + 2 * ZL_TILE + ZL_LOOKAHEAD), q_end, wtid);
+    if (!is_hasher) loaded = zl_load<RING>(S.ring32, gbase, loaded, min(q_end, t_first + 2 * ZL_TILE + ZL_LOOKAHEAD), q_end, wtid);
     __syncthreads();
     if (!is_hasher && hashing) {
-        zl_hash_tile(S.ring32, S.t_hash[0], S.t_exit, t_first, q_dict, q_end, wtid);
-        if (ntiles > 1) zl_hash_tile(S.ring32, S.t_hash[1], S.t_exit, t_first + ZL_TILE, q_dict, q_end, wtid);
+        zl_hash_tile<RING, HASH_BITS>(S.ring32, S.t_hash[0], S.t_exit, t_first, q_dict, q_end, wtid);
+        if (ntiles > 1) zl_hash_tile<RING, HASH_BITS>(S.ring32, S.t_hash[1], S.t_exit, t_first + ZL_TILE, q_dict, q_end, wtid);
     }
     __syncthreads();
     if (is_hasher && hashing && ntiles > 0) zl_hasher_tile<CHAIN>(S, prevd, S.t_hash[0], S.t_cand[0], t_first, lane);
@@ -271,7 +276,7 @@ zs_lz_kernel(const uint8_t *__restrict__ raw, const ZsChunk *__restrict__ chunks
                 zl_hasher_tile<CHAIN>(S, prevd, S.t_hash[(k + 1) & 1], S.t_cand[(k + 1) & 1], t0 + ZL_TILE, lane);
         } else {
             /* ---- A: stage tile k+2 (only ring bytes older than the window of tile k are replaced) ---- */
-            loaded = zl_load(S.ring32, gbase, loaded, min(q_end, t0 + 3 * ZL_TILE + ZL_LOOKAHEAD), q_end, wtid);
+            loaded = zl_load<RING>(S.ring32, gbase, loaded, min(q_end, t0 + 3 * ZL_TILE + ZL_LOOKAHEAD), q_end, wtid);
             const bool live = (t0 + ZL_TILE > q_start);           /* not a dictionary-only tile */
             if (live) {
                 /* ---- D: match lengths ---- */
@@ -295,11 +300,11 @@ zs_lz_kernel(const uint8_t *__restrict__ raw, const ZsChunk *__restrict__ chunks
                                 const bool same = lane > 0 && hp16 != ZL_NOHASH && ((hp16 ^ h16) & 0x7FFFu) == 0;
                                 d = (h16 == ZL_NOHASH) ? 0u : (same ? 1u : ((q - (uint32_t)cand[i]) & 0xFFFFu));
                             }
-                            if (d > min((uint32_t)P.max_dist, q - q_dict)) d = 0;
+                            if (d > min(min((uint32_t)P.max_dist, ZL_FAST_MAX_DIST), q - q_dict)) d = 0;
                             limit = q_end - q;
                         }
                         uint32_t best = 0;
-                        if (d) best = zl_match16(S.ring32, q, d);
+                        if (d) best = zl_match16<RING>(S.ring32, q, d);
                         const bool lng = d != 0 && best == 16 && limit > 16;
                         const uint32_t lm = __ballot_sync(0xFFFFFFFFu, lng);
                         if (lm) {
@@ -311,7 +316,7 @@ zs_lz_kernel(const uint8_t *__restrict__ raw, const ZsChunk *__restrict__ chunks
                             const uint32_t stop = (hm | ~lm) & gt;
                             const uint32_t nexth = stop ? (uint32_t)__ffs((int)stop) - 1u : 32u;
                             uint32_t ext = 0;
-                            if (head) ext = 16u + zl_match_ext(S.ring32, q + 16, d, min(limit, ZS_MAX_MATCH + (nexth - lane - 1u)) - 16u);
+                            if (head) ext = 16u + zl_match_ext<RING>(S.ring32, q + 16, d, min(limit, ZS_MAX_MATCH + (nexth - lane - 1u)) - 16u);
                             const uint32_t e = __shfl_sync(0xFFFFFFFFu, ext, hl & 31u);
                             if (lng) best = e - (lane - hl);
                         }
@@ -329,14 +334,14 @@ zs_lz_kernel(const uint8_t *__restrict__ raw, const ZsChunk *__restrict__ chunks
                             uint32_t maxl = min(ZS_MAX_MATCH, q_end - q);
                             uint32_t maxd = min((uint32_t)P.max_dist, q - q_dict);
                             if (P.mode == 1) {
-                                if (maxd >= 1) { best = zl_match_len(S.ring32, q, 1, maxl); bestd = 1; }
+                                if (maxd >= 1) { best = zl_match_len<RING>(S.ring32, q, 1, maxl); bestd = 1; }
                             } else {
                                 uint32_t d = cand[i];
                                 int budget = P.chain;
                                 while (d != 0 && d <= maxd) {
                                     /* cheap reject: the byte that would extend the best match must agree */
-                                    if (best < 3 || zl_ld8(S.ring32, q + best) == zl_ld8(S.ring32, q + best - d)) {
-                                        uint32_t l = zl_match_len(S.ring32, q, d, maxl);
+                                    if (best < 3 || zl_ld8<RING>(S.ring32, q + best) == zl_ld8<RING>(S.ring32, q + best - d)) {
+                                        uint32_t l = zl_match_len<RING>(S.ring32, q, d, maxl);
                                         if (l > best) { best = l; bestd = d; if (l >= (uint32_t)P.nice || l >= maxl) break; }
                                     }
                                     if (!CHAIN || budget-- <= 0) break;
@@ -418,7 +423,7 @@ zs_lz_kernel(const uint8_t *__restrict__ raw, const ZsChunk *__restrict__ chunks
                     }
                     bool v = ((marks >> lane) & 1u) && q >= q_start && q < q_end;
                     vmask[g] = __ballot_sync(0xFFFFFFFFu, v);
-                    val[g] = (n >= 3) ? zs_match(n, S.t_dist[i]) : zl_ld8(S.ring32, q);
+                    val[g] = (n >= 3) ? zs_match(n, S.t_dist[i]) : zl_ld8<RING>(S.ring32, q);
                     if (lane == 0) S.g_cnt[ww * ZL_GPW + g] = __popc(vmask[g]);
                 }
                 zl_bar_workers();
@@ -448,7 +453,7 @@ zs_lz_kernel(const uint8_t *__restrict__ raw, const ZsChunk *__restrict__ chunks
                 zl_bar_workers();       /* ring bytes staged above must be visible before hashing them */
             }
             /* ---- B: hashes of tile k+2 (its bytes were staged in A; every path above passed a worker barrier) ---- */
-            if (hashing && k + 2 < ntiles) zl_hash_tile(S.ring32, S.t_hash[k & 1], S.t_exit, t0 + 2 * ZL_TILE, q_dict, q_end, wtid);
+            if (hashing && k + 2 < ntiles) zl_hash_tile<RING, HASH_BITS>(S.ring32, S.t_hash[k & 1], S.t_exit, t0 + 2 * ZL_TILE, q_dict, q_end, wtid);
         }
         __syncthreads();
     }
@@ -458,7 +463,12 @@ zs_lz_kernel(const uint8_t *__restrict__ raw, const ZsChunk *__restrict__ chunks
 static_assert(ZL_GROUPS == 64, "group-count scan assumes 64 groups per tile");
 static_assert(ZL_GPW * ZL_WORKER_WARPS == ZL_GROUPS, "groups must divide evenly over the worker warps");
 
-extern "C" size_t zs_lz_smem_bytes(int chain) { return chain ? sizeof(ZlSmemChain) : sizeof(ZlSmem); }
+extern "C" size_t zs_lz_smem_bytes(int chain) { return chain ? sizeof(ZlSmem<true>) : sizeof(ZlSmem<false>); }
+/* longest match distance the single-candidate kernel can represent: its ring must hold the window of the tile
+ * being searched and the three tiles staged ahead of it */
+extern "C" uint32_t zs_lz_fast_max_dist(void) { return ZL_FAST_MAX_DIST; }
+static_assert(ZL_FAST_MAX_DIST + 3u * ZL_TILE + ZL_LOOKAHEAD <= ZlK<false>::RING, "fast ring too small");
+static_assert(ZS_WINDOW + 3u * ZL_TILE + ZL_LOOKAHEAD <= ZlK<true>::RING, "chain ring too small");
 
 extern "C" cudaError_t zs_lz_launch(cudaStream_t st, int chain, uint32_t nchunks, const uint8_t *raw,
                                     const ZsChunk *chunks, uint32_t *sym, uint32_t *chunk_nsym,
@@ -466,11 +476,11 @@ extern "C" cudaError_t zs_lz_launch(cudaStream_t st, int chain, uint32_t nchunks
 {
     if (nchunks == 0) return cudaSuccess;
     if (chain) {
-        cudaFuncSetAttribute(zs_lz_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ZlSmemChain));
-        zs_lz_kernel<true><<<nchunks, ZL_THREADS, sizeof(ZlSmemChain), st>>>(raw, chunks, sym, chunk_nsym, blk_in_start, P);
+        cudaFuncSetAttribute(zs_lz_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ZlSmem<true>));
+        zs_lz_kernel<true><<<nchunks, ZL_THREADS, sizeof(ZlSmem<true>), st>>>(raw, chunks, sym, chunk_nsym, blk_in_start, P);
     } else {
-        cudaFuncSetAttribute(zs_lz_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ZlSmem));
-        zs_lz_kernel<false><<<nchunks, ZL_THREADS, sizeof(ZlSmem), st>>>(raw, chunks, sym, chunk_nsym, blk_in_start, P);
+        cudaFuncSetAttribute(zs_lz_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ZlSmem<false>));
+        zs_lz_kernel<false><<<nchunks, ZL_THREADS, sizeof(ZlSmem<false>), st>>>(raw, chunks, sym, chunk_nsym, blk_in_start, P);
     }
     return cudaGetLastError();
 }

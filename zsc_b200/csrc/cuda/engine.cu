@@ -12,6 +12,7 @@
 
 /* kernel launchers (deflate_lz.cu, deflate_huff.cu, checksum.cu, inflate.cu) */
 extern "C" cudaError_t zs_lz_launch(cudaStream_t, int, uint32_t, const uint8_t *, const ZsChunk *, uint32_t *, uint32_t *, uint32_t *, ZsLzParams);
+extern "C" uint32_t zs_lz_fast_max_dist(void);
 extern "C" cudaError_t zs_huff_launch(cudaStream_t, uint32_t, uint32_t, const ZsChunk *, const uint32_t *, const ZsStream *, const uint32_t *,
                                       const uint32_t *, const uint32_t *, zh_block *, const ZsAdlerAcc *, const uint8_t *, uint8_t *,
                                       int32_t *, uint32_t *, uint32_t *, ZsLzParams, cudaEvent_t, cudaEvent_t);
@@ -281,6 +282,7 @@ static int zs_lz_params(const zscgpu_deflate_params *p, ZsLzParams *L, int *chai
     int wbits = p->window_bits ? p->window_bits : 15;
     if (wbits < 9 || wbits > 15) return -1;
     L->max_dist = 1 << wbits;
+    if (!*chain_kernel && (uint32_t)L->max_dist > zs_lz_fast_max_dist()) L->max_dist = (int32_t)zs_lz_fast_max_dist();
     /* zlib header (RFC 1950): CMF = method 8 + window size; FLG carries the level class
        (same values as reference src/deflate.c:1029-1049) */
     int lf = (p->strategy >= 2 || level < 2) ? 0 : (level < 6 ? 1 : (level == 6 ? 2 : 3));
