@@ -36,7 +36,8 @@ struct ZbSmem {
 __global__ void __launch_bounds__(ZB_THREADS)
 zs_block_kernel(const ZsChunk *__restrict__ chunks, const uint32_t *__restrict__ blk_chunk,
                 const uint32_t *__restrict__ sym, const uint32_t *__restrict__ chunk_nsym,
-                const uint32_t *__restrict__ blk_in_start, zh_block *__restrict__ blocks, ZsLzParams P)
+                const uint32_t *__restrict__ blk_in_start, zh_block *__restrict__ blocks,
+                uint4 *__restrict__ blk_meta, ZsLzParams P)
 {
     __shared__ ZbSmem S;
     const uint32_t b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -46,7 +47,7 @@ zs_block_kernel(const ZsChunk *__restrict__ chunks, const uint32_t *__restrict__
     const uint32_t nsym = chunk_nsym[c];
     uint32_t nblk = (nsym + ZS_BLOCK_SYMS - 1) / ZS_BLOCK_SYMS;
     if (nblk == 0) nblk = 1;
-    if (k >= nblk) { if (tid == 0) { blocks[b].type = ZH_UNUSED; blocks[b].flags = 0; } return; }
+    if (k >= nblk) { if (tid == 0) { blocks[b].type = ZH_UNUSED; blocks[b].flags = 0; blk_meta[b] = make_uint4(ZH_UNUSED, 0, 0, 0); } return; }
     const uint32_t cnt = min(ZS_BLOCK_SYMS, nsym - k * ZS_BLOCK_SYMS);
     const uint32_t *bs = sym + cd.sym_off + (uint64_t)k * ZS_BLOCK_SYMS;
 
@@ -148,7 +149,6 @@ zs_block_kernel(const ZsChunk *__restrict__ chunks, const uint32_t *__restrict__
     const int nl = max(S.max_l, 256) + 1, nd = S.max_d + 1, nseq = nl + nd;
     uint16_t *run_start = S.sc2.parent;                 /* the distance tree's scratch is free now */
     uint8_t *run_val = S.sc2.depth;
-    uint16_t *run_tok = reinterpret_cast<uint16_t *>(S.sc2.w);
     if (tid <= ZH_BLCODES) S.sc.blfreq[tid] = 0;
     {
         const int i0 = (int)tid * 3;
@@ -211,7 +211,6 @@ zs_block_kernel(const ZsChunk *__restrict__ chunks, const uint32_t *__restrict__
                 atomicAdd(&S.sc.blfreq[val], lits);
             }
         }
-        (void)run_tok;
     }
     __syncthreads();
     /* ---- code-length tree (19 symbols) on one thread, header size on all, decision ---- */
@@ -359,82 +358,109 @@ zs_block_kernel(const ZsChunk *__restrict__ chunks, const uint32_t *__restrict__
     const uint32_t *src = reinterpret_cast<const uint32_t *>(&S.blk);
     uint32_t *dst = reinterpret_cast<uint32_t *>(&blocks[b]);
     for (uint32_t i = tid; i < sizeof(zh_block) / 4; i += ZB_THREADS) dst[i] = src[i];
+    /* what the offset pass needs, 16 bytes per block instead of a walk over the large records */
+    if (tid == 0) blk_meta[b] = make_uint4(S.blk.type, S.blk.body_bits, S.blk.in_len, S.blk.flags);
 }
 
-/* ======================= K2b: offsets, one CTA per stream ======================= */
-#define ZO_THREADS 256
+/* ======================= K2b: stored-run merging (thread per chunk), offsets (one CTA per stream) ======================= */
+#define ZM_THREADS 128
+#define ZO_THREADS_MAX 1024
 
-__global__ void __launch_bounds__(ZO_THREADS)
-zs_offset_kernel(const ZsStream *__restrict__ streams, const ZsChunk *__restrict__ chunks,
-                 const uint32_t *__restrict__ blk_chunk, zh_block *__restrict__ blocks,
+/* Merge runs of adjacent stored blocks of a chunk into one stored block of <= 65535 bytes: the first keeps
+ * the header with the run's length, the others become payload-only continuations.  Keeps incompressible data
+ * at 5 bytes per 64 KiB, inside the reference's output bound. */
+__global__ void __launch_bounds__(ZM_THREADS)
+zs_stored_merge_kernel(const ZsChunk *__restrict__ chunks, uint32_t nchunks, zh_block *__restrict__ blocks, uint4 *__restrict__ blk_meta)
+{
+    const uint32_t c = blockIdx.x * ZM_THREADS + threadIdx.x;
+    if (c >= nchunks) return;
+    const uint32_t base = chunks[c].blk_base, capn = chunks[c].blk_cap;
+    uint32_t head = 0xFFFFFFFFu, total = 0;
+    for (uint32_t k = 0; k < capn; k++) {
+        uint4 mt = blk_meta[base + k];                      /* type, body_bits, in_len, flags */
+        if (mt.x == ZH_UNUSED) break;
+        if (mt.x == ZH_STORED) {
+            if (head != 0xFFFFFFFFu && total + mt.z <= 65535u) {
+                mt.x = ZH_STORED_CONT;
+                blk_meta[base + k] = mt;
+                blocks[base + k].type = ZH_STORED_CONT;
+                total += mt.z;
+                blocks[head].stored_total = total;
+                if (mt.w & ZB_LAST_OF_STREAM) blocks[head].hdr[0] |= 1u;
+            } else { head = base + k; total = mt.z; }
+        } else head = 0xFFFFFFFFu;
+        if (mt.w & (ZB_LAST_OF_SECTION | ZB_LAST_OF_STREAM)) head = 0xFFFFFFFFu;
+    }
+}
+
+__device__ __forceinline__ zk_elem zk_shfl_up(zk_elem e, int o)
+{
+    zk_elem r;
+    r.a = __shfl_up_sync(0xFFFFFFFFu, e.a, o); r.b = __shfl_up_sync(0xFFFFFFFFu, e.b, o);
+    r.al = __shfl_up_sync(0xFFFFFFFFu, e.al, o); r.pad = 0;
+    return r;
+}
+
+__global__ void __launch_bounds__(ZO_THREADS_MAX)
+zs_offset_kernel(const ZsStream *__restrict__ streams, uint4 *__restrict__ blk_meta, uint64_t *__restrict__ blk_bitoff,
                  const ZsAdlerAcc *__restrict__ adler_acc, uint32_t *__restrict__ comp32,
                  int32_t *__restrict__ res_ret, uint32_t *__restrict__ res_produced,
                  uint32_t *__restrict__ res_check, ZsLzParams P)
 {
-    __shared__ zk_elem part[ZO_THREADS];
-    __shared__ uint64_t s_end;
+    __shared__ zk_elem wpart[32];
     __shared__ int s_fail;
-    const uint32_t sidx = blockIdx.x, tid = threadIdx.x;
+    const uint32_t sidx = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
     const ZsStream st = streams[sidx];
-    /* Merge runs of adjacent stored blocks of a chunk into one stored block of <= 65535 bytes: the
-       first keeps the header with the run's length, the others become payload-only continuations.
-       Keeps incompressible data at 5 bytes per 64 KiB, inside the reference's output bound. */
-    for (uint32_t c = st.chunk_first + tid; c < st.chunk_first + st.chunk_count; c += ZO_THREADS) {
-        const uint32_t base = chunks[c].blk_base, capn = chunks[c].blk_cap;
-        uint32_t head = 0xFFFFFFFFu, total = 0;
-        for (uint32_t k = 0; k < capn; k++) {
-            zh_block *bp = &blocks[base + k];
-            const uint32_t type = bp->type;
-            if (type == ZH_UNUSED) break;
-            if (type == ZH_STORED) {
-                if (head != 0xFFFFFFFFu && total + bp->in_len <= 65535u) {
-                    bp->type = ZH_STORED_CONT;
-                    total += bp->in_len;
-                    blocks[head].stored_total = total;
-                    if (bp->flags & ZB_LAST_OF_STREAM) blocks[head].hdr[0] |= 1u;
-                } else { head = base + k; total = bp->in_len; }
-            } else head = 0xFFFFFFFFu;
-            if (bp->flags & (ZB_LAST_OF_SECTION | ZB_LAST_OF_STREAM)) head = 0xFFFFFFFFu;
+    const uint32_t per = (st.blk_count + nthr - 1) / nthr;
+    const uint32_t lo = min(st.blk_count, tid * per), hi = min(st.blk_count, lo + per);
+    zk_elem mine = zk_ident();
+    for (uint32_t i = lo; i < hi; i++) {
+        const uint4 mt = blk_meta[st.blk_first + i];
+        mine = zk_compose(mine, zk_elem_of_block(mt.x, mt.y, mt.z, mt.w, P.wrap));
+    }
+    /* exclusive scan of the per-thread elements (composition is associative, not commutative) */
+    zk_elem inc = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { zk_elem t = zk_shfl_up(inc, o); if ((int)lane >= o) inc = zk_compose(t, inc); }
+    if (lane == 31) wpart[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        const uint32_t nw = nthr >> 5;
+        zk_elem w = lane < nw ? wpart[lane] : zk_ident();
+        zk_elem wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { zk_elem t = zk_shfl_up(wi, o); if ((int)lane >= o) wi = zk_compose(t, wi); }
+        zk_elem wex = zk_shfl_up(wi, 1);
+        if (lane == 0) wex = zk_ident();
+        wpart[lane] = wex;                                   /* exclusive prefix of the warp totals */
+        if (lane == 31) {
+            const uint64_t x0 = st.comp_off * 8ull;
+            const uint64_t xe = zk_apply(wi, x0);
+            const uint64_t bytes = (xe - x0 + 7) >> 3;
+            const int fail = bytes > st.comp_cap;
+            s_fail = fail;
+            res_ret[sidx] = fail ? -5 /* Z_BUF_ERROR */ : 0;
+            res_produced[sidx] = fail ? 0u : (uint32_t)bytes;
+            uint32_t a = (uint32_t)(adler_acc[sidx].s1 % ZS_ADLER_BASE), bsum = (uint32_t)(adler_acc[sidx].s2 % ZS_ADLER_BASE);
+            /* adler32 of the stream = (1 + sum bytes, len + weighted sum) mod 65521 */
+            a = (a + 1) % ZS_ADLER_BASE;
+            bsum = (uint32_t)((bsum + (uint64_t)st.raw_len) % ZS_ADLER_BASE);
+            res_check[sidx] = (bsum << 16) | a;
+            if (!fail && (xe & 31)) comp32[xe >> 5] = 0;
         }
     }
     __syncthreads();
-    const uint32_t per = (st.blk_count + ZO_THREADS - 1) / ZO_THREADS;
-    const uint32_t lo = min(st.blk_count, tid * per), hi = min(st.blk_count, lo + per);
-    zk_elem acc = zk_ident();
-    for (uint32_t i = lo; i < hi; i++) {
-        const zh_block *bp = &blocks[st.blk_first + i];
-        acc = zk_compose(acc, zk_elem_of_block(bp->type, bp->body_bits, bp->in_len, bp->flags, P.wrap));
-    }
-    part[tid] = acc;
-    __syncthreads();
-    if (tid == 0) {
-        zk_elem run = zk_ident();
-        for (int i = 0; i < ZO_THREADS; i++) { zk_elem t = part[i]; part[i] = run; run = zk_compose(run, t); }
-        uint64_t x0 = st.comp_off * 8ull;
-        uint64_t xe = zk_apply(run, x0);
-        uint64_t bytes = (xe - x0 + 7) >> 3;
-        int fail = bytes > st.comp_cap;
-        s_end = xe; s_fail = fail;
-        res_ret[sidx] = fail ? -5 /* Z_BUF_ERROR */ : 0;
-        res_produced[sidx] = fail ? 0u : (uint32_t)bytes;
-        uint32_t a = (uint32_t)(adler_acc[sidx].s1 % ZS_ADLER_BASE), bsum = (uint32_t)(adler_acc[sidx].s2 % ZS_ADLER_BASE);
-        /* adler32 of the stream = (1 + sum bytes, len + weighted sum) mod 65521 */
-        a = (a + 1) % ZS_ADLER_BASE;
-        bsum = (uint32_t)((bsum + (uint64_t)st.raw_len) % ZS_ADLER_BASE);
-        res_check[sidx] = (bsum << 16) | a;
-        if (!fail && (xe & 31)) comp32[xe >> 5] = 0;
-    }
-    __syncthreads();
-    const uint64_t x0 = st.comp_off * 8ull;
+    zk_elem before = zk_shfl_up(inc, 1);
+    if (lane == 0) before = zk_ident();
+    before = zk_compose(wpart[warp], before);
     const int fail = s_fail;
-    uint64_t x = zk_apply(part[tid], x0);
+    uint64_t x = zk_apply(before, st.comp_off * 8ull);
     for (uint32_t i = lo; i < hi; i++) {
-        zh_block *bp = &blocks[st.blk_first + i];
-        uint32_t type = bp->type;
-        if (type == ZH_UNUSED) continue;
-        bp->bitoff = x;
-        if (fail) bp->flags |= ZB_STREAM_FAILED; else comp32[x >> 5] = 0;
-        x = zk_apply(zk_elem_of_block(type, bp->body_bits, bp->in_len, bp->flags, P.wrap), x);
+        uint4 mt = blk_meta[st.blk_first + i];
+        if (mt.x == ZH_UNUSED) continue;
+        blk_bitoff[st.blk_first + i] = x;
+        if (fail) { mt.w |= ZB_STREAM_FAILED; blk_meta[st.blk_first + i] = mt; } else comp32[x >> 5] = 0;
+        x = zk_apply(zk_elem_of_block(mt.x, mt.y, mt.z, mt.w & ~(uint32_t)ZB_STREAM_FAILED, P.wrap), x);
     }
 }
 
@@ -491,21 +517,23 @@ __device__ __forceinline__ void ze_put_byte(uint8_t *comp, uint64_t pos, uint32_
     else comp[pos] = (uint8_t)v;
 }
 
-__global__ void __launch_bounds__(ZE_THREADS)
+__global__ void __launch_bounds__(ZE_THREADS, 4)
 zs_encode_kernel(const zh_block *__restrict__ blocks, const uint32_t *__restrict__ blk_chunk,
                  const ZsChunk *__restrict__ chunks, const uint32_t *__restrict__ sym,
                  const uint8_t *__restrict__ raw, uint8_t *__restrict__ comp,
-                 const uint32_t *__restrict__ res_check, ZsLzParams P)
+                 const uint32_t *__restrict__ res_check, const uint4 *__restrict__ blk_meta,
+                 const uint64_t *__restrict__ blk_bitoff, ZsLzParams P)
 {
     extern __shared__ __align__(16) unsigned char ze_smem_raw[];
     ZeSmem &S = *reinterpret_cast<ZeSmem *>(ze_smem_raw);
     const uint32_t b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const zh_block *bp = &blocks[b];
-    const uint32_t type = bp->type, flags = bp->flags;
+    const uint4 mt = blk_meta[b];                          /* type, body_bits, in_len, flags */
+    const uint32_t type = mt.x, flags = mt.w;
     if (type == ZH_UNUSED || (flags & ZB_STREAM_FAILED)) return;
     const ZsChunk cd = chunks[blk_chunk[b]];
-    const uint64_t x = bp->bitoff;
-    const zk_elem el = zk_elem_of_block(type, bp->body_bits, bp->in_len, flags, P.wrap);
+    const uint64_t x = blk_bitoff[b];
+    const zk_elem el = zk_elem_of_block(type, mt.y, mt.z, flags, P.wrap);
     const uint64_t xe = zk_apply(el, x);
     const uint64_t w_first = x >> 5, w_last = (xe & 31) ? (xe >> 5) : ~0ull;
     const uint32_t hdr_bits = bp->hdr_bits;
@@ -520,7 +548,7 @@ zs_encode_kernel(const zh_block *__restrict__ blocks, const uint32_t *__restrict
     if (type == ZH_STORED || type == ZH_STORED_CONT) {
         /* [stream header][3-bit block header][pad][LEN][NLEN][bytes][suffix]: byte-granular writes.
            A continuation of a merged run is payload (+ suffix) only and starts byte aligned. */
-        const uint32_t in_len = bp->in_len;
+        const uint32_t in_len = mt.z;
         const uint32_t run_len = bp->stored_total;
         const uint64_t hb = x + pre_bits;                 /* bit position of the block header */
         const uint64_t d0 = type == ZH_STORED ? (zk_up8(hb + 3) >> 3) + 4 : (x >> 3);   /* first payload byte */
@@ -577,20 +605,24 @@ zs_encode_kernel(const zh_block *__restrict__ blocks, const uint32_t *__restrict
     }
     __syncthreads();
 
-    /* ---- pass 1: bits per thread run ---- */
-    uint32_t sy[ZE_RUN];
+    /* ---- pass 1: bits per thread run.  The run's symbols are read again in pass 2 (they sit in L1 / L2 by
+            then) rather than held in 32 registers: at <= 64 registers four CTAs share an SM ---- */
     const uint32_t *bs = sym + bp->sym_off;
     const uint32_t s0 = tid * ZE_RUN;
-#pragma unroll
-    for (int i = 0; i < ZE_RUN / 4; i++) {
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (s0 + i * 4 < nsym) v = __ldg(reinterpret_cast<const uint4 *>(bs + s0) + i);
-        sy[i * 4 + 0] = v.x; sy[i * 4 + 1] = v.y; sy[i * 4 + 2] = v.z; sy[i * 4 + 3] = v.w;
-    }
     uint32_t mybits = 0;
 #pragma unroll
-    for (int i = 0; i < ZE_RUN; i++) {
-        if (s0 + i < nsym) { uint32_t v0, n0, v1, n1; ze_sym_bits(S, sy[i], v0, n0, v1, n1); mybits += n0 + n1; }
+    for (int h = 0; h < ZE_RUN / 16; h++) {
+        uint4 v[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            v[i] = make_uint4(0, 0, 0, 0);
+            if (s0 + h * 16 + i * 4 < nsym) v[i] = __ldg(reinterpret_cast<const uint4 *>(bs + s0 + h * 16) + i);
+        }
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            const uint32_t sv = (i & 3) == 0 ? v[i >> 2].x : (i & 3) == 1 ? v[i >> 2].y : (i & 3) == 2 ? v[i >> 2].z : v[i >> 2].w;
+            if (s0 + h * 16 + i < nsym) { uint32_t v0, n0, v1, n1; ze_sym_bits(S, sv, v0, n0, v1, n1); mybits += n0 + n1; }
+        }
     }
     uint32_t inc = mybits;
 #pragma unroll
@@ -610,20 +642,30 @@ zs_encode_kernel(const zh_block *__restrict__ blocks, const uint32_t *__restrict
         unsigned long long acc = 0;
         bool first = true;
 #pragma unroll
-        for (int i = 0; i < ZE_RUN; i++) {
-            if (s0 + i < nsym) {
-                uint32_t v0, n0, v1, n1;
-                ze_sym_bits(S, sy[i], v0, n0, v1, n1);
-                acc |= (unsigned long long)v0 << fill; fill += n0;
-                if (fill >= 32) {
-                    if (first) { atomicOr(&S.stage[w], (uint32_t)acc); first = false; } else S.stage[w] = (uint32_t)acc;
-                    w++; acc >>= 32; fill -= 32;
-                }
-                if (n1) {
-                    acc |= (unsigned long long)v1 << fill; fill += n1;
+        for (int h = 0; h < ZE_RUN / 16; h++) {
+            uint4 v[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                v[i] = make_uint4(0, 0, 0, 0);
+                if (s0 + h * 16 + i * 4 < nsym) v[i] = __ldg(reinterpret_cast<const uint4 *>(bs + s0 + h * 16) + i);
+            }
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                const uint32_t sv = (i & 3) == 0 ? v[i >> 2].x : (i & 3) == 1 ? v[i >> 2].y : (i & 3) == 2 ? v[i >> 2].z : v[i >> 2].w;
+                if (s0 + h * 16 + i < nsym) {
+                    uint32_t v0, n0, v1, n1;
+                    ze_sym_bits(S, sv, v0, n0, v1, n1);
+                    acc |= (unsigned long long)v0 << fill; fill += n0;
                     if (fill >= 32) {
                         if (first) { atomicOr(&S.stage[w], (uint32_t)acc); first = false; } else S.stage[w] = (uint32_t)acc;
                         w++; acc >>= 32; fill -= 32;
+                    }
+                    if (n1) {
+                        acc |= (unsigned long long)v1 << fill; fill += n1;
+                        if (fill >= 32) {
+                            if (first) { atomicOr(&S.stage[w], (uint32_t)acc); first = false; } else S.stage[w] = (uint32_t)acc;
+                            w++; acc >>= 32; fill -= 32;
+                        }
                     }
                 }
             }
@@ -663,15 +705,22 @@ extern "C" cudaError_t zs_huff_launch(cudaStream_t st, uint32_t nblk_slots, uint
                                       zh_block *blocks, const ZsAdlerAcc *adler_acc,
                                       const uint8_t *raw, uint8_t *comp, int32_t *res_ret,
                                       uint32_t *res_produced, uint32_t *res_check, ZsLzParams P,
-                                      cudaEvent_t ev_after_block, cudaEvent_t ev_after_offset)
+                                      cudaEvent_t ev_after_block, cudaEvent_t ev_after_offset,
+                                      uint32_t nchunks, void *blk_meta_v, unsigned long long *blk_bitoff_v)
 {
     if (nblk_slots == 0 || nstreams == 0) return cudaSuccess;
-    zs_block_kernel<<<nblk_slots, ZB_THREADS, 0, st>>>(chunks, blk_chunk, sym, chunk_nsym, blk_in_start, blocks, P);
+    uint4 *blk_meta = reinterpret_cast<uint4 *>(blk_meta_v);
+    uint64_t *blk_bitoff = reinterpret_cast<uint64_t *>(blk_bitoff_v);
+    zs_block_kernel<<<nblk_slots, ZB_THREADS, 0, st>>>(chunks, blk_chunk, sym, chunk_nsym, blk_in_start, blocks, blk_meta, P);
     if (ev_after_block) cudaEventRecord(ev_after_block, st);
-    zs_offset_kernel<<<nstreams, ZO_THREADS, 0, st>>>(streams, chunks, blk_chunk, blocks, adler_acc,
-                                                      reinterpret_cast<uint32_t *>(comp), res_ret, res_produced, res_check, P);
+    zs_stored_merge_kernel<<<(nchunks + ZM_THREADS - 1) / ZM_THREADS, ZM_THREADS, 0, st>>>(chunks, nchunks, blocks, blk_meta);
+    /* few streams with many blocks each: wide CTAs; many small streams: narrow ones */
+    const uint32_t othreads = (nblk_slots / nstreams >= 1024u) ? ZO_THREADS_MAX : 128u;
+    zs_offset_kernel<<<nstreams, othreads, 0, st>>>(streams, blk_meta, blk_bitoff, adler_acc,
+                                                    reinterpret_cast<uint32_t *>(comp), res_ret, res_produced, res_check, P);
     if (ev_after_offset) cudaEventRecord(ev_after_offset, st);
     cudaFuncSetAttribute(zs_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ZeSmem));
-    zs_encode_kernel<<<nblk_slots, ZE_THREADS, sizeof(ZeSmem), st>>>(blocks, blk_chunk, chunks, sym, raw, comp, res_check, P);
+    cudaFuncSetAttribute(zs_encode_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+    zs_encode_kernel<<<nblk_slots, ZE_THREADS, sizeof(ZeSmem), st>>>(blocks, blk_chunk, chunks, sym, raw, comp, res_check, blk_meta, blk_bitoff, P);
     return cudaGetLastError();
 }

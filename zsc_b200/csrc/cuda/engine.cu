@@ -15,7 +15,8 @@ extern "C" cudaError_t zs_lz_launch(cudaStream_t, int, uint32_t, const uint8_t *
 extern "C" uint32_t zs_lz_fast_max_dist(void);
 extern "C" cudaError_t zs_huff_launch(cudaStream_t, uint32_t, uint32_t, const ZsChunk *, const uint32_t *, const ZsStream *, const uint32_t *,
                                       const uint32_t *, const uint32_t *, zh_block *, const ZsAdlerAcc *, const uint8_t *, uint8_t *,
-                                      int32_t *, uint32_t *, uint32_t *, ZsLzParams, cudaEvent_t, cudaEvent_t);
+                                      int32_t *, uint32_t *, uint32_t *, ZsLzParams, cudaEvent_t, cudaEvent_t,
+                                      uint32_t, void *, unsigned long long *);
 extern "C" cudaError_t zs_adler_chunks_launch(cudaStream_t, uint32_t, const uint8_t *, const ZsChunk *, const ZsStream *, ZsAdlerAcc *);
 extern "C" cudaError_t zs_adler_flat_launch(cudaStream_t, const uint8_t *, uint64_t, ZsAdlerAcc *, int);
 extern "C" cudaError_t zs_crc_init_launch(cudaStream_t);
@@ -40,6 +41,8 @@ struct zscgpu_engine {
     uint32_t *h_blk_chunk, *d_blk_chunk;
     uint32_t *d_chunk_nsym, *d_blk_in_start;
     zh_block *d_blocks;
+    uint4 *d_blk_meta;            /* per block slot: type, body_bits, in_len, flags (what the offset pass reads) */
+    unsigned long long *d_blk_bitoff;
     ZsAdlerAcc *d_adler;              /* per stream; slot max_streams is the flat-checksum slot */
     uint32_t *d_crc;                  /* [2] */
     uint32_t *d_aux;                  /* inflate: [2 * max_streams] trailer check + flags */
@@ -133,6 +136,8 @@ extern "C" int zscgpu_init(const zscgpu_config *cfg_in, zscgpu_engine **out)
     ZS_CUDA_CHECK(zs_dev(&e->d_chunk_nsym, cfg.max_chunks));
     ZS_CUDA_CHECK(zs_dev(&e->d_blk_in_start, e->blk_cap + 1));
     ZS_CUDA_CHECK(zs_dev(&e->d_blocks, e->blk_cap));
+    ZS_CUDA_CHECK(zs_dev(&e->d_blk_meta, e->blk_cap));
+    ZS_CUDA_CHECK(zs_dev(&e->d_blk_bitoff, e->blk_cap));
     ZS_CUDA_CHECK(zs_dev(&e->d_adler, cfg.max_streams + 1));
     ZS_CUDA_CHECK(zs_dev(&e->d_crc, 4));
     ZS_CUDA_CHECK(zs_dev(&e->d_aux, 2ull * cfg.max_streams));
@@ -163,7 +168,7 @@ extern "C" void zscgpu_destroy(zscgpu_engine *e)
     cudaFreeHost(e->h_chunks); cudaFree(e->d_chunks);
     cudaFreeHost(e->h_streams); cudaFree(e->d_streams);
     cudaFreeHost(e->h_blk_chunk); cudaFree(e->d_blk_chunk);
-    cudaFree(e->d_chunk_nsym); cudaFree(e->d_blk_in_start); cudaFree(e->d_blocks);
+    cudaFree(e->d_chunk_nsym); cudaFree(e->d_blk_in_start); cudaFree(e->d_blocks); cudaFree(e->d_blk_meta); cudaFree(e->d_blk_bitoff);
     cudaFree(e->d_adler); cudaFree(e->d_crc); cudaFree(e->d_aux); cudaFree(e->d_icold);
     cudaFree(e->d_ret); cudaFree(e->d_produced); cudaFree(e->d_consumed); cudaFree(e->d_check);
     cudaFreeHost(e->h_ret); cudaFreeHost(e->h_produced); cudaFreeHost(e->h_consumed); cudaFreeHost(e->h_check);
@@ -390,12 +395,12 @@ static int zs_deflate_launch_all(zscgpu_engine *e)
     ZS_CUDA_CHECK(cudaEventRecord(e->ev[10], e->stream));
     ZS_CUDA_CHECK(zs_huff_launch(e->stream, nb, n, e->d_chunks, e->d_blk_chunk, e->d_streams, e->d_sym, e->d_chunk_nsym,
                                  e->d_blk_in_start, e->d_blocks, e->d_adler, e->d_raw, e->d_comp, e->d_ret, e->d_produced, e->d_check, e->last_lz,
-                                 e->ev[11], e->ev[12]));
+                                 e->ev[11], e->ev[12], nc, e->d_blk_meta, e->d_blk_bitoff));
     ZS_CUDA_CHECK(cudaEventRecord(e->ev[13], e->stream));
     ZS_CUDA_CHECK(cudaMemcpyAsync(e->h_ret, e->d_ret, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, e->stream));
     ZS_CUDA_CHECK(cudaMemcpyAsync(e->h_produced, e->d_produced, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, e->stream));
     ZS_CUDA_CHECK(cudaMemcpyAsync(e->h_check, e->d_check, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, e->stream));
-    e->launches = 5;   /* adler, lz, block, offset, encode */
+    e->launches = 6;   /* adler, lz, block, stored-run merge, offset, encode */
     return ZSCGPU_OK;
 }
 
