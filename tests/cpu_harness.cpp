@@ -194,7 +194,7 @@ uint32_t h_deflate_model(const uint8_t *src, uint32_t n, uint32_t max_block_len,
     LzP P{params[0], params[1], params[2], params[3], params[4], params[5]};
     const int force = params[6], wrap = params[7];
     const uint32_t zhdr = (uint32_t)params[8];
-    const uint32_t BS = 8192, CHUNK = 262144;
+    const uint32_t BS = getenv("ZS_TEST_BS") ? (uint32_t)atoi(getenv("ZS_TEST_BS")) : 8192, CHUNK = 262144;
     BitW bw;
     uint32_t adler = adler32_ref(src, n);
     // positions are modelled with the source at a 16-byte aligned address

@@ -13,5 +13,5 @@ st = Engine.make_streams([0], [n], [0], [n + (n >> 3)])
 E.deflate_enqueue(st, 262144, level)
 r = E.fetch(1)[0]
 E.event(0); E.relaunch(); E.event(1); E.sync()
-print("ret", r.ret, "produced", r.produced, "ms", E.elapsed_ms(0, 1), "lz_ms", E.elapsed_ms(9, 10), "GB/s", n / 1e6 / E.elapsed_ms(0, 1))
+print("ret", r.ret, "produced", r.produced, "ms", E.elapsed_ms(0, 1), "lz_ms", E.elapsed_ms(9, 10), "block_ms", E.elapsed_ms(10, 11), "offs_ms", E.elapsed_ms(11, 12), "enc_ms", E.elapsed_ms(12, 13), "GB/s", n / 1e6 / E.elapsed_ms(0, 1))
 E.close()

@@ -39,7 +39,7 @@ zs_block_kernel(const ZsChunk *__restrict__ chunks, const uint32_t *__restrict__
                 const uint32_t *__restrict__ blk_in_start, zh_block *__restrict__ blocks,
                 uint4 *__restrict__ blk_meta, ZsLzParams P)
 {
-    __shared__ ZbSmem S;
+    __shared__ __align__(16) ZbSmem S;
     const uint32_t b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t c = blk_chunk[b];
     const ZsChunk cd = chunks[c];
@@ -57,13 +57,38 @@ zs_block_kernel(const ZsChunk *__restrict__ chunks, const uint32_t *__restrict__
     if (tid < 16) { S.bl_count[tid] = 0; S.cnt_l[tid] = 0; S.cnt_d[tid] = 0; }
     if (tid == 0) { S.m = 0; S.max_l = 0; S.overflow = 0; }
     __syncthreads();
-    for (uint32_t i = tid; i < cnt; i += ZB_THREADS) {
-        uint32_t s = bs[i];
-        if (s & ZS_MATCH) {
-            atomicAdd(&S.lfreq[warp][257 + zs_len_code((s >> 16) & 0xFF)], 1u);
-            atomicAdd(&S.dfreq[warp][zs_dist_code(s & 0x7FFF)], 1u);
-        } else {
-            atomicAdd(&S.lfreq[warp][s & 0xFF], 1u);
+    /* four 16-byte loads in flight per thread, then branch-light counting (the symbol arena is 16-byte
+       aligned per block: sym_off and ZS_BLOCK_SYMS are multiples of four) */
+    {
+        const uint4 *bs4 = reinterpret_cast<const uint4 *>(bs);
+        for (uint32_t i0 = tid * 4; i0 < cnt; i0 += ZB_THREADS * 16) {
+            uint4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const uint32_t i = i0 + (uint32_t)u * ZB_THREADS * 4;
+                v[u] = make_uint4(0, 0, 0, 0);
+                if (i < cnt) v[u] = __ldg(bs4 + (i >> 2));
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const uint32_t i = i0 + (uint32_t)u * ZB_THREADS * 4;
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    const uint32_t sv = e == 0 ? v[u].x : e == 1 ? v[u].y : e == 2 ? v[u].z : v[u].w;
+                    if (i + (uint32_t)e < cnt) {
+                        const bool mt = (sv & ZS_MATCH) != 0;
+                        const uint32_t lc = (sv >> 16) & 0xFFu, d = sv & 0x7FFFu;
+                        const uint32_t nl_ = 31u - (uint32_t)__clz((int)(lc | 4u));
+                        uint32_t lcode = ((nl_ - 1u) << 2) | ((lc >> (nl_ - 2u)) & 3u);
+                        lcode = lc < 4u ? lc : (lc == 255u ? 28u : lcode);
+                        const uint32_t nd_ = 31u - (uint32_t)__clz((int)(d | 2u));
+                        uint32_t dcode = (nd_ << 1) | ((d >> (nd_ - 1u)) & 1u);
+                        dcode = d < 2u ? d : dcode;
+                        atomicAdd(&S.lfreq[warp][mt ? 257u + lcode : (sv & 0xFFu)], 1u);
+                        if (mt) atomicAdd(&S.dfreq[warp][dcode], 1u);
+                    }
+                }
+            }
         }
     }
     __syncthreads();
@@ -88,12 +113,24 @@ zs_block_kernel(const ZsChunk *__restrict__ chunks, const uint32_t *__restrict__
     /* ---- rank sort of the keys (unique) on all threads; the distance tree meanwhile on one thread ---- */
     {
         uint32_t *sorted = S.sc.w + ZH_LCODES_PAD;          /* free until the merge starts */
-        for (int i = (int)tid; i < m; i += ZB_THREADS) {
-            const uint32_t key = S.sc.key[i];
-            int rank = 0;
-            for (int j = 0; j < m; j++) rank += (S.sc.key[j] < key) ? 1 : 0;
-            sorted[rank] = key;
+        /* a thread ranks its (up to three) keys in one sweep over the key array, four keys per load */
+        static_assert(ZH_LCODES_PAD <= 3 * ZB_THREADS && ZH_LCODES_PAD % 4 == 0, "rank sort covers three keys per thread");
+        for (int i = m + (int)tid; i < ((m + 3) & ~3); i += ZB_THREADS) S.sc.key[i] = 0xFFFFFFFFu;   /* pad to a multiple of 4 */
+        __syncthreads();
+        const uint32_t k0 = (int)tid < m ? S.sc.key[tid] : 0u;
+        const uint32_t k1 = (int)tid + ZB_THREADS < m ? S.sc.key[tid + ZB_THREADS] : 0u;
+        const uint32_t k2 = (int)tid + 2 * ZB_THREADS < m ? S.sc.key[tid + 2 * ZB_THREADS] : 0u;
+        uint32_t r0 = 0, r1 = 0, r2 = 0;
+        const uint4 *k4 = reinterpret_cast<const uint4 *>(S.sc.key);
+        for (int j = 0; j < (m + 3) >> 2; j++) {
+            const uint4 q = k4[j];
+            r0 += (q.x < k0) + (q.y < k0) + (q.z < k0) + (q.w < k0);
+            r1 += (q.x < k1) + (q.y < k1) + (q.z < k1) + (q.w < k1);
+            r2 += (q.x < k2) + (q.y < k2) + (q.z < k2) + (q.w < k2);
         }
+        if ((int)tid < m) sorted[r0] = k0;
+        if ((int)tid + ZB_THREADS < m) sorted[r1] = k1;
+        if ((int)tid + 2 * ZB_THREADS < m) sorted[r2] = k2;
         __syncthreads();
         for (int i = (int)tid; i < m; i += ZB_THREADS) S.sc.key[i] = sorted[i];
     }
