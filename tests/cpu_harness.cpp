@@ -21,6 +21,17 @@ int h_inflate(const uint8_t *in, uint32_t in_len, uint8_t *out, uint32_t out_cap
     return r.ret;
 }
 
+// the warp-per-stream form of the decoder (zi_sym_batch + cooperative writes), run serially
+int h_inflate_batched(const uint8_t *in, uint32_t in_len, uint8_t *out, uint32_t out_cap, int wrap, uint32_t *res7, uint32_t group)
+{
+    zi_tables T;
+    zi_result r;
+    zi_inflate_batched(in, in_len, out, out_cap, wrap, &T, &r, group);
+    res7[0] = (uint32_t)r.ret; res7[1] = (uint32_t)r.reason; res7[2] = r.produced; res7[3] = r.consumed;
+    res7[4] = r.data_errors; res7[5] = r.stored_check; res7[6] = r.have_check;
+    return r.ret;
+}
+
 // ---------------------------------------------------------------- LZ77 model (mirrors deflate_lz.cu)
 struct LzP { int mode, chain, nice, lazy, min_len, max_dist; };
 static const uint32_t TILE = 2048, WINDOW = 32768, NOHASH = 0xFFFF;

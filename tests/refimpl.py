@@ -56,6 +56,7 @@ def harness():
     if _har is None:
         L = C.CDLL(HARNESS_PATH, mode=C.RTLD_LOCAL)
         L.h_inflate.argtypes = [u8p, C.c_uint32, u8p, C.c_uint32, C.c_int, u32p]
+        L.h_inflate_batched.argtypes = [u8p, C.c_uint32, u8p, C.c_uint32, C.c_int, u32p, C.c_uint32]
         L.h_deflate_model.argtypes = [u8p, C.c_uint32, C.c_uint32, C.POINTER(C.c_int32), u8p, C.c_uint32, u32p, C.c_uint32, u32p]
         L.h_deflate_model.restype = C.c_uint32
         _har = L
@@ -69,6 +70,13 @@ def h_inflate(comp, cap, wrap=1):
     out = np.zeros(max(cap, 1), dtype=np.uint8)
     res = (C.c_uint32 * 7)()
     harness().h_inflate(padded.ctypes.data_as(u8p), len(comp), out.ctypes.data_as(u8p), cap, wrap, res)
+    # the group form of the same decoder (fast batch decode + generic steps) must agree in every field and byte
+    for group in (32, 8):
+        out2 = np.zeros(max(cap, 1), dtype=np.uint8)
+        res2 = (C.c_uint32 * 7)()
+        harness().h_inflate_batched(padded.ctypes.data_as(u8p), len(comp), out2.ctypes.data_as(u8p), cap, wrap, res2, group)
+        assert list(res) == list(res2), (group, list(res), list(res2))
+        assert np.array_equal(out[:res[2]], out2[:res2[2]])
     ret = C.c_int32(res[0]).value
     return ret, out[:res[2]].copy(), dict(reason=res[1], produced=res[2], consumed=res[3], data_errors=res[4],
                                           stored_check=res[5], have_check=res[6])

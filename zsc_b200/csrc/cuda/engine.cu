@@ -13,6 +13,8 @@
 /* kernel launchers (deflate_lz.cu, deflate_huff.cu, checksum.cu, inflate.cu) */
 extern "C" cudaError_t zs_lz_launch(cudaStream_t, int, uint32_t, const uint8_t *, const ZsChunk *, uint32_t *, uint32_t *, uint32_t *, ZsLzParams);
 extern "C" uint32_t zs_lz_fast_max_dist(void);
+extern "C" size_t zs_inflate_cold_bytes(void);
+extern "C" size_t zs_inflate_table_bytes(void);
 extern "C" cudaError_t zs_huff_launch(cudaStream_t, uint32_t, uint32_t, const ZsChunk *, const uint32_t *, const ZsStream *, const uint32_t *,
                                       const uint32_t *, const uint32_t *, zh_block *, const ZsAdlerAcc *, const uint8_t *, uint8_t *,
                                       int32_t *, uint32_t *, uint32_t *, ZsLzParams, cudaEvent_t, cudaEvent_t,
@@ -141,7 +143,7 @@ extern "C" int zscgpu_init(const zscgpu_config *cfg_in, zscgpu_engine **out)
     ZS_CUDA_CHECK(zs_dev(&e->d_adler, cfg.max_streams + 1));
     ZS_CUDA_CHECK(zs_dev(&e->d_crc, 4));
     ZS_CUDA_CHECK(zs_dev(&e->d_aux, 2ull * cfg.max_streams));
-    ZS_CUDA_CHECK(zs_dev(&e->d_icold, (640ull + 1280ull) * cfg.max_streams + 4096));   /* cold arrays, then decode tables */
+    ZS_CUDA_CHECK(zs_dev(&e->d_icold, (zs_inflate_cold_bytes() + zs_inflate_table_bytes()) * (size_t)cfg.max_streams + 4096));   /* cold arrays, then decode tables */
     ZS_CUDA_CHECK(zs_dev(&e->d_ret, cfg.max_streams));
     ZS_CUDA_CHECK(zs_dev(&e->d_produced, cfg.max_streams));
     ZS_CUDA_CHECK(zs_dev(&e->d_consumed, cfg.max_streams));
@@ -423,7 +425,7 @@ static int zs_inflate_launch_all(zscgpu_engine *e)
 {
     const uint32_t n = e->last_nstreams;
     ZS_CUDA_CHECK(zs_inflate_launch(e->stream, n, e->d_streams, e->d_comp, e->d_raw, e->last_wrap, e->d_ret, e->d_produced, e->d_consumed, e->d_check,
-                                    e->d_aux, e->d_adler, e->last_max_raw, e->d_icold, 640ull * e->cfg.max_streams));
+                                    e->d_aux, e->d_adler, e->last_max_raw, e->d_icold, (unsigned long long)zs_inflate_cold_bytes() * e->cfg.max_streams));
     ZS_CUDA_CHECK(cudaMemcpyAsync(e->h_ret, e->d_ret, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, e->stream));
     ZS_CUDA_CHECK(cudaMemcpyAsync(e->h_produced, e->d_produced, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, e->stream));
     ZS_CUDA_CHECK(cudaMemcpyAsync(e->h_consumed, e->d_consumed, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, e->stream));

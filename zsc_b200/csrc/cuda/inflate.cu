@@ -9,8 +9,15 @@
  */
 #include "common.cuh"
 #include "inflate_core.h"
+#include <stdlib.h>
 
 #define ZI_THREADS 32
+#ifndef ZS_INFLATE_GROUP
+#define ZS_INFLATE_GROUP 32                      /* lanes per stream in the group kernel: 32, 16 or 8 */
+#endif
+#ifndef ZS_INFLATE_LOCKSTEP_MIN
+#define ZS_INFLATE_LOCKSTEP_MIN 0xFFFFFFFFu      /* streams in a batch from which the thread-per-stream kernel is used */
+#endif
 
 __global__ void __launch_bounds__(ZI_THREADS)
 zs_inflate_kernel(uint32_t n, const ZsStream *__restrict__ streams, const uint8_t *__restrict__ comp,
@@ -49,6 +56,160 @@ zs_inflate_kernel(uint32_t n, const ZsStream *__restrict__ streams, const uint8_
     aux[2 * s + 1] = m.res.have_check | (m.res.data_errors ? 2u : 0u);
 }
 
+/* ======================= a group of G lanes per stream ======================= */
+/* The leader lane of a group runs the state machine.  Inside a compressed block it decodes up to G symbols
+ * into a record queue with zw_fast_decode — a pure accelerator: it only takes symbols whose codes resolve
+ * from the stream's shared-memory tables and that are valid, fit the output and cannot run past the input;
+ * at anything else (end of block, a bad code, the last bytes of a buffer) it stops in front of that symbol
+ * without consuming it and the generic zi_step, the code the CPU tests pin against the reference, takes
+ * over for one step.  The G lanes then write the batch together (zw_emit).  Groups of one warp synchronise
+ * with their own lane masks only, so they progress independently.  G = 32 is one warp per stream. */
+#define ZW_THREADS 128
+
+struct ZwLut { uint32_t len[32]; uint32_t dist[32]; };     /* base | extra bits << 16 (RFC 1951 3.2.5) */
+
+template <int G> struct ZwStream {
+    zi_tables T;
+    zi_aux X;
+    zi_fast F;
+    uint32_t q[G];
+};
+
+/* The records of one batch written by the G lanes of a group: output offsets from a prefix sum of the
+ * lengths, all literals at once, every match that reads nothing of this batch by its own lane, then the
+ * remaining matches in order, each copied by all lanes (distances shorter than the copy repeat their pattern;
+ * a copy longer than its distance >= G proceeds in G-byte steps that read what the previous step wrote). */
+template <int G>
+__device__ __forceinline__ void zw_emit(uint8_t *out, uint32_t base, const uint32_t *q, uint32_t n, uint32_t gl, uint32_t gmask, uint32_t gshift)
+{
+    const uint32_t r = gl < n ? q[gl] : 0u;
+    const bool is_match = gl < n && (r >> 31);
+    const uint32_t olen = gl < n ? (is_match ? ((r >> 16) & 0xFFu) + 3u : 1u) : 0u;
+    uint32_t inc = olen;
+#pragma unroll
+    for (int o = 1; o < G; o <<= 1) { const uint32_t t = __shfl_up_sync(gmask, inc, o, G); if ((int)gl >= o) inc += t; }
+    const uint32_t pos = inc - olen;
+    if (gl < n && !is_match) out[base + pos] = (uint8_t)r;
+    /* matches whose source lies entirely before this batch's output depend on nothing written here: every
+       lane copies its own, all at once (most matches of a batch; their lengths are short) */
+    const uint32_t dist = (r & 0x7FFFu) + 1u;
+    const bool own = is_match && dist >= pos + olen && olen <= 32u;
+    if (own) {
+        uint8_t *dst = out + base + pos;
+        const uint8_t *src = dst - dist;
+        for (uint32_t k = 0; k < olen; k++) dst[k] = src[k];
+    }
+    uint32_t mm = __ballot_sync(gmask, is_match && !own) >> gshift;
+    __syncwarp(gmask);
+    while (mm) {
+        const int j = __ffs((int)mm) - 1;
+        mm &= mm - 1;
+        const uint32_t p = base + __shfl_sync(gmask, pos, j, G);
+        const uint32_t L = __shfl_sync(gmask, olen, j, G);
+        const uint32_t D = (__shfl_sync(gmask, r, j, G) & 0x7FFFu) + 1u;
+        uint8_t *dst = out + p;
+        const uint8_t *src = dst - D;
+        if (D >= L) {
+            for (uint32_t k = gl; k < L; k += G) dst[k] = src[k];
+        } else if (D >= (uint32_t)G) {
+            for (uint32_t k0 = 0; k0 < L; k0 += G) {
+                const uint32_t k = k0 + gl;
+                if (k < L) dst[k] = src[k];
+                __syncwarp(gmask);
+            }
+        } else {
+            uint32_t k = gl, km = gl % D;
+            const uint32_t step = (uint32_t)G % D;
+            for (; k < L; k += G) { dst[k] = src[km]; km += step; if (km >= D) km -= D; }
+        }
+        __syncwarp(gmask);
+    }
+}
+
+template <int G>
+__global__ void __launch_bounds__(ZW_THREADS, 8)
+zs_inflate_group_kernel(uint32_t n, const ZsStream *__restrict__ streams, const uint8_t *__restrict__ comp,
+                        uint8_t *__restrict__ raw, int32_t wrap, int32_t *__restrict__ ret,
+                        uint32_t *__restrict__ produced, uint32_t *__restrict__ consumed,
+                        uint32_t *__restrict__ aux /* [2n]: stored check, flags */)
+{
+    constexpr int GROUPS = ZW_THREADS / G;
+    extern __shared__ __align__(16) unsigned char zw_smem_raw[];
+    ZwStream<G> *W = reinterpret_cast<ZwStream<G> *>(zw_smem_raw);
+    ZwLut &lut = *reinterpret_cast<ZwLut *>(zw_smem_raw + sizeof(ZwStream<G>) * GROUPS);
+    if (threadIdx.x < 29) {
+        const uint32_t c = threadIdx.x;
+        lut.len[c] = zi_lut_len(c);
+    }
+    if (threadIdx.x >= 32 && threadIdx.x < 62) {
+        const uint32_t d = threadIdx.x - 32;
+        lut.dist[d] = zi_lut_dist(d);
+    }
+    __syncthreads();
+    const uint32_t g = threadIdx.x / G, gl = threadIdx.x % G;
+    const uint32_t gshift = (threadIdx.x & 31u) - gl;                      /* first lane of the group within its warp */
+    const uint32_t gmask = (G == 32 ? 0xFFFFFFFFu : ((1u << (G & 31)) - 1u) << gshift);
+    const uint32_t s = blockIdx.x * GROUPS + g;
+    if (s >= n) return;
+    ZwStream<G> &w = W[g];
+    const ZsStream st = streams[s];
+    const uint8_t *in = comp + st.comp_off;
+    uint8_t *out = raw + st.raw_off;
+    zi_mach m;
+    zi_m_init(&m, in, st.comp_cap, out, st.raw_len, wrap, &w.T, &w.X, &w.F);
+    for (;;) {
+        const int state = __shfl_sync(gmask, m.state, 0, G);
+        if (state == ZM_DONE) break;
+        if (state == ZM_SYM) {
+            uint32_t cnt = 0, base = 0, vop = 0;
+            if (gl == 0) { base = m.io.op; cnt = zi_fast_batch(&m, lut.len, lut.dist, w.q, G, &vop); }
+            cnt = __shfl_sync(gmask, cnt, 0, G);
+            base = __shfl_sync(gmask, base, 0, G);
+            if (cnt) {
+                __syncwarp(gmask);                           /* the leader's queue writes are visible to the group */
+                zw_emit<G>(out, base, w.q, cnt, gl, gmask, gshift);
+                if (gl == 0) m.io.op = vop;
+            }
+            if (cnt < (uint32_t)G) {
+                /* the fast decoder stopped in front of something: one generic step */
+                if (gl == 0) zi_step(&m);
+                __syncwarp(gmask);
+            }
+        } else if (state == ZM_STORED) {
+            uint32_t cnt = 0, from = 0, to = 0;
+            if (gl == 0) { cnt = zi_stored_plan(&m); from = m.io.ip; to = m.io.op; }
+            cnt = __shfl_sync(gmask, cnt, 0, G);
+            from = __shfl_sync(gmask, from, 0, G);
+            to = __shfl_sync(gmask, to, 0, G);
+            for (uint32_t k = gl; k < cnt; k += G) out[to + k] = in[from + k];
+            __syncwarp(gmask);
+            if (gl == 0) zi_stored_done(&m, cnt);
+        } else {
+            if (gl == 0) zi_step(&m);
+            __syncwarp(gmask);
+        }
+    }
+    if (gl == 0) {
+        ret[s] = m.res.ret;
+        produced[s] = m.res.produced;
+        consumed[s] = m.res.consumed;
+        aux[2 * s] = m.res.stored_check;
+        aux[2 * s + 1] = m.res.have_check | (m.res.data_errors ? 2u : 0u);
+    }
+}
+
+template <int G>
+static cudaError_t zs_inflate_group_launch(cudaStream_t st, uint32_t n, const ZsStream *streams, const uint8_t *comp, uint8_t *raw, int32_t wrap,
+                                           int32_t *ret, uint32_t *produced, uint32_t *consumed, uint32_t *aux)
+{
+    constexpr int GROUPS = ZW_THREADS / G;
+    const size_t smem = sizeof(ZwStream<G>) * GROUPS + sizeof(ZwLut);
+    cudaFuncSetAttribute(zs_inflate_group_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(zs_inflate_group_kernel<G>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+    zs_inflate_group_kernel<G><<<(n + GROUPS - 1) / GROUPS, ZW_THREADS, smem, st>>>(n, streams, comp, raw, wrap, ret, produced, consumed, aux);
+    return cudaGetLastError();
+}
+
 __global__ void zs_inflate_check_kernel(uint32_t n, const ZsAdlerAcc *__restrict__ acc, const uint32_t *__restrict__ produced,
                                         const uint32_t *__restrict__ aux, int32_t wrap, int32_t *__restrict__ ret,
                                         uint32_t *__restrict__ check)
@@ -65,6 +226,9 @@ __global__ void zs_inflate_check_kernel(uint32_t n, const ZsAdlerAcc *__restrict
 extern "C" cudaError_t zs_adler_streams_launch(cudaStream_t st, uint32_t n, uint32_t max_len, const uint8_t *raw,
                                                const ZsStream *streams, const uint32_t *produced, ZsAdlerAcc *acc);
 
+extern "C" size_t zs_inflate_cold_bytes(void) { return sizeof(zi_aux); }
+extern "C" size_t zs_inflate_table_bytes(void) { return sizeof(zi_tables); }
+
 extern "C" cudaError_t zs_inflate_launch(cudaStream_t st, uint32_t n, const ZsStream *streams, const uint8_t *comp,
                                          uint8_t *raw, int32_t wrap, int32_t *ret, uint32_t *produced,
                                          uint32_t *consumed, uint32_t *check, uint32_t *aux, ZsAdlerAcc *acc,
@@ -77,6 +241,15 @@ extern "C" cudaError_t zs_inflate_launch(cudaStream_t st, uint32_t n, const ZsSt
 #else
     const size_t smem = 0;
 #endif
+    /* One warp per stream unless the batch is so wide that one thread per stream fills the machine better
+       (the lockstep kernel needs on the order of 10^5 streams in flight). */
+    static int grp = getenv("ZSC_INFLATE_GROUP") ? atoi(getenv("ZSC_INFLATE_GROUP")) : ZS_INFLATE_GROUP;   /* TEMP experiment knob */
+    if (grp != 0 && n < ZS_INFLATE_LOCKSTEP_MIN) {
+        cudaError_t ce = grp == 32 ? zs_inflate_group_launch<32>(st, n, streams, comp, raw, wrap, ret, produced, consumed, aux)
+                       : grp == 16 ? zs_inflate_group_launch<16>(st, n, streams, comp, raw, wrap, ret, produced, consumed, aux)
+                                                : zs_inflate_group_launch<8>(st, n, streams, comp, raw, wrap, ret, produced, consumed, aux);
+        if (ce != cudaSuccess) return ce;
+    } else
     zs_inflate_kernel<<<(n + ZI_THREADS - 1) / ZI_THREADS, ZI_THREADS, smem, st>>>(n, streams, comp, raw, wrap, ret, produced, consumed, aux, reinterpret_cast<zi_aux *>(cold), reinterpret_cast<zi_tables *>(reinterpret_cast<uint8_t *>(cold) + (size_t)tabs_off));
     cudaMemsetAsync(acc, 0, sizeof(ZsAdlerAcc) * n, st);
     cudaError_t ce = zs_adler_streams_launch(st, n, max_raw_len, raw, streams, produced, acc);

@@ -9,10 +9,10 @@
  * straight out of the output buffer, as the reference itself does on that path, src/inflate.c:1380).
  *
  * The decode tables are NOT the reference's op/bits/val two-level tables: each alphabet gets one
- * direct-lookup table of 16-bit entries (9 / 6 index bits) plus the canonical-code arrays
+ * direct-lookup table of 16-bit entries (10 / 8 index bits) plus the canonical-code arrays
  * (symbols sorted by length, per-length counts) that resolve the rare longer codes by
- * first-code comparison.  That keeps a stream's tables under 2 KiB so that 32 streams fit in one
- * warp's shared memory.
+ * first-code comparison.  That keeps a stream's tables at 3.6 KiB, so that every warp of an SM can hold its
+ * stream's tables in shared memory.
  *
  * Error behaviour follows the reference: any malformed header, code set, code, distance or
  * data check yields Z_DATA_ERROR (-3); running out of output room or input yields Z_BUF_ERROR (-5).
@@ -30,8 +30,8 @@
 #define ZID static inline
 #endif
 
-#define ZI_LBITS 9
-#define ZI_DBITS 6
+#define ZI_LBITS 10
+#define ZI_DBITS 8
 
 #define ZI_OK 0
 #define ZI_NEED_DICT 2
@@ -46,16 +46,18 @@ enum {
     ZI_E_INPUT_END, ZI_E_OUTPUT_FULL, ZI_E_NEED_DICT
 };
 
-typedef struct {                     /* hot: shared memory on the GPU, 1216 bytes per stream */
+typedef struct {                     /* hot: 2640 bytes per stream */
     uint16_t lit[1 << ZI_LBITS];     /* sym | len << 9 ; 0 = code longer than ZI_LBITS */
     uint16_t dist[1 << ZI_DBITS];    /* sym | len << 5 ; 0 = longer */
     uint16_t lcount[16];
     uint16_t dcount[16];
+    uint32_t lfirst, lindex, dfirst, dindex;   /* where zi_decode's canonical walk stands after the lengths the direct
+                                                  tables resolve (set with the tables; read by zi_fast_batch) */
 } zi_tables;
 
 typedef struct {                     /* first-level tables: shared memory on the GPU, 384 bytes per stream */
     uint16_t lit7[128];              /* literal/length codes of <= 7 bits, indexed by 7 bits; 0 = look further */
-    uint16_t dist6[64];              /* copy of zi_tables.dist */
+    uint16_t dist6[64];              /* distance codes of <= 6 bits, indexed by 6 bits; 0 = look further */
 } zi_fast;
 
 typedef struct {                     /* cold: only the rare codes longer than the direct tables read these
@@ -223,6 +225,14 @@ ZID int zi_decode(zi_io *io, const uint16_t *table, int tbits, const uint16_t *s
     return -1;
 }
 
+/* where zi_decode's canonical walk stands after the code lengths a direct table of tbits resolves */
+ZID void zi_walk_start(const uint16_t *count, int tbits, uint32_t *first_out, uint32_t *index_out)
+{
+    uint32_t first = 0, index = 0;
+    for (int k = 1; k <= tbits; k++) { const uint32_t c = count[k]; index += c; first = (first + c) << 1; }
+    *first_out = first; *index_out = index;
+}
+
 ZID int zi_fail(zi_result *r, int ret, int reason)
 {
     if (r->reason == ZI_E_NONE) r->reason = reason;
@@ -287,7 +297,8 @@ ZID int zi_block_head(zi_io *io, zi_tables *T, zi_aux *X, zi_fast *F, zi_result 
                 for (uint32_t i = 0; i < ncode; i++) { zi_refill(io); cl[order[i]] = (uint8_t)zi_take(io, 3); }
                 if (zi_overrun(io)) return zi_fail(res, ZI_BUF_ERROR, ZI_E_INPUT_END);
                 /* code-length code: a 7-bit direct table (128 entries) in the upper half of the literal
-                   table, which is dead until this header has been parsed (lens uses its first 320 bytes) */
+                   table (entries 256..383), which is dead until this header has been parsed (lens uses its
+                   first 320 bytes) */
                 uint16_t *cltab = T->lit + 256;
                 uint16_t clsorted[19], clcount[16];
                 if (zi_build(cl, 19, 7, cltab, clsorted, clcount, 5, 0)) return zi_fail(res, ZI_DATA_ERROR, ZI_E_CODELEN_SET);
@@ -342,7 +353,9 @@ ZID int zi_block_head(zi_io *io, zi_tables *T, zi_aux *X, zi_fast *F, zi_result 
     }
     /* first-level copies of the short codes */
     for (int i = 0; i < 128; i++) { uint16_t e = T->lit[i]; F->lit7[i] = (e && (e >> 9) <= 7) ? e : (uint16_t)0; }
-    for (int i = 0; i < 64; i++) F->dist6[i] = T->dist[i];
+    for (int i = 0; i < 64; i++) { uint16_t e = T->dist[i]; F->dist6[i] = (e && (e >> 5) <= 6) ? e : (uint16_t)0; }
+    zi_walk_start(T->lcount, ZI_LBITS, &T->lfirst, &T->lindex);
+    zi_walk_start(T->dcount, ZI_DBITS, &T->dfirst, &T->dindex);
     return ZI_OK;
 }
 
@@ -452,7 +465,7 @@ ZID void zi_step(zi_mach *m)
             zi_refill(io);
             int d;
             {
-                const uint32_t e6 = F->dist6[zi_peek(io, ZI_DBITS)];
+                const uint32_t e6 = F->dist6[zi_peek(io, 6)];
                 if (e6) { zi_drop(io, (int)(e6 >> 5)); d = (int)(e6 & 31u); }
                 else d = zi_decode(io, T->dist, ZI_DBITS, X->dsorted, T->dcount, 5);
             }
@@ -546,6 +559,176 @@ ZID void zi_step(zi_mach *m)
     }
 }
 
+/* ---- batch form of the symbol state: one warp per stream ------------------------------------------
+ * zs_inflate_warp_kernel gives a stream a whole warp: lane 0 runs this state machine, but inside a compressed
+ * block it decodes up to ZI_BATCH symbols into a record queue without touching the output
+ * (zi_sym_batch), and the 32 lanes then write the literals and perform the copies together.  Records use
+ * the LZ kernel's symbol format: literal byte, or bit 31 | (len - 3) << 16 | (dist - 1).
+ *
+ * A symbol only enters a batch when the longest match still fits the output and the longest code cannot run
+ * past the input, so inside a batch the only possible failures are data errors, with exactly the bits
+ * consumed and the output produced that zi_step would have at that point; everything near the ends of the
+ * buffers, and every other state, goes through zi_step itself.  Results are identical by construction and
+ * tests/ runs both forms over the same vectors. */
+#define ZI_BATCH 32
+
+ZID uint32_t zi_sym_batch(zi_mach *m, uint32_t *q, uint32_t *vop)
+{
+    zi_io *io = &m->io;
+    zi_result *res = &m->res;
+    zi_tables *T = m->T;
+    zi_aux *X = m->X;
+    zi_fast *F = m->F;
+    uint32_t n = 0, op = io->op;
+    while (n < ZI_BATCH) {
+        if ((uint64_t)op + 258u > io->out_cap || (uint64_t)io->ip + 16u > io->in_len) break;
+        zi_refill(io);
+        int s;
+        {
+            const uint32_t e7 = F->lit7[zi_peek(io, 7)];
+            if (e7) { zi_drop(io, (int)(e7 >> 9)); s = (int)(e7 & 511u); }
+            else s = zi_decode(io, T->lit, ZI_LBITS, X->lsorted, T->lcount, 9);
+        }
+        if (s < 0) { zi_m_fail(m, zi_fail(res, ZI_DATA_ERROR, ZI_E_LITLEN_CODE), 0); break; }
+        if (s < 256) { q[n++] = (uint32_t)s; op++; continue; }
+        if (s == 256) { m->state = m->last ? ZM_TRAIL : ZM_BLOCK; break; }
+        if (s > 285) { zi_m_fail(m, zi_fail(res, ZI_DATA_ERROR, ZI_E_LITLEN_CODE), 0); break; }
+        uint32_t c = (uint32_t)s - 257, len;
+        if (c < 8) len = 3 + c;
+        else if (c == 28) len = 258;
+        else { uint32_t eb = (c - 4) >> 2; len = 3 + ((4 + (c & 3)) << eb) + zi_take(io, (int)eb); }
+        zi_refill(io);
+        int d;
+        {
+            const uint32_t e6 = F->dist6[zi_peek(io, 6)];
+            if (e6) { zi_drop(io, (int)(e6 >> 5)); d = (int)(e6 & 31u); }
+            else d = zi_decode(io, T->dist, ZI_DBITS, X->dsorted, T->dcount, 5);
+        }
+        if (d < 0 || d > 29) { zi_m_fail(m, zi_fail(res, ZI_DATA_ERROR, ZI_E_DIST_CODE), 0); break; }
+        uint32_t dist;
+        if (d < 4) dist = 1 + (uint32_t)d;
+        else { uint32_t eb = ((uint32_t)d - 2) >> 1; dist = 1 + ((2 + ((uint32_t)d & 1)) << eb) + zi_take(io, (int)eb); }
+        if (dist > op || dist > m->win) { zi_m_fail(m, zi_fail(res, ZI_DATA_ERROR, ZI_E_DIST_TOO_FAR), 0); break; }
+        q[n++] = 0x80000000u | ((len - 3u) << 16) | (dist - 1u);
+        op += len;
+    }
+    *vop = op;
+    return n;
+}
+
+/* ---- the accelerated symbol decoder of the group kernel (zs_inflate_group_kernel) --------------------
+ * base | extra bits << 16 of a length code (0..28) / distance code (0..29), RFC 1951 3.2.5 */
+ZID uint32_t zi_lut_len(uint32_t c)
+{
+    const uint32_t eb = (c < 8 || c == 28) ? 0u : ((c - 4) >> 2);
+    return (c < 8 ? 3u + c : c == 28 ? 258u : 3u + ((4u + (c & 3u)) << eb)) | (eb << 16);
+}
+ZID uint32_t zi_lut_dist(uint32_t d)
+{
+    const uint32_t eb = d < 4 ? 0u : ((d - 2) >> 1);
+    return (d < 4 ? 1u + d : 1u + ((2u + (d & 1u)) << eb)) | (eb << 16);
+}
+ZID uint32_t zi_fast_batch(zi_mach *m, const uint32_t *lut_len, const uint32_t *lut_dist, uint32_t *q, uint32_t maxn, uint32_t *vop)
+{
+    const zi_tables *T = m->T;
+    const uint16_t *lit = T->lit, *dtab = T->dist;
+    uint32_t n = 0, op = m->io.op;
+    /* how many symbols this batch may take: each needs at most 258 bytes of output room and pulls at most
+       8 bytes of input (two refills); the last 16 input bytes are left to zi_step */
+    uint32_t nmax = maxn;
+    {
+        const uint32_t room = m->io.out_cap - op;
+        if (room < nmax * 258u) nmax = room / 258u;
+        const uint64_t need = (uint64_t)m->io.ip + 16u;
+        const uint32_t left = (uint64_t)m->io.in_len > need ? (uint32_t)(m->io.in_len - need) : 0u;
+        if (left < nmax * 8u) nmax = left / 8u;
+    }
+    if (nmax == 0) { *vop = op; return 0; }
+    zi_io io = m->io;                                    /* the cursor in registers for the whole batch */
+    const uint32_t win = m->win;
+    while (n < nmax) {
+        zi_refill(&io);                                  /* >= 33 bits: a literal/length code and its extra bits */
+        const uint64_t h = io.hold;
+        const uint32_t b = io.bits;
+        uint32_t l, sym;
+        {
+            const uint32_t e = lit[(uint32_t)h & ((1u << ZI_LBITS) - 1u)];
+            if (e) { l = e >> 9; sym = e & 511u; }
+            else {
+                const uint32_t v = zi_rev((uint32_t)h & 0x7FFFu, 15);
+                uint32_t first = T->lfirst, index = T->lindex;
+                l = 0; sym = 0;
+                for (uint32_t k = ZI_LBITS + 1; k <= 15; k++) {
+                    const uint32_t c = T->lcount[k], code = v >> (15 - k);
+                    if (l == 0 && code - first < c) { l = k; sym = m->X->lsorted[index + (code - first)]; }
+                    index += c; first = (first + c) << 1;
+                }
+                if (l == 0) break;
+            }
+        }
+        if (sym < 256u) { io.hold = h >> l; io.bits = b - l; q[n++] = sym; op++; continue; }
+        if (sym == 256u || sym > 285u) break;
+        const uint32_t lb = lut_len[sym - 257u], eb = lb >> 16;
+        const uint32_t len = (lb & 0xFFFFu) + ((uint32_t)(h >> l) & ((1u << eb) - 1u));
+        const uint32_t ip0 = io.ip, pre0 = io.pre, pv0 = io.pv;
+        io.hold = h >> (l + eb); io.bits = b - (l + eb);
+        zi_refill(&io);                                  /* >= 33 bits again: a distance code and its extra bits */
+        const uint64_t h2 = io.hold;
+        const uint32_t b2 = io.bits;
+        uint32_t l2, d;
+        {
+            const uint32_t e = dtab[(uint32_t)h2 & ((1u << ZI_DBITS) - 1u)];
+            if (e) { l2 = e >> 5; d = e & 31u; }
+            else {
+                const uint32_t v = zi_rev((uint32_t)h2 & 0x7FFFu, 15);
+                uint32_t first = T->dfirst, index = T->dindex;
+                l2 = 0; d = 31;
+                for (uint32_t k = ZI_DBITS + 1; k <= 15; k++) {
+                    const uint32_t c = T->dcount[k], code = v >> (15 - k);
+                    if (l2 == 0 && code - first < c) { l2 = k; d = m->X->dsorted[index + (code - first)]; }
+                    index += c; first = (first + c) << 1;
+                }
+            }
+        }
+        uint32_t dist = 0, eb2 = 0;
+        if (l2 != 0 && d <= 29u) {
+            const uint32_t db = lut_dist[d];
+            eb2 = db >> 16;
+            dist = (db & 0xFFFFu) + ((uint32_t)(h2 >> l2) & ((1u << eb2) - 1u));
+        }
+        if (dist == 0 || dist > op || dist > win) {
+            /* not ours: put the cursor back in front of the length code */
+            io.hold = h; io.bits = b; io.ip = ip0; io.pre = pre0; io.pv = pv0;
+            break;
+        }
+        io.hold = h2 >> (l2 + eb2); io.bits = b2 - (l2 + eb2);
+        q[n++] = 0x80000000u | ((len - 3u) << 16) | (dist - 1u);
+        op += len;
+    }
+    m->io.hold = io.hold; m->io.bits = io.bits; m->io.ip = io.ip; m->io.pre = io.pre; m->io.pv = io.pv;
+    *vop = op;
+    return n;
+}
+
+/* stored block in one piece: how many bytes can move now (the copy itself is the caller's), then the
+ * bookkeeping zi_step would have arrived at 16 bytes at a time */
+ZID uint32_t zi_stored_plan(const zi_mach *m)
+{
+    const zi_io *io = &m->io;
+    const uint32_t avail = io->ip < io->in_len ? io->in_len - io->ip : 0, room = io->out_cap - io->op;
+    uint32_t n = m->rem;
+    if (n > avail) n = avail;
+    if (n > room) n = room;
+    return n;
+}
+ZID void zi_stored_done(zi_mach *m, uint32_t n)
+{
+    zi_io *io = &m->io;
+    io->op += n; io->ip += n; io->pv = 0; m->rem -= n;
+    if (m->rem == 0) m->state = m->last ? ZM_TRAIL : ZM_BLOCK;
+    else zi_m_fail(m, zi_fail(&m->res, ZI_BUF_ERROR, io->out_cap == io->op ? ZI_E_OUTPUT_FULL : ZI_E_INPUT_END), 0);
+}
+
 /* Whole stream on one thread: wrapper (wrap 1 = zlib, 0 = raw), blocks, trailer, corruption recovery.
  * The adler32 of the output is verified by the caller (a separate HBM-streaming pass on the GPU);
  * res->stored_check/have_check report the trailer. */
@@ -557,6 +740,38 @@ ZID void zi_inflate(const uint8_t *in, uint32_t in_len, uint8_t *out, uint32_t o
     zi_fast F;
     zi_m_init(&m, in, in_len, out, out_cap, wrap, T, &X, &F);
     while (m.state != ZM_DONE) zi_step(&m);
+    *res = m.res;
+}
+
+/* The warp form run serially (host): same control flow as zs_inflate_warp_kernel with the cooperative writes
+ * replaced by plain loops.  Used by tests/ to pin the batch logic against zi_inflate on the CPU. */
+ZID void zi_inflate_batched(const uint8_t *in, uint32_t in_len, uint8_t *out, uint32_t out_cap,
+                            int wrap, zi_tables *T, zi_result *res, uint32_t group)
+{
+    zi_mach m;
+    zi_aux X;
+    zi_fast F;
+    uint32_t q[ZI_BATCH], lut_len[32], lut_dist[32];
+    for (uint32_t c = 0; c < 29; c++) lut_len[c] = zi_lut_len(c);
+    for (uint32_t d = 0; d < 30; d++) lut_dist[d] = zi_lut_dist(d);
+    zi_m_init(&m, in, in_len, out, out_cap, wrap, T, &X, &F);
+    while (m.state != ZM_DONE) {
+        if (m.state == ZM_SYM) {
+            uint32_t vop = 0, p = m.io.op;
+            const uint32_t n = zi_fast_batch(&m, lut_len, lut_dist, q, group, &vop);
+            for (uint32_t i = 0; i < n; i++) {
+                const uint32_t r = q[i];
+                if (r >> 31) { const uint32_t len = ((r >> 16) & 0xFF) + 3, dist = (r & 0x7FFF) + 1; for (uint32_t k = 0; k < len; k++, p++) out[p] = out[p - dist]; }
+                else out[p++] = (uint8_t)r;
+            }
+            if (n) m.io.op = vop;
+            if (n < group) zi_step(&m);
+        } else if (m.state == ZM_STORED) {
+            const uint32_t n = zi_stored_plan(&m);
+            for (uint32_t k = 0; k < n; k++) out[m.io.op + k] = in[m.io.ip + k];
+            zi_stored_done(&m, n);
+        } else zi_step(&m);
+    }
     *res = m.res;
 }
 
