@@ -1,6 +1,6 @@
 /* zscgpu.h — the C-ABI of the B200 DEFLATE engine.
  *
- * This is the thin layer the host C code (zsc_b200/csrc/host/*.c, the zsc_pub.h surface) calls;
+ * This is the thin layer the host C code (zsc_b200/csrc/host/zsc_api.c, the zsc_pub.h surface) calls;
  * it is also what a foreign-language binding (ctypes / cgo / JNI) would bind for batched,
  * device-resident work.  Plain pointers and sizes only; no CUDA or torch types.
  *
@@ -130,6 +130,11 @@ int zscgpu_inflate_batch(zscgpu_engine *e, const zscgpu_stream *streams, uint32_
 int zscgpu_deflate_enqueue(zscgpu_engine *e, const zscgpu_stream *streams, uint32_t n,
                            const zscgpu_deflate_params *p);
 int zscgpu_inflate_enqueue(zscgpu_engine *e, const zscgpu_stream *streams, uint32_t n, int32_t wrap);
+/* One large stream, its sections inflated in parallel: zsc_compress ends every max_block_len section with a
+ * full flush (reference src/zsc_compress.c:121-140), after which nothing refers back, so the sections decode
+ * like independent streams once a scan for the flush markers and a size-only pass have located them.  Same
+ * result as zscgpu_inflate_batch on that one stream (to which anything irregular falls back). */
+int zscgpu_inflate_sectioned(zscgpu_engine *e, const zscgpu_stream *stream, int32_t wrap, zscgpu_result *result);
 int zscgpu_fetch_results(zscgpu_engine *e, uint32_t n, zscgpu_result *res);
 /* Re-launch the kernels of the last enqueue without rebuilding descriptors (bench inner loop). */
 int zscgpu_relaunch(zscgpu_engine *e);

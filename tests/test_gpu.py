@@ -382,3 +382,90 @@ def test_host_call_in_waves_equals_single_shot(checker):
     rg, gz = Z.compress(x, 262144, 1, window_bits=31)
     assert rg == 0 and int.from_bytes(gz[-8:-4].tobytes(), "little") == zlib.crc32(x.tobytes())
     assert int.from_bytes(gz[-4:].tobytes(), "little") == n
+
+
+# ------------------------------------------------------------------ one large stream, sections in parallel
+def _both_ways(E, comp, cap, wrap=1):
+    """zscgpu_inflate_sectioned and zscgpu_inflate_batch on the same stream: results and bytes"""
+    E.upload(1, 0, comp)
+    st = Engine.make_streams([0], [cap], [0], [len(comp)])
+    a = E.inflate_sectioned(st, wrap)
+    out_a = E.download(0, 0, a.produced)
+    b = E.inflate(st, wrap)[0]
+    out_b = E.download(0, 0, b.produced)
+    assert (a.ret, a.produced, a.consumed) == (b.ret, b.produced, b.consumed)
+    assert np.array_equal(out_a, out_b)
+    if a.ret == 0:
+        assert a.check == b.check
+    return a, out_a
+
+
+def test_sectioned_inflate_equals_one_stream_inflate(checker):
+    n = 24 << 20
+    x = datagen.mixed(n, seed=21)
+    E = Engine(raw_bytes=n + (1 << 20), comp_bytes=n + (n >> 3) + (1 << 20), deflate_batch_max=n + (1 << 20), max_streams=8192, max_chunks=4096)
+    try:
+        for mbl, level in ((262144, 1), (65536, 6), (1 << 30, 1)):
+            r, comp = gpu_deflate(E, x, mbl, level)
+            assert r.ret == 0
+            a, out = _both_ways(E, comp, n)
+            assert a.ret == 0 and a.consumed == len(comp) and a.check == zlib.adler32(x.tobytes()) and np.array_equal(out, x)
+            # output one byte short, input cut: whatever the one-stream path answers
+            _both_ways(E, comp, n - 1)
+            _both_ways(E, comp[:len(comp) // 2], n)
+        # reference-compressed sections
+        if refimpl.have_ref():
+            rc, refc = checker.compress(x[:4 << 20], 100000, 6)
+            a, out = _both_ways(E, refc, 4 << 20)
+            assert a.ret == 0 and np.array_equal(out, x[:4 << 20])
+        # a flipped bit: recovery semantics come from the one-stream path
+        r, comp = gpu_deflate(E, x[:8 << 20], 262144, 1)
+        rng = np.random.default_rng(5)
+        for _ in range(4):
+            bad = comp.copy()
+            bad[int(rng.integers(2, len(bad)))] ^= 0x10
+            _both_ways(E, bad, 8 << 20)
+    finally:
+        E.close()
+
+
+def test_sectioned_inflate_on_irregular_streams():
+    """flush points the scan finds but zsc would not produce: sync flushes (history kept), sections of unequal size,
+    the marker pattern inside stored data"""
+    rng = np.random.default_rng(9)
+    text = datagen.fill(3 << 20, 31, datagen.TEXT).tobytes()
+    E = Engine(raw_bytes=8 << 20, comp_bytes=8 << 20, deflate_batch_max=1 << 20, max_streams=4096, max_chunks=64)
+    try:
+        # unequal sections with full flushes
+        c = zlib.compressobj(6)
+        parts, pos = [], 0
+        while pos < len(text):
+            step = int(rng.integers(1000, 400000))
+            parts.append(c.compress(text[pos:pos + step])); parts.append(c.flush(zlib.Z_FULL_FLUSH)); pos += step
+        parts.append(c.flush())
+        comp = np.frombuffer(b"".join(parts), np.uint8)
+        a, out = _both_ways(E, comp, len(text))
+        assert a.ret == 0 and out.tobytes() == text
+        # sync flushes keep the window: sections refer back, the sectioned path must notice and fall back
+        c = zlib.compressobj(6)
+        parts = []
+        for pos in range(0, len(text), 100000):
+            parts.append(c.compress(text[pos:pos + 100000])); parts.append(c.flush(zlib.Z_SYNC_FLUSH))
+        parts.append(c.flush())
+        comp = np.frombuffer(b"".join(parts), np.uint8)
+        a, out = _both_ways(E, comp, len(text))
+        assert a.ret == 0 and out.tobytes() == text
+        # the marker pattern as payload of stored blocks (coincidental candidates), full flushes between
+        blob = bytearray(rng.integers(0, 256, 600000, dtype=np.uint8).tobytes())
+        for p in range(1000, len(blob) - 8, 7919):
+            blob[p:p + 4] = b"\x00\x00\xff\xff"
+        c = zlib.compressobj(0)
+        parts = []
+        for pos in range(0, len(blob), 150000):
+            parts.append(c.compress(bytes(blob[pos:pos + 150000]))); parts.append(c.flush(zlib.Z_FULL_FLUSH))
+        parts.append(c.flush())
+        comp = np.frombuffer(b"".join(parts), np.uint8)
+        a, out = _both_ways(E, comp, len(blob))
+        assert a.ret == 0 and out.tobytes() == bytes(blob)
+    finally:
+        E.close()

@@ -51,7 +51,7 @@ ZSCGPU_SYMBOLS = [
     "zscgpu_raw_capacity", "zscgpu_comp_capacity", "zscgpu_cuda_stream", "zscgpu_upload", "zscgpu_download",
     "zscgpu_upload_async", "zscgpu_download_async", "zscgpu_sync", "zscgpu_copy_within",
     "zscgpu_host_register", "zscgpu_host_unregister", "zscgpu_deflate_batch", "zscgpu_inflate_batch",
-    "zscgpu_deflate_enqueue", "zscgpu_inflate_enqueue", "zscgpu_fetch_results", "zscgpu_relaunch",
+    "zscgpu_deflate_enqueue", "zscgpu_inflate_enqueue", "zscgpu_inflate_sectioned", "zscgpu_fetch_results", "zscgpu_relaunch",
     "zscgpu_last_launch_count", "zscgpu_compress_host", "zscgpu_uncompress_host", "zscgpu_checksum_host",
     "zscgpu_adler32", "zscgpu_crc32", "zscgpu_adler32_enqueue", "zscgpu_crc32_enqueue",
     "zscgpu_event_record", "zscgpu_event_elapsed_ms", "zscgpu_debug_fetch_symbols",
@@ -158,6 +158,7 @@ def lib():
         L.zscgpu_inflate_batch.argtypes = [vp, sp, u32, i32, rp]
         L.zscgpu_deflate_enqueue.argtypes = [vp, sp, u32, pp]
         L.zscgpu_inflate_enqueue.argtypes = [vp, sp, u32, i32]
+        L.zscgpu_inflate_sectioned.argtypes = [vp, sp, i32, rp]
         L.zscgpu_fetch_results.argtypes = [vp, u32, rp]
         L.zscgpu_relaunch.argtypes = [vp]
         L.zscgpu_last_launch_count.argtypes = [vp]; L.zscgpu_last_launch_count.restype = u32
@@ -316,6 +317,12 @@ class Engine:
     def inflate(self, streams, wrap=1):
         res = (Result * len(streams))()
         self._ck(self.L.zscgpu_inflate_batch(self.h, streams, len(streams), wrap, res))
+        return res
+
+    def inflate_sectioned(self, stream, wrap=1):
+        """one large stream (a 1-element stream array), its flush-delimited sections decoded in parallel"""
+        res = Result()
+        self._ck(self.L.zscgpu_inflate_sectioned(self.h, stream, wrap, C.byref(res)))
         return res
 
     def deflate_enqueue(self, streams, max_block_len, level, strategy=0, wrap=1, window_bits=15):

@@ -4,6 +4,7 @@
  * them to their device twins and launch kernels on the engine's one CUDA stream.
  */
 #include <mutex>
+#include <algorithm>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -13,8 +14,6 @@
 /* kernel launchers (deflate_lz.cu, deflate_huff.cu, checksum.cu, inflate.cu) */
 extern "C" cudaError_t zs_lz_launch(cudaStream_t, int, uint32_t, const uint8_t *, const ZsChunk *, uint32_t *, uint32_t *, uint32_t *, ZsLzParams);
 extern "C" uint32_t zs_lz_fast_max_dist(void);
-extern "C" size_t zs_inflate_cold_bytes(void);
-extern "C" size_t zs_inflate_table_bytes(void);
 extern "C" cudaError_t zs_huff_launch(cudaStream_t, uint32_t, uint32_t, const ZsChunk *, const uint32_t *, const ZsStream *, const uint32_t *,
                                       const uint32_t *, const uint32_t *, zh_block *, const ZsAdlerAcc *, const uint8_t *, uint8_t *,
                                       int32_t *, uint32_t *, uint32_t *, ZsLzParams, cudaEvent_t, cudaEvent_t,
@@ -24,7 +23,7 @@ extern "C" cudaError_t zs_adler_flat_launch(cudaStream_t, const uint8_t *, uint6
 extern "C" cudaError_t zs_crc_init_launch(cudaStream_t);
 extern "C" cudaError_t zs_crc_flat_launch(cudaStream_t, const uint8_t *, uint64_t, uint32_t, uint32_t *, int);
 extern "C" cudaError_t zs_inflate_launch(cudaStream_t, uint32_t, const ZsStream *, const uint8_t *, uint8_t *, int32_t,
-                                         int32_t *, uint32_t *, uint32_t *, uint32_t *, uint32_t *, ZsAdlerAcc *, uint32_t, void *, unsigned long long);
+                                         int32_t *, uint32_t *, uint32_t *, uint32_t *, uint32_t *, ZsAdlerAcc *, uint32_t, int);
 
 #define ZS_NEVENTS 16
 #define ZS_MAX_WAVES 64
@@ -48,7 +47,11 @@ struct zscgpu_engine {
     ZsAdlerAcc *d_adler;              /* per stream; slot max_streams is the flat-checksum slot */
     uint32_t *d_crc;                  /* [2] */
     uint32_t *d_aux;                  /* inflate: [2 * max_streams] trailer check + flags */
-    uint8_t *d_icold;                 /* inflate: 640 B per stream, canonical-code arrays of the rare long codes */
+    uint32_t *h_aux;                  /* the same on the host (section passes read the flags) */
+    uint32_t *d_cand, *h_cand;        /* sectioned inflate: [max_streams + 1] positions behind 00 00 FF FF, slot 0 = count */
+    uint32_t *sec_start, *sec_opts, *sec_flags, *sec_trailer, *sec_real, *sec_off;   /* its host scratch, [max_streams + 1] each */
+    zscgpu_stream *sec_st;            /* [max_streams] */
+    zscgpu_result *sec_r1, *sec_r2;   /* [max_streams] */
     uint32_t last_max_raw;
     int32_t *d_ret, *h_ret;
     uint32_t *d_produced, *h_produced, *d_consumed, *h_consumed, *d_check, *h_check;
@@ -60,6 +63,7 @@ struct zscgpu_engine {
     uint32_t last_nstreams, last_nchunks, last_nblk;
     int last_chain;
     int32_t last_wrap;
+    int last_with_check;
     ZsLzParams last_lz;
     uint32_t launches;
     std::mutex mu;
@@ -143,7 +147,20 @@ extern "C" int zscgpu_init(const zscgpu_config *cfg_in, zscgpu_engine **out)
     ZS_CUDA_CHECK(zs_dev(&e->d_adler, cfg.max_streams + 1));
     ZS_CUDA_CHECK(zs_dev(&e->d_crc, 4));
     ZS_CUDA_CHECK(zs_dev(&e->d_aux, 2ull * cfg.max_streams));
-    ZS_CUDA_CHECK(zs_dev(&e->d_icold, (zs_inflate_cold_bytes() + zs_inflate_table_bytes()) * (size_t)cfg.max_streams + 4096));   /* cold arrays, then decode tables */
+    ZS_CUDA_CHECK(zs_pinned(&e->h_aux, 2ull * cfg.max_streams));
+    ZS_CUDA_CHECK(zs_dev(&e->d_cand, (size_t)cfg.max_streams + 1));
+    ZS_CUDA_CHECK(zs_pinned(&e->h_cand, (size_t)cfg.max_streams + 1));
+    {
+        /* host scratch of the sectioned inflate, sized once here: nothing is allocated after init */
+        const size_t m1 = (size_t)cfg.max_streams + 1;
+        e->sec_start = (uint32_t *)malloc(6 * m1 * sizeof(uint32_t));
+        e->sec_st = (zscgpu_stream *)malloc(m1 * sizeof(zscgpu_stream));
+        e->sec_r1 = (zscgpu_result *)malloc(2 * m1 * sizeof(zscgpu_result));
+        if (!e->sec_start || !e->sec_st || !e->sec_r1) { snprintf(g_init_err, sizeof(g_init_err), "out of host memory"); return ZSCGPU_ERR_CUDA; }
+        e->sec_opts = e->sec_start + m1; e->sec_flags = e->sec_opts + m1; e->sec_trailer = e->sec_flags + m1;
+        e->sec_real = e->sec_trailer + m1; e->sec_off = e->sec_real + m1;
+        e->sec_r2 = e->sec_r1 + m1;
+    }
     ZS_CUDA_CHECK(zs_dev(&e->d_ret, cfg.max_streams));
     ZS_CUDA_CHECK(zs_dev(&e->d_produced, cfg.max_streams));
     ZS_CUDA_CHECK(zs_dev(&e->d_consumed, cfg.max_streams));
@@ -171,7 +188,8 @@ extern "C" void zscgpu_destroy(zscgpu_engine *e)
     cudaFreeHost(e->h_streams); cudaFree(e->d_streams);
     cudaFreeHost(e->h_blk_chunk); cudaFree(e->d_blk_chunk);
     cudaFree(e->d_chunk_nsym); cudaFree(e->d_blk_in_start); cudaFree(e->d_blocks); cudaFree(e->d_blk_meta); cudaFree(e->d_blk_bitoff);
-    cudaFree(e->d_adler); cudaFree(e->d_crc); cudaFree(e->d_aux); cudaFree(e->d_icold);
+    cudaFree(e->d_adler); cudaFree(e->d_crc); cudaFree(e->d_aux); cudaFreeHost(e->h_aux); cudaFree(e->d_cand); cudaFreeHost(e->h_cand);
+    free(e->sec_start); free(e->sec_st); free(e->sec_r1);
     cudaFree(e->d_ret); cudaFree(e->d_produced); cudaFree(e->d_consumed); cudaFree(e->d_check);
     cudaFreeHost(e->h_ret); cudaFreeHost(e->h_produced); cudaFreeHost(e->h_consumed); cudaFreeHost(e->h_check);
     for (int i = 0; i < ZS_NEVENTS; i++) cudaEventDestroy(e->ev[i]);
@@ -425,16 +443,18 @@ static int zs_inflate_launch_all(zscgpu_engine *e)
 {
     const uint32_t n = e->last_nstreams;
     ZS_CUDA_CHECK(zs_inflate_launch(e->stream, n, e->d_streams, e->d_comp, e->d_raw, e->last_wrap, e->d_ret, e->d_produced, e->d_consumed, e->d_check,
-                                    e->d_aux, e->d_adler, e->last_max_raw, e->d_icold, (unsigned long long)zs_inflate_cold_bytes() * e->cfg.max_streams));
+                                    e->d_aux, e->d_adler, e->last_max_raw, e->last_with_check));
     ZS_CUDA_CHECK(cudaMemcpyAsync(e->h_ret, e->d_ret, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, e->stream));
     ZS_CUDA_CHECK(cudaMemcpyAsync(e->h_produced, e->d_produced, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, e->stream));
     ZS_CUDA_CHECK(cudaMemcpyAsync(e->h_consumed, e->d_consumed, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, e->stream));
     ZS_CUDA_CHECK(cudaMemcpyAsync(e->h_check, e->d_check, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, e->stream));
-    e->launches = 3;   /* inflate, output adler, check */
+    if (!e->last_with_check) ZS_CUDA_CHECK(cudaMemcpyAsync(e->h_aux, e->d_aux, sizeof(uint32_t) * 2 * n, cudaMemcpyDeviceToHost, e->stream));
+    e->launches = e->last_with_check ? 3 : 1;   /* inflate, output adler, check */
     return ZSCGPU_OK;
 }
 
-extern "C" int zscgpu_inflate_enqueue(zscgpu_engine *e, const zscgpu_stream *streams, uint32_t n, int32_t wrap)
+/* opts: per-stream section options (ZsStream.chunk_first, see inflate.cu) or nullptr for whole streams */
+static int zs_inflate_enqueue_opts(zscgpu_engine *e, const zscgpu_stream *streams, uint32_t n, int32_t wrap, const uint32_t *opts)
 {
     std::lock_guard<std::mutex> lk(e->mu);
     if (!streams || n == 0 || n > e->cfg.max_streams || (wrap & 0xFF) > 1 || wrap < 0) { snprintf(e->err, sizeof(e->err), "bad inflate batch arguments"); return ZSCGPU_ERR_ARG; }
@@ -449,12 +469,133 @@ extern "C" int zscgpu_inflate_enqueue(zscgpu_engine *e, const zscgpu_stream *str
         ZsStream *S = &e->h_streams[s];
         memset(S, 0, sizeof(*S));
         S->raw_off = z->raw_off; S->comp_off = z->comp_off; S->raw_len = z->raw_len; S->comp_cap = z->comp_len;
+        if (opts) S->chunk_first = opts[s];
         if (z->raw_len > max_raw) max_raw = z->raw_len;
     }
     ZS_CUDA_CHECK(zs_desc_fetch(e, n, 0, 0));
     e->last_max_raw = max_raw;
-    e->last_kind = 2; e->last_nstreams = n; e->last_wrap = wrap;
+    e->last_kind = 2; e->last_nstreams = n; e->last_wrap = wrap; e->last_with_check = opts ? 0 : 1;
     return zs_inflate_launch_all(e);
+}
+extern "C" int zscgpu_inflate_enqueue(zscgpu_engine *e, const zscgpu_stream *streams, uint32_t n, int32_t wrap)
+{
+    return zs_inflate_enqueue_opts(e, streams, n, wrap, nullptr);
+}
+
+/* ----------------------------- one large stream, its sections in parallel -----------------------------
+ * zsc_compress ends every section with a full flush (00 00 FF FF behind an empty stored block) and the next
+ * section references nothing before it (reference src/zsc_compress.c:121-140), so the sections of ONE stream
+ * can be inflated like independent streams once their starts and output offsets are known:
+ *   1. a scan lists every position behind a 00 00 FF FF pattern (candidates; a few may be coincidences);
+ *   2. pass 1 decodes from the stream start and from every candidate without writing anything, each until
+ *      the first flush point or the end of the stream: that yields, per start, where it ends and how many
+ *      bytes it produces;
+ *   3. the host follows the chain start -> end = next start from offset 0 (coincidental candidates are never
+ *      reached) and prefix-sums the output sizes;
+ *   4. pass 2 decodes the real sections to their final places; one adler32 pass checks the whole output.
+ * Anything irregular (a section that fails, a flush point that is not a candidate, too many candidates, an
+ * output that does not fit) falls back to the ordinary one-stream path, which reproduces the reference's
+ * error and recovery behaviour byte for byte. */
+__global__ void zs_marker_scan_kernel(const uint8_t *__restrict__ comp, uint32_t len, uint32_t *__restrict__ cand, uint32_t cap)
+{
+    /* thread = one aligned word of the stream; it tests the four patterns that start in it */
+    const uintptr_t base = reinterpret_cast<uintptr_t>(comp) & ~(uintptr_t)3;
+    const uint32_t lead = (uint32_t)(reinterpret_cast<uintptr_t>(comp) - base);
+    const uint32_t nwords = (lead + len + 3) >> 2;
+    const uint32_t *w32 = reinterpret_cast<const uint32_t *>(base);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += gridDim.x * blockDim.x) {
+        const uint32_t w0 = __ldg(w32 + i), w1 = __ldg(w32 + i + 1);      /* the arenas are padded */
+#pragma unroll
+        for (uint32_t k = 0; k < 4; k++) {
+            const uint32_t v = __funnelshift_r(w0, w1, 8 * k);
+            const uint32_t p = i * 4 + k;                                /* byte position from base */
+            if (v == 0xFFFF0000u && p >= lead && p - lead + 4 <= len) {
+                const uint32_t idx = atomicAdd(&cand[0], 1u);
+                if (idx < cap) cand[1 + idx] = p - lead + 4;
+            }
+        }
+    }
+}
+
+extern "C" int zscgpu_inflate_sectioned(zscgpu_engine *e, const zscgpu_stream *stream, int32_t wrap, zscgpu_result *res)
+{
+    if (!stream || !res || (wrap & 0xFF) > 1 || wrap < 0) { snprintf(e->err, sizeof(e->err), "bad inflate arguments"); return ZSCGPU_ERR_ARG; }
+    if (stream->raw_off > e->cfg.raw_bytes || stream->raw_len > e->cfg.raw_bytes - stream->raw_off ||
+        stream->comp_off > e->cfg.comp_bytes || stream->comp_len > e->cfg.comp_bytes - stream->comp_off) {
+        snprintf(e->err, sizeof(e->err), "stream lies outside the arenas");
+        return ZSCGPU_ERR_CAPACITY;
+    }
+    const uint32_t cap = e->cfg.max_streams - 1;
+    uint32_t ncand = 0;
+    if (stream->comp_len >= 8) {
+        std::lock_guard<std::mutex> lk(e->mu);
+        ZS_CUDA_CHECK(cudaMemsetAsync(e->d_cand, 0, 4, e->stream));
+        zs_marker_scan_kernel<<<e->sms * 8, 256, 0, e->stream>>>(e->d_comp + stream->comp_off, stream->comp_len, e->d_cand, cap);
+        ZS_CUDA_CHECK(cudaGetLastError());
+        ZS_CUDA_CHECK(cudaMemcpyAsync(e->h_cand, e->d_cand, 4, cudaMemcpyDeviceToHost, e->stream));
+        ZS_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+        ncand = e->h_cand[0];
+        if (ncand && ncand <= cap) {
+            ZS_CUDA_CHECK(cudaMemcpyAsync(e->h_cand + 1, e->d_cand + 1, 4ull * ncand, cudaMemcpyDeviceToHost, e->stream));
+            ZS_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+        }
+    }
+    if (ncand == 0 || ncand > cap) return zscgpu_inflate_batch(e, stream, 1, wrap, res);
+    /* section starts, ascending; a pattern at the very end of the input starts nothing */
+    uint32_t *start = e->sec_start, *opts = e->sec_opts, *flags = e->sec_flags, *trailer = e->sec_trailer, *real = e->sec_real, *off = e->sec_off;
+    zscgpu_stream *st = e->sec_st;
+    zscgpu_result *r1 = e->sec_r1, *r2 = e->sec_r2;
+    start[0] = 0;
+    memcpy(start + 1, e->h_cand + 1, 4ull * ncand);
+    std::sort(start + 1, start + 1 + ncand);
+    uint32_t ns = ncand + 1;
+    while (ns > 1 && start[ns - 1] >= stream->comp_len) ns--;
+    if (ns < 2) return zscgpu_inflate_batch(e, stream, 1, wrap, res);
+
+    /* pass 1: sizes */
+    for (uint32_t k = 0; k < ns; k++) {
+        st[k].raw_off = stream->raw_off; st[k].raw_len = stream->raw_len;
+        st[k].comp_off = stream->comp_off + start[k]; st[k].comp_len = stream->comp_len - start[k];
+        opts[k] = 1u | 2u | (k ? 4u : 0u);
+    }
+    int rc = zs_inflate_enqueue_opts(e, st, ns, wrap, opts); if (rc) return rc;
+    rc = zscgpu_fetch_results(e, ns, r1); if (rc) return rc;
+    for (uint32_t k = 0; k < ns; k++) { trailer[k] = e->h_aux[2 * k]; flags[k] = e->h_aux[2 * k + 1]; }
+
+    /* the chain of real sections */
+    uint64_t total = 0;
+    uint32_t k = 0, nr = 0, end_pos = 0, stored_check = 0, have_check = 0;
+    bool ok = true;
+    for (;;) {
+        if (r1[k].ret != 0 || (flags[k] & 2u) || nr >= ns) { ok = false; break; }
+        real[nr] = k; off[nr] = (uint32_t)total; nr++;
+        total += r1[k].produced;
+        if (total > stream->raw_len) { ok = false; break; }
+        end_pos = start[k] + r1[k].consumed;
+        if (!(flags[k] & 4u)) { stored_check = trailer[k]; have_check = flags[k] & 1u; break; }   /* the stream ended here */
+        const uint32_t *it = std::lower_bound(start, start + ns, end_pos);
+        if (it == start + ns || *it != end_pos) { ok = false; break; }
+        k = (uint32_t)(it - start);
+    }
+    if (!ok) return zscgpu_inflate_batch(e, stream, 1, wrap, res);
+
+    /* pass 2: the real sections, each into its final place */
+    for (uint32_t i = 0; i < nr; i++) {
+        const uint32_t s = real[i];
+        st[i].raw_off = stream->raw_off + off[i]; st[i].raw_len = r1[s].produced;
+        st[i].comp_off = stream->comp_off + start[s]; st[i].comp_len = r1[s].consumed;
+        opts[i] = 2u | (s ? 4u : 0u);
+    }
+    rc = zs_inflate_enqueue_opts(e, st, nr, wrap, opts); if (rc) return rc;
+    rc = zscgpu_fetch_results(e, nr, r2); if (rc) return rc;
+    for (uint32_t i = 0; i < nr; i++)
+        if (r2[i].ret != 0 || r2[i].produced != r1[real[i]].produced) return zscgpu_inflate_batch(e, stream, 1, wrap, res);
+    uint32_t check = 1;
+    rc = zscgpu_adler32(e, stream->raw_off, total, 1u, &check); if (rc) return rc;
+    res->ret = ((wrap & 0xFF) == 1 && have_check && stored_check != check) ? -3 : 0;
+    res->produced = (uint32_t)total; res->consumed = end_pos; res->check = check;
+    e->launches = 4;   /* marker scan, size pass, decode pass, adler32 */
+    return ZSCGPU_OK;
 }
 
 extern "C" int zscgpu_relaunch(zscgpu_engine *e)
@@ -617,7 +758,8 @@ extern "C" int zscgpu_uncompress_host(zscgpu_engine *e, uint8_t *dest, uint32_t 
     zscgpu_stream st;
     st.raw_off = 0; st.comp_off = 0; st.comp_len = src_len;
     st.raw_len = (uint64_t)dest_cap > e->cfg.raw_bytes ? (uint32_t)e->cfg.raw_bytes : dest_cap;
-    r = zscgpu_inflate_batch(e, &st, 1, wrap, res); if (r) return r;
+    r = (src_len >= (64u << 10)) ? zscgpu_inflate_sectioned(e, &st, wrap, res) : zscgpu_inflate_batch(e, &st, 1, wrap, res);
+    if (r) return r;
     if (res->produced) return zscgpu_download(e, 0, dest, 0, res->produced);
     return ZSCGPU_OK;
 }

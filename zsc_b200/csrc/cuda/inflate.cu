@@ -1,60 +1,18 @@
-/* inflate.cu — batched inflate: one thread per stream, decode tables in shared memory (sm_100a).
+/* inflate.cu — batched inflate: a group of lanes per stream, decode tables in shared memory (sm_100a).
  *
  * GPU form of zsc_uncompress's hot loop (reference src/zsc_uncompr.c:103-127 -> inflate /
- * inflate_fast / inflate_table).  Streams are independent, so the batch is spread one stream per
- * thread; the 32 threads of a warp keep their 32 sets of tables (1856 B each, inflate_core.h) in
- * shared memory and decode in lockstep, which works well because reference-compressed streams end
- * their blocks on the same symbol count.  The data check (adler32 of the output against the
- * trailer, reference src/inflate.c:1322-1342) is a second, HBM-streaming pass over the output.
+ * inflate_fast / inflate_table).  Streams are independent, so a batch is spread one stream per warp (or
+ * half warp when the batch is wide): the group's leader lane decodes symbols into a small queue, the
+ * whole group writes them out, and the generic state machine of inflate_core.h handles every header, block
+ * boundary, buffer end and error exactly as the CPU tests pin it.  The data check (adler32 of the output
+ * against the trailer, reference src/inflate.c:1322-1342) is a second, HBM-streaming pass over the output.
  */
 #include "common.cuh"
 #include "inflate_core.h"
-#include <stdlib.h>
 
-#define ZI_THREADS 32
-#ifndef ZS_INFLATE_GROUP
-#define ZS_INFLATE_GROUP 32                      /* lanes per stream in the group kernel: 32, 16 or 8 */
+#ifndef ZS_INFLATE_WARP_MAX
+#define ZS_INFLATE_WARP_MAX 6144u                /* streams in a batch up to which each gets a whole warp */
 #endif
-#ifndef ZS_INFLATE_LOCKSTEP_MIN
-#define ZS_INFLATE_LOCKSTEP_MIN 0xFFFFFFFFu      /* streams in a batch from which the thread-per-stream kernel is used */
-#endif
-
-__global__ void __launch_bounds__(ZI_THREADS)
-zs_inflate_kernel(uint32_t n, const ZsStream *__restrict__ streams, const uint8_t *__restrict__ comp,
-                  uint8_t *__restrict__ raw, int32_t wrap, int32_t *__restrict__ ret,
-                  uint32_t *__restrict__ produced, uint32_t *__restrict__ consumed,
-                  uint32_t *__restrict__ aux /* [2n]: stored check, flags */, zi_aux *__restrict__ cold, zi_tables *__restrict__ tabs)
-{
-    const uint32_t s = blockIdx.x * ZI_THREADS + threadIdx.x;
-#ifdef ZI_TABLES_IN_SMEM
-    extern __shared__ __align__(16) unsigned char zi_smem_raw[];
-    zi_tables *T = reinterpret_cast<zi_tables *>(zi_smem_raw) + threadIdx.x;
-#else
-    /* decode tables live in global memory (they stay L2 / L1 resident): without a shared-memory footprint the
-       SM holds ~20 warps = 640 streams, and it is that parallelism, not table latency, that sets throughput */
-    zi_tables *T = tabs + (s < n ? s : 0);
-#endif
-    /* first-level tables (codes of <= 7 bits, distance table): 384 B per stream in shared memory */
-    __shared__ zi_fast fast[ZI_THREADS];
-    zi_fast *F = &fast[threadIdx.x];
-    zi_mach m;
-    if (s < n) {
-        const ZsStream st = streams[s];
-        zi_m_init(&m, comp + st.comp_off, st.comp_cap, raw + st.raw_off, st.raw_len, wrap, T, cold + s, F);
-    } else {
-        m.state = ZM_DONE;
-    }
-    /* lockstep: every lane advances its own stream by one bounded step, then the warp re-converges */
-    while (__any_sync(0xFFFFFFFFu, m.state != ZM_DONE)) {
-        if (m.state != ZM_DONE) zi_step(&m);
-    }
-    if (s >= n) return;
-    ret[s] = m.res.ret;
-    produced[s] = m.res.produced;
-    consumed[s] = m.res.consumed;
-    aux[2 * s] = m.res.stored_check;
-    aux[2 * s + 1] = m.res.have_check | (m.res.data_errors ? 2u : 0u);
-}
 
 /* ======================= a group of G lanes per stream ======================= */
 /* The leader lane of a group runs the state machine.  Inside a compressed block it decodes up to G symbols
@@ -155,8 +113,15 @@ zs_inflate_group_kernel(uint32_t n, const ZsStream *__restrict__ streams, const 
     const ZsStream st = streams[s];
     const uint8_t *in = comp + st.comp_off;
     uint8_t *out = raw + st.raw_off;
+    /* per-stream options of section-parallel decoding ride in ZsStream.chunk_first (unused by inflate):
+       ZI_OPT_* | 4 = this stream continues another one: no zlib header in front of its first block (the trailer,
+       if the batch's wrap has one, still follows its final block) */
+    const uint32_t sopt = st.chunk_first;
     zi_mach m;
     zi_m_init(&m, in, st.comp_cap, out, st.raw_len, wrap, &w.T, &w.X, &w.F);
+    m.opts = sopt & 3u;
+    if ((sopt & 4u) && m.state == ZM_HEAD) m.state = ZM_BLOCK;
+    const bool count_only = (sopt & ZI_OPT_COUNT_ONLY) != 0;
     for (;;) {
         const int state = __shfl_sync(gmask, m.state, 0, G);
         if (state == ZM_DONE) break;
@@ -167,7 +132,7 @@ zs_inflate_group_kernel(uint32_t n, const ZsStream *__restrict__ streams, const 
             base = __shfl_sync(gmask, base, 0, G);
             if (cnt) {
                 __syncwarp(gmask);                           /* the leader's queue writes are visible to the group */
-                zw_emit<G>(out, base, w.q, cnt, gl, gmask, gshift);
+                if (!count_only) zw_emit<G>(out, base, w.q, cnt, gl, gmask, gshift);
                 if (gl == 0) m.io.op = vop;
             }
             if (cnt < (uint32_t)G) {
@@ -181,7 +146,7 @@ zs_inflate_group_kernel(uint32_t n, const ZsStream *__restrict__ streams, const 
             cnt = __shfl_sync(gmask, cnt, 0, G);
             from = __shfl_sync(gmask, from, 0, G);
             to = __shfl_sync(gmask, to, 0, G);
-            for (uint32_t k = gl; k < cnt; k += G) out[to + k] = in[from + k];
+            if (!count_only) for (uint32_t k = gl; k < cnt; k += G) out[to + k] = in[from + k];
             __syncwarp(gmask);
             if (gl == 0) zi_stored_done(&m, cnt);
         } else {
@@ -194,7 +159,7 @@ zs_inflate_group_kernel(uint32_t n, const ZsStream *__restrict__ streams, const 
         produced[s] = m.res.produced;
         consumed[s] = m.res.consumed;
         aux[2 * s] = m.res.stored_check;
-        aux[2 * s + 1] = m.res.have_check | (m.res.data_errors ? 2u : 0u);
+        aux[2 * s + 1] = m.res.have_check | (m.res.data_errors ? 2u : 0u) | (m.res.at_flush ? 4u : 0u);
     }
 }
 
@@ -226,31 +191,17 @@ __global__ void zs_inflate_check_kernel(uint32_t n, const ZsAdlerAcc *__restrict
 extern "C" cudaError_t zs_adler_streams_launch(cudaStream_t st, uint32_t n, uint32_t max_len, const uint8_t *raw,
                                                const ZsStream *streams, const uint32_t *produced, ZsAdlerAcc *acc);
 
-extern "C" size_t zs_inflate_cold_bytes(void) { return sizeof(zi_aux); }
-extern "C" size_t zs_inflate_table_bytes(void) { return sizeof(zi_tables); }
-
 extern "C" cudaError_t zs_inflate_launch(cudaStream_t st, uint32_t n, const ZsStream *streams, const uint8_t *comp,
                                          uint8_t *raw, int32_t wrap, int32_t *ret, uint32_t *produced,
                                          uint32_t *consumed, uint32_t *check, uint32_t *aux, ZsAdlerAcc *acc,
-                                         uint32_t max_raw_len, void *cold, unsigned long long tabs_off)
+                                         uint32_t max_raw_len, int with_check)
 {
     if (n == 0) return cudaSuccess;
-#ifdef ZI_TABLES_IN_SMEM
-    const size_t smem = sizeof(zi_tables) * ZI_THREADS;
-    cudaFuncSetAttribute(zs_inflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-#else
-    const size_t smem = 0;
-#endif
-    /* One warp per stream unless the batch is so wide that one thread per stream fills the machine better
-       (the lockstep kernel needs on the order of 10^5 streams in flight). */
-    static int grp = getenv("ZSC_INFLATE_GROUP") ? atoi(getenv("ZSC_INFLATE_GROUP")) : ZS_INFLATE_GROUP;   /* TEMP experiment knob */
-    if (grp != 0 && n < ZS_INFLATE_LOCKSTEP_MIN) {
-        cudaError_t ce = grp == 32 ? zs_inflate_group_launch<32>(st, n, streams, comp, raw, wrap, ret, produced, consumed, aux)
-                       : grp == 16 ? zs_inflate_group_launch<16>(st, n, streams, comp, raw, wrap, ret, produced, consumed, aux)
-                                                : zs_inflate_group_launch<8>(st, n, streams, comp, raw, wrap, ret, produced, consumed, aux);
-        if (ce != cudaSuccess) return ce;
-    } else
-    zs_inflate_kernel<<<(n + ZI_THREADS - 1) / ZI_THREADS, ZI_THREADS, smem, st>>>(n, streams, comp, raw, wrap, ret, produced, consumed, aux, reinterpret_cast<zi_aux *>(cold), reinterpret_cast<zi_tables *>(reinterpret_cast<uint8_t *>(cold) + (size_t)tabs_off));
+    /* a warp per stream while that fills the machine (148 SMs x 32 warps), two streams per warp beyond */
+    cudaError_t ge = n <= ZS_INFLATE_WARP_MAX ? zs_inflate_group_launch<32>(st, n, streams, comp, raw, wrap, ret, produced, consumed, aux)
+                                              : zs_inflate_group_launch<16>(st, n, streams, comp, raw, wrap, ret, produced, consumed, aux);
+    if (ge != cudaSuccess) return ge;
+    if (!with_check) return cudaSuccess;               /* section passes: the caller checks the whole stream */
     cudaMemsetAsync(acc, 0, sizeof(ZsAdlerAcc) * n, st);
     cudaError_t ce = zs_adler_streams_launch(st, n, max_raw_len, raw, streams, produced, acc);
     if (ce != cudaSuccess) return ce;

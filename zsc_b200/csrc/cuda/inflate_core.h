@@ -88,6 +88,7 @@ typedef struct {
     uint32_t stored_check;  /* adler32 from the trailer */
     uint32_t have_check;    /* trailer was reached */
     int32_t last_reason;    /* ZI_E_* of the most recent failure */
+    uint32_t at_flush;      /* section mode: decoding stopped behind an empty non-final stored block (a flush point) */
 } zi_result;
 
 ZID void zi_refill(zi_io *io)
@@ -397,7 +398,11 @@ typedef struct {
     zi_fast *F;
     int32_t state, wrap;
     uint32_t last, rem, dist, win, maxw, held;
+    uint32_t opts;          /* ZI_OPT_*: section-parallel decoding of one stream (engine.cu zs_inflate_sectioned) */
 } zi_mach;
+
+#define ZI_OPT_COUNT_ONLY 1u        /* advance the output position without writing (sizes of the sections) */
+#define ZI_OPT_STOP_AT_FLUSH 2u     /* end, successfully, behind the first empty non-final stored block */
 
 ZID void zi_m_init(zi_mach *m, const uint8_t *in, uint32_t in_len, uint8_t *out, uint32_t out_cap, int wrap, zi_tables *T, zi_aux *X, zi_fast *F)
 {
@@ -409,7 +414,8 @@ ZID void zi_m_init(zi_mach *m, const uint8_t *in, uint32_t in_len, uint8_t *out,
     m->maxw = ((wrap >> 8) & 0xFF) ? (uint32_t)((wrap >> 8) & 0xFF) : 15u;
     m->wrap = wrap & 0xFF;
     m->win = 1u << m->maxw;
-    m->T = T; m->X = X; m->F = F; m->last = 0; m->rem = 0; m->dist = 0; m->held = 0;
+    m->T = T; m->X = X; m->F = F; m->last = 0; m->rem = 0; m->dist = 0; m->held = 0; m->opts = 0;
+    m->res.at_flush = 0;
     m->state = m->wrap == 1 ? ZM_HEAD : ZM_BLOCK;
 }
 
@@ -453,7 +459,8 @@ ZID void zi_step(zi_mach *m)
             if (s < 0) { zi_m_fail(m, zi_fail(res, ZI_DATA_ERROR, ZI_E_LITLEN_CODE), 0); break; }
             if (s < 256) {
                 if (io->op >= io->out_cap) { zi_m_fail(m, zi_fail(res, ZI_BUF_ERROR, ZI_E_OUTPUT_FULL), 0); break; }
-                io->out[io->op++] = (uint8_t)s;
+                if (!(m->opts & ZI_OPT_COUNT_ONLY)) io->out[io->op] = (uint8_t)s;
+                io->op++;
                 continue;
             }
             if (s == 256) { m->state = m->last ? ZM_TRAIL : ZM_BLOCK; break; }
@@ -486,7 +493,7 @@ ZID void zi_step(zi_mach *m)
         uint32_t room = io->out_cap - io->op;
         uint32_t n = m->rem < 16 ? m->rem : 16;
         if (n > room) n = room;
-        zi_copy_match(io->out + io->op, m->dist, n);
+        if (!(m->opts & ZI_OPT_COUNT_ONLY)) zi_copy_match(io->out + io->op, m->dist, n);
         io->op += n; m->rem -= n;
         if (m->rem == 0) m->state = ZM_SYM;
         else if (n == 0 || io->op >= io->out_cap) zi_m_fail(m, zi_fail(res, ZI_BUF_ERROR, ZI_E_OUTPUT_FULL), 0);
@@ -498,7 +505,7 @@ ZID void zi_step(zi_mach *m)
         uint32_t n = m->rem < 16 ? m->rem : 16;
         if (n > avail) n = avail;
         if (n > room) n = room;
-        zi_copy_fwd(io->out + io->op, io->in + pos, n);
+        if (!(m->opts & ZI_OPT_COUNT_ONLY)) zi_copy_fwd(io->out + io->op, io->in + pos, n);
         io->op += n; io->ip = pos + n; io->pv = 0; m->rem -= n;
         if (m->rem == 0) m->state = m->last ? ZM_TRAIL : ZM_BLOCK;
         else if (n == 0) zi_m_fail(m, zi_fail(res, ZI_BUF_ERROR, room == 0 ? ZI_E_OUTPUT_FULL : ZI_E_INPUT_END), 0);
@@ -521,8 +528,10 @@ ZID void zi_step(zi_mach *m)
         uint32_t type = 0, slen = 0;
         int r = zi_block_head(io, T, X, F, res, &m->last, &type, &slen);
         if (r != ZI_OK) { zi_m_fail(m, r, (r == ZI_DATA_ERROR && res->last_reason == ZI_E_STORED_LEN) ? 4u : 0u); return; }
-        if (type == 0) { m->rem = slen; m->state = slen ? ZM_STORED : (m->last ? ZM_TRAIL : ZM_BLOCK); }
-        else m->state = ZM_SYM;
+        if (type == 0) {
+            if (slen == 0 && !m->last && (m->opts & ZI_OPT_STOP_AT_FLUSH)) { res->at_flush = 1; zi_m_finish(m, ZI_OK); return; }
+            m->rem = slen; m->state = slen ? ZM_STORED : (m->last ? ZM_TRAIL : ZM_BLOCK);
+        } else m->state = ZM_SYM;
         return;
     }
     if (m->state == ZM_TRAIL) {
