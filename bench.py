@@ -187,7 +187,7 @@ def run_gpu(args, rank, world, local_rank):
 
     n = GIB
     E = Engine(raw_bytes=n + (1 << 20), comp_bytes=n + (n >> 3) + (1 << 20), deflate_batch_max=n + (1 << 20),
-               max_streams=16, max_chunks=8192, device=local_rank)
+               max_streams=8192, max_chunks=8192, device=local_rank)
     data = datagen.mixed(n, seed=1 + rank)
     cap = n + (n >> 3)
     dest = np.empty(cap, dtype=np.uint8)
@@ -207,6 +207,7 @@ def run_gpu(args, rank, world, local_rank):
 
     sampler = ClockSampler(local_rank)
     sampler.start()
+    launches0 = int(E.L.zscgpu_launch_total(E.h))
     # ---- timed: device-resident ----
     barrier(); E.sync()
     t_wall0 = time.perf_counter()
@@ -223,7 +224,9 @@ def run_gpu(args, rank, world, local_rank):
     e2e_steps = max(1, min(args.steps, 3))
     p = DeflateParams(SECTION, LEVEL, 0, 1, 15, 0)
     r1 = Result()
+    launches_resident = int(E.L.zscgpu_launch_total(E.h)) - launches0
     E.L.zscgpu_compress_host(E.h, dest.ctypes.data, cap, data.ctypes.data, n, C.byref(p), 0, C.byref(r1))   # warm
+    launches1 = int(E.L.zscgpu_launch_total(E.h))
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
@@ -231,6 +234,35 @@ def run_gpu(args, rank, world, local_rank):
         assert rc == 0 and r1.ret == 0
     barrier()
     e2e_s = allmax((time.perf_counter() - t0) / e2e_steps)
+    launches = launches_resident + int(E.L.zscgpu_launch_total(E.h)) - launches1     # kernels inside the two timed regions
+
+    # ---- the way back: this run's own stream through the section-parallel inflate, resident and end to end ----
+    inflate = None
+    try:
+        comp = dest[:r1.produced]
+        back = np.empty(n, dtype=np.uint8)
+        E.L.zscgpu_host_register(back.ctypes.data, back.nbytes)
+        E.upload(1, 0, comp)
+        st1 = Engine.make_streams([0], [n], [0], [len(comp)])
+        ri = E.inflate_sectioned(st1, 1)                                     # warm
+        assert ri.ret == 0 and ri.produced == n and ri.consumed == len(comp)
+        barrier(); t0 = time.perf_counter()
+        for _ in range(2):
+            ri = E.inflate_sectioned(st1, 1)
+        barrier(); inf_s = allmax((time.perf_counter() - t0) / 2)
+        r2 = Result()
+        E.L.zscgpu_uncompress_host(E.h, back.ctypes.data, n, comp.ctypes.data, len(comp), 1, C.byref(r2))   # warm
+        barrier(); t0 = time.perf_counter()
+        for _ in range(2):
+            rc = E.L.zscgpu_uncompress_host(E.h, back.ctypes.data, n, comp.ctypes.data, len(comp), 1, C.byref(r2))
+            assert rc == 0 and r2.ret == 0
+        barrier(); inf_e2e_s = allmax((time.perf_counter() - t0) / 2)
+        inflate = {"value": round(world * n / 1e9 / inf_s, 3), "unit": "GB/s of output",
+                   "e2e": round(world * n / 1e9 / inf_e2e_s, 3),
+                   "what": "the 1 GiB stream this run produced (4096 sections) back through zscgpu_inflate_sectioned / zscgpu_uncompress_host",
+                   "parity": "bit-exact with the input" if bool(np.array_equal(back, data)) else "MISMATCH"}
+    except Exception as ex:  # pragma: no cover
+        inflate = {"value": None, "error": repr(ex)}
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
@@ -270,7 +302,8 @@ def run_gpu(args, rank, world, local_rank):
                                   "offsets": round(pk[3], 3), "bitpack": round(pk[4], 3)}},
         "e2e": {"value": round(world * n / 1e9 / e2e_s, 3), "unit": "GB/s", "h2d_bytes_per_step": n,
                 "d2h_bytes_per_step": int(r1.produced), "api": "zscgpu_compress_host (the call behind zsc_compress), pinned host buffers"},
-        "gpu_launches": int(args.steps * 5 + e2e_steps * 5),
+        "gpu_launches": launches,
+        "inflate": inflate,
         "clocks": sampler.summary(),
     }
     if world == 1 and not args.no_cpu_baseline:

@@ -139,6 +139,8 @@ int zscgpu_fetch_results(zscgpu_engine *e, uint32_t n, zscgpu_result *res);
 /* Re-launch the kernels of the last enqueue without rebuilding descriptors (bench inner loop). */
 int zscgpu_relaunch(zscgpu_engine *e);
 uint32_t zscgpu_last_launch_count(const zscgpu_engine *e);
+/* kernels launched by this engine since zscgpu_init (bench.py reports the difference over its timed regions) */
+unsigned long long zscgpu_launch_total(const zscgpu_engine *e);
 
 /* One-shot calls on HOST buffers (what zsc_compress / zsc_uncompress / adler32 / crc32 use): copy in,
  * run a batch of one stream at offset 0 of the arenas, copy out.  comp_skip leaves room at the start

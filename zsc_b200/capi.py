@@ -52,7 +52,7 @@ ZSCGPU_SYMBOLS = [
     "zscgpu_upload_async", "zscgpu_download_async", "zscgpu_sync", "zscgpu_copy_within",
     "zscgpu_host_register", "zscgpu_host_unregister", "zscgpu_deflate_batch", "zscgpu_inflate_batch",
     "zscgpu_deflate_enqueue", "zscgpu_inflate_enqueue", "zscgpu_inflate_sectioned", "zscgpu_fetch_results", "zscgpu_relaunch",
-    "zscgpu_last_launch_count", "zscgpu_compress_host", "zscgpu_uncompress_host", "zscgpu_checksum_host",
+    "zscgpu_last_launch_count", "zscgpu_launch_total", "zscgpu_compress_host", "zscgpu_uncompress_host", "zscgpu_checksum_host",
     "zscgpu_adler32", "zscgpu_crc32", "zscgpu_adler32_enqueue", "zscgpu_crc32_enqueue",
     "zscgpu_event_record", "zscgpu_event_elapsed_ms", "zscgpu_debug_fetch_symbols",
     "zscgpu_adler32_combine", "zscgpu_crc32_combine",
@@ -159,6 +159,8 @@ def lib():
         L.zscgpu_deflate_enqueue.argtypes = [vp, sp, u32, pp]
         L.zscgpu_inflate_enqueue.argtypes = [vp, sp, u32, i32]
         L.zscgpu_inflate_sectioned.argtypes = [vp, sp, i32, rp]
+        L.zscgpu_launch_total.argtypes = [vp]
+        L.zscgpu_launch_total.restype = C.c_ulonglong
         L.zscgpu_fetch_results.argtypes = [vp, u32, rp]
         L.zscgpu_relaunch.argtypes = [vp]
         L.zscgpu_last_launch_count.argtypes = [vp]; L.zscgpu_last_launch_count.restype = u32

@@ -64,6 +64,7 @@ struct zscgpu_engine {
     int last_chain;
     int32_t last_wrap;
     int last_with_check;
+    unsigned long long launches_total;   /* kernels launched since init (zscgpu_launch_total) */
     ZsLzParams last_lz;
     uint32_t launches;
     std::mutex mu;
@@ -400,6 +401,7 @@ static cudaError_t zs_desc_fetch(zscgpu_engine *e, uint32_t n, uint32_t nc, uint
     uint32_t total = d.words[0] + d.words[1] + d.words[2];
     uint32_t grid = (total + 255) / 256; if (grid > 148) grid = 148; if (grid == 0) grid = 1;
     zs_desc_fetch_kernel<<<grid, 256, 0, e->stream>>>(d);
+    e->launches_total += 1;
     return cudaGetLastError();
 }
 
@@ -421,6 +423,7 @@ static int zs_deflate_launch_all(zscgpu_engine *e)
     ZS_CUDA_CHECK(cudaMemcpyAsync(e->h_produced, e->d_produced, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, e->stream));
     ZS_CUDA_CHECK(cudaMemcpyAsync(e->h_check, e->d_check, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, e->stream));
     e->launches = 6;   /* adler, lz, block, stored-run merge, offset, encode */
+    e->launches_total += 6;
     return ZSCGPU_OK;
 }
 
@@ -450,6 +453,7 @@ static int zs_inflate_launch_all(zscgpu_engine *e)
     ZS_CUDA_CHECK(cudaMemcpyAsync(e->h_check, e->d_check, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, e->stream));
     if (!e->last_with_check) ZS_CUDA_CHECK(cudaMemcpyAsync(e->h_aux, e->d_aux, sizeof(uint32_t) * 2 * n, cudaMemcpyDeviceToHost, e->stream));
     e->launches = e->last_with_check ? 3 : 1;   /* inflate, output adler, check */
+    e->launches_total += e->launches;
     return ZSCGPU_OK;
 }
 
@@ -532,6 +536,7 @@ extern "C" int zscgpu_inflate_sectioned(zscgpu_engine *e, const zscgpu_stream *s
         ZS_CUDA_CHECK(cudaMemsetAsync(e->d_cand, 0, 4, e->stream));
         zs_marker_scan_kernel<<<e->sms * 8, 256, 0, e->stream>>>(e->d_comp + stream->comp_off, stream->comp_len, e->d_cand, cap);
         ZS_CUDA_CHECK(cudaGetLastError());
+        e->launches_total += 1;
         ZS_CUDA_CHECK(cudaMemcpyAsync(e->h_cand, e->d_cand, 4, cudaMemcpyDeviceToHost, e->stream));
         ZS_CUDA_CHECK(cudaStreamSynchronize(e->stream));
         ncand = e->h_cand[0];
@@ -606,6 +611,7 @@ extern "C" int zscgpu_relaunch(zscgpu_engine *e)
     return ZSCGPU_ERR_ARG;
 }
 extern "C" uint32_t zscgpu_last_launch_count(const zscgpu_engine *e) { return e->launches; }
+extern "C" unsigned long long zscgpu_launch_total(const zscgpu_engine *e) { return e->launches_total; }
 
 extern "C" int zscgpu_fetch_results(zscgpu_engine *e, uint32_t n, zscgpu_result *res)
 {
@@ -787,6 +793,7 @@ extern "C" int zscgpu_adler32_enqueue(zscgpu_engine *e, uint64_t off, uint64_t l
     ZS_CUDA_CHECK(cudaMemsetAsync(acc, 0, sizeof(ZsAdlerAcc), e->stream));
     if (len) ZS_CUDA_CHECK(zs_adler_flat_launch(e->stream, p, len, acc, e->sms));
     e->launches = 1;
+    e->launches_total += 1;
     return ZSCGPU_OK;
 }
 extern "C" int zscgpu_adler32(zscgpu_engine *e, uint64_t off, uint64_t len, uint32_t init, uint32_t *out)
@@ -809,6 +816,7 @@ extern "C" int zscgpu_crc32_enqueue(zscgpu_engine *e, uint64_t off, uint64_t len
     ZS_CUDA_CHECK(cudaMemsetAsync(e->d_crc, 0, 8, e->stream));
     ZS_CUDA_CHECK(zs_crc_flat_launch(e->stream, p, len, 0, e->d_crc, e->sms));
     e->launches = 2;
+    e->launches_total += 2;
     return ZSCGPU_OK;
 }
 extern "C" int zscgpu_crc32(zscgpu_engine *e, uint64_t off, uint64_t len, uint32_t init, uint32_t *out)
