@@ -239,6 +239,8 @@ def run_gpu(args, rank, world, local_rank):
     # ---- the way back: this run's own stream through the section-parallel inflate, resident and end to end ----
     inflate = None
     try:
+        if world > 1:
+            raise RuntimeError("measured at N=1 only (a third pinned GiB per rank is not worth it for a side number)")
         comp = dest[:r1.produced]
         back = np.empty(n, dtype=np.uint8)
         E.L.zscgpu_host_register(back.ctypes.data, back.nbytes)
