@@ -29,15 +29,32 @@ struct ZbSmem {
     int m, max_l, max_d, overflow;
 };
 
+/* What the three block kernels hand to each other, per block slot (global memory):
+ * zs_block_kernel<0> leaves the sorted keys, the reduced histograms and the distance code lengths;
+ * zs_merge_kernel adds the parent links of the literal/length tree; zs_block_kernel<1> reads it all back. */
+struct ZbScratch {
+    uint32_t key[ZH_LCODES_PAD];
+    uint32_t lfreq[ZH_LCODES_PAD];
+    uint32_t dfreq[ZH_DCODES_PAD];
+    uint16_t parent[2 * ZH_LCODES_PAD];
+    uint8_t dlen[ZH_DCODES_PAD];
+    int32_t m, max_l, max_d, pad;
+};
+
 /* The serial recipe of zh_build_block (huff_build.h) spread over the CTA: key collection, sort, leaf depths,
- * costs, canonical codes and the header bit string run on all threads; only the two-queue merge, the RLE
- * tokenisation and the 19-symbol code-length tree stay on one thread.  Results are identical to the serial
- * form (tests compare the GPU stream with the host model bit for bit). */
+ * costs, canonical codes and the header bit string run on all threads; the distance tree and the 19-symbol
+ * code-length tree stay on one thread.  The two-queue merge of the literal/length tree — an inherently serial
+ * walk of up to 285 steps — is taken out into zs_merge_kernel, where every lane merges a different block
+ * (in here it kept one lane busy and 127 waiting for 41 % of a block's time): PHASE 0 is everything before
+ * it, PHASE 1 everything after.  Results are identical to the serial form (tests compare the GPU stream with
+ * the host model bit for bit). */
+template <int PHASE>
 __global__ void __launch_bounds__(ZB_THREADS)
 zs_block_kernel(const ZsChunk *__restrict__ chunks, const uint32_t *__restrict__ blk_chunk,
                 const uint32_t *__restrict__ sym, const uint32_t *__restrict__ chunk_nsym,
                 const uint32_t *__restrict__ blk_in_start, zh_block *__restrict__ blocks,
-                uint4 *__restrict__ blk_meta, ZsLzParams P)
+                uint4 *__restrict__ blk_meta, ZbScratch *__restrict__ scratch, uint32_t *__restrict__ used /* [0] = count, then slots */,
+                ZsLzParams P)
 {
     __shared__ __align__(16) ZbSmem S;
     const uint32_t b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -47,10 +64,12 @@ zs_block_kernel(const ZsChunk *__restrict__ chunks, const uint32_t *__restrict__
     const uint32_t nsym = chunk_nsym[c];
     uint32_t nblk = (nsym + ZS_BLOCK_SYMS - 1) / ZS_BLOCK_SYMS;
     if (nblk == 0) nblk = 1;
-    if (k >= nblk) { if (tid == 0) { blocks[b].type = ZH_UNUSED; blocks[b].flags = 0; blk_meta[b] = make_uint4(ZH_UNUSED, 0, 0, 0); } return; }
+    if (k >= nblk) { if (PHASE == 0 && tid == 0) { blocks[b].type = ZH_UNUSED; blocks[b].flags = 0; blk_meta[b] = make_uint4(ZH_UNUSED, 0, 0, 0); } return; }
     const uint32_t cnt = min(ZS_BLOCK_SYMS, nsym - k * ZS_BLOCK_SYMS);
     const uint32_t *bs = sym + cd.sym_off + (uint64_t)k * ZS_BLOCK_SYMS;
-
+    ZbScratch &X = scratch[b];
+    int m;
+  if (PHASE == 0) {
     /* ---- histogram ---- */
     for (uint32_t i = tid; i < ZB_WARPS * ZH_LCODES_PAD; i += ZB_THREADS) (&S.lfreq[0][0])[i] = 0;
     for (uint32_t i = tid; i < ZB_WARPS * ZH_DCODES_PAD; i += ZB_THREADS) (&S.dfreq[0][0])[i] = 0;
@@ -109,7 +128,7 @@ zs_block_kernel(const ZsChunk *__restrict__ chunks, const uint32_t *__restrict__
     __syncthreads();
     /* fewer than two used symbols (an empty block): the serial routine adds the dummy symbols */
     if (S.m < 2) { if (tid == 0) S.m = zh_lengths_prepare(S.lfreq[0], ZH_LCODES, &S.sc, &S.max_l); __syncthreads(); }
-    const int m = S.m;
+    m = S.m;
     /* ---- rank sort of the keys (unique) on all threads; the distance tree meanwhile on one thread ---- */
     {
         uint32_t *sorted = S.sc.w + ZH_LCODES_PAD;          /* free until the merge starts */
@@ -135,10 +154,24 @@ zs_block_kernel(const ZsChunk *__restrict__ chunks, const uint32_t *__restrict__
         for (int i = (int)tid; i < m; i += ZB_THREADS) S.sc.key[i] = sorted[i];
     }
     __syncthreads();
-    /* ---- merges: literal tree on thread 0, the whole distance tree on thread 32 ---- */
-    if (tid == 0) (void)zh_merge(m, &S.sc);
-    if (tid == 32) S.max_d = zh_lengths(S.dfreq[0], ZH_DCODES, 15, S.sc.dlen, &S.sc2);
+    /* ---- the whole distance tree on thread 32 while the others write the hand-over ---- */
+    if (tid == 32) { S.max_d = zh_lengths(S.dfreq[0], ZH_DCODES, 15, S.sc.dlen, &S.sc2); X.max_d = S.max_d; X.m = m; X.max_l = S.max_l; }
+    for (uint32_t i = tid; i < ZH_LCODES_PAD; i += ZB_THREADS) { X.key[i] = S.sc.key[i]; X.lfreq[i] = S.lfreq[0][i]; }
+    if (tid < ZH_DCODES_PAD) X.dfreq[tid] = S.dfreq[0][tid];
+    if (tid == 0) used[1 + atomicAdd(&used[0], 1u)] = b;
     __syncthreads();
+    if (tid < ZH_DCODES_PAD) X.dlen[tid] = S.sc.dlen[tid];
+    return;
+  } else {
+    /* ---- PHASE 1: read the hand-over back ---- */
+    if (tid < 16) { S.bl_count[tid] = 0; S.cnt_l[tid] = 0; S.cnt_d[tid] = 0; }
+    if (tid == 0) { S.m = X.m; S.max_l = X.max_l; S.max_d = X.max_d; S.overflow = 0; }
+    for (uint32_t i = tid; i < ZH_LCODES_PAD; i += ZB_THREADS) { S.sc.key[i] = X.key[i]; S.lfreq[0][i] = X.lfreq[i]; S.sc.llen[i] = 0; }
+    for (uint32_t i = tid; i < 2 * ZH_LCODES_PAD; i += ZB_THREADS) S.sc.parent[i] = X.parent[i];
+    if (tid < ZH_DCODES_PAD) { S.dfreq[0][tid] = X.dfreq[tid]; S.sc.dlen[tid] = X.dlen[tid]; }
+    __syncthreads();
+    m = S.m;
+  }
     /* ---- leaf depths in parallel, clipped to 15 ---- */
     {
         const uint32_t root = 2u * (uint32_t)m - 2u;
@@ -397,6 +430,37 @@ zs_block_kernel(const ZsChunk *__restrict__ chunks, const uint32_t *__restrict__
     for (uint32_t i = tid; i < sizeof(zh_block) / 4; i += ZB_THREADS) dst[i] = src[i];
     /* what the offset pass needs, 16 bytes per block instead of a walk over the large records */
     if (tid == 0) blk_meta[b] = make_uint4(S.blk.type, S.blk.body_bits, S.blk.in_len, S.blk.flags);
+}
+
+/* ======================= K2m: two-queue Huffman merge, one block per lane ======================= */
+#define ZMG_THREADS 64
+
+/* Leaves are the sorted keys (weight = key >> 9), read from the hand-over; the weights of the internal nodes,
+ * which the merge both appends and consumes in order, live in shared memory, one column per lane (bank =
+ * lane: conflict-free whatever row each lane is at).  Same picks as zh_merge (huff_build.h): the smaller
+ * head of the two queues, the leaf on ties. */
+__global__ void __launch_bounds__(ZMG_THREADS)
+zs_merge_kernel(ZbScratch *__restrict__ scratch, const uint32_t *__restrict__ used)
+{
+    extern __shared__ uint32_t zmg_w[];                    /* [ZH_LCODES_PAD][ZMG_THREADS] */
+    const uint32_t t = blockIdx.x * ZMG_THREADS + threadIdx.x;
+    if (t >= used[0]) return;
+    ZbScratch &X = scratch[used[1 + t]];
+    const int m = X.m;
+    uint32_t *w = zmg_w + threadIdx.x;
+    int a = 0, b = 0, e = 0;                               /* leaves taken, internal nodes taken, internal nodes made */
+    uint32_t la = X.key[0] >> 9, ib = 0xFFFFFFFFu;         /* heads of the two queues */
+    for (int it = 0; it < m - 1; it++) {
+        uint32_t sum; int x0, x1;
+        if (a < m && la <= ib) { x0 = a++; sum = la; la = a < m ? X.key[a] >> 9 : 0xFFFFFFFFu; }
+        else { x0 = m + b++; sum = ib; ib = b < e ? w[b * ZMG_THREADS] : 0xFFFFFFFFu; }
+        if (a < m && la <= ib) { x1 = a++; sum += la; la = a < m ? X.key[a] >> 9 : 0xFFFFFFFFu; }
+        else { x1 = m + b++; sum += ib; ib = b < e ? w[b * ZMG_THREADS] : 0xFFFFFFFFu; }
+        w[e * ZMG_THREADS] = sum;
+        X.parent[x0] = (uint16_t)(m + e); X.parent[x1] = (uint16_t)(m + e);
+        if (b == e) ib = sum;                              /* the queue was empty: the new node is its head */
+        e++;
+    }
 }
 
 /* ======================= K2b: stored-run merging (thread per chunk), offsets (one CTA per stream) ======================= */
@@ -734,6 +798,7 @@ zs_encode_kernel(const zh_block *__restrict__ blocks, const uint32_t *__restrict
 }
 
 extern "C" size_t zs_encode_smem_bytes(void) { return sizeof(ZeSmem); }
+extern "C" size_t zs_block_scratch_bytes(void) { return sizeof(ZbScratch); }
 
 extern "C" cudaError_t zs_huff_launch(cudaStream_t st, uint32_t nblk_slots, uint32_t nstreams,
                                       const ZsChunk *chunks, const uint32_t *blk_chunk,
@@ -743,12 +808,21 @@ extern "C" cudaError_t zs_huff_launch(cudaStream_t st, uint32_t nblk_slots, uint
                                       const uint8_t *raw, uint8_t *comp, int32_t *res_ret,
                                       uint32_t *res_produced, uint32_t *res_check, ZsLzParams P,
                                       cudaEvent_t ev_after_block, cudaEvent_t ev_after_offset,
-                                      uint32_t nchunks, void *blk_meta_v, unsigned long long *blk_bitoff_v)
+                                      uint32_t nchunks, void *blk_meta_v, unsigned long long *blk_bitoff_v,
+                                      void *blk_scratch_v, uint32_t *blk_used)
 {
     if (nblk_slots == 0 || nstreams == 0) return cudaSuccess;
     uint4 *blk_meta = reinterpret_cast<uint4 *>(blk_meta_v);
     uint64_t *blk_bitoff = reinterpret_cast<uint64_t *>(blk_bitoff_v);
-    zs_block_kernel<<<nblk_slots, ZB_THREADS, 0, st>>>(chunks, blk_chunk, sym, chunk_nsym, blk_in_start, blocks, blk_meta, P);
+    ZbScratch *scratch = reinterpret_cast<ZbScratch *>(blk_scratch_v);
+    cudaMemsetAsync(blk_used, 0, 4, st);
+    zs_block_kernel<0><<<nblk_slots, ZB_THREADS, 0, st>>>(chunks, blk_chunk, sym, chunk_nsym, blk_in_start, blocks, blk_meta, scratch, blk_used, P);
+    {
+        const size_t smem = sizeof(uint32_t) * ZH_LCODES_PAD * ZMG_THREADS;
+        cudaFuncSetAttribute(zs_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        zs_merge_kernel<<<(nblk_slots + ZMG_THREADS - 1) / ZMG_THREADS, ZMG_THREADS, smem, st>>>(scratch, blk_used);
+    }
+    zs_block_kernel<1><<<nblk_slots, ZB_THREADS, 0, st>>>(chunks, blk_chunk, sym, chunk_nsym, blk_in_start, blocks, blk_meta, scratch, blk_used, P);
     if (ev_after_block) cudaEventRecord(ev_after_block, st);
     zs_stored_merge_kernel<<<(nchunks + ZM_THREADS - 1) / ZM_THREADS, ZM_THREADS, 0, st>>>(chunks, nchunks, blocks, blk_meta);
     /* few streams with many blocks each: wide CTAs; many small streams: narrow ones */

@@ -17,7 +17,8 @@ extern "C" uint32_t zs_lz_fast_max_dist(void);
 extern "C" cudaError_t zs_huff_launch(cudaStream_t, uint32_t, uint32_t, const ZsChunk *, const uint32_t *, const ZsStream *, const uint32_t *,
                                       const uint32_t *, const uint32_t *, zh_block *, const ZsAdlerAcc *, const uint8_t *, uint8_t *,
                                       int32_t *, uint32_t *, uint32_t *, ZsLzParams, cudaEvent_t, cudaEvent_t,
-                                      uint32_t, void *, unsigned long long *);
+                                      uint32_t, void *, unsigned long long *, void *, uint32_t *);
+extern "C" size_t zs_block_scratch_bytes(void);
 extern "C" cudaError_t zs_adler_chunks_launch(cudaStream_t, uint32_t, const uint8_t *, const ZsChunk *, const ZsStream *, ZsAdlerAcc *);
 extern "C" cudaError_t zs_adler_flat_launch(cudaStream_t, const uint8_t *, uint64_t, ZsAdlerAcc *, int);
 extern "C" cudaError_t zs_crc_init_launch(cudaStream_t);
@@ -44,6 +45,8 @@ struct zscgpu_engine {
     zh_block *d_blocks;
     uint4 *d_blk_meta;            /* per block slot: type, body_bits, in_len, flags (what the offset pass reads) */
     unsigned long long *d_blk_bitoff;
+    uint8_t *d_blk_scratch;           /* per block slot: what the three block kernels hand to each other (deflate_huff.cu ZbScratch) */
+    uint32_t *d_blk_used;             /* [0] = number of used block slots of the launch, then their indices */
     ZsAdlerAcc *d_adler;              /* per stream; slot max_streams is the flat-checksum slot */
     uint32_t *d_crc;                  /* [2] */
     uint32_t *d_aux;                  /* inflate: [2 * max_streams] trailer check + flags */
@@ -145,6 +148,8 @@ extern "C" int zscgpu_init(const zscgpu_config *cfg_in, zscgpu_engine **out)
     ZS_CUDA_CHECK(zs_dev(&e->d_blocks, e->blk_cap));
     ZS_CUDA_CHECK(zs_dev(&e->d_blk_meta, e->blk_cap));
     ZS_CUDA_CHECK(zs_dev(&e->d_blk_bitoff, e->blk_cap));
+    ZS_CUDA_CHECK(zs_dev(&e->d_blk_scratch, (size_t)e->blk_cap * zs_block_scratch_bytes()));
+    ZS_CUDA_CHECK(zs_dev(&e->d_blk_used, (size_t)e->blk_cap + 1));
     ZS_CUDA_CHECK(zs_dev(&e->d_adler, cfg.max_streams + 1));
     ZS_CUDA_CHECK(zs_dev(&e->d_crc, 4));
     ZS_CUDA_CHECK(zs_dev(&e->d_aux, 2ull * cfg.max_streams));
@@ -188,7 +193,7 @@ extern "C" void zscgpu_destroy(zscgpu_engine *e)
     cudaFreeHost(e->h_chunks); cudaFree(e->d_chunks);
     cudaFreeHost(e->h_streams); cudaFree(e->d_streams);
     cudaFreeHost(e->h_blk_chunk); cudaFree(e->d_blk_chunk);
-    cudaFree(e->d_chunk_nsym); cudaFree(e->d_blk_in_start); cudaFree(e->d_blocks); cudaFree(e->d_blk_meta); cudaFree(e->d_blk_bitoff);
+    cudaFree(e->d_chunk_nsym); cudaFree(e->d_blk_in_start); cudaFree(e->d_blocks); cudaFree(e->d_blk_meta); cudaFree(e->d_blk_bitoff); cudaFree(e->d_blk_scratch); cudaFree(e->d_blk_used);
     cudaFree(e->d_adler); cudaFree(e->d_crc); cudaFree(e->d_aux); cudaFreeHost(e->h_aux); cudaFree(e->d_cand); cudaFreeHost(e->h_cand);
     free(e->sec_start); free(e->sec_st); free(e->sec_r1);
     cudaFree(e->d_ret); cudaFree(e->d_produced); cudaFree(e->d_consumed); cudaFree(e->d_check);
@@ -417,13 +422,13 @@ static int zs_deflate_launch_all(zscgpu_engine *e)
     ZS_CUDA_CHECK(cudaEventRecord(e->ev[10], e->stream));
     ZS_CUDA_CHECK(zs_huff_launch(e->stream, nb, n, e->d_chunks, e->d_blk_chunk, e->d_streams, e->d_sym, e->d_chunk_nsym,
                                  e->d_blk_in_start, e->d_blocks, e->d_adler, e->d_raw, e->d_comp, e->d_ret, e->d_produced, e->d_check, e->last_lz,
-                                 e->ev[11], e->ev[12], nc, e->d_blk_meta, e->d_blk_bitoff));
+                                 e->ev[11], e->ev[12], nc, e->d_blk_meta, e->d_blk_bitoff, e->d_blk_scratch, e->d_blk_used));
     ZS_CUDA_CHECK(cudaEventRecord(e->ev[13], e->stream));
     ZS_CUDA_CHECK(cudaMemcpyAsync(e->h_ret, e->d_ret, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, e->stream));
     ZS_CUDA_CHECK(cudaMemcpyAsync(e->h_produced, e->d_produced, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, e->stream));
     ZS_CUDA_CHECK(cudaMemcpyAsync(e->h_check, e->d_check, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, e->stream));
-    e->launches = 6;   /* adler, lz, block, stored-run merge, offset, encode */
-    e->launches_total += 6;
+    e->launches = 8;   /* adler, lz, block (histogram / tree merge / codes), stored-run merge, offset, encode */
+    e->launches_total += 8;
     return ZSCGPU_OK;
 }
 
