@@ -29,7 +29,6 @@ struct ZwLut { uint32_t len[32]; uint32_t dist[32]; };     /* base | extra bits 
 template <int G> struct ZwStream {
     zi_tables T;
     zi_aux X;
-    zi_fast F;
     uint32_t q[G];
 };
 
@@ -118,7 +117,7 @@ zs_inflate_group_kernel(uint32_t n, const ZsStream *__restrict__ streams, const 
        if the batch's wrap has one, still follows its final block) */
     const uint32_t sopt = st.chunk_first;
     zi_mach m;
-    zi_m_init(&m, in, st.comp_cap, out, st.raw_len, wrap, &w.T, &w.X, &w.F);
+    zi_m_init(&m, in, st.comp_cap, out, st.raw_len, wrap, &w.T, &w.X);
     m.opts = sopt & 3u;
     if ((sopt & 4u) && m.state == ZM_HEAD) m.state = ZM_BLOCK;
     const bool count_only = (sopt & ZI_OPT_COUNT_ONLY) != 0;

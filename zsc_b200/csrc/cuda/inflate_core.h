@@ -30,7 +30,9 @@
 #define ZID static inline
 #endif
 
+#ifndef ZI_LBITS
 #define ZI_LBITS 10
+#endif
 #define ZI_DBITS 8
 
 #define ZI_OK 0
@@ -54,11 +56,6 @@ typedef struct {                     /* hot: 2640 bytes per stream */
     uint32_t lfirst, lindex, dfirst, dindex;   /* where zi_decode's canonical walk stands after the lengths the direct
                                                   tables resolve (set with the tables; read by zi_fast_batch) */
 } zi_tables;
-
-typedef struct {                     /* first-level tables: shared memory on the GPU, 384 bytes per stream */
-    uint16_t lit7[128];              /* literal/length codes of <= 7 bits, indexed by 7 bits; 0 = look further */
-    uint16_t dist6[64];              /* distance codes of <= 6 bits, indexed by 6 bits; 0 = look further */
-} zi_fast;
 
 typedef struct {                     /* cold: only the rare codes longer than the direct tables read these
                                         (global memory on the GPU) */
@@ -244,7 +241,7 @@ ZID int zi_fail(zi_result *r, int ret, int reason)
 
 /* Block header: BFINAL / BTYPE, then either the stored-block length (cursor left on the first payload
  * byte) or the decode tables of a fixed / dynamic block.  Returns ZI_OK or the failure code. */
-ZID int zi_block_head(zi_io *io, zi_tables *T, zi_aux *X, zi_fast *F, zi_result *res, uint32_t *last_out, uint32_t *type_out, uint32_t *stored_len)
+ZID int zi_block_head(zi_io *io, zi_tables *T, zi_aux *X, zi_result *res, uint32_t *last_out, uint32_t *type_out, uint32_t *stored_len)
 {
     const uint8_t order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
     zi_refill(io);
@@ -352,9 +349,6 @@ ZID int zi_block_head(zi_io *io, zi_tables *T, zi_aux *X, zi_fast *F, zi_result 
                 }
             }
     }
-    /* first-level copies of the short codes */
-    for (int i = 0; i < 128; i++) { uint16_t e = T->lit[i]; F->lit7[i] = (e && (e >> 9) <= 7) ? e : (uint16_t)0; }
-    for (int i = 0; i < 64; i++) { uint16_t e = T->dist[i]; F->dist6[i] = (e && (e >> 5) <= 6) ? e : (uint16_t)0; }
     zi_walk_start(T->lcount, ZI_LBITS, &T->lfirst, &T->lindex);
     zi_walk_start(T->dcount, ZI_DBITS, &T->dfirst, &T->dindex);
     return ZI_OK;
@@ -395,7 +389,6 @@ typedef struct {
     zi_result res;
     zi_tables *T;
     zi_aux *X;
-    zi_fast *F;
     int32_t state, wrap;
     uint32_t last, rem, dist, win, maxw, held;
     uint32_t opts;          /* ZI_OPT_*: section-parallel decoding of one stream (engine.cu zs_inflate_sectioned) */
@@ -404,7 +397,7 @@ typedef struct {
 #define ZI_OPT_COUNT_ONLY 1u        /* advance the output position without writing (sizes of the sections) */
 #define ZI_OPT_STOP_AT_FLUSH 2u     /* end, successfully, behind the first empty non-final stored block */
 
-ZID void zi_m_init(zi_mach *m, const uint8_t *in, uint32_t in_len, uint8_t *out, uint32_t out_cap, int wrap, zi_tables *T, zi_aux *X, zi_fast *F)
+ZID void zi_m_init(zi_mach *m, const uint8_t *in, uint32_t in_len, uint8_t *out, uint32_t out_cap, int wrap, zi_tables *T, zi_aux *X)
 {
     m->io.in = in; m->io.in_len = in_len; m->io.ip = 0; m->io.hold = 0; m->io.bits = 0;
     m->io.out = out; m->io.out_cap = out_cap; m->io.op = 0; m->io.pre = 0; m->io.pv = 0;
@@ -414,7 +407,7 @@ ZID void zi_m_init(zi_mach *m, const uint8_t *in, uint32_t in_len, uint8_t *out,
     m->maxw = ((wrap >> 8) & 0xFF) ? (uint32_t)((wrap >> 8) & 0xFF) : 15u;
     m->wrap = wrap & 0xFF;
     m->win = 1u << m->maxw;
-    m->T = T; m->X = X; m->F = F; m->last = 0; m->rem = 0; m->dist = 0; m->held = 0; m->opts = 0;
+    m->T = T; m->X = X; m->last = 0; m->rem = 0; m->dist = 0; m->held = 0; m->opts = 0;
     m->res.at_flush = 0;
     m->state = m->wrap == 1 ? ZM_HEAD : ZM_BLOCK;
 }
@@ -444,17 +437,11 @@ ZID void zi_step(zi_mach *m)
     zi_result *res = &m->res;
     zi_tables *T = m->T;
     zi_aux *X = m->X;
-    zi_fast *F = m->F;
     if (m->state == ZM_SYM) {
         /* up to two symbols: most are literals, and two keep the lanes of a warp busy between copies */
         for (int rep = 0; rep < 2 && m->state == ZM_SYM; rep++) {
             zi_refill(io);
-            int s;
-            {
-                const uint32_t e7 = F->lit7[zi_peek(io, 7)];
-                if (e7) { zi_drop(io, (int)(e7 >> 9)); s = (int)(e7 & 511u); }
-                else s = zi_decode(io, T->lit, ZI_LBITS, X->lsorted, T->lcount, 9);
-            }
+            const int s = zi_decode(io, T->lit, ZI_LBITS, X->lsorted, T->lcount, 9);
             if (zi_overrun(io)) { zi_m_fail(m, zi_fail(res, ZI_BUF_ERROR, ZI_E_INPUT_END), 0); break; }
             if (s < 0) { zi_m_fail(m, zi_fail(res, ZI_DATA_ERROR, ZI_E_LITLEN_CODE), 0); break; }
             if (s < 256) {
@@ -470,12 +457,7 @@ ZID void zi_step(zi_mach *m)
             else if (c == 28) len = 258;
             else { uint32_t eb = (c - 4) >> 2; len = 3 + ((4 + (c & 3)) << eb) + zi_take(io, (int)eb); }
             zi_refill(io);
-            int d;
-            {
-                const uint32_t e6 = F->dist6[zi_peek(io, 6)];
-                if (e6) { zi_drop(io, (int)(e6 >> 5)); d = (int)(e6 & 31u); }
-                else d = zi_decode(io, T->dist, ZI_DBITS, X->dsorted, T->dcount, 5);
-            }
+            const int d = zi_decode(io, T->dist, ZI_DBITS, X->dsorted, T->dcount, 5);
             if (d < 0 || d > 29) {
                 int ov = zi_overrun(io);
                 zi_m_fail(m, zi_fail(res, ov ? ZI_BUF_ERROR : ZI_DATA_ERROR, ov ? ZI_E_INPUT_END : ZI_E_DIST_CODE), 0);
@@ -526,7 +508,7 @@ ZID void zi_step(zi_mach *m)
     }
     if (m->state == ZM_BLOCK) {
         uint32_t type = 0, slen = 0;
-        int r = zi_block_head(io, T, X, F, res, &m->last, &type, &slen);
+        int r = zi_block_head(io, T, X, res, &m->last, &type, &slen);
         if (r != ZI_OK) { zi_m_fail(m, r, (r == ZI_DATA_ERROR && res->last_reason == ZI_E_STORED_LEN) ? 4u : 0u); return; }
         if (type == 0) {
             if (slen == 0 && !m->last && (m->opts & ZI_OPT_STOP_AT_FLUSH)) { res->at_flush = 1; zi_m_finish(m, ZI_OK); return; }
@@ -568,62 +550,14 @@ ZID void zi_step(zi_mach *m)
     }
 }
 
-/* ---- batch form of the symbol state: one warp per stream ------------------------------------------
- * zs_inflate_warp_kernel gives a stream a whole warp: lane 0 runs this state machine, but inside a compressed
- * block it decodes up to ZI_BATCH symbols into a record queue without touching the output
- * (zi_sym_batch), and the 32 lanes then write the literals and perform the copies together.  Records use
- * the LZ kernel's symbol format: literal byte, or bit 31 | (len - 3) << 16 | (dist - 1).
- *
- * A symbol only enters a batch when the longest match still fits the output and the longest code cannot run
- * past the input, so inside a batch the only possible failures are data errors, with exactly the bits
- * consumed and the output produced that zi_step would have at that point; everything near the ends of the
- * buffers, and every other state, goes through zi_step itself.  Results are identical by construction and
- * tests/ runs both forms over the same vectors. */
+/* ---- group form of the decoder: G lanes per stream (zs_inflate_group_kernel) ------------------------
+ * The leader lane of a group runs the state machine above; inside a compressed block it first lets
+ * zi_fast_batch decode up to G symbols into a record queue without touching the output, and the G lanes then
+ * write the literals and perform the copies together.  Records use the LZ kernel's symbol format: literal
+ * byte, or bit 31 | (len - 3) << 16 | (dist - 1).  zi_fast_batch is a pure accelerator: whatever it does not
+ * take (see below) is left, unconsumed, to zi_step, so results are those of the one-thread decoder by
+ * construction; tests/ runs both forms over the same vectors and asserts equality. */
 #define ZI_BATCH 32
-
-ZID uint32_t zi_sym_batch(zi_mach *m, uint32_t *q, uint32_t *vop)
-{
-    zi_io *io = &m->io;
-    zi_result *res = &m->res;
-    zi_tables *T = m->T;
-    zi_aux *X = m->X;
-    zi_fast *F = m->F;
-    uint32_t n = 0, op = io->op;
-    while (n < ZI_BATCH) {
-        if ((uint64_t)op + 258u > io->out_cap || (uint64_t)io->ip + 16u > io->in_len) break;
-        zi_refill(io);
-        int s;
-        {
-            const uint32_t e7 = F->lit7[zi_peek(io, 7)];
-            if (e7) { zi_drop(io, (int)(e7 >> 9)); s = (int)(e7 & 511u); }
-            else s = zi_decode(io, T->lit, ZI_LBITS, X->lsorted, T->lcount, 9);
-        }
-        if (s < 0) { zi_m_fail(m, zi_fail(res, ZI_DATA_ERROR, ZI_E_LITLEN_CODE), 0); break; }
-        if (s < 256) { q[n++] = (uint32_t)s; op++; continue; }
-        if (s == 256) { m->state = m->last ? ZM_TRAIL : ZM_BLOCK; break; }
-        if (s > 285) { zi_m_fail(m, zi_fail(res, ZI_DATA_ERROR, ZI_E_LITLEN_CODE), 0); break; }
-        uint32_t c = (uint32_t)s - 257, len;
-        if (c < 8) len = 3 + c;
-        else if (c == 28) len = 258;
-        else { uint32_t eb = (c - 4) >> 2; len = 3 + ((4 + (c & 3)) << eb) + zi_take(io, (int)eb); }
-        zi_refill(io);
-        int d;
-        {
-            const uint32_t e6 = F->dist6[zi_peek(io, 6)];
-            if (e6) { zi_drop(io, (int)(e6 >> 5)); d = (int)(e6 & 31u); }
-            else d = zi_decode(io, T->dist, ZI_DBITS, X->dsorted, T->dcount, 5);
-        }
-        if (d < 0 || d > 29) { zi_m_fail(m, zi_fail(res, ZI_DATA_ERROR, ZI_E_DIST_CODE), 0); break; }
-        uint32_t dist;
-        if (d < 4) dist = 1 + (uint32_t)d;
-        else { uint32_t eb = ((uint32_t)d - 2) >> 1; dist = 1 + ((2 + ((uint32_t)d & 1)) << eb) + zi_take(io, (int)eb); }
-        if (dist > op || dist > m->win) { zi_m_fail(m, zi_fail(res, ZI_DATA_ERROR, ZI_E_DIST_TOO_FAR), 0); break; }
-        q[n++] = 0x80000000u | ((len - 3u) << 16) | (dist - 1u);
-        op += len;
-    }
-    *vop = op;
-    return n;
-}
 
 /* ---- the accelerated symbol decoder of the group kernel (zs_inflate_group_kernel) --------------------
  * base | extra bits << 16 of a length code (0..28) / distance code (0..29), RFC 1951 3.2.5 */
@@ -746,8 +680,7 @@ ZID void zi_inflate(const uint8_t *in, uint32_t in_len, uint8_t *out, uint32_t o
 {
     zi_mach m;
     zi_aux X;
-    zi_fast F;
-    zi_m_init(&m, in, in_len, out, out_cap, wrap, T, &X, &F);
+    zi_m_init(&m, in, in_len, out, out_cap, wrap, T, &X);
     while (m.state != ZM_DONE) zi_step(&m);
     *res = m.res;
 }
@@ -759,11 +692,10 @@ ZID void zi_inflate_batched(const uint8_t *in, uint32_t in_len, uint8_t *out, ui
 {
     zi_mach m;
     zi_aux X;
-    zi_fast F;
     uint32_t q[ZI_BATCH], lut_len[32], lut_dist[32];
     for (uint32_t c = 0; c < 29; c++) lut_len[c] = zi_lut_len(c);
     for (uint32_t d = 0; d < 30; d++) lut_dist[d] = zi_lut_dist(d);
-    zi_m_init(&m, in, in_len, out, out_cap, wrap, T, &X, &F);
+    zi_m_init(&m, in, in_len, out, out_cap, wrap, T, &X);
     while (m.state != ZM_DONE) {
         if (m.state == ZM_SYM) {
             uint32_t vop = 0, p = m.io.op;
