@@ -1,4 +1,5 @@
-"""Inflate throughput probe: N reference-compressed 256 KiB streams (levels 1/6/9 in thirds), replicated."""
+"""Inflate throughput probe: N reference-compressed 256 KiB streams (levels 1/6/9 in thirds), replicated.
+usage: prof_inflate.py UNIQ REP [G,G,...]   (G = forced lanes per stream, 0 = the engine's own choice)"""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -7,6 +8,7 @@ from zsc_b200 import Engine, datagen
 import refimpl
 uniq = int(sys.argv[1]) if len(sys.argv) > 1 else 512
 rep = int(sys.argv[2]) if len(sys.argv) > 2 else 8
+gs = [int(g) for g in sys.argv[3].split(",")] if len(sys.argv) > 3 else [0]
 S = 262144
 n = uniq * rep
 E = Engine(raw_bytes=n * S + (1 << 20), comp_bytes=n * 160000 + (1 << 20), deflate_batch_max=uniq * S + (1 << 20), max_streams=n, max_chunks=uniq + 16)
@@ -14,37 +16,49 @@ x = np.concatenate([datagen.mixed(uniq // 2 * S, seed=1), datagen.telemetry_buff
 R = refimpl.ref() if refimpl.have_ref() else None
 t = time.time()
 comps = []
-if R is not None and uniq <= 1024:
-    import bench
-    import ctypes as C
-    L = C.CDLL(refimpl.REF_PATH, mode=C.RTLD_LOCAL)
-    for i in range(uniq):
-        r, c = R.compress(x[i * S:(i + 1) * S], S, (1, 6, 9)[i % 3])
-        comps.append(c)
+cache = f"/tmp/zsc_prof_inflate_{uniq}.npz"
+if os.path.exists(cache):
+    z = np.load(cache)
+    comps = [z[f"c{i}"] for i in range(uniq)]
+elif R is not None and uniq <= 1024:
+    from concurrent.futures import ThreadPoolExecutor
+    def one(i):
+        return R.compress(x[i * S:(i + 1) * S], S, (1, 6, 9)[i % 3])[1]
+    with ThreadPoolExecutor(os.cpu_count() or 4) as ex:      # ctypes releases the GIL inside the reference
+        comps = list(ex.map(one, range(uniq)))
+    np.savez(cache, **{f"c{i}": c for i, c in enumerate(comps)})
 else:
     E.upload(0, 0, x)
     st = Engine.make_streams([i * S for i in range(uniq)], [S] * uniq, [i * 160000 for i in range(uniq)], [160000] * uniq)
     res = E.deflate(st, S, 6)
     for i in range(uniq):
         comps.append(E.download(1, i * 160000, res[i].produced))
-print("compressed", uniq, "streams in %.1fs" % (time.time() - t), "avg", sum(len(c) for c in comps) / uniq)
-offs, off = [], 0
-buf = np.zeros(n * 160000, np.uint8)
+print("compressed", uniq, "streams in %.1fs" % (time.time() - t), "avg", sum(len(c) for c in comps) / uniq, flush=True)
+one_rep = np.zeros(uniq * 160000, np.uint8)
+offs1, off = [], 0
+for i in range(uniq):
+    c = comps[i]
+    one_rep[off:off + len(c)] = c
+    offs1.append((off, len(c)))
+    off += (len(c) + 15) & ~15
+rep_bytes = off
+offs = []
 for r_ in range(rep):
-    for i in range(uniq):
-        c = comps[i]
-        buf[off:off + len(c)] = c
-        offs.append((off, len(c)))
-        off += (len(c) + 15) & ~15
-E.upload(1, 0, buf[:off])
+    E.upload(1, r_ * rep_bytes, one_rep[:rep_bytes])
+    offs += [(r_ * rep_bytes + o, l) for o, l in offs1]
 st = Engine.make_streams([i * S for i in range(n)], [S] * n, [o[0] for o in offs], [o[1] for o in offs])
-E.inflate_enqueue(st, 1)
-res = E.fetch(n)
-bad = sum(1 for r in res if r.ret != 0 or r.produced != S)
-back = E.download(0, 0, uniq * S)
-ok = bool(np.array_equal(back, x))
-ts = []
-for _ in range(3):
-    E.event(0); E.relaunch(); E.event(1); E.sync(); ts.append(E.elapsed_ms(0, 1))
-print("streams", n, "bad", bad, "bytes_ok", ok, "ms", [round(t, 2) for t in ts], "GB/s", round(n * S / 1e6 / min(ts), 2))
+for g in gs:
+    if g:
+        os.environ["ZSC_B200_INFLATE_G"] = str(g)
+    else:
+        os.environ.pop("ZSC_B200_INFLATE_G", None)
+    E.inflate_enqueue(st, 1)
+    res = E.fetch(n)
+    bad = sum(1 for r in res if r.ret != 0 or r.produced != S)
+    back = E.download(0, (rep - 1) * uniq * S, uniq * S)
+    ok = bool(np.array_equal(back, x))
+    ts = []
+    for _ in range(3):
+        E.event(0); E.relaunch(); E.event(1); E.sync(); ts.append(E.elapsed_ms(0, 1))
+    print("lib", os.environ.get("ZSC_B200_LIB", "default"), "G", g, "streams", n, "bad", bad, "bytes_ok", ok, "ms", [round(t, 2) for t in ts], "GB/s", round(n * S / 1e6 / min(ts), 2), flush=True)
 E.close()

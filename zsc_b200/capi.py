@@ -9,7 +9,7 @@ import os
 
 import numpy as np
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libzsc_b200.so")
+LIB_PATH = os.environ.get("ZSC_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libzsc_b200.so")   # the override is a tuning aid (tools/build_variant.sh)
 
 Z_OK, Z_STREAM_END, Z_NEED_DICT = 0, 1, 2
 Z_ERRNO, Z_STREAM_ERROR, Z_DATA_ERROR, Z_MEM_ERROR, Z_BUF_ERROR, Z_VERSION_ERROR = -1, -2, -3, -4, -5, -6

@@ -107,8 +107,14 @@ zs_adler_flat_kernel(const uint8_t *__restrict__ p, uint64_t len, ZsAdlerAcc *__
 #define ZC_SUB 256u                     /* bytes per thread */
 #define ZC_PIECE (ZC_THREADS * ZC_SUB)  /* bytes per CTA */
 
+#define ZF_THREADS 1024
+#define ZF_ROW 512u                     /* bytes one warp loads at a time: 32 lanes x 16 bytes */
+#define ZF_MIN_LEN (1u << 20)           /* shorter buffers take zs_crc_flat_kernel */
+
 __device__ uint32_t zc_table[8][256];   /* slicing tables, filled once by zs_crc_init_kernel */
 __device__ uint32_t zc_x2n[32];         /* x^(2^k) mod P, reflected */
+__device__ uint32_t zc_ftab[4][256];    /* fold tables: state byte k -> the state 512 zero bytes later (zs_crc_fold_kernel) */
+__device__ uint32_t zc_ffin[128];       /* x^(8 * (512 - 16 lane - 4 k)) mod P: a row's word to the end of that row */
 
 __host__ __device__ inline uint32_t zc_multmodp(uint32_t a, uint32_t b)
 {
@@ -146,6 +152,12 @@ __global__ void zs_crc_init_kernel()
         zc_x2n[0] = p;
         for (int n = 1; n < 32; n++) { p = zc_multmodp(p, p); zc_x2n[n] = p; }
     }
+    __syncthreads();
+    if (t < 256) {
+        const uint32_t xs = zc_x2nmodp(ZF_ROW, 3);
+        for (int k = 0; k < 4; k++) zc_ftab[k][t] = zc_multmodp(xs, t << (8 * k));
+    }
+    if (t < 128) zc_ffin[t] = zc_x2nmodp(ZF_ROW - 16u * (t >> 2) - 4u * (t & 3u), 3);
 }
 
 __global__ void __launch_bounds__(ZC_THREADS)
@@ -191,6 +203,93 @@ zs_crc_flat_kernel(const uint8_t *__restrict__ p, uint64_t len, uint32_t *__rest
     }
 }
 
+/* a * b mod P without branches (same product as zc_multmodp) */
+__device__ __forceinline__ uint32_t zc_mul(uint32_t a, uint32_t b)
+{
+    uint32_t p = 0;
+#pragma unroll
+    for (int i = 31; i >= 0; i--) {
+        p ^= b & (0u - ((a >> i) & 1u));
+        b = (b >> 1) ^ (ZC_POLY & (0u - (b & 1u)));
+    }
+    return p;
+}
+
+/* raw CRC of n < 512 bytes at p[off..], moved to the end of a buffer of len bytes */
+__device__ uint32_t zc_small(const uint8_t *__restrict__ p, uint64_t off, uint32_t n, uint64_t len)
+{
+    uint32_t c = 0;
+    for (uint32_t i = 0; i < n; i++) c = zc_table[0][(c ^ p[off + i]) & 0xFF] ^ (c >> 8);
+    const uint64_t after = len - off - n;
+    return after ? zc_multmodp(zc_x2nmodp(after, 3), c) : c;
+}
+
+/* CRC-32 of a large buffer at HBM speed.  The CRC register is linear in the message, so the buffer is read
+ * as it lies in memory — a warp loads rows of 512 bytes, lane l the 16 bytes at 16 l: perfectly coalesced —
+ * and every (lane, word-of-four) pair keeps its own register for the sub-message made of its words with
+ * zeros everywhere else.  Between two of its words lie 508 foreign bytes, so one step is
+ * c = F512(c ^ word): four table lookups, exactly the cost of slicing-by-4, with tables built for a
+ * 512-byte advance.  The tables are replicated per lane in shared memory ([entry][lane], 128 KiB), so the
+ * 32 lookups of a warp instruction hit 32 different banks whatever the data.  The last row of a region
+ * is advanced only to the region's end (x^(8 n) constants per lane and word), the 128 registers are XOR-ed,
+ * and the region's CRC is moved to the end of the buffer with x^(8 * bytes after), a product the lanes form
+ * together (one factor per bit of the distance, five shuffle steps). */
+__global__ void __launch_bounds__(ZF_THREADS, 1)
+zs_crc_fold_kernel(const uint8_t *__restrict__ p, uint64_t len, uint32_t head, uint64_t rows, uint32_t R,
+                   uint32_t *__restrict__ acc)
+{
+    extern __shared__ __align__(16) uint32_t zf_tab[];             /* [4 * 256][32] */
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#pragma unroll 4
+    for (uint32_t j = 0; j < 32; j++) { const uint32_t idx = j * ZF_THREADS + tid; zf_tab[idx] = (&zc_ftab[0][0])[idx >> 5]; }
+    __syncthreads();
+    const uint32_t *tl = zf_tab + lane;
+#define ZF_STEP(c, w) { const uint32_t v_ = (c) ^ (w); \
+        (c) = tl[(v_ & 0xFFu) * 32u] ^ tl[(256u + ((v_ >> 8) & 0xFFu)) * 32u] ^ tl[(512u + ((v_ >> 16) & 0xFFu)) * 32u] ^ tl[(768u + (v_ >> 24)) * 32u]; }
+    const uint4 *base = reinterpret_cast<const uint4 *>(p + head);
+    const uint64_t nwarps = (uint64_t)gridDim.x * (ZF_THREADS / 32);
+    for (uint64_t piece = (uint64_t)blockIdx.x * (ZF_THREADS / 32) + warp; piece * R < rows; piece += nwarps) {
+        const uint64_t r0 = piece * R;
+        const uint32_t nr = (uint32_t)min((uint64_t)R, rows - r0);
+        const uint4 *q = base + r0 * 32 + lane;
+        uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0, r = 0;
+        for (; r + 4 < nr; r += 4) {
+            const uint4 v0 = __ldg(q + (size_t)r * 32), v1 = __ldg(q + (size_t)(r + 1) * 32);
+            const uint4 v2 = __ldg(q + (size_t)(r + 2) * 32), v3 = __ldg(q + (size_t)(r + 3) * 32);
+            ZF_STEP(c0, v0.x) ZF_STEP(c1, v0.y) ZF_STEP(c2, v0.z) ZF_STEP(c3, v0.w)
+            ZF_STEP(c0, v1.x) ZF_STEP(c1, v1.y) ZF_STEP(c2, v1.z) ZF_STEP(c3, v1.w)
+            ZF_STEP(c0, v2.x) ZF_STEP(c1, v2.y) ZF_STEP(c2, v2.z) ZF_STEP(c3, v2.w)
+            ZF_STEP(c0, v3.x) ZF_STEP(c1, v3.y) ZF_STEP(c2, v3.z) ZF_STEP(c3, v3.w)
+        }
+        for (; r + 1 < nr; r++) {
+            const uint4 v = __ldg(q + (size_t)r * 32);
+            ZF_STEP(c0, v.x) ZF_STEP(c1, v.y) ZF_STEP(c2, v.z) ZF_STEP(c3, v.w)
+        }
+        const uint4 v = __ldg(q + (size_t)(nr - 1) * 32);
+        uint32_t x = zc_mul(zc_ffin[lane * 4 + 0], c0 ^ v.x) ^ zc_mul(zc_ffin[lane * 4 + 1], c1 ^ v.y) ^
+                     zc_mul(zc_ffin[lane * 4 + 2], c2 ^ v.z) ^ zc_mul(zc_ffin[lane * 4 + 3], c3 ^ v.w);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x ^= __shfl_xor_sync(0xFFFFFFFFu, x, o);
+        const uint64_t after = len - head - (r0 + nr) * ZF_ROW;
+        uint32_t f = ((after >> lane) & 1u) ? zc_x2n[(lane + 3) & 31] : 0x80000000u;
+        if (after >> 32) { if ((after >> (lane + 32)) & 1u) f = zc_mul(f, zc_x2n[(lane + 35) & 31]); }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) f = zc_mul(f, __shfl_xor_sync(0xFFFFFFFFu, f, o));
+        if (lane == 0) atomicXor(acc, zc_mul(f, x));
+    }
+#undef ZF_STEP
+    if (blockIdx.x == 0 && warp < 2) {
+        /* the unaligned head (< 16 bytes) and the bytes behind the last whole row (< 512) */
+        const uint64_t toff = head + rows * ZF_ROW;
+        uint32_t x = 0;
+        if (warp == 0) { const uint64_t o = toff + 16ull * lane; if (o < len) x = zc_small(p, o, (uint32_t)min((uint64_t)16, len - o), len); }
+        else if (lane == 0 && head) x = zc_small(p, 0, head, len);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x ^= __shfl_xor_sync(0xFFFFFFFFu, x, o);
+        if (lane == 0 && x) atomicXor(acc, x);
+    }
+}
+
 /* acc[0] = raw CRC of the buffer; finish: crc = x^(8 len) * (init ^ ~0) ^ raw ^ ~0 */
 __global__ void zs_crc_finish_kernel(uint32_t *acc, uint64_t len, uint32_t init)
 {
@@ -230,9 +329,24 @@ extern "C" cudaError_t zs_crc_init_launch(cudaStream_t st)
 }
 extern "C" cudaError_t zs_crc_flat_launch(cudaStream_t st, const uint8_t *p, uint64_t len, uint32_t init, uint32_t *acc2, int sms)
 {
-    uint64_t pieces = (len + ZC_PIECE - 1) / ZC_PIECE;
-    uint32_t grid = (uint32_t)(pieces < (uint64_t)sms * 8 ? (pieces ? pieces : 1) : (uint64_t)sms * 8);
-    zs_crc_flat_kernel<<<grid, ZC_THREADS, 0, st>>>(p, len, acc2);
+    if (len >= ZF_MIN_LEN) {
+        /* rows of 512 bytes behind the 16-byte alignment point, R rows per warp and pass, passes balanced */
+        const uint32_t head = (uint32_t)((16 - ((uintptr_t)p & 15)) & 15);
+        const uint64_t rows = (len - head) / ZF_ROW;
+        const uint64_t W = (uint64_t)sms * (ZF_THREADS / 32);
+        const uint64_t passes = (rows + W * 128 - 1) / (W * 128);
+        uint64_t R = (rows + W * passes - 1) / (W * passes);
+        if (R < 16) R = 16;
+        const uint64_t warps = (rows + R - 1) / R;
+        const uint32_t grid = (uint32_t)((warps + ZF_THREADS / 32 - 1) / (ZF_THREADS / 32) < (uint64_t)sms ? (warps + ZF_THREADS / 32 - 1) / (ZF_THREADS / 32) : (uint64_t)sms);
+        const int smem = 4 * 256 * 32 * 4;
+        cudaFuncSetAttribute(zs_crc_fold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        zs_crc_fold_kernel<<<grid, ZF_THREADS, smem, st>>>(p, len, head, rows, (uint32_t)R, acc2);
+    } else {
+        uint64_t pieces = (len + ZC_PIECE - 1) / ZC_PIECE;
+        uint32_t grid = (uint32_t)(pieces < (uint64_t)sms * 8 ? (pieces ? pieces : 1) : (uint64_t)sms * 8);
+        zs_crc_flat_kernel<<<grid, ZC_THREADS, 0, st>>>(p, len, acc2);
+    }
     zs_crc_finish_kernel<<<1, 1, 0, st>>>(acc2, len, init);
     return cudaGetLastError();
 }

@@ -24,7 +24,8 @@ extern "C" cudaError_t zs_adler_flat_launch(cudaStream_t, const uint8_t *, uint6
 extern "C" cudaError_t zs_crc_init_launch(cudaStream_t);
 extern "C" cudaError_t zs_crc_flat_launch(cudaStream_t, const uint8_t *, uint64_t, uint32_t, uint32_t *, int);
 extern "C" cudaError_t zs_inflate_launch(cudaStream_t, uint32_t, const ZsStream *, const uint8_t *, uint8_t *, int32_t,
-                                         int32_t *, uint32_t *, uint32_t *, uint32_t *, uint32_t *, ZsAdlerAcc *, uint32_t, int);
+                                         int32_t *, uint32_t *, uint32_t *, uint32_t *, uint32_t *, ZsAdlerAcc *, uint32_t, int, void *);
+extern "C" size_t zs_inflate_aux_bytes(void);
 
 #define ZS_NEVENTS 16
 #define ZS_MAX_WAVES 64
@@ -51,6 +52,7 @@ struct zscgpu_engine {
     uint32_t *d_crc;                  /* [2] */
     uint32_t *d_aux;                  /* inflate: [2 * max_streams] trailer check + flags */
     uint32_t *h_aux;                  /* the same on the host (section passes read the flags) */
+    uint8_t *d_inf_aux;               /* inflate: per stream, the sorted symbols of its current block (codes longer than the direct tables) */
     uint32_t *d_cand, *h_cand;        /* sectioned inflate: [max_streams + 1] positions behind 00 00 FF FF, slot 0 = count */
     uint32_t *sec_start, *sec_opts, *sec_flags, *sec_trailer, *sec_real, *sec_off;   /* its host scratch, [max_streams + 1] each */
     zscgpu_stream *sec_st;            /* [max_streams] */
@@ -154,6 +156,7 @@ extern "C" int zscgpu_init(const zscgpu_config *cfg_in, zscgpu_engine **out)
     ZS_CUDA_CHECK(zs_dev(&e->d_crc, 4));
     ZS_CUDA_CHECK(zs_dev(&e->d_aux, 2ull * cfg.max_streams));
     ZS_CUDA_CHECK(zs_pinned(&e->h_aux, 2ull * cfg.max_streams));
+    ZS_CUDA_CHECK(zs_dev(&e->d_inf_aux, (size_t)cfg.max_streams * zs_inflate_aux_bytes()));
     ZS_CUDA_CHECK(zs_dev(&e->d_cand, (size_t)cfg.max_streams + 1));
     ZS_CUDA_CHECK(zs_pinned(&e->h_cand, (size_t)cfg.max_streams + 1));
     {
@@ -194,7 +197,7 @@ extern "C" void zscgpu_destroy(zscgpu_engine *e)
     cudaFreeHost(e->h_streams); cudaFree(e->d_streams);
     cudaFreeHost(e->h_blk_chunk); cudaFree(e->d_blk_chunk);
     cudaFree(e->d_chunk_nsym); cudaFree(e->d_blk_in_start); cudaFree(e->d_blocks); cudaFree(e->d_blk_meta); cudaFree(e->d_blk_bitoff); cudaFree(e->d_blk_scratch); cudaFree(e->d_blk_used);
-    cudaFree(e->d_adler); cudaFree(e->d_crc); cudaFree(e->d_aux); cudaFreeHost(e->h_aux); cudaFree(e->d_cand); cudaFreeHost(e->h_cand);
+    cudaFree(e->d_adler); cudaFree(e->d_crc); cudaFree(e->d_aux); cudaFreeHost(e->h_aux); cudaFree(e->d_inf_aux); cudaFree(e->d_cand); cudaFreeHost(e->h_cand);
     free(e->sec_start); free(e->sec_st); free(e->sec_r1);
     cudaFree(e->d_ret); cudaFree(e->d_produced); cudaFree(e->d_consumed); cudaFree(e->d_check);
     cudaFreeHost(e->h_ret); cudaFreeHost(e->h_produced); cudaFreeHost(e->h_consumed); cudaFreeHost(e->h_check);
@@ -451,7 +454,7 @@ static int zs_inflate_launch_all(zscgpu_engine *e)
 {
     const uint32_t n = e->last_nstreams;
     ZS_CUDA_CHECK(zs_inflate_launch(e->stream, n, e->d_streams, e->d_comp, e->d_raw, e->last_wrap, e->d_ret, e->d_produced, e->d_consumed, e->d_check,
-                                    e->d_aux, e->d_adler, e->last_max_raw, e->last_with_check));
+                                    e->d_aux, e->d_adler, e->last_max_raw, e->last_with_check, e->d_inf_aux));
     ZS_CUDA_CHECK(cudaMemcpyAsync(e->h_ret, e->d_ret, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, e->stream));
     ZS_CUDA_CHECK(cudaMemcpyAsync(e->h_produced, e->d_produced, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, e->stream));
     ZS_CUDA_CHECK(cudaMemcpyAsync(e->h_consumed, e->d_consumed, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, e->stream));
