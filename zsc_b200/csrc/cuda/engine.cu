@@ -24,8 +24,7 @@ extern "C" cudaError_t zs_adler_flat_launch(cudaStream_t, const uint8_t *, uint6
 extern "C" cudaError_t zs_crc_init_launch(cudaStream_t);
 extern "C" cudaError_t zs_crc_flat_launch(cudaStream_t, const uint8_t *, uint64_t, uint32_t, uint32_t *, int);
 extern "C" cudaError_t zs_inflate_launch(cudaStream_t, uint32_t, const ZsStream *, const uint8_t *, uint8_t *, int32_t,
-                                         int32_t *, uint32_t *, uint32_t *, uint32_t *, uint32_t *, ZsAdlerAcc *, uint32_t, int, void *);
-extern "C" size_t zs_inflate_aux_bytes(void);
+                                         int32_t *, uint32_t *, uint32_t *, uint32_t *, uint32_t *, ZsAdlerAcc *, uint32_t, int);
 
 #define ZS_NEVENTS 16
 #define ZS_MAX_WAVES 64
@@ -52,7 +51,6 @@ struct zscgpu_engine {
     uint32_t *d_crc;                  /* [2] */
     uint32_t *d_aux;                  /* inflate: [2 * max_streams] trailer check + flags */
     uint32_t *h_aux;                  /* the same on the host (section passes read the flags) */
-    uint8_t *d_inf_aux;               /* inflate: per stream, the sorted symbols of its current block (codes longer than the direct tables) */
     uint32_t *d_cand, *h_cand;        /* sectioned inflate: [max_streams + 1] positions behind 00 00 FF FF, slot 0 = count */
     uint32_t *sec_start, *sec_opts, *sec_flags, *sec_trailer, *sec_real, *sec_off;   /* its host scratch, [max_streams + 1] each */
     zscgpu_stream *sec_st;            /* [max_streams] */
@@ -62,6 +60,8 @@ struct zscgpu_engine {
     uint32_t *d_produced, *h_produced, *d_consumed, *h_consumed, *d_check, *h_check;
     cudaEvent_t ev[ZS_NEVENTS];
     cudaStream_t copy_stream, d2h_stream;   /* host-buffer calls: uploads / downloads overlap the kernels */
+    cudaStream_t stream2;                   /* odd waves of a host-buffer call run here, so that they overlap the even ones */
+    cudaEvent_t ev_slice[2];                /* kernels + result copies of the wave in slice 0 / 1 are done */
     cudaEvent_t ev_wave[ZS_MAX_WAVES];
     /* last enqueue, for zscgpu_relaunch */
     int last_kind;                    /* 0 none, 1 deflate, 2 inflate */
@@ -83,7 +83,7 @@ static std::mutex g_mu;
 static int zs_fail(zscgpu_engine *e, cudaError_t ce, const char *what, int line)
 {
     char *dst = e ? e->err : g_init_err;
-    snprintf(dst, 512, "CUDA error %d (%s) at engine.cu:%d: %s", (int)ce, cudaGetErrorString(ce), line, what);
+    snprintf(dst, 512, "CUDA error %d (%s) at engine.cu:%d: %.300s", (int)ce, cudaGetErrorString(ce), line, what);
     return ZSCGPU_ERR_CUDA;
 }
 
@@ -151,12 +151,11 @@ extern "C" int zscgpu_init(const zscgpu_config *cfg_in, zscgpu_engine **out)
     ZS_CUDA_CHECK(zs_dev(&e->d_blk_meta, e->blk_cap));
     ZS_CUDA_CHECK(zs_dev(&e->d_blk_bitoff, e->blk_cap));
     ZS_CUDA_CHECK(zs_dev(&e->d_blk_scratch, (size_t)e->blk_cap * zs_block_scratch_bytes()));
-    ZS_CUDA_CHECK(zs_dev(&e->d_blk_used, (size_t)e->blk_cap + 1));
+    ZS_CUDA_CHECK(zs_dev(&e->d_blk_used, (size_t)e->blk_cap + 2));
     ZS_CUDA_CHECK(zs_dev(&e->d_adler, cfg.max_streams + 1));
     ZS_CUDA_CHECK(zs_dev(&e->d_crc, 4));
     ZS_CUDA_CHECK(zs_dev(&e->d_aux, 2ull * cfg.max_streams));
     ZS_CUDA_CHECK(zs_pinned(&e->h_aux, 2ull * cfg.max_streams));
-    ZS_CUDA_CHECK(zs_dev(&e->d_inf_aux, (size_t)cfg.max_streams * zs_inflate_aux_bytes()));
     ZS_CUDA_CHECK(zs_dev(&e->d_cand, (size_t)cfg.max_streams + 1));
     ZS_CUDA_CHECK(zs_pinned(&e->h_cand, (size_t)cfg.max_streams + 1));
     {
@@ -181,6 +180,8 @@ extern "C" int zscgpu_init(const zscgpu_config *cfg_in, zscgpu_engine **out)
     for (int i = 0; i < ZS_NEVENTS; i++) ZS_CUDA_CHECK(cudaEventCreate(&e->ev[i]));
     ZS_CUDA_CHECK(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
     ZS_CUDA_CHECK(cudaStreamCreateWithFlags(&e->d2h_stream, cudaStreamNonBlocking));
+    ZS_CUDA_CHECK(cudaStreamCreateWithFlags(&e->stream2, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) ZS_CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_slice[i], cudaEventDisableTiming));
     for (int i = 0; i < ZS_MAX_WAVES; i++) ZS_CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_wave[i], cudaEventDisableTiming));
     ZS_CUDA_CHECK(zs_crc_init_launch(e->stream));
     ZS_CUDA_CHECK(cudaStreamSynchronize(e->stream));
@@ -197,13 +198,14 @@ extern "C" void zscgpu_destroy(zscgpu_engine *e)
     cudaFreeHost(e->h_streams); cudaFree(e->d_streams);
     cudaFreeHost(e->h_blk_chunk); cudaFree(e->d_blk_chunk);
     cudaFree(e->d_chunk_nsym); cudaFree(e->d_blk_in_start); cudaFree(e->d_blocks); cudaFree(e->d_blk_meta); cudaFree(e->d_blk_bitoff); cudaFree(e->d_blk_scratch); cudaFree(e->d_blk_used);
-    cudaFree(e->d_adler); cudaFree(e->d_crc); cudaFree(e->d_aux); cudaFreeHost(e->h_aux); cudaFree(e->d_inf_aux); cudaFree(e->d_cand); cudaFreeHost(e->h_cand);
+    cudaFree(e->d_adler); cudaFree(e->d_crc); cudaFree(e->d_aux); cudaFreeHost(e->h_aux); cudaFree(e->d_cand); cudaFreeHost(e->h_cand);
     free(e->sec_start); free(e->sec_st); free(e->sec_r1);
     cudaFree(e->d_ret); cudaFree(e->d_produced); cudaFree(e->d_consumed); cudaFree(e->d_check);
     cudaFreeHost(e->h_ret); cudaFreeHost(e->h_produced); cudaFreeHost(e->h_consumed); cudaFreeHost(e->h_check);
     for (int i = 0; i < ZS_NEVENTS; i++) cudaEventDestroy(e->ev[i]);
     for (int i = 0; i < ZS_MAX_WAVES; i++) cudaEventDestroy(e->ev_wave[i]);
-    cudaStreamDestroy(e->copy_stream); cudaStreamDestroy(e->d2h_stream);
+    cudaStreamDestroy(e->copy_stream); cudaStreamDestroy(e->d2h_stream); cudaStreamDestroy(e->stream2);
+    for (int i = 0; i < 2; i++) cudaEventDestroy(e->ev_slice[i]);
     cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -326,11 +328,40 @@ static int zs_lz_params(const zscgpu_deflate_params *p, ZsLzParams *L, int *chai
     return 0;
 }
 
-static int zs_build_deflate_desc(zscgpu_engine *e, const zscgpu_stream *streams, uint32_t n, uint32_t mbl, int part,
+/* A slice of the descriptor, block and symbol arrays: a deflate batch uses all of them (zs_slice_whole); the
+ * waves of a host-buffer call alternate between two halves and two streams so that consecutive waves overlap
+ * on the GPU.  Indices inside descriptors are relative to the slice; kernels get offset pointers. */
+struct ZsSlice {
+    uint32_t chunk0, chunk_cap, blk0, blk_cap, stream0, stream_cap, used0;
+    uint64_t sym0, sym_cap;
+    cudaStream_t st;
+    bool timed;                       /* record the stage events (slots 8..13) */
+};
+static ZsSlice zs_slice_whole(zscgpu_engine *e)
+{
+    ZsSlice sl;
+    sl.chunk0 = 0; sl.chunk_cap = e->cfg.max_chunks; sl.blk0 = 0; sl.blk_cap = e->blk_cap; sl.stream0 = 0; sl.stream_cap = e->cfg.max_streams;
+    sl.used0 = 0; sl.sym0 = 0; sl.sym_cap = e->sym_cap; sl.st = e->stream; sl.timed = true;
+    return sl;
+}
+static ZsSlice zs_slice_half(zscgpu_engine *e, int h)
+{
+    ZsSlice sl;
+    sl.chunk_cap = e->cfg.max_chunks / 2; sl.chunk0 = h ? sl.chunk_cap : 0;
+    sl.blk_cap = e->blk_cap / 2; sl.blk0 = h ? sl.blk_cap : 0;
+    sl.stream_cap = e->cfg.max_streams / 2; sl.stream0 = h ? sl.stream_cap : 0;
+    sl.used0 = h ? sl.blk_cap + 1 : 0;
+    sl.sym_cap = (e->sym_cap / 2) & ~3ull; sl.sym0 = h ? sl.sym_cap : 0;
+    sl.st = h ? e->stream2 : e->stream; sl.timed = false;
+    return sl;
+}
+
+static int zs_build_deflate_desc(zscgpu_engine *e, const ZsSlice &sl, const zscgpu_stream *streams, uint32_t n, uint32_t mbl, int part,
                                  uint32_t *nchunks_out, uint32_t *nblk_out)
 {
     uint64_t sym = 0, total = 0;
     uint32_t nc = 0, nb = 0;
+    if (n > sl.stream_cap) { snprintf(e->err, sizeof(e->err), "batch has more streams than the slice holds"); return ZSCGPU_ERR_CAPACITY; }
     for (uint32_t s = 0; s < n; s++) {
         const zscgpu_stream *z = &streams[s];
         if (z->raw_off > e->cfg.raw_bytes || z->raw_len > e->cfg.raw_bytes - z->raw_off ||
@@ -338,7 +369,7 @@ static int zs_build_deflate_desc(zscgpu_engine *e, const zscgpu_stream *streams,
             snprintf(e->err, sizeof(e->err), "stream %u lies outside the arenas", s);
             return ZSCGPU_ERR_CAPACITY;
         }
-        ZsStream *S = &e->h_streams[s];
+        ZsStream *S = &e->h_streams[sl.stream0 + s];
         S->raw_off = z->raw_off; S->comp_off = z->comp_off; S->raw_len = z->raw_len; S->comp_cap = z->comp_len;
         S->blk_first = nb; S->chunk_first = nc;
         total += z->raw_len;
@@ -347,10 +378,10 @@ static int zs_build_deflate_desc(zscgpu_engine *e, const zscgpu_stream *streams,
             uint32_t sec = z->raw_len - pos < mbl ? z->raw_len - pos : mbl;
             uint32_t nsub = sec ? (sec + ZS_CHUNK_MAX - 1) / ZS_CHUNK_MAX : 1;
             for (uint32_t j = 0; j < nsub; j++) {
-                if (nc >= e->cfg.max_chunks) { snprintf(e->err, sizeof(e->err), "batch needs more than max_chunks=%u chunks", e->cfg.max_chunks); return ZSCGPU_ERR_CAPACITY; }
+                if (nc >= sl.chunk_cap) { snprintf(e->err, sizeof(e->err), "batch needs more than %u chunks (max_chunks=%u)", sl.chunk_cap, e->cfg.max_chunks); return ZSCGPU_ERR_CAPACITY; }
                 uint32_t coff = j * ZS_CHUNK_MAX;
                 uint32_t clen = sec - coff < ZS_CHUNK_MAX ? sec - coff : ZS_CHUNK_MAX;
-                ZsChunk *C = &e->h_chunks[nc];
+                ZsChunk *C = &e->h_chunks[sl.chunk0 + nc];
                 C->raw_off = z->raw_off + pos + coff;
                 C->sym_off = sym;
                 C->len = clen;
@@ -364,8 +395,8 @@ static int zs_build_deflate_desc(zscgpu_engine *e, const zscgpu_stream *streams,
                     C->flags |= ZC_LAST_OF_SECTION;
                     if (pos + sec >= z->raw_len && !(part & 2)) C->flags |= ZC_LAST_OF_STREAM;
                 }
-                if ((uint64_t)nb + C->blk_cap > e->blk_cap) { snprintf(e->err, sizeof(e->err), "batch needs too many block slots"); return ZSCGPU_ERR_CAPACITY; }
-                for (uint32_t k = 0; k < C->blk_cap; k++) e->h_blk_chunk[nb + k] = nc;
+                if ((uint64_t)nb + C->blk_cap > sl.blk_cap) { snprintf(e->err, sizeof(e->err), "batch needs too many block slots"); return ZSCGPU_ERR_CAPACITY; }
+                for (uint32_t k = 0; k < C->blk_cap; k++) e->h_blk_chunk[sl.blk0 + nb + k] = nc;
                 nb += C->blk_cap;
                 sym += ((uint64_t)clen + 3) & ~3ull;
                 if (clen == 0) sym += 4;
@@ -375,7 +406,7 @@ static int zs_build_deflate_desc(zscgpu_engine *e, const zscgpu_stream *streams,
         } while (pos < z->raw_len);
         S->blk_count = nb - S->blk_first; S->chunk_count = nc - S->chunk_first;
     }
-    if (total > e->cfg.deflate_batch_max || sym > e->sym_cap) {
+    if (total > e->cfg.deflate_batch_max || sym > sl.sym_cap) {
         snprintf(e->err, sizeof(e->err), "deflate batch of %llu bytes exceeds deflate_batch_max=%llu",
                  (unsigned long long)total, (unsigned long long)e->cfg.deflate_batch_max);
         return ZSCGPU_ERR_CAPACITY;
@@ -394,45 +425,57 @@ __global__ void __launch_bounds__(256) zs_desc_fetch_kernel(ZsDescFetch d)
         for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < d.words[k]; i += gridDim.x * blockDim.x)
             d.dst[k][i] = d.src[k][i];
 }
-static cudaError_t zs_desc_fetch(zscgpu_engine *e, uint32_t n, uint32_t nc, uint32_t nb)
+static cudaError_t zs_desc_fetch(zscgpu_engine *e, const ZsSlice &sl, uint32_t n, uint32_t nc, uint32_t nb)
 {
     ZsDescFetch d;
-    d.src[0] = (const uint32_t *)e->h_chunks;    d.dst[0] = (uint32_t *)e->d_chunks;    d.words[0] = (uint32_t)(sizeof(ZsChunk) / 4 * nc);
-    d.src[1] = (const uint32_t *)e->h_streams;   d.dst[1] = (uint32_t *)e->d_streams;   d.words[1] = (uint32_t)(sizeof(ZsStream) / 4 * n);
-    d.src[2] = (const uint32_t *)e->h_blk_chunk; d.dst[2] = (uint32_t *)e->d_blk_chunk; d.words[2] = nb;
+    const void *hbase[3] = {e->h_chunks, e->h_streams, e->h_blk_chunk};
+    const size_t hoff[3] = {sizeof(ZsChunk) * (size_t)sl.chunk0, sizeof(ZsStream) * (size_t)sl.stream0, sizeof(uint32_t) * (size_t)sl.blk0};
+    d.dst[0] = (uint32_t *)(e->d_chunks + sl.chunk0);     d.words[0] = (uint32_t)(sizeof(ZsChunk) / 4 * nc);
+    d.dst[1] = (uint32_t *)(e->d_streams + sl.stream0);   d.words[1] = (uint32_t)(sizeof(ZsStream) / 4 * n);
+    d.dst[2] = e->d_blk_chunk + sl.blk0;                  d.words[2] = nb;
     for (int k = 0; k < 3; k++) {
         void *dp = nullptr;
-        cudaError_t ce = cudaHostGetDevicePointer(&dp, (void *)d.src[k], 0);
+        cudaError_t ce = cudaHostGetDevicePointer(&dp, (void *)hbase[k], 0);
         if (ce != cudaSuccess) return ce;
-        d.src[k] = (const uint32_t *)dp;
+        d.src[k] = (const uint32_t *)((const uint8_t *)dp + hoff[k]);
     }
     uint32_t total = d.words[0] + d.words[1] + d.words[2];
     uint32_t grid = (total + 255) / 256; if (grid > 148) grid = 148; if (grid == 0) grid = 1;
-    zs_desc_fetch_kernel<<<grid, 256, 0, e->stream>>>(d);
+    zs_desc_fetch_kernel<<<grid, 256, 0, sl.st>>>(d);
     e->launches_total += 1;
     return cudaGetLastError();
 }
 
-static int zs_deflate_launch_all(zscgpu_engine *e)
+static int zs_deflate_launch_slice(zscgpu_engine *e, const ZsSlice &sl, uint32_t n, uint32_t nc, uint32_t nb, int chain, const ZsLzParams &L)
 {
-    const uint32_t n = e->last_nstreams, nc = e->last_nchunks, nb = e->last_nblk;
+    cudaStream_t st = sl.st;
+    ZsChunk *chunks = e->d_chunks + sl.chunk0;
+    ZsStream *streams = e->d_streams + sl.stream0;
+    uint32_t *sym = e->d_sym + sl.sym0;
+    ZsAdlerAcc *adler = e->d_adler + sl.stream0;
     /* event slots 8..13 bracket the kernels of the last deflate launch (see zscgpu.h) */
-    ZS_CUDA_CHECK(cudaMemsetAsync(e->d_adler, 0, sizeof(ZsAdlerAcc) * n, e->stream));
-    ZS_CUDA_CHECK(cudaEventRecord(e->ev[8], e->stream));
-    ZS_CUDA_CHECK(zs_adler_chunks_launch(e->stream, nc, e->d_raw, e->d_chunks, e->d_streams, e->d_adler));
-    ZS_CUDA_CHECK(cudaEventRecord(e->ev[9], e->stream));
-    ZS_CUDA_CHECK(zs_lz_launch(e->stream, e->last_chain, nc, e->d_raw, e->d_chunks, e->d_sym, e->d_chunk_nsym, e->d_blk_in_start, e->last_lz));
-    ZS_CUDA_CHECK(cudaEventRecord(e->ev[10], e->stream));
-    ZS_CUDA_CHECK(zs_huff_launch(e->stream, nb, n, e->d_chunks, e->d_blk_chunk, e->d_streams, e->d_sym, e->d_chunk_nsym,
-                                 e->d_blk_in_start, e->d_blocks, e->d_adler, e->d_raw, e->d_comp, e->d_ret, e->d_produced, e->d_check, e->last_lz,
-                                 e->ev[11], e->ev[12], nc, e->d_blk_meta, e->d_blk_bitoff, e->d_blk_scratch, e->d_blk_used));
-    ZS_CUDA_CHECK(cudaEventRecord(e->ev[13], e->stream));
-    ZS_CUDA_CHECK(cudaMemcpyAsync(e->h_ret, e->d_ret, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, e->stream));
-    ZS_CUDA_CHECK(cudaMemcpyAsync(e->h_produced, e->d_produced, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, e->stream));
-    ZS_CUDA_CHECK(cudaMemcpyAsync(e->h_check, e->d_check, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, e->stream));
+    ZS_CUDA_CHECK(cudaMemsetAsync(adler, 0, sizeof(ZsAdlerAcc) * n, st));
+    if (sl.timed) ZS_CUDA_CHECK(cudaEventRecord(e->ev[8], st));
+    ZS_CUDA_CHECK(zs_adler_chunks_launch(st, nc, e->d_raw, chunks, streams, adler));
+    if (sl.timed) ZS_CUDA_CHECK(cudaEventRecord(e->ev[9], st));
+    ZS_CUDA_CHECK(zs_lz_launch(st, chain, nc, e->d_raw, chunks, sym, e->d_chunk_nsym + sl.chunk0, e->d_blk_in_start + sl.blk0 + (sl.blk0 ? 1 : 0), L));
+    if (sl.timed) ZS_CUDA_CHECK(cudaEventRecord(e->ev[10], st));
+    ZS_CUDA_CHECK(zs_huff_launch(st, nb, n, chunks, e->d_blk_chunk + sl.blk0, streams, sym, e->d_chunk_nsym + sl.chunk0,
+                                 e->d_blk_in_start + sl.blk0 + (sl.blk0 ? 1 : 0), e->d_blocks + sl.blk0, adler, e->d_raw, e->d_comp,
+                                 e->d_ret + sl.stream0, e->d_produced + sl.stream0, e->d_check + sl.stream0, L,
+                                 sl.timed ? e->ev[11] : nullptr, sl.timed ? e->ev[12] : nullptr, nc, e->d_blk_meta + sl.blk0, e->d_blk_bitoff + sl.blk0,
+                                 e->d_blk_scratch + (size_t)sl.blk0 * zs_block_scratch_bytes(), e->d_blk_used + sl.used0));
+    if (sl.timed) ZS_CUDA_CHECK(cudaEventRecord(e->ev[13], st));
+    ZS_CUDA_CHECK(cudaMemcpyAsync(e->h_ret + sl.stream0, e->d_ret + sl.stream0, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
+    ZS_CUDA_CHECK(cudaMemcpyAsync(e->h_produced + sl.stream0, e->d_produced + sl.stream0, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, st));
+    ZS_CUDA_CHECK(cudaMemcpyAsync(e->h_check + sl.stream0, e->d_check + sl.stream0, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, st));
     e->launches = 8;   /* adler, lz, block (histogram / tree merge / codes), stored-run merge, offset, encode */
     e->launches_total += 8;
     return ZSCGPU_OK;
+}
+static int zs_deflate_launch_all(zscgpu_engine *e)
+{
+    return zs_deflate_launch_slice(e, zs_slice_whole(e), e->last_nstreams, e->last_nchunks, e->last_nblk, e->last_chain, e->last_lz);
 }
 
 extern "C" int zscgpu_deflate_enqueue(zscgpu_engine *e, const zscgpu_stream *streams, uint32_t n, const zscgpu_deflate_params *p)
@@ -442,10 +485,11 @@ extern "C" int zscgpu_deflate_enqueue(zscgpu_engine *e, const zscgpu_stream *str
     ZsLzParams L; int chain;
     if (zs_lz_params(p, &L, &chain)) { snprintf(e->err, sizeof(e->err), "bad level/strategy/wrap"); return ZSCGPU_ERR_ARG; }
     uint32_t nc = 0, nb = 0;
-    int r = zs_build_deflate_desc(e, streams, n, p->max_block_len, p->part, &nc, &nb);
+    const ZsSlice whole = zs_slice_whole(e);
+    int r = zs_build_deflate_desc(e, whole, streams, n, p->max_block_len, p->part, &nc, &nb);
     if (r) return r;
     static_assert(sizeof(ZsChunk) % 4 == 0 && sizeof(ZsStream) % 4 == 0, "descriptor structs are copied as words");
-    ZS_CUDA_CHECK(zs_desc_fetch(e, n, nc, nb));
+    ZS_CUDA_CHECK(zs_desc_fetch(e, whole, n, nc, nb));
     e->last_kind = 1; e->last_nstreams = n; e->last_nchunks = nc; e->last_nblk = nb; e->last_chain = chain; e->last_lz = L;
     return zs_deflate_launch_all(e);
 }
@@ -454,7 +498,7 @@ static int zs_inflate_launch_all(zscgpu_engine *e)
 {
     const uint32_t n = e->last_nstreams;
     ZS_CUDA_CHECK(zs_inflate_launch(e->stream, n, e->d_streams, e->d_comp, e->d_raw, e->last_wrap, e->d_ret, e->d_produced, e->d_consumed, e->d_check,
-                                    e->d_aux, e->d_adler, e->last_max_raw, e->last_with_check, e->d_inf_aux));
+                                    e->d_aux, e->d_adler, e->last_max_raw, e->last_with_check));
     ZS_CUDA_CHECK(cudaMemcpyAsync(e->h_ret, e->d_ret, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, e->stream));
     ZS_CUDA_CHECK(cudaMemcpyAsync(e->h_produced, e->d_produced, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, e->stream));
     ZS_CUDA_CHECK(cudaMemcpyAsync(e->h_consumed, e->d_consumed, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, e->stream));
@@ -484,7 +528,7 @@ static int zs_inflate_enqueue_opts(zscgpu_engine *e, const zscgpu_stream *stream
         if (opts) S->chunk_first = opts[s];
         if (z->raw_len > max_raw) max_raw = z->raw_len;
     }
-    ZS_CUDA_CHECK(zs_desc_fetch(e, n, 0, 0));
+    ZS_CUDA_CHECK(zs_desc_fetch(e, zs_slice_whole(e), n, 0, 0));
     e->last_max_raw = max_raw;
     e->last_kind = 2; e->last_nstreams = n; e->last_wrap = wrap; e->last_with_check = opts ? 0 : 1;
     return zs_inflate_launch_all(e);
@@ -663,47 +707,74 @@ static int zs_compress_host_waves(zscgpu_engine *e, uint8_t *dest, uint32_t dest
     ZsLzParams L; int chain;
     if (zs_lz_params(p, &L, &chain)) { snprintf(e->err, sizeof(e->err), "bad level/strategy/wrap"); return ZSCGPU_ERR_ARG; }
     auto room = [](uint64_t len) -> uint64_t { return (len + (len >> 3) + 4096 + 63) & ~63ull; };   /* comp arena room of a wave */
-    uint64_t comp_off = 0;
-    /* uploads run one wave ahead of the kernels on their own stream */
-    auto upload = [&](uint32_t w) -> cudaError_t {
-        const uint64_t off = (uint64_t)w * W, len = (src_len - off < W) ? src_len - off : W;
-        cudaError_t ce = cudaMemcpyAsync(e->d_raw + off, src + off, len, cudaMemcpyHostToDevice, e->copy_stream);
-        if (ce != cudaSuccess) return ce;
-        return cudaEventRecord(e->ev_wave[w], e->copy_stream);
-    };
-    ZS_CUDA_CHECK(upload(0));
+    auto wave_len = [&](uint32_t w) -> uint64_t { const uint64_t off = (uint64_t)w * W; return (src_len - off < W) ? src_len - off : W; };
+    /* every upload is queued at once on its own stream (one event per wave): the copy engine never waits for
+       the host, and the kernels of a wave start the moment its bytes have landed */
+    for (uint32_t w = 0; w < nw; w++) {
+        const uint64_t off = (uint64_t)w * W;
+        ZS_CUDA_CHECK(cudaMemcpyAsync(e->d_raw + off, src + off, wave_len(w), cudaMemcpyHostToDevice, e->copy_stream));
+        ZS_CUDA_CHECK(cudaEventRecord(e->ev_wave[w], e->copy_stream));
+    }
+    /* the gzip wrapper needs a CRC-32 per wave from the engine's one CRC slot: those calls keep one wave in
+       flight; everything else alternates between two slices of the descriptor arrays on two streams, so the
+       kernels of wave w + 1 fill the machine while wave w drains (its block / offset / bit-packing kernels and
+       the tail of its LZ kernel), and the host collects wave w - 1 while wave w runs */
+    const bool two = (p->wrap != 2);
+    const ZsSlice sl2[2] = {two ? zs_slice_half(e, 0) : zs_slice_whole(e), two ? zs_slice_half(e, 1) : zs_slice_whole(e)};
     zscgpu_deflate_params pp = *p;
-    pp.wrap = 0;
+    pp.wrap = 0;                                            /* every wave is a raw part; the wrapper is the host's */
+    ZsLzParams Lw; int chain_w;
+    if (zs_lz_params(&pp, &Lw, &chain_w)) { snprintf(e->err, sizeof(e->err), "bad level/strategy/wrap"); return ZSCGPU_ERR_ARG; }
     uint64_t out_pos = comp_skip + (p->wrap == 1 ? 2u : 0u);
+    uint64_t comp_off = 0;
+    uint64_t coff[ZS_MAX_WAVES];
     uint32_t check = (p->wrap == 2) ? 0u : 1u;
+    uint32_t crc_h[2] = {0, 0};
     res->ret = 0; res->produced = 0; res->consumed = src_len; res->check = 0;
     int rc = ZSCGPU_OK;
-    for (uint32_t w = 0; w < nw && rc == ZSCGPU_OK; w++) {
-        const uint64_t off = (uint64_t)w * W, len = (src_len - off < W) ? src_len - off : W;
-        ZS_CUDA_CHECK(cudaStreamWaitEvent(e->stream, e->ev_wave[w], 0));
+    bool stop = false;
+    /* collect wave v: wait for its kernels, queue the download of its bytes, fold its checksum */
+    auto finish = [&](uint32_t v) -> int {
+        const ZsSlice &sl = sl2[v & 1];
+        ZS_CUDA_CHECK(cudaEventSynchronize(e->ev_slice[v & 1]));
+        const int32_t ret = e->h_ret[sl.stream0];
+        const uint32_t produced = e->h_produced[sl.stream0], adler = e->h_check[sl.stream0];
+        if (ret != 0) { res->ret = ret; stop = true; return ZSCGPU_OK; }
+        if (out_pos + produced + (p->wrap == 1 ? 4u : 0u) > dest_cap) { res->ret = -5; stop = true; return ZSCGPU_OK; }
+        ZS_CUDA_CHECK(cudaMemcpyAsync(dest + out_pos, e->d_comp + coff[v], produced, cudaMemcpyDeviceToHost, e->d2h_stream));
+        out_pos += produced;
+        check = (p->wrap == 2) ? zscgpu_crc32_combine(check, crc_h[1], wave_len(v)) : zscgpu_adler32_combine(check, adler, wave_len(v));
+        return ZSCGPU_OK;
+    };
+    uint32_t enq = 0, fin = 0;
+    for (uint32_t w = 0; w < nw && rc == ZSCGPU_OK && !stop; w++) {
+        const ZsSlice &sl = sl2[w & 1];
+        const uint64_t off = (uint64_t)w * W, len = wave_len(w);
+        ZS_CUDA_CHECK(cudaStreamWaitEvent(sl.st, e->ev_wave[w], 0));
         zscgpu_stream st;
         st.raw_off = off; st.raw_len = (uint32_t)len; st.comp_off = comp_off; st.comp_len = (uint32_t)room(len);
+        coff[w] = comp_off;
         comp_off += room(len);
-        pp.part = (w > 0 ? 1 : 0) | (w + 1 < nw ? 2 : 0);
-        zscgpu_result r1;
-        rc = zscgpu_deflate_enqueue(e, &st, 1, &pp); if (rc) break;
-        if (w + 1 < nw) ZS_CUDA_CHECK(upload(w + 1));
-        uint32_t crc_part = 0;
+        const int part = (w > 0 ? 1 : 0) | (w + 1 < nw ? 2 : 0);
+        uint32_t nc = 0, nb = 0;
+        {
+            std::lock_guard<std::mutex> lk(e->mu);
+            rc = zs_build_deflate_desc(e, sl, &st, 1, pp.max_block_len, part, &nc, &nb); if (rc) break;
+            ZS_CUDA_CHECK(zs_desc_fetch(e, sl, 1, nc, nb));
+            rc = zs_deflate_launch_slice(e, sl, 1, nc, nb, chain_w, Lw); if (rc) break;
+            e->last_kind = 0;                                   /* nothing a relaunch could repeat */
+        }
         if (p->wrap == 2) {
             rc = zscgpu_crc32_enqueue(e, off, len); if (rc) break;
-            uint32_t h[2];
-            ZS_CUDA_CHECK(cudaMemcpyAsync(h, e->d_crc, 8, cudaMemcpyDeviceToHost, e->stream));
-            rc = zscgpu_fetch_results(e, 1, &r1); if (rc) break;
-            crc_part = h[1];
-        } else {
-            rc = zscgpu_fetch_results(e, 1, &r1); if (rc) break;
+            ZS_CUDA_CHECK(cudaMemcpyAsync(crc_h, e->d_crc, 8, cudaMemcpyDeviceToHost, e->stream));
         }
-        if (r1.ret != 0) { res->ret = r1.ret; break; }
-        if (out_pos + r1.produced + (p->wrap == 1 ? 4u : 0u) > dest_cap) { res->ret = -5; break; }
-        ZS_CUDA_CHECK(cudaMemcpyAsync(dest + out_pos, e->d_comp + st.comp_off, r1.produced, cudaMemcpyDeviceToHost, e->d2h_stream));
-        out_pos += r1.produced;
-        check = (p->wrap == 2) ? zscgpu_crc32_combine(check, crc_part, len) : zscgpu_adler32_combine(check, r1.check, len);
+        ZS_CUDA_CHECK(cudaEventRecord(e->ev_slice[w & 1], sl.st));
+        enq = w + 1;
+        if (!two) { rc = finish(w); fin = w + 1; }
+        else if (w >= 1) { rc = finish(w - 1); fin = w; }
     }
+    while (rc == ZSCGPU_OK && !stop && fin < enq) { rc = finish(fin); fin++; }
+    cudaStreamSynchronize(e->stream); cudaStreamSynchronize(e->stream2);
     ZS_CUDA_CHECK(cudaStreamSynchronize(e->d2h_stream));
     ZS_CUDA_CHECK(cudaStreamSynchronize(e->copy_stream));
     if (rc) return rc;
@@ -732,13 +803,18 @@ extern "C" int zscgpu_compress_host(zscgpu_engine *e, uint8_t *dest, uint32_t de
     if (p->max_block_len != 0 && src_len >= (128u << 20)) {
         const uint64_t mbl = p->max_block_len;
         const uint64_t cps = (mbl + ZS_CHUNK_MAX - 1) / ZS_CHUNK_MAX;                 /* chunks per section */
-        const uint64_t round_secs = (2ull * (uint64_t)e->sms + cps - 1) / cps;          /* sections in two rounds of chunks */
+        const char *rv = getenv("ZSC_B200_WAVE_ROUNDS");                                /* tuning aid */
+        const uint64_t rounds = rv && atoi(rv) > 0 ? (uint64_t)atoi(rv) : 1ull;
+        const uint64_t round_secs = (rounds * 2ull * (uint64_t)e->sms + cps - 1) / cps;   /* sections in `rounds` rounds of chunks (two CTAs per SM) */
         const uint64_t k = ((64ull << 20) + round_secs * mbl - 1) / (round_secs * mbl);
         uint64_t W = k * round_secs * mbl;
         uint64_t nw = ((uint64_t)src_len + W - 1) / W;
         if (nw > ZS_MAX_WAVES) { W = (((uint64_t)src_len + ZS_MAX_WAVES - 1) / ZS_MAX_WAVES + p->max_block_len - 1) / p->max_block_len * p->max_block_len; nw = ((uint64_t)src_len + W - 1) / W; }
         const uint64_t need = (uint64_t)src_len + ((uint64_t)src_len >> 3) + nw * (4096 + 64 + 8);
-        if (nw >= 2 && need <= e->cfg.comp_bytes && dest_cap > comp_skip)
+        /* two waves are in flight at a time, each in one half of the descriptor, block and symbol arrays */
+        const uint64_t wchunks = (W / mbl) * cps, wblks = W / ZS_BLOCK_SYMS + 2 * wchunks;
+        const bool fits = wchunks <= e->cfg.max_chunks / 2 && wblks <= e->blk_cap / 2 && W + 8 * wchunks + 64 <= e->sym_cap / 2;
+        if (nw >= 2 && fits && need <= e->cfg.comp_bytes && dest_cap > comp_skip)
             return zs_compress_host_waves(e, dest, dest_cap, src, src_len, p, comp_skip, res, W, (uint32_t)nw);
     }
     int r = zscgpu_upload_async(e, 0, 0, src, src_len); if (r) return r;
