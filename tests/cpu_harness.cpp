@@ -37,7 +37,11 @@ struct LzP { int mode, chain, nice, lazy, min_len, max_dist; };
 static const uint32_t TILE = 2048, WINDOW = 32768, NOHASH = 0xFFFF;
 static int g_near = 1;   /* lanes looked at below the current one (deflate_lz.cu looks at the previous lane only) */
 extern "C" void h_set_near(int n) { g_near = n; }
-static int g_hash_bits = 15;   /* 14 for the single-candidate kernel, 15 for the chain kernel (deflate_lz.cu ZlK) */
+static int g_hash_bits = 15;
+static uint64_t g_chain_steps = 0;   /* candidates visited beyond the first (a proxy for the chain kernel's work) */
+extern "C" uint64_t h_chain_steps(void) { uint64_t v = g_chain_steps; g_chain_steps = 0; return v; }
+static int g_skip_override = -1;     /* experiments: force the covering threshold */
+extern "C" void h_set_skip(int v) { g_skip_override = v; }   /* 14 for the single-candidate kernel, 15 for the chain kernel (deflate_lz.cu ZlK) */
 
 static inline uint32_t ld32(const uint8_t *p, uint32_t q, uint32_t q_end)
 {
@@ -92,32 +96,63 @@ static void lz_chunk(const uint8_t *data, uint32_t a, uint32_t dict_len, uint32_
             }
         }
         if (t0 + TILE <= q_start) continue;
-        for (uint32_t i = 0; i < TILE; i++) {
-            uint32_t q = t0 + i, best = 0, bestd = 0;
-            if (P.mode != 2 && q >= q_start && q + 3 <= q_end) {
-                uint32_t maxl = q_end - q < 258 ? q_end - q : 258;
-                uint32_t maxd = q - q_dict < (uint32_t)P.max_dist ? q - q_dict : (uint32_t)P.max_dist;
-                auto mlen = [&](uint32_t dd) { uint32_t l = 0; while (l < maxl && data[q + l] == data[q + l - dd]) l++; return l; };
-                if (P.mode == 1) { if (maxd >= 1) { best = mlen(1); bestd = 1; } }
-                else {
-                    uint32_t d = t_dist[i];
-                    int budget = P.chain;
-                    while (d != 0 && d <= maxd) {
-                        if (best < 3 || data[q + best] == data[q + best - d]) {
-                            uint32_t l = mlen(d);
-                            if (l > best) { best = l; bestd = d; if (l >= (uint32_t)P.nice || l >= maxl) break; }
-                        }
-                        if (P.chain == 0 || budget-- <= 0) break;
-                        uint32_t c = q - d;
-                        if (c + WINDOW < t0 + 2 * TILE) break;     /* the hasher runs one tile ahead */
-                        uint32_t step = prevd[c & (WINDOW - 1)];
-                        if (step == 0) break;
-                        d += step;
+        const uint32_t skip = (P.mode == 0 && P.chain > 0) ? (g_skip_override >= 0 ? (uint32_t)g_skip_override : zs_skip_len(P.chain)) : 0;
+        for (uint32_t g0 = 0; g0 < TILE; g0 += 32) {
+            /* a group of 32 positions, as a warp of the kernel sees it: first candidates, the covering rule, chains */
+            uint32_t best[32], bestd[32], maxl[32], maxd[32], dcur[32];
+            bool go[32];
+            for (uint32_t l = 0; l < 32; l++) {
+                const uint32_t i = g0 + l, q = t0 + i;
+                best[l] = bestd[l] = maxl[l] = maxd[l] = dcur[l] = 0; go[l] = false;
+                if (P.mode == 2 || !(q >= q_start && q + 3 <= q_end)) continue;
+                maxl[l] = q_end - q < 258 ? q_end - q : 258;
+                maxd[l] = q - q_dict < (uint32_t)P.max_dist ? q - q_dict : (uint32_t)P.max_dist;
+                auto mlen = [&](uint32_t dd) { uint32_t n = 0; while (n < maxl[l] && data[q + n] == data[q + n - dd]) n++; return n; };
+                if (P.mode == 1) { if (maxd[l] >= 1) { best[l] = mlen(1); bestd[l] = 1; } continue; }
+                dcur[l] = t_dist[i];
+                if (dcur[l] != 0 && dcur[l] <= maxd[l]) {
+                    const uint32_t n = mlen(dcur[l]);
+                    go[l] = true;
+                    if (n > 0) { best[l] = n; bestd[l] = dcur[l]; if (n >= (uint32_t)P.nice || n >= maxl[l]) go[l] = false; }
+                }
+            }
+            if (skip) {
+                uint32_t first_len[32], first_d[32];
+                for (uint32_t l = 0; l < 32; l++) { first_len[l] = best[l]; first_d[l] = bestd[l]; }
+                for (uint32_t u = 0; u < 32;) {
+                    const uint32_t Lu = first_len[u];
+                    if (Lu < skip) { u++; continue; }
+                    for (uint32_t l = u + 2; l < u + Lu && l < 32; l++) {
+                        if (maxl[l] == 0) continue;
+                        go[l] = false;
+                        const uint32_t pl = Lu - (l - u);
+                        if (pl > best[l]) { best[l] = pl; bestd[l] = first_d[u]; }
+                    }
+                    u += Lu;
+                }
+            }
+            for (uint32_t l = 0; l < 32; l++) {
+                const uint32_t i = g0 + l, q = t0 + i;
+                auto mlen = [&](uint32_t dd) { uint32_t n = 0; while (n < maxl[l] && data[q + n] == data[q + n - dd]) n++; return n; };
+                int budget = P.chain;
+                uint32_t d = dcur[l];
+                while (go[l]) {
+                    if (P.chain == 0 || budget-- <= 0) break;
+                    uint32_t c = q - d;
+                    if (c + WINDOW < t0 + 2 * TILE) break;     /* the hasher runs one tile ahead */
+                    uint32_t step = prevd[c & (WINDOW - 1)];
+                    if (step == 0) break;
+                    d += step;
+                    g_chain_steps++;
+                    if (d > maxd[l]) break;
+                    if (best[l] < 3 || data[q + best[l]] == data[q + best[l] - d]) {
+                        uint32_t n = mlen(d);
+                        if (n > best[l]) { best[l] = n; bestd[l] = d; if (n >= (uint32_t)P.nice || n >= maxl[l]) break; }
                     }
                 }
-                if (best < (uint32_t)P.min_len || (best == 3 && bestd > 4096)) { best = 0; bestd = 0; }
+                if (best[l] < (uint32_t)P.min_len || (best[l] == 3 && bestd[l] > 4096)) { best[l] = 0; bestd[l] = 0; }
+                t_len[i] = (uint16_t)best[l]; t_dist[i] = (uint16_t)bestd[l];
             }
-            t_len[i] = (uint16_t)best; t_dist[i] = (uint16_t)bestd;
         }
         // parse: next(p) walk from carry
         uint32_t s = carry - t0;

@@ -32,7 +32,7 @@ struct ZbSmem {
 /* What the three block kernels hand to each other, per block slot (global memory):
  * zs_block_kernel<0> leaves the sorted keys, the reduced histograms and the distance code lengths;
  * zs_merge_kernel adds the parent links of the literal/length tree; zs_block_kernel<1> reads it all back. */
-struct ZbScratch {
+struct __align__(16) ZbScratch {
     uint32_t key[ZH_LCODES_PAD];
     uint32_t lfreq[ZH_LCODES_PAD];
     uint32_t dfreq[ZH_DCODES_PAD];
@@ -154,13 +154,12 @@ zs_block_kernel(const ZsChunk *__restrict__ chunks, const uint32_t *__restrict__
         for (int i = (int)tid; i < m; i += ZB_THREADS) S.sc.key[i] = sorted[i];
     }
     __syncthreads();
-    /* ---- the whole distance tree on thread 32 while the others write the hand-over ---- */
-    if (tid == 32) { S.max_d = zh_lengths(S.dfreq[0], ZH_DCODES, 15, S.sc.dlen, &S.sc2); X.max_d = S.max_d; X.m = m; X.max_l = S.max_l; }
+    /* ---- the hand-over (the distance tree, a serial job of one thread, is built in zs_merge_kernel where every
+       lane has one to build; in here it kept 127 threads waiting for 37 % of the kernel's time) ---- */
+    if (tid == 32) { X.m = m; X.max_l = S.max_l; }
     for (uint32_t i = tid; i < ZH_LCODES_PAD; i += ZB_THREADS) { X.key[i] = S.sc.key[i]; X.lfreq[i] = S.lfreq[0][i]; }
     if (tid < ZH_DCODES_PAD) X.dfreq[tid] = S.dfreq[0][tid];
     if (tid == 0) used[1 + atomicAdd(&used[0], 1u)] = b;
-    __syncthreads();
-    if (tid < ZH_DCODES_PAD) X.dlen[tid] = S.sc.dlen[tid];
     return;
   } else {
     /* ---- PHASE 1: read the hand-over back ---- */
@@ -432,34 +431,58 @@ zs_block_kernel(const ZsChunk *__restrict__ chunks, const uint32_t *__restrict__
     if (tid == 0) blk_meta[b] = make_uint4(S.blk.type, S.blk.body_bits, S.blk.in_len, S.blk.flags);
 }
 
-/* ======================= K2m: two-queue Huffman merge, one block per lane ======================= */
+/* ======================= K2m: the serial tree work, one block per lane ======================= */
 #define ZMG_THREADS 64
 
-/* Leaves are the sorted keys (weight = key >> 9), read from the hand-over; the weights of the internal nodes,
- * which the merge both appends and consumes in order, live in shared memory, one column per lane (bank =
- * lane: conflict-free whatever row each lane is at).  Same picks as zh_merge (huff_build.h): the smaller
- * head of the two queues, the leaf on ties. */
+/* Two inherently serial jobs of a block, done where every lane has one of each to do:
+ * (1) the two-queue merge of the literal/length tree.  Leaves are the sorted keys (weight = key >> 9 <= 8193,
+ *     16 bits); they are first copied from the hand-over into shared memory — in the loop they would be
+ *     dependent global loads, one L2 round trip per merge step — next to the weights of the internal nodes,
+ *     which the merge both appends and consumes in order; one column per lane.  Same picks as zh_merge
+ *     (huff_build.h): the smaller head of the two queues, the leaf on ties.
+ * (2) the whole distance tree (30 symbols: sort, merge, depths, length limit) with zh_lengths on a
+ *     thread-private scratch. */
 __global__ void __launch_bounds__(ZMG_THREADS)
 zs_merge_kernel(ZbScratch *__restrict__ scratch, const uint32_t *__restrict__ used)
 {
-    extern __shared__ uint32_t zmg_w[];                    /* [ZH_LCODES_PAD][ZMG_THREADS] */
+    extern __shared__ uint16_t zmg_w[];                    /* [2][ZH_LCODES_PAD][ZMG_THREADS]: leaves, internal nodes */
     const uint32_t t = blockIdx.x * ZMG_THREADS + threadIdx.x;
     if (t >= used[0]) return;
     ZbScratch &X = scratch[used[1 + t]];
     const int m = X.m;
-    uint32_t *w = zmg_w + threadIdx.x;
+    uint16_t *wl = zmg_w + threadIdx.x;
+    uint16_t *w = zmg_w + ZH_LCODES_PAD * ZMG_THREADS + threadIdx.x;
+    {
+        const uint4 *k4 = reinterpret_cast<const uint4 *>(X.key);
+#pragma unroll 4
+        for (int j = 0; j < (m + 3) >> 2; j++) {
+            const uint4 q = k4[j];
+            wl[(4 * j + 0) * ZMG_THREADS] = (uint16_t)(q.x >> 9); wl[(4 * j + 1) * ZMG_THREADS] = (uint16_t)(q.y >> 9);
+            wl[(4 * j + 2) * ZMG_THREADS] = (uint16_t)(q.z >> 9); wl[(4 * j + 3) * ZMG_THREADS] = (uint16_t)(q.w >> 9);
+        }
+    }
     int a = 0, b = 0, e = 0;                               /* leaves taken, internal nodes taken, internal nodes made */
-    uint32_t la = X.key[0] >> 9, ib = 0xFFFFFFFFu;         /* heads of the two queues */
+    uint32_t la = wl[0], ib = 0xFFFFFFFFu;                 /* heads of the two queues */
     for (int it = 0; it < m - 1; it++) {
         uint32_t sum; int x0, x1;
-        if (a < m && la <= ib) { x0 = a++; sum = la; la = a < m ? X.key[a] >> 9 : 0xFFFFFFFFu; }
+        if (a < m && la <= ib) { x0 = a++; sum = la; la = a < m ? wl[a * ZMG_THREADS] : 0xFFFFFFFFu; }
         else { x0 = m + b++; sum = ib; ib = b < e ? w[b * ZMG_THREADS] : 0xFFFFFFFFu; }
-        if (a < m && la <= ib) { x1 = a++; sum += la; la = a < m ? X.key[a] >> 9 : 0xFFFFFFFFu; }
+        if (a < m && la <= ib) { x1 = a++; sum += la; la = a < m ? wl[a * ZMG_THREADS] : 0xFFFFFFFFu; }
         else { x1 = m + b++; sum += ib; ib = b < e ? w[b * ZMG_THREADS] : 0xFFFFFFFFu; }
-        w[e * ZMG_THREADS] = sum;
+        w[e * ZMG_THREADS] = (uint16_t)sum;
         X.parent[x0] = (uint16_t)(m + e); X.parent[x1] = (uint16_t)(m + e);
         if (b == e) ib = sum;                              /* the queue was empty: the new node is its head */
         e++;
+    }
+    {
+        zh_small sc;
+        uint32_t df[ZH_DCODES_PAD];
+        uint8_t dl[ZH_DCODES_PAD];
+        const uint4 *f4 = reinterpret_cast<const uint4 *>(X.dfreq);
+#pragma unroll
+        for (int j = 0; j < ZH_DCODES_PAD / 4; j++) { const uint4 q = f4[j]; df[4 * j] = q.x; df[4 * j + 1] = q.y; df[4 * j + 2] = q.z; df[4 * j + 3] = q.w; }
+        X.max_d = zh_lengths(df, ZH_DCODES, 15, dl, &sc);
+        for (int i = 0; i < ZH_DCODES_PAD; i++) X.dlen[i] = i < ZH_DCODES ? dl[i] : 0;
     }
 }
 
@@ -818,7 +841,7 @@ extern "C" cudaError_t zs_huff_launch(cudaStream_t st, uint32_t nblk_slots, uint
     cudaMemsetAsync(blk_used, 0, 4, st);
     zs_block_kernel<0><<<nblk_slots, ZB_THREADS, 0, st>>>(chunks, blk_chunk, sym, chunk_nsym, blk_in_start, blocks, blk_meta, scratch, blk_used, P);
     {
-        const size_t smem = sizeof(uint32_t) * ZH_LCODES_PAD * ZMG_THREADS;
+        const size_t smem = sizeof(uint16_t) * 2 * ZH_LCODES_PAD * ZMG_THREADS;
         cudaFuncSetAttribute(zs_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         zs_merge_kernel<<<(nblk_slots + ZMG_THREADS - 1) / ZMG_THREADS, ZMG_THREADS, smem, st>>>(scratch, blk_used);
     }

@@ -327,34 +327,66 @@ zs_lz_kernel(const uint8_t *__restrict__ raw, const ZsChunk *__restrict__ chunks
                         S.t_dist[i] = (uint16_t)bestd;
                     }
                 } else if (P.mode != 2) {
+                    /* Hash chains (levels 2..9) or distance-1 runs (Z_RLE).  Every lane first tries its first
+                       candidate.  A serial deflate never searches inside a match it has taken; the position-parallel
+                       form of that rule (levels >= 4, zs_skip_len): going through the 32 lanes in order, a lane
+                       whose first candidate is at least skip bytes long covers the lanes behind it, except the
+                       next one (the lazy-evaluation candidate); covered lanes keep the better of their own first
+                       candidate and the covering match shortened by their offset and do not walk their chain.
+                       On telemetry-like data most positions are covered and the chain walks, which dominate
+                       the kernel, shrink accordingly.  tests/cpu_harness.cpp mirrors the rule exactly. */
+                    const uint32_t skip = (CHAIN && P.mode == 0) ? zs_skip_len(P.chain) : 0u;
                     for (uint32_t i = wtid; i < ZL_TILE; i += ZL_WORKERS) {
-                        uint32_t q = t0 + i;
-                        uint32_t best = 0, bestd = 0;
+                        const uint32_t q = t0 + i;
+                        uint32_t best = 0, bestd = 0, maxl = 0, maxd = 0, d = 0;
+                        int budget = P.chain;
+                        bool go = false;
                         if (q >= q_start && q + 3 <= q_end) {
-                            uint32_t maxl = min(ZS_MAX_MATCH, q_end - q);
-                            uint32_t maxd = min((uint32_t)P.max_dist, q - q_dict);
+                            maxl = min(ZS_MAX_MATCH, q_end - q);
+                            maxd = min((uint32_t)P.max_dist, q - q_dict);
                             if (P.mode == 1) {
                                 if (maxd >= 1) { best = zl_match_len<RING>(S.ring32, q, 1, maxl); bestd = 1; }
                             } else {
-                                uint32_t d = cand[i];
-                                int budget = P.chain;
-                                while (d != 0 && d <= maxd) {
-                                    /* cheap reject: the byte that would extend the best match must agree */
-                                    if (best < 3 || zl_ld8<RING>(S.ring32, q + best) == zl_ld8<RING>(S.ring32, q + best - d)) {
-                                        uint32_t l = zl_match_len<RING>(S.ring32, q, d, maxl);
-                                        if (l > best) { best = l; bestd = d; if (l >= (uint32_t)P.nice || l >= maxl) break; }
-                                    }
-                                    if (!CHAIN || budget-- <= 0) break;
-                                    uint32_t c = q - d;
-                                    /* links of positions the hasher may be recycling right now are off limits */
-                                    if (c + ZS_WINDOW < t0 + 2 * ZL_TILE) break;
-                                    uint32_t step = prevd[c & (ZS_WINDOW - 1)];
-                                    if (step == 0) break;
-                                    d += step;
+                                d = cand[i];
+                                if (d != 0 && d <= maxd) {
+                                    const uint32_t l = zl_match_len<RING>(S.ring32, q, d, maxl);
+                                    go = true;
+                                    if (l > 0) { best = l; bestd = d; if (l >= (uint32_t)P.nice || l >= maxl) go = false; }
                                 }
                             }
-                            if (best < (uint32_t)P.min_len || (best == 3 && bestd > ZS_TOO_FAR)) { best = 0; bestd = 0; }
                         }
+                        if constexpr (CHAIN) if (skip) {
+                            const uint32_t long_m = __ballot_sync(0xFFFFFFFFu, best >= skip);
+                            uint32_t next = 0;
+                            while (next < 32u) {
+                                const uint32_t m2 = long_m & (0xFFFFFFFFu << next);
+                                if (!m2) break;
+                                const uint32_t u = (uint32_t)__ffs((int)m2) - 1u;
+                                const uint32_t Lu = __shfl_sync(0xFFFFFFFFu, best, u), Du = __shfl_sync(0xFFFFFFFFu, bestd, u);
+                                if (lane >= u + 2u && lane < u + Lu && maxl != 0) {
+                                    go = false;
+                                    const uint32_t pl = Lu - (lane - u);
+                                    if (pl > best) { best = pl; bestd = Du; }
+                                }
+                                next = u + Lu;
+                            }
+                        }
+                        while (go) {
+                            if (!CHAIN || budget-- <= 0) break;
+                            const uint32_t c = q - d;
+                            /* links of positions the hasher may be recycling right now are off limits */
+                            if (c + ZS_WINDOW < t0 + 2 * ZL_TILE) break;
+                            const uint32_t step = prevd[c & (ZS_WINDOW - 1)];
+                            if (step == 0) break;
+                            d += step;
+                            if (d > maxd) break;
+                            /* cheap reject: the byte that would extend the best match must agree */
+                            if (best < 3 || zl_ld8<RING>(S.ring32, q + best) == zl_ld8<RING>(S.ring32, q + best - d)) {
+                                const uint32_t l = zl_match_len<RING>(S.ring32, q, d, maxl);
+                                if (l > best) { best = l; bestd = d; if (l >= (uint32_t)P.nice || l >= maxl) break; }
+                            }
+                        }
+                        if (best < (uint32_t)P.min_len || (best == 3 && bestd > ZS_TOO_FAR)) { best = 0; bestd = 0; }
                         S.t_len[i] = (uint16_t)best;
                         S.t_dist[i] = (uint16_t)bestd;
                     }

@@ -68,6 +68,23 @@ typedef struct {
     uint32_t tmpfreq[ZH_LCODES_PAD];
 } zh_scratch;
 
+/* Chain search (levels 2..9): first-candidate matches of at least this many bytes cover the positions behind
+ * them, which then skip their chain walk (deflate_lz.cu; 0 = every position walks its chain).  Derived from the
+ * chain depth so that the kernel and the host model (tests/cpu_harness.cpp) agree without another parameter:
+ * levels 2-3 (chain 1, 3) have nothing worth skipping, levels 4-9 use 16 (measured on the host model: a threshold of
+ * 32 changes nothing, 8 costs text more than the 2 % the ratio gate allows). */
+ZHD static inline uint32_t zs_skip_len(int chain) { return chain < 7 ? 0u : 16u; }
+
+/* the same working arrays sized for the 30-symbol distance alphabet (a lane-per-block kernel keeps one per
+   thread): the stage functions below are templates over the scratch type and behave identically on both */
+typedef struct {
+    uint32_t key[ZH_DCODES_PAD];
+    uint32_t w[2 * ZH_DCODES_PAD];
+    uint16_t parent[2 * ZH_DCODES_PAD];
+    uint8_t  depth[2 * ZH_DCODES_PAD];
+    uint32_t tmpfreq[ZH_DCODES_PAD];
+} zh_small;
+
 ZHD static inline int zh_extra_lbits(int c) { return (c < 8 || c == 28) ? 0 : ((c - 4) >> 2); }
 ZHD static inline int zh_extra_dbits(int c) { return c < 4 ? 0 : ((c - 2) >> 1); }
 
@@ -86,7 +103,7 @@ ZHD static inline uint32_t zh_bitrev(uint32_t v, int n)
  * sort on all its threads: prepare (keys = (freq << 9) | symbol of the used symbols; at least two symbols
  * end up with a code, as the reference guarantees for its trees, src/trees.c:595-610, so that the decoder
  * always sees a complete code), sort ascending, finish (two-queue merge, depths, length limit). */
-ZHD static inline int zh_lengths_prepare(const uint32_t *freq_in, int n, zh_scratch *s, int *max_code_out)
+template <class SC> ZHD static inline int zh_lengths_prepare(const uint32_t *freq_in, int n, SC *s, int *max_code_out)
 {
     uint32_t *freq = s->tmpfreq;
     int m = 0, max_code = -1;
@@ -121,7 +138,7 @@ ZHD static inline void zh_sort_keys(uint32_t *key, int m)
 
 /* two-queue merge over the sorted keys: leaves [0,m), internal nodes [m, 2m-1) in creation (= weight)
  * order; fills s->w and s->parent, returns the node count (root = count - 1) */
-ZHD static inline int zh_merge(int m, zh_scratch *s)
+template <class SC> ZHD static inline int zh_merge(int m, SC *s)
 {
     for (int i = 0; i < m; i++) s->w[i] = s->key[i] >> 9;
     int a = 0, b = m, e = m;
@@ -141,7 +158,7 @@ ZHD static inline int zh_merge(int m, zh_scratch *s)
  * sibling, which removes exactly one unit (the repair idea of the reference's gen_bitlen overflow loop,
  * src/trees.c:474-507, restated on the Kraft sum); then lengths are handed out by frequency, longest to
  * rarest (s->depth[i] of the i-th sorted key). */
-ZHD static inline void zh_repair(int maxbits, uint32_t *bl_count, zh_scratch *s)
+template <class SC> ZHD static inline void zh_repair(int maxbits, uint32_t *bl_count, SC *s)
 {
     int64_t excess = -((int64_t)1 << maxbits);
     for (int l = 1; l <= maxbits; l++) excess += (int64_t)bl_count[l] << (maxbits - l);
@@ -156,7 +173,7 @@ ZHD static inline void zh_repair(int maxbits, uint32_t *bl_count, zh_scratch *s)
         for (uint32_t k = 0; k < bl_count[bits]; k++) { s->depth[i] = (uint8_t)bits; i++; }
 }
 
-ZHD static inline void zh_lengths_finish(int m, int n, int maxbits, uint8_t *len, zh_scratch *s)
+template <class SC> ZHD static inline void zh_lengths_finish(int m, int n, int maxbits, uint8_t *len, SC *s)
 {
     for (int i = 0; i < n; i++) len[i] = 0;
     int e = zh_merge(m, s);
@@ -180,7 +197,7 @@ ZHD static inline void zh_lengths_finish(int m, int n, int maxbits, uint8_t *len
 }
 
 /* all three stages; returns the largest symbol index with a non-zero length */
-ZHD static inline int zh_lengths(const uint32_t *freq_in, int n, int maxbits, uint8_t *len, zh_scratch *s)
+template <class SC> ZHD static inline int zh_lengths(const uint32_t *freq_in, int n, int maxbits, uint8_t *len, SC *s)
 {
     int max_code;
     int m = zh_lengths_prepare(freq_in, n, s, &max_code);
