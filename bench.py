@@ -293,7 +293,7 @@ def run_gpu(args, rank, world, local_rank):
     inflate = None
     try:
         if world > 1:
-            raise RuntimeError("measured at N=1 only (a third pinned GiB per rank is not worth it for a side number)")
+            raise NotImplementedError
         comp = dest[:r1.produced]
         back = np.empty(n, dtype=np.uint8)
         E.L.zscgpu_host_register(back.ctypes.data, back.nbytes)
@@ -316,6 +316,8 @@ def run_gpu(args, rank, world, local_rank):
                    "e2e": round(world * n / 1e9 / inf_e2e_s, 3),
                    "what": "the 1 GiB stream this run produced (4096 sections) back through zscgpu_inflate_sectioned / zscgpu_uncompress_host",
                    "parity": "bit-exact with the input" if bool(np.array_equal(back, data)) else "MISMATCH"}
+    except NotImplementedError:
+        inflate = {"value": None, "note": "side measurement, taken at N=1 only"}
     except Exception as ex:  # pragma: no cover
         inflate = {"value": None, "error": repr(ex)}
     sampler.stop_flag = True
@@ -361,8 +363,8 @@ def run_gpu(args, rank, world, local_rank):
                      "kernel_share_of_step": round(lz / ms_per_step, 4),
                      "stage_ms": {"adler32": round(pk[0], 3), "lz77": round(pk[1], 3), "block_codes": round(pk[2], 3),
                                   "offsets": round(pk[3], 3), "bitpack": round(pk[4], 3)}},
-        "e2e": {"value": round(world * n / 1e9 / e2e_s, 3), "unit": "GB/s", "h2d_bytes_per_step": n,
-                "d2h_bytes_per_step": int(r1.produced), "api": "zscgpu_compress_host (the call behind zsc_compress), pinned host buffers"},
+        "e2e": {"value": round(world * n / 1e9 / e2e_s, 3), "unit": "GB/s", "h2d_bytes_per_step": world * n,
+                "d2h_bytes_per_step": world * int(r1.produced), "api": "zscgpu_compress_host (the call behind zsc_compress), pinned host buffers"},
         "gpu_launches": launches,
         "inflate": inflate,
         "inflate_batched": inflate4,
