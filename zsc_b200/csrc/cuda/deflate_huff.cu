@@ -54,10 +54,10 @@ zs_block_kernel(const ZsChunk *__restrict__ chunks, const uint32_t *__restrict__
                 const uint32_t *__restrict__ sym, const uint32_t *__restrict__ chunk_nsym,
                 const uint32_t *__restrict__ blk_in_start, zh_block *__restrict__ blocks,
                 uint4 *__restrict__ blk_meta, ZbScratch *__restrict__ scratch, uint32_t *__restrict__ used /* [0] = count, then slots */,
-                ZsLzParams P)
+                ZsLzParams P, uint32_t slot0 /* first block slot of this launch */)
 {
     __shared__ __align__(16) ZbSmem S;
-    const uint32_t b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t b = slot0 + blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t c = blk_chunk[b];
     const ZsChunk cd = chunks[c];
     const uint32_t k = b - cd.blk_base;
@@ -442,16 +442,21 @@ zs_block_kernel(const ZsChunk *__restrict__ chunks, const uint32_t *__restrict__
  *     (huff_build.h): the smaller head of the two queues, the leaf on ties.
  * (2) the whole distance tree (30 symbols: sort, merge, depths, length limit) with zh_lengths on a
  *     thread-private scratch. */
-__global__ void __launch_bounds__(ZMG_THREADS)
+__global__ void __launch_bounds__(2 * ZMG_THREADS)
 zs_merge_kernel(ZbScratch *__restrict__ scratch, const uint32_t *__restrict__ used)
 {
     extern __shared__ uint16_t zmg_w[];                    /* [2][ZH_LCODES_PAD][ZMG_THREADS]: leaves, internal nodes */
-    const uint32_t t = blockIdx.x * ZMG_THREADS + threadIdx.x;
+    /* the two jobs of a block run on two different threads (warps 0-1: merges, warps 2-3: distance trees): twice the
+       warps per SM for a kernel that is pure latency, and the jobs overlap instead of following each other */
+    const uint32_t col = threadIdx.x % ZMG_THREADS;
+    const bool dist_job = threadIdx.x >= ZMG_THREADS;
+    const uint32_t t = blockIdx.x * ZMG_THREADS + col;
     if (t >= used[0]) return;
     ZbScratch &X = scratch[used[1 + t]];
+    if (!dist_job) {
     const int m = X.m;
-    uint16_t *wl = zmg_w + threadIdx.x;
-    uint16_t *w = zmg_w + ZH_LCODES_PAD * ZMG_THREADS + threadIdx.x;
+    uint16_t *wl = zmg_w + col;
+    uint16_t *w = zmg_w + ZH_LCODES_PAD * ZMG_THREADS + col;
     {
         const uint4 *k4 = reinterpret_cast<const uint4 *>(X.key);
 #pragma unroll 4
@@ -474,7 +479,7 @@ zs_merge_kernel(ZbScratch *__restrict__ scratch, const uint32_t *__restrict__ us
         if (b == e) ib = sum;                              /* the queue was empty: the new node is its head */
         e++;
     }
-    {
+    } else {
         zh_small sc;
         uint32_t df[ZH_DCODES_PAD];
         uint8_t dl[ZH_DCODES_PAD];
@@ -823,30 +828,39 @@ zs_encode_kernel(const zh_block *__restrict__ blocks, const uint32_t *__restrict
 extern "C" size_t zs_encode_smem_bytes(void) { return sizeof(ZeSmem); }
 extern "C" size_t zs_block_scratch_bytes(void) { return sizeof(ZbScratch); }
 
+/* The block stage (histogram + sort, tree merges, codes + header) of the block slots [slot0, slot0 + nslots). */
+extern "C" cudaError_t zs_block_stage_launch(cudaStream_t st, uint32_t slot0, uint32_t nslots,
+                                             const ZsChunk *chunks, const uint32_t *blk_chunk, const uint32_t *sym,
+                                             const uint32_t *chunk_nsym, const uint32_t *blk_in_start, zh_block *blocks,
+                                             ZsLzParams P, void *blk_meta_v, void *blk_scratch_v, uint32_t *blk_used)
+{
+    if (nslots == 0) return cudaSuccess;
+    uint4 *blk_meta = reinterpret_cast<uint4 *>(blk_meta_v);
+    ZbScratch *scratch = reinterpret_cast<ZbScratch *>(blk_scratch_v);
+    cudaMemsetAsync(blk_used, 0, 4, st);
+    zs_block_kernel<0><<<nslots, ZB_THREADS, 0, st>>>(chunks, blk_chunk, sym, chunk_nsym, blk_in_start, blocks, blk_meta, scratch, blk_used, P, slot0);
+    {
+        const size_t smem = sizeof(uint16_t) * 2 * ZH_LCODES_PAD * ZMG_THREADS;
+        cudaFuncSetAttribute(zs_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        zs_merge_kernel<<<(nslots + ZMG_THREADS - 1) / ZMG_THREADS, 2 * ZMG_THREADS, smem, st>>>(scratch, blk_used);
+    }
+    zs_block_kernel<1><<<nslots, ZB_THREADS, 0, st>>>(chunks, blk_chunk, sym, chunk_nsym, blk_in_start, blocks, blk_meta, scratch, blk_used, P, slot0);
+    return cudaGetLastError();
+}
+
+/* Everything behind the block stage: stored-run merging, the offset scan, bit packing. */
 extern "C" cudaError_t zs_huff_launch(cudaStream_t st, uint32_t nblk_slots, uint32_t nstreams,
                                       const ZsChunk *chunks, const uint32_t *blk_chunk,
                                       const ZsStream *streams, const uint32_t *sym,
-                                      const uint32_t *chunk_nsym, const uint32_t *blk_in_start,
                                       zh_block *blocks, const ZsAdlerAcc *adler_acc,
                                       const uint8_t *raw, uint8_t *comp, int32_t *res_ret,
                                       uint32_t *res_produced, uint32_t *res_check, ZsLzParams P,
-                                      cudaEvent_t ev_after_block, cudaEvent_t ev_after_offset,
-                                      uint32_t nchunks, void *blk_meta_v, unsigned long long *blk_bitoff_v,
-                                      void *blk_scratch_v, uint32_t *blk_used)
+                                      cudaEvent_t ev_after_offset,
+                                      uint32_t nchunks, void *blk_meta_v, unsigned long long *blk_bitoff_v)
 {
     if (nblk_slots == 0 || nstreams == 0) return cudaSuccess;
     uint4 *blk_meta = reinterpret_cast<uint4 *>(blk_meta_v);
     uint64_t *blk_bitoff = reinterpret_cast<uint64_t *>(blk_bitoff_v);
-    ZbScratch *scratch = reinterpret_cast<ZbScratch *>(blk_scratch_v);
-    cudaMemsetAsync(blk_used, 0, 4, st);
-    zs_block_kernel<0><<<nblk_slots, ZB_THREADS, 0, st>>>(chunks, blk_chunk, sym, chunk_nsym, blk_in_start, blocks, blk_meta, scratch, blk_used, P);
-    {
-        const size_t smem = sizeof(uint16_t) * 2 * ZH_LCODES_PAD * ZMG_THREADS;
-        cudaFuncSetAttribute(zs_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        zs_merge_kernel<<<(nblk_slots + ZMG_THREADS - 1) / ZMG_THREADS, ZMG_THREADS, smem, st>>>(scratch, blk_used);
-    }
-    zs_block_kernel<1><<<nblk_slots, ZB_THREADS, 0, st>>>(chunks, blk_chunk, sym, chunk_nsym, blk_in_start, blocks, blk_meta, scratch, blk_used, P);
-    if (ev_after_block) cudaEventRecord(ev_after_block, st);
     zs_stored_merge_kernel<<<(nchunks + ZM_THREADS - 1) / ZM_THREADS, ZM_THREADS, 0, st>>>(chunks, nchunks, blocks, blk_meta);
     /* few streams with many blocks each: wide CTAs; many small streams: narrow ones */
     const uint32_t othreads = (nblk_slots / nstreams >= 1024u) ? ZO_THREADS_MAX : 128u;

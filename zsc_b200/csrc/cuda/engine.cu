@@ -14,10 +14,11 @@
 /* kernel launchers (deflate_lz.cu, deflate_huff.cu, checksum.cu, inflate.cu) */
 extern "C" cudaError_t zs_lz_launch(cudaStream_t, int, uint32_t, const uint8_t *, const ZsChunk *, uint32_t *, uint32_t *, uint32_t *, ZsLzParams);
 extern "C" uint32_t zs_lz_fast_max_dist(void);
+extern "C" cudaError_t zs_block_stage_launch(cudaStream_t, uint32_t, uint32_t, const ZsChunk *, const uint32_t *, const uint32_t *,
+                                             const uint32_t *, const uint32_t *, zh_block *, ZsLzParams, void *, void *, uint32_t *);
 extern "C" cudaError_t zs_huff_launch(cudaStream_t, uint32_t, uint32_t, const ZsChunk *, const uint32_t *, const ZsStream *, const uint32_t *,
-                                      const uint32_t *, const uint32_t *, zh_block *, const ZsAdlerAcc *, const uint8_t *, uint8_t *,
-                                      int32_t *, uint32_t *, uint32_t *, ZsLzParams, cudaEvent_t, cudaEvent_t,
-                                      uint32_t, void *, unsigned long long *, void *, uint32_t *);
+                                      zh_block *, const ZsAdlerAcc *, const uint8_t *, uint8_t *, int32_t *, uint32_t *, uint32_t *, ZsLzParams,
+                                      cudaEvent_t, uint32_t, void *, unsigned long long *);
 extern "C" size_t zs_block_scratch_bytes(void);
 extern "C" cudaError_t zs_adler_chunks_launch(cudaStream_t, uint32_t, const uint8_t *, const ZsChunk *, const ZsStream *, ZsAdlerAcc *);
 extern "C" cudaError_t zs_adler_flat_launch(cudaStream_t, const uint8_t *, uint64_t, ZsAdlerAcc *, int);
@@ -453,23 +454,30 @@ static int zs_deflate_launch_slice(zscgpu_engine *e, const ZsSlice &sl, uint32_t
     ZsStream *streams = e->d_streams + sl.stream0;
     uint32_t *sym = e->d_sym + sl.sym0;
     ZsAdlerAcc *adler = e->d_adler + sl.stream0;
-    /* event slots 8..13 bracket the kernels of the last deflate launch (see zscgpu.h) */
+    /* event slots 8..13 bracket the kernels of the last deflate launch (see zscgpu.h).  Measured and dropped: the
+       adler32 pass or the block stage of one half on a side stream beside the LZ kernel — whatever runs beside that
+       kernel takes SM slots from it and the step stays within 0.1 ms of the plain sequence. */
+    uint32_t *chunk_nsym = e->d_chunk_nsym + sl.chunk0, *blk_in_start = e->d_blk_in_start + sl.blk0 + (sl.blk0 ? 1 : 0);
+    uint32_t *blk_chunk = e->d_blk_chunk + sl.blk0;
+    zh_block *blocks = e->d_blocks + sl.blk0;
+    uint4 *blk_meta = e->d_blk_meta + sl.blk0;
     ZS_CUDA_CHECK(cudaMemsetAsync(adler, 0, sizeof(ZsAdlerAcc) * n, st));
     if (sl.timed) ZS_CUDA_CHECK(cudaEventRecord(e->ev[8], st));
     ZS_CUDA_CHECK(zs_adler_chunks_launch(st, nc, e->d_raw, chunks, streams, adler));
     if (sl.timed) ZS_CUDA_CHECK(cudaEventRecord(e->ev[9], st));
-    ZS_CUDA_CHECK(zs_lz_launch(st, chain, nc, e->d_raw, chunks, sym, e->d_chunk_nsym + sl.chunk0, e->d_blk_in_start + sl.blk0 + (sl.blk0 ? 1 : 0), L));
+    ZS_CUDA_CHECK(zs_lz_launch(st, chain, nc, e->d_raw, chunks, sym, chunk_nsym, blk_in_start, L));
     if (sl.timed) ZS_CUDA_CHECK(cudaEventRecord(e->ev[10], st));
-    ZS_CUDA_CHECK(zs_huff_launch(st, nb, n, chunks, e->d_blk_chunk + sl.blk0, streams, sym, e->d_chunk_nsym + sl.chunk0,
-                                 e->d_blk_in_start + sl.blk0 + (sl.blk0 ? 1 : 0), e->d_blocks + sl.blk0, adler, e->d_raw, e->d_comp,
+    ZS_CUDA_CHECK(zs_block_stage_launch(st, 0, nb, chunks, blk_chunk, sym, chunk_nsym, blk_in_start, blocks, L, blk_meta,
+                                        e->d_blk_scratch + (size_t)sl.blk0 * zs_block_scratch_bytes(), e->d_blk_used + sl.used0));
+    if (sl.timed) ZS_CUDA_CHECK(cudaEventRecord(e->ev[11], st));
+    ZS_CUDA_CHECK(zs_huff_launch(st, nb, n, chunks, blk_chunk, streams, sym, blocks, adler, e->d_raw, e->d_comp,
                                  e->d_ret + sl.stream0, e->d_produced + sl.stream0, e->d_check + sl.stream0, L,
-                                 sl.timed ? e->ev[11] : nullptr, sl.timed ? e->ev[12] : nullptr, nc, e->d_blk_meta + sl.blk0, e->d_blk_bitoff + sl.blk0,
-                                 e->d_blk_scratch + (size_t)sl.blk0 * zs_block_scratch_bytes(), e->d_blk_used + sl.used0));
+                                 sl.timed ? e->ev[12] : nullptr, nc, blk_meta, e->d_blk_bitoff + sl.blk0));
     if (sl.timed) ZS_CUDA_CHECK(cudaEventRecord(e->ev[13], st));
     ZS_CUDA_CHECK(cudaMemcpyAsync(e->h_ret + sl.stream0, e->d_ret + sl.stream0, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
     ZS_CUDA_CHECK(cudaMemcpyAsync(e->h_produced + sl.stream0, e->d_produced + sl.stream0, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, st));
     ZS_CUDA_CHECK(cudaMemcpyAsync(e->h_check + sl.stream0, e->d_check + sl.stream0, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, st));
-    e->launches = 8;   /* adler, lz, block (histogram / tree merge / codes), stored-run merge, offset, encode */
+    e->launches = 8;   /* adler, lz, block stage (histogram / tree merges / codes), stored-run merge, offset, encode */
     e->launches_total += 8;
     return ZSCGPU_OK;
 }
