@@ -410,6 +410,10 @@ def test_sectioned_inflate_equals_one_stream_inflate(checker):
             assert r.ret == 0
             a, out = _both_ways(E, comp, n)
             assert a.ret == 0 and a.consumed == len(comp) and a.check == zlib.adler32(x.tobytes()) and np.array_equal(out, x)
+            if mbl < n:
+                # equal sections and an exact capacity: the one-pass form (marker scan, decode, adler32) must have served it
+                E.inflate_sectioned(Engine.make_streams([0], [n], [0], [len(comp)]), 1)
+                assert E.L.zscgpu_last_launch_count(E.h) == 3
             # output one byte short, input cut: whatever the one-stream path answers
             _both_ways(E, comp, n - 1)
             _both_ways(E, comp[:len(comp) // 2], n)

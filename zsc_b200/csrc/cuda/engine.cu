@@ -617,6 +617,49 @@ extern "C" int zscgpu_inflate_sectioned(zscgpu_engine *e, const zscgpu_stream *s
     while (ns > 1 && start[ns - 1] >= stream->comp_len) ns--;
     if (ns < 2) return zscgpu_inflate_batch(e, stream, 1, wrap, res);
 
+    /* One pass when the stream looks like zsc_compress made it: K sections of exactly max_block_len bytes and a
+       shorter last one (reference src/zsc_compress.c:121-140).  If the caller's capacity N is the size of the data,
+       the section size S satisfies (K - 1) S < N <= K S; section sizes are round numbers, so of that range the
+       value with the most trailing zero bits is tried: every candidate is decoded straight to k * S with room S.
+       The result stands only if the sections chain exactly — each but the last produced S bytes and stopped at a
+       flush point exactly where the next candidate starts, the last one reached the end of the stream — and
+       the data check over the whole output agrees; otherwise the two passes below run as if nothing had happened. */
+    if (ns >= 8 && stream->raw_len >= ns) {
+        const uint64_t N = stream->raw_len, K = ns;
+        const uint64_t lo = (N + K - 1) / K, hi = (N - 1) / (K - 1);
+        uint64_t S = 0;
+        for (int bsh = 31; bsh >= 8 && !S; bsh--) { const uint64_t x = (hi >> bsh) << bsh; if (x >= lo && x > 0) S = x; }
+        if (S) {
+            for (uint32_t k = 0; k < ns; k++) {
+                st[k].raw_off = stream->raw_off + (uint64_t)k * S;
+                st[k].raw_len = (uint32_t)(k + 1 < ns ? S : N - (uint64_t)k * S);
+                st[k].comp_off = stream->comp_off + start[k]; st[k].comp_len = stream->comp_len - start[k];
+                opts[k] = 2u | (k ? 4u : 0u);
+            }
+            int rcs = zs_inflate_enqueue_opts(e, st, ns, wrap, opts); if (rcs) return rcs;
+            rcs = zscgpu_fetch_results(e, ns, r1); if (rcs) return rcs;
+            bool good = true;
+            uint64_t total = 0;
+            uint32_t end_pos = 0, stored_check = 0, have_check = 0;
+            for (uint32_t k = 0; k < ns && good; k++) {
+                const uint32_t f = e->h_aux[2 * k + 1];
+                if (r1[k].ret != 0 || (f & 2u)) good = false;
+                else if (k + 1 < ns) good = (f & 4u) && r1[k].produced == S && start[k] + r1[k].consumed == start[k + 1];
+                else { good = !(f & 4u); stored_check = e->h_aux[2 * k]; have_check = f & 1u; end_pos = start[k] + r1[k].consumed; }
+                total += r1[k].produced;
+            }
+            if (good) {
+                uint32_t check = 1;
+                rcs = zscgpu_adler32(e, stream->raw_off, total, 1u, &check); if (rcs) return rcs;
+                if (!((wrap & 0xFF) == 1 && have_check && stored_check != check)) {
+                    res->ret = 0; res->produced = (uint32_t)total; res->consumed = end_pos; res->check = check;
+                    e->launches = 3;   /* marker scan, decode pass, adler32 */
+                    return ZSCGPU_OK;
+                }
+            }
+        }
+    }
+
     /* pass 1: sizes */
     for (uint32_t k = 0; k < ns; k++) {
         st[k].raw_off = stream->raw_off; st[k].raw_len = stream->raw_len;
