@@ -571,10 +571,28 @@ ZID uint32_t zi_lut_dist(uint32_t d)
     const uint32_t eb = d < 4 ? 0u : ((d - 2) >> 1);
     return (d < 4 ? 1u + d : 1u + ((2u + (d & 1u)) << eb)) | (eb << 16);
 }
+/* On the GPU the decode tables, the base/extra-bits tables and the record queue of zi_fast_batch are in shared
+ * memory.  Their 32-bit shared-space addresses are taken once and made opaque to the compiler: left to itself it
+ * recomputes them from threadIdx for every symbol (two S2R and five arithmetic instructions, measured as 6 of the
+ * 35 instructions of the literal path) because the loop is short of registers. */
+#ifdef __CUDA_ARCH__
+typedef uint32_t zi_sa;
+static __device__ __forceinline__ zi_sa zi_sa_of(const void *p) { uint32_t v = (uint32_t)__cvta_generic_to_shared(p); asm volatile("" : "+r"(v)); return v; }
+static __device__ __forceinline__ uint32_t zi_sa_ld16(zi_sa a) { uint16_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a)); return v; }
+static __device__ __forceinline__ uint32_t zi_sa_ld32(zi_sa a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+static __device__ __forceinline__ void zi_sa_st32(zi_sa a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v)); }
+#else
+typedef uintptr_t zi_sa;
+static inline zi_sa zi_sa_of(const void *p) { return (zi_sa)p; }
+static inline uint32_t zi_sa_ld16(zi_sa a) { return *(const uint16_t *)a; }
+static inline uint32_t zi_sa_ld32(zi_sa a) { return *(const uint32_t *)a; }
+static inline void zi_sa_st32(zi_sa a, uint32_t v) { *(uint32_t *)a = v; }
+#endif
+
 ZID uint32_t zi_fast_batch(zi_mach *m, const uint32_t *lut_len, const uint32_t *lut_dist, uint32_t *q, uint32_t maxn, uint32_t *vop)
 {
     const zi_tables *T = m->T;
-    const uint16_t *lit = T->lit, *dtab = T->dist;
+    const zi_sa lit_a = zi_sa_of(T->lit), dist_a = zi_sa_of(T->dist), len_a = zi_sa_of(lut_len), dl_a = zi_sa_of(lut_dist), q_a = zi_sa_of(q);
     uint32_t n = 0, op = m->io.op;
     /* how many symbols this batch may take: each needs at most 258 bytes of output room and pulls at most
        8 bytes of input (two refills); the last 16 input bytes are left to zi_step */
@@ -595,7 +613,7 @@ ZID uint32_t zi_fast_batch(zi_mach *m, const uint32_t *lut_len, const uint32_t *
         const uint32_t b = io.bits;
         uint32_t l, sym;
         {
-            const uint32_t e = lit[(uint32_t)h & ((1u << ZI_LBITS) - 1u)];
+            const uint32_t e = zi_sa_ld16(lit_a + 2u * ((uint32_t)h & ((1u << ZI_LBITS) - 1u)));
             if (e) { l = e >> 9; sym = e & 511u; }
             else {
                 const uint32_t v = zi_rev((uint32_t)h & 0x7FFFu, 15);
@@ -609,9 +627,9 @@ ZID uint32_t zi_fast_batch(zi_mach *m, const uint32_t *lut_len, const uint32_t *
                 if (l == 0) break;
             }
         }
-        if (sym < 256u) { io.hold = h >> l; io.bits = b - l; q[n++] = sym; op++; continue; }
+        if (sym < 256u) { io.hold = h >> l; io.bits = b - l; zi_sa_st32(q_a + 4u * n, sym); n++; op++; continue; }
         if (sym == 256u || sym > 285u) break;
-        const uint32_t lb = lut_len[sym - 257u], eb = lb >> 16;
+        const uint32_t lb = zi_sa_ld32(len_a + 4u * (sym - 257u)), eb = lb >> 16;
         const uint32_t len = (lb & 0xFFFFu) + ((uint32_t)(h >> l) & ((1u << eb) - 1u));
         const uint32_t ip0 = io.ip, pre0 = io.pre, pv0 = io.pv;
         io.hold = h >> (l + eb); io.bits = b - (l + eb);
@@ -620,7 +638,7 @@ ZID uint32_t zi_fast_batch(zi_mach *m, const uint32_t *lut_len, const uint32_t *
         const uint32_t b2 = io.bits;
         uint32_t l2, d;
         {
-            const uint32_t e = dtab[(uint32_t)h2 & ((1u << ZI_DBITS) - 1u)];
+            const uint32_t e = zi_sa_ld16(dist_a + 2u * ((uint32_t)h2 & ((1u << ZI_DBITS) - 1u)));
             if (e) { l2 = e >> 5; d = e & 31u; }
             else {
                 const uint32_t v = zi_rev((uint32_t)h2 & 0x7FFFu, 15);
@@ -635,7 +653,7 @@ ZID uint32_t zi_fast_batch(zi_mach *m, const uint32_t *lut_len, const uint32_t *
         }
         uint32_t dist = 0, eb2 = 0;
         if (l2 != 0 && d <= 29u) {
-            const uint32_t db = lut_dist[d];
+            const uint32_t db = zi_sa_ld32(dl_a + 4u * d);
             eb2 = db >> 16;
             dist = (db & 0xFFFFu) + ((uint32_t)(h2 >> l2) & ((1u << eb2) - 1u));
         }
@@ -645,7 +663,7 @@ ZID uint32_t zi_fast_batch(zi_mach *m, const uint32_t *lut_len, const uint32_t *
             break;
         }
         io.hold = h2 >> (l2 + eb2); io.bits = b2 - (l2 + eb2);
-        q[n++] = 0x80000000u | ((len - 3u) << 16) | (dist - 1u);
+        zi_sa_st32(q_a + 4u * n, 0x80000000u | ((len - 3u) << 16) | (dist - 1u)); n++;
         op += len;
     }
     m->io.hold = io.hold; m->io.bits = io.bits; m->io.ip = io.ip; m->io.pre = io.pre; m->io.pv = io.pv;
