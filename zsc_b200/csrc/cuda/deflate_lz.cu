@@ -371,19 +371,26 @@ zs_lz_kernel(const uint8_t *__restrict__ raw, const ZsChunk *__restrict__ chunks
                                 next = u + Lu;
                             }
                         }
+                        /* The walk is a pointer chase through the link array: per candidate one link lookup and one
+                           byte of the ring (cheap reject: the byte that would extend the best match must agree).
+                           Both depend only on the candidate's distance, so the link of the candidate about to be
+                           examined is requested together with its reject byte (a link read too early is simply not
+                           used when the checks below say so); the byte behind the best match is kept in a register. */
+                        uint32_t step_next = go ? (uint32_t)prevd[(q - d) & (ZS_WINDOW - 1)] : 0u;
+                        uint32_t tail = go ? zl_ld8<RING>(S.ring32, q + best) : 0u;
+                        const uint32_t c_min = t0 + 2 * ZL_TILE - ZS_WINDOW;     /* links of positions the hasher may be recycling right now are off limits */
                         while (go) {
                             if (!CHAIN || budget-- <= 0) break;
-                            const uint32_t c = q - d;
-                            /* links of positions the hasher may be recycling right now are off limits */
-                            if (c + ZS_WINDOW < t0 + 2 * ZL_TILE) break;
-                            const uint32_t step = prevd[c & (ZS_WINDOW - 1)];
+                            if ((int32_t)(q - d - c_min) < 0) break;
+                            const uint32_t step = step_next;
                             if (step == 0) break;
                             d += step;
                             if (d > maxd) break;
-                            /* cheap reject: the byte that would extend the best match must agree */
-                            if (best < 3 || zl_ld8<RING>(S.ring32, q + best) == zl_ld8<RING>(S.ring32, q + best - d)) {
+                            step_next = prevd[(q - d) & (ZS_WINDOW - 1)];
+                            const uint32_t rb = zl_ld8<RING>(S.ring32, q + best - d);
+                            if (best < 3 || rb == tail) {
                                 const uint32_t l = zl_match_len<RING>(S.ring32, q, d, maxl);
-                                if (l > best) { best = l; bestd = d; if (l >= (uint32_t)P.nice || l >= maxl) break; }
+                                if (l > best) { best = l; bestd = d; if (l >= (uint32_t)P.nice || l >= maxl) break; tail = zl_ld8<RING>(S.ring32, q + best); }
                             }
                         }
                         if (best < (uint32_t)P.min_len || (best == 3 && bestd > ZS_TOO_FAR)) { best = 0; bestd = 0; }
