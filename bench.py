@@ -216,6 +216,41 @@ def inflate_config4(device):
         E.close()
 
 
+def deflate_config2(device):
+    """BASELINE configs[2]: 4096 independent 256 KiB telemetry-like buffers, one stream each, at levels 6 and 9 (hash
+    chains + lazy parse, the chain kernel), device resident; ratio against the reference on the first 64 buffers."""
+    from zsc_b200 import Engine, datagen
+    import refimpl
+    nbuf, S, slot = 4096, 262144, 300000
+    n = nbuf * S
+    x = datagen.telemetry_buffers(nbuf, S, seed=1000)
+    E = Engine(raw_bytes=n + (1 << 20), comp_bytes=nbuf * slot + (1 << 20), deflate_batch_max=n + (1 << 20), max_streams=nbuf, max_chunks=nbuf + 16, device=device)
+    out = {}
+    try:
+        E.upload(0, 0, x)
+        st = Engine.make_streams([i * S for i in range(nbuf)], [S] * nbuf, [i * slot for i in range(nbuf)], [slot] * nbuf)
+        for level in (6, 9):
+            E.deflate_enqueue(st, S, level)
+            res = E.fetch(nbuf)
+            assert all(r.ret == 0 for r in res)
+            csize = sum(r.produced for r in res)
+            E.event(0); E.relaunch(); E.event(1); E.sync()
+            ms = E.elapsed_ms(0, 1)
+            row = {"value": round(n / 1e6 / ms, 3), "unit": "GB/s", "ms": round(ms, 2), "ratio": round(n / csize, 4)}
+            if refimpl.have_ref():
+                R = refimpl.ref()
+                k = 64
+                ref_c = sum(len(R.compress(x[i * S:(i + 1) * S], S, level)[1]) for i in range(k))
+                ours = sum(res[i].produced for i in range(k))
+                back = R.uncompress(E.download(1, 0, res[0].produced), S)
+                row["size_vs_reference"] = round(ours / ref_c, 4)
+                row["parity"] = "reference inflates buffer 0 bit-exact" if back[0] == 0 and bool(np.array_equal(back[1], x[:S])) else "MISMATCH"
+            out[str(level)] = row
+        return {"workload": "configs[2]: 4096 x 256 KiB telemetry-like buffers, one zlib stream each", "levels": out}
+    finally:
+        E.close()
+
+
 def run_gpu(args, rank, world, local_rank):
     from zsc_b200 import Engine, datagen, DeflateParams, Result
     dist = None
@@ -322,6 +357,12 @@ def run_gpu(args, rank, world, local_rank):
         inflate = {"value": None, "error": repr(ex)}
     sampler.stop_flag = True
     sampler.join(timeout=2)
+    levels = None
+    if world == 1 and not args.no_inflate_batch:
+        try:
+            levels = deflate_config2(local_rank)
+        except Exception as ex:  # pragma: no cover
+            levels = {"error": repr(ex)}
     inflate4 = None
     if world == 1 and not args.no_inflate_batch:
         try:
@@ -368,6 +409,7 @@ def run_gpu(args, rank, world, local_rank):
         "gpu_launches": launches,
         "inflate": inflate,
         "inflate_batched": inflate4,
+        "deflate_levels_6_9": levels,
         "clocks": sampler.summary(),
     }
     if world == 1 and not args.no_cpu_baseline:
@@ -395,7 +437,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="zsc_b200", choices=["zsc_b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-inflate-batch", action="store_true", help="skip the configs[3] side measurement (16 GiB batched inflate)")
+    ap.add_argument("--no-inflate-batch", action="store_true", help="skip the side measurements (configs[2] levels 6/9, configs[3] 16 GiB batched inflate)")
     args = ap.parse_args()
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     if args.warmup < 3 and args.impl != "reference":

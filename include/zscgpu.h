@@ -26,6 +26,13 @@
  *
  * All functions return 0 on success or a negative zscgpu_status; stream-level results use the
  * reference's ZlibReturn values (Z_OK 0, Z_DATA_ERROR -3, Z_BUF_ERROR -5 ...).
+ *
+ * Threading: the zsc_pub.h entry points and the one-shot host-buffer calls below (zscgpu_compress_host,
+ * zscgpu_uncompress_host, zscgpu_checksum_host) may be called from any number of threads — they serialise on the
+ * engine, as every call uses the whole arenas.  The batched, device-resident calls (enqueue / relaunch / fetch,
+ * upload / download) belong to ONE thread per engine at a time: the descriptor arrays and result slots of an
+ * engine hold one batch.  Concurrency beyond that is one engine per caller (zscgpu_init is cheap to repeat with
+ * smaller arenas) or, across GPUs, one engine per device.
  */
 #ifndef ZSCGPU_H
 #define ZSCGPU_H
