@@ -142,6 +142,9 @@ int zscgpu_inflate_enqueue(zscgpu_engine *e, const zscgpu_stream *streams, uint3
  * like independent streams once a scan for the flush markers and a size-only pass have located them.  Same
  * result as zscgpu_inflate_batch on that one stream (to which anything irregular falls back). */
 int zscgpu_inflate_sectioned(zscgpu_engine *e, const zscgpu_stream *stream, int32_t wrap, zscgpu_result *result);
+/* The section size zscgpu_inflate_sectioned tries first (one decode pass instead of two) for a stream of `sections`
+ * flush-delimited sections whose data fills `total` bytes; 0 when no plausible uniform size exists.  Pure arithmetic. */
+uint64_t zscgpu_guess_section_size(uint64_t total, uint32_t sections);
 int zscgpu_fetch_results(zscgpu_engine *e, uint32_t n, zscgpu_result *res);
 /* Re-launch the kernels of the last enqueue without rebuilding descriptors (bench inner loop). */
 int zscgpu_relaunch(zscgpu_engine *e);

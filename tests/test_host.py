@@ -36,6 +36,30 @@ def test_library_exports_every_declared_symbol():
     assert declared <= set(capi.ZSC_SYMBOLS), declared - set(capi.ZSC_SYMBOLS)
 
 
+def test_section_size_guess_of_the_one_pass_inflate():
+    """zscgpu_guess_section_size: for every stream zsc_compress can make (sections of max_block_len, a shorter last
+    one) with a round max_block_len and an exact capacity the guess is max_block_len; it never leaves the range the
+    section count allows; it declines when nothing round fits."""
+    L = capi.lib()
+    f = L.zscgpu_guess_section_size
+    f.argtypes = [C.c_uint64, C.c_uint32]; f.restype = C.c_uint64
+    rng = np.random.default_rng(3)
+    for mbl in (4096, 65536, 100000 // 32 * 32 * 8, 262144, 1 << 20, 3 << 18):
+        for _ in range(200):
+            k = int(rng.integers(8, 5000))
+            last = int(rng.integers(1, mbl + 1))
+            total = (k - 1) * mbl + last
+            if total >= 1 << 32:
+                continue
+            g = f(total, k)
+            assert g == 0 or ((k - 1) * g < total <= k * g)
+            if mbl & (mbl - 1) == 0:
+                assert g == mbl, (mbl, k, last, g)       # a power of two is always the roundest value of its range
+    assert f((1 << 30), 4096) == 262144 and f((1 << 30) + 5, 4097) == 262144
+    assert f(10, 2) == 0 and f(5, 8) == 0 and f(1000, 1) == 0
+    assert f(8 * 1000 + 1, 9) == 0                      # the range [889, 1000] holds no multiple of 256
+
+
 def test_size_check_functions_match_reference_fixture():
     Z = capi.zsc()
     for row in load("ref_sizes.json")["rows"]:

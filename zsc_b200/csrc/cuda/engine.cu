@@ -581,6 +581,18 @@ __global__ void zs_marker_scan_kernel(const uint8_t *__restrict__ comp, uint32_t
     }
 }
 
+/* The uniform section size a stream of `sections` flush-delimited sections most plausibly has when its data fills
+ * `total` bytes: (sections - 1) S < total <= sections S, and of that range the value with the most trailing zero
+ * bits (at least 8: max_block_len is a round number in practice).  0 = no such value; the caller then measures. */
+extern "C" uint64_t zscgpu_guess_section_size(uint64_t total, uint32_t sections)
+{
+    if (sections < 2 || total < sections) return 0;
+    const uint64_t K = sections;
+    const uint64_t lo = (total + K - 1) / K, hi = (total - 1) / (K - 1);
+    for (int bsh = 40; bsh >= 8; bsh--) { const uint64_t x = (hi >> bsh) << bsh; if (x >= lo && x > 0) return x; }
+    return 0;
+}
+
 extern "C" int zscgpu_inflate_sectioned(zscgpu_engine *e, const zscgpu_stream *stream, int32_t wrap, zscgpu_result *res)
 {
     if (!stream || !res || (wrap & 0xFF) > 1 || wrap < 0) { snprintf(e->err, sizeof(e->err), "bad inflate arguments"); return ZSCGPU_ERR_ARG; }
@@ -625,10 +637,8 @@ extern "C" int zscgpu_inflate_sectioned(zscgpu_engine *e, const zscgpu_stream *s
        flush point exactly where the next candidate starts, the last one reached the end of the stream — and
        the data check over the whole output agrees; otherwise the two passes below run as if nothing had happened. */
     if (ns >= 8 && stream->raw_len >= ns) {
-        const uint64_t N = stream->raw_len, K = ns;
-        const uint64_t lo = (N + K - 1) / K, hi = (N - 1) / (K - 1);
-        uint64_t S = 0;
-        for (int bsh = 31; bsh >= 8 && !S; bsh--) { const uint64_t x = (hi >> bsh) << bsh; if (x >= lo && x > 0) S = x; }
+        const uint64_t N = stream->raw_len;
+        const uint64_t S = zscgpu_guess_section_size(N, ns);
         if (S) {
             for (uint32_t k = 0; k < ns; k++) {
                 st[k].raw_off = stream->raw_off + (uint64_t)k * S;
