@@ -1,5 +1,5 @@
 """Inflate throughput probe: N reference-compressed 256 KiB streams (levels 1/6/9 in thirds), replicated.
-usage: prof_inflate.py UNIQ REP [G,G,...]   (G = forced lanes per stream, 0 = the engine's own choice)"""
+usage: prof_inflate.py UNIQ REP   (build variants of the engine with tools/build_variant.sh and pick one with ZSC_B200_LIB)"""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -8,7 +8,7 @@ from zsc_b200 import Engine, datagen
 import refimpl
 uniq = int(sys.argv[1]) if len(sys.argv) > 1 else 512
 rep = int(sys.argv[2]) if len(sys.argv) > 2 else 8
-gs = [int(g) for g in sys.argv[3].split(",")] if len(sys.argv) > 3 else [0]
+gs = [0]
 S = 262144
 n = uniq * rep
 E = Engine(raw_bytes=n * S + (1 << 20), comp_bytes=n * 160000 + (1 << 20), deflate_batch_max=uniq * S + (1 << 20), max_streams=n, max_chunks=uniq + 16)
@@ -48,10 +48,6 @@ for r_ in range(rep):
     offs += [(r_ * rep_bytes + o, l) for o, l in offs1]
 st = Engine.make_streams([i * S for i in range(n)], [S] * n, [o[0] for o in offs], [o[1] for o in offs])
 for g in gs:
-    if g:
-        os.environ["ZSC_B200_INFLATE_G"] = str(g)
-    else:
-        os.environ.pop("ZSC_B200_INFLATE_G", None)
     E.inflate_enqueue(st, 1)
     res = E.fetch(n)
     bad = sum(1 for r in res if r.ret != 0 or r.produced != S)
