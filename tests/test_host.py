@@ -114,6 +114,47 @@ def test_argument_errors_are_reported_before_any_gpu_work():
     assert L.adler32_z(0, None, 0) == 1 and L.crc32_z(0, None, 0) == 0                 # src/adler32.c:82-84, src/crc32.c:507
 
 
+DEATH_CASES = [
+    ("zsc_compress", "source", "L.zsc_compress(buf, C.byref(n), None, 100, 100, work, 400000, 6)"),
+    ("zsc_compress", "dest", "L.zsc_compress(None, C.byref(n), buf, 100, 100, work, 400000, 6)"),
+    ("zsc_compress", "dest_len", "L.zsc_compress(buf, None, buf, 100, 100, work, 400000, 6)"),
+    ("zsc_compress", "work", "L.zsc_compress(buf, C.byref(n), buf, 100, 100, None, 400000, 6)"),
+    ("zsc_compress", "max_block_len", "L.zsc_compress(buf, C.byref(n), buf, 100, 0, work, 400000, 6)"),
+    ("zsc_uncompress", "source", "L.zsc_uncompress(buf, C.byref(n), None, C.byref(m), work, 400000)"),
+    ("zsc_uncompress", "source_len", "L.zsc_uncompress(buf, C.byref(n), buf, None, work, 400000)"),
+    ("zsc_uncompress", "dest", "L.zsc_uncompress(None, C.byref(n), buf, C.byref(m), work, 400000)"),
+    ("zsc_uncompress", "dest_len", "L.zsc_uncompress(buf, None, buf, C.byref(m), work, 400000)"),
+    ("zsc_uncompress", "work", "L.zsc_uncompress(buf, C.byref(n), buf, C.byref(m), None, 400000)"),
+    ("zsc_compress_get_max_output_size", "size_out", "L.zsc_compress_get_max_output_size(1000, 100, 6, None)"),
+    ("zsc_compress_get_min_work_buf_size", "size_out", "L.zsc_compress_get_min_work_buf_size(None)"),
+    ("zsc_uncompress_get_min_work_buf_size", "size_out", "L.zsc_uncompress_get_min_work_buf_size(None)"),
+]
+
+
+@pytest.mark.parametrize("fn,param,call", DEATH_CASES, ids=[f"{c[0]}-{c[1]}" for c in DEATH_CASES])
+def test_null_arguments_fire_the_assertion_naming_the_parameter(fn, param, call):
+    """The reference's death tests (test/zlib_gtest.cpp:2105-2390): a NULL source / dest / dest_len / work /
+    source_len / size_out, or max_block_len == 0, fires ZSC_ASSERT with the parameter in the message — before any
+    GPU work, so this holds on a machine without one.  Each case runs in its own process."""
+    import subprocess
+    import sys
+    code = (
+        "import ctypes as C, sys\n"
+        f"sys.path.insert(0, {ROOT!r})\n"
+        "from zsc_b200 import capi\n"
+        "L = capi.lib()\n"
+        "buf = (C.c_uint8 * 4096)(); work = (C.c_uint8 * 400000)()\n"
+        "n = C.c_uint32(4096); m = C.c_uint32(100)\n"
+        "for f in ('zsc_compress', 'zsc_uncompress', 'zsc_compress_get_max_output_size', 'zsc_compress_get_min_work_buf_size', 'zsc_uncompress_get_min_work_buf_size'):\n"
+        "    getattr(L, f).argtypes = None\n"
+        f"{call}\n"
+        "print('survived')\n"
+    )
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert r.returncode != 0 and "survived" not in r.stdout, (r.returncode, r.stdout, r.stderr)
+    assert "Assertion" in r.stderr and re.search(rf"\b{param} != ", r.stderr), r.stderr
+
+
 @pytest.mark.skipif(has_gpu(), reason="checks the no-GPU behaviour")
 def test_no_cpu_fallback_without_a_gpu(capfd):
     """With no B200 the codec entry points must fail loudly, not fall back to a CPU path."""
