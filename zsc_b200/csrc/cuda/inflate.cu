@@ -9,7 +9,6 @@
  */
 #include "common.cuh"
 #include "inflate_core.h"
-#include <stdlib.h>
 
 #ifndef ZS_INFLATE_WARP_MAX
 #define ZS_INFLATE_WARP_MAX 6144u                /* streams in a batch up to which each gets a whole warp */
@@ -17,33 +16,19 @@
 
 /* ======================= a group of G lanes per stream ======================= */
 /* The leader lane of a group runs the state machine.  Inside a compressed block it decodes up to G symbols
- * into a record queue with zw_fast_decode — a pure accelerator: it only takes symbols whose codes resolve
+ * into a record queue with zi_fast_batch — a pure accelerator: it only takes symbols whose codes resolve
  * from the stream's shared-memory tables and that are valid, fit the output and cannot run past the input;
  * at anything else (end of block, a bad code, the last bytes of a buffer) it stops in front of that symbol
  * without consuming it and the generic zi_step, the code the CPU tests pin against the reference, takes
  * over for one step.  The G lanes then write the batch together (zw_emit).  Groups of one warp synchronise
  * with their own lane masks only, so they progress independently.  G = 32 is one warp per stream. */
 #define ZW_THREADS 128
-#ifndef ZW_MIN_CTAS
-#define ZW_MIN_CTAS 8
-#endif
-#ifndef ZS_INFLATE_G_WIDE
-#define ZS_INFLATE_G_WIDE 16                     /* lanes per stream in batches beyond 2 * ZS_INFLATE_WARP_MAX streams */
-#endif
 
 struct ZwLut { uint32_t len[32]; uint32_t dist[32]; };     /* base | extra bits << 16 (RFC 1951 3.2.5) */
 
-#ifndef ZW_X_SHARED
-#define ZW_X_SHARED 1                            /* sorted symbols (long codes) in shared memory rather than global */
-#endif
-#ifndef ZW_OWN_BATCH
-#define ZW_OWN_BATCH 0
-#endif
 template <int G> struct ZwStream {
     zi_tables T;
-#if ZW_X_SHARED
     zi_aux X;
-#endif
     uint32_t q[G];
 };
 
@@ -67,20 +52,21 @@ __device__ __forceinline__ void zw_emit(uint8_t *out, uint32_t base, const uint3
     const uint32_t dist = (r & 0x7FFFu) + 1u;
     const bool own = is_match && dist >= pos + olen && olen <= 32u;
     if (own) {
-        /* the source ends before this batch begins, so no load depends on a store: eight loads in flight */
         uint8_t *dst = out + base + pos;
         const uint8_t *src = dst - dist;
-#if !ZW_OWN_BATCH
-        for (uint32_t k = 0; k < olen; k++) dst[k] = src[k];
-#else
-        for (uint32_t k0 = 0; k0 < olen; k0 += 8) {
-            uint8_t t[8];
-#pragma unroll
-            for (uint32_t k = 0; k < 8; k++) if (k0 + k < olen) t[k] = src[k0 + k];
-#pragma unroll
-            for (uint32_t k = 0; k < 8; k++) if (k0 + k < olen) dst[k0 + k] = t[k];
+        /* the source ends before this batch begins, so no load depends on a store of the copy: the three bytes every
+           match has go in one round trip, the rest four at a time (byte after byte the loop was one L2 round trip
+           per byte and held a quarter of the kernel's stall samples) */
+        {
+            const uint8_t b0 = src[0], b1 = src[1], b2 = src[2];
+            dst[0] = b0; dst[1] = b1; dst[2] = b2;
         }
-#endif
+        uint32_t k = 3;
+        for (; k + 4 <= olen; k += 4) {
+            const uint8_t b0 = src[k], b1 = src[k + 1], b2 = src[k + 2], b3 = src[k + 3];
+            dst[k] = b0; dst[k + 1] = b1; dst[k + 2] = b2; dst[k + 3] = b3;
+        }
+        for (; k < olen; k++) dst[k] = src[k];
     }
     uint32_t mm = __ballot_sync(gmask, is_match && !own) >> gshift;
     __syncwarp(gmask);
@@ -110,12 +96,11 @@ __device__ __forceinline__ void zw_emit(uint8_t *out, uint32_t base, const uint3
 }
 
 template <int G>
-__global__ void __launch_bounds__(ZW_THREADS, ZW_MIN_CTAS)
+__global__ void __launch_bounds__(ZW_THREADS, 8)
 zs_inflate_group_kernel(uint32_t n, const ZsStream *__restrict__ streams, const uint8_t *__restrict__ comp,
                         uint8_t *__restrict__ raw, int32_t wrap, int32_t *__restrict__ ret,
                         uint32_t *__restrict__ produced, uint32_t *__restrict__ consumed,
-                        uint32_t *__restrict__ aux /* [2n]: stored check, flags */,
-                        zi_aux *__restrict__ xaux /* [n]: sorted symbols of the stream's current block (long codes only) */)
+                        uint32_t *__restrict__ aux /* [2n]: stored check, flags */)
 {
     constexpr int GROUPS = ZW_THREADS / G;
     extern __shared__ __align__(16) unsigned char zw_smem_raw[];
@@ -144,11 +129,7 @@ zs_inflate_group_kernel(uint32_t n, const ZsStream *__restrict__ streams, const 
        if the batch's wrap has one, still follows its final block) */
     const uint32_t sopt = st.chunk_first;
     zi_mach m;
-    #if ZW_X_SHARED
     zi_m_init(&m, in, st.comp_cap, out, st.raw_len, wrap, &w.T, &w.X);
-#else
-    zi_m_init(&m, in, st.comp_cap, out, st.raw_len, wrap, &w.T, &xaux[s]);
-#endif
     m.opts = sopt & 3u;
     if ((sopt & 4u) && m.state == ZM_HEAD) m.state = ZM_BLOCK;
     const bool count_only = (sopt & ZI_OPT_COUNT_ONLY) != 0;
@@ -195,13 +176,13 @@ zs_inflate_group_kernel(uint32_t n, const ZsStream *__restrict__ streams, const 
 
 template <int G>
 static cudaError_t zs_inflate_group_launch(cudaStream_t st, uint32_t n, const ZsStream *streams, const uint8_t *comp, uint8_t *raw, int32_t wrap,
-                                           int32_t *ret, uint32_t *produced, uint32_t *consumed, uint32_t *aux, zi_aux *xaux)
+                                           int32_t *ret, uint32_t *produced, uint32_t *consumed, uint32_t *aux)
 {
     constexpr int GROUPS = ZW_THREADS / G;
     const size_t smem = sizeof(ZwStream<G>) * GROUPS + sizeof(ZwLut);
     cudaFuncSetAttribute(zs_inflate_group_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncSetAttribute(zs_inflate_group_kernel<G>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
-    zs_inflate_group_kernel<G><<<(n + GROUPS - 1) / GROUPS, ZW_THREADS, smem, st>>>(n, streams, comp, raw, wrap, ret, produced, consumed, aux, xaux);
+    zs_inflate_group_kernel<G><<<(n + GROUPS - 1) / GROUPS, ZW_THREADS, smem, st>>>(n, streams, comp, raw, wrap, ret, produced, consumed, aux);
     return cudaGetLastError();
 }
 
@@ -224,23 +205,15 @@ extern "C" cudaError_t zs_adler_streams_launch(cudaStream_t st, uint32_t n, uint
 extern "C" cudaError_t zs_inflate_launch(cudaStream_t st, uint32_t n, const ZsStream *streams, const uint8_t *comp,
                                          uint8_t *raw, int32_t wrap, int32_t *ret, uint32_t *produced,
                                          uint32_t *consumed, uint32_t *check, uint32_t *aux, ZsAdlerAcc *acc,
-                                         uint32_t max_raw_len, int with_check, void *xaux_v)
+                                         uint32_t max_raw_len, int with_check)
 {
     if (n == 0) return cudaSuccess;
-    zi_aux *xaux = static_cast<zi_aux *>(xaux_v);
-    /* a warp per stream while that fills the machine (148 SMs x 32 warps); wider batches put more streams
-       into a warp: every stream's leader lane decodes at the same time, so the decode cost per symbol falls
-       with the group size while the write cost per warp stays what it is */
-    const char *fv = getenv("ZSC_B200_INFLATE_G");               /* tuning aid: force the group size */
-    const int forced = fv ? atoi(fv) : 0;
-    const int G = forced ? forced : n <= ZS_INFLATE_WARP_MAX ? 32 : n <= 2 * ZS_INFLATE_WARP_MAX ? 16 : ZS_INFLATE_G_WIDE;
-    cudaError_t ge;
-    switch (G) {
-    case 32: ge = zs_inflate_group_launch<32>(st, n, streams, comp, raw, wrap, ret, produced, consumed, aux, xaux); break;
-    case 16: ge = zs_inflate_group_launch<16>(st, n, streams, comp, raw, wrap, ret, produced, consumed, aux, xaux); break;
-    case 8: ge = zs_inflate_group_launch<8>(st, n, streams, comp, raw, wrap, ret, produced, consumed, aux, xaux); break;
-    default: ge = zs_inflate_group_launch<4>(st, n, streams, comp, raw, wrap, ret, produced, consumed, aux, xaux); break;
-    }
+    /* a warp per stream while that fills the machine (148 SMs x 32 warps), two streams per warp beyond: both
+       leaders of a warp decode at the same time, the decode cost per symbol halves.  Smaller groups measured
+       slower (8 lanes: 40 GB/s, 4 lanes: 25 GB/s against 54 GB/s at 65 536 streams): shared memory holds 64 streams per
+       SM whatever the group size, so fewer lanes per stream only mean fewer warps to hide latency with. */
+    cudaError_t ge = n <= ZS_INFLATE_WARP_MAX ? zs_inflate_group_launch<32>(st, n, streams, comp, raw, wrap, ret, produced, consumed, aux)
+                                              : zs_inflate_group_launch<16>(st, n, streams, comp, raw, wrap, ret, produced, consumed, aux);
     if (ge != cudaSuccess) return ge;
     if (!with_check) return cudaSuccess;               /* section passes: the caller checks the whole stream */
     cudaMemsetAsync(acc, 0, sizeof(ZsAdlerAcc) * n, st);
@@ -250,4 +223,3 @@ extern "C" cudaError_t zs_inflate_launch(cudaStream_t st, uint32_t n, const ZsSt
     return cudaGetLastError();
 }
 
-extern "C" size_t zs_inflate_aux_bytes(void) { return sizeof(zi_aux); }
