@@ -114,6 +114,24 @@ def test_argument_errors_are_reported_before_any_gpu_work():
     assert L.adler32_z(0, None, 0) == 1 and L.crc32_z(0, None, 0) == 0                 # src/adler32.c:82-84, src/crc32.c:507
 
 
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the reference's own zsc_compress2 on the host cores, oracle/_ref): one JSON line
+    with the metric of the GPU arm, impl = reference, a cpu_baseline describing the run and an e2e equal to the value."""
+    import subprocess
+    import sys
+    if not refimpl.have_ref():
+        pytest.skip("oracle/_ref not present")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "deflate_level1_input_GBps" and line["unit"] == "GB/s"
+    assert line["value"] > 0 and line["higher_is_better"] is True and line["vs_baseline"] is None and line["dtype"] == "u8"
+    assert line["cpu_baseline"]["kind"] == "reference" and line["cpu_baseline"]["cores"] >= 1 and line["cpu_baseline"]["value"] == line["value"]
+    assert line["e2e"] == {"value": line["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in line["config"] and 2.0 < line["ratio"] < 2.6
+
+
 DEATH_CASES = [
     ("zsc_compress", "source", "L.zsc_compress(buf, C.byref(n), None, 100, 100, work, 400000, 6)"),
     ("zsc_compress", "dest", "L.zsc_compress(None, C.byref(n), buf, 100, 100, work, 400000, 6)"),
