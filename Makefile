@@ -10,7 +10,7 @@ ARCH = -gencode arch=compute_100a,code=sm_100a
 NVFLAGS = $(ARCH) -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Iinclude -Izsc_b200/csrc/cuda $(EXTRA_NVFLAGS)
 CFLAGS = -std=gnu11 -O2 -fPIC -Wall -Wextra -Iinclude
 
-CU = deflate_lz deflate_huff checksum inflate engine
+CU = deflate_lz deflate_chain deflate_huff checksum inflate engine
 CU_OBJS = $(foreach f,$(CU),build/$(f).o)
 LIB = zsc_b200/libzsc_b200.so
 
@@ -19,7 +19,7 @@ all: $(LIB) testlibs
 build:
 	mkdir -p build
 
-build/%.o: zsc_b200/csrc/cuda/%.cu zsc_b200/csrc/cuda/common.cuh zsc_b200/csrc/cuda/huff_build.h zsc_b200/csrc/cuda/inflate_core.h include/zscgpu.h | build
+build/%.o: zsc_b200/csrc/cuda/%.cu zsc_b200/csrc/cuda/common.cuh zsc_b200/csrc/cuda/lz_common.cuh zsc_b200/csrc/cuda/huff_build.h zsc_b200/csrc/cuda/inflate_core.h include/zscgpu.h | build
 	$(NVCC) $(NVFLAGS) -c $< -o $@
 
 build/zsc_api.o: zsc_b200/csrc/host/zsc_api.c include/zsc/zsc_pub.h include/zscgpu.h | build

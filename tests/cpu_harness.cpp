@@ -33,15 +33,11 @@ int h_inflate_batched(const uint8_t *in, uint32_t in_len, uint8_t *out, uint32_t
 }
 
 // ---------------------------------------------------------------- LZ77 model (mirrors deflate_lz.cu)
-struct LzP { int mode, chain, nice, lazy, min_len, max_dist; };
+struct LzP { int mode, chain, nice, lazy, min_len, max_dist, good, max_lazy; };
 static const uint32_t TILE = 2048, WINDOW = 32768, NOHASH = 0xFFFF;
-static int g_near = 1;   /* lanes looked at below the current one (deflate_lz.cu looks at the previous lane only) */
-extern "C" void h_set_near(int n) { g_near = n; }
 static int g_hash_bits = 15;
 static uint64_t g_chain_steps = 0;   /* candidates visited beyond the first (a proxy for the chain kernel's work) */
 extern "C" uint64_t h_chain_steps(void) { uint64_t v = g_chain_steps; g_chain_steps = 0; return v; }
-static int g_skip_override = -1;     /* experiments: force the covering threshold */
-extern "C" void h_set_skip(int v) { g_skip_override = v; }   /* 14 for the single-candidate kernel, 15 for the chain kernel (deflate_lz.cu ZlK) */
 
 static inline uint32_t ld32(const uint8_t *p, uint32_t q, uint32_t q_end)
 {
@@ -60,8 +56,8 @@ static void lz_chunk(const uint8_t *data, uint32_t a, uint32_t dict_len, uint32_
                      std::vector<uint32_t> &blk_start, uint32_t block_syms)
 {
     const uint32_t q_dict = a, q_start = a + dict_len, q_end = q_start + len;
-    g_hash_bits = (P.mode == 0 && P.chain > 0) ? 15 : 14;
-    std::vector<uint16_t> head(32768, 0), prevd(WINDOW, 0);
+    g_hash_bits = 14;
+    std::vector<uint16_t> head(32768, 0);
     std::vector<uint16_t> t_dist(TILE), t_len(TILE + 32, 0);
     uint32_t carry = q_start;
     const uint32_t t_first = P.mode == 0 ? 0 : (q_start / TILE) * TILE;
@@ -81,7 +77,7 @@ static void lz_chunk(const uint8_t *data, uint32_t a, uint32_t dict_len, uint32_
                     /* candidates come from the table as it stood before this group of 32 positions,
                        unless one of the ZL_NEAR preceding lanes has the same hash */
                     d[l] = (q - head[h[l]]) & 0xFFFF;
-                    for (int j = 1; j <= g_near && j <= (int)l; j++) if (h[l - j] == h[l]) { d[l] = (uint32_t)j; break; }
+                    if (l > 0 && h[l - 1] == h[l]) d[l] = 1;
                 }
                 for (uint32_t l = 0; l < 32; l++) {
                     uint32_t q = t0 + g * 32 + l;
@@ -91,68 +87,25 @@ static void lz_chunk(const uint8_t *data, uint32_t a, uint32_t dict_len, uint32_
                     bool below = false;
                     for (uint32_t j = 0; j < l; j++) if (h[j] == h[l]) below = true;
                     if (!below) head[h[l]] = (uint16_t)q;
-                    prevd[q & (WINDOW - 1)] = (uint16_t)d[l];
                 }
             }
         }
         if (t0 + TILE <= q_start) continue;
-        const uint32_t skip = (P.mode == 0 && P.chain > 0) ? (g_skip_override >= 0 ? (uint32_t)g_skip_override : zs_skip_len(P.chain)) : 0;
-        for (uint32_t g0 = 0; g0 < TILE; g0 += 32) {
-            /* a group of 32 positions, as a warp of the kernel sees it: first candidates, the covering rule, chains */
-            uint32_t best[32], bestd[32], maxl[32], maxd[32], dcur[32];
-            bool go[32];
-            for (uint32_t l = 0; l < 32; l++) {
-                const uint32_t i = g0 + l, q = t0 + i;
-                best[l] = bestd[l] = maxl[l] = maxd[l] = dcur[l] = 0; go[l] = false;
-                if (P.mode == 2 || !(q >= q_start && q + 3 <= q_end)) continue;
-                maxl[l] = q_end - q < 258 ? q_end - q : 258;
-                maxd[l] = q - q_dict < (uint32_t)P.max_dist ? q - q_dict : (uint32_t)P.max_dist;
-                auto mlen = [&](uint32_t dd) { uint32_t n = 0; while (n < maxl[l] && data[q + n] == data[q + n - dd]) n++; return n; };
-                if (P.mode == 1) { if (maxd[l] >= 1) { best[l] = mlen(1); bestd[l] = 1; } continue; }
-                dcur[l] = t_dist[i];
-                if (dcur[l] != 0 && dcur[l] <= maxd[l]) {
-                    const uint32_t n = mlen(dcur[l]);
-                    go[l] = true;
-                    if (n > 0) { best[l] = n; bestd[l] = dcur[l]; if (n >= (uint32_t)P.nice || n >= maxl[l]) go[l] = false; }
+        for (uint32_t i = 0; i < TILE; i++) {
+            const uint32_t q = t0 + i;
+            uint32_t best = 0, bestd = 0;
+            if (P.mode != 2 && q >= q_start && q + 3 <= q_end) {
+                const uint32_t maxl = q_end - q < 258 ? q_end - q : 258;
+                const uint32_t maxd = q - q_dict < (uint32_t)P.max_dist ? q - q_dict : (uint32_t)P.max_dist;
+                auto mlen = [&](uint32_t dd) { uint32_t n = 0; while (n < maxl && data[q + n] == data[q + n - dd]) n++; return n; };
+                if (P.mode == 1) { if (maxd >= 1) { best = mlen(1); bestd = 1; } }
+                else {
+                    const uint32_t d = t_dist[i];
+                    if (d != 0 && d <= maxd) { best = mlen(d); bestd = d; }
                 }
             }
-            if (skip) {
-                uint32_t first_len[32], first_d[32];
-                for (uint32_t l = 0; l < 32; l++) { first_len[l] = best[l]; first_d[l] = bestd[l]; }
-                for (uint32_t u = 0; u < 32;) {
-                    const uint32_t Lu = first_len[u];
-                    if (Lu < skip) { u++; continue; }
-                    for (uint32_t l = u + 2; l < u + Lu && l < 32; l++) {
-                        if (maxl[l] == 0) continue;
-                        go[l] = false;
-                        const uint32_t pl = Lu - (l - u);
-                        if (pl > best[l]) { best[l] = pl; bestd[l] = first_d[u]; }
-                    }
-                    u += Lu;
-                }
-            }
-            for (uint32_t l = 0; l < 32; l++) {
-                const uint32_t i = g0 + l, q = t0 + i;
-                auto mlen = [&](uint32_t dd) { uint32_t n = 0; while (n < maxl[l] && data[q + n] == data[q + n - dd]) n++; return n; };
-                int budget = P.chain;
-                uint32_t d = dcur[l];
-                while (go[l]) {
-                    if (P.chain == 0 || budget-- <= 0) break;
-                    uint32_t c = q - d;
-                    if (c + WINDOW < t0 + 2 * TILE) break;     /* the hasher runs one tile ahead */
-                    uint32_t step = prevd[c & (WINDOW - 1)];
-                    if (step == 0) break;
-                    d += step;
-                    g_chain_steps++;
-                    if (d > maxd[l]) break;
-                    if (best[l] < 3 || data[q + best[l]] == data[q + best[l] - d]) {
-                        uint32_t n = mlen(d);
-                        if (n > best[l]) { best[l] = n; bestd[l] = d; if (n >= (uint32_t)P.nice || n >= maxl[l]) break; }
-                    }
-                }
-                if (best[l] < (uint32_t)P.min_len || (best[l] == 3 && bestd[l] > 4096)) { best[l] = 0; bestd[l] = 0; }
-                t_len[i] = (uint16_t)best[l]; t_dist[i] = (uint16_t)bestd[l];
-            }
+            if (best < (uint32_t)P.min_len || (best == 3 && bestd > 4096)) { best = 0; bestd = 0; }
+            t_len[i] = (uint16_t)best; t_dist[i] = (uint16_t)bestd;
         }
         // parse: next(p) walk from carry
         uint32_t s = carry - t0;
@@ -161,6 +114,137 @@ static void lz_chunk(const uint8_t *data, uint32_t a, uint32_t dict_len, uint32_
             bool take = L >= 3;
             if (take && P.lazy && t_len[s + 1] > L) take = false;
             uint32_t q = t0 + s;
+            if (q >= q_start && q < q_end) {
+                if ((sym.size() % block_syms) == 0) blk_start.push_back(q - q_start);
+                sym.push_back(take ? zs_match(L, t_dist[s]) : data[q]);
+            }
+            s += take ? L : 1;
+        }
+        carry = t0 + s;
+    }
+}
+
+
+// ---------------------------------------------------------------- chain search model (mirrors deflate_chain.cu, levels 2..9)
+// Tiles of ZC_TILE positions.  Hash pass: per group of 32 positions, a position's first candidate is the nearest lower
+// lane of the group with the same hash, else the head-table entry as it stood before the group; the highest lane of
+// each hash then holds the slot, so every occurrence stays reachable through the links.  The links of a tile are
+// published when the tile is searched, so a walk from the tile may follow links of positions >= t0 + ZC_TILE - 32768.
+// Search: every position compares its first candidate; then ZC_ROUNDS rounds of { parse the tile with the lengths
+// known so far; positions the parse visits, and the positions right behind the matches it takes (the lazy-evaluation
+// candidates), walk their chains a bounded number of steps further }, the last round to the end of the budget.
+static void lz_chunk_chain(const uint8_t *data, uint32_t a, uint32_t dict_len, uint32_t len, const LzP &P, std::vector<uint32_t> &sym,
+                           std::vector<uint32_t> &blk_start, uint32_t block_syms)
+{
+    const uint32_t CT = ZC_TILE;
+    const uint32_t q_dict = a, q_start = a + dict_len, q_end = q_start + len;
+    g_hash_bits = 14;
+    std::vector<uint16_t> head(32768, 0), prevd(WINDOW, 0), t_cand(CT), t_len(CT + 32, 0), t_dist(CT);
+    std::vector<uint32_t> best(CT), bestd(CT), cur(CT);
+    std::vector<int> budget(CT);
+    std::vector<uint8_t> cut(CT), mark(CT + 1);
+    uint32_t carry = q_start;
+    if (len == 0) blk_start.push_back(0);
+    for (uint32_t t0 = 0; t0 < q_end; t0 += CT) {
+        for (uint32_t g = 0; g < CT / 32; g++) {
+            uint32_t h[32], d[32];
+            for (uint32_t l = 0; l < 32; l++) {
+                const uint32_t q = t0 + g * 32 + l;
+                h[l] = (q >= q_dict && q + 3 <= q_end) ? hash3(ld32(data, q, q_end)) : NOHASH;
+            }
+            for (uint32_t l = 0; l < 32; l++) {
+                const uint32_t q = t0 + g * 32 + l;
+                d[l] = 0;
+                if (h[l] == NOHASH) continue;
+                d[l] = (q - head[h[l]]) & 0xFFFF;
+                for (int j = (int)l - 1; j >= 0; j--) if (h[j] == h[l]) { d[l] = l - (uint32_t)j; break; }
+            }
+            for (uint32_t l = 0; l < 32; l++) {
+                const uint32_t q = t0 + g * 32 + l;
+                t_cand[g * 32 + l] = (uint16_t)d[l];
+                if (h[l] == NOHASH) continue;
+                bool last = true;
+                for (uint32_t j = l + 1; j < 32; j++) if (h[j] == h[l]) last = false;
+                if (last) head[h[l]] = (uint16_t)q;
+                prevd[q & (WINDOW - 1)] = (uint16_t)d[l];
+            }
+        }
+        if (t0 + CT <= q_start) continue;
+        auto MAXL = [&](uint32_t q) { return q_end - q < 258 ? q_end - q : 258u; };
+        auto MAXD = [&](uint32_t q) { return q - q_dict < (uint32_t)P.max_dist ? q - q_dict : (uint32_t)P.max_dist; };
+        auto mlen = [&](uint32_t q, uint32_t dd, uint32_t ml) { uint32_t n = 0; while (n < ml && data[q + n] == data[q + n - dd]) n++; return n; };
+        auto walk = [&](uint32_t i, int steps) {
+            const uint32_t q = t0 + i, ml = MAXL(q), md = MAXD(q);
+            uint32_t d = cur[i];
+            while (d != 0 && steps-- > 0 && budget[i] > 0) {
+                const uint32_t c = q - d;
+                if (c + WINDOW < t0 + CT) { d = 0; break; }             /* its link has been recycled */
+                const uint32_t step = prevd[c & (WINDOW - 1)];
+                if (step == 0) { d = 0; break; }
+                d += step;
+                g_chain_steps++;
+                if (d > md) { d = 0; break; }
+                budget[i]--;
+                const uint32_t eff = best[i] < 2 ? 2 : best[i];
+                if (data[q + eff] == data[q + eff - d] && data[q + eff - 1] == data[q + eff - 1 - d]) {
+                    const uint32_t n = mlen(q, d, ml);
+                    if (n > best[i]) { best[i] = n; bestd[i] = d; if (n >= (uint32_t)P.nice || n >= ml) { d = 0; break; } }
+                }
+            }
+            if (budget[i] <= 0) d = 0;
+            cur[i] = d;
+        };
+        for (uint32_t i = 0; i < CT; i++) {
+            const uint32_t q = t0 + i;
+            best[i] = bestd[i] = cur[i] = 0; budget[i] = P.chain; cut[i] = 0;
+            if (!(q >= q_start && q + 3 <= q_end)) continue;
+            const uint32_t ml = MAXL(q), md = MAXD(q), d = t_cand[i];
+            if (d != 0 && d <= md) {
+                const uint32_t n = mlen(q, d, ml);
+                cur[i] = d;
+                if (n > 0) { best[i] = n; bestd[i] = d; if (n >= (uint32_t)P.nice || n >= ml) cur[i] = 0; }
+            }
+        }
+        auto filt = [&]() {
+            for (uint32_t i = 0; i < CT; i++) {
+                uint32_t b = best[i], bd = bestd[i];
+                if (b < (uint32_t)P.min_len || (b == 3 && bd > 4096)) { b = 0; bd = 0; }
+                t_len[i] = (uint16_t)b; t_dist[i] = (uint16_t)bd;
+            }
+        };
+        for (int r = 0; r < ZC_ROUNDS; r++) {
+            filt();
+            for (uint32_t i = 0; i <= CT; i++) mark[i] = 0;
+            uint32_t s = carry - t0;
+            while (s < CT) {
+                const uint32_t L = t_len[s];
+                bool take = L >= 3;
+                if (take && P.lazy && t_len[s + 1] > L) take = false;
+                mark[s] = take ? 2 : 1;
+                s += take ? L : 1;
+            }
+            uint32_t nwalk = 0;
+            for (uint32_t i = 0; i < CT; i++) {
+                if (cur[i] == 0) continue;
+                bool need = mark[i] != 0;
+                if (i > 0 && mark[i - 1]) {
+                    const uint32_t Lp = t_len[i - 1];
+                    if (mark[i - 1] == 2 && P.lazy && Lp < (uint32_t)P.max_lazy) need = true;
+                    if (need && Lp >= (uint32_t)P.good && !cut[i]) { budget[i] >>= 2; cut[i] = 1; }   /* "good enough" before it: a quarter of the budget */
+                }
+                if (!need) continue;
+                nwalk++;
+                walk(i, zc_round_cap(r));
+            }
+            if (nwalk == 0) break;
+        }
+        filt();
+        uint32_t s = carry - t0;
+        while (s < CT) {
+            const uint32_t L = t_len[s];
+            bool take = L >= 3;
+            if (take && P.lazy && t_len[s + 1] > L) take = false;
+            const uint32_t q = t0 + s;
             if (q >= q_start && q < q_end) {
                 if ((sym.size() % block_syms) == 0) blk_start.push_back(q - q_start);
                 sym.push_back(take ? zs_match(L, t_dist[s]) : data[q]);
@@ -233,11 +317,11 @@ static uint32_t adler32_ref(const uint8_t *p, uint64_t n)
 }
 
 // Full model of one zscgpu deflate stream.  Returns compressed size (or 0 if cap too small).
-// params: [mode, chain, nice, lazy, min_len, max_dist, force_type, wrap, zhdr]
+// params: [mode, chain, nice, lazy, min_len, max_dist, force_type, wrap, zhdr, good, max_lazy]
 uint32_t h_deflate_model(const uint8_t *src, uint32_t n, uint32_t max_block_len, const int32_t *params,
                          uint8_t *out, uint32_t cap, uint32_t *sym_out, uint32_t sym_cap, uint32_t *nsym_out)
 {
-    LzP P{params[0], params[1], params[2], params[3], params[4], params[5]};
+    LzP P{params[0], params[1], params[2], params[3], params[4], params[5], params[9], params[10]};
     const int force = params[6], wrap = params[7];
     const uint32_t zhdr = (uint32_t)params[8];
     const uint32_t BS = getenv("ZS_TEST_BS") ? (uint32_t)atoi(getenv("ZS_TEST_BS")) : 8192, CHUNK = 262144;
@@ -255,7 +339,8 @@ uint32_t h_deflate_model(const uint8_t *src, uint32_t n, uint32_t max_block_len,
             uint32_t cstart = pos + coff;
             uint32_t a = (cstart - dict) & 15;
             std::vector<uint32_t> sym, bstart;
-            lz_chunk(src + (cstart - dict) - a, a, dict, clen, P, sym, bstart, BS);
+            if (P.mode == 0 && P.chain > 0) lz_chunk_chain(src + (cstart - dict) - a, a, dict, clen, P, sym, bstart, BS);
+            else lz_chunk(src + (cstart - dict) - a, a, dict, clen, P, sym, bstart, BS);
             uint32_t nblk = (uint32_t)((sym.size() + BS - 1) / BS);
             if (nblk == 0) nblk = 1;
             std::vector<zh_block> blks(nblk);

@@ -34,6 +34,24 @@ def ref():
     return _ref
 
 
+def ref_uncompress_batch(comp, comp_off, comp_len, raw_len, threads=None):
+    """zsc_uncompress of n independent streams packed in `comp`, by the reference itself, one pthread per core
+    (oracle/ref_probe.c:refprobe_batch).  Returns (rets, produced, out) with stream i at out[sum(raw_len[:i]):]."""
+    L = ref().L
+    n = len(comp_off)
+    u64p, i32p = C.POINTER(C.c_uint64), C.POINTER(C.c_int32)
+    L.refprobe_batch.argtypes = [C.c_int, C.c_int, C.c_uint32, C.c_void_p, u64p, u32p, C.c_void_p, u64p, u32p, u32p, i32p,
+                                 C.c_uint32, C.c_int32, C.c_int32]
+    comp = np.ascontiguousarray(comp, dtype=np.uint8)
+    roff = np.concatenate([[0], np.cumsum(np.asarray(raw_len, dtype=np.uint64))]).astype(np.uint64)
+    out = np.empty(int(roff[-1]) + 16, dtype=np.uint8)
+    so = (C.c_uint64 * n)(*[int(v) for v in comp_off]); sl = (C.c_uint32 * n)(*[int(v) for v in comp_len])
+    do = (C.c_uint64 * n)(*[int(v) for v in roff[:-1]]); dc = (C.c_uint32 * n)(*[int(v) for v in raw_len])
+    dl = (C.c_uint32 * n)(); rt = (C.c_int32 * n)()
+    L.refprobe_batch(1, threads or (os.cpu_count() or 4), n, comp.ctypes.data, so, sl, out.ctypes.data, do, dc, dl, rt, 0, 0, 0)
+    return list(rt), list(dl), out[:int(roff[-1])]
+
+
 _ora = None
 
 
@@ -82,16 +100,20 @@ def h_inflate(comp, cap, wrap=1):
                                           stored_check=res[5], have_check=res[6])
 
 
-# level -> [mode, chain, nice, lazy, min_len, max_dist, force_type, wrap, zhdr]; must mirror zs_lz_params (engine.cu)
+# level -> [mode, chain, nice, lazy, min_len, max_dist, force_type, wrap, zhdr, good, max_lazy]; must mirror zs_lz_params (engine.cu)
 FAST_MAX_DIST = 32768 - 3 * 2048 - 272
+#            level:  0    1    2    3    4    5    6    7    8     9
+CHAIN_TAB = [0, 0, 1, 3, 48, 192, 256, 384, 768, 1536]
+NICE_TAB = [0, 258, 258, 258, 16, 32, 128, 128, 258, 258]
+GOOD_TAB = [0, 258, 258, 258, 4, 8, 8, 8, 32, 32]
+MAX_LAZY_TAB = [0, 258, 258, 258, 4, 16, 16, 32, 128, 258]
 
 
 def lz_params(level, strategy=0, wrap=1, wbits=15):
     if level == -1:
         level = 6
-    chain = [0, 0, 1, 3, 7, 15, 127, 255, 1023, 4095][level]
-    nice = [0, 258, 258, 258, 32, 64, 128, 128, 258, 258][level]
-    lazy = [0, 0, 1, 1, 1, 1, 1, 1, 1, 1][level]
+    chain, nice, good, max_lazy = CHAIN_TAB[level], NICE_TAB[level], GOOD_TAB[level], MAX_LAZY_TAB[level]
+    lazy = 0 if level < 2 else 1
     mode, min_len, force = 0, 3, -1
     if strategy == 2:
         mode = 2
@@ -110,7 +132,7 @@ def lz_params(level, strategy=0, wrap=1, wbits=15):
     max_dist = 1 << wbits
     if not (mode == 0 and chain > 0):
         max_dist = min(max_dist, FAST_MAX_DIST)     # single-candidate kernel: 32 KiB ring (deflate_lz.cu ZL_FAST_MAX_DIST)
-    return [mode, chain, nice, lazy, min_len, max_dist, force, wrap, zhdr]
+    return [mode, chain, nice, lazy, min_len, max_dist, force, wrap, zhdr, good, max_lazy]
 
 
 def model_deflate(src, max_block_len, level, strategy=0, wrap=1, wbits=15):
@@ -123,7 +145,7 @@ def model_deflate(src, max_block_len, level, strategy=0, wrap=1, wbits=15):
     out = np.zeros(cap, dtype=np.uint8)
     syms = np.zeros(max(n, 1), dtype=np.uint32)
     nsym = C.c_uint32(0)
-    p = (C.c_int32 * 9)(*lz_params(level, strategy, wrap, wbits))
+    p = (C.c_int32 * 11)(*lz_params(level, strategy, wrap, wbits))
     sz = harness().h_deflate_model(padded.ctypes.data_as(u8p), n, max_block_len, p, out.ctypes.data_as(u8p), cap,
                                    syms.ctypes.data_as(u32p), len(syms), C.byref(nsym))
     return out[:sz].copy(), syms[:nsym.value].copy()

@@ -44,7 +44,7 @@ struct ZsStream {
 /* LZ77 search parameters for one batch (derived from level/strategy in engine.cu). */
 struct ZsLzParams {
     int32_t mode;        /* 0 hash search, 1 run-length (distance 1 only), 2 literals only */
-    int32_t chain;       /* candidates tried beyond the first */
+    int32_t chain;       /* candidates tried beyond the first (0: the single-candidate kernel) */
     int32_t nice;        /* stop the search at this match length */
     int32_t lazy;        /* 1: defer a match when the next position has a longer one */
     int32_t min_len;     /* shortest match kept (3; 6 for Z_FILTERED) */
@@ -52,6 +52,8 @@ struct ZsLzParams {
     int32_t wrap;        /* 0 raw, 1 zlib, 2 gzip body */
     int32_t zhdr;        /* the two zlib header bytes, little-endian packed */
     int32_t max_dist;    /* 1 << window_bits */
+    int32_t good;        /* chain kernel: behind a match at least this long a position searches with a quarter of the budget */
+    int32_t max_lazy;    /* chain kernel: behind a taken match at least this long the next position is not searched deeper */
 };
 
 /* Adler-32 accumulators: sum of bytes and position-weighted sum, both already reduced mod 65521. */

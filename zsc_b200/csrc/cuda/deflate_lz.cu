@@ -22,34 +22,25 @@
  * can cost ratio but never correctness.  Every step is deterministic: tests/cpu_harness.cpp holds
  * a scalar model that predicts the symbol stream bit for bit.
  */
-#include "common.cuh"
+#include "lz_common.cuh"
 
-#define ZL_WORKER_WARPS 16
-#define ZL_WORKERS (ZL_WORKER_WARPS * 32)          /* 512 worker threads */
-#define ZL_THREADS (ZL_WORKERS + 32)               /* + the hasher warp */
 #define ZL_TILE 2048
 #define ZL_GROUPS (ZL_TILE / 32)
 #define ZL_GPW (ZL_GROUPS / ZL_WORKER_WARPS)       /* consecutive groups per worker warp (one block) */
 #define ZL_BLOCK (ZL_GPW * 32)                     /* 128 positions */
-/* Two layouts.  The chain kernel (levels 2..9) keeps a 64 KiB ring, a 15-bit head table and the 32 Ki link
- * array: one CTA per SM.  The single-candidate kernel (level 1, Z_RLE, Z_HUFFMAN_ONLY) uses a 32 KiB ring and a
- * 14-bit head table so that two CTAs share an SM (2 x 97 KB of shared memory, 56 registers): the second CTA's
+/* The single-candidate kernel (level 1, Z_RLE, Z_HUFFMAN_ONLY; levels 2..9 are deflate_chain.cu) uses a 32 KiB ring
+ * and a 14-bit head table so that two CTAs share an SM (2 x 97 KB of shared memory, 56 registers): the second CTA's
  * warps fill the issue slots the first leaves empty at its barriers and shared-memory round trips.  A 32 KiB
  * ring holds the three staged tiles plus the window, which bounds match distances to ZL_FAST_MAX_DIST. */
-template <bool CHAIN> struct ZlK {
-    static constexpr uint32_t RING = CHAIN ? 65536u : 32768u;
-    static constexpr uint32_t HASH_BITS = CHAIN ? 15u : 14u;
-};
-#define ZL_MIRROR 32u                               /* bytes of the ring start repeated after its end */
-#define ZL_LOOKAHEAD 272u                          /* >= 258 + 3, multiple of 16 */
+#define ZL_RING 32768u
+#define ZL_HASH_BITS 14u
 #define ZL_FAST_MAX_DIST (32768u - 3u * ZL_TILE - ZL_LOOKAHEAD)   /* 26352: see zs_lz_fast_max_dist() */
 #define ZL_NOHASH 0xFFFFu
 #define ZL_NOTFIRST 0x8000u                      /* t_hash flag: a lower lane of the group has the same hash */
-#define ZL_NONE 0xFFFFu
 
-template <bool CHAIN> struct ZlSmem {
-    uint32_t ring32[ZlK<CHAIN>::RING / 4 + ZL_MIRROR / 4];   /* + a mirror of the first bytes: multi-word reads never wrap */
-    uint16_t head[1u << ZlK<CHAIN>::HASH_BITS];
+struct ZlSmem {
+    uint32_t ring32[ZL_RING / 4 + ZL_MIRROR / 4];   /* + a mirror of the first bytes: multi-word reads never wrap */
+    uint16_t head[1u << ZL_HASH_BITS];
     uint16_t t_hash[2][ZL_TILE];      /* double buffered: written by workers, read by the hasher */
     uint16_t t_cand[2][ZL_TILE];      /* double buffered: written by the hasher, read by workers */
     uint16_t t_dist[ZL_TILE];         /* best distance per position */
@@ -61,103 +52,8 @@ template <bool CHAIN> struct ZlSmem {
     uint32_t g_off[ZL_GROUPS];
     uint32_t carry;                   /* absolute q of the next parse start */
     uint32_t nsym;                    /* symbols emitted so far */
-    uint16_t prevd[CHAIN ? ZS_WINDOW : 2];   /* chain kernel: distance from a position to the previous one with the same hash */
+    unsigned long long stage_bar;     /* mbarrier of the bulk-copy staging (lz_common.cuh) */
 };
-
-__device__ __forceinline__ void zl_bar_workers() { asm volatile("bar.sync 1, %0;" ::"n"(ZL_WORKERS) : "memory"); }
-
-template <uint32_t RING> __device__ __forceinline__ uint32_t zl_ld32(const uint32_t *ring32, uint32_t q)
-{
-    uint32_t i = (q >> 2) & (RING / 4 - 1);
-    uint32_t w0 = ring32[i], w1 = ring32[i + 1];
-    return __funnelshift_r(w0, w1, (q & 3) * 8);
-}
-template <uint32_t RING> __device__ __forceinline__ uint32_t zl_ld8(const uint32_t *ring32, uint32_t q)
-{
-    return ((const uint8_t *)ring32)[q & (RING - 1)];
-}
-template <uint32_t HASH_BITS> __device__ __forceinline__ uint32_t zl_hash(uint32_t v)
-{
-    uint32_t h = ((v & 0xFFFFFFu) * 2654435761u) >> (32 - HASH_BITS);
-    return h == 0x7FFFu ? 0x7FFEu : h;          /* 0x7FFF | ZL_NOTFIRST would collide with ZL_NOHASH */
-}
-
-/* length of the common prefix of the strings at q and q - d, at most maxl */
-template <uint32_t RING> __device__ __forceinline__ uint32_t zl_match_len(const uint32_t *ring32, uint32_t q, uint32_t d, uint32_t maxl)
-{
-    uint32_t l = 0;
-    while (l < maxl) {
-        uint32_t x = zl_ld32<RING>(ring32, q + l) ^ zl_ld32<RING>(ring32, q + l - d);
-        if (x) { l += (uint32_t)(__ffs((int)x) - 1) >> 3; break; }
-        l += 4;
-    }
-    return l < maxl ? l : maxl;
-}
-
-/* common prefix of the strings at q and q - d, looking at 16 bytes only (branch-free: 0..16) */
-template <uint32_t RING> __device__ __forceinline__ uint32_t zl_match16(const uint32_t *ring32, uint32_t q, uint32_t d)
-{
-    const uint32_t qb = q - d;
-    const uint32_t ia = (q >> 2) & (RING / 4 - 1), ib = (qb >> 2) & (RING / 4 - 1);
-    const uint32_t sa = (q & 3) * 8, sb = (qb & 3) * 8;
-    uint32_t a[5], b[5];
-#pragma unroll
-    for (int k = 0; k < 5; k++) { a[k] = ring32[ia + k]; b[k] = ring32[ib + k]; }
-    uint32_t len = 16;
-#pragma unroll
-    for (int k = 3; k >= 0; k--) {
-        const uint32_t x = __funnelshift_r(a[k], a[k + 1], sa) ^ __funnelshift_r(b[k], b[k + 1], sb);
-        if (x) len = 4 * k + ((uint32_t)(__ffs((int)x) - 1) >> 3);
-    }
-    return len;
-}
-
-/* same, eight bytes per step (three aligned words per side, two funnel shifts) */
-template <uint32_t RING> __device__ __forceinline__ uint32_t zl_match_ext(const uint32_t *ring32, uint32_t q, uint32_t d, uint32_t limit)
-{
-    uint32_t l = 0;
-    while (l < limit) {
-        const uint32_t qa = q + l, qb = qa - d;
-        const uint32_t ia = (qa >> 2) & (RING / 4 - 1), ib = (qb >> 2) & (RING / 4 - 1);
-        const uint32_t a0 = ring32[ia], a1 = ring32[ia + 1], a2 = ring32[ia + 2];
-        const uint32_t b0 = ring32[ib], b1 = ring32[ib + 1], b2 = ring32[ib + 2];
-        const uint32_t sa = (qa & 3) * 8, sb = (qb & 3) * 8;
-        const uint32_t x0 = __funnelshift_r(a0, a1, sa) ^ __funnelshift_r(b0, b1, sb);
-        const uint32_t x1 = __funnelshift_r(a1, a2, sa) ^ __funnelshift_r(b1, b2, sb);
-        if (x0) { l += (uint32_t)(__ffs((int)x0) - 1) >> 3; break; }
-        if (x1) { l += 4 + ((uint32_t)(__ffs((int)x1) - 1) >> 3); break; }
-        l += 8;
-    }
-    return l < limit ? l : limit;
-}
-
-/* workers: copy input bytes [from, to) into the ring (16-byte vectors; bytes for the ragged end) */
-template <uint32_t RING> __device__ __forceinline__ uint32_t zl_load(uint32_t *ring32, const uint8_t *gbase, uint32_t loaded, uint32_t need, uint32_t q_end, uint32_t wtid)
-{
-    uint8_t *ring8 = (uint8_t *)ring32;
-    if (need <= loaded) return loaded;
-    uint32_t full_end = need & ~15u;
-    for (uint32_t q = loaded + wtid * 16; q < full_end; q += ZL_WORKERS * 16) {
-        uint4 v = __ldg(reinterpret_cast<const uint4 *>(gbase + q));
-        const uint32_t r = q & (RING - 1);
-        *reinterpret_cast<uint4 *>(&ring8[r]) = v;
-        if (r < ZL_MIRROR) *reinterpret_cast<uint4 *>(&ring8[RING + r]) = v;
-    }
-    uint32_t tail0 = max(loaded, full_end);
-    for (uint32_t q = tail0 + wtid; q < need; q += ZL_WORKERS) {
-        const uint32_t r = q & (RING - 1);
-        const uint8_t v = __ldg(gbase + q);
-        ring8[r] = v;
-        if (r < ZL_MIRROR) ring8[RING + r] = v;
-    }
-    /* zero a few bytes past the very end so 4-byte compares read defined data */
-    if (need == q_end && wtid < 8) {
-        const uint32_t r = (q_end + wtid) & (RING - 1);
-        ring8[r] = 0;
-        if (r < ZL_MIRROR) ring8[RING + r] = 0;
-    }
-    return (need == q_end) ? need : full_end;
-}
 
 /* workers: 3-byte hashes of one tile (positions i, i + 512, ...: a warp covers one group of 32), 15 bits +
  * ZL_NOTFIRST when a lower lane of the group has the same hash.  Finding those duplicates here, on 16 warps
@@ -200,8 +96,7 @@ template <uint32_t RING, uint32_t HASH_BITS> __device__ __forceinline__ void zl_
  * stood before the group; afterwards the lowest lane of every hash holds the slot.  The workers have flagged
  * every other lane ZL_NOTFIRST, so the stores of a group never collide and the walk is a plain in-order
  * stream of shared-memory loads and stores with nothing to wait for. */
-template <bool CHAIN>
-__device__ __forceinline__ void zl_hasher_tile(ZlSmem<CHAIN> &S, uint16_t *prevd, const uint16_t *t_hash, uint16_t *t_cand, uint32_t t0, uint32_t lane)
+__device__ __forceinline__ void zl_hasher_tile(ZlSmem &S, const uint16_t *t_hash, uint16_t *t_cand, uint32_t t0, uint32_t lane)
 {
 #pragma unroll 4
     for (uint32_t g = 0; g < ZL_GROUPS; g++) {
@@ -211,30 +106,19 @@ __device__ __forceinline__ void zl_hasher_tile(ZlSmem<CHAIN> &S, uint16_t *prevd
         const uint32_t hs = valid ? (h16 & 0x7FFFu) : 0;
         const uint32_t old = S.head[hs];                                    /* table as it stood before the group */
         if (valid && !(h16 & ZL_NOTFIRST)) S.head[hs] = (uint16_t)q;        /* the first lane of each hash claims it */
-        if (CHAIN) {
-            const uint32_t hp = __shfl_up_sync(0xFFFFFFFFu, h16, 1);
-            const bool same = valid && lane > 0 && hp != ZL_NOHASH && ((hp ^ h16) & 0x7FFFu) == 0;
-            uint32_t d = same ? 1u : ((q - old) & 0xFFFFu);
-            if (!valid) d = 0;
-            t_cand[i] = (uint16_t)d;
-            if (valid) prevd[q & (ZS_WINDOW - 1)] = (uint16_t)d;
-        } else {
-            t_cand[i] = (uint16_t)old;                                      /* the workers turn it into a distance */
-        }
+        t_cand[i] = (uint16_t)old;                                          /* the workers turn it into a distance */
         __syncwarp();
     }
 }
 
-template <bool CHAIN>
-__global__ void __launch_bounds__(ZL_THREADS, CHAIN ? 1 : 2)
+__global__ void __launch_bounds__(ZL_THREADS, 2)
 zs_lz_kernel(const uint8_t *__restrict__ raw, const ZsChunk *__restrict__ chunks,
              uint32_t *__restrict__ sym, uint32_t *__restrict__ chunk_nsym,
              uint32_t *__restrict__ blk_in_start, ZsLzParams P)
 {
     extern __shared__ __align__(16) unsigned char zl_smem_raw[];
-    ZlSmem<CHAIN> &S = *reinterpret_cast<ZlSmem<CHAIN> *>(zl_smem_raw);
-    uint16_t *prevd = S.prevd;
-    constexpr uint32_t RING = ZlK<CHAIN>::RING, HASH_BITS = ZlK<CHAIN>::HASH_BITS;
+    ZlSmem &S = *reinterpret_cast<ZlSmem *>(zl_smem_raw);
+    constexpr uint32_t RING = ZL_RING, HASH_BITS = ZL_HASH_BITS;
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool is_hasher = (warp == 0);
@@ -244,44 +128,56 @@ zs_lz_kernel(const uint8_t *__restrict__ raw, const ZsChunk *__restrict__ chunks
     const uint32_t a = (uint32_t)(src_addr & 15);
     const uint8_t *gbase = (const uint8_t *)(src_addr - a);       /* q = 0 */
     const uint32_t q_dict = a, q_start = a + cd.dict_len, q_end = q_start + cd.len;
+    const uint32_t q_end16 = (q_end + 15u) & ~15u;                 /* staging moves whole 16-byte pieces (the arenas are padded) */
     uint32_t *out_sym = sym + cd.sym_off;
     const bool hashing = (P.mode == 0);
 
     for (uint32_t i = tid; i < (1u << HASH_BITS) / 2; i += ZL_THREADS) ((uint32_t *)S.head)[i] = 0;
-    if (CHAIN) for (uint32_t i = tid; i < ZS_WINDOW / 2; i += ZL_THREADS) ((uint32_t *)prevd)[i] = 0;
     for (uint32_t i = tid; i < ZL_TILE + 32; i += ZL_THREADS) S.t_len[i] = 0;
-    if (tid == 0) { S.carry = q_start; S.nsym = 0; if (cd.len == 0) blk_in_start[cd.blk_base] = 0; }
+    if (tid == 0) { S.carry = q_start; S.nsym = 0; if (cd.len == 0) blk_in_start[cd.blk_base] = 0; zl_mbar_init(&S.stage_bar, 1); }
+    __syncthreads();
 
     /* tiles are [t_first + k * ZL_TILE, ...); with hashing the dictionary is walked too */
     const uint32_t t_first = hashing ? 0 : (q_start / ZL_TILE) * ZL_TILE;
     const uint32_t ntiles = q_end > t_first ? (q_end - t_first + ZL_TILE - 1) / ZL_TILE : 0;
     uint32_t loaded = hashing ? 0 : ((t_first > ZS_WINDOW ? t_first - ZS_WINDOW : 0) & ~15u);
+    uint32_t stage_phase = 0;                                      /* completed phases of the staging barrier */
 
-    /* ---- prologue: stage tiles 0 and 1, hash them, head-table pass of tile 0 ---- */
-    if (!is_hasher) loaded = zl_load<RING>(S.ring32, gbase, loaded, min(q_end, t_first + 2 * ZL_TILE + ZL_LOOKAHEAD), q_end, wtid);
-    __syncthreads();
+    /* ---- prologue: stage tiles 0 and 1 (bulk copy issued by one thread), hash them, head-table pass of tile 0 ---- */
+    {
+        const uint32_t need = min(q_end16, t_first + 2 * ZL_TILE + ZL_LOOKAHEAD);
+        if (need > loaded) {
+            if (tid == 0) zl_stage_bulk<RING>(S.ring32, gbase, loaded, need, &S.stage_bar);
+            zl_mbar_wait(&S.stage_bar, stage_phase & 1u);
+            stage_phase++;
+            loaded = need;
+        }
+    }
     if (!is_hasher && hashing) {
         zl_hash_tile<RING, HASH_BITS>(S.ring32, S.t_hash[0], S.t_exit, t_first, q_dict, q_end, wtid);
         if (ntiles > 1) zl_hash_tile<RING, HASH_BITS>(S.ring32, S.t_hash[1], S.t_exit, t_first + ZL_TILE, q_dict, q_end, wtid);
     }
     __syncthreads();
-    if (is_hasher && hashing && ntiles > 0) zl_hasher_tile<CHAIN>(S, prevd, S.t_hash[0], S.t_cand[0], t_first, lane);
+    if (is_hasher && hashing && ntiles > 0) zl_hasher_tile(S, S.t_hash[0], S.t_cand[0], t_first, lane);
     __syncthreads();
 
     for (uint32_t k = 0; k < ntiles; k++) {
         const uint32_t t0 = t_first + k * ZL_TILE;
+        /* ---- A: stage tile k+2 (only ring bytes older than the window of tile k are replaced): one thread queues the
+           bulk copies, the workers wait for the bytes right before they hash that tile (phase B) ---- */
+        const uint32_t need = min(q_end16, t0 + 3 * ZL_TILE + ZL_LOOKAHEAD);
+        const bool staging = need > loaded;
         if (is_hasher) {
+            if (staging && lane == 0) zl_stage_bulk<RING>(S.ring32, gbase, loaded, need, &S.stage_bar);
             /* one tile ahead of the workers */
             if (hashing && k + 1 < ntiles)
-                zl_hasher_tile<CHAIN>(S, prevd, S.t_hash[(k + 1) & 1], S.t_cand[(k + 1) & 1], t0 + ZL_TILE, lane);
+                zl_hasher_tile(S, S.t_hash[(k + 1) & 1], S.t_cand[(k + 1) & 1], t0 + ZL_TILE, lane);
         } else {
-            /* ---- A: stage tile k+2 (only ring bytes older than the window of tile k are replaced) ---- */
-            loaded = zl_load<RING>(S.ring32, gbase, loaded, min(q_end, t0 + 3 * ZL_TILE + ZL_LOOKAHEAD), q_end, wtid);
             const bool live = (t0 + ZL_TILE > q_start);           /* not a dictionary-only tile */
             if (live) {
                 /* ---- D: match lengths ---- */
                 const uint16_t *cand = S.t_cand[k & 1];
-                if (P.mode != 2 && !CHAIN) {
+                if (P.mode != 2) {
                     /* One candidate per position.  First every lane compares 16 bytes (no divergence); that
                        settles all short matches.  Lanes that matched all 16 are long matches, and neighbouring
                        long lanes with the same distance are inside the same match: only the first lane of
@@ -322,77 +218,6 @@ zs_lz_kernel(const uint8_t *__restrict__ raw, const ZsChunk *__restrict__ chunks
                         }
                         best = min(best, min(limit, ZS_MAX_MATCH));
                         uint32_t bestd = d;
-                        if (best < (uint32_t)P.min_len || (best == 3 && bestd > ZS_TOO_FAR)) { best = 0; bestd = 0; }
-                        S.t_len[i] = (uint16_t)best;
-                        S.t_dist[i] = (uint16_t)bestd;
-                    }
-                } else if (P.mode != 2) {
-                    /* Hash chains (levels 2..9) or distance-1 runs (Z_RLE).  Every lane first tries its first
-                       candidate.  A serial deflate never searches inside a match it has taken; the position-parallel
-                       form of that rule (levels >= 4, zs_skip_len): going through the 32 lanes in order, a lane
-                       whose first candidate is at least skip bytes long covers the lanes behind it, except the
-                       next one (the lazy-evaluation candidate); covered lanes keep the better of their own first
-                       candidate and the covering match shortened by their offset and do not walk their chain.
-                       On telemetry-like data most positions are covered and the chain walks, which dominate
-                       the kernel, shrink accordingly.  tests/cpu_harness.cpp mirrors the rule exactly. */
-                    const uint32_t skip = (CHAIN && P.mode == 0) ? zs_skip_len(P.chain) : 0u;
-                    for (uint32_t i = wtid; i < ZL_TILE; i += ZL_WORKERS) {
-                        const uint32_t q = t0 + i;
-                        uint32_t best = 0, bestd = 0, maxl = 0, maxd = 0, d = 0;
-                        int budget = P.chain;
-                        bool go = false;
-                        if (q >= q_start && q + 3 <= q_end) {
-                            maxl = min(ZS_MAX_MATCH, q_end - q);
-                            maxd = min((uint32_t)P.max_dist, q - q_dict);
-                            if (P.mode == 1) {
-                                if (maxd >= 1) { best = zl_match_len<RING>(S.ring32, q, 1, maxl); bestd = 1; }
-                            } else {
-                                d = cand[i];
-                                if (d != 0 && d <= maxd) {
-                                    const uint32_t l = zl_match_len<RING>(S.ring32, q, d, maxl);
-                                    go = true;
-                                    if (l > 0) { best = l; bestd = d; if (l >= (uint32_t)P.nice || l >= maxl) go = false; }
-                                }
-                            }
-                        }
-                        if constexpr (CHAIN) if (skip) {
-                            const uint32_t long_m = __ballot_sync(0xFFFFFFFFu, best >= skip);
-                            uint32_t next = 0;
-                            while (next < 32u) {
-                                const uint32_t m2 = long_m & (0xFFFFFFFFu << next);
-                                if (!m2) break;
-                                const uint32_t u = (uint32_t)__ffs((int)m2) - 1u;
-                                const uint32_t Lu = __shfl_sync(0xFFFFFFFFu, best, u), Du = __shfl_sync(0xFFFFFFFFu, bestd, u);
-                                if (lane >= u + 2u && lane < u + Lu && maxl != 0) {
-                                    go = false;
-                                    const uint32_t pl = Lu - (lane - u);
-                                    if (pl > best) { best = pl; bestd = Du; }
-                                }
-                                next = u + Lu;
-                            }
-                        }
-                        /* The walk is a pointer chase through the link array: per candidate one link lookup and one
-                           byte of the ring (cheap reject: the byte that would extend the best match must agree).
-                           Both depend only on the candidate's distance, so the link of the candidate about to be
-                           examined is requested together with its reject byte (a link read too early is simply not
-                           used when the checks below say so); the byte behind the best match is kept in a register. */
-                        uint32_t step_next = go ? (uint32_t)prevd[(q - d) & (ZS_WINDOW - 1)] : 0u;
-                        uint32_t tail = go ? zl_ld8<RING>(S.ring32, q + best) : 0u;
-                        const uint32_t c_min = t0 + 2 * ZL_TILE - ZS_WINDOW;     /* links of positions the hasher may be recycling right now are off limits */
-                        while (go) {
-                            if (!CHAIN || budget-- <= 0) break;
-                            if ((int32_t)(q - d - c_min) < 0) break;
-                            const uint32_t step = step_next;
-                            if (step == 0) break;
-                            d += step;
-                            if (d > maxd) break;
-                            step_next = prevd[(q - d) & (ZS_WINDOW - 1)];
-                            const uint32_t rb = zl_ld8<RING>(S.ring32, q + best - d);
-                            if (best < 3 || rb == tail) {
-                                const uint32_t l = zl_match_len<RING>(S.ring32, q, d, maxl);
-                                if (l > best) { best = l; bestd = d; if (l >= (uint32_t)P.nice || l >= maxl) break; tail = zl_ld8<RING>(S.ring32, q + best); }
-                            }
-                        }
                         if (best < (uint32_t)P.min_len || (best == 3 && bestd > ZS_TOO_FAR)) { best = 0; bestd = 0; }
                         S.t_len[i] = (uint16_t)best;
                         S.t_dist[i] = (uint16_t)bestd;
@@ -488,12 +313,12 @@ zs_lz_kernel(const uint8_t *__restrict__ raw, const ZsChunk *__restrict__ chunks
                         if ((idx & (ZS_BLOCK_SYMS - 1)) == 0) blk_in_start[cd.blk_base + idx / ZS_BLOCK_SYMS] = q - q_start;
                     }
                 }
-            } else {
-                zl_bar_workers();       /* ring bytes staged above must be visible before hashing them */
             }
-            /* ---- B: hashes of tile k+2 (its bytes were staged in A; every path above passed a worker barrier) ---- */
+            /* ---- B: hashes of tile k+2 (its bytes were queued in A; wait until they have landed) ---- */
+            if (staging) zl_mbar_wait(&S.stage_bar, stage_phase & 1u);
             if (hashing && k + 2 < ntiles) zl_hash_tile<RING, HASH_BITS>(S.ring32, S.t_hash[k & 1], S.t_exit, t0 + 2 * ZL_TILE, q_dict, q_end, wtid);
         }
+        if (staging) { stage_phase++; loaded = need; }
         __syncthreads();
     }
     if (tid == 0) chunk_nsym[blockIdx.x] = S.nsym;
@@ -502,24 +327,18 @@ zs_lz_kernel(const uint8_t *__restrict__ raw, const ZsChunk *__restrict__ chunks
 static_assert(ZL_GROUPS == 64, "group-count scan assumes 64 groups per tile");
 static_assert(ZL_GPW * ZL_WORKER_WARPS == ZL_GROUPS, "groups must divide evenly over the worker warps");
 
-extern "C" size_t zs_lz_smem_bytes(int chain) { return chain ? sizeof(ZlSmem<true>) : sizeof(ZlSmem<false>); }
+extern "C" size_t zs_lz_smem_bytes(void) { return sizeof(ZlSmem); }
 /* longest match distance the single-candidate kernel can represent: its ring must hold the window of the tile
  * being searched and the three tiles staged ahead of it */
 extern "C" uint32_t zs_lz_fast_max_dist(void) { return ZL_FAST_MAX_DIST; }
-static_assert(ZL_FAST_MAX_DIST + 3u * ZL_TILE + ZL_LOOKAHEAD <= ZlK<false>::RING, "fast ring too small");
-static_assert(ZS_WINDOW + 3u * ZL_TILE + ZL_LOOKAHEAD <= ZlK<true>::RING, "chain ring too small");
+static_assert(ZL_FAST_MAX_DIST + 3u * ZL_TILE + ZL_LOOKAHEAD <= ZL_RING, "fast ring too small");
 
-extern "C" cudaError_t zs_lz_launch(cudaStream_t st, int chain, uint32_t nchunks, const uint8_t *raw,
+extern "C" cudaError_t zs_lz_launch(cudaStream_t st, uint32_t nchunks, const uint8_t *raw,
                                     const ZsChunk *chunks, uint32_t *sym, uint32_t *chunk_nsym,
                                     uint32_t *blk_in_start, ZsLzParams P)
 {
     if (nchunks == 0) return cudaSuccess;
-    if (chain) {
-        cudaFuncSetAttribute(zs_lz_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ZlSmem<true>));
-        zs_lz_kernel<true><<<nchunks, ZL_THREADS, sizeof(ZlSmem<true>), st>>>(raw, chunks, sym, chunk_nsym, blk_in_start, P);
-    } else {
-        cudaFuncSetAttribute(zs_lz_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ZlSmem<false>));
-        zs_lz_kernel<false><<<nchunks, ZL_THREADS, sizeof(ZlSmem<false>), st>>>(raw, chunks, sym, chunk_nsym, blk_in_start, P);
-    }
+    cudaFuncSetAttribute(zs_lz_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ZlSmem));
+    zs_lz_kernel<<<nchunks, ZL_THREADS, sizeof(ZlSmem), st>>>(raw, chunks, sym, chunk_nsym, blk_in_start, P);
     return cudaGetLastError();
 }

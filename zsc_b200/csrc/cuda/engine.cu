@@ -12,7 +12,8 @@
 #include "zscgpu.h"
 
 /* kernel launchers (deflate_lz.cu, deflate_huff.cu, checksum.cu, inflate.cu) */
-extern "C" cudaError_t zs_lz_launch(cudaStream_t, int, uint32_t, const uint8_t *, const ZsChunk *, uint32_t *, uint32_t *, uint32_t *, ZsLzParams);
+extern "C" cudaError_t zs_lz_launch(cudaStream_t, uint32_t, const uint8_t *, const ZsChunk *, uint32_t *, uint32_t *, uint32_t *, ZsLzParams);
+extern "C" cudaError_t zs_lzc_launch(cudaStream_t, uint32_t, const uint8_t *, const ZsChunk *, uint32_t *, uint32_t *, uint32_t *, ZsLzParams);
 extern "C" uint32_t zs_lz_fast_max_dist(void);
 extern "C" cudaError_t zs_block_stage_launch(cudaStream_t, uint32_t, uint32_t, const ZsChunk *, const uint32_t *, const uint32_t *,
                                              const uint32_t *, const uint32_t *, zh_block *, ZsLzParams, void *, void *, uint32_t *);
@@ -297,18 +298,23 @@ extern "C" int zscgpu_event_elapsed_ms(zscgpu_engine *e, int a, int b, float *ms
 
 /* ----------------------------- deflate ----------------------------- */
 
-/* level/strategy -> search parameters.  The reference's configuration_table (src/deflate.c:146-158)
- * tunes a serial hash-chain search; these are the equivalents for the group-parallel search,
- * chosen so the ratio stays within 2 % of the reference at the same level (tests/test_ratio.py). */
+/* level/strategy -> search parameters.  The reference's configuration_table (src/deflate.c:146-158) tunes a serial
+ * hash-chain search whose budget only counts candidates that pass its quick reject (src/deflate.c:1462-1469: the
+ * decrement sits behind the `continue`), so its nominal 128 reaches far deeper.  Here every candidate counts; good,
+ * max_lazy and nice are the reference's, the budgets are sized so that the output stays within 1 % of the reference's at
+ * the same level on text, telemetry and mixed data (tests/test_gpu.py ratio gates; tests/refimpl.py mirrors the table). */
 static int zs_lz_params(const zscgpu_deflate_params *p, ZsLzParams *L, int *chain_kernel)
 {
     int level = p->level == -1 ? 6 : p->level;
     if (level < 0 || level > 9 || p->strategy < 0 || p->strategy > 4 || p->wrap < 0 || p->wrap > 2) return -1;
     memset(L, 0, sizeof(*L));
     L->mode = 0; L->min_len = 3; L->force_type = -1; L->wrap = p->wrap;
-    static const int chain_tab[10] = {0, 0, 1, 3, 7, 15, 127, 255, 1023, 4095};
-    static const int nice_tab[10] = {0, 258, 258, 258, 32, 64, 128, 128, 258, 258};
+    static const int chain_tab[10] = {0, 0, 1, 3, 48, 192, 256, 384, 768, 1536};
+    static const int nice_tab[10] = {0, 258, 258, 258, 16, 32, 128, 128, 258, 258};
+    static const int good_tab[10] = {0, 258, 258, 258, 4, 8, 8, 8, 32, 32};
+    static const int max_lazy_tab[10] = {0, 258, 258, 258, 4, 16, 16, 32, 128, 258};
     static const int lazy_tab[10] = {0, 0, 1, 1, 1, 1, 1, 1, 1, 1};
+    L->good = good_tab[level]; L->max_lazy = max_lazy_tab[level];
     L->chain = chain_tab[level]; L->nice = nice_tab[level]; L->lazy = lazy_tab[level];
     if (p->strategy == 2 /* Z_HUFFMAN_ONLY */) L->mode = 2;
     else if (p->strategy == 3 /* Z_RLE */) { L->mode = 1; L->lazy = 0; }
@@ -465,7 +471,8 @@ static int zs_deflate_launch_slice(zscgpu_engine *e, const ZsSlice &sl, uint32_t
     if (sl.timed) ZS_CUDA_CHECK(cudaEventRecord(e->ev[8], st));
     ZS_CUDA_CHECK(zs_adler_chunks_launch(st, nc, e->d_raw, chunks, streams, adler));
     if (sl.timed) ZS_CUDA_CHECK(cudaEventRecord(e->ev[9], st));
-    ZS_CUDA_CHECK(zs_lz_launch(st, chain, nc, e->d_raw, chunks, sym, chunk_nsym, blk_in_start, L));
+    ZS_CUDA_CHECK(chain ? zs_lzc_launch(st, nc, e->d_raw, chunks, sym, chunk_nsym, blk_in_start, L)
+                        : zs_lz_launch(st, nc, e->d_raw, chunks, sym, chunk_nsym, blk_in_start, L));
     if (sl.timed) ZS_CUDA_CHECK(cudaEventRecord(e->ev[10], st));
     ZS_CUDA_CHECK(zs_block_stage_launch(st, 0, nb, chunks, blk_chunk, sym, chunk_nsym, blk_in_start, blocks, L, blk_meta,
                                         e->d_blk_scratch + (size_t)sl.blk0 * zs_block_scratch_bytes(), e->d_blk_used + sl.used0));

@@ -68,12 +68,13 @@ typedef struct {
     uint32_t tmpfreq[ZH_LCODES_PAD];
 } zh_scratch;
 
-/* Chain search (levels 2..9): first-candidate matches of at least this many bytes cover the positions behind
- * them, which then skip their chain walk (deflate_lz.cu; 0 = every position walks its chain).  Derived from the
- * chain depth so that the kernel and the host model (tests/cpu_harness.cpp) agree without another parameter:
- * levels 2-3 (chain 1, 3) have nothing worth skipping, levels 4-9 use 16 (measured on the host model: a threshold of
- * 32 changes nothing, 8 costs text more than the 2 % the ratio gate allows). */
-ZHD static inline uint32_t zs_skip_len(int chain) { return chain < 7 ? 0u : 16u; }
+/* Chain search (levels 2..9, deflate_chain.cu; tests/cpu_harness.cpp mirrors it): tiles of ZC_TILE positions are
+ * searched in ZC_ROUNDS rounds.  A round parses the tile with the match lengths known so far and lets the positions
+ * the parse visits (and the lazy-evaluation candidates behind the matches it takes) follow their hash chains
+ * zc_round_cap(r) candidates further; the last round goes to the end of the level's budget. */
+#define ZC_TILE 2048u
+#define ZC_ROUNDS 4
+ZHD static inline int zc_round_cap(int r) { return r + 1 < ZC_ROUNDS ? (4 << (3 * r)) : 0x7FFFFFFF; }
 
 /* the same working arrays sized for the 30-symbol distance alphabet (a lane-per-block kernel keeps one per
    thread): the stage functions below are templates over the scratch type and behave identically on both */
