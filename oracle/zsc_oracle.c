@@ -159,7 +159,7 @@ I32 zsc_uncompress_get_min_work_buf_size(U32 *out) { return zsc_uncompress_get_m
 typedef struct {
     const U8 *in; U32 in_len, in_pos;       /* next byte to pull */
     U32 hold; int bits;                     /* bit accumulator, LSB first (src/inflate.c NEEDBITS/DROPBITS :640-690) */
-    U8 *out; U32 out_cap, out_pos;
+    U8 *out; U32 out_cap, out_pos, out_base;   /* out_base: output position of the last resynchronisation */
     U32 dmax;                               /* largest legal distance (window size from the header, :774-779) */
     const char *msg;
     int short_in, short_out;                /* why decoding stopped, when it did not finish */
@@ -243,7 +243,7 @@ static int ora_codes(ora_strm *s, const ora_code *lc, const ora_code *dc)
             if (d < 0 || d >= 30) { s->msg = "invalid distance code"; return -1; }
             if (!ora_need(s, ora_dext[d])) return -2;
             U32 dist = ora_dbase[d] + ora_bitsv(s, ora_dext[d]);
-            if (dist > s->dmax || dist > s->out_pos) { s->msg = "invalid distance too far back"; return -1; }   /* inffast.c:184-189, inflate.c:1280-1286 */
+            if (dist > s->dmax || dist > s->out_pos - s->out_base) { s->msg = "invalid distance too far back"; return -1; }   /* inffast.c:184-189, inflate.c:1280-1286 */
             while (len--) {
                 if (s->out_pos >= s->out_cap) { s->short_out = 1; return -2; }
                 s->out[s->out_pos] = s->out[s->out_pos - dist];
@@ -462,6 +462,7 @@ I32 zsc_uncompress_gzip2(U8 *dest, U32 *dest_len, const U8 *source, U32 *source_
         held = 0;
         if (nx > s.in_len) { s.in_pos = s.in_len; terminal = Z_DATA_ERROR; break; }                    /* :1587 */
         s.in_pos = nx; rc = 0; check_from = s.out_pos;
+        s.out_base = s.out_pos; s.dmax = 32768u;          /* inflateReset inside inflateSync: whave = 0, dmax = 32768 (src/inflate.c:301,324) */
     }
     *dest_len = s.out_pos;
     *source_len = s.in_pos - (U32)(s.bits >> 3);

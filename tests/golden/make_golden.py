@@ -6,6 +6,8 @@ Run here (the container that has /root/reference); the fixtures travel, the refe
                          (:367-371, :399-411, :583-613, :643-658) with the expectation written there, and the
                          result of the reference's one-shot zsc_uncompress_gzip2 on each
   bad_headers.json       the hand-built bad zlib / gzip headers of reference test/zlib_gtest.cpp:1815-1918
+  resync_vectors.json    corrupted streams whose recovery depends on what inflateSync resets (window emptied, distance
+                         limit back to 32768)
   ref_streams.json       small seeded inputs, compressed by the reference at several levels / strategies /
                          section sizes: compressed bytes, sizes, adler32, crc32
   ref_sizes.json         the size-check functions over the (window_bits, mem_level, level, len) grid, and
@@ -82,6 +84,45 @@ def bad_headers():
     return out
 
 
+def resync_vectors():
+    """Streams whose recovery path exercises what inflateSync resets (reference src/inflate.c:1547-1604 ->
+    inflateReset :295-330: empty window, dmax back to 32768): a back-reference across a resynchronisation point, and a
+    small-window header whose limit no longer applies behind one.  Built with Python's zlib, answered by the reference."""
+    import zlib
+    rng = np.random.default_rng(1234)
+    out = []
+    text = datagen.fill(6000, 41, datagen.TEXT).tobytes()
+    # (a) sync flushes keep the window, so the section behind the marker refers back across it; a flipped bit in the
+    #     first section sends the decoder to the marker, where those distances reach behind the new start
+    c = zlib.compressobj(6)
+    a = c.compress(text[:3000]) + c.flush(zlib.Z_SYNC_FLUSH)
+    b = c.compress(text[1000:4000]) + c.flush(zlib.Z_FULL_FLUSH)
+    d = c.compress(text[3000:]) + c.flush()
+    for flip in (10, 40, len(a) // 2):
+        bad = bytearray(a + b + d)
+        bad[flip] ^= 0x04
+        out.append({"what": f"back-reference across a resync point (flip at {flip})", "hex": bytes(bad).hex(), "window_bits": 15})
+    # (b) header says window_bits 9; the body (raw deflate made with a 32 KiB window) has a first section with short
+    #     distances, a full flush, then a block that repeats 1000 random bytes at distance 1000 (> 512)
+    blob = rng.integers(0, 256, 1000, dtype=np.uint8).tobytes()
+    c = zlib.compressobj(6, zlib.DEFLATED, -15)
+    s1 = c.compress(b"abcabcabcabcabc" * 20) + c.flush(zlib.Z_FULL_FLUSH)
+    s2 = c.compress(blob + blob) + c.flush()
+    hdr = (8 + ((9 - 8) << 4)) << 8
+    hdr += 31 - (hdr % 31)
+    head = bytes([hdr >> 8, hdr & 0xFF])
+    trailer = zlib.adler32(b"abcabcabcabcabc" * 20 + blob + blob).to_bytes(4, "big")
+    good = head + s1 + s2 + trailer
+    out.append({"what": "window_bits 9 header, distance 1000 behind it: too far back", "hex": good.hex(), "window_bits": 15})
+    bad = bytearray(good)
+    bad[2] |= 0x06                                   # block type 3 in the first block header: a certain data error
+    out.append({"what": "window_bits 9 header, first section corrupted: the limit is 32768 again behind the resync point", "hex": bytes(bad).hex(), "window_bits": 15})
+    for x in out:
+        x["ref"] = run_ref_uncompress(bytes.fromhex(x["hex"]), x["window_bits"], cap=20000)
+        x["ref"]["out_hex"] = None
+    return out
+
+
 def ref_streams():
     inputs = {
         "mixed20k": datagen.fill(20000, 11, datagen.MIXED),
@@ -130,7 +171,10 @@ def ref_sizes():
 
 
 if __name__ == "__main__":
-    for name, fn in (("infcover_vectors", infcover), ("bad_headers", bad_headers), ("ref_streams", ref_streams), ("ref_sizes", ref_sizes)):
+    which = sys.argv[1:] or ["infcover_vectors", "bad_headers", "resync_vectors", "ref_streams", "ref_sizes"]
+    for name, fn in (("infcover_vectors", infcover), ("bad_headers", bad_headers), ("resync_vectors", resync_vectors), ("ref_streams", ref_streams), ("ref_sizes", ref_sizes)):
+        if name not in which:
+            continue
         with open(os.path.join(HERE, name + ".json"), "w") as f:
             json.dump(fn(), f, indent=0)
         print("wrote", name)

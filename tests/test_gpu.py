@@ -198,7 +198,7 @@ def test_inflate_reference_streams_fixture_through_zsc_pub():
         assert r == 0 and used == len(comp) and np.array_equal(out, x), s["input"]
 
 
-@pytest.mark.parametrize("fixture", ["infcover_vectors.json", "bad_headers.json"])
+@pytest.mark.parametrize("fixture", ["infcover_vectors.json", "bad_headers.json", "resync_vectors.json"])
 def test_inflate_known_answer_vectors_through_zsc_pub(fixture):
     """reference test/infcover.c / test/zlib_gtest.cpp:1815-1918 vectors: same return code, same output"""
     Z = capi.zsc()

@@ -23,7 +23,7 @@ def vec_bytes(x):
     return bytes(int(t, 16) for t in x["hex"].split()) if "kind" in x else bytes.fromhex(x["hex"])
 
 
-@pytest.mark.parametrize("fixture", ["infcover_vectors.json", "bad_headers.json"])
+@pytest.mark.parametrize("fixture", ["infcover_vectors.json", "bad_headers.json", "resync_vectors.json"])
 def test_oracle_known_answer_vectors(fixture):
     O = refimpl.oracle()
     for x in load(fixture):

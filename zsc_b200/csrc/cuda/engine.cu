@@ -309,7 +309,7 @@ static int zs_lz_params(const zscgpu_deflate_params *p, ZsLzParams *L, int *chai
     if (level < 0 || level > 9 || p->strategy < 0 || p->strategy > 4 || p->wrap < 0 || p->wrap > 2) return -1;
     memset(L, 0, sizeof(*L));
     L->mode = 0; L->min_len = 3; L->force_type = -1; L->wrap = p->wrap;
-    static const int chain_tab[10] = {0, 0, 1, 3, 48, 192, 256, 384, 768, 1536};
+    static const int chain_tab[10] = {0, 0, 4, 8, 48, 192, 256, 384, 768, 1536};
     static const int nice_tab[10] = {0, 258, 258, 258, 16, 32, 128, 128, 258, 258};
     static const int good_tab[10] = {0, 258, 258, 258, 4, 8, 8, 8, 32, 32};
     static const int max_lazy_tab[10] = {0, 258, 258, 258, 4, 16, 16, 32, 128, 258};

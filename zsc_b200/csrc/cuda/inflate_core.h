@@ -391,6 +391,7 @@ typedef struct {
     zi_aux *X;
     int32_t state, wrap;
     uint32_t last, rem, dist, win, maxw, held;
+    uint32_t base;          /* output position of the last resynchronisation: no distance may reach behind it */
     uint32_t opts;          /* ZI_OPT_*: section-parallel decoding of one stream (engine.cu zs_inflate_sectioned) */
 } zi_mach;
 
@@ -407,7 +408,7 @@ ZID void zi_m_init(zi_mach *m, const uint8_t *in, uint32_t in_len, uint8_t *out,
     m->maxw = ((wrap >> 8) & 0xFF) ? (uint32_t)((wrap >> 8) & 0xFF) : 15u;
     m->wrap = wrap & 0xFF;
     m->win = 1u << m->maxw;
-    m->T = T; m->X = X; m->last = 0; m->rem = 0; m->dist = 0; m->held = 0; m->opts = 0;
+    m->T = T; m->X = X; m->last = 0; m->rem = 0; m->dist = 0; m->held = 0; m->opts = 0; m->base = 0;
     m->res.at_flush = 0;
     m->state = m->wrap == 1 ? ZM_HEAD : ZM_BLOCK;
 }
@@ -467,7 +468,7 @@ ZID void zi_step(zi_mach *m)
             if (d < 4) dist = 1 + (uint32_t)d;
             else { uint32_t eb = ((uint32_t)d - 2) >> 1; dist = 1 + ((2 + ((uint32_t)d & 1)) << eb) + zi_take(io, (int)eb); }
             if (zi_overrun(io)) { zi_m_fail(m, zi_fail(res, ZI_BUF_ERROR, ZI_E_INPUT_END), 0); break; }
-            if (dist > io->op || dist > m->win) { zi_m_fail(m, zi_fail(res, ZI_DATA_ERROR, ZI_E_DIST_TOO_FAR), 0); break; }
+            if (dist > io->op - m->base || dist > m->win) { zi_m_fail(m, zi_fail(res, ZI_DATA_ERROR, ZI_E_DIST_TOO_FAR), 0); break; }
             m->rem = len; m->dist = dist; m->state = ZM_COPY;
         }
     }
@@ -545,6 +546,10 @@ ZID void zi_step(zi_mach *m)
         uint32_t nx = zi_sync(io->in, io->in_len, pos - held);
         if (nx > io->in_len) { zi_seek(io, io->in_len); zi_m_finish(m, ZI_DATA_ERROR); return; }
         zi_seek(io, nx);
+        /* inflateSync resets the stream (src/inflate.c:1593 -> inflateReset: whave = 0, dmax = 32768) and the next
+           inflate() call measures distances from its own first output byte (src/inflate.c:1284-1295, inffast.c:190-200) */
+        m->base = io->op;
+        m->win = 32768u;
         m->state = ZM_BLOCK;
         return;
     }
@@ -606,7 +611,7 @@ ZID uint32_t zi_fast_batch(zi_mach *m, const uint32_t *lut_len, const uint32_t *
     }
     if (nmax == 0) { *vop = op; return 0; }
     zi_io io = m->io;                                    /* the cursor in registers for the whole batch */
-    const uint32_t win = m->win;
+    const uint32_t win = m->win, base = m->base;
     while (n < nmax) {
         zi_refill(&io);                                  /* >= 33 bits: a literal/length code and its extra bits */
         const uint64_t h = io.hold;
@@ -657,7 +662,7 @@ ZID uint32_t zi_fast_batch(zi_mach *m, const uint32_t *lut_len, const uint32_t *
             eb2 = db >> 16;
             dist = (db & 0xFFFFu) + ((uint32_t)(h2 >> l2) & ((1u << eb2) - 1u));
         }
-        if (dist == 0 || dist > op || dist > win) {
+        if (dist == 0 || dist > op - base || dist > win) {
             /* not ours: put the cursor back in front of the length code */
             io.hold = h; io.bits = b; io.ip = ip0; io.pre = pre0; io.pv = pv0;
             break;
@@ -703,7 +708,7 @@ ZID void zi_inflate(const uint8_t *in, uint32_t in_len, uint8_t *out, uint32_t o
     *res = m.res;
 }
 
-/* The warp form run serially (host): same control flow as zs_inflate_warp_kernel with the cooperative writes
+/* The group form run serially (host): same control flow as zs_inflate_group_kernel with the cooperative writes
  * replaced by plain loops.  Used by tests/ to pin the batch logic against zi_inflate on the CPU. */
 ZID void zi_inflate_batched(const uint8_t *in, uint32_t in_len, uint8_t *out, uint32_t out_cap,
                             int wrap, zi_tables *T, zi_result *res, uint32_t group)
