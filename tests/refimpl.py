@@ -103,7 +103,7 @@ def h_inflate(comp, cap, wrap=1):
 # level -> [mode, chain, nice, lazy, min_len, max_dist, force_type, wrap, zhdr, good, max_lazy]; must mirror zs_lz_params (engine.cu)
 FAST_MAX_DIST = 32768 - 3 * 2048 - 272
 #            level:  0    1    2    3    4    5    6    7    8     9
-CHAIN_TAB = [0, 0, 4, 8, 48, 192, 256, 384, 768, 1536]
+CHAIN_TAB = [0, 0, 4, 8, 48, 128, 160, 256, 384, 512]
 NICE_TAB = [0, 258, 258, 258, 16, 32, 128, 128, 258, 258]
 GOOD_TAB = [0, 258, 258, 258, 4, 8, 8, 8, 32, 32]
 MAX_LAZY_TAB = [0, 258, 258, 258, 4, 16, 16, 32, 128, 258]

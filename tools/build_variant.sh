@@ -6,7 +6,7 @@ cd "$(dirname "$0")/.."
 name=$1; flags=$2
 d=build/var/$name
 mkdir -p $d
-for f in deflate_lz deflate_huff checksum inflate engine; do
+for f in deflate_lz deflate_chain deflate_huff checksum inflate engine; do
   nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Iinclude -Izsc_b200/csrc/cuda $flags -c zsc_b200/csrc/cuda/$f.cu -o $d/$f.o &
 done
 wait

@@ -16,8 +16,8 @@
  *     lazy-evaluation candidates, unless the match is already max_lazy long) into a work list, and the 512 worker
  *     threads follow the chains of the listed positions zc_round_cap(r) candidates further (a quarter of the budget
  *     behind a match that is already `good`).  Positions the parse never visits are never searched deeper — on the
- *     BASELINE workloads a third of the positions walk at all, 8-13 candidates per input byte at level 6 instead of
- *     37-44 when every position walks, at the same output size;
+ *     BASELINE workloads a third of the positions walk at all, 7-9 candidates per input byte at level 6 instead of
+ *     37-44 when every position walks, at a smaller output size;
  *   - the final parse emits 32-bit symbols exactly like deflate_lz.cu.
  *
  * The reference's budget counts only candidates that pass its quick reject (the MISRA rewrite of longest_match moved
@@ -167,26 +167,30 @@ __device__ __forceinline__ void zc_parse(ZcSmem &S, const ZsLzParams &P, uint32_
     }
 }
 
-/* follow the chain of tile position i up to `cap` candidates further */
-__device__ __forceinline__ void zc_walk(ZcSmem &S, const ZsLzParams &P, uint32_t i, uint32_t t0, int cap, uint32_t q_dict, uint32_t q_end)
+/* Follow the chain of tile position i up to `cap` candidates further.  One step = one candidate: its link and its
+ * reject byte are requested together (one shared-memory round trip on the chain); the full comparison runs only when
+ * the two bytes behind the best match agree.  The listed positions are dealt out statically, one walk per thread and
+ * pass: handing them out dynamically (a lane takes the next position when its walk ends) and a burst loop over the
+ * active lanes measured 20-25 % slower at every budget (profiles/r02e_chain_variants.log) — the walks that decide a
+ * round's duration are the few that run to the end of the budget, and those are on the critical path either way. */
+__device__ __forceinline__ void zc_walk_one(ZcSmem &S, const ZsLzParams &P, uint32_t i, uint32_t t0, int cap, uint32_t q_dict, uint32_t q_end)
 {
     const uint32_t q = t0 + i;
     const uint32_t ml = min(ZS_MAX_MATCH, q_end - q);
     const uint32_t md = min((uint32_t)P.max_dist, q - q_dict);
-    const uint32_t lim = i + ZS_WINDOW - ZC_TILE;        /* links of candidates farther back than this have been recycled */
+    const uint32_t lim = i + ZS_WINDOW - ZC_TILE;
     uint32_t d = S.cur[i], best = S.best[i], bestd = S.bestd[i];
     int bud = S.budget[i];
-    int steps = cap < bud ? cap : bud;                   /* candidates this call may examine */
+    int steps = cap < bud ? cap : bud;
     bud -= steps;
     uint32_t eff = best < 2 ? 2u : best;
     uint32_t tail = zl_ld8<ZC_RING>(S.ring32, q + eff), tail1 = zl_ld8<ZC_RING>(S.ring32, q + eff - 1);
     uint32_t step = (d != 0 && d <= lim) ? (uint32_t)S.prevd[(q - d) & (ZS_WINDOW - 1)] : 0u;
     while (steps > 0) {
-        if (step == 0) { d = 0; break; }                 /* end of the chain (or its link has been recycled) */
+        if (step == 0) { d = 0; break; }
         d += step;
         if (d > md) { d = 0; break; }
         steps--;
-        /* the link of this candidate is requested together with its reject byte: one shared-memory round trip per step */
         step = d <= lim ? (uint32_t)S.prevd[(q - d) & (ZS_WINDOW - 1)] : 0u;
         const uint32_t rb = zl_ld8<ZC_RING>(S.ring32, q + eff - d);
         if (rb == tail && zl_ld8<ZC_RING>(S.ring32, q + eff - 1 - d) == tail1) {
@@ -199,7 +203,7 @@ __device__ __forceinline__ void zc_walk(ZcSmem &S, const ZsLzParams &P, uint32_t
             }
         }
     }
-    bud += steps;                                        /* unused part of this call's share */
+    bud += steps;
     if (bud <= 0) d = 0;
     S.cur[i] = (uint16_t)d; S.budget[i] = (int16_t)bud; S.best[i] = (uint16_t)best; S.bestd[i] = (uint16_t)bestd;
 }
@@ -346,7 +350,7 @@ zs_lzc_kernel(const uint8_t *__restrict__ raw, const ZsChunk *__restrict__ chunk
                     const uint32_t n = S.list_n;
                     if (n == 0) break;
                     const int cap = zc_round_cap(r);
-                    for (uint32_t j = wtid; j < n; j += ZL_WORKERS) zc_walk(S, P, S.list[j], t0, cap, q_dict, q_end);
+                    for (uint32_t j = wtid; j < n; j += ZL_WORKERS) zc_walk_one(S, P, S.list[j], t0, cap, q_dict, q_end);
                     zl_bar_workers();
                 }
 

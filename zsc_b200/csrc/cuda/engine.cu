@@ -309,13 +309,16 @@ static int zs_lz_params(const zscgpu_deflate_params *p, ZsLzParams *L, int *chai
     if (level < 0 || level > 9 || p->strategy < 0 || p->strategy > 4 || p->wrap < 0 || p->wrap > 2) return -1;
     memset(L, 0, sizeof(*L));
     L->mode = 0; L->min_len = 3; L->force_type = -1; L->wrap = p->wrap;
-    static const int chain_tab[10] = {0, 0, 4, 8, 48, 192, 256, 384, 768, 1536};
+    static const int chain_tab[10] = {0, 0, 4, 8, 48, 128, 160, 256, 384, 512};
     static const int nice_tab[10] = {0, 258, 258, 258, 16, 32, 128, 128, 258, 258};
     static const int good_tab[10] = {0, 258, 258, 258, 4, 8, 8, 8, 32, 32};
     static const int max_lazy_tab[10] = {0, 258, 258, 258, 4, 16, 16, 32, 128, 258};
     static const int lazy_tab[10] = {0, 0, 1, 1, 1, 1, 1, 1, 1, 1};
     L->good = good_tab[level]; L->max_lazy = max_lazy_tab[level];
     L->chain = chain_tab[level]; L->nice = nice_tab[level]; L->lazy = lazy_tab[level];
+#ifdef ZSC_TUNING
+    if (getenv("ZSC_B200_CHAIN_BUDGET") && L->chain > 0) L->chain = atoi(getenv("ZSC_B200_CHAIN_BUDGET"));   /* tuning builds only (tools/build_variant.sh) */
+#endif
     if (p->strategy == 2 /* Z_HUFFMAN_ONLY */) L->mode = 2;
     else if (p->strategy == 3 /* Z_RLE */) { L->mode = 1; L->lazy = 0; }
     else if (p->strategy == 1 /* Z_FILTERED */) L->min_len = 6;

@@ -73,8 +73,12 @@ typedef struct {
  * the parse visits (and the lazy-evaluation candidates behind the matches it takes) follow their hash chains
  * zc_round_cap(r) candidates further; the last round goes to the end of the level's budget. */
 #define ZC_TILE 2048u
-#define ZC_ROUNDS 4
-ZHD static inline int zc_round_cap(int r) { return r + 1 < ZC_ROUNDS ? (4 << (3 * r)) : 0x7FFFFFFF; }
+#ifndef ZC_ROUNDS
+#define ZC_ROUNDS 2
+#define ZC_CAP0 32
+#define ZC_CAP_SHIFT 2
+#endif
+ZHD static inline int zc_round_cap(int r) { return r + 1 < ZC_ROUNDS ? (ZC_CAP0 << (ZC_CAP_SHIFT * r)) : 0x7FFFFFFF; }
 
 /* the same working arrays sized for the 30-symbol distance alphabet (a lane-per-block kernel keeps one per
    thread): the stage functions below are templates over the scratch type and behave identically on both */
