@@ -196,7 +196,7 @@ static void lz_chunk_chain(const uint8_t *data, uint32_t a, uint32_t dict_len, u
         };
         for (uint32_t i = 0; i < CT; i++) {
             const uint32_t q = t0 + i;
-            best[i] = bestd[i] = cur[i] = 0; budget[i] = P.chain; cut[i] = 0;
+            best[i] = bestd[i] = cur[i] = 0; budget[i] = zc_budget(P.chain, len); cut[i] = 0;
             if (!(q >= q_start && q + 3 <= q_end)) continue;
             const uint32_t ml = MAXL(q), md = MAXD(q), d = t_cand[i];
             if (d != 0 && d <= md) {

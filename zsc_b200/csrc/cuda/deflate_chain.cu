@@ -300,7 +300,7 @@ zs_lzc_kernel(const uint8_t *__restrict__ raw, const ZsChunk *__restrict__ chunk
                     S.best[i] = (uint16_t)best;
                     S.bestd[i] = (uint16_t)(best ? d : 0u);
                     S.cur[i] = (uint16_t)((d != 0 && !(best >= (uint32_t)P.nice || best >= ml)) ? d : 0u);
-                    S.budget[i] = (int16_t)P.chain;
+                    S.budget[i] = (int16_t)zc_budget(P.chain, cd.len);
                 }
                 if (wtid < ZC_GROUPS) S.cutbits[wtid] = 0;
                 zl_bar_workers();

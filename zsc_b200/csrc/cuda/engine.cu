@@ -26,7 +26,7 @@ extern "C" cudaError_t zs_adler_flat_launch(cudaStream_t, const uint8_t *, uint6
 extern "C" cudaError_t zs_crc_init_launch(cudaStream_t);
 extern "C" cudaError_t zs_crc_flat_launch(cudaStream_t, const uint8_t *, uint64_t, uint32_t, uint32_t *, int);
 extern "C" cudaError_t zs_inflate_launch(cudaStream_t, uint32_t, const ZsStream *, const uint8_t *, uint8_t *, int32_t,
-                                         int32_t *, uint32_t *, uint32_t *, uint32_t *, uint32_t *, ZsAdlerAcc *, uint32_t, int);
+                                         int32_t *, uint32_t *, uint32_t *, uint32_t *, uint32_t *, ZsAdlerAcc *, uint32_t, int, uint32_t *, int);
 
 #define ZS_NEVENTS 16
 #define ZS_MAX_WAVES 64
@@ -51,6 +51,7 @@ struct zscgpu_engine {
     uint32_t *d_blk_used;             /* [0] = number of used block slots of the launch, then their indices */
     ZsAdlerAcc *d_adler;              /* per stream; slot max_streams is the flat-checksum slot */
     uint32_t *d_crc;                  /* [2] */
+    uint32_t *d_ctr;                  /* inflate: next unclaimed stream of the batch */
     uint32_t *d_aux;                  /* inflate: [2 * max_streams] trailer check + flags */
     uint32_t *h_aux;                  /* the same on the host (section passes read the flags) */
     uint32_t *d_cand, *h_cand;        /* sectioned inflate: [max_streams + 1] positions behind 00 00 FF FF, slot 0 = count */
@@ -75,11 +76,13 @@ struct zscgpu_engine {
     ZsLzParams last_lz;
     uint32_t launches;
     std::mutex mu;
+    std::mutex call_mu;               /* serialises the one-shot host-buffer calls of this engine (they share offset 0 of the arenas) */
     char err[512];
 };
 
 static char g_init_err[512];
 static zscgpu_engine *g_engine;
+static bool g_init_failed;            /* a failed default init is not retried on every zsc_* call (zscgpu_global_shutdown clears it) */
 static std::mutex g_mu;
 
 static int zs_fail(zscgpu_engine *e, cudaError_t ce, const char *what, int line)
@@ -106,6 +109,8 @@ extern "C" void zscgpu_default_config(zscgpu_config *cfg)
 template <typename T> static cudaError_t zs_pinned(T **p, size_t n) { return cudaHostAlloc((void **)p, n * sizeof(T), cudaHostAllocMapped); }
 template <typename T> static cudaError_t zs_dev(T **p, size_t n) { return cudaMalloc((void **)p, n * sizeof(T)); }
 
+static int zs_init_engine(zscgpu_engine *e, const zscgpu_config &cfg, const cudaDeviceProp &prop);
+
 extern "C" int zscgpu_init(const zscgpu_config *cfg_in, zscgpu_engine **out)
 {
     zscgpu_engine *e = nullptr;
@@ -128,7 +133,21 @@ extern "C" int zscgpu_init(const zscgpu_config *cfg_in, zscgpu_engine **out)
         return ZSCGPU_ERR_NO_DEVICE;
     }
     ZS_CUDA_CHECK(cudaSetDevice(cfg.device));
-    e = new zscgpu_engine();
+    e = new zscgpu_engine();                      /* value-initialised: every pointer and handle starts out null */
+    const int rc = zs_init_engine(e, cfg, prop);
+    if (rc != ZSCGPU_OK) {
+        /* one way out of a failed init: keep the message where zscgpu_last_error(NULL) finds it, release whatever
+           had been allocated (zscgpu_destroy tolerates a half-built engine) */
+        if (e->err[0]) snprintf(g_init_err, sizeof(g_init_err), "%s", e->err);
+        zscgpu_destroy(e);
+        return rc;
+    }
+    *out = e;
+    return ZSCGPU_OK;
+}
+
+static int zs_init_engine(zscgpu_engine *e, const zscgpu_config &cfg, const cudaDeviceProp &prop)
+{
     e->cfg = cfg;
     e->sms = prop.multiProcessorCount;
     e->err[0] = 0;
@@ -156,6 +175,7 @@ extern "C" int zscgpu_init(const zscgpu_config *cfg_in, zscgpu_engine **out)
     ZS_CUDA_CHECK(zs_dev(&e->d_blk_used, (size_t)e->blk_cap + 2));
     ZS_CUDA_CHECK(zs_dev(&e->d_adler, cfg.max_streams + 1));
     ZS_CUDA_CHECK(zs_dev(&e->d_crc, 4));
+    ZS_CUDA_CHECK(zs_dev(&e->d_ctr, 16));
     ZS_CUDA_CHECK(zs_dev(&e->d_aux, 2ull * cfg.max_streams));
     ZS_CUDA_CHECK(zs_pinned(&e->h_aux, 2ull * cfg.max_streams));
     ZS_CUDA_CHECK(zs_dev(&e->d_cand, (size_t)cfg.max_streams + 1));
@@ -166,7 +186,7 @@ extern "C" int zscgpu_init(const zscgpu_config *cfg_in, zscgpu_engine **out)
         e->sec_start = (uint32_t *)malloc(6 * m1 * sizeof(uint32_t));
         e->sec_st = (zscgpu_stream *)malloc(m1 * sizeof(zscgpu_stream));
         e->sec_r1 = (zscgpu_result *)malloc(2 * m1 * sizeof(zscgpu_result));
-        if (!e->sec_start || !e->sec_st || !e->sec_r1) { snprintf(g_init_err, sizeof(g_init_err), "out of host memory"); return ZSCGPU_ERR_CUDA; }
+        if (!e->sec_start || !e->sec_st || !e->sec_r1) { snprintf(e->err, sizeof(e->err), "out of host memory"); return ZSCGPU_ERR_CUDA; }
         e->sec_opts = e->sec_start + m1; e->sec_flags = e->sec_opts + m1; e->sec_trailer = e->sec_flags + m1;
         e->sec_real = e->sec_trailer + m1; e->sec_off = e->sec_real + m1;
         e->sec_r2 = e->sec_r1 + m1;
@@ -187,28 +207,31 @@ extern "C" int zscgpu_init(const zscgpu_config *cfg_in, zscgpu_engine **out)
     for (int i = 0; i < ZS_MAX_WAVES; i++) ZS_CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_wave[i], cudaEventDisableTiming));
     ZS_CUDA_CHECK(zs_crc_init_launch(e->stream));
     ZS_CUDA_CHECK(cudaStreamSynchronize(e->stream));
-    *out = e;
     return ZSCGPU_OK;
 }
 
 extern "C" void zscgpu_destroy(zscgpu_engine *e)
 {
     if (!e) return;
-    cudaStreamSynchronize(e->stream);
+    cudaSetDevice(e->cfg.device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
     cudaFree(e->d_raw); cudaFree(e->d_comp); cudaFree(e->d_sym);
     cudaFreeHost(e->h_chunks); cudaFree(e->d_chunks);
     cudaFreeHost(e->h_streams); cudaFree(e->d_streams);
     cudaFreeHost(e->h_blk_chunk); cudaFree(e->d_blk_chunk);
     cudaFree(e->d_chunk_nsym); cudaFree(e->d_blk_in_start); cudaFree(e->d_blocks); cudaFree(e->d_blk_meta); cudaFree(e->d_blk_bitoff); cudaFree(e->d_blk_scratch); cudaFree(e->d_blk_used);
-    cudaFree(e->d_adler); cudaFree(e->d_crc); cudaFree(e->d_aux); cudaFreeHost(e->h_aux); cudaFree(e->d_cand); cudaFreeHost(e->h_cand);
+    cudaFree(e->d_adler); cudaFree(e->d_crc); cudaFree(e->d_ctr); cudaFree(e->d_aux); cudaFreeHost(e->h_aux); cudaFree(e->d_cand); cudaFreeHost(e->h_cand);
     free(e->sec_start); free(e->sec_st); free(e->sec_r1);
     cudaFree(e->d_ret); cudaFree(e->d_produced); cudaFree(e->d_consumed); cudaFree(e->d_check);
     cudaFreeHost(e->h_ret); cudaFreeHost(e->h_produced); cudaFreeHost(e->h_consumed); cudaFreeHost(e->h_check);
-    for (int i = 0; i < ZS_NEVENTS; i++) cudaEventDestroy(e->ev[i]);
-    for (int i = 0; i < ZS_MAX_WAVES; i++) cudaEventDestroy(e->ev_wave[i]);
-    cudaStreamDestroy(e->copy_stream); cudaStreamDestroy(e->d2h_stream); cudaStreamDestroy(e->stream2);
-    for (int i = 0; i < 2; i++) cudaEventDestroy(e->ev_slice[i]);
-    cudaStreamDestroy(e->stream);
+    for (int i = 0; i < ZS_NEVENTS; i++) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
+    for (int i = 0; i < ZS_MAX_WAVES; i++) if (e->ev_wave[i]) cudaEventDestroy(e->ev_wave[i]);
+    if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+    if (e->d2h_stream) cudaStreamDestroy(e->d2h_stream);
+    if (e->stream2) cudaStreamDestroy(e->stream2);
+    for (int i = 0; i < 2; i++) if (e->ev_slice[i]) cudaEventDestroy(e->ev_slice[i]);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    cudaGetLastError();                           /* a half-built engine may have tripped on a null handle above */
     delete e;
 }
 
@@ -216,12 +239,14 @@ extern "C" int zscgpu_global_init(const zscgpu_config *cfg)
 {
     std::lock_guard<std::mutex> lk(g_mu);
     if (g_engine) return ZSCGPU_OK;
-    return zscgpu_init(cfg, &g_engine);
+    const int rc = zscgpu_init(cfg, &g_engine);
+    g_init_failed = (rc != ZSCGPU_OK);
+    return rc;
 }
 extern "C" zscgpu_engine *zscgpu_global(void)
 {
     std::lock_guard<std::mutex> lk(g_mu);
-    if (!g_engine) (void)zscgpu_init(nullptr, &g_engine);
+    if (!g_engine && !g_init_failed) g_init_failed = (zscgpu_init(nullptr, &g_engine) != ZSCGPU_OK);
     return g_engine;
 }
 extern "C" void zscgpu_global_shutdown(void)
@@ -229,6 +254,7 @@ extern "C" void zscgpu_global_shutdown(void)
     std::lock_guard<std::mutex> lk(g_mu);
     zscgpu_destroy(g_engine);
     g_engine = nullptr;
+    g_init_failed = false;
 }
 
 extern "C" void *zscgpu_raw_ptr(zscgpu_engine *e) { return e->d_raw; }
@@ -236,6 +262,10 @@ extern "C" void *zscgpu_comp_ptr(zscgpu_engine *e) { return e->d_comp; }
 extern "C" uint64_t zscgpu_raw_capacity(const zscgpu_engine *e) { return e->cfg.raw_bytes; }
 extern "C" uint64_t zscgpu_comp_capacity(const zscgpu_engine *e) { return e->cfg.comp_bytes; }
 extern "C" void *zscgpu_cuda_stream(zscgpu_engine *e) { return (void *)e->stream; }
+
+/* Every entry point that touches CUDA selects the engine's device first: callers may come from any thread, and a
+ * process may hold engines on several GPUs. */
+#define ZS_ENTER(e) do { cudaError_t _d = cudaSetDevice((e)->cfg.device); if (_d != cudaSuccess) return zs_fail((e), _d, "cudaSetDevice", __LINE__); } while (0)
 
 static int zs_arena(zscgpu_engine *e, int which, uint64_t off, uint64_t n, uint8_t **p)
 {
@@ -246,17 +276,19 @@ static int zs_arena(zscgpu_engine *e, int which, uint64_t off, uint64_t n, uint8
 }
 extern "C" int zscgpu_upload_async(zscgpu_engine *e, int which, uint64_t off, const void *host, uint64_t n)
 {
+    ZS_ENTER(e);
     uint8_t *p; int r = zs_arena(e, which, off, n, &p); if (r) return r;
     if (n) ZS_CUDA_CHECK(cudaMemcpyAsync(p, host, n, cudaMemcpyHostToDevice, e->stream));
     return ZSCGPU_OK;
 }
 extern "C" int zscgpu_download_async(zscgpu_engine *e, int which, void *host, uint64_t off, uint64_t n)
 {
+    ZS_ENTER(e);
     uint8_t *p; int r = zs_arena(e, which, off, n, &p); if (r) return r;
     if (n) ZS_CUDA_CHECK(cudaMemcpyAsync(host, p, n, cudaMemcpyDeviceToHost, e->stream));
     return ZSCGPU_OK;
 }
-extern "C" int zscgpu_sync(zscgpu_engine *e) { ZS_CUDA_CHECK(cudaStreamSynchronize(e->stream)); return ZSCGPU_OK; }
+extern "C" int zscgpu_sync(zscgpu_engine *e) { ZS_ENTER(e); ZS_CUDA_CHECK(cudaStreamSynchronize(e->stream)); return ZSCGPU_OK; }
 extern "C" int zscgpu_upload(zscgpu_engine *e, int which, uint64_t off, const void *host, uint64_t n)
 {
     int r = zscgpu_upload_async(e, which, off, host, n); if (r) return r;
@@ -269,6 +301,7 @@ extern "C" int zscgpu_download(zscgpu_engine *e, int which, void *host, uint64_t
 }
 extern "C" int zscgpu_copy_within(zscgpu_engine *e, int which, uint64_t dst_off, uint64_t src_off, uint64_t n)
 {
+    ZS_ENTER(e);
     uint8_t *d, *s;
     int r = zs_arena(e, which, dst_off, n, &d); if (r) return r;
     r = zs_arena(e, which, src_off, n, &s); if (r) return r;
@@ -284,12 +317,14 @@ extern "C" int zscgpu_host_unregister(void *p) { return cudaHostUnregister(p) ==
 
 extern "C" int zscgpu_event_record(zscgpu_engine *e, int slot)
 {
+    ZS_ENTER(e);
     if (slot < 0 || slot >= ZS_NEVENTS) return ZSCGPU_ERR_ARG;
     ZS_CUDA_CHECK(cudaEventRecord(e->ev[slot], e->stream));
     return ZSCGPU_OK;
 }
 extern "C" int zscgpu_event_elapsed_ms(zscgpu_engine *e, int a, int b, float *ms)
 {
+    ZS_ENTER(e);
     if (a < 0 || a >= ZS_NEVENTS || b < 0 || b >= ZS_NEVENTS) return ZSCGPU_ERR_ARG;
     ZS_CUDA_CHECK(cudaEventSynchronize(e->ev[b]));
     ZS_CUDA_CHECK(cudaEventElapsedTime(ms, e->ev[a], e->ev[b]));
@@ -378,6 +413,11 @@ static int zs_build_deflate_desc(zscgpu_engine *e, const ZsSlice &sl, const zscg
             z->comp_off > e->cfg.comp_bytes || z->comp_len > e->cfg.comp_bytes - z->comp_off) {
             snprintf(e->err, sizeof(e->err), "stream %u lies outside the arenas", s);
             return ZSCGPU_ERR_CAPACITY;
+        }
+        if (z->comp_off & 3u) {
+            /* the offset pass clears and the bit packer ORs whole 32-bit words at a stream's first and last byte */
+            snprintf(e->err, sizeof(e->err), "stream %u: comp_off must be a multiple of 4 (deflate output regions are word granular)", s);
+            return ZSCGPU_ERR_ARG;
         }
         ZsStream *S = &e->h_streams[sl.stream0 + s];
         S->raw_off = z->raw_off; S->comp_off = z->comp_off; S->raw_len = z->raw_len; S->comp_cap = z->comp_len;
@@ -499,6 +539,7 @@ static int zs_deflate_launch_all(zscgpu_engine *e)
 extern "C" int zscgpu_deflate_enqueue(zscgpu_engine *e, const zscgpu_stream *streams, uint32_t n, const zscgpu_deflate_params *p)
 {
     std::lock_guard<std::mutex> lk(e->mu);
+    ZS_ENTER(e);
     if (!streams || !p || n == 0 || n > e->cfg.max_streams || p->max_block_len == 0) { snprintf(e->err, sizeof(e->err), "bad deflate batch arguments"); return ZSCGPU_ERR_ARG; }
     ZsLzParams L; int chain;
     if (zs_lz_params(p, &L, &chain)) { snprintf(e->err, sizeof(e->err), "bad level/strategy/wrap"); return ZSCGPU_ERR_ARG; }
@@ -516,7 +557,7 @@ static int zs_inflate_launch_all(zscgpu_engine *e)
 {
     const uint32_t n = e->last_nstreams;
     ZS_CUDA_CHECK(zs_inflate_launch(e->stream, n, e->d_streams, e->d_comp, e->d_raw, e->last_wrap, e->d_ret, e->d_produced, e->d_consumed, e->d_check,
-                                    e->d_aux, e->d_adler, e->last_max_raw, e->last_with_check));
+                                    e->d_aux, e->d_adler, e->last_max_raw, e->last_with_check, e->d_ctr, e->sms));
     ZS_CUDA_CHECK(cudaMemcpyAsync(e->h_ret, e->d_ret, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, e->stream));
     ZS_CUDA_CHECK(cudaMemcpyAsync(e->h_produced, e->d_produced, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, e->stream));
     ZS_CUDA_CHECK(cudaMemcpyAsync(e->h_consumed, e->d_consumed, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, e->stream));
@@ -531,6 +572,7 @@ static int zs_inflate_launch_all(zscgpu_engine *e)
 static int zs_inflate_enqueue_opts(zscgpu_engine *e, const zscgpu_stream *streams, uint32_t n, int32_t wrap, const uint32_t *opts)
 {
     std::lock_guard<std::mutex> lk(e->mu);
+    ZS_ENTER(e);
     if (!streams || n == 0 || n > e->cfg.max_streams || (wrap & 0xFF) > 1 || wrap < 0) { snprintf(e->err, sizeof(e->err), "bad inflate batch arguments"); return ZSCGPU_ERR_ARG; }
     uint32_t max_raw = 0;
     for (uint32_t s = 0; s < n; s++) {
@@ -605,6 +647,7 @@ extern "C" uint64_t zscgpu_guess_section_size(uint64_t total, uint32_t sections)
 
 extern "C" int zscgpu_inflate_sectioned(zscgpu_engine *e, const zscgpu_stream *stream, int32_t wrap, zscgpu_result *res)
 {
+    ZS_ENTER(e);
     if (!stream || !res || (wrap & 0xFF) > 1 || wrap < 0) { snprintf(e->err, sizeof(e->err), "bad inflate arguments"); return ZSCGPU_ERR_ARG; }
     if (stream->raw_off > e->cfg.raw_bytes || stream->raw_len > e->cfg.raw_bytes - stream->raw_off ||
         stream->comp_off > e->cfg.comp_bytes || stream->comp_len > e->cfg.comp_bytes - stream->comp_off) {
@@ -729,6 +772,7 @@ extern "C" int zscgpu_inflate_sectioned(zscgpu_engine *e, const zscgpu_stream *s
 extern "C" int zscgpu_relaunch(zscgpu_engine *e)
 {
     std::lock_guard<std::mutex> lk(e->mu);
+    ZS_ENTER(e);
     if (e->last_kind == 1) return zs_deflate_launch_all(e);
     if (e->last_kind == 2) return zs_inflate_launch_all(e);
     return ZSCGPU_ERR_ARG;
@@ -739,6 +783,7 @@ extern "C" unsigned long long zscgpu_launch_total(const zscgpu_engine *e) { retu
 extern "C" int zscgpu_fetch_results(zscgpu_engine *e, uint32_t n, zscgpu_result *res)
 {
     std::lock_guard<std::mutex> lk(e->mu);
+    ZS_ENTER(e);
     if (n != e->last_nstreams || !res) return ZSCGPU_ERR_ARG;
     ZS_CUDA_CHECK(cudaStreamSynchronize(e->stream));
     for (uint32_t i = 0; i < n; i++) {
@@ -764,9 +809,9 @@ extern "C" int zscgpu_inflate_batch(zscgpu_engine *e, const zscgpu_stream *strea
 }
 
 /* ----------------------------- one-shot host-buffer calls ----------------------------- */
-/* The zsc_pub.h entry points land here: copy in, run the batch of one stream, copy out.  `call_mu`
- * serialises whole calls because they all use offset 0 of the arenas. */
-static std::mutex g_call_mu;
+/* The zsc_pub.h entry points land here: copy in, run the batch of one stream, copy out.  The engine's `call_mu`
+ * serialises whole calls on ONE engine because they all use offset 0 of its arenas; calls on different engines
+ * (other GPUs, or a second engine with smaller arenas on the same GPU) run concurrently. */
 
 /* Large host buffers are processed in waves of whole sections: the upload of wave w+1 (copy engine), the
  * kernels of wave w and the download of wave w-1 (second copy engine) overlap.  Every wave is deflated as a
@@ -864,7 +909,8 @@ static int zs_compress_host_waves(zscgpu_engine *e, uint8_t *dest, uint32_t dest
 extern "C" int zscgpu_compress_host(zscgpu_engine *e, uint8_t *dest, uint32_t dest_cap, const uint8_t *src, uint32_t src_len,
                                     const zscgpu_deflate_params *p, uint32_t comp_skip, zscgpu_result *res)
 {
-    std::lock_guard<std::mutex> lk(g_call_mu);
+    std::lock_guard<std::mutex> lk(e->call_mu);
+    ZS_ENTER(e);
     if ((uint64_t)src_len > e->cfg.raw_bytes || (uint64_t)src_len > e->cfg.deflate_batch_max) {
         snprintf(e->err, sizeof(e->err), "source of %u bytes exceeds the engine's arenas (raw %llu B)", src_len, (unsigned long long)e->cfg.raw_bytes);
         return ZSCGPU_ERR_CAPACITY;
@@ -874,9 +920,7 @@ extern "C" int zscgpu_compress_host(zscgpu_engine *e, uint8_t *dest, uint32_t de
     if (p->max_block_len != 0 && src_len >= (128u << 20)) {
         const uint64_t mbl = p->max_block_len;
         const uint64_t cps = (mbl + ZS_CHUNK_MAX - 1) / ZS_CHUNK_MAX;                 /* chunks per section */
-        const char *rv = getenv("ZSC_B200_WAVE_ROUNDS");                                /* tuning aid */
-        const uint64_t rounds = rv && atoi(rv) > 0 ? (uint64_t)atoi(rv) : 1ull;
-        const uint64_t round_secs = (rounds * 2ull * (uint64_t)e->sms + cps - 1) / cps;   /* sections in `rounds` rounds of chunks (two CTAs per SM) */
+        const uint64_t round_secs = (2ull * (uint64_t)e->sms + cps - 1) / cps;       /* sections in one round of chunks (two CTAs per SM); two and three rounds per wave measured slower */
         const uint64_t k = ((64ull << 20) + round_secs * mbl - 1) / (round_secs * mbl);
         uint64_t W = k * round_secs * mbl;
         uint64_t nw = ((uint64_t)src_len + W - 1) / W;
@@ -890,9 +934,10 @@ extern "C" int zscgpu_compress_host(zscgpu_engine *e, uint8_t *dest, uint32_t de
     }
     int r = zscgpu_upload_async(e, 0, 0, src, src_len); if (r) return r;
     zscgpu_stream st;
-    st.raw_off = 0; st.raw_len = src_len; st.comp_off = comp_skip;
+    const uint32_t dskip = (comp_skip + 3u) & ~3u;          /* where the stream lies in the comp arena (word aligned) */
+    st.raw_off = 0; st.raw_len = src_len; st.comp_off = dskip;
     uint64_t cap = dest_cap > comp_skip ? dest_cap - comp_skip : 0;
-    if (cap > e->cfg.comp_bytes - comp_skip) cap = e->cfg.comp_bytes - comp_skip;
+    if (cap > e->cfg.comp_bytes - dskip) cap = e->cfg.comp_bytes - dskip;
     st.comp_len = (uint32_t)cap;
     r = zscgpu_deflate_enqueue(e, &st, 1, p); if (r) return r;
     if (p->wrap == 2) { r = zscgpu_crc32_enqueue(e, 0, src_len); if (r) return r; }
@@ -903,14 +948,15 @@ extern "C" int zscgpu_compress_host(zscgpu_engine *e, uint8_t *dest, uint32_t de
         ZS_CUDA_CHECK(cudaStreamSynchronize(e->stream));
         res->check = h[1];
     }
-    if (res->ret == 0 && res->produced) return zscgpu_download(e, 1, dest + comp_skip, comp_skip, res->produced);
+    if (res->ret == 0 && res->produced) return zscgpu_download(e, 1, dest + comp_skip, dskip, res->produced);
     return ZSCGPU_OK;
 }
 
 extern "C" int zscgpu_uncompress_host(zscgpu_engine *e, uint8_t *dest, uint32_t dest_cap, const uint8_t *src, uint32_t src_len,
                                       int32_t wrap, zscgpu_result *res)
 {
-    std::lock_guard<std::mutex> lk(g_call_mu);
+    std::lock_guard<std::mutex> lk(e->call_mu);
+    ZS_ENTER(e);
     if ((uint64_t)src_len > e->cfg.comp_bytes) {
         snprintf(e->err, sizeof(e->err), "source of %u bytes exceeds the comp arena (%llu B)", src_len, (unsigned long long)e->cfg.comp_bytes);
         return ZSCGPU_ERR_CAPACITY;
@@ -921,13 +967,18 @@ extern "C" int zscgpu_uncompress_host(zscgpu_engine *e, uint8_t *dest, uint32_t 
     st.raw_len = (uint64_t)dest_cap > e->cfg.raw_bytes ? (uint32_t)e->cfg.raw_bytes : dest_cap;
     r = (src_len >= (64u << 10)) ? zscgpu_inflate_sectioned(e, &st, wrap, res) : zscgpu_inflate_batch(e, &st, 1, wrap, res);
     if (r) return r;
+    if (st.raw_len < dest_cap && res->ret == -5 && res->produced == st.raw_len) {
+        snprintf(e->err, sizeof(e->err), "output exceeds the raw arena (%llu B): configure a larger engine with zscgpu_global_init", (unsigned long long)e->cfg.raw_bytes);
+        return ZSCGPU_ERR_CAPACITY;
+    }
     if (res->produced) return zscgpu_download(e, 0, dest, 0, res->produced);
     return ZSCGPU_OK;
 }
 
 extern "C" int zscgpu_checksum_host(zscgpu_engine *e, int kind, uint32_t init, const uint8_t *buf, uint64_t len, uint32_t *out)
 {
-    std::lock_guard<std::mutex> lk(g_call_mu);
+    std::lock_guard<std::mutex> lk(e->call_mu);
+    ZS_ENTER(e);
     uint32_t v = init;
     uint64_t done = 0;
     do {
@@ -943,6 +994,7 @@ extern "C" int zscgpu_checksum_host(zscgpu_engine *e, int kind, uint32_t init, c
 /* ----------------------------- checksums ----------------------------- */
 extern "C" int zscgpu_adler32_enqueue(zscgpu_engine *e, uint64_t off, uint64_t len)
 {
+    ZS_ENTER(e);
     uint8_t *p; int r = zs_arena(e, 0, off, len, &p); if (r) return r;
     ZsAdlerAcc *acc = e->d_adler + e->cfg.max_streams;
     ZS_CUDA_CHECK(cudaMemsetAsync(acc, 0, sizeof(ZsAdlerAcc), e->stream));
@@ -954,6 +1006,7 @@ extern "C" int zscgpu_adler32_enqueue(zscgpu_engine *e, uint64_t off, uint64_t l
 extern "C" int zscgpu_adler32(zscgpu_engine *e, uint64_t off, uint64_t len, uint32_t init, uint32_t *out)
 {
     std::lock_guard<std::mutex> lk(e->mu);
+    ZS_ENTER(e);
     int r = zscgpu_adler32_enqueue(e, off, len); if (r) return r;
     ZsAdlerAcc h;
     ZS_CUDA_CHECK(cudaMemcpyAsync(&h, e->d_adler + e->cfg.max_streams, sizeof(h), cudaMemcpyDeviceToHost, e->stream));
@@ -967,6 +1020,7 @@ extern "C" int zscgpu_adler32(zscgpu_engine *e, uint64_t off, uint64_t len, uint
 }
 extern "C" int zscgpu_crc32_enqueue(zscgpu_engine *e, uint64_t off, uint64_t len)
 {
+    ZS_ENTER(e);
     uint8_t *p; int r = zs_arena(e, 0, off, len, &p); if (r) return r;
     ZS_CUDA_CHECK(cudaMemsetAsync(e->d_crc, 0, 8, e->stream));
     ZS_CUDA_CHECK(zs_crc_flat_launch(e->stream, p, len, 0, e->d_crc, e->sms));
@@ -977,6 +1031,7 @@ extern "C" int zscgpu_crc32_enqueue(zscgpu_engine *e, uint64_t off, uint64_t len
 extern "C" int zscgpu_crc32(zscgpu_engine *e, uint64_t off, uint64_t len, uint32_t init, uint32_t *out)
 {
     std::lock_guard<std::mutex> lk(e->mu);
+    ZS_ENTER(e);
     uint8_t *p; int r = zs_arena(e, 0, off, len, &p); if (r) return r;
     ZS_CUDA_CHECK(cudaMemsetAsync(e->d_crc, 0, 8, e->stream));
     ZS_CUDA_CHECK(zs_crc_flat_launch(e->stream, p, len, init, e->d_crc, e->sms));
@@ -991,6 +1046,7 @@ extern "C" int zscgpu_crc32(zscgpu_engine *e, uint64_t off, uint64_t len, uint32
 extern "C" int zscgpu_debug_fetch_symbols(zscgpu_engine *e, uint32_t chunk, uint32_t *out, uint32_t cap, uint32_t *nsym)
 {
     std::lock_guard<std::mutex> lk(e->mu);
+    ZS_ENTER(e);
     if (e->last_kind != 1 || chunk >= e->last_nchunks) return ZSCGPU_ERR_ARG;
     ZS_CUDA_CHECK(cudaStreamSynchronize(e->stream));
     uint32_t n = 0;

@@ -78,6 +78,10 @@ typedef struct {
 #define ZC_CAP0 32
 #define ZC_CAP_SHIFT 2
 #endif
+/* candidates a position may examine beyond the first: the level's budget in full 256 KiB chunks, up to eight times that in
+ * shorter ones (262144 / length, rounded down) — there the whole search costs microseconds, and small inputs and small
+ * sections are the ones that lose most to a shallow search */
+ZHD static inline int zc_budget(int chain, uint32_t chunk_len) { return chain * (int)(262144u / (chunk_len < 32768u ? 32768u : chunk_len)); }
 ZHD static inline int zc_round_cap(int r) { return r + 1 < ZC_ROUNDS ? (ZC_CAP0 << (ZC_CAP_SHIFT * r)) : 0x7FFFFFFF; }
 
 /* the same working arrays sized for the 30-symbol distance alphabet (a lane-per-block kernel keeps one per
