@@ -1,20 +1,28 @@
 #!/usr/bin/env python
-"""bench.py — headline benchmark of the zsc-b200 engine (BASELINE.json configs[1]).
+"""bench.py — benchmark of the zsc-b200 engine.  Headline: BASELINE.json configs[1].
 
-Workload (per GPU): 1 GiB synthetic mixed text/binary (tools/datagen.c, seed 1 + rank), compressed
+Workload of the headline (per GPU): 1 GiB synthetic mixed text/binary (tools/datagen.c, seed 1 + rank), compressed
 as ONE zsc_compress-shaped stream at level 1 with max_block_len = 256 KiB (4096 independently
 decodable sections).  A "step" is one full pass of the deflate path over that buffer.
 
   value      input GB/s, inputs resident in HBM, CUDA events on the engine's stream, max over ranks
   e2e        the same pass through the host-buffer C-ABI call behind zsc_compress
-             (zscgpu_compress_host: H2D of the 1 GiB, all kernels, D2H of the compressed stream)
+             (zscgpu_compress_host: H2D of the 1 GiB, all kernels, D2H of the compressed stream), plus zsc_compress
+             itself with pinned and with pageable caller buffers, plus the per-rank copy rates that bound it
   roofline   the LZ77 kernel (dominant): (N + C) algorithmic bytes / its event-timed duration
              against the measured HBM copy bandwidth in MEASURED_PEAKS.json
   cpu_baseline  the reference's own zsc_compress2 (oracle/_ref, compiled from /root/reference) on the
              host cores, bounded sample of the same workload
 
-`--impl reference` times only the reference arm.  Launch with torchrun for --gpus > 1 (one rank per
-GPU, independent 1 GiB per rank: the path shards with no collective, scaling is "weak").
+Side legs in the same JSON line (skipped with --no-side), each with its own parity check, roofline and CPU baseline:
+  canterbury_shaped   configs[0]: the reference's Performance test shape through zsc_compress / zsc_uncompress (N = 1)
+  deflate_levels_6_9  configs[2]: 4096 telemetry buffers at levels 6 and 9, buffers partitioned over the ranks
+  inflate_batched     configs[3]: 16 GiB of reference-compressed streams, streams partitioned over the ranks
+  checksums, strategies   configs[4]: adler32 / crc32 over 8 GiB sharded over the ranks + host combine; Z_HUFFMAN_ONLY / Z_RLE
+  one_stream_over_ranks   one 2 GiB logical stream split over the GPUs by section range, stitched on the host (N > 1)
+
+`--impl reference` times only the reference arm.  Launch with torchrun for --gpus > 1 (one rank per GPU; the headline
+gives every rank its own 1 GiB — the path shards with no collective, scaling "weak" — the side legs split a fixed job).
 """
 import argparse
 import ctypes as C
@@ -163,19 +171,49 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
-def inflate_config4(device):
+def rank_range(n, rank, world):
+    """contiguous share of n units for this rank (GPU g gets [g*ceil(n/G), (g+1)*ceil(n/G)))"""
+    per = -(-n // world)
+    lo = min(n, rank * per)
+    return lo, min(n, lo + per)
+
+
+def ref_batch(kind, data, src_off, src_len, dst_cap, threads, level=6, mbl=SECTION, strategy=0):
+    """n independent reference calls (kind 0 zsc_compress2, 1 zsc_uncompress) on `threads` host threads, timed"""
+    from refimpl import REF_PATH
+    L = C.CDLL(REF_PATH, mode=C.RTLD_LOCAL)
+    u64p, u32p, i32p = C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.POINTER(C.c_int32)
+    L.refprobe_batch.argtypes = [C.c_int, C.c_int, C.c_uint32, C.c_void_p, u64p, u32p, C.c_void_p, u64p, u32p, u32p, i32p,
+                                 C.c_uint32, C.c_int32, C.c_int32]
+    n = len(src_off)
+    doff = np.concatenate([[0], np.cumsum(np.asarray(dst_cap, dtype=np.uint64))]).astype(np.uint64)
+    dst = np.empty(int(doff[-1]) + 16, dtype=np.uint8)
+    so = (C.c_uint64 * n)(*[int(v) for v in src_off]); sl = (C.c_uint32 * n)(*[int(v) for v in src_len])
+    do = (C.c_uint64 * n)(*[int(v) for v in doff[:-1]]); dc = (C.c_uint32 * n)(*[int(v) for v in dst_cap])
+    dl = (C.c_uint32 * n)(); rt = (C.c_int32 * n)()
+    t = time.perf_counter()
+    L.refprobe_batch(kind, threads, n, data.ctypes.data, so, sl, dst.ctypes.data, do, dc, dl, rt, mbl, level, strategy)
+    dt = time.perf_counter() - t
+    assert all(r == 0 for r in rt), "reference call failed"
+    return dt, list(dl)
+
+
+def inflate_config3(device, rank, world, barrier, allmax, peak):
     """BASELINE configs[3]: batched inflate of 16 GiB of reference-compressed streams — 512 unique 256 KiB buffers
     (half configs[1] mixed data, half configs[2] telemetry) compressed by the reference at levels 1/6/9 in equal
-    thirds, replicated 128x in device memory = 65 536 independent zlib streams per pass.  The reference is only the
-    producer of the inputs here (as the config demands); the thing timed is zscgpu_inflate_batch's kernels."""
+    thirds, replicated 128x in device memory = 65 536 independent zlib streams per pass, partitioned over the ranks by
+    contiguous stream ranges (strong scaling: the 16 GiB are the whole job).  The reference is only the producer of the
+    inputs here (as the config demands); the thing timed is zscgpu_inflate_batch's kernels."""
     from concurrent.futures import ThreadPoolExecutor
     from zsc_b200 import Engine, datagen
     import refimpl
-    uniq, rep, S, slot = 512, 128, 262144, 160000
+    uniq, rep_all, S, slot = 512, 128, 262144, 160000
+    r_lo, r_hi = rank_range(rep_all, rank, world)
+    rep = r_hi - r_lo
     n = uniq * rep
     x = np.concatenate([datagen.mixed(uniq // 2 * S, seed=1), datagen.telemetry_buffers(uniq - uniq // 2, S, seed=1000)])
     E = Engine(raw_bytes=n * S + (1 << 20), comp_bytes=n * slot + (1 << 20), deflate_batch_max=uniq * S + (1 << 20),
-               max_streams=n, max_chunks=uniq + 16, device=device)
+               max_streams=max(n, 64), max_chunks=uniq + 16, device=device)
     try:
         if refimpl.have_ref():
             R = refimpl.ref()
@@ -205,25 +243,41 @@ def inflate_config4(device):
         same = all(bool(np.array_equal(E.download(0, k * uniq * S, uniq * S), x)) for k in (0, rep - 1))
         ts = []
         for _ in range(3):
-            E.event(0); E.relaunch(); E.event(1); E.sync(); ts.append(E.elapsed_ms(0, 1))
+            barrier(); E.sync()
+            E.event(0); E.relaunch(); E.event(1); E.sync(); ts.append(allmax(E.elapsed_ms(0, 1)))
         t = sum(ts) / len(ts)
-        csum = sum(len(c) for c in comps) * rep
-        return {"value": round(n * S / 1e6 / t, 2), "unit": "GB/s of output", "ms": round(t, 2), "streams": n, "output_bytes": n * S,
-                "compressed_bytes": csum, "producer": producer, "launches_per_pass": 3,
-                "parity": "all streams Z_OK with the trailer adler32 verified; first and last replica bit-exact with the inputs" if bad == 0 and same else f"MISMATCH ({bad} bad streams)",
-                "roofline": {"bound": "hbm", "achieved": round((n * S + csum) / 1e6 / t, 1), "unit": "GB/s", "algorithmic_bytes": n * S + csum}}
+        csum1 = sum(len(c) for c in comps)
+        n_all, csum = uniq * rep_all, csum1 * rep_all
+        out = {"value": round(n_all * S / 1e6 / t, 2), "unit": "GB/s of output", "ms": round(t, 2), "streams": n_all, "output_bytes": n_all * S,
+               "compressed_bytes": csum, "producer": producer, "launches_per_pass": 3, "scaling": "strong", "streams_per_rank": n,
+               "parity": "all streams Z_OK with the trailer adler32 verified; first and last replica bit-exact with the inputs" if bad == 0 and same else f"MISMATCH ({bad} bad streams)",
+               "roofline": {"bound": "hbm", "kernel": "zs_inflate_group_kernel<16>", "achieved": round((n_all * S + csum) / world / 1e6 / t, 1), "peak": peak, "unit": "GB/s",
+                            "frac": round((n_all * S + csum) / world / 1e6 / t / peak, 5), "algorithmic_bytes": (n_all * S + csum) // world,
+                            "note": "C + N per pass and GPU over the whole pass (decode, output adler32, check kernels)"}}
+        if rank == 0 and refimpl.have_ref():
+            cores = os.cpu_count() or 1
+            packed = np.concatenate(comps)
+            poff = np.concatenate([[0], np.cumsum([len(c) for c in comps])])[:-1]
+            dt, prods = ref_batch(1, packed, poff, [len(c) for c in comps], [S] * uniq, cores)
+            out["cpu_baseline"] = {"value": round(uniq * S / 1e9 / dt, 3), "unit": "GB/s of output", "cores": cores, "kind": "reference",
+                                   "sample": f"the {uniq} unique streams ({uniq * S >> 20} MiB of output) through the reference's zsc_uncompress, one pthread per core"}
+        return out
     finally:
         E.close()
 
 
-def deflate_config2(device):
+def deflate_config2(device, rank, world, barrier, allmax, peak):
     """BASELINE configs[2]: 4096 independent 256 KiB telemetry-like buffers, one stream each, at levels 6 and 9 (hash
-    chains + lazy parse, the chain kernel), device resident; ratio against the reference on the first 64 buffers."""
+    chains + lazy parse, the chain kernel), device resident, partitioned over the ranks by contiguous buffer ranges
+    (strong scaling); every stream goes back through the reference's zsc_uncompress, size against the reference's on
+    the first 64 buffers of rank 0."""
     from zsc_b200 import Engine, datagen
     import refimpl
-    nbuf, S, slot = 4096, 262144, 300000
+    nall, S, slot = 4096, 262144, 300000
+    lo, hi = rank_range(nall, rank, world)
+    nbuf = hi - lo
     n = nbuf * S
-    x = datagen.telemetry_buffers(nbuf, S, seed=1000)
+    x = datagen.fill(n, 1000 + lo, datagen.TELEMETRY, piece=S)       # buffer i is seeded with 1000 + i whatever the rank
     E = Engine(raw_bytes=n + (1 << 20), comp_bytes=nbuf * slot + (1 << 20), deflate_batch_max=n + (1 << 20), max_streams=nbuf, max_chunks=nbuf + 16, device=device)
     out = {}
     try:
@@ -234,25 +288,208 @@ def deflate_config2(device):
             res = E.fetch(nbuf)
             assert all(r.ret == 0 for r in res)
             csize = sum(r.produced for r in res)
+            barrier(); E.sync()
             E.event(0); E.relaunch(); E.event(1); E.sync()
-            ms = E.elapsed_ms(0, 1)
-            row = {"value": round(n / 1e6 / ms, 3), "unit": "GB/s", "ms": round(ms, 2), "ratio": round(n / csize, 4)}
+            ms = allmax(E.elapsed_ms(0, 1))
+            lz_ms = E.elapsed_ms(9, 10)
+            row = {"value": round(nall * S / 1e6 / ms, 3), "unit": "GB/s", "ms": round(ms, 2), "ratio": round(n / csize, 4),
+                   "roofline": {"bound": "hbm", "kernel": "zs_lzc_kernel", "achieved": round((n + csize) / 1e6 / lz_ms, 2), "peak": peak, "unit": "GB/s",
+                                "frac": round((n + csize) / 1e6 / lz_ms / peak, 5), "kernel_ms": round(lz_ms, 2), "algorithmic_bytes": int(n + csize)}}
             if refimpl.have_ref():
                 R = refimpl.ref()
-                k = 64
-                ref_c = sum(len(R.compress(x[i * S:(i + 1) * S], S, level)[1]) for i in range(k))
+                k = min(64, nbuf)
+                ref_c = sum(len(R.compress(x[i * S:(i + 1) * S], S, level)[1]) for i in range(k)) if rank == 0 else 1
                 ours = sum(res[i].produced for i in range(k))
-                row["size_vs_reference"] = round(ours / ref_c, 4)
-                # every one of the 4096 streams through the reference's own zsc_uncompress (host threads, untimed)
+                if rank == 0:
+                    row["size_vs_reference"] = round(ours / ref_c, 4)
+                # every stream of this rank through the reference's own zsc_uncompress (host threads, untimed)
                 comp_all = E.download(1, 0, nbuf * slot)
                 rets, prods, outb = refimpl.ref_uncompress_batch(comp_all, [i * slot for i in range(nbuf)], [r.produced for r in res], [S] * nbuf)
                 okn = sum(1 for i in range(nbuf) if rets[i] == 0 and prods[i] == S)
                 same = bool(np.array_equal(outb, x))
-                row["parity"] = f"reference inflates {okn}/{nbuf} streams" + (", all bytes equal the inputs" if same else ", BYTES MISMATCH")
+                row["parity"] = f"reference inflates {okn}/{nbuf} streams of rank 0" + (", all bytes equal the inputs" if same else ", BYTES MISMATCH")
             out[str(level)] = row
-        return {"workload": "configs[2]: 4096 x 256 KiB telemetry-like buffers, one zlib stream each", "levels": out}
+        res_line = {"workload": "configs[2]: 4096 x 256 KiB telemetry-like buffers, one zlib stream each", "scaling": "strong", "buffers_per_rank": nbuf, "levels": out}
+        if rank == 0 and refimpl.have_ref():
+            cores = os.cpu_count() or 1
+            k = min(nbuf, max(cores, 32))
+            dt, _ = ref_batch(0, x, [i * S for i in range(k)], [S] * k, [slot] * k, cores, level=6)
+            res_line["cpu_baseline"] = {"value": round(k * S / 1e9 / dt, 4), "unit": "GB/s", "cores": cores, "kind": "reference", "level": 6,
+                                        "sample": f"the first {k} buffers through the reference's zsc_compress2 at level 6, one pthread per core"}
+        return res_line
     finally:
         E.close()
+
+
+def canterbury_config0(device):
+    """BASELINE configs[0], the reference's own Performance test (test/zlib_gtest.cpp:2400-2892): 11 Canterbury-shaped
+    buffers, max_block_len 100 000, level 6, zsc_compress then zsc_uncompress — through the zsc_pub.h entry points
+    themselves on ordinary (pageable) host buffers, timed per call with the host clock, next to the reference on one
+    host thread in the same run.  At these sizes a call is launch- and latency-bound on the GPU; the line says so."""
+    from zsc_b200 import datagen, zsc
+    import refimpl
+    Z = zsc()
+    R = refimpl.ref() if refimpl.have_ref() else None
+    bufs = datagen.canterbury_shaped()
+    Z.compress(bufs[0], 100000, 6)                       # first call initialises the process-wide engine
+    rows, tot = [], {"gpu_c": 0.0, "gpu_u": 0.0, "ref_c": 0.0, "ref_u": 0.0, "size": 0, "ref_size": 0, "bytes": 0}
+    ok = True
+    for x in bufs:
+        t = time.perf_counter(); r, comp = Z.compress(x, 100000, 6); tc = time.perf_counter() - t
+        t = time.perf_counter(); r2, back, used = Z.uncompress(comp, len(x)); tu = time.perf_counter() - t
+        ok = ok and r == 0 and r2 == 0 and bool(np.array_equal(back, x))
+        row = {"bytes": len(x), "compressed": len(comp), "compress_ms": round(tc * 1e3, 3), "uncompress_ms": round(tu * 1e3, 3)}
+        tot["gpu_c"] += tc; tot["gpu_u"] += tu; tot["size"] += len(comp); tot["bytes"] += len(x)
+        if R is not None:
+            t = time.perf_counter(); rr, rcomp = R.compress(x, 100000, 6); rtc = time.perf_counter() - t
+            t = time.perf_counter(); rr2, rback, rused = R.uncompress(comp, len(x)); rtu = time.perf_counter() - t     # the reference inflates OUR stream
+            ok = ok and rr == 0 and rr2 == 0 and bool(np.array_equal(rback, x))
+            row.update({"ref_compressed": len(rcomp), "ref_compress_ms": round(rtc * 1e3, 3), "ref_uncompress_ms": round(rtu * 1e3, 3)})
+            tot["ref_c"] += rtc; tot["ref_u"] += rtu; tot["ref_size"] += len(rcomp)
+        rows.append(row)
+    out = {"workload": "configs[0]: 11 Canterbury-shaped buffers (2 810 784 B), max_block_len 100 000, level 6, zsc_compress + zsc_uncompress on pageable host buffers",
+           "compress_MBps": round(tot["bytes"] / 1e6 / tot["gpu_c"], 1), "uncompress_MBps": round(tot["bytes"] / 1e6 / tot["gpu_u"], 1),
+           "compressed_bytes": tot["size"], "parity": "round trip bit-exact; the reference inflates every stream" if ok else "MISMATCH", "buffers": rows}
+    if R is not None:
+        out["cpu_baseline"] = {"compress_MBps": round(tot["bytes"] / 1e6 / tot["ref_c"], 1), "uncompress_MBps": round(tot["bytes"] / 1e6 / tot["ref_u"], 1),
+                               "cores": 1, "kind": "reference", "sample": "the same 11 calls through the reference on one host thread", "compressed_bytes": tot["ref_size"]}
+        out["size_vs_reference"] = round(tot["size"] / tot["ref_size"], 4)
+        out["verdict"] = ("GPU slower than one host core on this shape: calls of 4 KB - 1 MB are bound by launch latency, the PCIe round trip and one CTA per "
+                          "100 000-byte section" if tot["gpu_c"] > tot["ref_c"] else "GPU faster than one host core on this shape")
+    return out
+
+
+def checksums_config4(device, rank, world, barrier, allmax, peak):
+    """BASELINE configs[4], first half: adler32 / crc32 over 8 GiB of uniform-random bytes (seed 5), sharded over the
+    ranks in contiguous ranges and combined on the host (zscgpu_adler32_combine / zscgpu_crc32_combine); on one GPU the
+    8 GiB are additionally checked as 8 shards + combine.  Bit-exact against Python's zlib on a strided sample and, for
+    the whole buffer, against the value combined from independently computed pieces."""
+    from zsc_b200 import Engine, datagen, shard
+    import zlib
+    total = 8 << 30
+    lo, hi = rank_range(total >> 20, rank, world)
+    n = (hi - lo) << 20
+    E = Engine(raw_bytes=n + (1 << 20), comp_bytes=1 << 20, deflate_batch_max=1 << 20, max_streams=64, max_chunks=64, device=device)
+    try:
+        piece = 1 << 30
+        host_a, host_c = 1, 0
+        for off in range(0, n, piece):
+            m = min(piece, n - off)
+            x = datagen.fill(m, 5 + ((lo << 20) + off) // piece, datagen.RANDOM)
+            E.upload(0, off, x)
+            if off == 0:
+                host_a, host_c = zlib.adler32(x[:64 << 20].tobytes()), zlib.crc32(x[:64 << 20].tobytes())
+        ok = E.adler32(0, min(n, 64 << 20)) == host_a and E.crc32(0, min(n, 64 << 20)) == host_c
+        res = {}
+        for name, fn, enq in (("adler32", E.adler32, E.L.zscgpu_adler32_enqueue), ("crc32", E.crc32, E.L.zscgpu_crc32_enqueue)):
+            v = fn(0, n)
+            ts = []
+            for _ in range(3):
+                barrier(); E.sync()
+                E.event(0); enq(E.h, 0, n); E.event(1); E.sync(); ts.append(allmax(E.elapsed_ms(0, 1)))
+            t = min(ts)
+            # the same value from 8 shards combined on the host
+            cuts = [i * (n // 8) + (i % 3) for i in range(8)] + [n]
+            acc = 1 if name == "adler32" else 0
+            for a_, b_ in zip(cuts[:-1], cuts[1:]):
+                acc = (shard.adler32_combine if name == "adler32" else shard.crc32_combine)(acc, fn(a_, b_ - a_), b_ - a_)
+            ok = ok and acc == v
+            res[name] = {"value": round(total / 1e6 / t, 1), "unit": "GB/s", "ms": round(t, 3), "rank0_value": int(v),
+                         "roofline": {"bound": "hbm", "achieved": round(n / 1e6 / t, 1), "peak": peak, "unit": "GB/s", "frac": round(n / 1e6 / t / peak, 4),
+                                      "algorithmic_bytes": n}}
+        out = {"workload": "configs[4]: adler32 / crc32 over 8 GiB of random bytes, contiguous shards per rank + host combine", "scaling": "strong",
+               "bytes_per_rank": n, "parity": "bit-exact with zlib on the first 64 MiB; whole-range value == 8 shards combined on the host" if ok else "MISMATCH", **res}
+        if rank == 0:
+            import refimpl
+            if refimpl.have_ref():
+                R = refimpl.ref()
+                y = datagen.fill(256 << 20, 5, datagen.RANDOM)
+                t0 = time.perf_counter(); R.adler32(y); ta = time.perf_counter() - t0
+                t0 = time.perf_counter(); R.crc32(y); tc = time.perf_counter() - t0
+                out["cpu_baseline"] = {"adler32": round(len(y) / 1e9 / ta, 3), "crc32": round(len(y) / 1e9 / tc, 3), "unit": "GB/s", "cores": 1, "kind": "reference",
+                                       "sample": "256 MiB through the reference's adler32_z / crc32_z on one host thread"}
+        return out
+    finally:
+        E.close()
+
+
+def strategies_config4(E, data, n, st, cap):
+    """BASELINE configs[4], second half: the 1 GiB of configs[1] at Z_HUFFMAN_ONLY and Z_RLE (level 6), resident; size
+    against the reference's on the first 64 MiB, a 64 MiB prefix of each stream through the reference's inflate."""
+    import refimpl
+    out = {}
+    for name, strat in (("Z_HUFFMAN_ONLY", 2), ("Z_RLE", 3)):
+        E.deflate_enqueue(st, SECTION, 6, strat)
+        res = E.fetch(1)
+        assert res[0].ret == 0
+        ts = []
+        for _ in range(2):
+            E.event(0); E.relaunch(); E.event(1); E.sync(); ts.append(E.elapsed_ms(0, 1))
+        row = {"value": round(n / 1e6 / min(ts), 2), "unit": "GB/s", "ms": round(min(ts), 2), "ratio": round(n / res[0].produced, 4)}
+        if refimpl.have_ref():
+            R = refimpl.ref()
+            m = 64 << 20
+            p = DeflateSample(E, data, m, strat)
+            rc, refc = R.compress(data[:m], SECTION, 6, strategy=strat)
+            rr, back, used = R.uncompress(p, m)
+            row["size_vs_reference"] = round(len(p) / len(refc), 4)
+            row["parity"] = "reference inflates the 64 MiB sample bit-exact" if rr == 0 and bool(np.array_equal(back, data[:m])) else "MISMATCH"
+        out[name] = row
+    return {"workload": "configs[4]: the 1 GiB of configs[1] at level 6, Z_HUFFMAN_ONLY / Z_RLE, device resident", **out}
+
+
+def DeflateSample(E, data, m, strat):
+    """the first m bytes of the resident buffer as their own stream at level 6 / `strat` -> compressed bytes"""
+    from zsc_b200 import Engine
+    st = Engine.make_streams([0], [m], [0], [m + (m >> 3) + 4096])
+    r = E.deflate(st, SECTION, 6, strat)[0]
+    assert r.ret == 0
+    return E.download(1, 0, r.produced)
+
+
+def one_stream_over_ranks(E, data_all_fn, rank, world, dist, local_rank):
+    """north_star / SURVEY 8e: ONE logical stream split over the GPUs by contiguous section ranges; every rank deflates
+    its range as a raw part, the parts are gathered on rank 0, concatenated behind a zlib header with the adler32s
+    folded on the host (zscgpu_adler32_combine), and the stitched stream goes through the reference's zsc_uncompress."""
+    import torch
+    from zsc_b200 import Engine, shard
+    import refimpl
+    total = 2 << 30                                          # a 2 GiB logical stream, 8192 sections
+    nsec = total // SECTION
+    lo, hi = shard.partition(nsec, world)[rank]
+    b0, b1 = shard.byte_range(lo, hi, SECTION, total)
+    x = data_all_fn(b0, b1)
+    n = b1 - b0
+    E.upload(0, 0, x)
+    cap = n + (n >> 3) + 4096
+    st = Engine.make_streams([0], [n], [0], [cap])
+    part = (1 if rank > 0 else 0) | (2 if rank < world - 1 else 0)
+    t0 = time.perf_counter()
+    r = E.deflate(st, SECTION, LEVEL, 0, 0, 15, part)[0]
+    dt = time.perf_counter() - t0
+    assert r.ret == 0
+    comp = E.download(1, 0, r.produced)
+    meta = torch.tensor([r.produced, r.check, n], dtype=torch.int64, device=f"cuda:{local_rank}")
+    metas = [torch.zeros_like(meta) for _ in range(world)]
+    dist.all_gather(metas, meta)
+    sizes = [int(m[0]) for m in metas]
+    mx = max(sizes)
+    buf = torch.zeros(mx, dtype=torch.uint8, device=f"cuda:{local_rank}")
+    buf[:r.produced] = torch.from_numpy(comp).to(buf.device)
+    bufs = [torch.zeros_like(buf) for _ in range(world)] if rank == 0 else None
+    dist.gather(buf, bufs, dst=0)                              # collection of the finished parts, not a data-path collective
+    if rank != 0:
+        return None
+    parts = [bufs[i][:sizes[i]].cpu().numpy().tobytes() for i in range(world)]
+    stream = np.frombuffer(shard.stitch(parts, [int(m[1]) for m in metas], [int(m[2]) for m in metas], LEVEL), np.uint8)
+    res = {"workload": f"one {total >> 30} GiB logical stream ({nsec} sections) split over {world} engines by section range, parts stitched on the host",
+           "compressed_bytes": int(len(stream)), "deflate_GBps_slowest_rank": round(n / 1e9 / dt, 2)}
+    if refimpl.have_ref():
+        whole = np.concatenate([data_all_fn(*shard.byte_range(l_, h_, SECTION, total)) for l_, h_ in shard.partition(nsec, world)])
+        rr, out, used = refimpl.ref().uncompress(stream, total)
+        res["parity"] = ("reference zsc_uncompress inflates the stitched stream bit-exact (adler32 trailer folded on the host)"
+                         if rr == 0 and used == len(stream) and bool(np.array_equal(out, whole)) else f"MISMATCH (reference returned {rr})")
+    return res
 
 
 def bind_to_gpu_numa_node(gpu):
@@ -288,7 +525,7 @@ def bind_to_gpu_numa_node(gpu):
 
 def run_gpu(args, rank, world, local_rank):
     numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
-    from zsc_b200 import Engine, datagen, DeflateParams, Result
+    from zsc_b200 import Engine, EngineConfig, datagen, DeflateParams, Result, lib, zsc
     dist = None
     if world > 1:
         import torch
@@ -309,6 +546,15 @@ def run_gpu(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def allsum(v):
+        if dist is None:
+            return v
+        import torch
+        t = torch.tensor([v], dtype=torch.float64, device=f"cuda:{local_rank}")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    peak, peak_src = measured_peak()
     n = GIB
     E = Engine(raw_bytes=n + (1 << 20), comp_bytes=n + (n >> 3) + (1 << 20), deflate_batch_max=n + (1 << 20),
                max_streams=8192, max_chunks=8192, device=local_rank)
@@ -320,7 +566,7 @@ def run_gpu(args, rank, world, local_rank):
     E.upload(0, 0, data)
     st = Engine.make_streams([0], [n], [0], [cap])
 
-    # ---- warm-up (also the parity spot-check of this very run) ----
+    # ---- warm-up ----
     E.deflate_enqueue(st, SECTION, LEVEL)
     res = E.fetch(1)
     assert res[0].ret == 0, f"deflate failed: {res[0].ret}"
@@ -344,8 +590,8 @@ def run_gpu(args, rank, world, local_rank):
     E.sync(); barrier()
     t_wall = time.perf_counter() - t_wall0
     total_ms = allmax(sum(step_ms))
-    # ---- timed: end to end through the host-buffer call ----
-    e2e_steps = max(1, min(args.steps, 3))
+    # ---- timed: end to end through the host-buffer call (pinned caller buffers) ----
+    e2e_steps = max(1, min(args.steps, 5))
     p = DeflateParams(SECTION, LEVEL, 0, 1, 15, 0)
     r1 = Result()
     launches_resident = int(E.L.zscgpu_launch_total(E.h)) - launches0
@@ -357,14 +603,52 @@ def run_gpu(args, rank, world, local_rank):
         rc = E.L.zscgpu_compress_host(E.h, dest.ctypes.data, cap, data.ctypes.data, n, C.byref(p), 0, C.byref(r1))
         assert rc == 0 and r1.ret == 0
     barrier()
-    e2e_s = allmax((time.perf_counter() - t0) / e2e_steps)
+    my_e2e_s = (time.perf_counter() - t0) / e2e_steps
+    e2e_s = allmax(my_e2e_s)
     launches = launches_resident + int(E.L.zscgpu_launch_total(E.h)) - launches1     # kernels inside the two timed regions
+    # per-rank host<->device rates, measured alone on this rank's buffers while every rank does the same (names the e2e limiter)
+    barrier(); t0 = time.perf_counter(); E.upload(0, 0, data); h2d_s = time.perf_counter() - t0
+    barrier(); t0 = time.perf_counter(); E.L.zscgpu_download(E.h, 1, dest.ctypes.data, 0, int(r1.produced)); d2h_s = time.perf_counter() - t0
+    copy_rates = {"h2d_GBps_per_rank_all_ranks_copying": round(n / 1e9 / allmax(h2d_s), 1),
+                  "d2h_GBps_per_rank_all_ranks_copying": round(int(r1.produced) / 1e9 / allmax(d2h_s), 1),
+                  "h2d_GBps_sum": round(world * n / 1e9 / allmax(h2d_s), 1)}
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    # ---- the zsc_pub.h call itself (zsc_compress on the process-wide engine), pageable and pinned caller buffers ----
+    api = None
+    try:
+        cfg = EngineConfig()
+        lib().zscgpu_default_config(C.byref(cfg))
+        cfg.device = local_rank
+        lib().zscgpu_global_init(C.byref(cfg))
+        Z = zsc()
+        wl = Z.compress_work_size()[1]
+        work = np.empty(wl, np.uint8)
+        src_pageable = data.copy() if world == 1 else None       # a fresh allocation nobody registered
+        dst_pageable = np.empty(cap, np.uint8) if world == 1 else None
+        api = {}
+        for name, sbuf, dbuf in (("pinned", data, dest), ("pageable", src_pageable, dst_pageable)):
+            if sbuf is None:
+                continue
+            dl = C.c_uint32(cap)
+            args_ = (dbuf.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(dl), sbuf.ctypes.data_as(C.POINTER(C.c_uint8)), n, SECTION,
+                     work.ctypes.data_as(C.POINTER(C.c_uint8)), wl, LEVEL)
+            assert Z.L.zsc_compress(*args_) == 0                  # warm
+            barrier(); t0 = time.perf_counter()
+            for _ in range(2):
+                dl.value = cap
+                assert Z.L.zsc_compress(*args_) == 0
+            barrier()
+            api[name] = round(world * n / 1e9 / allmax((time.perf_counter() - t0) / 2), 3)
+        api["what"] = "zsc_compress (zsc_pub.h) on the process-wide engine, 1 GiB per call and rank, caller buffers pinned / ordinary pageable memory"
+        lib().zscgpu_global_shutdown()
+    except Exception as ex:  # pragma: no cover
+        api = {"error": repr(ex)}
 
     # ---- the way back: this run's own stream through the section-parallel inflate, resident and end to end ----
     inflate = None
     try:
-        if world > 1:
-            raise NotImplementedError
         comp = dest[:r1.produced]
         back = np.empty(n, dtype=np.uint8)
         E.L.zscgpu_host_register(back.ctypes.data, back.nbytes)
@@ -385,26 +669,12 @@ def run_gpu(args, rank, world, local_rank):
         barrier(); inf_e2e_s = allmax((time.perf_counter() - t0) / 2)
         inflate = {"value": round(world * n / 1e9 / inf_s, 3), "unit": "GB/s of output",
                    "e2e": round(world * n / 1e9 / inf_e2e_s, 3),
-                   "what": "the 1 GiB stream this run produced (4096 sections) back through zscgpu_inflate_sectioned / zscgpu_uncompress_host",
+                   "what": "the 1 GiB stream this run produced (4096 sections) back through zscgpu_inflate_sectioned / zscgpu_uncompress_host, per rank",
                    "parity": "bit-exact with the input" if bool(np.array_equal(back, data)) else "MISMATCH"}
-    except NotImplementedError:
-        inflate = {"value": None, "note": "side measurement, taken at N=1 only"}
+        E.L.zscgpu_host_unregister(back.ctypes.data)
+        del back
     except Exception as ex:  # pragma: no cover
         inflate = {"value": None, "error": repr(ex)}
-    sampler.stop_flag = True
-    sampler.join(timeout=2)
-    levels = None
-    if world == 1 and not args.no_inflate_batch:
-        try:
-            levels = deflate_config2(local_rank)
-        except Exception as ex:  # pragma: no cover
-            levels = {"error": repr(ex)}
-    inflate4 = None
-    if world == 1 and not args.no_inflate_batch:
-        try:
-            inflate4 = inflate_config4(local_rank)
-        except Exception as ex:  # pragma: no cover
-            inflate4 = {"value": None, "error": repr(ex)}
 
     # ---- parity of this run's output: the whole 1 GiB stream (4096 sections, header, adler32 trailer) through the
     # reference's own zsc_uncompress, outside the timed regions; Python's zlib when oracle/_ref is absent ----
@@ -422,16 +692,49 @@ def run_gpu(args, rank, world, local_rank):
             parity = "python zlib inflates the whole stream bit-exact (oracle/_ref absent)" if okp else "MISMATCH"
     except Exception as ex:  # pragma: no cover
         parity = f"check failed: {ex!r}"
+    parity_ok = allsum(0.0 if parity.startswith("MISMATCH") or parity.startswith("check failed") else 1.0)
+
+    side = {}
+    if not args.no_side:
+        # configs[4] second half on the resident 1 GiB (N = 1), then the engine of the headline leg is released
+        if world == 1:
+            try:
+                side["strategies"] = strategies_config4(E, data, n, st, cap)
+            except Exception as ex:  # pragma: no cover
+                side["strategies"] = {"error": repr(ex)}
+        if world > 1:
+            try:
+                E.L.zscgpu_host_unregister(data.ctypes.data)
+                side["one_stream_over_ranks"] = one_stream_over_ranks(
+                    E, lambda b0, b1: _slice_mixed(datagen, 77, b0, b1), rank, world, dist, local_rank)
+            except Exception as ex:  # pragma: no cover
+                side["one_stream_over_ranks"] = {"error": repr(ex)}
+    E.close()
+    del dest
+    if not args.no_side:
+        for key, fn in (("deflate_levels_6_9", deflate_config2), ("inflate_batched", inflate_config3), ("checksums", checksums_config4)):
+            try:
+                side[key] = fn(local_rank, rank, world, barrier, allmax, peak)
+            except Exception as ex:  # pragma: no cover
+                side[key] = {"error": repr(ex)}
+        if world == 1:
+            try:
+                side["canterbury_shaped"] = canterbury_config0(local_rank)
+            except Exception as ex:  # pragma: no cover
+                side["canterbury_shaped"] = {"error": repr(ex)}
 
     if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
         return
     ms_per_step = total_ms / args.steps
     value = world * n / 1e9 / (ms_per_step / 1e3)
-    peak, peak_src = measured_peak()
     lz = sum(lz_ms) / len(lz_ms)
     alg_bytes = n + csize
     achieved = alg_bytes / 1e9 / (lz / 1e3)
     pk = [sum(p_[i] for p_ in parts) / len(parts) for i in range(5)]
+    if world > 1:
+        parity += f" (all {world} ranks)" if parity_ok == world else f" ({int(parity_ok)}/{world} ranks OK)"
     line = {
         "metric": METRIC, "value": round(value, 3), "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -441,20 +744,22 @@ def run_gpu(args, rank, world, local_rank):
                    "l2": "inputs (1 GiB) and symbol scratch (1.3 GiB) far exceed the 126 MB L2; no flush needed",
                    "parity": parity, "wall_s_timed_region": round(t_wall, 3),
                    "host_numa_node_of_rank0": numa},
-        "roofline": {"bound": "hbm", "kernel": "zs_lz_kernel<false>", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
-                     "frac": round(achieved / peak, 5), "traffic": ncu_traffic(), "peak_source": peak_src,
+        "roofline": {"bound": "hbm", "kernel": "zs_lz_kernel", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
+                     "frac": round(achieved / peak, 5), "traffic": ncu_traffic(), "traffic_source": "profiles/lz_kernel_traffic.json (ncu --set full of this kernel; see its commit field)",
+                     "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": int(alg_bytes), "kernel_ms": round(lz, 3),
                      "kernel_share_of_step": round(lz / ms_per_step, 4),
                      "stage_ms": {"adler32": round(pk[0], 3), "lz77": round(pk[1], 3), "block_codes": round(pk[2], 3),
                                   "offsets": round(pk[3], 3), "bitpack": round(pk[4], 3)}},
         "e2e": {"value": round(world * n / 1e9 / e2e_s, 3), "unit": "GB/s", "h2d_bytes_per_step": world * n,
-                "d2h_bytes_per_step": world * int(r1.produced), "api": "zscgpu_compress_host (the call behind zsc_compress), pinned host buffers"},
+                "d2h_bytes_per_step": world * int(r1.produced), "steps": e2e_steps,
+                "api": "zscgpu_compress_host (the call behind zsc_compress), pinned host buffers", "zsc_compress": api,
+                "copy_rates": copy_rates},
         "gpu_launches": launches,
         "inflate": inflate,
-        "inflate_batched": inflate4,
-        "deflate_levels_6_9": levels,
         "clocks": sampler.summary(),
     }
+    line.update(side)
     if world == 1 and not args.no_cpu_baseline:
         try:
             cores = os.cpu_count() or 1
@@ -468,9 +773,14 @@ def run_gpu(args, rank, world, local_rank):
         except Exception as ex:
             line["cpu_baseline"] = {"value": None, "unit": "GB/s", "cores": 0, "kind": "reference", "sample": f"unavailable: {ex!r}"}
     print(json.dumps(line), flush=True)
-    E.close()
     if dist is not None:
         dist.destroy_process_group()
+
+
+def _slice_mixed(datagen, seed, b0, b1):
+    """bytes [b0, b1) of the mixed workload with this seed (tools/datagen.c generates 1 MiB pieces from (seed, piece index))"""
+    piece = 1 << 20
+    return datagen.fill(-(-b1 // piece) * piece, seed, datagen.MIXED)[b0:b1].copy()
 
 
 def main():
@@ -480,7 +790,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="zsc_b200", choices=["zsc_b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-inflate-batch", action="store_true", help="skip the side measurements (configs[2] levels 6/9, configs[3] 16 GiB batched inflate)")
+    ap.add_argument("--no-side", "--no-inflate-batch", dest="no_side", action="store_true",
+                    help="skip the side legs (configs[0] Canterbury-shaped, configs[2] levels 6/9, configs[3] 16 GiB batched inflate, configs[4] checksums and strategies, one stream over N GPUs)")
     args = ap.parse_args()
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     if args.warmup < 3 and args.impl != "reference":

@@ -187,162 +187,6 @@ static cudaError_t zs_inflate_group_launch(cudaStream_t st, uint32_t n, const Zs
     return cudaGetLastError();
 }
 
-/* ======================= a lane per stream decodes, writer warps write =======================
- * Wide batches (thousands of streams).  Huffman decoding never looks at the output, so it can run ahead of the
- * writing: the 64 lanes of two decoder warps each own one stream and decode, in lockstep, bursts of up to ZX_Q symbols
- * into that stream's record queue (zi_fast_batch — the same accelerator the group kernel uses, but on 32 lanes of a
- * warp at once instead of one); the other warps of the CTA are writers: while the decoders fill one half of the
- * double-buffered queues, each writer warp empties the other half of the streams it owns (zw_emit<32>: offsets by
- * prefix sum, literals at once, matches coalesced).  A stream's batches are always written by the same warp, in order,
- * so a match can read what an earlier batch wrote.  Everything the accelerator does not take (block ends, the last
- * bytes of a buffer, errors, recovery) is done by the generic zi_step on the decoder lane itself, as in every other
- * form of the decoder — it writes its few bytes directly, and therefore only runs once the stream's previous batch
- * has been written (the lane sits out one phase).  Stored blocks are handed to the writers as one copy.
- * Finished lanes take the next stream of the batch from a global counter, so ragged batches stay balanced.
- * Results are those of the one-thread decoder by construction (zi_fast_batch and zi_step are the code tests/ pins). */
-#define ZX_DEC_WARPS 2
-#define ZX_STREAMS (ZX_DEC_WARPS * 32)
-#define ZX_WR_WARPS 14
-#define ZX_THREADS ((ZX_DEC_WARPS + ZX_WR_WARPS) * 32)
-#define ZX_Q 32
-
-struct ZxStream {
-    zi_tables T;
-    zi_aux X;
-    uint32_t q[2][ZX_Q];
-};
-struct ZxCtl {                        /* what a decoder lane hands to the writer of its stream, per phase parity */
-    uint8_t *out[2];                  /* the stream's output buffer (nullptr: a count-only stream, nothing is written) */
-    const uint8_t *in[2];             /* ... and input (stored blocks are copied from it) */
-    uint32_t cnt[2], base[2];         /* records in q[par] and the output position of the first */
-    uint32_t st_n[2], st_from[2], st_to[2];   /* a stored-block copy that precedes the records */
-};
-
-__global__ void __launch_bounds__(ZX_THREADS, 1)
-zs_inflate_lanes_kernel(uint32_t n, const ZsStream *__restrict__ streams, const uint8_t *__restrict__ comp,
-                        uint8_t *__restrict__ raw, int32_t wrap, int32_t *__restrict__ ret,
-                        uint32_t *__restrict__ produced, uint32_t *__restrict__ consumed,
-                        uint32_t *__restrict__ aux, uint32_t *__restrict__ next_stream)
-{
-    extern __shared__ __align__(16) unsigned char zx_smem_raw[];
-    ZxStream *W = reinterpret_cast<ZxStream *>(zx_smem_raw);
-    ZxCtl *ctl = reinterpret_cast<ZxCtl *>(zx_smem_raw + sizeof(ZxStream) * ZX_STREAMS);
-    ZwLut &lut = *reinterpret_cast<ZwLut *>(zx_smem_raw + sizeof(ZxStream) * ZX_STREAMS + sizeof(ZxCtl) * ZX_STREAMS);
-    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const bool decoder = warp < ZX_DEC_WARPS;
-    if (tid < 29) lut.len[tid] = zi_lut_len(tid);
-    if (tid >= 32 && tid < 62) lut.dist[tid - 32] = zi_lut_dist(tid - 32);
-    if (tid < ZX_STREAMS) { ZxCtl &c = ctl[tid]; c.cnt[0] = c.cnt[1] = 0; c.st_n[0] = c.st_n[1] = 0; }
-    __syncthreads();
-
-    zi_mach m;
-    bool have = false, more = true;   /* this lane owns a stream / the batch may still have unclaimed streams */
-    uint32_t sid = 0;
-    uint32_t last_emit = 0xFFFFFFF0u; /* phase in which this lane last handed a batch to its writer */
-    uint8_t *s_out = nullptr;        /* output and input of the lane's stream */
-    const uint8_t *s_in = nullptr;
-    m.state = ZM_DONE;
-
-    for (uint32_t phase = 0;; phase++) {
-        const uint32_t par = phase & 1u;
-        int alive = 0;
-        if (decoder) {
-            ZxStream &w = W[tid];
-            ZxCtl &c = ctl[tid];
-            bool emitted = false;
-            c.cnt[par] = 0; c.st_n[par] = 0;          /* this half was drained during the previous phase */
-            /* a bounded number of machine steps per phase; a lane stops early once it has handed over a batch */
-            for (int it = 0; it < 8; it++) {
-                if (!have) {
-                    if (!more) break;
-                    sid = atomicAdd(next_stream, 1u);
-                    if (sid >= n) { more = false; break; }
-                    const ZsStream st = streams[sid];
-                    zi_m_init(&m, comp + st.comp_off, st.comp_cap, raw + st.raw_off, st.raw_len, wrap, &w.T, &w.X);
-                    const uint32_t sopt = st.chunk_first;              /* section options, see zs_inflate_group_kernel */
-                    m.opts = sopt & 3u;
-                    if ((sopt & 4u) && m.state == ZM_HEAD) m.state = ZM_BLOCK;
-                    s_out = (sopt & ZI_OPT_COUNT_ONLY) ? nullptr : raw + st.raw_off; s_in = comp + st.comp_off;
-                    have = true;
-                }
-                const int state = m.state;
-                if (state == ZM_DONE) {
-                    ret[sid] = m.res.ret; produced[sid] = m.res.produced; consumed[sid] = m.res.consumed;
-                    aux[2 * sid] = m.res.stored_check;
-                    aux[2 * sid + 1] = m.res.have_check | (m.res.data_errors ? 2u : 0u) | (m.res.at_flush ? 4u : 0u);
-                    have = false;
-                    if (emitted) break;                /* the next stream would reuse this half of the queue */
-                    continue;
-                }
-                if (state == ZM_SYM) {
-                    if (emitted) break;
-                    uint32_t vop = 0;
-                    const uint32_t base = m.io.op;
-                    const uint32_t cnt = zi_fast_batch(&m, lut.len, lut.dist, w.q[par], ZX_Q, &vop);
-                    if (cnt) {
-                        m.io.op = vop;
-                        c.cnt[par] = cnt; c.base[par] = base; c.out[par] = s_out; c.in[par] = s_in;
-                        emitted = true; last_emit = phase;
-                        if (cnt == ZX_Q) break;
-                    }
-                    if (cnt < ZX_Q) {
-                        /* the accelerator stopped in front of something: one generic step, which writes by itself and so
-                           needs every earlier batch of this stream written (handed over in phase p: written by the end of p + 1) */
-                        if (emitted || last_emit + 1 == phase) break;
-                        zi_step(&m);
-                    }
-                    continue;
-                }
-                if (state == ZM_STORED) {
-                    if (emitted) break;
-                    const uint32_t k = zi_stored_plan(&m);
-                    c.st_n[par] = k; c.st_from[par] = m.io.ip; c.st_to[par] = m.io.op;
-                    zi_stored_done(&m, k);
-                    if (k) { c.out[par] = s_out; c.in[par] = s_in; emitted = true; last_emit = phase; }
-                    continue;
-                }
-                if (state == ZM_COPY) {
-                    if (emitted || last_emit + 1 == phase) break;      /* writes by itself, see above */
-                    zi_step(&m);
-                    continue;
-                }
-                zi_step(&m);                           /* header, block header, trailer, recovery: no output */
-            }
-            alive = (have || emitted || more) ? 1 : 0;
-        } else if (phase > 0) {
-            /* writers: the half the decoders filled in the previous phase */
-            const uint32_t pp = par ^ 1u;
-            for (uint32_t s = warp - ZX_DEC_WARPS; s < ZX_STREAMS; s += ZX_WR_WARPS) {
-                const ZxCtl &c = ctl[s];
-                const uint32_t sn = c.st_n[pp], cnt = c.cnt[pp];
-                if (!(sn | cnt)) continue;
-                uint8_t *out = c.out[pp];
-                if (out == nullptr) continue;          /* count-only streams write nothing */
-                if (sn) {
-                    const uint8_t *src = c.in[pp] + c.st_from[pp];
-                    uint8_t *dst = out + c.st_to[pp];
-                    for (uint32_t k = lane; k < sn; k += 32) dst[k] = src[k];
-                    __syncwarp();
-                }
-                if (cnt) zw_emit<32>(out, c.base[pp], W[s].q[pp], cnt, lane, 0xFFFFFFFFu, 0u);
-            }
-        }
-        if (!__syncthreads_or(alive)) break;
-    }
-}
-
-static cudaError_t zs_inflate_lanes_launch(cudaStream_t st, uint32_t n, const ZsStream *streams, const uint8_t *comp, uint8_t *raw, int32_t wrap,
-                                           int32_t *ret, uint32_t *produced, uint32_t *consumed, uint32_t *aux, uint32_t *next_stream, int sms)
-{
-    const size_t smem = sizeof(ZxStream) * ZX_STREAMS + sizeof(ZxCtl) * ZX_STREAMS + sizeof(ZwLut);
-    cudaFuncSetAttribute(zs_inflate_lanes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaMemsetAsync(next_stream, 0, sizeof(uint32_t), st);
-    uint32_t grid = (n + ZX_STREAMS - 1) / ZX_STREAMS;
-    if (grid > (uint32_t)sms) grid = (uint32_t)sms;
-    zs_inflate_lanes_kernel<<<grid, ZX_THREADS, smem, st>>>(n, streams, comp, raw, wrap, ret, produced, consumed, aux, next_stream);
-    return cudaGetLastError();
-}
-
 __global__ void zs_inflate_check_kernel(uint32_t n, const ZsAdlerAcc *__restrict__ acc, const uint32_t *__restrict__ produced,
                                         const uint32_t *__restrict__ aux, int32_t wrap, int32_t *__restrict__ ret,
                                         uint32_t *__restrict__ check)
@@ -359,25 +203,22 @@ __global__ void zs_inflate_check_kernel(uint32_t n, const ZsAdlerAcc *__restrict
 extern "C" cudaError_t zs_adler_streams_launch(cudaStream_t st, uint32_t n, uint32_t max_len, const uint8_t *raw,
                                                const ZsStream *streams, const uint32_t *produced, ZsAdlerAcc *acc);
 
-#ifndef ZS_INFLATE_LANES_MIN
-#define ZS_INFLATE_LANES_MIN 6145u               /* streams in a batch from which the lane-per-stream kernel takes over */
-#endif
 extern "C" cudaError_t zs_inflate_launch(cudaStream_t st, uint32_t n, const ZsStream *streams, const uint8_t *comp,
                                          uint8_t *raw, int32_t wrap, int32_t *ret, uint32_t *produced,
                                          uint32_t *consumed, uint32_t *check, uint32_t *aux, ZsAdlerAcc *acc,
                                          uint32_t max_raw_len, int with_check, uint32_t *counter, int sms)
 {
     if (n == 0) return cudaSuccess;
-    uint32_t lanes_min = ZS_INFLATE_LANES_MIN;
-#ifdef ZSC_TUNING
-    if (getenv("ZSC_B200_INFLATE_LANES_MIN")) lanes_min = (uint32_t)atoi(getenv("ZSC_B200_INFLATE_LANES_MIN"));
-#endif
+    (void)counter; (void)sms;
     /* a warp per stream while that fills the machine (148 SMs x 32 warps), two streams per warp beyond: both
        leaders of a warp decode at the same time, the decode cost per symbol halves.  Smaller groups measured
        slower (8 lanes: 40 GB/s, 4 lanes: 25 GB/s against 54 GB/s at 65 536 streams): shared memory holds 64 streams per
-       SM whatever the group size, so fewer lanes per stream only mean fewer warps to hide latency with. */
-    cudaError_t ge = n >= lanes_min ? zs_inflate_lanes_launch(st, n, streams, comp, raw, wrap, ret, produced, consumed, aux, counter, sms)
-                     : n <= ZS_INFLATE_WARP_MAX ? zs_inflate_group_launch<32>(st, n, streams, comp, raw, wrap, ret, produced, consumed, aux)
+       SM whatever the group size, so fewer lanes per stream only mean fewer warps to hide latency with.  Also measured
+       and dropped (round 2, profiles/r02_exp_inflate_lanes_*.log): a lane per stream on a few decoder warps in lockstep
+       feeding writer warps through double-buffered queues — 4.4 instead of 15 warp-instructions per output byte, but
+       33-41 GB/s at 16 384 streams and 32 GB/s at 65 536: with 64 streams per SM there are too few decoder warps, and
+       every lockstep step pays the literal, the match and the refill path one after the other (1900 cycles a symbol). */
+    cudaError_t ge = n <= ZS_INFLATE_WARP_MAX ? zs_inflate_group_launch<32>(st, n, streams, comp, raw, wrap, ret, produced, consumed, aux)
                                               : zs_inflate_group_launch<16>(st, n, streams, comp, raw, wrap, ret, produced, consumed, aux);
     if (ge != cudaSuccess) return ge;
     if (!with_check) return cudaSuccess;               /* section passes: the caller checks the whole stream */
