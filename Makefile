@@ -22,10 +22,10 @@ build:
 build/%.o: zsc_b200/csrc/cuda/%.cu zsc_b200/csrc/cuda/common.cuh zsc_b200/csrc/cuda/lz_common.cuh zsc_b200/csrc/cuda/huff_build.h zsc_b200/csrc/cuda/inflate_core.h include/zscgpu.h | build
 	$(NVCC) $(NVFLAGS) -c $< -o $@
 
-build/zsc_api.o: zsc_b200/csrc/host/zsc_api.c include/zsc/zsc_pub.h include/zscgpu.h | build
+build/zsc_%.o: zsc_b200/csrc/host/zsc_%.c include/zsc/zsc_pub.h include/zsc/zlib.h include/zscgpu.h | build
 	$(CC) $(CFLAGS) -c $< -o $@
 
-$(LIB): $(CU_OBJS) build/zsc_api.o
+$(LIB): $(CU_OBJS) build/zsc_api.o build/zsc_stream.o
 	$(NVCC) $(ARCH) -shared -o $@ $^ -Xlinker -Bsymbolic -cudart static -lpthread
 
 testlibs: tests/libzsc_cpuharness.so tools/libzscgen.so

@@ -91,6 +91,9 @@ typedef struct {
                                 part (the last section ends with a full-flush marker, no final block and no
                                 trailer).  Parts concatenate byte-wise; result.check is the part's own
                                 adler32, to be folded with zscgpu_adler32_combine. */
+    uint32_t hist_len;       /* preset dictionary / history: this many bytes (<= 32768) directly in front of every
+                                stream's raw_off belong to the match window of its first section (deflateSetDictionary
+                                and the chunk-by-chunk deflate() of the streaming API; 0 otherwise) */
 } zscgpu_deflate_params;
 
 void zscgpu_default_config(zscgpu_config *cfg);
@@ -162,6 +165,25 @@ int zscgpu_uncompress_host(zscgpu_engine *e, uint8_t *dest, uint32_t dest_cap, c
                            uint32_t src_len, int32_t wrap, zscgpu_result *res);
 int zscgpu_checksum_host(zscgpu_engine *e, int kind, uint32_t init, const uint8_t *buf, uint64_t len,
                          uint32_t *out);
+
+/* The z_stream API's inflate (reference include/zsc/zlib.h:303 inflate, :818 inflateSetDictionary, :856 inflateSync): the
+ * decoder state of a stream lives in one of a fixed pool of device slots between calls.  A step stages `in_len` new
+ * input bytes behind the `in_left` bytes the previous step left unread, decodes until the input runs out, `out_cap`
+ * bytes are produced, the stream ends or an error stops it, and copies the produced bytes to `out`.
+ * status: 0 more input needed, 1 output full, 2 stream end (trailer read: stored_check / have_check), 3 data error
+ * (the stream waits for zscgpu_inflate_stream_sync), 4 preset dictionary needed (stored_check = its adler32),
+ * 5 flush point found (sync only).  in_pos = bytes of the staged input (in_left + in_len) that were used up. */
+typedef struct {
+    uint32_t status, in_pos, produced, adler, stored_check, have_check;
+} zscgpu_stream_step;
+#define ZSCGPU_STREAM_IN_MAX 65536u
+#define ZSCGPU_STREAM_OUT_MAX 32768u
+int zscgpu_inflate_stream_open(zscgpu_engine *e, int32_t wrap, int32_t *slot);      /* wrap as for zscgpu_inflate_batch */
+int zscgpu_inflate_stream_close(zscgpu_engine *e, int32_t slot);
+int zscgpu_inflate_stream_reset(zscgpu_engine *e, int32_t slot, int32_t wrap);
+int zscgpu_inflate_stream_step(zscgpu_engine *e, int32_t slot, const uint8_t *in, uint32_t in_len, uint32_t in_left,
+                               uint8_t *out, uint32_t out_cap, int32_t sync, zscgpu_stream_step *res);
+int zscgpu_inflate_stream_set_dict(zscgpu_engine *e, int32_t slot, const uint8_t *dict, uint32_t len);
 
 /* Checksums over raw-arena bytes [off, off+len): value continues from `init` (adler: 1, crc: 0 to start). */
 int zscgpu_adler32(zscgpu_engine *e, uint64_t off, uint64_t len, uint32_t init, uint32_t *out);

@@ -11,5 +11,6 @@ for f in deflate_lz deflate_chain deflate_huff checksum inflate engine; do
 done
 wait
 gcc -std=gnu11 -O2 -fPIC -Iinclude -c zsc_b200/csrc/host/zsc_api.c -o $d/zsc_api.o
+gcc -std=gnu11 -O2 -fPIC -Iinclude -c zsc_b200/csrc/host/zsc_stream.c -o $d/zsc_stream.o
 nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $d/libzsc_b200.so $d/*.o -Xlinker -Bsymbolic -cudart static -lpthread
 echo built $d/libzsc_b200.so

@@ -34,7 +34,7 @@ class Result(C.Structure):
 
 class DeflateParams(C.Structure):
     _fields_ = [("max_block_len", C.c_uint32), ("level", C.c_int32), ("strategy", C.c_int32),
-                ("wrap", C.c_int32), ("window_bits", C.c_int32), ("part", C.c_int32)]
+                ("wrap", C.c_int32), ("window_bits", C.c_int32), ("part", C.c_int32), ("hist_len", C.c_uint32)]
 
 
 class GzHeader(C.Structure):
@@ -56,6 +56,8 @@ ZSCGPU_SYMBOLS = [
     "zscgpu_adler32", "zscgpu_crc32", "zscgpu_adler32_enqueue", "zscgpu_crc32_enqueue",
     "zscgpu_event_record", "zscgpu_event_elapsed_ms", "zscgpu_debug_fetch_symbols",
     "zscgpu_adler32_combine", "zscgpu_crc32_combine",
+    "zscgpu_inflate_stream_open", "zscgpu_inflate_stream_close", "zscgpu_inflate_stream_reset", "zscgpu_inflate_stream_step",
+    "zscgpu_inflate_stream_set_dict",
 ]
 ZSC_SYMBOLS = [
     "zsc_compress_get_min_work_buf_size", "zsc_compress_get_min_work_buf_size2",
@@ -66,6 +68,43 @@ ZSC_SYMBOLS = [
     "zsc_uncompress", "zsc_uncompress_gzip", "zsc_uncompress2", "zsc_uncompress_gzip2",
     "adler32", "adler32_z", "crc32", "crc32_z", "zError", "zlibVersion",
 ]
+# the z_stream API (include/zsc/zlib.h)
+ZSTREAM_SYMBOLS = [
+    "deflateInit_", "deflateInit2_", "deflate", "deflateEnd", "deflateReset", "deflateSetDictionary", "deflateBoundNoStream",
+    "deflateWorkSize", "deflateWorkSize2", "inflateInit_", "inflateInit2_", "inflate", "inflateEnd", "inflateReset",
+    "inflateReset2", "inflateSetDictionary", "inflateSync", "inflateWorkSize", "inflateWorkSize2",
+]
+
+
+class ZStream(C.Structure):
+    """z_stream of include/zsc/zlib_types_pub.h (same layout as the reference's)"""
+    _fields_ = [("next_in", u8p), ("avail_in", C.c_uint32), ("total_in", C.c_uint32),
+                ("next_out", u8p), ("avail_out", C.c_uint32), ("total_out", C.c_uint32),
+                ("next_work", u8p), ("avail_work", C.c_uint32),
+                ("msg", C.c_char_p), ("state", C.c_void_p), ("data_type", C.c_int32), ("adler", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+def declare_zstream(L):
+    """argtypes of the z_stream API on a loaded library (ours or the reference's)"""
+    I, U, zp = C.c_int32, C.c_uint32, C.POINTER(ZStream)
+    L.deflateInit2_.argtypes = [zp, I, I, I, I, I, C.c_char_p, I]
+    L.deflate.argtypes = [zp, I]
+    L.deflateEnd.argtypes = [zp]
+    L.deflateReset.argtypes = [zp]
+    L.deflateSetDictionary.argtypes = [zp, u8p, U]
+    L.deflateWorkSize2.argtypes = [I, I, u32p]
+    L.inflateInit2_.argtypes = [zp, I, C.c_char_p, I]
+    L.inflate.argtypes = [zp, I]
+    L.inflateEnd.argtypes = [zp]
+    L.inflateReset.argtypes = [zp]
+    L.inflateSetDictionary.argtypes = [zp, u8p, U]
+    L.inflateSync.argtypes = [zp]
+    L.inflateWorkSize2.argtypes = [I, u32p]
+    for n in ("deflateInit2_", "deflate", "deflateEnd", "deflateReset", "deflateSetDictionary", "deflateWorkSize2",
+              "inflateInit2_", "inflate", "inflateEnd", "inflateReset", "inflateSetDictionary", "inflateSync", "inflateWorkSize2"):
+        getattr(L, n).restype = I
+    return L
+
 
 
 class _Tolerant:

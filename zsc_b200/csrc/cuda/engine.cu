@@ -28,7 +28,12 @@ extern "C" cudaError_t zs_crc_flat_launch(cudaStream_t, const uint8_t *, uint64_
 extern "C" cudaError_t zs_inflate_launch(cudaStream_t, uint32_t, const ZsStream *, const uint8_t *, uint8_t *, int32_t,
                                          int32_t *, uint32_t *, uint32_t *, uint32_t *, uint32_t *, ZsAdlerAcc *, uint32_t, int, uint32_t *, int);
 
+extern "C" cudaError_t zs_inflate_stream_launch(cudaStream_t, void *, uint8_t *, uint8_t *, uint32_t, uint32_t, int32_t, uint32_t *);
+extern "C" size_t zs_inflate_stream_slot_bytes(void);
+
 #define ZS_NEVENTS 16
+#define ZS_STREAM_SLOTS 16                       /* z_stream inflate states that can be open at a time */
+#define ZS_STREAM_HIST 32768u
 #define ZS_MAX_WAVES 64
 
 struct zscgpu_engine {
@@ -52,6 +57,9 @@ struct zscgpu_engine {
     ZsAdlerAcc *d_adler;              /* per stream; slot max_streams is the flat-checksum slot */
     uint32_t *d_crc;                  /* [2] */
     uint32_t *d_ctr;                  /* inflate: next unclaimed stream of the batch */
+    uint8_t *d_sslots, *d_sin, *d_sout;   /* streaming inflate: ZS_STREAM_SLOTS x (machine + tables | input staging | history + output staging) */
+    uint32_t *d_sres, *h_sres;        /* ... and the eight result words of a step */
+    bool sslot_used[ZS_STREAM_SLOTS];
     uint32_t *d_aux;                  /* inflate: [2 * max_streams] trailer check + flags */
     uint32_t *h_aux;                  /* the same on the host (section passes read the flags) */
     uint32_t *d_cand, *h_cand;        /* sectioned inflate: [max_streams + 1] positions behind 00 00 FF FF, slot 0 = count */
@@ -176,6 +184,11 @@ static int zs_init_engine(zscgpu_engine *e, const zscgpu_config &cfg, const cuda
     ZS_CUDA_CHECK(zs_dev(&e->d_adler, cfg.max_streams + 1));
     ZS_CUDA_CHECK(zs_dev(&e->d_crc, 4));
     ZS_CUDA_CHECK(zs_dev(&e->d_ctr, 16));
+    ZS_CUDA_CHECK(zs_dev(&e->d_sslots, ZS_STREAM_SLOTS * zs_inflate_stream_slot_bytes()));
+    ZS_CUDA_CHECK(zs_dev(&e->d_sin, (size_t)ZS_STREAM_SLOTS * (ZSCGPU_STREAM_IN_MAX + 256)));
+    ZS_CUDA_CHECK(zs_dev(&e->d_sout, (size_t)ZS_STREAM_SLOTS * (ZS_STREAM_HIST + ZSCGPU_STREAM_OUT_MAX + 256)));
+    ZS_CUDA_CHECK(zs_dev(&e->d_sres, 8 * ZS_STREAM_SLOTS));
+    ZS_CUDA_CHECK(zs_pinned(&e->h_sres, 8 * ZS_STREAM_SLOTS));
     ZS_CUDA_CHECK(zs_dev(&e->d_aux, 2ull * cfg.max_streams));
     ZS_CUDA_CHECK(zs_pinned(&e->h_aux, 2ull * cfg.max_streams));
     ZS_CUDA_CHECK(zs_dev(&e->d_cand, (size_t)cfg.max_streams + 1));
@@ -220,7 +233,7 @@ extern "C" void zscgpu_destroy(zscgpu_engine *e)
     cudaFreeHost(e->h_streams); cudaFree(e->d_streams);
     cudaFreeHost(e->h_blk_chunk); cudaFree(e->d_blk_chunk);
     cudaFree(e->d_chunk_nsym); cudaFree(e->d_blk_in_start); cudaFree(e->d_blocks); cudaFree(e->d_blk_meta); cudaFree(e->d_blk_bitoff); cudaFree(e->d_blk_scratch); cudaFree(e->d_blk_used);
-    cudaFree(e->d_adler); cudaFree(e->d_crc); cudaFree(e->d_ctr); cudaFree(e->d_aux); cudaFreeHost(e->h_aux); cudaFree(e->d_cand); cudaFreeHost(e->h_cand);
+    cudaFree(e->d_adler); cudaFree(e->d_crc); cudaFree(e->d_ctr); cudaFree(e->d_sslots); cudaFree(e->d_sin); cudaFree(e->d_sout); cudaFree(e->d_sres); cudaFreeHost(e->h_sres); cudaFree(e->d_aux); cudaFreeHost(e->h_aux); cudaFree(e->d_cand); cudaFreeHost(e->h_cand);
     free(e->sec_start); free(e->sec_st); free(e->sec_r1);
     cudaFree(e->d_ret); cudaFree(e->d_produced); cudaFree(e->d_consumed); cudaFree(e->d_check);
     cudaFreeHost(e->h_ret); cudaFreeHost(e->h_produced); cudaFreeHost(e->h_consumed); cudaFreeHost(e->h_check);
@@ -402,7 +415,7 @@ static ZsSlice zs_slice_half(zscgpu_engine *e, int h)
 }
 
 static int zs_build_deflate_desc(zscgpu_engine *e, const ZsSlice &sl, const zscgpu_stream *streams, uint32_t n, uint32_t mbl, int part,
-                                 uint32_t *nchunks_out, uint32_t *nblk_out)
+                                 uint32_t *nchunks_out, uint32_t *nblk_out, uint32_t hist_len = 0)
 {
     uint64_t sym = 0, total = 0;
     uint32_t nc = 0, nb = 0;
@@ -413,6 +426,10 @@ static int zs_build_deflate_desc(zscgpu_engine *e, const ZsSlice &sl, const zscg
             z->comp_off > e->cfg.comp_bytes || z->comp_len > e->cfg.comp_bytes - z->comp_off) {
             snprintf(e->err, sizeof(e->err), "stream %u lies outside the arenas", s);
             return ZSCGPU_ERR_CAPACITY;
+        }
+        if (hist_len > ZS_WINDOW || z->raw_off < hist_len) {
+            snprintf(e->err, sizeof(e->err), "stream %u: hist_len bytes must lie in front of raw_off (and be at most 32768)", s);
+            return ZSCGPU_ERR_ARG;
         }
         if (z->comp_off & 3u) {
             /* the offset pass clears and the bit packer ORs whole 32-bit words at a stream's first and last byte */
@@ -436,6 +453,7 @@ static int zs_build_deflate_desc(zscgpu_engine *e, const ZsSlice &sl, const zscg
                 C->sym_off = sym;
                 C->len = clen;
                 C->dict_len = coff < ZS_WINDOW ? coff : ZS_WINDOW;
+                if (pos == 0 && j == 0) C->dict_len = hist_len;      /* preset dictionary / history of a stream continued chunk by chunk */
                 C->blk_base = nb;
                 C->blk_cap = clen ? (clen + ZS_BLOCK_SYMS - 1) / ZS_BLOCK_SYMS : 1;
                 C->stream = s;
@@ -545,7 +563,7 @@ extern "C" int zscgpu_deflate_enqueue(zscgpu_engine *e, const zscgpu_stream *str
     if (zs_lz_params(p, &L, &chain)) { snprintf(e->err, sizeof(e->err), "bad level/strategy/wrap"); return ZSCGPU_ERR_ARG; }
     uint32_t nc = 0, nb = 0;
     const ZsSlice whole = zs_slice_whole(e);
-    int r = zs_build_deflate_desc(e, whole, streams, n, p->max_block_len, p->part, &nc, &nb);
+    int r = zs_build_deflate_desc(e, whole, streams, n, p->max_block_len, p->part, &nc, &nb, p->hist_len);
     if (r) return r;
     static_assert(sizeof(ZsChunk) % 4 == 0 && sizeof(ZsStream) % 4 == 0, "descriptor structs are copied as words");
     ZS_CUDA_CHECK(zs_desc_fetch(e, whole, n, nc, nb));
@@ -917,7 +935,7 @@ extern "C" int zscgpu_compress_host(zscgpu_engine *e, uint8_t *dest, uint32_t de
     }
     /* waves of whole sections when the buffer is large enough to make overlap pay: at least 64 MiB each and,
        since the LZ kernel runs one chunk per SM at a time, a chunk count that is a multiple of 2 x SMs */
-    if (p->max_block_len != 0 && src_len >= (128u << 20)) {
+    if (p->max_block_len != 0 && src_len >= (128u << 20) && p->hist_len == 0) {
         const uint64_t mbl = p->max_block_len;
         const uint64_t cps = (mbl + ZS_CHUNK_MAX - 1) / ZS_CHUNK_MAX;                 /* chunks per section */
         const uint64_t round_secs = (2ull * (uint64_t)e->sms + cps - 1) / cps;       /* sections in one round of chunks (two CTAs per SM); two and three rounds per wave measured slower */
@@ -932,10 +950,11 @@ extern "C" int zscgpu_compress_host(zscgpu_engine *e, uint8_t *dest, uint32_t de
         if (nw >= 2 && fits && need <= e->cfg.comp_bytes && dest_cap > comp_skip)
             return zs_compress_host_waves(e, dest, dest_cap, src, src_len, p, comp_skip, res, W, (uint32_t)nw);
     }
+    if (p->hist_len > src_len) { snprintf(e->err, sizeof(e->err), "hist_len exceeds the source"); return ZSCGPU_ERR_ARG; }
     int r = zscgpu_upload_async(e, 0, 0, src, src_len); if (r) return r;
     zscgpu_stream st;
     const uint32_t dskip = (comp_skip + 3u) & ~3u;          /* where the stream lies in the comp arena (word aligned) */
-    st.raw_off = 0; st.raw_len = src_len; st.comp_off = dskip;
+    st.raw_off = p->hist_len; st.raw_len = src_len - p->hist_len; st.comp_off = dskip;     /* src = history, then the data */
     uint64_t cap = dest_cap > comp_skip ? dest_cap - comp_skip : 0;
     if (cap > e->cfg.comp_bytes - dskip) cap = e->cfg.comp_bytes - dskip;
     st.comp_len = (uint32_t)cap;
@@ -988,6 +1007,89 @@ extern "C" int zscgpu_checksum_host(zscgpu_engine *e, int kind, uint32_t init, c
         done += n;
     } while (done < len);
     *out = v;
+    return ZSCGPU_OK;
+}
+
+/* ----------------------------- z_stream inflate: resumable decoder slots ----------------------------- */
+static int zs_sslot(zscgpu_engine *e, int32_t slot)
+{
+    if (slot < 0 || slot >= ZS_STREAM_SLOTS || !e->sslot_used[slot]) { snprintf(e->err, sizeof(e->err), "bad stream slot %d", slot); return ZSCGPU_ERR_ARG; }
+    return ZSCGPU_OK;
+}
+#define ZS_SSLOT_PTRS(e, slot) \
+    void *sp = (e)->d_sslots + (size_t)(slot) * zs_inflate_stream_slot_bytes(); \
+    uint8_t *sin = (e)->d_sin + (size_t)(slot) * (ZSCGPU_STREAM_IN_MAX + 256); \
+    uint8_t *sout = (e)->d_sout + (size_t)(slot) * (ZS_STREAM_HIST + ZSCGPU_STREAM_OUT_MAX + 256); \
+    uint32_t *dres = (e)->d_sres + 8 * (slot), *hres = (e)->h_sres + 8 * (slot)
+
+extern "C" int zscgpu_inflate_stream_reset(zscgpu_engine *e, int32_t slot, int32_t wrap)
+{
+    std::lock_guard<std::mutex> lk(e->mu);
+    ZS_ENTER(e);
+    int r = zs_sslot(e, slot); if (r) return r;
+    ZS_SSLOT_PTRS(e, slot);
+    (void)hres;
+    ZS_CUDA_CHECK(zs_inflate_stream_launch(e->stream, sp, sin, sout, 0, (uint32_t)wrap, 2, dres));
+    ZS_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    e->launches_total += 1;
+    return ZSCGPU_OK;
+}
+extern "C" int zscgpu_inflate_stream_open(zscgpu_engine *e, int32_t wrap, int32_t *slot)
+{
+    if (!slot || (wrap & 0xFF) > 1 || wrap < 0) return ZSCGPU_ERR_ARG;
+    {
+        std::lock_guard<std::mutex> lk(e->mu);
+        int s = 0;
+        while (s < ZS_STREAM_SLOTS && e->sslot_used[s]) s++;
+        if (s == ZS_STREAM_SLOTS) { snprintf(e->err, sizeof(e->err), "all %d stream slots are open", ZS_STREAM_SLOTS); return ZSCGPU_ERR_CAPACITY; }
+        e->sslot_used[s] = true;
+        *slot = s;
+    }
+    return zscgpu_inflate_stream_reset(e, *slot, wrap);
+}
+extern "C" int zscgpu_inflate_stream_close(zscgpu_engine *e, int32_t slot)
+{
+    std::lock_guard<std::mutex> lk(e->mu);
+    int r = zs_sslot(e, slot); if (r) return r;
+    e->sslot_used[slot] = false;
+    return ZSCGPU_OK;
+}
+extern "C" int zscgpu_inflate_stream_step(zscgpu_engine *e, int32_t slot, const uint8_t *in, uint32_t in_len, uint32_t in_left,
+                                          uint8_t *out, uint32_t out_cap, int32_t sync, zscgpu_stream_step *res)
+{
+    std::lock_guard<std::mutex> lk(e->mu);
+    ZS_ENTER(e);
+    int r = zs_sslot(e, slot); if (r) return r;
+    if (!res || (uint64_t)in_left + in_len > ZSCGPU_STREAM_IN_MAX || out_cap > ZSCGPU_STREAM_OUT_MAX || (in_len && !in) || (out_cap && !out)) {
+        snprintf(e->err, sizeof(e->err), "bad stream step arguments");
+        return ZSCGPU_ERR_ARG;
+    }
+    ZS_SSLOT_PTRS(e, slot);
+    if (in_len) ZS_CUDA_CHECK(cudaMemcpyAsync(sin + in_left, in, in_len, cudaMemcpyHostToDevice, e->stream));
+    ZS_CUDA_CHECK(zs_inflate_stream_launch(e->stream, sp, sin, sout, in_left + in_len, out_cap, sync ? 1 : 0, dres));
+    ZS_CUDA_CHECK(cudaMemcpyAsync(hres, dres, 32, cudaMemcpyDeviceToHost, e->stream));
+    ZS_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    e->launches_total += 1;
+    res->status = hres[0]; res->in_pos = hres[1]; res->produced = hres[2]; res->adler = hres[3];
+    res->stored_check = hres[4]; res->have_check = hres[5];
+    if (res->produced) {
+        ZS_CUDA_CHECK(cudaMemcpyAsync(out, sout + ZS_STREAM_HIST, res->produced, cudaMemcpyDeviceToHost, e->stream));
+        ZS_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    }
+    return ZSCGPU_OK;
+}
+extern "C" int zscgpu_inflate_stream_set_dict(zscgpu_engine *e, int32_t slot, const uint8_t *dict, uint32_t len)
+{
+    std::lock_guard<std::mutex> lk(e->mu);
+    ZS_ENTER(e);
+    int r = zs_sslot(e, slot); if (r) return r;
+    if (!dict || len > ZS_STREAM_HIST) { snprintf(e->err, sizeof(e->err), "bad dictionary"); return ZSCGPU_ERR_ARG; }
+    ZS_SSLOT_PTRS(e, slot);
+    (void)hres;
+    if (len) ZS_CUDA_CHECK(cudaMemcpyAsync(sout + ZS_STREAM_HIST - len, dict, len, cudaMemcpyHostToDevice, e->stream));
+    ZS_CUDA_CHECK(zs_inflate_stream_launch(e->stream, sp, sin, sout, 0, len, 3, dres));
+    ZS_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    e->launches_total += 1;
     return ZSCGPU_OK;
 }
 

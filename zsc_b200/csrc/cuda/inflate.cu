@@ -11,6 +11,8 @@
 #include "common.cuh"
 #include "inflate_core.h"
 
+#define ZSI_HIST 32768u                           /* history kept in front of a streaming slot's output staging */
+
 #ifndef ZS_INFLATE_WARP_MAX
 #define ZS_INFLATE_WARP_MAX 6144u                /* streams in a batch up to which each gets a whole warp */
 #endif
@@ -199,6 +201,158 @@ __global__ void zs_inflate_check_kernel(uint32_t n, const ZsAdlerAcc *__restrict
     check[s] = v;
     if ((wrap & 0xFF) == 1 && ret[s] == 0 && (aux[2 * s + 1] & 1u) && aux[2 * s] != v) ret[s] = -3;   /* incorrect data check */
 }
+
+/* ======================= one z_stream, resumable (the streaming API: inflate / inflateSync) =======================
+ * The decoder state of a stream lives in a device slot between calls (machine, tables, up to ZSI_IN staged input
+ * bytes, 32 KiB of history in front of an output staging buffer).  A call runs the same state machine as everything
+ * else (zi_step) on one lane until the staged input runs out, the output staging is full, the stream ends, or an
+ * error stops it.  zi_step assumes all input and output present, so every step is taken on a copy of the machine and
+ * thrown away when it ends in "input ended" / "output full": a step never consumes half a symbol or half a header,
+ * which makes the machine resumable without touching the code the known-answer tests pin.  A data error is reported
+ * and the machine waits in ZM_RECOVER for inflateSync (the one-shot path recovers by itself; the z_stream API leaves
+ * that to the caller: reference src/inflate.c:1356-1360, :1547). */
+struct ZsInfSlot {
+    zi_mach m;
+    zi_tables T;
+    zi_aux X;
+};
+struct ZsInfStepArgs {
+    ZsInfSlot *slot;
+    uint8_t *in;            /* staging: in_have bytes */
+    uint8_t *out;           /* ZSI_HIST bytes of history, then the output staging */
+    uint32_t in_have, out_cap;
+    int32_t mode;           /* 0 inflate, 1 inflateSync (look for a flush point), 2 reset (wrap in out_cap), 3 dictionary of out_cap bytes installed */
+    uint32_t *res;          /* [8]: status, input position reached, produced, adler32 of the produced bytes, stored check / DICTID, have_check, new history length */
+};
+enum { ZSI_NEED_INPUT = 0, ZSI_OUTPUT_FULL = 1, ZSI_END = 2, ZSI_DATA_ERROR = 3, ZSI_NEED_DICT = 4, ZSI_SYNC_FOUND = 5 };
+
+__device__ __forceinline__ void zsi_move_down(uint8_t *dst, const uint8_t *src, uint32_t n, uint32_t lane)
+{
+    /* overlapping move towards lower addresses: every round loads before it stores */
+    for (uint32_t k0 = 0; k0 < n; k0 += 32) {
+        const uint32_t k = k0 + lane;
+        uint8_t b = 0;
+        if (k < n) b = src[k];
+        __syncwarp();
+        if (k < n) dst[k] = b;
+        __syncwarp();
+    }
+}
+
+__global__ void __launch_bounds__(32, 1) zs_inflate_stream_kernel(ZsInfStepArgs a)
+{
+    __shared__ zi_tables T;
+    __shared__ zi_aux X;
+    __shared__ uint32_t sh[4];
+    const uint32_t lane = threadIdx.x;
+    ZsInfSlot *slot = a.slot;
+    if (a.mode == 2) {
+        if (lane == 0) {
+            zi_mach m;
+            zi_m_init(&m, a.in, 0, a.out + ZSI_HIST, 0, (int)a.out_cap, nullptr, nullptr);
+            m.opts = ZI_OPT_STREAMING;
+            slot->m = m;
+        }
+        return;
+    }
+    if (a.mode == 3) {
+        if (lane == 0) {
+            slot->m.hist = a.out_cap;                       /* the bytes lie right in front of the output staging */
+            if (slot->m.state == ZM_DICT) slot->m.state = ZM_BLOCK;
+        }
+        return;
+    }
+    for (uint32_t i = lane; i < sizeof(zi_tables) / 4; i += 32) ((uint32_t *)&T)[i] = ((const uint32_t *)&slot->T)[i];
+    for (uint32_t i = lane; i < sizeof(zi_aux) / 4; i += 32) ((uint32_t *)&X)[i] = ((const uint32_t *)&slot->X)[i];
+    __syncwarp();
+    uint8_t *out = a.out + ZSI_HIST;
+    if (lane == 0) {
+        zi_mach m = slot->m;
+        m.T = &T; m.X = &X;
+        m.io.in = a.in; m.io.in_len = a.in_have; m.io.pv = 0;
+        m.io.out = out; m.io.out_cap = a.out_cap; m.io.op = 0; m.base = 0;
+        uint32_t status = ZSI_NEED_INPUT;
+        if (a.mode == 1 && m.state != ZM_DONE) {
+            /* inflateSync: search the staged input for 00 00 FF FF (zi_sync, the reference's syncsearch); the bits still
+               buffered are dropped first, as the reference's byte-aligned restart does */
+            uint32_t pos = m.io.ip - (m.io.bits >> 3);
+            if (pos > m.io.in_len) pos = m.io.in_len;
+            const uint32_t held = m.state == ZM_RECOVER ? m.held : 0u;
+            const uint32_t nx = zi_sync(m.io.in, m.io.in_len, pos >= held ? pos - held : 0u);
+            if (nx > m.io.in_len) {
+                /* not here: everything but a possible marker prefix is used up */
+                zi_seek(&m.io, m.io.in_len > 3 ? m.io.in_len - 3 : 0);
+                m.held = 0; m.state = ZM_RECOVER;
+                status = ZSI_DATA_ERROR;
+            } else {
+                zi_seek(&m.io, nx);
+                m.held = 0; m.hist = 0; m.win = 32768u; m.state = ZM_BLOCK;
+                status = ZSI_SYNC_FOUND;
+            }
+        } else {
+            for (;;) {
+                if (m.state == ZM_DONE) { status = (m.res.ret == ZI_OK) ? ZSI_END : ZSI_DATA_ERROR; break; }
+                if (m.state == ZM_DICT) { status = ZSI_NEED_DICT; break; }
+                if (m.state == ZM_RECOVER) { status = ZSI_DATA_ERROR; break; }
+                zi_mach snap = m;
+                zi_step(&m);
+                if (m.state == ZM_DONE && m.res.ret == ZI_BUF_ERROR) {
+                    const int why = m.res.last_reason;
+                    m = snap;                                   /* the step did not happen */
+                    status = (why == ZI_E_OUTPUT_FULL) ? ZSI_OUTPUT_FULL : ZSI_NEED_INPUT;
+                    break;
+                }
+            }
+        }
+        /* hand back the whole bytes still in the bit buffer; a partial byte stays in it */
+        uint32_t pos = m.io.ip - (m.io.bits >> 3);
+        if (pos > m.io.in_len) pos = m.io.in_len;
+        if (m.state == ZM_RECOVER && status == ZSI_DATA_ERROR && a.mode == 0) {
+            const uint32_t held = m.held < pos ? m.held : pos;  /* inflateSync starts its search at the bytes the reference still holds */
+            pos -= held; m.held = held;
+            m.io.hold = 0; m.io.bits = 0;
+        } else {
+            const uint32_t keep = m.io.bits & 7u;
+            m.io.hold &= (1ull << keep) - 1ull;
+            m.io.bits = keep;
+        }
+        m.io.ip = 0; m.io.pv = 0;
+        const uint32_t valid = m.io.op - m.base + m.hist;
+        const uint32_t nh = valid < ZSI_HIST ? valid : ZSI_HIST;
+        sh[0] = pos; sh[1] = m.io.op; sh[2] = nh; sh[3] = status;
+        a.res[0] = status; a.res[1] = pos; a.res[2] = m.io.op;
+        a.res[4] = m.res.stored_check; a.res[5] = m.res.have_check; a.res[6] = nh; a.res[7] = (uint32_t)m.res.ret;
+        m.hist = nh; m.base = 0;
+        if (m.state == ZM_RECOVER && a.mode == 0) m.io.ip = m.held;      /* the search of inflateSync starts `held` bytes into the leftover... */
+        slot->m = m;
+    }
+    __syncwarp();
+    const uint32_t pos = sh[0], produced = sh[1], nh = sh[2];
+    /* adler32 of the produced bytes (as a stream of its own; the host folds it into the running value) */
+    {
+        unsigned long long s1 = 0, s2 = 0;
+        for (uint32_t i = lane; i < produced; i += 32) { const uint32_t b = out[i]; s1 += b; s2 += (unsigned long long)(produced - i) * b; }
+        for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_down_sync(0xFFFFFFFFu, s1, o); s2 += __shfl_down_sync(0xFFFFFFFFu, s2, o); }
+        if (lane == 0) {
+            const uint32_t A = (uint32_t)((s1 + 1) % ZS_ADLER_BASE), B = (uint32_t)((s2 + produced) % ZS_ADLER_BASE);
+            a.res[3] = (B << 16) | A;
+        }
+    }
+    /* tables back to the slot; unread input to the front of the staging; the newest history in front of the output staging */
+    for (uint32_t i = lane; i < sizeof(zi_tables) / 4; i += 32) ((uint32_t *)&slot->T)[i] = ((const uint32_t *)&T)[i];
+    for (uint32_t i = lane; i < sizeof(zi_aux) / 4; i += 32) ((uint32_t *)&slot->X)[i] = ((const uint32_t *)&X)[i];
+    if (pos) zsi_move_down(a.in, a.in + pos, a.in_have - pos, lane);
+    if (produced) zsi_move_down(out - nh, out + produced - nh, nh, lane);
+}
+
+extern "C" cudaError_t zs_inflate_stream_launch(cudaStream_t st, void *slot, uint8_t *in, uint8_t *out, uint32_t in_have, uint32_t out_cap, int32_t mode, uint32_t *res)
+{
+    ZsInfStepArgs a;
+    a.slot = (ZsInfSlot *)slot; a.in = in; a.out = out; a.in_have = in_have; a.out_cap = out_cap; a.mode = mode; a.res = res;
+    zs_inflate_stream_kernel<<<1, 32, 0, st>>>(a);
+    return cudaGetLastError();
+}
+extern "C" size_t zs_inflate_stream_slot_bytes(void) { return sizeof(ZsInfSlot); }
 
 extern "C" cudaError_t zs_adler_streams_launch(cudaStream_t st, uint32_t n, uint32_t max_len, const uint8_t *raw,
                                                const ZsStream *streams, const uint32_t *produced, ZsAdlerAcc *acc);

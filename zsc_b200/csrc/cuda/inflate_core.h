@@ -382,7 +382,7 @@ ZID uint32_t zi_sync(const uint8_t *in, uint32_t in_len, uint32_t from)
  * LEN/NLEN, the 32-bit check value).  No bytes left and nothing held -> Z_BUF_ERROR; no marker ->
  * Z_DATA_ERROR with all input consumed; marker -> decoding continues behind it and output keeps
  * appending; a stream that needed any recovery ends as Z_DATA_ERROR. */
-enum { ZM_HEAD = 0, ZM_BLOCK, ZM_SYM, ZM_COPY, ZM_STORED, ZM_TRAIL, ZM_RECOVER, ZM_DONE };
+enum { ZM_HEAD = 0, ZM_BLOCK, ZM_SYM, ZM_COPY, ZM_STORED, ZM_TRAIL, ZM_RECOVER, ZM_DONE, ZM_DICT /* streaming: waiting for inflateSetDictionary */ };
 
 typedef struct {
     zi_io io;
@@ -392,11 +392,14 @@ typedef struct {
     int32_t state, wrap;
     uint32_t last, rem, dist, win, maxw, held;
     uint32_t base;          /* output position of the last resynchronisation: no distance may reach behind it */
+    uint32_t hist;          /* streaming: valid bytes in front of out[0] (earlier calls' output or a preset dictionary) */
     uint32_t opts;          /* ZI_OPT_*: section-parallel decoding of one stream (engine.cu zs_inflate_sectioned) */
 } zi_mach;
 
 #define ZI_OPT_COUNT_ONLY 1u        /* advance the output position without writing (sizes of the sections) */
 #define ZI_OPT_STOP_AT_FLUSH 2u     /* end, successfully, behind the first empty non-final stored block */
+#define ZI_OPT_STREAMING 8u         /* the z_stream API (zs_inflate_stream_kernel): a preset-dictionary header waits in ZM_DICT
+                                       instead of ending the stream with Z_NEED_DICT (4 is taken by the kernels' section flag) */
 
 ZID void zi_m_init(zi_mach *m, const uint8_t *in, uint32_t in_len, uint8_t *out, uint32_t out_cap, int wrap, zi_tables *T, zi_aux *X)
 {
@@ -408,7 +411,7 @@ ZID void zi_m_init(zi_mach *m, const uint8_t *in, uint32_t in_len, uint8_t *out,
     m->maxw = ((wrap >> 8) & 0xFF) ? (uint32_t)((wrap >> 8) & 0xFF) : 15u;
     m->wrap = wrap & 0xFF;
     m->win = 1u << m->maxw;
-    m->T = T; m->X = X; m->last = 0; m->rem = 0; m->dist = 0; m->held = 0; m->opts = 0; m->base = 0;
+    m->T = T; m->X = X; m->last = 0; m->rem = 0; m->dist = 0; m->held = 0; m->opts = 0; m->base = 0; m->hist = 0;
     m->res.at_flush = 0;
     m->state = m->wrap == 1 ? ZM_HEAD : ZM_BLOCK;
 }
@@ -468,7 +471,7 @@ ZID void zi_step(zi_mach *m)
             if (d < 4) dist = 1 + (uint32_t)d;
             else { uint32_t eb = ((uint32_t)d - 2) >> 1; dist = 1 + ((2 + ((uint32_t)d & 1)) << eb) + zi_take(io, (int)eb); }
             if (zi_overrun(io)) { zi_m_fail(m, zi_fail(res, ZI_BUF_ERROR, ZI_E_INPUT_END), 0); break; }
-            if (dist > io->op - m->base || dist > m->win) { zi_m_fail(m, zi_fail(res, ZI_DATA_ERROR, ZI_E_DIST_TOO_FAR), 0); break; }
+            if (dist > io->op - m->base + m->hist || dist > m->win) { zi_m_fail(m, zi_fail(res, ZI_DATA_ERROR, ZI_E_DIST_TOO_FAR), 0); break; }
             m->rem = len; m->dist = dist; m->state = ZM_COPY;
         }
     }
@@ -502,7 +505,20 @@ ZID void zi_step(zi_mach *m)
         else if ((((h & 0xFF) << 8) | (h >> 8)) % 31) r = zi_fail(res, ZI_DATA_ERROR, ZI_E_HEADER_CHECK);
         else if ((h & 0xF) != 8) r = zi_fail(res, ZI_DATA_ERROR, ZI_E_METHOD);
         else if (((h >> 4) & 0xF) + 8 > m->maxw) r = zi_fail(res, ZI_DATA_ERROR, ZI_E_WINDOW);
-        else if (h & 0x2000) r = zi_fail(res, ZI_NEED_DICT, ZI_E_NEED_DICT);
+        else if (h & 0x2000) {
+            if (m->opts & ZI_OPT_STREAMING) {
+                /* DICTID follows the header (src/inflate.c:957-973): report it and wait for the dictionary */
+                zi_refill(io);
+                const uint32_t t = zi_take32(io);
+                if (zi_overrun(io)) r = zi_fail(res, ZI_BUF_ERROR, ZI_E_INPUT_END);
+                else {
+                    res->stored_check = ((t & 0xFF) << 24) | ((t & 0xFF00) << 8) | ((t >> 8) & 0xFF00) | (t >> 24);
+                    m->win = 1u << (((h >> 4) & 0xF) + 8);
+                    m->state = ZM_DICT;
+                    return;
+                }
+            } else r = zi_fail(res, ZI_NEED_DICT, ZI_E_NEED_DICT);
+        }
         if (r == ZI_OK) { m->win = 1u << (((h >> 4) & 0xF) + 8); m->state = ZM_BLOCK; }
         else zi_m_fail(m, r, 2);
         return;
@@ -549,6 +565,7 @@ ZID void zi_step(zi_mach *m)
         /* inflateSync resets the stream (src/inflate.c:1593 -> inflateReset: whave = 0, dmax = 32768) and the next
            inflate() call measures distances from its own first output byte (src/inflate.c:1284-1295, inffast.c:190-200) */
         m->base = io->op;
+        m->hist = 0;
         m->win = 32768u;
         m->state = ZM_BLOCK;
         return;
@@ -611,7 +628,7 @@ ZID uint32_t zi_fast_batch(zi_mach *m, const uint32_t *lut_len, const uint32_t *
     }
     if (nmax == 0) { *vop = op; return 0; }
     zi_io io = m->io;                                    /* the cursor in registers for the whole batch */
-    const uint32_t win = m->win, base = m->base;
+    const uint32_t win = m->win, base = m->base - m->hist;   /* (wraps when hist > base: the comparison below is on the difference) */
     while (n < nmax) {
         zi_refill(&io);                                  /* >= 33 bits: a literal/length code and its extra bits */
         const uint64_t h = io.hold;

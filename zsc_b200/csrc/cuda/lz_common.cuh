@@ -110,6 +110,11 @@ template <uint32_t RING> __device__ __forceinline__ void zl_stage_bulk(uint32_t 
     uint8_t *ring8 = (uint8_t *)ring32;
     uint32_t bytes = to - from;
     const uint32_t wrap = (from | (RING - 1)) + 1;                 /* next multiple of RING above `from` */
+    if (to <= wrap && (from & (RING - 1)) >= ZL_MIRROR) {          /* the usual case: one piece, clear of the ring's ends */
+        zl_mbar_expect_tx(bar, bytes);
+        zl_bulk_g2s(ring8 + (from & (RING - 1)), gbase + from, bytes, bar);
+        return;
+    }
     for (uint32_t h = 0; h < ZL_MIRROR; h += 16) {
         const uint32_t m0 = (from & ~(RING - 1)) + h, m1 = wrap + h;   /* positions whose ring offset is h */
         if ((m0 >= from && m0 < to) || (m1 >= from && m1 < to)) bytes += 16;
