@@ -140,7 +140,9 @@ zs_lz_kernel(const uint8_t *__restrict__ raw, const ZsChunk *__restrict__ chunks
     /* tiles are [t_first + k * ZL_TILE, ...); with hashing the dictionary is walked too */
     const uint32_t t_first = hashing ? 0 : (q_start / ZL_TILE) * ZL_TILE;
     const uint32_t ntiles = q_end > t_first ? (q_end - t_first + ZL_TILE - 1) / ZL_TILE : 0;
-    uint32_t loaded = hashing ? 0 : ((t_first > ZS_WINDOW ? t_first - ZS_WINDOW : 0) & ~15u);
+    /* without hashing (Z_RLE, Z_HUFFMAN_ONLY, level 0) nothing farther back than the byte before the first position is ever
+       read: staging starts just below the first tile (a staging step must stay below the ring size, lz_common.cuh) */
+    uint32_t loaded = hashing ? 0 : (t_first >= 16u ? t_first - 16u : 0u);
     uint32_t stage_phase = 0;                                      /* completed phases of the staging barrier */
 
     /* ---- prologue: stage tiles 0 and 1 (bulk copy issued by one thread), hash them, head-table pass of tile 0 ---- */
