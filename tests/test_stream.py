@@ -46,7 +46,10 @@ class Driver:
             s.next_in = C.cast(C.byref(src, pos), capi.u8p)
             s.avail_in = end - pos
             pos = end
+            guard = 0
             while True:
+                guard += 1
+                assert guard < 100000, "deflate makes no progress"
                 s.next_out = C.cast(obuf, capi.u8p)
                 s.avail_out = out_chunk
                 r = self.L.deflate(C.byref(s), flush)
@@ -73,7 +76,10 @@ class Driver:
         obuf = (C.c_uint8 * out_chunk)()
         out, codes, pos, r = bytearray(), [], 0, 0
         saw_dict = False
+        guard = 0
         while r not in (1,) and len(out) < cap:
+            guard += 1
+            assert guard < 200000 + 4 * (len(comp) // max(in_chunk, 1)), "inflate makes no progress"
             if s.avail_in == 0 and pos < len(comp):
                 n = min(in_chunk, len(comp) - pos)
                 s.next_in = C.cast(C.byref(src, pos), capi.u8p)

@@ -959,7 +959,7 @@ extern "C" int zscgpu_compress_host(zscgpu_engine *e, uint8_t *dest, uint32_t de
     if (cap > e->cfg.comp_bytes - dskip) cap = e->cfg.comp_bytes - dskip;
     st.comp_len = (uint32_t)cap;
     r = zscgpu_deflate_enqueue(e, &st, 1, p); if (r) return r;
-    if (p->wrap == 2) { r = zscgpu_crc32_enqueue(e, 0, src_len); if (r) return r; }
+    if (p->wrap == 2) { r = zscgpu_crc32_enqueue(e, p->hist_len, src_len - p->hist_len); if (r) return r; }   /* of the data, not of the history in front of it */
     r = zscgpu_fetch_results(e, 1, res); if (r) return r;
     if (p->wrap == 2) {
         uint32_t h[2];

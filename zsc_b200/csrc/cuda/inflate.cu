@@ -271,6 +271,7 @@ __global__ void __launch_bounds__(32, 1) zs_inflate_stream_kernel(ZsInfStepArgs 
         m.T = &T; m.X = &X;
         m.io.in = a.in; m.io.in_len = a.in_have; m.io.pv = 0;
         m.io.out = out; m.io.out_cap = a.out_cap; m.io.op = 0; m.base = 0;
+        if (m.skip && a.in_have) { zi_refill(&m.io); zi_drop(&m.io, (int)m.skip); m.skip = 0; }   /* the first staged byte was partly used */
         uint32_t status = ZSI_NEED_INPUT;
         if (a.mode == 1 && m.state != ZM_DONE) {
             /* inflateSync: search the staged input for 00 00 FF FF (zi_sync, the reference's syncsearch); the bits still
@@ -312,9 +313,10 @@ __global__ void __launch_bounds__(32, 1) zs_inflate_stream_kernel(ZsInfStepArgs 
             pos -= held; m.held = held;
             m.io.hold = 0; m.io.bits = 0;
         } else {
+            /* a partly used byte stays staged (the cursor never runs ahead of the input); its used bits are skipped next time */
             const uint32_t keep = m.io.bits & 7u;
-            m.io.hold &= (1ull << keep) - 1ull;
-            m.io.bits = keep;
+            if (keep && pos > 0) { pos -= 1; m.skip = 8u - keep; }
+            m.io.hold = 0; m.io.bits = 0;
         }
         m.io.ip = 0; m.io.pv = 0;
         const uint32_t valid = m.io.op - m.base + m.hist;

@@ -393,6 +393,7 @@ typedef struct {
     uint32_t last, rem, dist, win, maxw, held;
     uint32_t base;          /* output position of the last resynchronisation: no distance may reach behind it */
     uint32_t hist;          /* streaming: valid bytes in front of out[0] (earlier calls' output or a preset dictionary) */
+    uint32_t skip;          /* streaming: bits of in[0] an earlier call has already used */
     uint32_t opts;          /* ZI_OPT_*: section-parallel decoding of one stream (engine.cu zs_inflate_sectioned) */
 } zi_mach;
 
@@ -411,7 +412,7 @@ ZID void zi_m_init(zi_mach *m, const uint8_t *in, uint32_t in_len, uint8_t *out,
     m->maxw = ((wrap >> 8) & 0xFF) ? (uint32_t)((wrap >> 8) & 0xFF) : 15u;
     m->wrap = wrap & 0xFF;
     m->win = 1u << m->maxw;
-    m->T = T; m->X = X; m->last = 0; m->rem = 0; m->dist = 0; m->held = 0; m->opts = 0; m->base = 0; m->hist = 0;
+    m->T = T; m->X = X; m->last = 0; m->rem = 0; m->dist = 0; m->held = 0; m->opts = 0; m->base = 0; m->hist = 0; m->skip = 0;
     m->res.at_flush = 0;
     m->state = m->wrap == 1 ? ZM_HEAD : ZM_BLOCK;
 }
