@@ -56,7 +56,7 @@ struct zscgpu_engine {
     uint32_t *d_blk_used;             /* [0] = number of used block slots of the launch, then their indices */
     ZsAdlerAcc *d_adler;              /* per stream; slot max_streams is the flat-checksum slot */
     uint32_t *d_crc;                  /* [2] */
-    uint32_t *d_ctr;                  /* inflate: next unclaimed stream of the batch */
+    uint32_t *d_ctr;                  /* inflate: per stream, the sorted symbols of the current block (zi_aux, 640 B) */
     uint8_t *d_sslots, *d_sin, *d_sout;   /* streaming inflate: ZS_STREAM_SLOTS x (machine + tables | input staging | history + output staging) */
     uint32_t *d_sres, *h_sres;        /* ... and the eight result words of a step */
     bool sslot_used[ZS_STREAM_SLOTS];
@@ -183,7 +183,7 @@ static int zs_init_engine(zscgpu_engine *e, const zscgpu_config &cfg, const cuda
     ZS_CUDA_CHECK(zs_dev(&e->d_blk_used, (size_t)e->blk_cap + 2));
     ZS_CUDA_CHECK(zs_dev(&e->d_adler, cfg.max_streams + 1));
     ZS_CUDA_CHECK(zs_dev(&e->d_crc, 4));
-    ZS_CUDA_CHECK(zs_dev(&e->d_ctr, 16));
+    ZS_CUDA_CHECK(zs_dev(&e->d_ctr, (size_t)cfg.max_streams * 160u));      /* 640 B per stream */
     ZS_CUDA_CHECK(zs_dev(&e->d_sslots, ZS_STREAM_SLOTS * zs_inflate_stream_slot_bytes()));
     ZS_CUDA_CHECK(zs_dev(&e->d_sin, (size_t)ZS_STREAM_SLOTS * (ZSCGPU_STREAM_IN_MAX + 256)));
     ZS_CUDA_CHECK(zs_dev(&e->d_sout, (size_t)ZS_STREAM_SLOTS * (ZS_STREAM_HIST + ZSCGPU_STREAM_OUT_MAX + 256)));

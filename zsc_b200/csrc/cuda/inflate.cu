@@ -15,6 +15,7 @@
 
 #ifndef ZS_INFLATE_WARP_MAX
 #define ZS_INFLATE_WARP_MAX 6144u                /* streams in a batch up to which each gets a whole warp */
+#define ZS_INFLATE_G16_MAX 12288u                /* ... and up to which each gets half a warp; beyond, a quarter */
 #endif
 
 /* ======================= a group of G lanes per stream ======================= */
@@ -29,9 +30,8 @@
 
 struct ZwLut { uint32_t len[32]; uint32_t dist[32]; };     /* base | extra bits << 16 (RFC 1951 3.2.5) */
 
-template <int G> struct ZwStream {
+template <int G> struct ZwStream {          /* per stream in shared memory: both table levels and the record queue (1.6 KB + 4 G) */
     zi_tables T;
-    zi_aux X;
     uint32_t q[G];
 };
 
@@ -103,7 +103,8 @@ __global__ void __launch_bounds__(ZW_THREADS, 8)
 zs_inflate_group_kernel(uint32_t n, const ZsStream *__restrict__ streams, const uint8_t *__restrict__ comp,
                         uint8_t *__restrict__ raw, int32_t wrap, int32_t *__restrict__ ret,
                         uint32_t *__restrict__ produced, uint32_t *__restrict__ consumed,
-                        uint32_t *__restrict__ aux /* [2n]: stored check, flags */)
+                        uint32_t *__restrict__ aux /* [2n]: stored check, flags */,
+                        zi_aux *__restrict__ xpool /* [n]: sorted symbols, read only by the rare codes no table level resolves */)
 {
     constexpr int GROUPS = ZW_THREADS / G;
     extern __shared__ __align__(16) unsigned char zw_smem_raw[];
@@ -132,7 +133,7 @@ zs_inflate_group_kernel(uint32_t n, const ZsStream *__restrict__ streams, const 
        if the batch's wrap has one, still follows its final block) */
     const uint32_t sopt = st.chunk_first;
     zi_mach m;
-    zi_m_init(&m, in, st.comp_cap, out, st.raw_len, wrap, &w.T, &w.X);
+    zi_m_init(&m, in, st.comp_cap, out, st.raw_len, wrap, &w.T, &xpool[s]);
     m.opts = sopt & 3u;
     if ((sopt & 4u) && m.state == ZM_HEAD) m.state = ZM_BLOCK;
     const bool count_only = (sopt & ZI_OPT_COUNT_ONLY) != 0;
@@ -179,13 +180,13 @@ zs_inflate_group_kernel(uint32_t n, const ZsStream *__restrict__ streams, const 
 
 template <int G>
 static cudaError_t zs_inflate_group_launch(cudaStream_t st, uint32_t n, const ZsStream *streams, const uint8_t *comp, uint8_t *raw, int32_t wrap,
-                                           int32_t *ret, uint32_t *produced, uint32_t *consumed, uint32_t *aux)
+                                           int32_t *ret, uint32_t *produced, uint32_t *consumed, uint32_t *aux, zi_aux *xpool)
 {
     constexpr int GROUPS = ZW_THREADS / G;
     const size_t smem = sizeof(ZwStream<G>) * GROUPS + sizeof(ZwLut);
     cudaFuncSetAttribute(zs_inflate_group_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncSetAttribute(zs_inflate_group_kernel<G>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
-    zs_inflate_group_kernel<G><<<(n + GROUPS - 1) / GROUPS, ZW_THREADS, smem, st>>>(n, streams, comp, raw, wrap, ret, produced, consumed, aux);
+    zs_inflate_group_kernel<G><<<(n + GROUPS - 1) / GROUPS, ZW_THREADS, smem, st>>>(n, streams, comp, raw, wrap, ret, produced, consumed, aux, xpool);
     return cudaGetLastError();
 }
 
@@ -362,20 +363,20 @@ extern "C" cudaError_t zs_adler_streams_launch(cudaStream_t st, uint32_t n, uint
 extern "C" cudaError_t zs_inflate_launch(cudaStream_t st, uint32_t n, const ZsStream *streams, const uint8_t *comp,
                                          uint8_t *raw, int32_t wrap, int32_t *ret, uint32_t *produced,
                                          uint32_t *consumed, uint32_t *check, uint32_t *aux, ZsAdlerAcc *acc,
-                                         uint32_t max_raw_len, int with_check, uint32_t *counter, int sms)
+                                         uint32_t max_raw_len, int with_check, uint32_t *counter /* zi_aux[n] */, int sms)
 {
     if (n == 0) return cudaSuccess;
-    (void)counter; (void)sms;
-    /* a warp per stream while that fills the machine (148 SMs x 32 warps), two streams per warp beyond: both
-       leaders of a warp decode at the same time, the decode cost per symbol halves.  Smaller groups measured
-       slower (8 lanes: 40 GB/s, 4 lanes: 25 GB/s against 54 GB/s at 65 536 streams): shared memory holds 64 streams per
-       SM whatever the group size, so fewer lanes per stream only mean fewer warps to hide latency with.  Also measured
-       and dropped (round 2, profiles/r02_exp_inflate_lanes_*.log): a lane per stream on a few decoder warps in lockstep
-       feeding writer warps through double-buffered queues — 4.4 instead of 15 warp-instructions per output byte, but
-       33-41 GB/s at 16 384 streams and 32 GB/s at 65 536: with 64 streams per SM there are too few decoder warps, and
-       every lockstep step pays the literal, the match and the refill path one after the other (1900 cycles a symbol). */
-    cudaError_t ge = n <= ZS_INFLATE_WARP_MAX ? zs_inflate_group_launch<32>(st, n, streams, comp, raw, wrap, ret, produced, consumed, aux)
-                                              : zs_inflate_group_launch<16>(st, n, streams, comp, raw, wrap, ret, produced, consumed, aux);
+    (void)sms;
+    zi_aux *xpool = reinterpret_cast<zi_aux *>(counter);
+    /* a warp per stream while that fills the machine (148 SMs x 32 warps); beyond, several streams per warp: their
+       leaders decode at the same time, and the two-level tables (1.6 KB per stream) let 128 streams share an SM */
+    uint32_t g = n <= ZS_INFLATE_WARP_MAX ? 32u : (n <= ZS_INFLATE_G16_MAX ? 16u : 8u);
+#ifdef ZSC_TUNING
+    if (getenv("ZSC_B200_INFLATE_G")) g = (uint32_t)atoi(getenv("ZSC_B200_INFLATE_G"));
+#endif
+    cudaError_t ge = g == 32 ? zs_inflate_group_launch<32>(st, n, streams, comp, raw, wrap, ret, produced, consumed, aux, xpool)
+                   : g == 16 ? zs_inflate_group_launch<16>(st, n, streams, comp, raw, wrap, ret, produced, consumed, aux, xpool)
+                             : zs_inflate_group_launch<8>(st, n, streams, comp, raw, wrap, ret, produced, consumed, aux, xpool);
     if (ge != cudaSuccess) return ge;
     if (!with_check) return cudaSuccess;               /* section passes: the caller checks the whole stream */
     cudaMemsetAsync(acc, 0, sizeof(ZsAdlerAcc) * n, st);

@@ -30,10 +30,9 @@
 #define ZID static inline
 #endif
 
-#ifndef ZI_LBITS
-#define ZI_LBITS 10
-#endif
-#define ZI_DBITS 8
+#define ZI_LBITS 9                   /* root bits of the literal/length table */
+#define ZI_DBITS 6                   /* root bits of the distance table */
+#define ZI_POOL 192                  /* second-level entries, shared by both alphabets of a block */
 
 #define ZI_OK 0
 #define ZI_NEED_DICT 2
@@ -48,11 +47,17 @@ enum {
     ZI_E_INPUT_END, ZI_E_OUTPUT_FULL, ZI_E_NEED_DICT
 };
 
-typedef struct {                     /* hot: 2640 bytes per stream */
-    uint16_t lit[1 << ZI_LBITS];     /* sym | len << 9 ; 0 = code longer than ZI_LBITS */
-    uint16_t dist[1 << ZI_DBITS];    /* sym | len << 5 ; 0 = longer */
+/* Table entries (both alphabets): 0 = not resolved here (the canonical walk decides); bit 15 clear: sym | len << 9, a
+ * whole code of len <= 15 bits; bit 15 set: a link, pool index | sub-table bits << 10 — the next bits of the input index a
+ * second-level table in `pool` whose entries have the first form.  Sub-tables are handed out while the pool lasts; what
+ * does not fit (or is wider than 7 bits) stays 0 and goes through the walk, so the pool can be small. */
+typedef struct {                     /* hot: 1624 bytes per stream */
+    uint16_t lit[1 << ZI_LBITS];
+    uint16_t dist[1 << ZI_DBITS];
+    uint16_t pool[ZI_POOL];
     uint16_t lcount[16];
     uint16_t dcount[16];
+    uint32_t pool_used;
     uint32_t lfirst, lindex, dfirst, dindex;   /* where zi_decode's canonical walk stands after the lengths the direct
                                                   tables resolve (set with the tables; read by zi_fast_batch) */
 } zi_tables;
@@ -231,6 +236,96 @@ ZID void zi_walk_start(const uint16_t *count, int tbits, uint32_t *first_out, ui
     *first_out = first; *index_out = index;
 }
 
+/* direct entries of the codes of at most `root` bits (sorted / count as zi_build leaves them) */
+ZID void zi_fill_root(const uint16_t *sorted, const uint16_t *count, int root, uint16_t *table)
+{
+    for (int i = 0; i < (1 << root); i++) table[i] = 0;
+    uint32_t code = 0; int k = 0;
+    for (int l = 1; l <= root; l++) {
+        for (int c = 0; c < count[l]; c++, k++, code++) {
+            const uint32_t r = zi_rev(code, l);
+            const uint16_t e = (uint16_t)(sorted[k] | (l << 9));
+            for (uint32_t j = r; j < (1u << root); j += (1u << l)) table[j] = e;
+        }
+        code <<= 1;
+    }
+}
+
+/* second-level tables for the codes longer than `root` bits, as far as the pool lasts */
+ZID void zi_fill_long(const uint16_t *sorted, const uint16_t *count, int root, uint16_t *table, uint16_t *pool, uint32_t *pool_used)
+{
+    uint32_t code = 0; int k = 0, any = 0;
+    for (int l = 1; l <= root; l++) { code = (code + count[l]) << 1; k += count[l]; }
+    for (int l = root + 1; l <= 15; l++) any += count[l];
+    if (!any) return;
+    const uint32_t rmask = (1u << root) - 1u;
+    /* longest code under every root slot: lengths ascend, the last marker written wins */
+    uint32_t c2 = code;
+    for (int l = root + 1; l <= 15; l++) {
+        for (int c = 0; c < count[l]; c++, c2++) table[zi_rev(c2, l) & rmask] = (uint16_t)(0x4000u | (uint32_t)(l - root));
+        c2 <<= 1;
+    }
+    for (uint32_t s = 0; s <= rmask; s++) {
+        const uint32_t e = table[s];
+        if ((e & 0xC000u) != 0x4000u) continue;
+        const uint32_t sb = e & 15u, need = 1u << sb;
+        if (sb > 7u || *pool_used + need > ZI_POOL) { table[s] = 0; continue; }
+        for (uint32_t j = 0; j < need; j++) pool[*pool_used + j] = 0;
+        table[s] = (uint16_t)(0x8000u | (sb << 10) | *pool_used);
+        *pool_used += need;
+    }
+    for (int l = root + 1; l <= 15; l++) {
+        for (int c = 0; c < count[l]; c++, k++, code++) {
+            const uint32_t r = zi_rev(code, l), e = table[r & rmask];
+            if (!(e & 0x8000u)) continue;
+            const uint32_t sb = (e >> 10) & 7u, off = e & 0x3FFu;
+            const uint16_t v = (uint16_t)(sorted[k] | (l << 9));
+            for (uint32_t j = r >> root; j < (1u << sb); j += (1u << (l - root))) pool[off + j] = v;
+        }
+        code <<= 1;
+    }
+}
+
+/* counts, sorted symbols and both table levels of one alphabet; same accept / reject rule as zi_build */
+ZID int zi_build2(const uint8_t *lens, int n, int root, uint16_t *table, uint16_t *pool, uint32_t *pool_used,
+                  uint16_t *sorted, uint16_t *count, int allow_incomplete)
+{
+    uint16_t offs[16];
+    for (int i = 0; i < 16; i++) count[i] = 0;
+    for (int i = 0; i < n; i++) count[lens[i]]++;
+    int maxl = 15;
+    while (maxl > 0 && count[maxl] == 0) maxl--;
+    if (maxl == 0) { count[0] = 0; for (int i = 0; i < (1 << root); i++) table[i] = 0; return allow_incomplete ? 0 : -1; }
+    int left = 1;
+    for (int l = 1; l <= 15; l++) { left <<= 1; left -= count[l]; if (left < 0) return -1; }
+    if (left > 0 && (!allow_incomplete || maxl != 1)) return -1;
+    offs[1] = 0;
+    for (int l = 1; l < 15; l++) offs[l + 1] = (uint16_t)(offs[l] + count[l]);
+    for (int i = 0; i < n; i++) if (lens[i]) sorted[offs[lens[i]]++] = (uint16_t)i;
+    count[0] = 0;
+    zi_fill_root(sorted, count, root, table);
+    zi_fill_long(sorted, count, root, table, pool, pool_used);
+    return 0;
+}
+
+/* Decode one symbol through both table levels, else by the canonical walk. Returns the symbol or -1 (invalid code). */
+ZID int zi_decode2(zi_io *io, const uint16_t *table, int root, const uint16_t *pool, const uint16_t *sorted, const uint16_t *count)
+{
+    const uint32_t b = zi_peek(io, 15);
+    uint32_t e = table[b & ((1u << root) - 1u)];
+    if (e & 0x8000u) e = pool[(e & 0x3FFu) + ((b >> root) & ((1u << ((e >> 10) & 7u)) - 1u))];
+    if (e) { zi_drop(io, (int)(e >> 9)); return (int)(e & 511u); }
+    const uint32_t v = zi_rev(b, 15);
+    uint32_t first = 0, index = 0;
+    for (int l = 1; l <= 15; l++) {
+        const uint32_t c = count[l];
+        const uint32_t code = v >> (15 - l);
+        if (l > root && code - first < c) { zi_drop(io, l); return (int)sorted[index + (code - first)]; }
+        index += c; first = (first + c) << 1;
+    }
+    return -1;
+}
+
 ZID int zi_fail(zi_result *r, int ret, int reason)
 {
     if (r->reason == ZI_E_NONE) r->reason = reason;
@@ -267,7 +362,8 @@ ZID int zi_block_head(zi_io *io, zi_tables *T, zi_aux *X, zi_result *res, uint32
                    used, src/inflate.c:122-206), literal/length lengths 8/9/7/8 in closed form */
                 uint8_t tmp[32];
                 for (int i = 0; i < 32; i++) tmp[i] = 5;
-                (void)zi_build(tmp, 32, ZI_DBITS, T->dist, X->dsorted, T->dcount, 5, 1);
+                T->pool_used = 0;
+                (void)zi_build2(tmp, 32, ZI_DBITS, T->dist, T->pool, &T->pool_used, X->dsorted, T->dcount, 1);
                 for (int i = 0; i < 16; i++) T->lcount[i] = 0;
                 T->lcount[7] = 24; T->lcount[8] = 152; T->lcount[9] = 112;
                 int k = 0;
@@ -275,16 +371,7 @@ ZID int zi_block_head(zi_io *io, zi_tables *T, zi_aux *X, zi_result *res, uint32
                 for (int i = 0; i < 144; i++) X->lsorted[k++] = (uint16_t)i;
                 for (int i = 280; i < 288; i++) X->lsorted[k++] = (uint16_t)i;
                 for (int i = 144; i < 256; i++) X->lsorted[k++] = (uint16_t)i;
-                for (int i = 0; i < (1 << ZI_LBITS); i++) T->lit[i] = 0;
-                uint32_t code = 0; k = 0;
-                for (int l = 7; l <= 9; l++) {
-                    for (int c = 0; c < T->lcount[l]; c++, k++, code++) {
-                        uint32_t r = zi_rev(code, l);
-                        uint16_t e = (uint16_t)(X->lsorted[k] | (l << 9));
-                        for (uint32_t j = r; j < (1u << ZI_LBITS); j += (1u << l)) T->lit[j] = e;
-                    }
-                    code <<= 1;
-                }
+                zi_fill_root(X->lsorted, T->lcount, ZI_LBITS, T->lit);      /* no code is longer than 9 bits */
             } else {
                 zi_refill(io);
                 uint32_t nlen = zi_take(io, 5) + 257, ndist = zi_take(io, 5) + 1, ncode = zi_take(io, 4) + 4;
@@ -321,9 +408,10 @@ ZID int zi_block_head(zi_io *io, zi_tables *T, zi_aux *X, zi_result *res, uint32
                 }
                 if (lens[256] == 0) return zi_fail(res, ZI_DATA_ERROR, ZI_E_NO_EOB);
                 /* distance tables first (they overwrite the code-length table), from the tail of lens */
-                if (zi_build(lens + nlen, (int)ndist, ZI_DBITS, T->dist, X->dsorted, T->dcount, 5, 1))
+                T->pool_used = 0;
+                if (zi_build2(lens + nlen, (int)ndist, ZI_DBITS, T->dist, T->pool, &T->pool_used, X->dsorted, T->dcount, 1))
                     return zi_fail(res, ZI_DATA_ERROR, ZI_E_DIST_SET);
-                /* literal/length: sorted + counts while lens is alive, then the table over it */
+                /* literal/length: sorted + counts while lens is alive, then the tables over it */
                 {
                     uint16_t offs[16];
                     for (int k = 0; k < 16; k++) T->lcount[k] = 0;
@@ -336,16 +424,8 @@ ZID int zi_block_head(zi_io *io, zi_tables *T, zi_aux *X, zi_result *res, uint32
                     offs[1] = 0;
                     for (int l = 1; l < 15; l++) offs[l + 1] = (uint16_t)(offs[l] + T->lcount[l]);
                     for (uint32_t k = 0; k < nlen; k++) if (lens[k]) X->lsorted[offs[lens[k]]++] = (uint16_t)k;
-                    for (int k = 0; k < (1 << ZI_LBITS); k++) T->lit[k] = 0;
-                    uint32_t code = 0; int k = 0;
-                    for (int l = 1; l <= maxl && l <= ZI_LBITS; l++) {
-                        for (int c = 0; c < T->lcount[l]; c++, k++, code++) {
-                            uint32_t r = zi_rev(code, l);
-                            uint16_t e = (uint16_t)(X->lsorted[k] | (l << 9));
-                            for (uint32_t j = r; j < (1u << ZI_LBITS); j += (1u << l)) T->lit[j] = e;
-                        }
-                        code <<= 1;
-                    }
+                    zi_fill_root(X->lsorted, T->lcount, ZI_LBITS, T->lit);
+                    zi_fill_long(X->lsorted, T->lcount, ZI_LBITS, T->lit, T->pool, &T->pool_used);
                 }
             }
     }
@@ -446,7 +526,7 @@ ZID void zi_step(zi_mach *m)
         /* up to two symbols: most are literals, and two keep the lanes of a warp busy between copies */
         for (int rep = 0; rep < 2 && m->state == ZM_SYM; rep++) {
             zi_refill(io);
-            const int s = zi_decode(io, T->lit, ZI_LBITS, X->lsorted, T->lcount, 9);
+            const int s = zi_decode2(io, T->lit, ZI_LBITS, T->pool, X->lsorted, T->lcount);
             if (zi_overrun(io)) { zi_m_fail(m, zi_fail(res, ZI_BUF_ERROR, ZI_E_INPUT_END), 0); break; }
             if (s < 0) { zi_m_fail(m, zi_fail(res, ZI_DATA_ERROR, ZI_E_LITLEN_CODE), 0); break; }
             if (s < 256) {
@@ -462,7 +542,7 @@ ZID void zi_step(zi_mach *m)
             else if (c == 28) len = 258;
             else { uint32_t eb = (c - 4) >> 2; len = 3 + ((4 + (c & 3)) << eb) + zi_take(io, (int)eb); }
             zi_refill(io);
-            const int d = zi_decode(io, T->dist, ZI_DBITS, X->dsorted, T->dcount, 5);
+            const int d = zi_decode2(io, T->dist, ZI_DBITS, T->pool, X->dsorted, T->dcount);
             if (d < 0 || d > 29) {
                 int ov = zi_overrun(io);
                 zi_m_fail(m, zi_fail(res, ov ? ZI_BUF_ERROR : ZI_DATA_ERROR, ov ? ZI_E_INPUT_END : ZI_E_DIST_CODE), 0);
@@ -615,7 +695,7 @@ static inline void zi_sa_st32(zi_sa a, uint32_t v) { *(uint32_t *)a = v; }
 ZID uint32_t zi_fast_batch(zi_mach *m, const uint32_t *lut_len, const uint32_t *lut_dist, uint32_t *q, uint32_t maxn, uint32_t *vop)
 {
     const zi_tables *T = m->T;
-    const zi_sa lit_a = zi_sa_of(T->lit), dist_a = zi_sa_of(T->dist), len_a = zi_sa_of(lut_len), dl_a = zi_sa_of(lut_dist), q_a = zi_sa_of(q);
+    const zi_sa lit_a = zi_sa_of(T->lit), dist_a = zi_sa_of(T->dist), pool_a = zi_sa_of(T->pool), len_a = zi_sa_of(lut_len), dl_a = zi_sa_of(lut_dist), q_a = zi_sa_of(q);
     uint32_t n = 0, op = m->io.op;
     /* how many symbols this batch may take: each needs at most 258 bytes of output room and pulls at most
        8 bytes of input (two refills); the last 16 input bytes are left to zi_step */
@@ -636,7 +716,8 @@ ZID uint32_t zi_fast_batch(zi_mach *m, const uint32_t *lut_len, const uint32_t *
         const uint32_t b = io.bits;
         uint32_t l, sym;
         {
-            const uint32_t e = zi_sa_ld16(lit_a + 2u * ((uint32_t)h & ((1u << ZI_LBITS) - 1u)));
+            uint32_t e = zi_sa_ld16(lit_a + 2u * ((uint32_t)h & ((1u << ZI_LBITS) - 1u)));
+            if (e & 0x8000u) e = zi_sa_ld16(pool_a + 2u * ((e & 0x3FFu) + (((uint32_t)h >> ZI_LBITS) & ((1u << ((e >> 10) & 7u)) - 1u))));
             if (e) { l = e >> 9; sym = e & 511u; }
             else {
                 const uint32_t v = zi_rev((uint32_t)h & 0x7FFFu, 15);
@@ -661,8 +742,9 @@ ZID uint32_t zi_fast_batch(zi_mach *m, const uint32_t *lut_len, const uint32_t *
         const uint32_t b2 = io.bits;
         uint32_t l2, d;
         {
-            const uint32_t e = zi_sa_ld16(dist_a + 2u * ((uint32_t)h2 & ((1u << ZI_DBITS) - 1u)));
-            if (e) { l2 = e >> 5; d = e & 31u; }
+            uint32_t e = zi_sa_ld16(dist_a + 2u * ((uint32_t)h2 & ((1u << ZI_DBITS) - 1u)));
+            if (e & 0x8000u) e = zi_sa_ld16(pool_a + 2u * ((e & 0x3FFu) + (((uint32_t)h2 >> ZI_DBITS) & ((1u << ((e >> 10) & 7u)) - 1u))));
+            if (e) { l2 = e >> 9; d = e & 511u; }
             else {
                 const uint32_t v = zi_rev((uint32_t)h2 & 0x7FFFu, 15);
                 uint32_t first = T->dfirst, index = T->dindex;
