@@ -12,7 +12,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a B200 (run on the GPU box with -m gpu)")
     # the shared libraries are build artefacts (git-ignored); make sure they exist before collecting
-    need = [os.path.join(ROOT, "zsc_b200", "libzsc_b200.so"), os.path.join(ROOT, "tests", "libzsc_cpuharness.so"),
+    need = [os.path.join(ROOT, "zsc_b200", "libzsc_b200.so"), os.path.join(ROOT, "tests", "libzsc_cpuharness.so"), os.path.join(ROOT, "tests", "libzsc_cpuharness_n.so"),
             os.path.join(ROOT, "tools", "libzscgen.so"), os.path.join(ROOT, "oracle", "libzsc_oracle.so")]
     if not all(os.path.exists(p) for p in need):
         subprocess.run(["make", "-j8", "zsc_b200/libzsc_b200.so", "testlibs"], cwd=ROOT, check=True)

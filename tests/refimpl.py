@@ -67,6 +67,18 @@ def oracle():
 
 
 _har = None
+_har_n = None
+
+
+def harness_narrow():
+    """the harness compiled with the table geometry of narrow batches (10 / 8 root bits)"""
+    global _har_n
+    if _har_n is None:
+        L = C.CDLL(HARNESS_PATH.replace(".so", "_n.so"), mode=C.RTLD_LOCAL)
+        L.h_inflate.argtypes = [u8p, C.c_uint32, u8p, C.c_uint32, C.c_int, u32p]
+        L.h_inflate_batched.argtypes = [u8p, C.c_uint32, u8p, C.c_uint32, C.c_int, u32p, C.c_uint32]
+        _har_n = L
+    return _har_n
 
 
 def harness():
@@ -88,13 +100,18 @@ def h_inflate(comp, cap, wrap=1):
     out = np.zeros(max(cap, 1), dtype=np.uint8)
     res = (C.c_uint32 * 7)()
     harness().h_inflate(padded.ctypes.data_as(u8p), len(comp), out.ctypes.data_as(u8p), cap, wrap, res)
-    # the group form of the same decoder (fast batch decode + generic steps) must agree in every field and byte
-    for group in (32, 8):
+    # the group form of the same decoder (fast batch decode + generic steps) must agree in every field and byte, with
+    # the compact table geometry (wide batches) and with the wide roots (narrow batches)
+    for H, group in ((harness(), 32), (harness(), 8), (harness_narrow(), 32), (harness_narrow(), 16)):
         out2 = np.zeros(max(cap, 1), dtype=np.uint8)
         res2 = (C.c_uint32 * 7)()
-        harness().h_inflate_batched(padded.ctypes.data_as(u8p), len(comp), out2.ctypes.data_as(u8p), cap, wrap, res2, group)
+        H.h_inflate_batched(padded.ctypes.data_as(u8p), len(comp), out2.ctypes.data_as(u8p), cap, wrap, res2, group)
         assert list(res) == list(res2), (group, list(res), list(res2))
         assert np.array_equal(out[:res[2]], out2[:res2[2]])
+    res3 = (C.c_uint32 * 7)()
+    out3 = np.zeros(max(cap, 1), dtype=np.uint8)
+    harness_narrow().h_inflate(padded.ctypes.data_as(u8p), len(comp), out3.ctypes.data_as(u8p), cap, wrap, res3)
+    assert list(res) == list(res3) and np.array_equal(out[:res[2]], out3[:res3[2]])
     ret = C.c_int32(res[0]).value
     return ret, out[:res[2]].copy(), dict(reason=res[1], produced=res[2], consumed=res[3], data_errors=res[4],
                                           stored_check=res[5], have_check=res[6])

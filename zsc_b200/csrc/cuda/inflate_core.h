@@ -19,7 +19,8 @@
  * The functions are `__host__ __device__` so tests/ can run the GPU's exact decode logic on the
  * CPU against the reference's known-answer vectors.
  */
-#ifndef ZSC_INFLATE_CORE_H
+/* (inflate.cu includes this file twice, in two namespaces with two table geometries: ZI_REINCLUDE lifts the guard) */
+#if !defined(ZSC_INFLATE_CORE_H) || defined(ZI_REINCLUDE)
 #define ZSC_INFLATE_CORE_H
 
 #include <stdint.h>
@@ -30,9 +31,14 @@
 #define ZID static inline
 #endif
 
+/* Table geometry.  The default (9 / 6 root bits, 192 second-level entries: 1.6 KB per stream) is the one wide batches
+ * use, where shared memory decides how many streams an SM holds; narrow batches (one warp per stream, latency bound)
+ * use 10 / 8 root bits (inflate.cu).  Results do not depend on the geometry. */
+#ifndef ZI_LBITS
 #define ZI_LBITS 9                   /* root bits of the literal/length table */
 #define ZI_DBITS 6                   /* root bits of the distance table */
 #define ZI_POOL 192                  /* second-level entries, shared by both alphabets of a block */
+#endif
 
 #define ZI_OK 0
 #define ZI_NEED_DICT 2

@@ -266,7 +266,7 @@ ZlibReturn zsc_compress_gzip2(U8 *dest, U32 *dest_len, const U8 *source, U32 sou
 
     zscgpu_deflate_params p;
     p.max_block_len = max_block_len; p.level = level; p.strategy = (I32)strategy;
-    p.wrap = wb.wrap; p.window_bits = wb.wbits; p.part = 0;
+    p.wrap = wb.wrap; p.window_bits = wb.wbits; p.part = 0; p.hist_len = 0;
     zscgpu_result res;
     U32 cap = dest_len_in;
     if (wb.wrap == 2) cap -= 8;                       /* room for CRC32 + ISIZE */
