@@ -393,7 +393,7 @@ zs_lzc_kernel(const uint8_t *__restrict__ raw, const ZsChunk *__restrict__ chunk
                 }
             }
             /* ---- hashes of tile k+2 (its bytes were queued at the top; wait until they have landed) ---- */
-            if (staging) zl_mbar_wait(&S.stage_bar, stage_phase & 1u);
+            if (staging) { if (lane == 0) zl_mbar_wait(&S.stage_bar, stage_phase & 1u); __syncwarp(); }   /* one poll per warp */
             if (k + 2 < ntiles) zc_hash_tile(S.ring32, S.t_hash[k & 1], t0 + 2 * ZC_TILE, q_dict, q_end, wtid);
         }
         if (staging) { stage_phase++; loaded = need; }

@@ -317,7 +317,7 @@ zs_lz_kernel(const uint8_t *__restrict__ raw, const ZsChunk *__restrict__ chunks
                 }
             }
             /* ---- B: hashes of tile k+2 (its bytes were queued in A; wait until they have landed) ---- */
-            if (staging) zl_mbar_wait(&S.stage_bar, stage_phase & 1u);
+            if (staging) { if (lane == 0) zl_mbar_wait(&S.stage_bar, stage_phase & 1u); __syncwarp(); }   /* one poll per warp */
             if (hashing && k + 2 < ntiles) zl_hash_tile<RING, HASH_BITS>(S.ring32, S.t_hash[k & 1], S.t_exit, t0 + 2 * ZL_TILE, q_dict, q_end, wtid);
         }
         if (staging) { stage_phase++; loaded = need; }
