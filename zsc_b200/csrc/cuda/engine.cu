@@ -4,6 +4,9 @@
  * them to their device twins and launch kernels on the engine's one CUDA stream.
  */
 #include <mutex>
+#include <condition_variable>
+#include <thread>
+#include <vector>
 #include <algorithm>
 #include <stdio.h>
 #include <stdlib.h>
@@ -32,6 +35,53 @@ extern "C" cudaError_t zs_inflate_stream_launch(cudaStream_t, void *, uint8_t *,
 extern "C" size_t zs_inflate_stream_slot_bytes(void);
 
 #define ZS_NEVENTS 16
+#define ZS_STAGE_BUFS 4                          /* pinned staging buffers per direction (pageable caller buffers) */
+#define ZS_STAGE_BYTES (8u << 20)
+
+/* Helper threads that copy between pageable caller memory and the pinned staging buffers: one memcpy thread moves
+ * ~10 GB/s, the PCIe link five times that.  Created once in zscgpu_init. */
+struct ZsCopyPool {
+    std::vector<std::thread> th;
+    std::mutex mu;
+    std::condition_variable cv, cv_done;
+    uint64_t gen = 0;
+    int pending = 0, n = 0;
+    bool quit = false;
+    uint8_t *dst = nullptr; const uint8_t *src = nullptr; size_t len = 0;
+    void run(int idx)
+    {
+        uint64_t seen = 0;
+        for (;;) {
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [&] { return quit || gen != seen; });
+            if (quit) return;
+            seen = gen;
+            uint8_t *d = dst; const uint8_t *s2 = src; const size_t L = len;
+            lk.unlock();
+            const size_t per = (((L + (size_t)n - 1) / (size_t)n) + 4095) & ~(size_t)4095;
+            const size_t lo = std::min(L, (size_t)idx * per), hi = std::min(L, lo + per);
+            if (hi > lo) memcpy(d + lo, s2 + lo, hi - lo);
+            lk.lock();
+            if (--pending == 0) cv_done.notify_one();
+        }
+    }
+    void start(int nthreads) { n = nthreads; for (int i = 0; i < n; i++) th.emplace_back([this, i] { run(i); }); }
+    void stop()
+    {
+        { std::lock_guard<std::mutex> lk(mu); quit = true; }
+        cv.notify_all();
+        for (auto &t : th) t.join();
+        th.clear();
+    }
+    void copy(uint8_t *d, const uint8_t *s2, size_t L)
+    {
+        if (L < (1u << 20) || n <= 1) { memcpy(d, s2, L); return; }
+        { std::lock_guard<std::mutex> lk(mu); dst = d; src = s2; len = L; pending = n; gen++; }
+        cv.notify_all();
+        std::unique_lock<std::mutex> lk(mu);
+        cv_done.wait(lk, [&] { return pending == 0; });
+    }
+};
 #define ZS_STREAM_SLOTS 16                       /* z_stream inflate states that can be open at a time */
 #define ZS_STREAM_HIST 32768u
 #define ZS_MAX_WAVES 64
@@ -60,6 +110,10 @@ struct zscgpu_engine {
     uint8_t *d_sslots, *d_sin, *d_sout;   /* streaming inflate: ZS_STREAM_SLOTS x (machine + tables | input staging | history + output staging) */
     uint32_t *d_sres, *h_sres;        /* ... and the eight result words of a step */
     bool sslot_used[ZS_STREAM_SLOTS];
+    uint8_t *h_stage[2 * ZS_STAGE_BUFS];  /* pinned staging: [0, ZS_STAGE_BUFS) host -> device, the rest device -> host */
+    cudaEvent_t ev_stage[2 * ZS_STAGE_BUFS];
+    bool stage_busy[2 * ZS_STAGE_BUFS];
+    ZsCopyPool *pool;
     uint32_t *d_aux;                  /* inflate: [2 * max_streams] trailer check + flags */
     uint32_t *h_aux;                  /* the same on the host (section passes read the flags) */
     uint32_t *d_cand, *h_cand;        /* sectioned inflate: [max_streams + 1] positions behind 00 00 FF FF, slot 0 = count */
@@ -218,6 +272,15 @@ static int zs_init_engine(zscgpu_engine *e, const zscgpu_config &cfg, const cuda
     ZS_CUDA_CHECK(cudaStreamCreateWithFlags(&e->stream2, cudaStreamNonBlocking));
     for (int i = 0; i < 2; i++) ZS_CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_slice[i], cudaEventDisableTiming));
     for (int i = 0; i < ZS_MAX_WAVES; i++) ZS_CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_wave[i], cudaEventDisableTiming));
+    for (int i = 0; i < 2 * ZS_STAGE_BUFS; i++) {
+        ZS_CUDA_CHECK(cudaHostAlloc((void **)&e->h_stage[i], ZS_STAGE_BYTES, cudaHostAllocDefault));
+        ZS_CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_stage[i], cudaEventDisableTiming));
+    }
+    e->pool = new ZsCopyPool();
+    {
+        const unsigned hc = std::thread::hardware_concurrency();
+        e->pool->start((int)std::max(1u, std::min(8u, hc / 2)));
+    }
     ZS_CUDA_CHECK(zs_crc_init_launch(e->stream));
     ZS_CUDA_CHECK(cudaStreamSynchronize(e->stream));
     return ZSCGPU_OK;
@@ -228,6 +291,8 @@ extern "C" void zscgpu_destroy(zscgpu_engine *e)
     if (!e) return;
     cudaSetDevice(e->cfg.device);
     if (e->stream) cudaStreamSynchronize(e->stream);
+    if (e->pool) { e->pool->stop(); delete e->pool; }
+    for (int i = 0; i < 2 * ZS_STAGE_BUFS; i++) { if (e->h_stage[i]) cudaFreeHost(e->h_stage[i]); if (e->ev_stage[i]) cudaEventDestroy(e->ev_stage[i]); }
     cudaFree(e->d_raw); cudaFree(e->d_comp); cudaFree(e->d_sym);
     cudaFreeHost(e->h_chunks); cudaFree(e->d_chunks);
     cudaFreeHost(e->h_streams); cudaFree(e->d_streams);
@@ -826,6 +891,52 @@ extern "C" int zscgpu_inflate_batch(zscgpu_engine *e, const zscgpu_stream *strea
     return zscgpu_fetch_results(e, n, res);
 }
 
+/* ----------------------------- pageable caller buffers ----------------------------- */
+/* cudaMemcpyAsync from or to pageable memory is staged by the runtime, synchronously and on one thread (8 GB/s end to
+ * end on a 1 GiB zsc_compress).  Callers of zsc_compress pass ordinary memory, so the engine stages such buffers itself:
+ * helper threads copy 8 MiB pieces into pinned buffers, the copy engine moves them, four buffers per direction keep
+ * both busy. */
+static bool zs_is_pageable(const void *p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return true; }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+static int zs_stage_h2d(zscgpu_engine *e, uint8_t *dev, const uint8_t *host, uint64_t n, cudaStream_t st)
+{
+    for (uint64_t off = 0, k = 0; off < n; off += ZS_STAGE_BYTES, k++) {
+        const int b = (int)(k % ZS_STAGE_BUFS);
+        const uint64_t m = std::min<uint64_t>(ZS_STAGE_BYTES, n - off);
+        if (e->stage_busy[b]) ZS_CUDA_CHECK(cudaEventSynchronize(e->ev_stage[b]));
+        e->pool->copy(e->h_stage[b], host + off, (size_t)m);
+        ZS_CUDA_CHECK(cudaMemcpyAsync(dev + off, e->h_stage[b], m, cudaMemcpyHostToDevice, st));
+        ZS_CUDA_CHECK(cudaEventRecord(e->ev_stage[b], st));
+        e->stage_busy[b] = true;
+    }
+    return ZSCGPU_OK;
+}
+/* returns when `host` holds the bytes */
+static int zs_stage_d2h(zscgpu_engine *e, uint8_t *host, const uint8_t *dev, uint64_t n, cudaStream_t st)
+{
+    const uint64_t pieces = (n + ZS_STAGE_BYTES - 1) / ZS_STAGE_BYTES;
+    auto issue = [&](uint64_t k) -> cudaError_t {
+        const int b = ZS_STAGE_BUFS + (int)(k % ZS_STAGE_BUFS);
+        const uint64_t off = k * ZS_STAGE_BYTES, m = std::min<uint64_t>(ZS_STAGE_BYTES, n - off);
+        cudaError_t ce = cudaMemcpyAsync(e->h_stage[b], dev + off, m, cudaMemcpyDeviceToHost, st);
+        if (ce != cudaSuccess) return ce;
+        return cudaEventRecord(e->ev_stage[b], st);
+    };
+    for (uint64_t k = 0; k < pieces && k < ZS_STAGE_BUFS - 1; k++) ZS_CUDA_CHECK(issue(k));
+    for (uint64_t k = 0; k < pieces; k++) {
+        if (k + ZS_STAGE_BUFS - 1 < pieces) ZS_CUDA_CHECK(issue(k + ZS_STAGE_BUFS - 1));
+        const int b = ZS_STAGE_BUFS + (int)(k % ZS_STAGE_BUFS);
+        const uint64_t off = k * ZS_STAGE_BYTES, m = std::min<uint64_t>(ZS_STAGE_BYTES, n - off);
+        ZS_CUDA_CHECK(cudaEventSynchronize(e->ev_stage[b]));
+        e->pool->copy(host + off, e->h_stage[b], (size_t)m);
+    }
+    return ZSCGPU_OK;
+}
+
 /* ----------------------------- one-shot host-buffer calls ----------------------------- */
 /* The zsc_pub.h entry points land here: copy in, run the batch of one stream, copy out.  The engine's `call_mu`
  * serialises whole calls on ONE engine because they all use offset 0 of its arenas; calls on different engines
@@ -844,7 +955,8 @@ static int zs_compress_host_waves(zscgpu_engine *e, uint8_t *dest, uint32_t dest
     auto wave_len = [&](uint32_t w) -> uint64_t { const uint64_t off = (uint64_t)w * W; return (src_len - off < W) ? src_len - off : W; };
     /* every upload is queued at once on its own stream (one event per wave): the copy engine never waits for
        the host, and the kernels of a wave start the moment its bytes have landed */
-    for (uint32_t w = 0; w < nw; w++) {
+    const bool src_pageable = zs_is_pageable(src), dst_pageable = zs_is_pageable(dest);
+    for (uint32_t w = 0; w < nw && !src_pageable; w++) {
         const uint64_t off = (uint64_t)w * W;
         ZS_CUDA_CHECK(cudaMemcpyAsync(e->d_raw + off, src + off, wave_len(w), cudaMemcpyHostToDevice, e->copy_stream));
         ZS_CUDA_CHECK(cudaEventRecord(e->ev_wave[w], e->copy_stream));
@@ -875,7 +987,8 @@ static int zs_compress_host_waves(zscgpu_engine *e, uint8_t *dest, uint32_t dest
         const uint32_t produced = e->h_produced[sl.stream0], adler = e->h_check[sl.stream0];
         if (ret != 0) { res->ret = ret; stop = true; return ZSCGPU_OK; }
         if (out_pos + produced + (p->wrap == 1 ? 4u : 0u) > dest_cap) { res->ret = -5; stop = true; return ZSCGPU_OK; }
-        ZS_CUDA_CHECK(cudaMemcpyAsync(dest + out_pos, e->d_comp + coff[v], produced, cudaMemcpyDeviceToHost, e->d2h_stream));
+        if (dst_pageable) { int sr = zs_stage_d2h(e, dest + out_pos, e->d_comp + coff[v], produced, e->d2h_stream); if (sr) return sr; }
+        else ZS_CUDA_CHECK(cudaMemcpyAsync(dest + out_pos, e->d_comp + coff[v], produced, cudaMemcpyDeviceToHost, e->d2h_stream));
         out_pos += produced;
         check = (p->wrap == 2) ? zscgpu_crc32_combine(check, crc_h[1], wave_len(v)) : zscgpu_adler32_combine(check, adler, wave_len(v));
         return ZSCGPU_OK;
@@ -884,6 +997,11 @@ static int zs_compress_host_waves(zscgpu_engine *e, uint8_t *dest, uint32_t dest
     for (uint32_t w = 0; w < nw && rc == ZSCGPU_OK && !stop; w++) {
         const ZsSlice &sl = sl2[w & 1];
         const uint64_t off = (uint64_t)w * W, len = wave_len(w);
+        if (src_pageable) {
+            /* staged while the kernels of the previous wave run */
+            rc = zs_stage_h2d(e, e->d_raw + off, src + off, len, e->copy_stream); if (rc) break;
+            ZS_CUDA_CHECK(cudaEventRecord(e->ev_wave[w], e->copy_stream));
+        }
         ZS_CUDA_CHECK(cudaStreamWaitEvent(sl.st, e->ev_wave[w], 0));
         zscgpu_stream st;
         st.raw_off = off; st.raw_len = (uint32_t)len; st.comp_off = comp_off; st.comp_len = (uint32_t)room(len);
@@ -951,7 +1069,8 @@ extern "C" int zscgpu_compress_host(zscgpu_engine *e, uint8_t *dest, uint32_t de
             return zs_compress_host_waves(e, dest, dest_cap, src, src_len, p, comp_skip, res, W, (uint32_t)nw);
     }
     if (p->hist_len > src_len) { snprintf(e->err, sizeof(e->err), "hist_len exceeds the source"); return ZSCGPU_ERR_ARG; }
-    int r = zscgpu_upload_async(e, 0, 0, src, src_len); if (r) return r;
+    int r = (src_len >= (4u << 20) && zs_is_pageable(src)) ? zs_stage_h2d(e, e->d_raw, src, src_len, e->stream) : zscgpu_upload_async(e, 0, 0, src, src_len);
+    if (r) return r;
     zscgpu_stream st;
     const uint32_t dskip = (comp_skip + 3u) & ~3u;          /* where the stream lies in the comp arena (word aligned) */
     st.raw_off = p->hist_len; st.raw_len = src_len - p->hist_len; st.comp_off = dskip;     /* src = history, then the data */
@@ -967,7 +1086,10 @@ extern "C" int zscgpu_compress_host(zscgpu_engine *e, uint8_t *dest, uint32_t de
         ZS_CUDA_CHECK(cudaStreamSynchronize(e->stream));
         res->check = h[1];
     }
-    if (res->ret == 0 && res->produced) return zscgpu_download(e, 1, dest + comp_skip, dskip, res->produced);
+    if (res->ret == 0 && res->produced) {
+        if (res->produced >= (4u << 20) && zs_is_pageable(dest)) return zs_stage_d2h(e, dest + comp_skip, e->d_comp + dskip, res->produced, e->stream);
+        return zscgpu_download(e, 1, dest + comp_skip, dskip, res->produced);
+    }
     return ZSCGPU_OK;
 }
 
@@ -980,7 +1102,8 @@ extern "C" int zscgpu_uncompress_host(zscgpu_engine *e, uint8_t *dest, uint32_t 
         snprintf(e->err, sizeof(e->err), "source of %u bytes exceeds the comp arena (%llu B)", src_len, (unsigned long long)e->cfg.comp_bytes);
         return ZSCGPU_ERR_CAPACITY;
     }
-    int r = zscgpu_upload_async(e, 1, 0, src, src_len); if (r) return r;
+    int r = (src_len >= (4u << 20) && zs_is_pageable(src)) ? zs_stage_h2d(e, e->d_comp, src, src_len, e->stream) : zscgpu_upload_async(e, 1, 0, src, src_len);
+    if (r) return r;
     zscgpu_stream st;
     st.raw_off = 0; st.comp_off = 0; st.comp_len = src_len;
     st.raw_len = (uint64_t)dest_cap > e->cfg.raw_bytes ? (uint32_t)e->cfg.raw_bytes : dest_cap;
@@ -990,7 +1113,10 @@ extern "C" int zscgpu_uncompress_host(zscgpu_engine *e, uint8_t *dest, uint32_t 
         snprintf(e->err, sizeof(e->err), "output exceeds the raw arena (%llu B): configure a larger engine with zscgpu_global_init", (unsigned long long)e->cfg.raw_bytes);
         return ZSCGPU_ERR_CAPACITY;
     }
-    if (res->produced) return zscgpu_download(e, 0, dest, 0, res->produced);
+    if (res->produced) {
+        if (res->produced >= (4u << 20) && zs_is_pageable(dest)) return zs_stage_d2h(e, dest, e->d_raw, res->produced, e->stream);
+        return zscgpu_download(e, 0, dest, 0, res->produced);
+    }
     return ZSCGPU_OK;
 }
 
