@@ -1074,9 +1074,14 @@ extern "C" int zscgpu_compress_host(zscgpu_engine *e, uint8_t *dest, uint32_t de
     zscgpu_stream st;
     const uint32_t dskip = (comp_skip + 3u) & ~3u;          /* where the stream lies in the comp arena (word aligned) */
     st.raw_off = p->hist_len; st.raw_len = src_len - p->hist_len; st.comp_off = dskip;     /* src = history, then the data */
-    uint64_t cap = dest_cap > comp_skip ? dest_cap - comp_skip : 0;
-    if (cap > e->cfg.comp_bytes - dskip) cap = e->cfg.comp_bytes - dskip;
-    st.comp_len = (uint32_t)cap;
+    const uint64_t cap = dest_cap > comp_skip ? dest_cap - comp_skip : 0;           /* what the caller's buffer holds */
+    /* the stream is built in the arena with all the room it can need; if it turns out larger than the caller's buffer, the
+       part that fits is handed out with Z_BUF_ERROR, as the reference leaves a filled buffer (src/zsc_compress.c:140) */
+    uint64_t room = (uint64_t)src_len + ((uint64_t)src_len >> 3) + 5ull * ((uint64_t)src_len / (p->max_block_len ? p->max_block_len : 1u) + 2) + 4096;
+    if (room < cap) room = cap;
+    if (room > e->cfg.comp_bytes - dskip) room = e->cfg.comp_bytes - dskip;
+    if (room > 0xFFFFFFFFull) room = 0xFFFFFFFFull;
+    st.comp_len = (uint32_t)room;
     r = zscgpu_deflate_enqueue(e, &st, 1, p); if (r) return r;
     if (p->wrap == 2) { r = zscgpu_crc32_enqueue(e, p->hist_len, src_len - p->hist_len); if (r) return r; }   /* of the data, not of the history in front of it */
     r = zscgpu_fetch_results(e, 1, res); if (r) return r;
@@ -1086,7 +1091,8 @@ extern "C" int zscgpu_compress_host(zscgpu_engine *e, uint8_t *dest, uint32_t de
         ZS_CUDA_CHECK(cudaStreamSynchronize(e->stream));
         res->check = h[1];
     }
-    if (res->ret == 0 && res->produced) {
+    if (res->ret == 0 && res->produced > cap) { res->ret = -5; res->produced = (uint32_t)cap; }     /* Z_BUF_ERROR, buffer filled */
+    if ((res->ret == 0 || res->ret == -5) && res->produced) {
         if (res->produced >= (4u << 20) && zs_is_pageable(dest)) return zs_stage_d2h(e, dest + comp_skip, e->d_comp + dskip, res->produced, e->stream);
         return zscgpu_download(e, 1, dest + comp_skip, dskip, res->produced);
     }

@@ -281,6 +281,7 @@ ZlibReturn zsc_compress_gzip2(U8 *dest, U32 *dest_len, const U8 *source, U32 sou
             ZSC_WARN2("In zsc_compress_gzip2(), output buffer (%u bytes) was smaller than bound (%u bytes). "
                       "Output may not have fit in the buffer.", dest_len_in, bound);
         }
+        if (res.ret == Z_BUF_ERROR) *dest_len = hlen + res.produced;      /* total_out: what was written before the room ran out (reference src/zsc_compress.c:140) */
         return (ZlibReturn)res.ret;
     }
     U32 total = hlen + res.produced;
