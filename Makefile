@@ -19,7 +19,7 @@ all: $(LIB) testlibs
 build:
 	mkdir -p build
 
-build/%.o: zsc_b200/csrc/cuda/%.cu zsc_b200/csrc/cuda/inflate_group.inc zsc_b200/csrc/cuda/common.cuh zsc_b200/csrc/cuda/lz_common.cuh zsc_b200/csrc/cuda/huff_build.h zsc_b200/csrc/cuda/inflate_core.h include/zscgpu.h | build
+build/%.o: zsc_b200/csrc/cuda/%.cu zsc_b200/csrc/cuda/inflate_group.inc zsc_b200/csrc/cuda/inflate_spec.inc zsc_b200/csrc/cuda/inflate_spec.h zsc_b200/csrc/cuda/common.cuh zsc_b200/csrc/cuda/lz_common.cuh zsc_b200/csrc/cuda/huff_build.h zsc_b200/csrc/cuda/inflate_core.h include/zscgpu.h | build
 	$(NVCC) $(NVFLAGS) -c $< -o $@
 
 build/zsc_%.o: zsc_b200/csrc/host/zsc_%.c include/zsc/zsc_pub.h include/zsc/zlib.h include/zscgpu.h | build
@@ -28,14 +28,18 @@ build/zsc_%.o: zsc_b200/csrc/host/zsc_%.c include/zsc/zsc_pub.h include/zsc/zlib
 $(LIB): $(CU_OBJS) build/zsc_api.o build/zsc_stream.o
 	$(NVCC) $(ARCH) -shared -o $@ $^ -Xlinker -Bsymbolic -cudart static -lpthread
 
-testlibs: tests/libzsc_cpuharness.so tests/libzsc_cpuharness_n.so tools/libzscgen.so
+testlibs: tests/libzsc_cpuharness.so tests/libzsc_cpuharness_n.so tests/libzsc_cpuharness_w.so tools/libzscgen.so
 
-tests/libzsc_cpuharness.so: tests/cpu_harness.cpp zsc_b200/csrc/cuda/huff_build.h zsc_b200/csrc/cuda/inflate_core.h
+tests/libzsc_cpuharness.so: tests/cpu_harness.cpp zsc_b200/csrc/cuda/huff_build.h zsc_b200/csrc/cuda/inflate_core.h zsc_b200/csrc/cuda/inflate_spec.h
 	$(CXX) -O2 -fPIC -shared -std=c++17 -Izsc_b200/csrc/cuda -o $@ tests/cpu_harness.cpp
 
 # the same harness with the decode tables of narrow batches (10 / 8 root bits, inflate.cu namespace zn)
-tests/libzsc_cpuharness_n.so: tests/cpu_harness.cpp zsc_b200/csrc/cuda/huff_build.h zsc_b200/csrc/cuda/inflate_core.h
+tests/libzsc_cpuharness_n.so: tests/cpu_harness.cpp zsc_b200/csrc/cuda/huff_build.h zsc_b200/csrc/cuda/inflate_core.h zsc_b200/csrc/cuda/inflate_spec.h
 	$(CXX) -O2 -fPIC -shared -std=c++17 -DZI_LBITS=10 -DZI_DBITS=8 -DZI_POOL=256 -Izsc_b200/csrc/cuda -o $@ tests/cpu_harness.cpp
+
+# ... and with the speculative decoder's geometry of wide batches (regions of 256 bits, inflate.cu namespace zm)
+tests/libzsc_cpuharness_w.so: tests/cpu_harness.cpp zsc_b200/csrc/cuda/huff_build.h zsc_b200/csrc/cuda/inflate_core.h zsc_b200/csrc/cuda/inflate_spec.h
+	$(CXX) -O2 -fPIC -shared -std=c++17 -DZI_LBITS=10 -DZI_DBITS=8 -DZI_POOL=256 -DZP_R=256u -DZP_CAP=64u -Izsc_b200/csrc/cuda -o $@ tests/cpu_harness.cpp
 
 tools/libzscgen.so: tools/datagen.c
 	$(CC) -O2 -fPIC -shared -o $@ tools/datagen.c -lm -lpthread
@@ -44,7 +48,7 @@ oracle:
 	$(MAKE) -C oracle all
 
 clean:
-	rm -rf build $(LIB) tests/libzsc_cpuharness.so tests/libzsc_cpuharness_n.so tools/libzscgen.so
+	rm -rf build $(LIB) tests/libzsc_cpuharness.so tests/libzsc_cpuharness_n.so tests/libzsc_cpuharness_w.so tools/libzscgen.so
 	$(MAKE) -C oracle clean
 
 .PHONY: all testlibs oracle clean

@@ -8,6 +8,8 @@
 #include <vector>
 #include "huff_build.h"
 #include "inflate_core.h"
+#define ZP_STATS
+#include "inflate_spec.h"
 
 extern "C" {
 
@@ -31,6 +33,18 @@ int h_inflate_batched(const uint8_t *in, uint32_t in_len, uint8_t *out, uint32_t
     res7[4] = r.data_errors; res7[5] = r.stored_check; res7[6] = r.have_check;
     return r.ret;
 }
+
+// the speculative warp decoder (inflate_spec.h), lanes one after the other
+int h_inflate_spec(const uint8_t *in, uint32_t in_len, uint8_t *out, uint32_t out_cap, int wrap, uint32_t *res7, uint32_t opts)
+{
+    zi_tables T;
+    zi_result r;
+    zi_inflate_spec(in, in_len, out, out_cap, wrap, &T, &r, opts);
+    res7[0] = (uint32_t)r.ret; res7[1] = (uint32_t)r.reason; res7[2] = r.produced; res7[3] = r.consumed;
+    res7[4] = r.data_errors; res7[5] = r.stored_check; res7[6] = r.have_check;
+    return r.ret;
+}
+void h_spec_stats(uint64_t *out8, int reset) { for (int i = 0; i < 16; i++) { out8[i] = zp_stat[i]; if (reset) zp_stat[i] = 0; } }
 
 // ---------------------------------------------------------------- LZ77 model (mirrors deflate_lz.cu)
 struct LzP { int mode, chain, nice, lazy, min_len, max_dist, good, max_lazy; };

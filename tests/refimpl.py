@@ -77,8 +77,23 @@ def harness_narrow():
         L = C.CDLL(HARNESS_PATH.replace(".so", "_n.so"), mode=C.RTLD_LOCAL)
         L.h_inflate.argtypes = [u8p, C.c_uint32, u8p, C.c_uint32, C.c_int, u32p]
         L.h_inflate_batched.argtypes = [u8p, C.c_uint32, u8p, C.c_uint32, C.c_int, u32p, C.c_uint32]
+        L.h_inflate_spec.argtypes = [u8p, C.c_uint32, u8p, C.c_uint32, C.c_int, u32p, C.c_uint32]
         _har_n = L
     return _har_n
+
+
+_har_w = None
+
+
+def harness_wide():
+    """the harness compiled with the speculative decoder's geometry of wide batches (regions of 256 bits)"""
+    global _har_w
+    if _har_w is None:
+        L = C.CDLL(HARNESS_PATH.replace(".so", "_w.so"), mode=C.RTLD_LOCAL)
+        L.h_inflate.argtypes = [u8p, C.c_uint32, u8p, C.c_uint32, C.c_int, u32p]
+        L.h_inflate_spec.argtypes = [u8p, C.c_uint32, u8p, C.c_uint32, C.c_int, u32p, C.c_uint32]
+        _har_w = L
+    return _har_w
 
 
 def harness():
@@ -108,6 +123,14 @@ def h_inflate(comp, cap, wrap=1):
         H.h_inflate_batched(padded.ctypes.data_as(u8p), len(comp), out2.ctypes.data_as(u8p), cap, wrap, res2, group)
         assert list(res) == list(res2), (group, list(res), list(res2))
         assert np.array_equal(out[:res[2]], out2[:res2[2]])
+    # the speculative warp decoder (inflate_spec.h, lanes one after the other), in both of its geometries, writing and counting
+    for H in (harness_narrow(), harness_wide()):
+        for opts in (0, 1):
+            out2 = np.zeros(max(cap, 1), dtype=np.uint8)
+            res2 = (C.c_uint32 * 7)()
+            H.h_inflate_spec(padded.ctypes.data_as(u8p), len(comp), out2.ctypes.data_as(u8p), cap, wrap, res2, opts)
+            assert list(res) == list(res2), ("spec", opts, list(res), list(res2))
+            assert opts or np.array_equal(out[:res[2]], out2[:res2[2]])
     res3 = (C.c_uint32 * 7)()
     out3 = np.zeros(max(cap, 1), dtype=np.uint8)
     harness_narrow().h_inflate(padded.ctypes.data_as(u8p), len(comp), out3.ctypes.data_as(u8p), cap, wrap, res3)

@@ -236,6 +236,45 @@ def test_inflate_batch_of_reference_streams(engine, checker):
         assert np.array_equal(out, x)
 
 
+@pytest.mark.parametrize("n", [96, 900])
+def test_inflate_batch_with_corrupted_streams_equals_reference(engine, n):
+    """a batch in which every third stream is damaged, at both widths of the speculative warp decoder (96 streams: each
+    stream's window in shared memory; 900: without): code, counts and bytes of every stream as the reference's
+    zsc_uncompress (src/zsc_uncompr.c:103-127, recovery at the next marker included)"""
+    if not refimpl.have_ref():
+        pytest.skip("oracle/_ref not present")
+    R = refimpl.ref()
+    rng = np.random.default_rng(5)
+    uniq = []
+    for i in range(12):
+        x = datagen.fill(70000 + 997 * i, 300 + i, (datagen.MIXED, datagen.TELEMETRY, datagen.TEXT)[i % 3], piece=1 << 20)
+        rc, c = R.compress(x, 20000 if i % 2 else 262144, (1, 6, 9)[i % 3])
+        assert rc == 0
+        uniq.append((x, c))
+    coff, roff, desc, comps, caps = 0, 0, [], [], []
+    for i in range(n):
+        x, c = uniq[i % len(uniq)]
+        c = c.copy()
+        if i % 3 == 1:
+            c[int(rng.integers(2, len(c)))] ^= 1 << int(rng.integers(0, 8))
+        elif i % 9 == 2:
+            c = c[:int(rng.integers(len(c) // 2, len(c)))]
+        cap = len(x) if i % 5 else len(x) - 1000                       # some outputs do not fit
+        engine.upload(1, coff, c)
+        desc.append((roff, cap, coff, len(c))); comps.append(c); caps.append(cap)
+        coff += len(c) + 1; roff += cap + 3
+    res = engine.inflate(Engine.make_streams(*zip(*desc)), 1)
+    rets, prods, outs = refimpl.ref_uncompress_batch(np.concatenate(comps), np.cumsum([0] + [len(c) for c in comps[:-1]]), [len(c) for c in comps], caps)
+    ro = 0
+    seen = set()
+    for i, (d, r) in enumerate(zip(desc, res)):
+        assert r.ret == rets[i] and r.produced == prods[i], (i, r.ret, rets[i], r.produced, prods[i])
+        assert np.array_equal(engine.download(0, d[0], r.produced), outs[ro:ro + prods[i]]), i
+        ro += caps[i]
+        seen.add(r.ret)
+    assert {0, capi.Z_DATA_ERROR, capi.Z_BUF_ERROR} <= seen
+
+
 def test_inflate_corruption_recovery_matches_checker(checker):
     """flip one byte (reference test/zlib_gtest.cpp:696-699): same code, same recovered bytes as the checker"""
     Z = capi.zsc()

@@ -57,4 +57,15 @@ for g in gs:
     for _ in range(3):
         E.event(0); E.relaunch(); E.event(1); E.sync(); ts.append(E.elapsed_ms(0, 1))
     print("lib", os.environ.get("ZSC_B200_LIB", "default"), "G", g, "streams", n, "bad", bad, "bytes_ok", ok, "ms", [round(t, 2) for t in ts], "GB/s", round(n * S / 1e6 / min(ts), 2), flush=True)
+import ctypes as _C
+try:
+    _L = _C.CDLL(os.environ.get("ZSC_B200_LIB") or os.path.join(ROOT, "zsc_b200", "libzsc_b200.so"))
+    _f = _L.zs_inflate_spec_prof
+    a = (_C.c_uint64 * 16)(); _f(a, 1); a = list(a)
+    launches = 4
+    names = ["setup", "phase1", "phase2", "chain+measure", "emit", "flush", "cursor", "old path"]
+    rounds = max(a[8], 1)
+    print("spec profile per round (cycles of lane 0):", {nm: round(a[i] / rounds) for i, nm in enumerate(names)}, "rounds/stream", round(a[8] / launches / n, 1), "sym/round", round(a[9] / rounds), "bytes/round", round(a[10] / rounds), "kernel cycles/stream", round(a[11] / launches / n))
+except AttributeError:
+    pass
 E.close()

@@ -31,7 +31,28 @@ namespace zw {
 namespace zn {
 #include "inflate_core.h"
 #include "inflate_group.inc"
+#include "inflate_spec.h"
+#include "inflate_spec.inc"
 }
+/* The speculative warp decoder (inflate_spec.h) exists twice as well: `zn` with regions of 384 bits and each stream's
+ * window in shared memory (50 KB per stream, 4 per SM: few streams, latency decides), `zm` with regions of 256 bits and
+ * no window (12 KB per stream, 18 per SM: the batch fills the machine).  Same code, same results. */
+#ifndef ZP_WIDE_R
+#define ZP_WIDE_R 256u
+#define ZP_WIDE_CAP 64u
+#endif
+#undef ZP_R
+#undef ZP_CAP
+#define ZP_R ZP_WIDE_R
+#define ZP_CAP ZP_WIDE_CAP
+#define ZP_NO_PROFILE
+namespace zm {
+#include "inflate_core.h"
+#include "inflate_group.inc"
+#include "inflate_spec.h"
+#include "inflate_spec.inc"
+}
+#undef ZP_NO_PROFILE
 #undef ZI_REINCLUDE
 using namespace zw;                                          /* the streaming kernel below uses the compact geometry */
 
@@ -39,7 +60,9 @@ using namespace zw;                                          /* the streaming ke
 
 #ifndef ZS_INFLATE_WARP_MAX
 #define ZS_INFLATE_WARP_MAX 6144u                /* streams in a batch up to which each gets a whole warp */
-#define ZS_INFLATE_G16_MAX 12288u                /* ... and up to which each gets half a warp; beyond, a quarter */
+#define ZS_INFLATE_G16_MAX 12288u
+#define ZS_INFLATE_RING_MAX 640u                 /* streams in a batch up to which the speculative warp decoder keeps each stream's window in shared memory (4 x 148 fit at once) */
+#define ZS_INFLATE_SPEC_MAX 12288u               /* ... and up to which it is used at all */                /* ... and up to which each gets half a warp; beyond, a quarter */
 #endif
 
 __global__ void zs_inflate_check_kernel(uint32_t n, const ZsAdlerAcc *__restrict__ acc, const uint32_t *__restrict__ produced,
@@ -226,7 +249,15 @@ extern "C" cudaError_t zs_inflate_launch(cudaStream_t st, uint32_t n, const ZsSt
 #ifdef ZSC_TUNING
     if (getenv("ZSC_B200_INFLATE_G")) g = (uint32_t)atoi(getenv("ZSC_B200_INFLATE_G"));
 #endif
-    cudaError_t ge = g == 32 ? zn::zs_inflate_group_launch<32>(st, n, streams, comp, raw, wrap, ret, produced, consumed, aux, reinterpret_cast<zn::zi_aux *>(counter))
+    /* up to ZS_INFLATE_SPEC_MAX streams: a warp per stream with all of its lanes decoding (inflate_spec.inc), 1 = with the
+       stream's window in shared memory, 2 = without; beyond, quarter-warp groups with one decoding lane each */
+    int spec = n <= ZS_INFLATE_RING_MAX ? 1 : (n <= ZS_INFLATE_SPEC_MAX ? 2 : 0);
+#ifdef ZSC_TUNING
+    if (getenv("ZSC_B200_INFLATE_SPEC")) spec = atoi(getenv("ZSC_B200_INFLATE_SPEC"));
+#endif
+    cudaError_t ge = spec == 1 ? zn::zs_inflate_spec_launch<true>(st, n, streams, comp, raw, wrap, ret, produced, consumed, aux, reinterpret_cast<zn::zi_aux *>(counter))
+                   : spec == 2 ? zm::zs_inflate_spec_launch<false>(st, n, streams, comp, raw, wrap, ret, produced, consumed, aux, reinterpret_cast<zm::zi_aux *>(counter))
+                   : g == 32 ? zn::zs_inflate_group_launch<32>(st, n, streams, comp, raw, wrap, ret, produced, consumed, aux, reinterpret_cast<zn::zi_aux *>(counter))
                    : g == 16 ? zn::zs_inflate_group_launch<16>(st, n, streams, comp, raw, wrap, ret, produced, consumed, aux, reinterpret_cast<zn::zi_aux *>(counter))
                              : zw::zs_inflate_group_launch<8>(st, n, streams, comp, raw, wrap, ret, produced, consumed, aux, reinterpret_cast<zw::zi_aux *>(counter));
     if (ge != cudaSuccess) return ge;

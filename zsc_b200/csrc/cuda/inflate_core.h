@@ -183,6 +183,15 @@ ZID uint32_t zi_rev(uint32_t v, int n)
     return r;
 }
 
+ZID int zi_popc(uint32_t v)
+{
+#ifdef __CUDA_ARCH__
+    return __popc(v);
+#else
+    return __builtin_popcount(v);
+#endif
+}
+
 /* Build one alphabet's tables from code lengths. kind 0: code-length/literal alphabets must be
  * complete; an incomplete set is tolerated only when its longest code is 1 bit and kind != 0
  * (same rule as the reference, src/inftrees.c:168-177).  Returns 0 or -1. */
