@@ -148,6 +148,7 @@ int zscgpu_inflate_sectioned(zscgpu_engine *e, const zscgpu_stream *stream, int3
 /* The section size zscgpu_inflate_sectioned tries first (one decode pass instead of two) for a stream of `sections`
  * flush-delimited sections whose data fills `total` bytes; 0 when no plausible uniform size exists.  Pure arithmetic. */
 uint64_t zscgpu_guess_section_size(uint64_t total, uint32_t sections);
+uint64_t zscgpu_guess_section_size10(uint64_t total, uint32_t sections);   /* ... the same with decimal roundness */
 int zscgpu_fetch_results(zscgpu_engine *e, uint32_t n, zscgpu_result *res);
 /* Re-launch the kernels of the last enqueue without rebuilding descriptors (bench inner loop). */
 int zscgpu_relaunch(zscgpu_engine *e);

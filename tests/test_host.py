@@ -58,6 +58,20 @@ def test_section_size_guess_of_the_one_pass_inflate():
     assert f((1 << 30), 4096) == 262144 and f((1 << 30) + 5, 4097) == 262144
     assert f(10, 2) == 0 and f(5, 8) == 0 and f(1000, 1) == 0
     assert f(8 * 1000 + 1, 9) == 0                      # the range [889, 1000] holds no multiple of 256
+    # the decimal twin: a max_block_len like the reference's own Performance test uses (100 000, test/zlib_gtest.cpp:2400-2892)
+    f10 = L.zscgpu_guess_section_size10
+    f10.argtypes = [C.c_uint64, C.c_uint32]; f10.restype = C.c_uint64
+    for mbl in (1000, 50000, 100000, 250000, 3000000):
+        for _ in range(200):
+            k = int(rng.integers(2, 3000))
+            total = (k - 1) * mbl + int(rng.integers(1, mbl + 1))
+            if total >= 1 << 32:
+                continue
+            g = f10(total, k)
+            assert g == 0 or ((k - 1) * g < total <= k * g)
+            if k >= 300:
+                assert g == mbl, (mbl, k, total, g)     # (with few sections another equally round number may share the range)
+    assert f10(1029744, 11) == 100000 and f10(152089, 2) == 100000 and f10(10, 2) == 0
 
 
 def test_size_check_functions_match_reference_fixture():

@@ -61,11 +61,13 @@ import ctypes as _C
 try:
     _L = _C.CDLL(os.environ.get("ZSC_B200_LIB") or os.path.join(ROOT, "zsc_b200", "libzsc_b200.so"))
     _f = _L.zs_inflate_spec_prof
-    a = (_C.c_uint64 * 16)(); _f(a, 1); a = list(a)
+    a = (_C.c_uint64 * 24)(); _f(a, 1); a = list(a)
     launches = 4
     names = ["setup", "phase1", "phase2", "chain+measure", "emit", "flush", "cursor", "old path"]
     rounds = max(a[8], 1)
     print("spec profile per round (cycles of lane 0):", {nm: round(a[i] / rounds) for i, nm in enumerate(names)}, "rounds/stream", round(a[8] / launches / n, 1), "sym/round", round(a[9] / rounds), "bytes/round", round(a[10] / rounds), "kernel cycles/stream", round(a[11] / launches / n))
+    sw = max(a[20], 1)
+    print("emit per sweep: sweeps/round", round(a[20] / rounds, 1), "level calc", round(a[13] / sw), "own copies", round(a[14] / sw), "long copies + sync", round(a[15] / sw), "levels", round(a[16] / sw, 2), "matches", round(a[17] / sw, 1), "reaching in", round(a[18] / sw, 1), "long", round(a[19] / sw, 2), "fetch + scan", round(a[12] / sw))
 except AttributeError:
     pass
 E.close()

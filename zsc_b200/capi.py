@@ -52,7 +52,7 @@ ZSCGPU_SYMBOLS = [
     "zscgpu_upload_async", "zscgpu_download_async", "zscgpu_sync", "zscgpu_copy_within",
     "zscgpu_host_register", "zscgpu_host_unregister", "zscgpu_deflate_batch", "zscgpu_inflate_batch",
     "zscgpu_deflate_enqueue", "zscgpu_inflate_enqueue", "zscgpu_inflate_sectioned", "zscgpu_fetch_results", "zscgpu_relaunch",
-    "zscgpu_last_launch_count", "zscgpu_launch_total", "zscgpu_guess_section_size", "zscgpu_compress_host", "zscgpu_uncompress_host", "zscgpu_checksum_host",
+    "zscgpu_last_launch_count", "zscgpu_launch_total", "zscgpu_guess_section_size", "zscgpu_guess_section_size10", "zscgpu_compress_host", "zscgpu_uncompress_host", "zscgpu_checksum_host",
     "zscgpu_adler32", "zscgpu_crc32", "zscgpu_adler32_enqueue", "zscgpu_crc32_enqueue",
     "zscgpu_event_record", "zscgpu_event_elapsed_ms", "zscgpu_debug_fetch_symbols",
     "zscgpu_adler32_combine", "zscgpu_crc32_combine",

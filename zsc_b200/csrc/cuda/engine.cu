@@ -86,6 +86,8 @@ struct ZsCopyPool {
 #define ZS_STREAM_HIST 32768u
 #define ZS_MAX_WAVES 64
 
+#define ZS_SEC_SCRATCH (16ull << 20)           /* behind the raw arena: where zscgpu_inflate_sectioned tries a second section size */
+#define ZS_SEC_SMALL 256u                      /* sections up to which it tries two sizes and measures in the same launch */
 struct zscgpu_engine {
     zscgpu_config cfg;
     int sms;
@@ -217,7 +219,7 @@ static int zs_init_engine(zscgpu_engine *e, const zscgpu_config &cfg, const cuda
     e->launches = 0;
     ZS_CUDA_CHECK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     /* arenas, padded so that vector loads and word-granular stores at the ends stay inside */
-    ZS_CUDA_CHECK(zs_dev(&e->d_raw, cfg.raw_bytes + 4096));
+    ZS_CUDA_CHECK(zs_dev(&e->d_raw, cfg.raw_bytes + 4096 + ZS_SEC_SCRATCH + 4096));   /* + the scratch of zscgpu_inflate_sectioned */
     ZS_CUDA_CHECK(zs_dev(&e->d_comp, cfg.comp_bytes + 4096));
     e->sym_cap = cfg.deflate_batch_max + 4ull * cfg.max_chunks + 64;
     ZS_CUDA_CHECK(zs_dev(&e->d_sym, e->sym_cap));
@@ -658,9 +660,10 @@ static int zs_inflate_enqueue_opts(zscgpu_engine *e, const zscgpu_stream *stream
     ZS_ENTER(e);
     if (!streams || n == 0 || n > e->cfg.max_streams || (wrap & 0xFF) > 1 || wrap < 0) { snprintf(e->err, sizeof(e->err), "bad inflate batch arguments"); return ZSCGPU_ERR_ARG; }
     uint32_t max_raw = 0;
+    const uint64_t raw_room = e->cfg.raw_bytes + (opts ? 4096 + ZS_SEC_SCRATCH : 0);   /* (section passes may use the scratch) */
     for (uint32_t s = 0; s < n; s++) {
         const zscgpu_stream *z = &streams[s];
-        if (z->raw_off > e->cfg.raw_bytes || z->raw_len > e->cfg.raw_bytes - z->raw_off ||
+        if (z->raw_off > raw_room || z->raw_len > raw_room - z->raw_off ||
             z->comp_off > e->cfg.comp_bytes || z->comp_len > e->cfg.comp_bytes - z->comp_off) {
             snprintf(e->err, sizeof(e->err), "stream %u lies outside the arenas", s);
             return ZSCGPU_ERR_CAPACITY;
@@ -728,6 +731,24 @@ extern "C" uint64_t zscgpu_guess_section_size(uint64_t total, uint32_t sections)
     return 0;
 }
 
+/* ... and the value with the most trailing decimal zeros (at least two): max_block_len = 100 000 is as round as 131 072 */
+extern "C" uint64_t zscgpu_guess_section_size10(uint64_t total, uint32_t sections)
+{
+    if (sections < 2 || total < sections) return 0;
+    const uint64_t K = sections;
+    const uint64_t lo = (total + K - 1) / K, hi = (total - 1) / (K - 1);
+    for (uint64_t p = 1000000000ull; p >= 100; p /= 10) { const uint64_t x = (hi / p) * p; if (x >= lo && x > 0) return x; }
+    return 0;
+}
+static double zs_roundness(uint64_t x)          /* in bits */
+{
+    if (!x) return 0;
+    int b = 0, d = 0;
+    while (!((x >> b) & 1)) b++;
+    for (uint64_t y = x; y % 10 == 0; y /= 10) d++;
+    return b > 3.32 * d ? b : 3.32 * d;
+}
+
 extern "C" int zscgpu_inflate_sectioned(zscgpu_engine *e, const zscgpu_stream *stream, int32_t wrap, zscgpu_result *res)
 {
     ZS_ENTER(e);
@@ -772,9 +793,57 @@ extern "C" int zscgpu_inflate_sectioned(zscgpu_engine *e, const zscgpu_stream *s
        The result stands only if the sections chain exactly — each but the last produced S bytes and stopped at a
        flush point exactly where the next candidate starts, the last one reached the end of the stream — and
        the data check over the whole output agrees; otherwise the two passes below run as if nothing had happened. */
-    if (ns >= 8 && stream->raw_len >= ns) {
-        const uint64_t N = stream->raw_len;
-        const uint64_t S = zscgpu_guess_section_size(N, ns);
+    /* did the sections [g0, g0 + ns) of the last launch, decoded straight to k * S, chain exactly? */
+    uint64_t g_total = 0;
+    uint32_t g_end = 0, g_stored = 0, g_have = 0;
+    auto chained = [&](uint32_t g0, uint64_t S) -> bool {
+        g_total = 0;
+        for (uint32_t k = 0; k < ns; k++) {
+            const uint32_t f = e->h_aux[2 * (g0 + k) + 1];
+            const zscgpu_result &r = r1[g0 + k];
+            if (r.ret != 0 || (f & 2u)) return false;
+            if (k + 1 < ns) { if (!((f & 4u) && r.produced == S && start[k] + r.consumed == start[k + 1])) return false; }
+            else { if (f & 4u) return false; g_stored = e->h_aux[2 * (g0 + k)]; g_have = f & 1u; g_end = start[k] + r.consumed; }
+            g_total += r.produced;
+        }
+        return true;
+    };
+    auto accept = [&](int launches) -> int {        /* the data check over the whole output decides */
+        uint32_t check = 1;
+        int rcs = zscgpu_adler32(e, stream->raw_off, g_total, 1u, &check); if (rcs) return rcs;
+        if ((wrap & 0xFF) == 1 && g_have && g_stored != check) return 1;
+        res->ret = 0; res->produced = (uint32_t)g_total; res->consumed = g_end; res->check = check;
+        e->launches = launches;
+        return ZSCGPU_OK;
+    };
+    const uint64_t N = stream->raw_len;
+    bool measured = false;
+    if (ns <= ZS_SEC_SMALL && N >= ns && 3ull * ns <= e->cfg.max_streams) {
+        /* Few sections: the machine has room for several attempts at once.  One launch decodes every candidate straight to
+           k * S for the roundest binary S (in place), for the roundest decimal S (into the scratch behind the arena) and
+           once more without writing, measuring (pass 1 below).  A guess that chains and passes the data check stands. */
+        uint64_t SA = zscgpu_guess_section_size(N, ns), SB = zscgpu_guess_section_size10(N, ns);
+        if (SB == SA || N > ZS_SEC_SCRATCH) SB = 0;
+        if (!SA) { SA = SB; SB = 0; }
+        const uint64_t scratch = e->cfg.raw_bytes + 4096;
+        uint32_t n = 0, gA = 0, gB = 0, gC = 0;
+        if (SA) { gA = n; for (uint32_t k = 0; k < ns; k++, n++) { st[n].raw_off = stream->raw_off + (uint64_t)k * SA; st[n].raw_len = (uint32_t)(k + 1 < ns ? SA : N - (uint64_t)k * SA); st[n].comp_off = stream->comp_off + start[k]; st[n].comp_len = stream->comp_len - start[k]; opts[n] = 2u | (k ? 4u : 0u); } }
+        if (SB) { gB = n; for (uint32_t k = 0; k < ns; k++, n++) { st[n].raw_off = scratch + (uint64_t)k * SB; st[n].raw_len = (uint32_t)(k + 1 < ns ? SB : N - (uint64_t)k * SB); st[n].comp_off = stream->comp_off + start[k]; st[n].comp_len = stream->comp_len - start[k]; opts[n] = 2u | (k ? 4u : 0u); } }
+        gC = n;
+        for (uint32_t k = 0; k < ns; k++, n++) { st[n].raw_off = stream->raw_off; st[n].raw_len = stream->raw_len; st[n].comp_off = stream->comp_off + start[k]; st[n].comp_len = stream->comp_len - start[k]; opts[n] = 1u | 2u | (k ? 4u : 0u); }
+        int rcs = zs_inflate_enqueue_opts(e, st, n, wrap, opts); if (rcs) return rcs;
+        rcs = zscgpu_fetch_results(e, n, r1); if (rcs) return rcs;
+        if (SA && chained(gA, SA)) { rcs = accept(3); if (rcs <= 0) return rcs; }
+        if (SB && chained(gB, SB)) {
+            ZS_CUDA_CHECK(cudaMemcpyAsync(e->d_raw + stream->raw_off, e->d_raw + scratch, g_total, cudaMemcpyDeviceToDevice, e->stream));
+            rcs = accept(3); if (rcs <= 0) return rcs;
+        }
+        for (uint32_t k = 0; k < ns; k++) { r1[k] = r1[gC + k]; trailer[k] = e->h_aux[2 * (gC + k)]; flags[k] = e->h_aux[2 * (gC + k) + 1]; }
+        measured = true;
+    } else if (ns >= 8 && N >= ns) {
+        /* Many sections: one attempt, with the rounder of the two guesses (in bits: 3.32 per decimal zero). */
+        const uint64_t Sb = zscgpu_guess_section_size(N, ns), Sd = zscgpu_guess_section_size10(N, ns);
+        const uint64_t S = zs_roundness(Sd) > zs_roundness(Sb) ? Sd : Sb;
         if (S) {
             for (uint32_t k = 0; k < ns; k++) {
                 st[k].raw_off = stream->raw_off + (uint64_t)k * S;
@@ -784,37 +853,22 @@ extern "C" int zscgpu_inflate_sectioned(zscgpu_engine *e, const zscgpu_stream *s
             }
             int rcs = zs_inflate_enqueue_opts(e, st, ns, wrap, opts); if (rcs) return rcs;
             rcs = zscgpu_fetch_results(e, ns, r1); if (rcs) return rcs;
-            bool good = true;
-            uint64_t total = 0;
-            uint32_t end_pos = 0, stored_check = 0, have_check = 0;
-            for (uint32_t k = 0; k < ns && good; k++) {
-                const uint32_t f = e->h_aux[2 * k + 1];
-                if (r1[k].ret != 0 || (f & 2u)) good = false;
-                else if (k + 1 < ns) good = (f & 4u) && r1[k].produced == S && start[k] + r1[k].consumed == start[k + 1];
-                else { good = !(f & 4u); stored_check = e->h_aux[2 * k]; have_check = f & 1u; end_pos = start[k] + r1[k].consumed; }
-                total += r1[k].produced;
-            }
-            if (good) {
-                uint32_t check = 1;
-                rcs = zscgpu_adler32(e, stream->raw_off, total, 1u, &check); if (rcs) return rcs;
-                if (!((wrap & 0xFF) == 1 && have_check && stored_check != check)) {
-                    res->ret = 0; res->produced = (uint32_t)total; res->consumed = end_pos; res->check = check;
-                    e->launches = 3;   /* marker scan, decode pass, adler32 */
-                    return ZSCGPU_OK;
-                }
-            }
+            if (chained(0, S)) { rcs = accept(3); if (rcs <= 0) return rcs; }
         }
     }
 
     /* pass 1: sizes */
-    for (uint32_t k = 0; k < ns; k++) {
-        st[k].raw_off = stream->raw_off; st[k].raw_len = stream->raw_len;
-        st[k].comp_off = stream->comp_off + start[k]; st[k].comp_len = stream->comp_len - start[k];
-        opts[k] = 1u | 2u | (k ? 4u : 0u);
+    int rc = 0;
+    if (!measured) {
+        for (uint32_t k = 0; k < ns; k++) {
+            st[k].raw_off = stream->raw_off; st[k].raw_len = stream->raw_len;
+            st[k].comp_off = stream->comp_off + start[k]; st[k].comp_len = stream->comp_len - start[k];
+            opts[k] = 1u | 2u | (k ? 4u : 0u);
+        }
+        rc = zs_inflate_enqueue_opts(e, st, ns, wrap, opts); if (rc) return rc;
+        rc = zscgpu_fetch_results(e, ns, r1); if (rc) return rc;
+        for (uint32_t k = 0; k < ns; k++) { trailer[k] = e->h_aux[2 * k]; flags[k] = e->h_aux[2 * k + 1]; }
     }
-    int rc = zs_inflate_enqueue_opts(e, st, ns, wrap, opts); if (rc) return rc;
-    rc = zscgpu_fetch_results(e, ns, r1); if (rc) return rc;
-    for (uint32_t k = 0; k < ns; k++) { trailer[k] = e->h_aux[2 * k]; flags[k] = e->h_aux[2 * k + 1]; }
 
     /* the chain of real sections */
     uint64_t total = 0;
@@ -1113,7 +1167,7 @@ extern "C" int zscgpu_uncompress_host(zscgpu_engine *e, uint8_t *dest, uint32_t 
     zscgpu_stream st;
     st.raw_off = 0; st.comp_off = 0; st.comp_len = src_len;
     st.raw_len = (uint64_t)dest_cap > e->cfg.raw_bytes ? (uint32_t)e->cfg.raw_bytes : dest_cap;
-    r = (src_len >= (64u << 10)) ? zscgpu_inflate_sectioned(e, &st, wrap, res) : zscgpu_inflate_batch(e, &st, 1, wrap, res);
+    r = (src_len >= (8u << 10)) ? zscgpu_inflate_sectioned(e, &st, wrap, res) : zscgpu_inflate_batch(e, &st, 1, wrap, res);
     if (r) return r;
     if (st.raw_len < dest_cap && res->ret == -5 && res->produced == st.raw_len) {
         snprintf(e->err, sizeof(e->err), "output exceeds the raw arena (%llu B): configure a larger engine with zscgpu_global_init", (unsigned long long)e->cfg.raw_bytes);

@@ -259,10 +259,16 @@ static inline uint32_t zp_round_host(zi_mach *m, const uint32_t *lut_len, const 
     for (uint32_t k = 0; k < R.nl; k++) {
         if (!L[k].valid) continue;
         zp_measure(&L[k], S, k);
+        if (total + L[k].sum > room) {
+            /* the output ends inside this round: the chain is cut behind the last lane whose symbols still fit */
+            if (k == 0) bad = 1;
+            for (uint32_t j = k; j < R.nl; j++) L[j].valid = 0;
+            break;
+        }
+        last = k;
         L[k].start = op0 + total;
         if (L[k].reach > (uint32_t)(L[k].start - floor_)) bad = 1;
-        total += L[k].sum; nsym += L[k].nrec - L[k].a;
-        if (total > room) bad = 1;                                    /* (sums stay far below 2^32: 32 lanes x 64 symbols x 258) */
+        total += L[k].sum; nsym += L[k].nrec - L[k].a;            /* (sums stay far below 2^32: 32 lanes x 96 symbols x 258) */
     }
 #ifdef ZP_STATS
     zp_stat[0]++; zp_stat[5] += R.nl;
