@@ -251,9 +251,25 @@ def inflate_config3(device, rank, world, barrier, allmax, peak):
         out = {"value": round(n_all * S / 1e6 / t, 2), "unit": "GB/s of output", "ms": round(t, 2), "streams": n_all, "output_bytes": n_all * S,
                "compressed_bytes": csum, "producer": producer, "launches_per_pass": 3, "scaling": "strong", "streams_per_rank": n,
                "parity": "all streams Z_OK with the trailer adler32 verified; first and last replica bit-exact with the inputs" if bad == 0 and same else f"MISMATCH ({bad} bad streams)",
-               "roofline": {"bound": "hbm", "kernel": "zs_inflate_group_kernel<16>", "achieved": round((n_all * S + csum) / world / 1e6 / t, 1), "peak": peak, "unit": "GB/s",
+               "roofline": {"bound": "hbm", "kernel": "zs_inflate_group_kernel<8>" if n > 12288 else "zs_inflate_spec_kernel", "achieved": round((n_all * S + csum) / world / 1e6 / t, 1), "peak": peak, "unit": "GB/s",
                             "frac": round((n_all * S + csum) / world / 1e6 / t / peak, 5), "algorithmic_bytes": (n_all * S + csum) // world,
                             "note": "C + N per pass and GPU over the whole pass (decode, output adler32, check kernels)"}}
+        if world == 1:
+            # the same streams in narrower batches: up to 12 288 streams a warp decodes one stream with all 32 lanes
+            # (zs_inflate_spec_kernel, inflate_spec.h), up to 640 with the stream's window in shared memory
+            nb = {}
+            for k in (64, 512, 4096):
+                if k > n:
+                    continue
+                stk = Engine.make_streams([i * S for i in range(k)], [S] * k, [o[0] for o in offs[:k]], [o[1] for o in offs[:k]])
+                E.inflate_enqueue(stk, 1)
+                resk = E.fetch(k)
+                okk = all(r.ret == 0 and r.produced == S for r in resk) and bool(np.array_equal(E.download(0, 0, min(k, uniq) * S), x[:min(k, uniq) * S]))
+                tk = []
+                for _ in range(3):
+                    E.sync(); E.event(0); E.relaunch(); E.event(1); E.sync(); tk.append(E.elapsed_ms(0, 1))
+                nb[str(k)] = {"value": round(k * S / 1e6 / min(tk), 2), "ms": round(min(tk), 3), "parity": "bit-exact" if okk else "MISMATCH"}
+            out["narrower_batches"] = dict(nb, unit="GB/s of output", kernel="zs_inflate_spec_kernel (a warp per stream, every lane decoding)")
         if rank == 0 and refimpl.have_ref():
             cores = os.cpu_count() or 1
             packed = np.concatenate(comps)

@@ -4,6 +4,7 @@
  * them to their device twins and launch kernels on the engine's one CUDA stream.
  */
 #include <mutex>
+#include <time.h>
 #include <condition_variable>
 #include <thread>
 #include <vector>
@@ -128,6 +129,7 @@ struct zscgpu_engine {
     cudaEvent_t ev[ZS_NEVENTS];
     cudaStream_t copy_stream, d2h_stream;   /* host-buffer calls: uploads / downloads overlap the kernels */
     cudaStream_t stream2;                   /* odd waves of a host-buffer call run here, so that they overlap the even ones */
+    cudaStream_t stream_lo;                 /* lowest priority: the second wave of zscgpu_uncompress_host takes the SM slots the first one frees */
     cudaEvent_t ev_slice[2];                /* kernels + result copies of the wave in slice 0 / 1 are done */
     cudaEvent_t ev_wave[ZS_MAX_WAVES];
     /* last enqueue, for zscgpu_relaunch */
@@ -272,6 +274,11 @@ static int zs_init_engine(zscgpu_engine *e, const zscgpu_config &cfg, const cuda
     ZS_CUDA_CHECK(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
     ZS_CUDA_CHECK(cudaStreamCreateWithFlags(&e->d2h_stream, cudaStreamNonBlocking));
     ZS_CUDA_CHECK(cudaStreamCreateWithFlags(&e->stream2, cudaStreamNonBlocking));
+    {
+        int lo = 0, hi = 0;                 /* (numerically greatest = lowest priority) */
+        ZS_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        ZS_CUDA_CHECK(cudaStreamCreateWithPriority(&e->stream_lo, cudaStreamNonBlocking, lo));
+    }
     for (int i = 0; i < 2; i++) ZS_CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_slice[i], cudaEventDisableTiming));
     for (int i = 0; i < ZS_MAX_WAVES; i++) ZS_CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_wave[i], cudaEventDisableTiming));
     for (int i = 0; i < 2 * ZS_STAGE_BUFS; i++) {
@@ -309,6 +316,7 @@ extern "C" void zscgpu_destroy(zscgpu_engine *e)
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     if (e->d2h_stream) cudaStreamDestroy(e->d2h_stream);
     if (e->stream2) cudaStreamDestroy(e->stream2);
+    if (e->stream_lo) cudaStreamDestroy(e->stream_lo);
     for (int i = 0; i < 2; i++) if (e->ev_slice[i]) cudaEventDestroy(e->ev_slice[i]);
     if (e->stream) cudaStreamDestroy(e->stream);
     cudaGetLastError();                           /* a half-built engine may have tripped on a null handle above */
@@ -654,10 +662,8 @@ static int zs_inflate_launch_all(zscgpu_engine *e)
 }
 
 /* opts: per-stream section options (ZsStream.chunk_first, see inflate.cu) or nullptr for whole streams */
-static int zs_inflate_enqueue_opts(zscgpu_engine *e, const zscgpu_stream *streams, uint32_t n, int32_t wrap, const uint32_t *opts)
+static int zs_inflate_desc(zscgpu_engine *e, const zscgpu_stream *streams, uint32_t n, int32_t wrap, const uint32_t *opts)
 {
-    std::lock_guard<std::mutex> lk(e->mu);
-    ZS_ENTER(e);
     if (!streams || n == 0 || n > e->cfg.max_streams || (wrap & 0xFF) > 1 || wrap < 0) { snprintf(e->err, sizeof(e->err), "bad inflate batch arguments"); return ZSCGPU_ERR_ARG; }
     uint32_t max_raw = 0;
     const uint64_t raw_room = e->cfg.raw_bytes + (opts ? 4096 + ZS_SEC_SCRATCH : 0);   /* (section passes may use the scratch) */
@@ -677,6 +683,14 @@ static int zs_inflate_enqueue_opts(zscgpu_engine *e, const zscgpu_stream *stream
     ZS_CUDA_CHECK(zs_desc_fetch(e, zs_slice_whole(e), n, 0, 0));
     e->last_max_raw = max_raw;
     e->last_kind = 2; e->last_nstreams = n; e->last_wrap = wrap; e->last_with_check = opts ? 0 : 1;
+    return ZSCGPU_OK;
+}
+static int zs_inflate_enqueue_opts(zscgpu_engine *e, const zscgpu_stream *streams, uint32_t n, int32_t wrap, const uint32_t *opts)
+{
+    std::lock_guard<std::mutex> lk(e->mu);
+    ZS_ENTER(e);
+    int r = zs_inflate_desc(e, streams, n, wrap, opts);
+    if (r) return r;
     return zs_inflate_launch_all(e);
 }
 extern "C" int zscgpu_inflate_enqueue(zscgpu_engine *e, const zscgpu_stream *streams, uint32_t n, int32_t wrap)
@@ -731,6 +745,39 @@ extern "C" uint64_t zscgpu_guess_section_size(uint64_t total, uint32_t sections)
     return 0;
 }
 
+/* the candidate section starts of a stream: 0 and every position behind a 00 00 FF FF pattern, ascending, in e->sec_start;
+   *ns_out = 0 when there are none or too many */
+static int zs_section_starts(zscgpu_engine *e, const zscgpu_stream *stream, uint32_t *ns_out)
+{
+    const uint32_t cap = e->cfg.max_streams - 1;
+    uint32_t ncand = 0;
+    *ns_out = 0;
+    if (stream->comp_len >= 8) {
+        std::lock_guard<std::mutex> lk(e->mu);
+        ZS_CUDA_CHECK(cudaMemsetAsync(e->d_cand, 0, 4, e->stream));
+        zs_marker_scan_kernel<<<e->sms * 8, 256, 0, e->stream>>>(e->d_comp + stream->comp_off, stream->comp_len, e->d_cand, cap);
+        ZS_CUDA_CHECK(cudaGetLastError());
+        e->launches_total += 1;
+        ZS_CUDA_CHECK(cudaMemcpyAsync(e->h_cand, e->d_cand, 4, cudaMemcpyDeviceToHost, e->stream));
+        ZS_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+        ncand = e->h_cand[0];
+        if (ncand && ncand <= cap) {
+            ZS_CUDA_CHECK(cudaMemcpyAsync(e->h_cand + 1, e->d_cand + 1, 4ull * ncand, cudaMemcpyDeviceToHost, e->stream));
+            ZS_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+        }
+    }
+    if (ncand == 0 || ncand > cap) return ZSCGPU_OK;
+    /* ascending; a pattern at the very end of the input starts nothing */
+    uint32_t *start = e->sec_start;
+    start[0] = 0;
+    memcpy(start + 1, e->h_cand + 1, 4ull * ncand);
+    std::sort(start + 1, start + 1 + ncand);
+    uint32_t ns = ncand + 1;
+    while (ns > 1 && start[ns - 1] >= stream->comp_len) ns--;
+    *ns_out = ns;
+    return ZSCGPU_OK;
+}
+
 /* ... and the value with the most trailing decimal zeros (at least two): max_block_len = 100 000 is as round as 131 072 */
 extern "C" uint64_t zscgpu_guess_section_size10(uint64_t total, uint32_t sections)
 {
@@ -758,41 +805,20 @@ extern "C" int zscgpu_inflate_sectioned(zscgpu_engine *e, const zscgpu_stream *s
         snprintf(e->err, sizeof(e->err), "stream lies outside the arenas");
         return ZSCGPU_ERR_CAPACITY;
     }
-    const uint32_t cap = e->cfg.max_streams - 1;
-    uint32_t ncand = 0;
-    if (stream->comp_len >= 8) {
-        std::lock_guard<std::mutex> lk(e->mu);
-        ZS_CUDA_CHECK(cudaMemsetAsync(e->d_cand, 0, 4, e->stream));
-        zs_marker_scan_kernel<<<e->sms * 8, 256, 0, e->stream>>>(e->d_comp + stream->comp_off, stream->comp_len, e->d_cand, cap);
-        ZS_CUDA_CHECK(cudaGetLastError());
-        e->launches_total += 1;
-        ZS_CUDA_CHECK(cudaMemcpyAsync(e->h_cand, e->d_cand, 4, cudaMemcpyDeviceToHost, e->stream));
-        ZS_CUDA_CHECK(cudaStreamSynchronize(e->stream));
-        ncand = e->h_cand[0];
-        if (ncand && ncand <= cap) {
-            ZS_CUDA_CHECK(cudaMemcpyAsync(e->h_cand + 1, e->d_cand + 1, 4ull * ncand, cudaMemcpyDeviceToHost, e->stream));
-            ZS_CUDA_CHECK(cudaStreamSynchronize(e->stream));
-        }
-    }
-    if (ncand == 0 || ncand > cap) return zscgpu_inflate_batch(e, stream, 1, wrap, res);
-    /* section starts, ascending; a pattern at the very end of the input starts nothing */
     uint32_t *start = e->sec_start, *opts = e->sec_opts, *flags = e->sec_flags, *trailer = e->sec_trailer, *real = e->sec_real, *off = e->sec_off;
     zscgpu_stream *st = e->sec_st;
     zscgpu_result *r1 = e->sec_r1, *r2 = e->sec_r2;
-    start[0] = 0;
-    memcpy(start + 1, e->h_cand + 1, 4ull * ncand);
-    std::sort(start + 1, start + 1 + ncand);
-    uint32_t ns = ncand + 1;
-    while (ns > 1 && start[ns - 1] >= stream->comp_len) ns--;
+    uint32_t ns = 0;
+    { int rs = zs_section_starts(e, stream, &ns); if (rs) return rs; }
     if (ns < 2) return zscgpu_inflate_batch(e, stream, 1, wrap, res);
 
-    /* One pass when the stream looks like zsc_compress made it: K sections of exactly max_block_len bytes and a
-       shorter last one (reference src/zsc_compress.c:121-140).  If the caller's capacity N is the size of the data,
-       the section size S satisfies (K - 1) S < N <= K S; section sizes are round numbers, so of that range the
-       value with the most trailing zero bits is tried: every candidate is decoded straight to k * S with room S.
-       The result stands only if the sections chain exactly — each but the last produced S bytes and stopped at a
-       flush point exactly where the next candidate starts, the last one reached the end of the stream — and
-       the data check over the whole output agrees; otherwise the two passes below run as if nothing had happened. */
+    /* One pass when the stream looks like zsc_compress made it: K sections of exactly max_block_len bytes and a shorter
+       last one (reference src/zsc_compress.c:121-140).  If the caller's capacity N is the size of the data, the section
+       size S satisfies (K - 1) S < N <= K S; section sizes are round numbers, so the roundest value of that range is
+       tried: every candidate is decoded straight to k * S with room S.  The result stands only if the sections chain
+       exactly — each but the last produced S bytes and stopped at a flush point exactly where the next candidate starts,
+       the last one reached the end of the stream — and the data check over the whole output agrees; otherwise the two
+       passes below run as if nothing had happened. */
     /* did the sections [g0, g0 + ns) of the last launch, decoded straight to k * S, chain exactly? */
     uint64_t g_total = 0;
     uint32_t g_end = 0, g_stored = 0, g_have = 0;
@@ -1153,6 +1179,109 @@ extern "C" int zscgpu_compress_host(zscgpu_engine *e, uint8_t *dest, uint32_t de
     return ZSCGPU_OK;
 }
 
+/* zscgpu_uncompress_host on a large stream: the sections are decoded in a few waves on two streams, and the bytes of a
+ * wave go down to the host while the later waves are still decoding (the download of a GiB takes as long as decoding it).
+ * Only for streams that look like zsc_compress made them (one pass straight to k * S, see zscgpu_inflate_sectioned);
+ * *done = 0 leaves everything to the ordinary path, which then also overwrites whatever this attempt wrote to `dest`. */
+static int zs_uncompress_host_waves(zscgpu_engine *e, uint8_t *dest, const zscgpu_stream *stream, int32_t wrap, zscgpu_result *res, int *done)
+{
+    *done = 0;
+    uint32_t ns = 0;
+    { int rs = zs_section_starts(e, stream, &ns); if (rs) return rs; }
+    const uint64_t N = stream->raw_len;
+    if (ns < 1024 || N < ns) return ZSCGPU_OK;
+    const uint64_t Sb = zscgpu_guess_section_size(N, ns), Sd = zscgpu_guess_section_size10(N, ns);
+    const uint64_t S = zs_roundness(Sd) > zs_roundness(Sb) ? Sd : Sb;
+    if (!S) return ZSCGPU_OK;
+    uint32_t *start = e->sec_start, *opts = e->sec_opts;
+    zscgpu_stream *st = e->sec_st;
+    for (uint32_t k = 0; k < ns; k++) {
+        st[k].raw_off = stream->raw_off + (uint64_t)k * S;
+        st[k].raw_len = (uint32_t)(k + 1 < ns ? S : N - (uint64_t)k * S);
+        st[k].comp_off = stream->comp_off + start[k]; st[k].comp_len = stream->comp_len - start[k];
+        opts[k] = 2u | (k ? 4u : 0u);
+    }
+    const bool pageable = zs_is_pageable(dest);
+    /* two waves on two streams: as many sections as are sure to be resident at once (the kernel holds 16 warps per SM; at 14
+       and more per SM a few CTAs of the first wave now and then had to wait for a slot, which doubled its time: measured,
+       profiles/README.md), and the rest, whose warps start where the first wave leaves room and as its warps end — the
+       first wave's bytes go down while the second decodes */
+    uint32_t nw = 2;
+    uint32_t slots = 12u * (uint32_t)e->sms;
+#ifdef ZSC_TUNING
+    if (getenv("ZSC_B200_UNC_SLOTS")) slots = (uint32_t)atoi(getenv("ZSC_B200_UNC_SLOTS")) * (uint32_t)e->sms;
+#endif
+    uint32_t cut[ZS_MAX_WAVES + 1] = {0, ns > slots ? slots : ns / 2, ns};
+#ifdef ZSC_TUNING
+    const bool trace = getenv("ZSC_B200_TRACE") != nullptr;
+    auto now_ms = []() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; };
+    const double t_begin = now_ms();
+    if (getenv("ZSC_B200_UNC_WAVES")) { nw = (uint32_t)atoi(getenv("ZSC_B200_UNC_WAVES")); for (uint32_t v = 0; v <= nw; v++) cut[v] = (uint32_t)((uint64_t)ns * v / nw); }
+#endif
+    {
+        std::lock_guard<std::mutex> lk(e->mu);
+        int r = zs_inflate_desc(e, st, ns, wrap, opts); if (r) return r;
+        ZS_CUDA_CHECK(cudaEventRecord(e->ev_slice[0], e->stream));
+        ZS_CUDA_CHECK(cudaStreamWaitEvent(e->stream2, e->ev_slice[0], 0));
+        ZS_CUDA_CHECK(cudaStreamWaitEvent(e->stream_lo, e->ev_slice[0], 0));
+        for (uint32_t v = 0; v < nw; v++) {
+            const uint32_t k0 = cut[v], k1 = cut[v + 1];
+            cudaStream_t cs = (v & 1) ? (nw == 2 ? e->stream_lo : e->stream2) : e->stream;
+#ifdef ZSC_TUNING
+            if (getenv("ZSC_B200_UNC_STREAMS") && atoi(getenv("ZSC_B200_UNC_STREAMS")) == 3 && v % 3 == 2) cs = e->copy_stream;
+            if (getenv("ZSC_B200_UNC_STREAMS") && atoi(getenv("ZSC_B200_UNC_STREAMS")) == 1) cs = e->stream;
+#endif
+            ZS_CUDA_CHECK(zs_inflate_launch(cs, k1 - k0, e->d_streams + k0, e->d_comp, e->d_raw, wrap, e->d_ret + k0, e->d_produced + k0, e->d_consumed + k0,
+                                            e->d_check + k0, e->d_aux + 2ull * k0, e->d_adler + k0, e->last_max_raw, 0, e->d_ctr + 160ull * k0, -1));
+            ZS_CUDA_CHECK(cudaEventRecord(e->ev_wave[v], cs));
+            e->launches_total += 1;
+        }
+        /* the results of all waves, behind both streams */
+        for (uint32_t v = 0; v < nw; v++) ZS_CUDA_CHECK(cudaStreamWaitEvent(e->stream, e->ev_wave[v], 0));
+        ZS_CUDA_CHECK(cudaMemcpyAsync(e->h_ret, e->d_ret, sizeof(int32_t) * ns, cudaMemcpyDeviceToHost, e->stream));
+        ZS_CUDA_CHECK(cudaMemcpyAsync(e->h_produced, e->d_produced, sizeof(uint32_t) * ns, cudaMemcpyDeviceToHost, e->stream));
+        ZS_CUDA_CHECK(cudaMemcpyAsync(e->h_consumed, e->d_consumed, sizeof(uint32_t) * ns, cudaMemcpyDeviceToHost, e->stream));
+        ZS_CUDA_CHECK(cudaMemcpyAsync(e->h_aux, e->d_aux, sizeof(uint32_t) * 2 * ns, cudaMemcpyDeviceToHost, e->stream));
+        ZS_CUDA_CHECK(cudaEventRecord(e->ev_slice[1], e->stream));
+    }
+    /* the bytes of every wave, as soon as it is done (a section that turns out wrong makes the whole attempt void) */
+    for (uint32_t v = 0; v < nw; v++) {
+        const uint32_t k0 = cut[v], k1 = cut[v + 1];
+        const uint64_t b0 = (uint64_t)k0 * S, b1 = k1 == ns ? N : (uint64_t)k1 * S;
+        ZS_CUDA_CHECK(cudaStreamWaitEvent(e->d2h_stream, e->ev_wave[v], 0));
+#ifdef ZSC_TUNING
+        if (trace) { cudaEventSynchronize(e->ev_wave[v]); fprintf(stderr, "wave %u (%u sections) decoded at %.2f ms\n", v, k1 - k0, now_ms() - t_begin); }
+#endif
+        if (pageable) { int sr = zs_stage_d2h(e, dest + b0, e->d_raw + stream->raw_off + b0, b1 - b0, e->d2h_stream); if (sr) return sr; }
+        else ZS_CUDA_CHECK(cudaMemcpyAsync(dest + b0, e->d_raw + stream->raw_off + b0, b1 - b0, cudaMemcpyDeviceToHost, e->d2h_stream));
+    }
+    ZS_CUDA_CHECK(cudaEventSynchronize(e->ev_slice[1]));
+    bool good = true;
+    uint64_t total = 0;
+    uint32_t end_pos = 0, stored = 0, have = 0;
+    for (uint32_t k = 0; k < ns && good; k++) {
+        const uint32_t f = e->h_aux[2 * k + 1];
+        if (e->h_ret[k] != 0 || (f & 2u)) good = false;
+        else if (k + 1 < ns) good = (f & 4u) && e->h_produced[k] == S && start[k] + e->h_consumed[k] == start[k + 1];
+        else { good = !(f & 4u); stored = e->h_aux[2 * k]; have = f & 1u; end_pos = start[k] + e->h_consumed[k]; }
+        total += e->h_produced[k];
+    }
+    uint32_t check = 1;
+    if (good) {
+        int rcs = zscgpu_adler32(e, stream->raw_off, total, 1u, &check); if (rcs) return rcs;
+        if ((wrap & 0xFF) == 1 && have && stored != check) good = false;
+    }
+    ZS_CUDA_CHECK(cudaStreamSynchronize(e->d2h_stream));
+#ifdef ZSC_TUNING
+    if (trace) fprintf(stderr, "all bytes down at %.2f ms, good %d\n", now_ms() - t_begin, (int)good);
+#endif
+    if (!good) return ZSCGPU_OK;
+    res->ret = 0; res->produced = (uint32_t)total; res->consumed = end_pos; res->check = check;
+    e->launches = 2 + (int)nw;   /* marker scan, the waves, adler32 */
+    *done = 1;
+    return ZSCGPU_OK;
+}
+
 extern "C" int zscgpu_uncompress_host(zscgpu_engine *e, uint8_t *dest, uint32_t dest_cap, const uint8_t *src, uint32_t src_len,
                                       int32_t wrap, zscgpu_result *res)
 {
@@ -1167,6 +1296,12 @@ extern "C" int zscgpu_uncompress_host(zscgpu_engine *e, uint8_t *dest, uint32_t 
     zscgpu_stream st;
     st.raw_off = 0; st.comp_off = 0; st.comp_len = src_len;
     st.raw_len = (uint64_t)dest_cap > e->cfg.raw_bytes ? (uint32_t)e->cfg.raw_bytes : dest_cap;
+    if (src_len >= (32u << 20)) {
+        int done = 0;
+        r = zs_uncompress_host_waves(e, dest, &st, wrap, res, &done);
+        if (r) return r;
+        if (done) return ZSCGPU_OK;
+    }
     r = (src_len >= (8u << 10)) ? zscgpu_inflate_sectioned(e, &st, wrap, res) : zscgpu_inflate_batch(e, &st, 1, wrap, res);
     if (r) return r;
     if (st.raw_len < dest_cap && res->ret == -5 && res->produced == st.raw_len) {

@@ -238,10 +238,10 @@ extern "C" cudaError_t zs_adler_streams_launch(cudaStream_t st, uint32_t n, uint
 extern "C" cudaError_t zs_inflate_launch(cudaStream_t st, uint32_t n, const ZsStream *streams, const uint8_t *comp,
                                          uint8_t *raw, int32_t wrap, int32_t *ret, uint32_t *produced,
                                          uint32_t *consumed, uint32_t *check, uint32_t *aux, ZsAdlerAcc *acc,
-                                         uint32_t max_raw_len, int with_check, uint32_t *counter /* zi_aux[n] */, int sms)
+                                         uint32_t max_raw_len, int with_check, uint32_t *counter /* zi_aux[n] */, int sms /* < 0: one wave of several */)
 {
     if (n == 0) return cudaSuccess;
-    (void)sms;
+    const int wide_hint = sms < 0;                     /* the batch is one wave of a larger job: the machine is shared, no window in shared memory */
     static_assert(sizeof(zw::zi_aux) == 640 && sizeof(zn::zi_aux) == 640, "engine.cu sizes the zi_aux pool with 640 bytes per stream");
     /* a warp per stream while that fills the machine (148 SMs x 32 warps); beyond, several streams per warp: their
        leaders decode at the same time, and the two-level tables (1.6 KB per stream) let 128 streams share an SM */
@@ -251,7 +251,7 @@ extern "C" cudaError_t zs_inflate_launch(cudaStream_t st, uint32_t n, const ZsSt
 #endif
     /* up to ZS_INFLATE_SPEC_MAX streams: a warp per stream with all of its lanes decoding (inflate_spec.inc), 1 = with the
        stream's window in shared memory, 2 = without; beyond, quarter-warp groups with one decoding lane each */
-    int spec = n <= ZS_INFLATE_RING_MAX ? 1 : (n <= ZS_INFLATE_SPEC_MAX ? 2 : 0);
+    int spec = (n <= ZS_INFLATE_RING_MAX && !wide_hint) ? 1 : (n <= ZS_INFLATE_SPEC_MAX ? 2 : 0);
 #ifdef ZSC_TUNING
     if (getenv("ZSC_B200_INFLATE_SPEC")) spec = atoi(getenv("ZSC_B200_INFLATE_SPEC"));
 #endif
