@@ -37,9 +37,9 @@ tests/libzsc_cpuharness.so: tests/cpu_harness.cpp zsc_b200/csrc/cuda/huff_build.
 tests/libzsc_cpuharness_n.so: tests/cpu_harness.cpp zsc_b200/csrc/cuda/huff_build.h zsc_b200/csrc/cuda/inflate_core.h zsc_b200/csrc/cuda/inflate_spec.h
 	$(CXX) -O2 -fPIC -shared -std=c++17 -DZI_LBITS=10 -DZI_DBITS=8 -DZI_POOL=256 -Izsc_b200/csrc/cuda -o $@ tests/cpu_harness.cpp
 
-# ... and with the speculative decoder's geometry of wide batches (regions of 256 bits, inflate.cu namespace zm)
+# ... and with the speculative decoder's geometry of wide batches (regions of 320 bits, inflate.cu namespace zm)
 tests/libzsc_cpuharness_w.so: tests/cpu_harness.cpp zsc_b200/csrc/cuda/huff_build.h zsc_b200/csrc/cuda/inflate_core.h zsc_b200/csrc/cuda/inflate_spec.h
-	$(CXX) -O2 -fPIC -shared -std=c++17 -DZI_LBITS=10 -DZI_DBITS=8 -DZI_POOL=256 -DZP_R=256u -DZP_CAP=64u -Izsc_b200/csrc/cuda -o $@ tests/cpu_harness.cpp
+	$(CXX) -O2 -fPIC -shared -std=c++17 -DZI_LBITS=10 -DZI_DBITS=8 -DZI_POOL=256 -DZP_R=320u -DZP_CAP=80u -Izsc_b200/csrc/cuda -o $@ tests/cpu_harness.cpp
 
 tools/libzscgen.so: tools/datagen.c
 	$(CC) -O2 -fPIC -shared -o $@ tools/datagen.c -lm -lpthread

@@ -370,8 +370,8 @@ def canterbury_config0(device):
         out["cpu_baseline"] = {"compress_MBps": round(tot["bytes"] / 1e6 / tot["ref_c"], 1), "uncompress_MBps": round(tot["bytes"] / 1e6 / tot["ref_u"], 1),
                                "cores": 1, "kind": "reference", "sample": "the same 11 calls through the reference on one host thread", "compressed_bytes": tot["ref_size"]}
         out["size_vs_reference"] = round(tot["size"] / tot["ref_size"], 4)
-        out["verdict"] = ("GPU slower than one host core on this shape: calls of 4 KB - 1 MB are bound by launch latency, the PCIe round trip and one CTA per "
-                          "100 000-byte section" if tot["gpu_c"] > tot["ref_c"] else "GPU faster than one host core on this shape")
+        out["verdict"] = ("compress: GPU %.1f x one host core; uncompress: GPU %.2f x one host core (calls of 4 KB - 1 MB: launch latency, the PCIe round "
+                          "trip and one warp per 100 000-byte section bound the GPU side)" % (tot["ref_c"] / tot["gpu_c"], tot["ref_u"] / tot["gpu_u"]))
     return out
 
 
