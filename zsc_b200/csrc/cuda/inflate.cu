@@ -34,8 +34,8 @@ namespace zn {
 #include "inflate_spec.h"
 #include "inflate_spec.inc"
 }
-/* The speculative warp decoder (inflate_spec.h) exists twice as well: `zn` with regions of 384 bits and each stream's
- * window in shared memory (50 KB per stream, 4 per SM: few streams, latency decides), `zm` with regions of 320 bits and
+/* The speculative warp decoder (inflate_spec.h) exists twice as well: `zn` with regions of 512 bits and each stream's
+ * window in shared memory (55 KB per stream, 4 per SM: few streams, latency decides), `zm` with regions of 320 bits and
  * no window (15 KB per stream, 14 per SM: the batch fills the machine; measured against 128 / 192 / 256 / 384 bits).  Same code, same results. */
 #ifndef ZP_WIDE_R
 #define ZP_WIDE_R 320u

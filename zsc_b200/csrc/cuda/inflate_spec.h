@@ -28,8 +28,8 @@
 #define ZSC_INFLATE_SPEC_H
 
 #ifndef ZP_R
-#define ZP_R 384u                    /* input bits per region (a multiple of 32) */
-#define ZP_CAP 96u                   /* symbols a lane can hold per round */
+#define ZP_R 512u                    /* input bits per region (a multiple of 32) */
+#define ZP_CAP 128u                  /* symbols a lane can hold per round */
 #endif
 #define ZP_RS 33u                    /* row stride of the symbol array (words): a column read hits 32 banks */
 #ifndef ZP_RETRY
