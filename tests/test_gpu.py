@@ -236,10 +236,11 @@ def test_inflate_batch_of_reference_streams(engine, checker):
         assert np.array_equal(out, x)
 
 
-@pytest.mark.parametrize("n", [96, 900])
+@pytest.mark.parametrize("n", [96, 500, 900])
 def test_inflate_batch_with_corrupted_streams_equals_reference(engine, n):
-    """a batch in which every third stream is damaged, at both widths of the speculative warp decoder (96 streams: each
-    stream's window in shared memory; 900: without): code, counts and bytes of every stream as the reference's
+    """a batch in which every third stream is damaged, at the three widths of the speculative warp decoder (96 streams: two
+    warps per stream, one decoding ahead of the one that writes; 500: one warp per stream, its window in shared memory;
+    900: without the window): code, counts and bytes of every stream as the reference's
     zsc_uncompress (src/zsc_uncompr.c:103-127, recovery at the next marker included)"""
     if not refimpl.have_ref():
         pytest.skip("oracle/_ref not present")

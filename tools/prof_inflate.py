@@ -68,6 +68,10 @@ try:
     print("spec profile per round (cycles of lane 0):", {nm: round(a[i] / rounds) for i, nm in enumerate(names)}, "rounds/stream", round(a[8] / launches / n, 1), "sym/round", round(a[9] / rounds), "bytes/round", round(a[10] / rounds), "kernel cycles/stream", round(a[11] / launches / n))
     sw = max(a[20], 1)
     print("emit per sweep: sweeps/round", round(a[20] / rounds, 1), "level calc", round(a[13] / sw), "own copies", round(a[14] / sw), "long copies + sync", round(a[15] / sw), "levels", round(a[16] / sw, 2), "matches", round(a[17] / sw, 1), "reaching in", round(a[18] / sw, 1), "long", round(a[19] / sw, 2), "fetch + scan", round(a[12] / sw))
+    if a[23]:
+        print("decode set-up: broadcasts", round(a[7] / rounds), "bitmap", round(a[23] / rounds), "(the rest of 'setup': the lanes' readers)")
+    if a[21] or a[22]:
+        print("two warps per stream: the decoder waits for a free buffer", round(a[21] / rounds), "cycles per round, the writer for a chain", round(a[22] / rounds))
 except AttributeError:
     pass
 E.close()

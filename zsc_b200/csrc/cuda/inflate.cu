@@ -252,10 +252,12 @@ extern "C" cudaError_t zs_inflate_launch(cudaStream_t st, uint32_t n, const ZsSt
     /* up to ZS_INFLATE_SPEC_MAX streams: a warp per stream with all of its lanes decoding (inflate_spec.inc), 1 = with the
        stream's window in shared memory, 2 = without; beyond, quarter-warp groups with one decoding lane each */
     int spec = (n <= ZS_INFLATE_RING_MAX && !wide_hint) ? 1 : (n <= ZS_INFLATE_SPEC_MAX ? 2 : 0);
+    if (spec == 1 && sms > 0 && n <= 3u * (uint32_t)sms) spec = 3;   /* three per SM fit with two warps each: one decodes the next round while the other writes this one */
 #ifdef ZSC_TUNING
     if (getenv("ZSC_B200_INFLATE_SPEC")) spec = atoi(getenv("ZSC_B200_INFLATE_SPEC"));
 #endif
-    cudaError_t ge = spec == 1 ? zn::zs_inflate_spec_launch<true>(st, n, streams, comp, raw, wrap, ret, produced, consumed, aux, reinterpret_cast<zn::zi_aux *>(counter))
+    cudaError_t ge = spec == 3 ? zn::zs_inflate_pipe_launch<0>(st, n, streams, comp, raw, wrap, ret, produced, consumed, aux, reinterpret_cast<zn::zi_aux *>(counter))
+                   : spec == 1 ? zn::zs_inflate_spec_launch<true>(st, n, streams, comp, raw, wrap, ret, produced, consumed, aux, reinterpret_cast<zn::zi_aux *>(counter))
                    : spec == 2 ? zm::zs_inflate_spec_launch<false>(st, n, streams, comp, raw, wrap, ret, produced, consumed, aux, reinterpret_cast<zm::zi_aux *>(counter))
                    : g == 32 ? zn::zs_inflate_group_launch<32>(st, n, streams, comp, raw, wrap, ret, produced, consumed, aux, reinterpret_cast<zn::zi_aux *>(counter))
                    : g == 16 ? zn::zs_inflate_group_launch<16>(st, n, streams, comp, raw, wrap, ret, produced, consumed, aux, reinterpret_cast<zn::zi_aux *>(counter))
