@@ -256,7 +256,8 @@ def inflate_config3(device, rank, world, barrier, allmax, peak):
                             "note": "C + N per pass and GPU over the whole pass (decode, output adler32, check kernels)"}}
         if world == 1:
             # the same streams in narrower batches: up to 12 288 streams a warp decodes one stream with all 32 lanes
-            # (zs_inflate_spec_kernel, inflate_spec.h), up to 640 with the stream's window in shared memory
+            # (zs_inflate_spec_kernel, inflate_spec.h), up to 640 with the stream's window in shared memory, up to 444 with a
+            # second warp per stream that writes one round while the first decodes the next (zs_inflate_pipe_kernel)
             nb = {}
             for k in (64, 512, 4096):
                 if k > n:
@@ -269,7 +270,7 @@ def inflate_config3(device, rank, world, barrier, allmax, peak):
                 for _ in range(3):
                     E.sync(); E.event(0); E.relaunch(); E.event(1); E.sync(); tk.append(E.elapsed_ms(0, 1))
                 nb[str(k)] = {"value": round(k * S / 1e6 / min(tk), 2), "ms": round(min(tk), 3), "parity": "bit-exact" if okk else "MISMATCH"}
-            out["narrower_batches"] = dict(nb, unit="GB/s of output", kernel="zs_inflate_spec_kernel (a warp per stream, every lane decoding)")
+            out["narrower_batches"] = dict(nb, unit="GB/s of output", kernel="the speculative warp decoder: zs_inflate_pipe_kernel up to 444 streams (two warps per stream), zs_inflate_spec_kernel beyond")
         if rank == 0 and refimpl.have_ref():
             cores = os.cpu_count() or 1
             packed = np.concatenate(comps)

@@ -61,7 +61,7 @@ import ctypes as _C
 try:
     _L = _C.CDLL(os.environ.get("ZSC_B200_LIB") or os.path.join(ROOT, "zsc_b200", "libzsc_b200.so"))
     _f = _L.zs_inflate_spec_prof
-    a = (_C.c_uint64 * 24)(); _f(a, 1); a = list(a)
+    a = (_C.c_uint64 * 32)(); _f(a, 1); a = list(a)
     launches = 4
     names = ["setup", "phase1", "phase2", "chain+measure", "emit", "flush", "cursor", "old path"]
     rounds = max(a[8], 1)
@@ -71,7 +71,8 @@ try:
     if a[23]:
         print("decode set-up: broadcasts", round(a[7] / rounds), "bitmap", round(a[23] / rounds), "(the rest of 'setup': the lanes' readers)")
     if a[21] or a[22]:
-        print("two warps per stream: the decoder waits for a free buffer", round(a[21] / rounds), "cycles per round, the writer for a chain", round(a[22] / rounds))
+        print("two warps per stream: the decoder waits for a free buffer", round(a[21] / rounds), "cycles per round, the writer for a chain", round(a[22] / rounds),
+              "; writer warp: lifetime", round(a[24] / launches / n), "of which inside zp_round_emit", round(a[25] / launches / n), "per stream")
 except AttributeError:
     pass
 E.close()
