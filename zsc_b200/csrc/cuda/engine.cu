@@ -32,6 +32,7 @@ extern "C" cudaError_t zs_crc_flat_launch(cudaStream_t, const uint8_t *, uint64_
 extern "C" cudaError_t zs_inflate_launch(cudaStream_t, uint32_t, const ZsStream *, const uint8_t *, uint8_t *, int32_t,
                                          int32_t *, uint32_t *, uint32_t *, uint32_t *, uint32_t *, ZsAdlerAcc *, uint32_t, int, uint32_t *, int);
 
+extern "C" cudaError_t zs_inflate_preload(void);
 extern "C" cudaError_t zs_inflate_stream_launch(cudaStream_t, void *, uint8_t *, uint8_t *, uint32_t, uint32_t, int32_t, uint32_t *);
 extern "C" size_t zs_inflate_stream_slot_bytes(void);
 
@@ -291,6 +292,7 @@ static int zs_init_engine(zscgpu_engine *e, const zscgpu_config &cfg, const cuda
         e->pool->start((int)std::max(1u, std::min(8u, hc / 2)));
     }
     ZS_CUDA_CHECK(zs_crc_init_launch(e->stream));
+    ZS_CUDA_CHECK(zs_inflate_preload());                    /* (lazy module loading would otherwise cost the first zsc_uncompress 10 ms) */
     ZS_CUDA_CHECK(cudaStreamSynchronize(e->stream));
     return ZSCGPU_OK;
 }

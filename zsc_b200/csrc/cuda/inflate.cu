@@ -232,6 +232,20 @@ extern "C" cudaError_t zs_inflate_stream_launch(cudaStream_t st, void *slot, uin
 }
 extern "C" size_t zs_inflate_stream_slot_bytes(void) { return sizeof(ZsInfSlot); }
 
+/* zscgpu_init: the inflate kernels are large; loaded here, not inside the first call (module loading is lazy) */
+extern "C" cudaError_t zs_inflate_preload(void)
+{
+    cudaFuncAttributes fa;
+    cudaError_t ce;
+    if ((ce = cudaFuncGetAttributes(&fa, zn::zs_inflate_pipe_kernel<2>)) != cudaSuccess) return ce;
+    if ((ce = cudaFuncGetAttributes(&fa, zn::zs_inflate_pipe_kernel<3>)) != cudaSuccess) return ce;
+    if ((ce = cudaFuncGetAttributes(&fa, zn::zs_inflate_spec_kernel<true>)) != cudaSuccess) return ce;
+    if ((ce = cudaFuncGetAttributes(&fa, zm::zs_inflate_spec_kernel<false>)) != cudaSuccess) return ce;
+    if ((ce = cudaFuncGetAttributes(&fa, zw::zs_inflate_group_kernel<8>)) != cudaSuccess) return ce;
+    if ((ce = cudaFuncGetAttributes(&fa, zs_inflate_stream_kernel)) != cudaSuccess) return ce;
+    return cudaFuncGetAttributes(&fa, zs_inflate_check_kernel);
+}
+
 extern "C" cudaError_t zs_adler_streams_launch(cudaStream_t st, uint32_t n, uint32_t max_len, const uint8_t *raw,
                                                const ZsStream *streams, const uint32_t *produced, ZsAdlerAcc *acc);
 
@@ -252,11 +266,14 @@ extern "C" cudaError_t zs_inflate_launch(cudaStream_t st, uint32_t n, const ZsSt
     /* up to ZS_INFLATE_SPEC_MAX streams: a warp per stream with all of its lanes decoding (inflate_spec.inc), 1 = with the
        stream's window in shared memory, 2 = without; beyond, quarter-warp groups with one decoding lane each */
     int spec = (n <= ZS_INFLATE_RING_MAX && !wide_hint) ? 1 : (n <= ZS_INFLATE_SPEC_MAX ? 2 : 0);
-    if (spec == 1 && sms > 0 && n <= 3u * (uint32_t)sms) spec = 3;   /* three per SM fit with two warps each: one decodes the next round while the other writes this one */
+    /* two warps per stream while three (or, with three symbol buffers instead of two, two) streams per SM hold the batch:
+       one warp decodes ahead while the other writes (a fourth buffer: no further gain, measured) */
+    if (spec == 1 && sms > 0 && n <= 3u * (uint32_t)sms) spec = n <= 2u * (uint32_t)sms ? 4 : 3;
 #ifdef ZSC_TUNING
     if (getenv("ZSC_B200_INFLATE_SPEC")) spec = atoi(getenv("ZSC_B200_INFLATE_SPEC"));
 #endif
-    cudaError_t ge = spec == 3 ? zn::zs_inflate_pipe_launch<0>(st, n, streams, comp, raw, wrap, ret, produced, consumed, aux, reinterpret_cast<zn::zi_aux *>(counter))
+    cudaError_t ge = spec == 4 ? zn::zs_inflate_pipe_launch<3>(st, n, streams, comp, raw, wrap, ret, produced, consumed, aux, reinterpret_cast<zn::zi_aux *>(counter))
+                   : spec == 3 ? zn::zs_inflate_pipe_launch<2>(st, n, streams, comp, raw, wrap, ret, produced, consumed, aux, reinterpret_cast<zn::zi_aux *>(counter))
                    : spec == 1 ? zn::zs_inflate_spec_launch<true>(st, n, streams, comp, raw, wrap, ret, produced, consumed, aux, reinterpret_cast<zn::zi_aux *>(counter))
                    : spec == 2 ? zm::zs_inflate_spec_launch<false>(st, n, streams, comp, raw, wrap, ret, produced, consumed, aux, reinterpret_cast<zm::zi_aux *>(counter))
                    : g == 32 ? zn::zs_inflate_group_launch<32>(st, n, streams, comp, raw, wrap, ret, produced, consumed, aux, reinterpret_cast<zn::zi_aux *>(counter))
