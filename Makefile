@@ -37,7 +37,8 @@ tests/libzsc_cpuharness.so: tests/cpu_harness.cpp zsc_b200/csrc/cuda/huff_build.
 tests/libzsc_cpuharness_n.so: tests/cpu_harness.cpp zsc_b200/csrc/cuda/huff_build.h zsc_b200/csrc/cuda/inflate_core.h zsc_b200/csrc/cuda/inflate_spec.h
 	$(CXX) -O2 -fPIC -shared -std=c++17 -DZI_LBITS=10 -DZI_DBITS=8 -DZI_POOL=256 -Izsc_b200/csrc/cuda -o $@ tests/cpu_harness.cpp
 
-# ... and with the speculative decoder's geometry of wide batches (regions of 320 bits, inflate.cu namespace zm)
+# ... and with a second geometry of the speculative decoder (regions of 320 bits; the product uses 512 everywhere, the lane
+# functions must not depend on it)
 tests/libzsc_cpuharness_w.so: tests/cpu_harness.cpp zsc_b200/csrc/cuda/huff_build.h zsc_b200/csrc/cuda/inflate_core.h zsc_b200/csrc/cuda/inflate_spec.h
 	$(CXX) -O2 -fPIC -shared -std=c++17 -DZI_LBITS=10 -DZI_DBITS=8 -DZI_POOL=256 -DZP_R=320u -DZP_CAP=80u -Izsc_b200/csrc/cuda -o $@ tests/cpu_harness.cpp
 

@@ -86,7 +86,7 @@ _har_w = None
 
 
 def harness_wide():
-    """the harness compiled with the speculative decoder's geometry of wide batches (regions of 320 bits)"""
+    """the harness compiled with a second geometry of the speculative decoder (regions of 320 bits, 80 symbols per lane)"""
     global _har_w
     if _har_w is None:
         L = C.CDLL(HARNESS_PATH.replace(".so", "_w.so"), mode=C.RTLD_LOCAL)

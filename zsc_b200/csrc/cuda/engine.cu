@@ -30,7 +30,8 @@ extern "C" cudaError_t zs_adler_flat_launch(cudaStream_t, const uint8_t *, uint6
 extern "C" cudaError_t zs_crc_init_launch(cudaStream_t);
 extern "C" cudaError_t zs_crc_flat_launch(cudaStream_t, const uint8_t *, uint64_t, uint32_t, uint32_t *, int);
 extern "C" cudaError_t zs_inflate_launch(cudaStream_t, uint32_t, const ZsStream *, const uint8_t *, uint8_t *, int32_t,
-                                         int32_t *, uint32_t *, uint32_t *, uint32_t *, uint32_t *, ZsAdlerAcc *, uint32_t, int, uint32_t *, int);
+                                         int32_t *, uint32_t *, uint32_t *, uint32_t *, uint32_t *, ZsAdlerAcc *, uint32_t, int, uint32_t *, int, uint32_t *);
+extern "C" size_t zs_inflate_spec_scratch_bytes(void);
 
 extern "C" cudaError_t zs_inflate_preload(void);
 extern "C" cudaError_t zs_inflate_stream_launch(cudaStream_t, void *, uint8_t *, uint8_t *, uint32_t, uint32_t, int32_t, uint32_t *);
@@ -111,6 +112,7 @@ struct zscgpu_engine {
     ZsAdlerAcc *d_adler;              /* per stream; slot max_streams is the flat-checksum slot */
     uint32_t *d_crc;                  /* [2] */
     uint32_t *d_ctr;                  /* inflate: per stream, the sorted symbols of the current block (zi_aux, 640 B) */
+    uint32_t *d_spec_rec;             /* inflate: per stream, the symbols of a round of the wide speculative decoder (17 KB) */
     uint8_t *d_sslots, *d_sin, *d_sout;   /* streaming inflate: ZS_STREAM_SLOTS x (machine + tables | input staging | history + output staging) */
     uint32_t *d_sres, *h_sres;        /* ... and the eight result words of a step */
     bool sslot_used[ZS_STREAM_SLOTS];
@@ -243,6 +245,7 @@ static int zs_init_engine(zscgpu_engine *e, const zscgpu_config &cfg, const cuda
     ZS_CUDA_CHECK(zs_dev(&e->d_adler, cfg.max_streams + 1));
     ZS_CUDA_CHECK(zs_dev(&e->d_crc, 4));
     ZS_CUDA_CHECK(zs_dev(&e->d_ctr, (size_t)cfg.max_streams * 160u));      /* 640 B per stream */
+    ZS_CUDA_CHECK(zs_dev(&e->d_spec_rec, (size_t)cfg.max_streams * (zs_inflate_spec_scratch_bytes() / 4)));
     ZS_CUDA_CHECK(zs_dev(&e->d_sslots, ZS_STREAM_SLOTS * zs_inflate_stream_slot_bytes()));
     ZS_CUDA_CHECK(zs_dev(&e->d_sin, (size_t)ZS_STREAM_SLOTS * (ZSCGPU_STREAM_IN_MAX + 256)));
     ZS_CUDA_CHECK(zs_dev(&e->d_sout, (size_t)ZS_STREAM_SLOTS * (ZS_STREAM_HIST + ZSCGPU_STREAM_OUT_MAX + 256)));
@@ -309,7 +312,7 @@ extern "C" void zscgpu_destroy(zscgpu_engine *e)
     cudaFreeHost(e->h_streams); cudaFree(e->d_streams);
     cudaFreeHost(e->h_blk_chunk); cudaFree(e->d_blk_chunk);
     cudaFree(e->d_chunk_nsym); cudaFree(e->d_blk_in_start); cudaFree(e->d_blocks); cudaFree(e->d_blk_meta); cudaFree(e->d_blk_bitoff); cudaFree(e->d_blk_scratch); cudaFree(e->d_blk_used);
-    cudaFree(e->d_adler); cudaFree(e->d_crc); cudaFree(e->d_ctr); cudaFree(e->d_sslots); cudaFree(e->d_sin); cudaFree(e->d_sout); cudaFree(e->d_sres); cudaFreeHost(e->h_sres); cudaFree(e->d_aux); cudaFreeHost(e->h_aux); cudaFree(e->d_cand); cudaFreeHost(e->h_cand);
+    cudaFree(e->d_adler); cudaFree(e->d_crc); cudaFree(e->d_ctr); cudaFree(e->d_spec_rec); cudaFree(e->d_sslots); cudaFree(e->d_sin); cudaFree(e->d_sout); cudaFree(e->d_sres); cudaFreeHost(e->h_sres); cudaFree(e->d_aux); cudaFreeHost(e->h_aux); cudaFree(e->d_cand); cudaFreeHost(e->h_cand);
     free(e->sec_start); free(e->sec_st); free(e->sec_r1);
     cudaFree(e->d_ret); cudaFree(e->d_produced); cudaFree(e->d_consumed); cudaFree(e->d_check);
     cudaFreeHost(e->h_ret); cudaFreeHost(e->h_produced); cudaFreeHost(e->h_consumed); cudaFreeHost(e->h_check);
@@ -652,7 +655,7 @@ static int zs_inflate_launch_all(zscgpu_engine *e)
 {
     const uint32_t n = e->last_nstreams;
     ZS_CUDA_CHECK(zs_inflate_launch(e->stream, n, e->d_streams, e->d_comp, e->d_raw, e->last_wrap, e->d_ret, e->d_produced, e->d_consumed, e->d_check,
-                                    e->d_aux, e->d_adler, e->last_max_raw, e->last_with_check, e->d_ctr, e->sms));
+                                    e->d_aux, e->d_adler, e->last_max_raw, e->last_with_check, e->d_ctr, e->sms, e->d_spec_rec));
     ZS_CUDA_CHECK(cudaMemcpyAsync(e->h_ret, e->d_ret, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, e->stream));
     ZS_CUDA_CHECK(cudaMemcpyAsync(e->h_produced, e->d_produced, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, e->stream));
     ZS_CUDA_CHECK(cudaMemcpyAsync(e->h_consumed, e->d_consumed, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, e->stream));
@@ -1234,7 +1237,8 @@ static int zs_uncompress_host_waves(zscgpu_engine *e, uint8_t *dest, const zscgp
             if (getenv("ZSC_B200_UNC_STREAMS") && atoi(getenv("ZSC_B200_UNC_STREAMS")) == 1) cs = e->stream;
 #endif
             ZS_CUDA_CHECK(zs_inflate_launch(cs, k1 - k0, e->d_streams + k0, e->d_comp, e->d_raw, wrap, e->d_ret + k0, e->d_produced + k0, e->d_consumed + k0,
-                                            e->d_check + k0, e->d_aux + 2ull * k0, e->d_adler + k0, e->last_max_raw, 0, e->d_ctr + 160ull * k0, -1));
+                                            e->d_check + k0, e->d_aux + 2ull * k0, e->d_adler + k0, e->last_max_raw, 0, e->d_ctr + 160ull * k0, -1,
+                                            e->d_spec_rec + (size_t)k0 * (zs_inflate_spec_scratch_bytes() / 4)));
             ZS_CUDA_CHECK(cudaEventRecord(e->ev_wave[v], cs));
             e->launches_total += 1;
         }

@@ -34,18 +34,22 @@ namespace zn {
 #include "inflate_spec.h"
 #include "inflate_spec.inc"
 }
-/* The speculative warp decoder (inflate_spec.h) exists twice as well: `zn` with regions of 512 bits and each stream's
- * window in shared memory (55 KB per stream, 4 per SM: few streams, latency decides), `zm` with regions of 320 bits and
- * no window (15 KB per stream, 14 per SM: the batch fills the machine; measured against 128 / 192 / 256 / 384 bits).  Same code, same results. */
+/* The speculative warp decoder (inflate_spec.h) exists twice as well: `zn` keeps each stream's window and the symbols of a
+ * round in shared memory (55 KB per stream, 4 per SM, 75 KB and 3 or 2 per SM with a second warp: few streams, latency
+ * decides); `zm` keeps only tables and bitmap there (5 KB), the symbols in a scratch in global memory (17 KB per stream,
+ * written once and read once per round: L2 traffic) and writes straight to global memory: 28 streams per SM — the batch fills
+ * the machine.  Same code, same results.  (Measured: symbols in shared memory, 15 KB per stream and 14 per SM: 55 instead of
+ * 73 GB/s at 4096 streams; regions of 320 / 384 / 640 / 768 bits, 24 / 32 streams per SM: profiles/README.md.) */
 #ifndef ZP_WIDE_R
-#define ZP_WIDE_R 320u
-#define ZP_WIDE_CAP 80u
+#define ZP_WIDE_R 512u
+#define ZP_WIDE_CAP 128u
 #endif
 #undef ZP_R
 #undef ZP_CAP
 #define ZP_R ZP_WIDE_R
 #define ZP_CAP ZP_WIDE_CAP
 #define ZP_NO_PROFILE
+#define ZP_REC_GLOBAL
 namespace zm {
 #include "inflate_core.h"
 #include "inflate_group.inc"
@@ -53,6 +57,7 @@ namespace zm {
 #include "inflate_spec.inc"
 }
 #undef ZP_NO_PROFILE
+#undef ZP_REC_GLOBAL
 #undef ZI_REINCLUDE
 using namespace zw;                                          /* the streaming kernel below uses the compact geometry */
 
@@ -232,6 +237,8 @@ extern "C" cudaError_t zs_inflate_stream_launch(cudaStream_t st, void *slot, uin
 }
 extern "C" size_t zs_inflate_stream_slot_bytes(void) { return sizeof(ZsInfSlot); }
 
+extern "C" size_t zs_inflate_spec_scratch_bytes(void) { return (size_t)ZP_WIDE_CAP * 33u * 4u; }   /* per stream, of the wide build */
+
 /* zscgpu_init: the inflate kernels are large; loaded here, not inside the first call (module loading is lazy) */
 extern "C" cudaError_t zs_inflate_preload(void)
 {
@@ -252,7 +259,8 @@ extern "C" cudaError_t zs_adler_streams_launch(cudaStream_t st, uint32_t n, uint
 extern "C" cudaError_t zs_inflate_launch(cudaStream_t st, uint32_t n, const ZsStream *streams, const uint8_t *comp,
                                          uint8_t *raw, int32_t wrap, int32_t *ret, uint32_t *produced,
                                          uint32_t *consumed, uint32_t *check, uint32_t *aux, ZsAdlerAcc *acc,
-                                         uint32_t max_raw_len, int with_check, uint32_t *counter /* zi_aux[n] */, int sms /* < 0: one wave of several */)
+                                         uint32_t max_raw_len, int with_check, uint32_t *counter /* zi_aux[n] */, int sms /* < 0: one wave of several */,
+                                         uint32_t *spec_scratch /* [n] x zs_inflate_spec_scratch_bytes() */)
 {
     if (n == 0) return cudaSuccess;
     const int wide_hint = sms < 0;                     /* the batch is one wave of a larger job: the machine is shared, no window in shared memory */
@@ -263,19 +271,22 @@ extern "C" cudaError_t zs_inflate_launch(cudaStream_t st, uint32_t n, const ZsSt
 #ifdef ZSC_TUNING
     if (getenv("ZSC_B200_INFLATE_G")) g = (uint32_t)atoi(getenv("ZSC_B200_INFLATE_G"));
 #endif
-    /* up to ZS_INFLATE_SPEC_MAX streams: a warp per stream with all of its lanes decoding (inflate_spec.inc), 1 = with the
-       stream's window in shared memory, 2 = without; beyond, quarter-warp groups with one decoding lane each */
-    int spec = (n <= ZS_INFLATE_RING_MAX && !wide_hint) ? 1 : (n <= ZS_INFLATE_SPEC_MAX ? 2 : 0);
-    /* two warps per stream while three (or, with three symbol buffers instead of two, two) streams per SM hold the batch:
-       one warp decodes ahead while the other writes (a fourth buffer: no further gain, measured) */
-    if (spec == 1 && sms > 0 && n <= 3u * (uint32_t)sms) spec = n <= 2u * (uint32_t)sms ? 4 : 3;
+    /* A warp per stream with all of its lanes decoding (inflate_spec.inc).  4 / 3: two warps per stream, one decoding ahead of
+       the one that writes, while two / three streams per SM hold the batch (or hold it in two turns); 1: one warp, the stream's
+       window in shared memory, while four per SM hold it; 2: the wide build, 28 streams per SM.  (0: the group kernels, one
+       decoding lane per group of 8 / 16 / 32: without a scratch, and in tuning builds — the wide build passed them at every
+       batch size.) */
+    const uint32_t nsm = sms > 0 ? (uint32_t)sms : 0u;
+    int spec = 2;
+    if (!wide_hint && nsm) spec = n <= 2u * nsm ? 4 : n <= 3u * nsm ? 3 : n <= 4u * nsm ? 1 : n <= 6u * nsm ? 3 : 2;
+    if (!spec_scratch && spec == 2) spec = 0;
 #ifdef ZSC_TUNING
     if (getenv("ZSC_B200_INFLATE_SPEC")) spec = atoi(getenv("ZSC_B200_INFLATE_SPEC"));
 #endif
     cudaError_t ge = spec == 4 ? zn::zs_inflate_pipe_launch<3>(st, n, streams, comp, raw, wrap, ret, produced, consumed, aux, reinterpret_cast<zn::zi_aux *>(counter))
                    : spec == 3 ? zn::zs_inflate_pipe_launch<2>(st, n, streams, comp, raw, wrap, ret, produced, consumed, aux, reinterpret_cast<zn::zi_aux *>(counter))
                    : spec == 1 ? zn::zs_inflate_spec_launch<true>(st, n, streams, comp, raw, wrap, ret, produced, consumed, aux, reinterpret_cast<zn::zi_aux *>(counter))
-                   : spec == 2 ? zm::zs_inflate_spec_launch<false>(st, n, streams, comp, raw, wrap, ret, produced, consumed, aux, reinterpret_cast<zm::zi_aux *>(counter))
+                   : spec == 2 ? zm::zs_inflate_spec_launch<false>(st, n, streams, comp, raw, wrap, ret, produced, consumed, aux, reinterpret_cast<zm::zi_aux *>(counter), spec_scratch)
                    : g == 32 ? zn::zs_inflate_group_launch<32>(st, n, streams, comp, raw, wrap, ret, produced, consumed, aux, reinterpret_cast<zn::zi_aux *>(counter))
                    : g == 16 ? zn::zs_inflate_group_launch<16>(st, n, streams, comp, raw, wrap, ret, produced, consumed, aux, reinterpret_cast<zn::zi_aux *>(counter))
                              : zw::zs_inflate_group_launch<8>(st, n, streams, comp, raw, wrap, ret, produced, consumed, aux, reinterpret_cast<zw::zi_aux *>(counter));

@@ -44,9 +44,24 @@
 #endif
 #define ZP_MARGIN 128u               /* input bits behind the round that stay with zi_step */
 
+/* The symbols of a round: in the scratch itself (shared memory on the device), or — ZP_REC_GLOBAL, the build for wide batches —
+ * in global memory behind a pointer, so that shared memory holds only tables and bitmap and more streams share an SM. */
+#undef ZP_REC_ST
+#undef ZP_REC_LD
+#ifdef ZP_REC_GLOBAL
+#define ZP_REC_ST(S, lane, i, v) ((S)->rec[(i) * ZP_RS + (lane)] = (v))
+#define ZP_REC_LD(S, lane, i) ((S)->rec[(i) * ZP_RS + (lane)])
+#else
+#define ZP_REC_ST(S, lane, i, v) zi_sa_st32(zi_sa_of((S)->rec) + 4u * ((i) * ZP_RS + (lane)), (v))
+#define ZP_REC_LD(S, lane, i) zi_sa_ld32(zi_sa_of((S)->rec) + 4u * ((i) * ZP_RS + (lane)))
+#endif
 typedef struct {
     uint32_t bitmap[ZP_NL * ZP_R / 32u];     /* bit b: some lane began a literal/length code b bits into the round, inside its own region */
+#ifdef ZP_REC_GLOBAL
+    uint32_t *rec;
+#else
     uint32_t rec[ZP_CAP * ZP_RS];            /* symbol i of lane k at [i * ZP_RS + k]: literal byte, or bit 31 | (len - 3) << 16 | (dist - 1) */
+#endif
 } zp_scratch;
 
 enum { ZP_RUNNING = 0, ZP_MERGED, ZP_SPAN_END, ZP_FULL, ZP_STOP };
@@ -102,7 +117,7 @@ ZID void zp_run(zp_lane *L, const zp_round *R, const zi_tables *T, const zi_aux 
                 zp_scratch *S, uint32_t lane, int phase, uint32_t budget)
 {
     const zi_sa lit_a = zi_sa_of(T->lit), dist_a = zi_sa_of(T->dist), pool_a = zi_sa_of(T->pool), len_a = zi_sa_of(lut_len), dl_a = zi_sa_of(lut_dist);
-    const zi_sa rec_a = zi_sa_of(S->rec) + 4u * lane, bm_a = zi_sa_of(S->bitmap);
+    const zi_sa bm_a = zi_sa_of(S->bitmap);
     if (L->reason != ZP_RUNNING) return;
     const uint32_t own_end = (lane + 1u) * ZP_R;
     for (;;) {
@@ -183,7 +198,7 @@ ZID void zp_run(zp_lane *L, const zp_round *R, const zi_tables *T, const zi_aux 
             r = 0x80000000u | ((len - 3u) << 16) | (dist - 1u);
             used = l + eb + l2 + eb2;
         }
-        if (!lead_in) { zi_sa_st32(rec_a + 4u * ZP_RS * L->nrec, r); L->nrec++; }
+        if (!lead_in) { ZP_REC_ST(S, lane, L->nrec, r); L->nrec++; }
         L->rel = rel + used;
         if (--budget == 0) return;
         continue;
@@ -210,10 +225,9 @@ ZID void zp_run(zp_lane *L, const zp_round *R, const zi_tables *T, const zi_aux 
 /* output bytes of the symbols [a, nrec) of a lane, and how far their matches reach in front of the first of them */
 ZID void zp_measure(zp_lane *L, const zp_scratch *S, uint32_t lane)
 {
-    const zi_sa rec_a = zi_sa_of(S->rec) + 4u * lane;
     uint32_t sum = 0, reach = 0;
     for (uint32_t i = L->a; i < L->nrec; i++) {
-        const uint32_t r = zi_sa_ld32(rec_a + 4u * ZP_RS * i);
+        const uint32_t r = ZP_REC_LD(S, lane, i);
         if (r >> 31) {
             const uint32_t len = ((r >> 16) & 0xFFu) + 3u, dist = (r & 0x7FFFu) + 1u;
             if (dist > sum && dist - sum > reach) reach = dist - sum;
