@@ -251,13 +251,14 @@ def inflate_config3(device, rank, world, barrier, allmax, peak):
         out = {"value": round(n_all * S / 1e6 / t, 2), "unit": "GB/s of output", "ms": round(t, 2), "streams": n_all, "output_bytes": n_all * S,
                "compressed_bytes": csum, "producer": producer, "launches_per_pass": 3, "scaling": "strong", "streams_per_rank": n,
                "parity": "all streams Z_OK with the trailer adler32 verified; first and last replica bit-exact with the inputs" if bad == 0 and same else f"MISMATCH ({bad} bad streams)",
-               "roofline": {"bound": "hbm", "kernel": "zs_inflate_group_kernel<8>" if n > 12288 else "zs_inflate_spec_kernel", "achieved": round((n_all * S + csum) / world / 1e6 / t, 1), "peak": peak, "unit": "GB/s",
+               "roofline": {"bound": "hbm", "kernel": "zs_inflate_spec_kernel<false>" if n > 888 else "zs_inflate_pipe_kernel", "achieved": round((n_all * S + csum) / world / 1e6 / t, 1), "peak": peak, "unit": "GB/s",
                             "frac": round((n_all * S + csum) / world / 1e6 / t / peak, 5), "algorithmic_bytes": (n_all * S + csum) // world,
                             "note": "C + N per pass and GPU over the whole pass (decode, output adler32, check kernels)"}}
         if world == 1:
-            # the same streams in narrower batches: up to 12 288 streams a warp decodes one stream with all 32 lanes
-            # (zs_inflate_spec_kernel, inflate_spec.h), up to 640 with the stream's window in shared memory, up to 444 with a
-            # second warp per stream that writes one round while the first decodes the next (zs_inflate_pipe_kernel)
+            # the same streams in narrower batches (a warp decodes one stream with all 32 lanes at every width, inflate_spec.h):
+            # beyond 888 streams the wide build (28 streams per SM), up to 592 one warp per stream with the stream's window in
+            # shared memory, up to 444 (and again up to 888, in two turns) with a second warp per stream that writes one round
+            # while the first decodes the next (zs_inflate_pipe_kernel)
             nb = {}
             for k in (64, 512, 4096):
                 if k > n:
@@ -270,7 +271,7 @@ def inflate_config3(device, rank, world, barrier, allmax, peak):
                 for _ in range(3):
                     E.sync(); E.event(0); E.relaunch(); E.event(1); E.sync(); tk.append(E.elapsed_ms(0, 1))
                 nb[str(k)] = {"value": round(k * S / 1e6 / min(tk), 2), "ms": round(min(tk), 3), "parity": "bit-exact" if okk else "MISMATCH"}
-            out["narrower_batches"] = dict(nb, unit="GB/s of output", kernel="the speculative warp decoder: zs_inflate_pipe_kernel up to 444 streams (two warps per stream), zs_inflate_spec_kernel beyond")
+            out["narrower_batches"] = dict(nb, unit="GB/s of output", kernel="the speculative warp decoder: zs_inflate_pipe_kernel at 64 streams (two warps per stream), zs_inflate_spec_kernel<true> at 512, <false> at 4096")
         if rank == 0 and refimpl.have_ref():
             cores = os.cpu_count() or 1
             packed = np.concatenate(comps)

@@ -406,6 +406,24 @@ def test_sharded_stream_parts_stitch_into_one_valid_stream(engine, checker):
     assert np.array_equal(whole, stream)                               # identical to the single-engine stream
 
 
+def test_uncompress_of_a_stream_of_more_sections_than_the_machine_holds(checker):
+    """zscgpu_uncompress_host decodes a large stream in waves of 28 sections per SM and sends a wave's bytes down while the
+    next decodes: 6144 sections of 16 KiB (two waves) and a corrupted copy of the stream — same result as the reference"""
+    Z = capi.zsc()
+    x = datagen.fill(96 << 20, 41, datagen.MIXED)
+    rc, comp = Z.compress(x, 16384, 1)
+    assert rc == 0 and len(comp) >= 32 << 20
+    r, back, used = Z.uncompress(comp, len(x))
+    assert r == 0 and used == len(comp) and np.array_equal(back, x)
+    rr, out, used2 = checker.uncompress(comp, len(x))
+    assert rr == 0 and np.array_equal(out, x)
+    bad = comp.copy()
+    bad[len(bad) // 3] ^= 0x20
+    r, back, used = Z.uncompress(bad, len(x))
+    rr, out, used2 = checker.uncompress(bad, len(x))
+    assert r == rr and used == used2 and len(back) == len(out) and np.array_equal(back, out)
+
+
 # ------------------------------------------------------------------ full BASELINE size, size-independent properties
 def test_full_size_round_trip_1GiB_level1():
     """configs[1] at full size: deflate L1 -> GPU inflate round trip, checksum of the round trip equals the

@@ -132,7 +132,6 @@ struct zscgpu_engine {
     cudaEvent_t ev[ZS_NEVENTS];
     cudaStream_t copy_stream, d2h_stream;   /* host-buffer calls: uploads / downloads overlap the kernels */
     cudaStream_t stream2;                   /* odd waves of a host-buffer call run here, so that they overlap the even ones */
-    cudaStream_t stream_lo;                 /* lowest priority: the second wave of zscgpu_uncompress_host takes the SM slots the first one frees */
     cudaEvent_t ev_slice[2];                /* kernels + result copies of the wave in slice 0 / 1 are done */
     cudaEvent_t ev_wave[ZS_MAX_WAVES];
     /* last enqueue, for zscgpu_relaunch */
@@ -278,11 +277,6 @@ static int zs_init_engine(zscgpu_engine *e, const zscgpu_config &cfg, const cuda
     ZS_CUDA_CHECK(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
     ZS_CUDA_CHECK(cudaStreamCreateWithFlags(&e->d2h_stream, cudaStreamNonBlocking));
     ZS_CUDA_CHECK(cudaStreamCreateWithFlags(&e->stream2, cudaStreamNonBlocking));
-    {
-        int lo = 0, hi = 0;                 /* (numerically greatest = lowest priority) */
-        ZS_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-        ZS_CUDA_CHECK(cudaStreamCreateWithPriority(&e->stream_lo, cudaStreamNonBlocking, lo));
-    }
     for (int i = 0; i < 2; i++) ZS_CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_slice[i], cudaEventDisableTiming));
     for (int i = 0; i < ZS_MAX_WAVES; i++) ZS_CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_wave[i], cudaEventDisableTiming));
     for (int i = 0; i < 2 * ZS_STAGE_BUFS; i++) {
@@ -321,7 +315,6 @@ extern "C" void zscgpu_destroy(zscgpu_engine *e)
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     if (e->d2h_stream) cudaStreamDestroy(e->d2h_stream);
     if (e->stream2) cudaStreamDestroy(e->stream2);
-    if (e->stream_lo) cudaStreamDestroy(e->stream_lo);
     for (int i = 0; i < 2; i++) if (e->ev_slice[i]) cudaEventDestroy(e->ev_slice[i]);
     if (e->stream) cudaStreamDestroy(e->stream);
     cudaGetLastError();                           /* a half-built engine may have tripped on a null handle above */
@@ -1184,8 +1177,8 @@ extern "C" int zscgpu_compress_host(zscgpu_engine *e, uint8_t *dest, uint32_t de
     return ZSCGPU_OK;
 }
 
-/* zscgpu_uncompress_host on a large stream: the sections are decoded in a few waves on two streams, and the bytes of a
- * wave go down to the host while the later waves are still decoding (the download of a GiB takes as long as decoding it).
+/* zscgpu_uncompress_host on a large stream: the sections are decoded in waves, and the bytes of a wave go down to the host
+ * while the later waves are still decoding.
  * Only for streams that look like zsc_compress made them (one pass straight to k * S, see zscgpu_inflate_sectioned);
  * *done = 0 leaves everything to the ordinary path, which then also overwrites whatever this attempt wrote to `dest`. */
 static int zs_uncompress_host_waves(zscgpu_engine *e, uint8_t *dest, const zscgpu_stream *stream, int32_t wrap, zscgpu_result *res, int *done)
@@ -1207,16 +1200,16 @@ static int zs_uncompress_host_waves(zscgpu_engine *e, uint8_t *dest, const zscgp
         opts[k] = 2u | (k ? 4u : 0u);
     }
     const bool pageable = zs_is_pageable(dest);
-    /* two waves on two streams: as many sections as are sure to be resident at once (the kernel holds 16 warps per SM; at 14
-       and more per SM a few CTAs of the first wave now and then had to wait for a slot, which doubled its time: measured,
-       profiles/README.md), and the rest, whose warps start where the first wave leaves room and as its warps end — the
-       first wave's bytes go down while the second decodes */
-    uint32_t nw = 2;
-    uint32_t slots = 12u * (uint32_t)e->sms;
-#ifdef ZSC_TUNING
-    if (getenv("ZSC_B200_UNC_SLOTS")) slots = (uint32_t)atoi(getenv("ZSC_B200_UNC_SLOTS")) * (uint32_t)e->sms;
-#endif
-    uint32_t cut[ZS_MAX_WAVES + 1] = {0, ns > slots ? slots : ns / 2, ns};
+    /* Waves of as many sections as the machine holds at once (28 per SM, inflate.cu), one behind the other on one stream:
+       the bytes of a wave go down while the next one decodes.  A stream of up to that many sections is one wave — its
+       sections all end within a few milliseconds of each other, there is nothing to overlap; measured with 2 / 3 / 4
+       waves, side by side and one behind the other (profiles/README.md): the kernel is bound by the latency of a
+       section, not by the machine, so a wave of half the sections takes three quarters of the time of all. */
+    const uint32_t per_wave = 28u * (uint32_t)e->sms;
+    uint32_t nw = (ns + per_wave - 1) / per_wave;
+    if (nw > ZS_MAX_WAVES) nw = ZS_MAX_WAVES;
+    uint32_t cut[ZS_MAX_WAVES + 1];
+    for (uint32_t v = 0; v <= nw; v++) cut[v] = (uint32_t)((uint64_t)ns * v / nw);
 #ifdef ZSC_TUNING
     const bool trace = getenv("ZSC_B200_TRACE") != nullptr;
     auto now_ms = []() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; };
@@ -1228,13 +1221,11 @@ static int zs_uncompress_host_waves(zscgpu_engine *e, uint8_t *dest, const zscgp
         int r = zs_inflate_desc(e, st, ns, wrap, opts); if (r) return r;
         ZS_CUDA_CHECK(cudaEventRecord(e->ev_slice[0], e->stream));
         ZS_CUDA_CHECK(cudaStreamWaitEvent(e->stream2, e->ev_slice[0], 0));
-        ZS_CUDA_CHECK(cudaStreamWaitEvent(e->stream_lo, e->ev_slice[0], 0));
         for (uint32_t v = 0; v < nw; v++) {
             const uint32_t k0 = cut[v], k1 = cut[v + 1];
-            cudaStream_t cs = (v & 1) ? (nw == 2 ? e->stream_lo : e->stream2) : e->stream;
+            cudaStream_t cs = e->stream;
 #ifdef ZSC_TUNING
-            if (getenv("ZSC_B200_UNC_STREAMS") && atoi(getenv("ZSC_B200_UNC_STREAMS")) == 3 && v % 3 == 2) cs = e->copy_stream;
-            if (getenv("ZSC_B200_UNC_STREAMS") && atoi(getenv("ZSC_B200_UNC_STREAMS")) == 1) cs = e->stream;
+            if (getenv("ZSC_B200_UNC_STREAMS") && atoi(getenv("ZSC_B200_UNC_STREAMS")) >= 2 && (v & 1)) cs = e->stream2;   /* (odd waves beside the even ones) */
 #endif
             ZS_CUDA_CHECK(zs_inflate_launch(cs, k1 - k0, e->d_streams + k0, e->d_comp, e->d_raw, wrap, e->d_ret + k0, e->d_produced + k0, e->d_consumed + k0,
                                             e->d_check + k0, e->d_aux + 2ull * k0, e->d_adler + k0, e->last_max_raw, 0, e->d_ctr + 160ull * k0, -1,
