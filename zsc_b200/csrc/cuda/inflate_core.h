@@ -251,10 +251,12 @@ ZID void zi_walk_start(const uint16_t *count, int tbits, uint32_t *first_out, ui
     *first_out = first; *index_out = index;
 }
 
-/* direct entries of the codes of at most `root` bits (sorted / count as zi_build leaves them) */
-ZID void zi_fill_root(const uint16_t *sorted, const uint16_t *count, int root, uint16_t *table)
+/* direct entries of the codes of at most `root` bits (sorted / count as zi_build leaves them).  `complete`: the code leaves no
+ * bit pattern unused, so every root slot is written here or, as the prefix of longer codes, by zi_fill_long: no need to clear
+ * the table first (a thousand stores per block on one lane). */
+ZID void zi_fill_root(const uint16_t *sorted, const uint16_t *count, int root, uint16_t *table, int complete)
 {
-    for (int i = 0; i < (1 << root); i++) table[i] = 0;
+    if (!complete) for (int i = 0; i < (1 << root); i++) table[i] = 0;
     uint32_t code = 0; int k = 0;
     for (int l = 1; l <= root; l++) {
         for (int c = 0; c < count[l]; c++, k++, code++) {
@@ -280,18 +282,22 @@ ZID void zi_fill_long(const uint16_t *sorted, const uint16_t *count, int root, u
         for (int c = 0; c < count[l]; c++, c2++) table[zi_rev(c2, l) & rmask] = (uint16_t)(0x4000u | (uint32_t)(l - root));
         c2 <<= 1;
     }
-    for (uint32_t s = 0; s <= rmask; s++) {
-        const uint32_t e = table[s];
-        if ((e & 0xC000u) != 0x4000u) continue;
-        const uint32_t sb = e & 15u, need = 1u << sb;
-        if (sb > 7u || *pool_used + need > ZI_POOL) { table[s] = 0; continue; }
-        for (uint32_t j = 0; j < need; j++) pool[*pool_used + j] = 0;
-        table[s] = (uint16_t)(0x8000u | (sb << 10) | *pool_used);
-        *pool_used += need;
-    }
+    /* sub-tables are handed out in code order, each when the first code under its root slot comes by (a walk over the
+       long codes, a few dozen, instead of one over all root slots) */
     for (int l = root + 1; l <= 15; l++) {
         for (int c = 0; c < count[l]; c++, k++, code++) {
-            const uint32_t r = zi_rev(code, l), e = table[r & rmask];
+            const uint32_t r = zi_rev(code, l), slot = r & rmask;
+            uint32_t e = table[slot];
+            if ((e & 0xC000u) == 0x4000u) {
+                const uint32_t sb = e & 15u, need = 1u << sb;
+                if (sb > 7u || *pool_used + need > ZI_POOL) e = 0;
+                else {
+                    for (uint32_t j = 0; j < need; j++) pool[*pool_used + j] = 0;
+                    e = 0x8000u | (sb << 10) | *pool_used;
+                    *pool_used += need;
+                }
+                table[slot] = (uint16_t)e;
+            }
             if (!(e & 0x8000u)) continue;
             const uint32_t sb = (e >> 10) & 7u, off = e & 0x3FFu;
             const uint16_t v = (uint16_t)(sorted[k] | (l << 9));
@@ -318,7 +324,7 @@ ZID int zi_build2(const uint8_t *lens, int n, int root, uint16_t *table, uint16_
     for (int l = 1; l < 15; l++) offs[l + 1] = (uint16_t)(offs[l] + count[l]);
     for (int i = 0; i < n; i++) if (lens[i]) sorted[offs[lens[i]]++] = (uint16_t)i;
     count[0] = 0;
-    zi_fill_root(sorted, count, root, table);
+    zi_fill_root(sorted, count, root, table, left == 0);
     zi_fill_long(sorted, count, root, table, pool, pool_used);
     return 0;
 }
@@ -386,7 +392,7 @@ ZID int zi_block_head(zi_io *io, zi_tables *T, zi_aux *X, zi_result *res, uint32
                 for (int i = 0; i < 144; i++) X->lsorted[k++] = (uint16_t)i;
                 for (int i = 280; i < 288; i++) X->lsorted[k++] = (uint16_t)i;
                 for (int i = 144; i < 256; i++) X->lsorted[k++] = (uint16_t)i;
-                zi_fill_root(X->lsorted, T->lcount, ZI_LBITS, T->lit);      /* no code is longer than 9 bits */
+                zi_fill_root(X->lsorted, T->lcount, ZI_LBITS, T->lit, 1);   /* no code is longer than 9 bits */
             } else {
                 zi_refill(io);
                 uint32_t nlen = zi_take(io, 5) + 257, ndist = zi_take(io, 5) + 1, ncode = zi_take(io, 4) + 4;
@@ -439,7 +445,7 @@ ZID int zi_block_head(zi_io *io, zi_tables *T, zi_aux *X, zi_result *res, uint32
                     offs[1] = 0;
                     for (int l = 1; l < 15; l++) offs[l + 1] = (uint16_t)(offs[l] + T->lcount[l]);
                     for (uint32_t k = 0; k < nlen; k++) if (lens[k]) X->lsorted[offs[lens[k]]++] = (uint16_t)k;
-                    zi_fill_root(X->lsorted, T->lcount, ZI_LBITS, T->lit);
+                    zi_fill_root(X->lsorted, T->lcount, ZI_LBITS, T->lit, left == 0);
                     zi_fill_long(X->lsorted, T->lcount, ZI_LBITS, T->lit, T->pool, &T->pool_used);
                 }
             }
