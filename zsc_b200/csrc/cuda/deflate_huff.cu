@@ -595,7 +595,8 @@ zs_offset_kernel(const ZsStream *__restrict__ streams, uint4 *__restrict__ blk_m
 
 /* ======================= K3: bit packing, one CTA per block ======================= */
 #define ZE_THREADS 256
-#define ZE_RUN 32                                   /* symbols per thread */
+#define ZE_SUB 8                                    /* symbols per thread and round */
+#define ZE_ROUNDS 4
 #define ZE_STAGE_WORDS 12480                        /* 16 + 3072 + 8192*48 + 15 + 47 bits, rounded up */
 
 struct ZeSmem {
@@ -603,11 +604,11 @@ struct ZeSmem {
     uint32_t lcode[ZH_LCODES_PAD];
     uint32_t dcode[ZH_DCODES_PAD];
     uint32_t lenmap[256];       /* (len code bits | extra << codelen) | nbits << 24 */
-    uint32_t wsum[ZE_THREADS / 32];
+    uint32_t wsum[2][ZE_THREADS / 32];
     uint32_t total_bits;
 };
 
-static_assert(ZS_BLOCK_SYMS == ZE_THREADS * ZE_RUN, "one run of ZE_RUN symbols per thread");
+static_assert(ZS_BLOCK_SYMS == ZE_THREADS * ZE_SUB * ZE_ROUNDS && ZE_SUB % 4 == 0, "ZE_ROUNDS rounds of ZE_SUB symbols per thread");
 
 __device__ __forceinline__ void ze_or_bits(uint32_t *stage, uint32_t pos, uint64_t v, uint32_t n)
 {
@@ -734,73 +735,70 @@ zs_encode_kernel(const zh_block *__restrict__ blocks, const uint32_t *__restrict
     }
     __syncthreads();
 
-    /* ---- pass 1: bits per thread run.  The run's symbols are read again in pass 2 (they sit in L1 / L2 by
-            then) rather than held in 32 registers: at <= 64 registers four CTAs share an SM ---- */
+    /* ---- the block in ZE_ROUNDS rounds of ZE_SUB symbols per thread.  A round computes the code bits of its symbols ONCE
+            and keeps them in registers (two words per symbol: length part | bits << 24, distance part under a sentinel
+            bit), a block-wide prefix sum of the bit counts gives every thread its position, then the thread packs its
+            run: only the first and the last word of a run can be shared with a neighbour ---- */
     const uint32_t *bs = sym + bp->sym_off;
-    const uint32_t s0 = tid * ZE_RUN;
-    uint32_t mybits = 0;
-#pragma unroll
-    for (int h = 0; h < ZE_RUN / 16; h++) {
-        uint4 v[4];
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            v[i] = make_uint4(0, 0, 0, 0);
-            if (s0 + h * 16 + i * 4 < nsym) v[i] = __ldg(reinterpret_cast<const uint4 *>(bs + s0 + h * 16) + i);
-        }
-#pragma unroll
-        for (int i = 0; i < 16; i++) {
-            const uint32_t sv = (i & 3) == 0 ? v[i >> 2].x : (i & 3) == 1 ? v[i >> 2].y : (i & 3) == 2 ? v[i >> 2].z : v[i >> 2].w;
-            if (s0 + h * 16 + i < nsym) { uint32_t v0, n0, v1, n1; ze_sym_bits(S, sv, v0, n0, v1, n1); mybits += n0 + n1; }
-        }
-    }
-    uint32_t inc = mybits;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, o); if ((int)lane >= o) inc += t; }
-    if (lane == 31) S.wsum[warp] = inc;
-    __syncthreads();
-    uint32_t wbase = 0;
-    for (uint32_t w = 0; w < warp; w++) wbase += S.wsum[w];
-    if (tid == ZE_THREADS - 1) S.total_bits = wbase + inc;
     const uint32_t sympos = lbase + pre_bits + hdr_bits;
-    uint32_t pos = sympos + wbase + inc - mybits;
-
-    /* ---- pass 2: pack the run; only its first and last words can be shared with neighbours ---- */
-    if (mybits) {
-        uint32_t w = pos >> 5;
-        uint32_t fill = pos & 31;
-        unsigned long long acc = 0;
-        bool first = true;
+    uint32_t base = sympos;                              /* bit position of the round's first symbol */
+#pragma unroll 1
+    for (uint32_t r = 0; r < ZE_ROUNDS; r++) {
+        const uint32_t s0 = (r * ZE_THREADS + tid) * ZE_SUB;
+        if (r * ZE_THREADS * ZE_SUB >= nsym) break;      /* uniform */
+        uint32_t ca[ZE_SUB], cb[ZE_SUB];
+        uint32_t mybits = 0;
+        {
+            uint4 v[ZE_SUB / 4];
 #pragma unroll
-        for (int h = 0; h < ZE_RUN / 16; h++) {
-            uint4 v[4];
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
+            for (int i = 0; i < ZE_SUB / 4; i++) {
                 v[i] = make_uint4(0, 0, 0, 0);
-                if (s0 + h * 16 + i * 4 < nsym) v[i] = __ldg(reinterpret_cast<const uint4 *>(bs + s0 + h * 16) + i);
+                if (s0 + i * 4 < nsym) v[i] = __ldg(reinterpret_cast<const uint4 *>(bs + s0) + i);
             }
 #pragma unroll
-            for (int i = 0; i < 16; i++) {
+            for (int i = 0; i < ZE_SUB; i++) {
                 const uint32_t sv = (i & 3) == 0 ? v[i >> 2].x : (i & 3) == 1 ? v[i >> 2].y : (i & 3) == 2 ? v[i >> 2].z : v[i >> 2].w;
-                if (s0 + h * 16 + i < nsym) {
-                    uint32_t v0, n0, v1, n1;
-                    ze_sym_bits(S, sv, v0, n0, v1, n1);
-                    acc |= (unsigned long long)v0 << fill; fill += n0;
+                uint32_t v0 = 0, n0 = 0, v1 = 0, n1 = 0;
+                if (s0 + i < nsym) ze_sym_bits(S, sv, v0, n0, v1, n1);
+                ca[i] = v0 | (n0 << 24); cb[i] = v1 | (1u << n1);
+                mybits += n0 + n1;
+            }
+        }
+        uint32_t inc = mybits;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, o); if ((int)lane >= o) inc += t; }
+        if (lane == 31) S.wsum[r & 1][warp] = inc;
+        __syncthreads();
+        uint32_t wbase = 0, total = 0;
+#pragma unroll
+        for (uint32_t w = 0; w < ZE_THREADS / 32; w++) { const uint32_t t = S.wsum[r & 1][w]; total += t; if (w < warp) wbase += t; }
+        uint32_t pos = base + wbase + inc - mybits;
+        base += total;
+        if (mybits) {
+            uint32_t w = pos >> 5;
+            uint32_t fill = pos & 31;
+            unsigned long long acc = 0;
+            bool first = true;
+#pragma unroll
+            for (int i = 0; i < ZE_SUB; i++) {
+                acc |= (unsigned long long)(ca[i] & 0xFFFFFFu) << fill; fill += ca[i] >> 24;
+                if (fill >= 32) {
+                    if (first) { atomicOr(&S.stage[w], (uint32_t)acc); first = false; } else S.stage[w] = (uint32_t)acc;
+                    w++; acc >>= 32; fill -= 32;
+                }
+                if (cb[i] > 1u) {
+                    const uint32_t n1 = 31u - (uint32_t)__clz((int)cb[i]);
+                    acc |= (unsigned long long)(cb[i] ^ (1u << n1)) << fill; fill += n1;
                     if (fill >= 32) {
                         if (first) { atomicOr(&S.stage[w], (uint32_t)acc); first = false; } else S.stage[w] = (uint32_t)acc;
                         w++; acc >>= 32; fill -= 32;
                     }
-                    if (n1) {
-                        acc |= (unsigned long long)v1 << fill; fill += n1;
-                        if (fill >= 32) {
-                            if (first) { atomicOr(&S.stage[w], (uint32_t)acc); first = false; } else S.stage[w] = (uint32_t)acc;
-                            w++; acc >>= 32; fill -= 32;
-                        }
-                    }
                 }
             }
+            if (fill) atomicOr(&S.stage[w], (uint32_t)acc);
         }
-        if (fill) atomicOr(&S.stage[w], (uint32_t)acc);
     }
+    if (tid == 0) S.total_bits = base - sympos;
     __syncthreads();
     if (tid == 0) {
         /* end-of-block, then the suffix */
