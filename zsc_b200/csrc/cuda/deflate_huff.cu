@@ -41,9 +41,79 @@ struct __align__(16) ZbScratch {
     int32_t m, max_l, max_d, pad;
 };
 
+/* zh_lengths (huff_build.h) for an alphabet of n <= 30 symbols on one warp, lane = symbol: the same dummy symbols, the
+ * same sort order (frequency, then symbol), the same two-queue merge (the leaf on ties), the same repair of lengths
+ * beyond maxbits — the same lengths.  Weights, parents and depths live in registers and travel by shuffles; `sw` is 32
+ * words of shared scratch of this warp.  Returns the largest symbol with a code; *len_out = the length of symbol `lane`. */
+__device__ __forceinline__ int zb_lengths_warp(uint32_t f, int n, int maxbits, uint32_t *sw, uint32_t *len_out)
+{
+    const uint32_t FULL = 0xFFFFFFFFu;
+    const int lane = (int)(threadIdx.x & 31);
+    if (lane >= n) f = 0;
+    uint32_t usedm = __ballot_sync(FULL, f != 0);
+    int m = __popc(usedm);
+    int max_code = usedm ? 31 - __clz((int)usedm) : -1;
+    while (m < 2) {                                         /* zh_lengths_prepare: at least two symbols get a code */
+        const int node = (max_code < 2) ? ++max_code : 0;
+        if (lane == node) f = 1;
+        usedm |= 1u << node; m++;
+    }
+    const uint32_t key = (f << 9) | (uint32_t)lane;
+    int rank = 0;
+    for (int j = 0; j < n; j++) { const uint32_t kj = __shfl_sync(FULL, key, j); rank += (((usedm >> j) & 1u) && kj < key) ? 1 : 0; }
+    if (f) sw[rank] = key;
+    __syncwarp();
+    const uint32_t skey = lane < m ? sw[lane] : 0u;         /* lane i: the i-th smallest key */
+    __syncwarp();
+    const uint32_t wl = skey >> 9;                          /* leaf weights; wi: lane e holds internal node e */
+    uint32_t wi = 0;
+    int pl = 0, pi = 0;                                     /* parent (an internal node's number) of leaf `lane` / internal node `lane` */
+    int a = 0, b = 0, e = 0;
+    for (int it = 0; it < m - 1; it++) {
+        uint32_t sum, la = __shfl_sync(FULL, wl, a & 31), ib = __shfl_sync(FULL, wi, b & 31);
+        if (a < m && (b >= e || la <= ib)) { if (lane == a) pl = e; sum = la; a++; } else { if (lane == b) pi = e; sum = ib; b++; }
+        la = __shfl_sync(FULL, wl, a & 31); ib = __shfl_sync(FULL, wi, b & 31);
+        if (a < m && (b >= e || la <= ib)) { if (lane == a) pl = e; sum += la; a++; } else { if (lane == b) pi = e; sum += ib; b++; }
+        if (lane == e) wi = sum;
+        e++;
+    }
+    uint32_t di = 0;                                        /* depth of internal node `lane`; the root (e - 1) has 0 */
+    for (int i = e - 2; i >= 0; i--) { const int p = __shfl_sync(FULL, pi, i); const uint32_t d = __shfl_sync(FULL, di, p) + 1u; if (lane == i) di = d; }
+    uint32_t dl = __shfl_sync(FULL, di, pl) + 1u;
+    const bool isleaf = lane < m;
+    const bool ov = isleaf && dl > (uint32_t)maxbits;
+    if (ov) dl = (uint32_t)maxbits;
+    if (__ballot_sync(FULL, ov)) {                          /* zh_repair, bl_count[l] on lane l */
+        uint32_t cnt = 0;
+        for (int bits = 1; bits <= maxbits; bits++) { const uint32_t c = (uint32_t)__popc(__ballot_sync(FULL, isleaf && dl == (uint32_t)bits)); if (lane == bits) cnt = c; }
+        int ex = (lane >= 1 && lane <= maxbits) ? (int)(cnt << (maxbits - lane)) : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ex += __shfl_xor_sync(FULL, ex, o);
+        int excess = ex - (1 << maxbits);
+        while (excess > 0) {
+            const uint32_t nz = __ballot_sync(FULL, cnt != 0 && lane >= 1 && lane < maxbits);
+            const int bits = 31 - __clz((int)nz);
+            if (lane == bits) cnt--;
+            if (lane == bits + 1) cnt += 2;
+            if (lane == maxbits) cnt--;
+            excess--;
+        }
+        uint32_t dnew = 0, run = 0;
+        for (int bits = maxbits; bits >= 1; bits--) { const uint32_t c = __shfl_sync(FULL, cnt, bits); if ((uint32_t)lane >= run && (uint32_t)lane < run + c) dnew = (uint32_t)bits; run += c; }
+        dl = dnew;
+    }
+    sw[lane] = 0;
+    __syncwarp();
+    if (isleaf) sw[skey & 0x1Fu] = dl;
+    __syncwarp();
+    *len_out = sw[lane];
+    __syncwarp();
+    return max_code;
+}
+
 /* The serial recipe of zh_build_block (huff_build.h) spread over the CTA: key collection, sort, leaf depths,
  * costs, canonical codes and the header bit string run on all threads; the distance tree and the 19-symbol
- * code-length tree stay on one thread.  The two-queue merge of the literal/length tree — an inherently serial
+ * code-length tree are built by one warp each (zb_lengths_warp).  The two-queue merge of the literal/length tree — an inherently serial
  * walk of up to 285 steps — is taken out into zs_merge_kernel, where every lane merges a different block
  * (in here it kept one lane busy and 127 waiting for 41 % of a block's time): PHASE 0 is everything before
  * it, PHASE 1 everything after.  Results are identical to the serial form (tests compare the GPU stream with
@@ -129,29 +199,32 @@ zs_block_kernel(const ZsChunk *__restrict__ chunks, const uint32_t *__restrict__
     /* fewer than two used symbols (an empty block): the serial routine adds the dummy symbols */
     if (S.m < 2) { if (tid == 0) S.m = zh_lengths_prepare(S.lfreq[0], ZH_LCODES, &S.sc, &S.max_l); __syncthreads(); }
     m = S.m;
-    /* ---- rank sort of the keys (unique) on all threads; the distance tree meanwhile on one thread ---- */
+    /* ---- the distance tree on one warp (zs_merge_kernel had it as a one-thread job in local memory, the longer of its
+            two jobs); the other warps go on to the sort ---- */
+    if (warp == ZB_WARPS - 1) {
+        uint32_t dl;
+        const int md = zb_lengths_warp(S.dfreq[0][lane], ZH_DCODES, 15, S.sc2.tmpfreq, &dl);
+        X.dlen[lane] = (uint8_t)dl;
+        if (lane == 0) X.max_d = md;
+    }
+    /* ---- bitonic sort of the keys (unique) on all threads, in a power-of-two array padded with 0xFFFFFFFF (a rank sort —
+            every key against every other — was 41 % of this kernel's instructions) ---- */
     {
-        uint32_t *sorted = S.sc.w + ZH_LCODES_PAD;          /* free until the merge starts */
-        /* a thread ranks its (up to three) keys in one sweep over the key array, four keys per load */
-        static_assert(ZH_LCODES_PAD <= 3 * ZB_THREADS && ZH_LCODES_PAD % 4 == 0, "rank sort covers three keys per thread");
-        for (int i = m + (int)tid; i < ((m + 3) & ~3); i += ZB_THREADS) S.sc.key[i] = 0xFFFFFFFFu;   /* pad to a multiple of 4 */
+        uint32_t *A = S.sc.w;                               /* 2 * ZH_LCODES_PAD words, free until the merge starts */
+        static_assert(2 * ZH_LCODES_PAD >= 512 && ZH_LCODES <= 512, "the sort array holds 512 keys");
+        const uint32_t N = m <= 128 ? 128u : m <= 256 ? 256u : 512u;
+        for (uint32_t i = tid; i < N; i += ZB_THREADS) A[i] = (int)i < m ? S.sc.key[i] : 0xFFFFFFFFu;
         __syncthreads();
-        const uint32_t k0 = (int)tid < m ? S.sc.key[tid] : 0u;
-        const uint32_t k1 = (int)tid + ZB_THREADS < m ? S.sc.key[tid + ZB_THREADS] : 0u;
-        const uint32_t k2 = (int)tid + 2 * ZB_THREADS < m ? S.sc.key[tid + 2 * ZB_THREADS] : 0u;
-        uint32_t r0 = 0, r1 = 0, r2 = 0;
-        const uint4 *k4 = reinterpret_cast<const uint4 *>(S.sc.key);
-        for (int j = 0; j < (m + 3) >> 2; j++) {
-            const uint4 q = k4[j];
-            r0 += (q.x < k0) + (q.y < k0) + (q.z < k0) + (q.w < k0);
-            r1 += (q.x < k1) + (q.y < k1) + (q.z < k1) + (q.w < k1);
-            r2 += (q.x < k2) + (q.y < k2) + (q.z < k2) + (q.w < k2);
-        }
-        if ((int)tid < m) sorted[r0] = k0;
-        if ((int)tid + ZB_THREADS < m) sorted[r1] = k1;
-        if ((int)tid + 2 * ZB_THREADS < m) sorted[r2] = k2;
-        __syncthreads();
-        for (int i = (int)tid; i < m; i += ZB_THREADS) S.sc.key[i] = sorted[i];
+        for (uint32_t kk = 2; kk <= N; kk <<= 1)
+            for (uint32_t j = kk >> 1; j > 0; j >>= 1) {
+                for (uint32_t p = tid; p < (N >> 1); p += ZB_THREADS) {
+                    const uint32_t i = ((p & ~(j - 1u)) << 1) | (p & (j - 1u)), l = i | j;
+                    const uint32_t x = A[i], y = A[l];
+                    if ((x > y) == ((i & kk) == 0u)) { A[i] = y; A[l] = x; }
+                }
+                __syncthreads();
+            }
+        for (int i = (int)tid; i < ((m + 3) & ~3); i += ZB_THREADS) S.sc.key[i] = A[i];     /* the pad to a multiple of 4 is 0xFFFFFFFF */
     }
     __syncthreads();
     /* ---- the hand-over (the distance tree, a serial job of one thread, is built in zs_merge_kernel where every
@@ -283,9 +356,14 @@ zs_block_kernel(const ZsChunk *__restrict__ chunks, const uint32_t *__restrict__
     }
     __syncthreads();
     /* ---- code-length tree (19 symbols) on one thread, header size on all, decision ---- */
+    if (warp == 0) {
+        uint32_t bl;
+        (void)zb_lengths_warp(lane < ZH_BLCODES ? S.sc.blfreq[lane] : 0u, ZH_BLCODES, 7, S.sc.tmpfreq, &bl);
+        if (lane < ZH_BLCODES) S.sc.bllen[lane] = (uint8_t)bl;
+        __syncwarp();
+    }
     if (tid == 0) {
         const int bl_order[ZH_BLCODES] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
-        (void)zh_lengths(S.sc.blfreq, ZH_BLCODES, 7, S.sc.bllen, &S.sc);
         int nbl = ZH_BLCODES;
         while (nbl > 4 && S.sc.bllen[bl_order[nbl - 1]] == 0) nbl--;
         S.D.nbl = nbl; S.D.nl = nl; S.D.nd = nd;
@@ -434,26 +512,20 @@ zs_block_kernel(const ZsChunk *__restrict__ chunks, const uint32_t *__restrict__
 /* ======================= K2m: the serial tree work, one block per lane ======================= */
 #define ZMG_THREADS 64
 
-/* Two inherently serial jobs of a block, done where every lane has one of each to do:
- * (1) the two-queue merge of the literal/length tree.  Leaves are the sorted keys (weight = key >> 9 <= 8193,
- *     16 bits); they are first copied from the hand-over into shared memory — in the loop they would be
- *     dependent global loads, one L2 round trip per merge step — next to the weights of the internal nodes,
- *     which the merge both appends and consumes in order; one column per lane.  Same picks as zh_merge
- *     (huff_build.h): the smaller head of the two queues, the leaf on ties.
- * (2) the whole distance tree (30 symbols: sort, merge, depths, length limit) with zh_lengths on a
- *     thread-private scratch. */
-__global__ void __launch_bounds__(2 * ZMG_THREADS)
+/* The one inherently serial job of a block, done where every lane has one to do: the two-queue merge of the
+ * literal/length tree.  Leaves are the sorted keys (weight = key >> 9 <= 8193, 16 bits); they are first copied from the
+ * hand-over into shared memory — in the loop they would be dependent global loads, one L2 round trip per merge step —
+ * next to the weights of the internal nodes, which the merge both appends and consumes in order; one column per lane.  Same picks as zh_merge (huff_build.h): the smaller head of the two queues, the leaf on
+ * ties.  (The distance tree and the code-length tree, 30 and 19 symbols, are built by a warp each inside
+ * zs_block_kernel<0> / <1>: zb_lengths_warp.) */
+__global__ void __launch_bounds__(ZMG_THREADS)
 zs_merge_kernel(ZbScratch *__restrict__ scratch, const uint32_t *__restrict__ used)
 {
     extern __shared__ uint16_t zmg_w[];                    /* [2][ZH_LCODES_PAD][ZMG_THREADS]: leaves, internal nodes */
-    /* the two jobs of a block run on two different threads (warps 0-1: merges, warps 2-3: distance trees): twice the
-       warps per SM for a kernel that is pure latency, and the jobs overlap instead of following each other */
-    const uint32_t col = threadIdx.x % ZMG_THREADS;
-    const bool dist_job = threadIdx.x >= ZMG_THREADS;
+    const uint32_t col = threadIdx.x;
     const uint32_t t = blockIdx.x * ZMG_THREADS + col;
     if (t >= used[0]) return;
     ZbScratch &X = scratch[used[1 + t]];
-    if (!dist_job) {
     const int m = X.m;
     uint16_t *wl = zmg_w + col;
     uint16_t *w = zmg_w + ZH_LCODES_PAD * ZMG_THREADS + col;
@@ -467,7 +539,7 @@ zs_merge_kernel(ZbScratch *__restrict__ scratch, const uint32_t *__restrict__ us
         }
     }
     int a = 0, b = 0, e = 0;                               /* leaves taken, internal nodes taken, internal nodes made */
-    uint32_t la = wl[0], ib = 0xFFFFFFFFu;                 /* heads of the two queues */
+    uint32_t la = wl[0], ib = 0xFFFFFFFFu;                  /* heads of the two queues */
     for (int it = 0; it < m - 1; it++) {
         uint32_t sum; int x0, x1;
         if (a < m && la <= ib) { x0 = a++; sum = la; la = a < m ? wl[a * ZMG_THREADS] : 0xFFFFFFFFu; }
@@ -478,16 +550,6 @@ zs_merge_kernel(ZbScratch *__restrict__ scratch, const uint32_t *__restrict__ us
         X.parent[x0] = (uint16_t)(m + e); X.parent[x1] = (uint16_t)(m + e);
         if (b == e) ib = sum;                              /* the queue was empty: the new node is its head */
         e++;
-    }
-    } else {
-        zh_small sc;
-        uint32_t df[ZH_DCODES_PAD];
-        uint8_t dl[ZH_DCODES_PAD];
-        const uint4 *f4 = reinterpret_cast<const uint4 *>(X.dfreq);
-#pragma unroll
-        for (int j = 0; j < ZH_DCODES_PAD / 4; j++) { const uint4 q = f4[j]; df[4 * j] = q.x; df[4 * j + 1] = q.y; df[4 * j + 2] = q.z; df[4 * j + 3] = q.w; }
-        X.max_d = zh_lengths(df, ZH_DCODES, 15, dl, &sc);
-        for (int i = 0; i < ZH_DCODES_PAD; i++) X.dlen[i] = i < ZH_DCODES ? dl[i] : 0;
     }
 }
 
@@ -595,8 +657,10 @@ zs_offset_kernel(const ZsStream *__restrict__ streams, uint4 *__restrict__ blk_m
 
 /* ======================= K3: bit packing, one CTA per block ======================= */
 #define ZE_THREADS 256
-#define ZE_SUB 8                                    /* symbols per thread and round */
-#define ZE_ROUNDS 4
+#ifndef ZE_SUB
+#define ZE_SUB 8                                    /* symbols per thread and round (16: no gain, measured) */
+#endif
+#define ZE_ROUNDS (ZS_BLOCK_SYMS / (ZE_THREADS * ZE_SUB))
 #define ZE_STAGE_WORDS 12480                        /* 16 + 3072 + 8192*48 + 15 + 47 bits, rounded up */
 
 struct ZeSmem {
@@ -840,7 +904,7 @@ extern "C" cudaError_t zs_block_stage_launch(cudaStream_t st, uint32_t slot0, ui
     {
         const size_t smem = sizeof(uint16_t) * 2 * ZH_LCODES_PAD * ZMG_THREADS;
         cudaFuncSetAttribute(zs_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        zs_merge_kernel<<<(nslots + ZMG_THREADS - 1) / ZMG_THREADS, 2 * ZMG_THREADS, smem, st>>>(scratch, blk_used);
+        zs_merge_kernel<<<(nslots + ZMG_THREADS - 1) / ZMG_THREADS, ZMG_THREADS, smem, st>>>(scratch, blk_used);
     }
     zs_block_kernel<1><<<nslots, ZB_THREADS, 0, st>>>(chunks, blk_chunk, sym, chunk_nsym, blk_in_start, blocks, blk_meta, scratch, blk_used, P, slot0);
     return cudaGetLastError();
