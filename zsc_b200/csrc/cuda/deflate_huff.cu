@@ -592,22 +592,37 @@ __device__ __forceinline__ zk_elem zk_shfl_up(zk_elem e, int o)
     return r;
 }
 
+/* PHASE 2: a stream's whole offset scan on one CTA.  PHASE 0 / 1: one large stream cut into gridDim.y parts of consecutive
+ * block slots (the one CTA of a 1 GiB stream spent 0.2 ms on its 131 072 strided 16-byte records — one SM's load/store
+ * unit, a sector per request): phase 0 leaves the composed element of every part in part_total, phase 1 repeats the scan
+ * of its part, puts the parts before it in front and writes the offsets; part 0 also writes the stream's results. */
+#define ZO_PARTS_MAX 64
+template <int PHASE>
 __global__ void __launch_bounds__(ZO_THREADS_MAX)
 zs_offset_kernel(const ZsStream *__restrict__ streams, uint4 *__restrict__ blk_meta, uint64_t *__restrict__ blk_bitoff,
                  const ZsAdlerAcc *__restrict__ adler_acc, uint32_t *__restrict__ comp32,
                  int32_t *__restrict__ res_ret, uint32_t *__restrict__ res_produced,
-                 uint32_t *__restrict__ res_check, ZsLzParams P)
+                 uint32_t *__restrict__ res_check, ZsLzParams P, zk_elem *__restrict__ part_total)
 {
     __shared__ zk_elem wpart[32];
+    __shared__ zk_elem s_pre;
     __shared__ int s_fail;
     const uint32_t sidx = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t part = PHASE == 2 ? 0u : blockIdx.y, nparts = PHASE == 2 ? 1u : gridDim.y;
     const ZsStream st = streams[sidx];
-    const uint32_t per = (st.blk_count + nthr - 1) / nthr;
-    const uint32_t lo = min(st.blk_count, tid * per), hi = min(st.blk_count, lo + per);
+    const uint32_t per_part = (st.blk_count + nparts - 1) / nparts;
+    const uint32_t p_lo = min(st.blk_count, part * per_part), p_hi = min(st.blk_count, p_lo + per_part);
+    const uint32_t per = (p_hi - p_lo + nthr - 1) / nthr;
+    const uint32_t lo = min(p_hi, p_lo + tid * per), hi = min(p_hi, lo + per);
+    /* a thread's records are read eight at a time (the loop is a chain of compositions) */
     zk_elem mine = zk_ident();
-    for (uint32_t i = lo; i < hi; i++) {
-        const uint4 mt = blk_meta[st.blk_first + i];
-        mine = zk_compose(mine, zk_elem_of_block(mt.x, mt.y, mt.z, mt.w, P.wrap));
+    for (uint32_t i = lo; i < hi; i += 8) {
+        uint4 mt[8];
+#pragma unroll
+        for (uint32_t u = 0; u < 8; u++) mt[u] = (i + u < hi) ? blk_meta[st.blk_first + i + u] : make_uint4(ZH_UNUSED, 0, 0, 0);
+#pragma unroll
+        for (uint32_t u = 0; u < 8; u++)
+            if (i + u < hi) mine = zk_compose(mine, zk_elem_of_block(mt[u].x, mt[u].y, mt[u].z, mt[u].w, P.wrap));
     }
     /* exclusive scan of the per-thread elements (composition is associative, not commutative) */
     zk_elem inc = mine;
@@ -625,33 +640,53 @@ zs_offset_kernel(const ZsStream *__restrict__ streams, uint4 *__restrict__ blk_m
         if (lane == 0) wex = zk_ident();
         wpart[lane] = wex;                                   /* exclusive prefix of the warp totals */
         if (lane == 31) {
-            const uint64_t x0 = st.comp_off * 8ull;
-            const uint64_t xe = zk_apply(wi, x0);
-            const uint64_t bytes = (xe - x0 + 7) >> 3;
-            const int fail = bytes > st.comp_cap;
-            s_fail = fail;
-            res_ret[sidx] = fail ? -5 /* Z_BUF_ERROR */ : 0;
-            res_produced[sidx] = fail ? 0u : (uint32_t)bytes;
-            uint32_t a = (uint32_t)(adler_acc[sidx].s1 % ZS_ADLER_BASE), bsum = (uint32_t)(adler_acc[sidx].s2 % ZS_ADLER_BASE);
-            /* adler32 of the stream = (1 + sum bytes, len + weighted sum) mod 65521 */
-            a = (a + 1) % ZS_ADLER_BASE;
-            bsum = (uint32_t)((bsum + (uint64_t)st.raw_len) % ZS_ADLER_BASE);
-            res_check[sidx] = (bsum << 16) | a;
-            if (!fail && (xe & 31)) comp32[xe >> 5] = 0;
+            if (PHASE == 0) part_total[sidx * ZO_PARTS_MAX + part] = wi;
+            else {
+                zk_elem pre = zk_ident(), all = wi;          /* the parts before this one; the whole stream */
+                if (PHASE == 1) {
+                    for (uint32_t q = 0; q < part; q++) pre = zk_compose(pre, part_total[sidx * ZO_PARTS_MAX + q]);
+                    all = zk_compose(pre, wi);
+                    for (uint32_t q = part + 1; q < nparts; q++) all = zk_compose(all, part_total[sidx * ZO_PARTS_MAX + q]);
+                }
+                s_pre = pre;
+                const uint64_t x0 = st.comp_off * 8ull;
+                const uint64_t xe = zk_apply(all, x0);
+                const uint64_t bytes = (xe - x0 + 7) >> 3;
+                const int fail = bytes > st.comp_cap;
+                s_fail = fail;
+                if (part == 0) {
+                    res_ret[sidx] = fail ? -5 /* Z_BUF_ERROR */ : 0;
+                    res_produced[sidx] = fail ? 0u : (uint32_t)bytes;
+                    uint32_t a = (uint32_t)(adler_acc[sidx].s1 % ZS_ADLER_BASE), bsum = (uint32_t)(adler_acc[sidx].s2 % ZS_ADLER_BASE);
+                    /* adler32 of the stream = (1 + sum bytes, len + weighted sum) mod 65521 */
+                    a = (a + 1) % ZS_ADLER_BASE;
+                    bsum = (uint32_t)((bsum + (uint64_t)st.raw_len) % ZS_ADLER_BASE);
+                    res_check[sidx] = (bsum << 16) | a;
+                    if (!fail && (xe & 31)) comp32[xe >> 5] = 0;
+                }
+            }
         }
     }
+    if (PHASE == 0) return;
     __syncthreads();
     zk_elem before = zk_shfl_up(inc, 1);
     if (lane == 0) before = zk_ident();
-    before = zk_compose(wpart[warp], before);
+    before = zk_compose(s_pre, zk_compose(wpart[warp], before));
     const int fail = s_fail;
     uint64_t x = zk_apply(before, st.comp_off * 8ull);
-    for (uint32_t i = lo; i < hi; i++) {
-        uint4 mt = blk_meta[st.blk_first + i];
-        if (mt.x == ZH_UNUSED) continue;
-        blk_bitoff[st.blk_first + i] = x;
-        if (fail) { mt.w |= ZB_STREAM_FAILED; blk_meta[st.blk_first + i] = mt; } else comp32[x >> 5] = 0;
-        x = zk_apply(zk_elem_of_block(mt.x, mt.y, mt.z, mt.w & ~(uint32_t)ZB_STREAM_FAILED, P.wrap), x);
+    for (uint32_t i0 = lo; i0 < hi; i0 += 8) {
+        uint4 m8[8];
+#pragma unroll
+        for (uint32_t u = 0; u < 8; u++) m8[u] = (i0 + u < hi) ? blk_meta[st.blk_first + i0 + u] : make_uint4(ZH_UNUSED, 0, 0, 0);
+#pragma unroll
+        for (uint32_t u = 0; u < 8; u++) {
+            const uint32_t i = i0 + u;
+            uint4 mt = m8[u];
+            if (mt.x == ZH_UNUSED) continue;                 /* (also the records beyond hi) */
+            blk_bitoff[st.blk_first + i] = x;
+            if (fail) { mt.w |= ZB_STREAM_FAILED; blk_meta[st.blk_first + i] = mt; } else comp32[x >> 5] = 0;
+            x = zk_apply(zk_elem_of_block(mt.x, mt.y, mt.z, mt.w & ~(uint32_t)ZB_STREAM_FAILED, P.wrap), x);
+        }
     }
 }
 
@@ -889,6 +924,7 @@ zs_encode_kernel(const zh_block *__restrict__ blocks, const uint32_t *__restrict
 
 extern "C" size_t zs_encode_smem_bytes(void) { return sizeof(ZeSmem); }
 extern "C" size_t zs_block_scratch_bytes(void) { return sizeof(ZbScratch); }
+extern "C" size_t zs_offset_part_bytes(void) { return sizeof(zk_elem) * ZO_PARTS_MAX; }
 
 /* The block stage (histogram + sort, tree merges, codes + header) of the block slots [slot0, slot0 + nslots). */
 extern "C" cudaError_t zs_block_stage_launch(cudaStream_t st, uint32_t slot0, uint32_t nslots,
@@ -918,7 +954,7 @@ extern "C" cudaError_t zs_huff_launch(cudaStream_t st, uint32_t nblk_slots, uint
                                       const uint8_t *raw, uint8_t *comp, int32_t *res_ret,
                                       uint32_t *res_produced, uint32_t *res_check, ZsLzParams P,
                                       cudaEvent_t ev_after_offset,
-                                      uint32_t nchunks, void *blk_meta_v, unsigned long long *blk_bitoff_v)
+                                      uint32_t nchunks, void *blk_meta_v, unsigned long long *blk_bitoff_v, void *off_part_v /* zs_offset_part_bytes() */)
 {
     if (nblk_slots == 0 || nstreams == 0) return cudaSuccess;
     uint4 *blk_meta = reinterpret_cast<uint4 *>(blk_meta_v);
@@ -926,8 +962,15 @@ extern "C" cudaError_t zs_huff_launch(cudaStream_t st, uint32_t nblk_slots, uint
     zs_stored_merge_kernel<<<(nchunks + ZM_THREADS - 1) / ZM_THREADS, ZM_THREADS, 0, st>>>(chunks, nchunks, blocks, blk_meta);
     /* few streams with many blocks each: wide CTAs; many small streams: narrow ones */
     const uint32_t othreads = (nblk_slots / nstreams >= 1024u) ? ZO_THREADS_MAX : 128u;
-    zs_offset_kernel<<<nstreams, othreads, 0, st>>>(streams, blk_meta, blk_bitoff, adler_acc,
-                                                    reinterpret_cast<uint32_t *>(comp), res_ret, res_produced, res_check, P);
+    zk_elem *part_total = reinterpret_cast<zk_elem *>(off_part_v);
+    if (nstreams == 1 && nblk_slots >= 16384u && part_total) {
+        /* one large stream: its slots in parts of about 2048 */
+        const dim3 grid(1, min((uint32_t)ZO_PARTS_MAX, nblk_slots / 2048u));
+        zs_offset_kernel<0><<<grid, 256, 0, st>>>(streams, blk_meta, blk_bitoff, adler_acc, reinterpret_cast<uint32_t *>(comp), res_ret, res_produced, res_check, P, part_total);
+        zs_offset_kernel<1><<<grid, 256, 0, st>>>(streams, blk_meta, blk_bitoff, adler_acc, reinterpret_cast<uint32_t *>(comp), res_ret, res_produced, res_check, P, part_total);
+    } else
+        zs_offset_kernel<2><<<nstreams, othreads, 0, st>>>(streams, blk_meta, blk_bitoff, adler_acc,
+                                                           reinterpret_cast<uint32_t *>(comp), res_ret, res_produced, res_check, P, part_total);
     if (ev_after_offset) cudaEventRecord(ev_after_offset, st);
     cudaFuncSetAttribute(zs_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ZeSmem));
     cudaFuncSetAttribute(zs_encode_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);

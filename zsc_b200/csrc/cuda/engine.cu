@@ -23,7 +23,8 @@ extern "C" cudaError_t zs_block_stage_launch(cudaStream_t, uint32_t, uint32_t, c
                                              const uint32_t *, const uint32_t *, zh_block *, ZsLzParams, void *, void *, uint32_t *);
 extern "C" cudaError_t zs_huff_launch(cudaStream_t, uint32_t, uint32_t, const ZsChunk *, const uint32_t *, const ZsStream *, const uint32_t *,
                                       zh_block *, const ZsAdlerAcc *, const uint8_t *, uint8_t *, int32_t *, uint32_t *, uint32_t *, ZsLzParams,
-                                      cudaEvent_t, uint32_t, void *, unsigned long long *);
+                                      cudaEvent_t, uint32_t, void *, unsigned long long *, void *);
+extern "C" size_t zs_offset_part_bytes(void);
 extern "C" size_t zs_block_scratch_bytes(void);
 extern "C" cudaError_t zs_adler_chunks_launch(cudaStream_t, uint32_t, const uint8_t *, const ZsChunk *, const ZsStream *, ZsAdlerAcc *);
 extern "C" cudaError_t zs_adler_flat_launch(cudaStream_t, const uint8_t *, uint64_t, ZsAdlerAcc *, int);
@@ -107,6 +108,7 @@ struct zscgpu_engine {
     zh_block *d_blocks;
     uint4 *d_blk_meta;            /* per block slot: type, body_bits, in_len, flags (what the offset pass reads) */
     unsigned long long *d_blk_bitoff;
+    uint8_t *d_off_part;              /* the part totals of a large stream's offset scan, one set per slice (zs_offset_part_bytes) */
     uint8_t *d_blk_scratch;           /* per block slot: what the three block kernels hand to each other (deflate_huff.cu ZbScratch) */
     uint32_t *d_blk_used;             /* [0] = number of used block slots of the launch, then their indices */
     ZsAdlerAcc *d_adler;              /* per stream; slot max_streams is the flat-checksum slot */
@@ -239,6 +241,7 @@ static int zs_init_engine(zscgpu_engine *e, const zscgpu_config &cfg, const cuda
     ZS_CUDA_CHECK(zs_dev(&e->d_blocks, e->blk_cap));
     ZS_CUDA_CHECK(zs_dev(&e->d_blk_meta, e->blk_cap));
     ZS_CUDA_CHECK(zs_dev(&e->d_blk_bitoff, e->blk_cap));
+    ZS_CUDA_CHECK(zs_dev(&e->d_off_part, 2 * zs_offset_part_bytes()));
     ZS_CUDA_CHECK(zs_dev(&e->d_blk_scratch, (size_t)e->blk_cap * zs_block_scratch_bytes()));
     ZS_CUDA_CHECK(zs_dev(&e->d_blk_used, (size_t)e->blk_cap + 2));
     ZS_CUDA_CHECK(zs_dev(&e->d_adler, cfg.max_streams + 1));
@@ -305,7 +308,7 @@ extern "C" void zscgpu_destroy(zscgpu_engine *e)
     cudaFreeHost(e->h_chunks); cudaFree(e->d_chunks);
     cudaFreeHost(e->h_streams); cudaFree(e->d_streams);
     cudaFreeHost(e->h_blk_chunk); cudaFree(e->d_blk_chunk);
-    cudaFree(e->d_chunk_nsym); cudaFree(e->d_blk_in_start); cudaFree(e->d_blocks); cudaFree(e->d_blk_meta); cudaFree(e->d_blk_bitoff); cudaFree(e->d_blk_scratch); cudaFree(e->d_blk_used);
+    cudaFree(e->d_chunk_nsym); cudaFree(e->d_blk_in_start); cudaFree(e->d_blocks); cudaFree(e->d_blk_meta); cudaFree(e->d_blk_bitoff); cudaFree(e->d_off_part); cudaFree(e->d_blk_scratch); cudaFree(e->d_blk_used);
     cudaFree(e->d_adler); cudaFree(e->d_crc); cudaFree(e->d_ctr); cudaFree(e->d_spec_rec); cudaFree(e->d_sslots); cudaFree(e->d_sin); cudaFree(e->d_sout); cudaFree(e->d_sres); cudaFreeHost(e->h_sres); cudaFree(e->d_aux); cudaFreeHost(e->h_aux); cudaFree(e->d_cand); cudaFreeHost(e->h_cand);
     free(e->sec_start); free(e->sec_st); free(e->sec_r1);
     cudaFree(e->d_ret); cudaFree(e->d_produced); cudaFree(e->d_consumed); cudaFree(e->d_check);
@@ -613,7 +616,8 @@ static int zs_deflate_launch_slice(zscgpu_engine *e, const ZsSlice &sl, uint32_t
     if (sl.timed) ZS_CUDA_CHECK(cudaEventRecord(e->ev[11], st));
     ZS_CUDA_CHECK(zs_huff_launch(st, nb, n, chunks, blk_chunk, streams, sym, blocks, adler, e->d_raw, e->d_comp,
                                  e->d_ret + sl.stream0, e->d_produced + sl.stream0, e->d_check + sl.stream0, L,
-                                 sl.timed ? e->ev[12] : nullptr, nc, blk_meta, e->d_blk_bitoff + sl.blk0));
+                                 sl.timed ? e->ev[12] : nullptr, nc, blk_meta, e->d_blk_bitoff + sl.blk0,
+                                 e->d_off_part + (sl.blk0 ? zs_offset_part_bytes() : 0)));
     if (sl.timed) ZS_CUDA_CHECK(cudaEventRecord(e->ev[13], st));
     ZS_CUDA_CHECK(cudaMemcpyAsync(e->h_ret + sl.stream0, e->d_ret + sl.stream0, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
     ZS_CUDA_CHECK(cudaMemcpyAsync(e->h_produced + sl.stream0, e->d_produced + sl.stream0, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, st));
