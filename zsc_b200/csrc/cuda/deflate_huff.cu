@@ -31,12 +31,12 @@ struct ZbSmem {
 
 /* What the three block kernels hand to each other, per block slot (global memory):
  * zs_block_kernel<0> leaves the sorted keys, the reduced histograms and the distance code lengths;
- * zs_merge_kernel adds the parent links of the literal/length tree; zs_block_kernel<1> reads it all back. */
+ * zs_merge_kernel adds the leaf depths of the literal/length tree; zs_block_kernel<1> reads it all back. */
 struct __align__(16) ZbScratch {
     uint32_t key[ZH_LCODES_PAD];
     uint32_t lfreq[ZH_LCODES_PAD];
     uint32_t dfreq[ZH_DCODES_PAD];
-    uint16_t parent[2 * ZH_LCODES_PAD];
+    uint8_t depth[ZH_LCODES_PAD];           /* depth of the i-th sorted leaf in the literal/length tree (not yet limited) */
     uint8_t dlen[ZH_DCODES_PAD];
     int32_t m, max_l, max_d, pad;
 };
@@ -239,21 +239,16 @@ zs_block_kernel(const ZsChunk *__restrict__ chunks, const uint32_t *__restrict__
     if (tid < 16) { S.bl_count[tid] = 0; S.cnt_l[tid] = 0; S.cnt_d[tid] = 0; }
     if (tid == 0) { S.m = X.m; S.max_l = X.max_l; S.max_d = X.max_d; S.overflow = 0; }
     for (uint32_t i = tid; i < ZH_LCODES_PAD; i += ZB_THREADS) { S.sc.key[i] = X.key[i]; S.lfreq[0][i] = X.lfreq[i]; S.sc.llen[i] = 0; }
-    for (uint32_t i = tid; i < 2 * ZH_LCODES_PAD; i += ZB_THREADS) S.sc.parent[i] = X.parent[i];
     if (tid < ZH_DCODES_PAD) { S.dfreq[0][tid] = X.dfreq[tid]; S.sc.dlen[tid] = X.dlen[tid]; }
     __syncthreads();
     m = S.m;
   }
-    /* ---- leaf depths in parallel, clipped to 15 ---- */
-    {
-        const uint32_t root = 2u * (uint32_t)m - 2u;
-        for (int i = (int)tid; i < m; i += ZB_THREADS) {
-            uint32_t d = 1, p = S.sc.parent[i];
-            while (p != root) { p = S.sc.parent[p]; d++; }
-            if (d > 15) { d = 15; atomicAdd(&S.overflow, 1); }
-            S.sc.depth[i] = (uint8_t)d;
-            atomicAdd(&S.bl_count[d], 1u);
-        }
+    /* ---- leaf depths (from zs_merge_kernel), clipped to 15 ---- */
+    for (int i = (int)tid; i < m; i += ZB_THREADS) {
+        uint32_t d = X.depth[i];
+        if (d > 15) { d = 15; atomicAdd(&S.overflow, 1); }
+        S.sc.depth[i] = (uint8_t)d;
+        atomicAdd(&S.bl_count[d], 1u);
     }
     __syncthreads();
     if (S.overflow > 0) { if (tid == 0) zh_repair(15, S.bl_count, &S.sc); __syncthreads(); }
@@ -538,18 +533,30 @@ zs_merge_kernel(ZbScratch *__restrict__ scratch, const uint32_t *__restrict__ us
             wl[(4 * j + 2) * ZMG_THREADS] = (uint16_t)(q.z >> 9); wl[(4 * j + 3) * ZMG_THREADS] = (uint16_t)(q.w >> 9);
         }
     }
+    /* A node that leaves its queue leaves a free slot behind: its parent's number goes there (shared memory; as scattered
+       16-bit stores to global memory the links were what this kernel waited for).  Afterwards the slots of the internal
+       nodes turn from parents into depths, root first, and the depths of the leaves go out four to a word. */
     int a = 0, b = 0, e = 0;                               /* leaves taken, internal nodes taken, internal nodes made */
-    uint32_t la = wl[0], ib = 0xFFFFFFFFu;                  /* heads of the two queues */
+    uint32_t la = wl[0], ib = 0xFFFFFFFFu;                 /* heads of the two queues */
     for (int it = 0; it < m - 1; it++) {
-        uint32_t sum; int x0, x1;
-        if (a < m && la <= ib) { x0 = a++; sum = la; la = a < m ? wl[a * ZMG_THREADS] : 0xFFFFFFFFu; }
-        else { x0 = m + b++; sum = ib; ib = b < e ? w[b * ZMG_THREADS] : 0xFFFFFFFFu; }
-        if (a < m && la <= ib) { x1 = a++; sum += la; la = a < m ? wl[a * ZMG_THREADS] : 0xFFFFFFFFu; }
-        else { x1 = m + b++; sum += ib; ib = b < e ? w[b * ZMG_THREADS] : 0xFFFFFFFFu; }
+        uint32_t sum;
+        if (a < m && la <= ib) { sum = la; wl[a * ZMG_THREADS] = (uint16_t)e; a++; la = a < m ? wl[a * ZMG_THREADS] : 0xFFFFFFFFu; }
+        else { sum = ib; w[b * ZMG_THREADS] = (uint16_t)e; b++; ib = b < e ? w[b * ZMG_THREADS] : 0xFFFFFFFFu; }
+        if (a < m && la <= ib) { sum += la; wl[a * ZMG_THREADS] = (uint16_t)e; a++; la = a < m ? wl[a * ZMG_THREADS] : 0xFFFFFFFFu; }
+        else { sum += ib; w[b * ZMG_THREADS] = (uint16_t)e; b++; ib = b < e ? w[b * ZMG_THREADS] : 0xFFFFFFFFu; }
         w[e * ZMG_THREADS] = (uint16_t)sum;
-        X.parent[x0] = (uint16_t)(m + e); X.parent[x1] = (uint16_t)(m + e);
         if (b == e) ib = sum;                              /* the queue was empty: the new node is its head */
         e++;
+    }
+    w[(e - 1) * ZMG_THREADS] = 0;                          /* the root */
+    for (int i = e - 2; i >= 0; i--) { const uint32_t p = w[i * ZMG_THREADS]; w[i * ZMG_THREADS] = (uint16_t)(w[p * ZMG_THREADS] + 1u); }
+    uint32_t *d32 = reinterpret_cast<uint32_t *>(X.depth);
+    for (int i = 0; i < m; i += 4) {
+        uint32_t v = 0;
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+            if (i + u < m) { const uint32_t d = (uint32_t)w[(uint32_t)wl[(i + u) * ZMG_THREADS] * ZMG_THREADS] + 1u; v |= (d > 255u ? 255u : d) << (8 * u); }
+        d32[i >> 2] = v;
     }
 }
 
