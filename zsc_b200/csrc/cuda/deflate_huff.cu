@@ -25,6 +25,7 @@ struct ZbSmem {
     uint32_t red[2][ZB_WARPS];
     uint32_t scan[ZB_WARPS];
     uint32_t ccnt[9][16];
+    uint16_t lct[256];      /* len - 3 -> 257 + length code */
     zh_decision D;
     int m, max_l, max_d, overflow;
 };
@@ -145,6 +146,7 @@ zs_block_kernel(const ZsChunk *__restrict__ chunks, const uint32_t *__restrict__
     for (uint32_t i = tid; i < ZB_WARPS * ZH_DCODES_PAD; i += ZB_THREADS) (&S.dfreq[0][0])[i] = 0;
     if (tid < 16) { S.bl_count[tid] = 0; S.cnt_l[tid] = 0; S.cnt_d[tid] = 0; }
     if (tid == 0) { S.m = 0; S.max_l = 0; S.overflow = 0; }
+    for (uint32_t i = tid; i < 256; i += ZB_THREADS) S.lct[i] = (uint16_t)(257 + zs_len_code(i));
     __syncthreads();
     /* four 16-byte loads in flight per thread, then branch-light counting (the symbol arena is 16-byte
        aligned per block: sym_off and ZS_BLOCK_SYMS are multiples of four) */
@@ -166,14 +168,13 @@ zs_block_kernel(const ZsChunk *__restrict__ chunks, const uint32_t *__restrict__
                     const uint32_t sv = e == 0 ? v[u].x : e == 1 ? v[u].y : e == 2 ? v[u].z : v[u].w;
                     if (i + (uint32_t)e < cnt) {
                         const bool mt = (sv & ZS_MATCH) != 0;
-                        const uint32_t lc = (sv >> 16) & 0xFFu, d = sv & 0x7FFFu;
-                        const uint32_t nl_ = 31u - (uint32_t)__clz((int)(lc | 4u));
-                        uint32_t lcode = ((nl_ - 1u) << 2) | ((lc >> (nl_ - 2u)) & 3u);
-                        lcode = lc < 4u ? lc : (lc == 255u ? 28u : lcode);
+                        const uint32_t d = sv & 0x7FFFu;
+                        /* literal: its byte; match: 257 + length code, from a table (ten instructions otherwise) */
+                        const uint32_t li = mt ? (uint32_t)S.lct[(sv >> 16) & 0xFFu] : (sv & 0xFFu);
                         const uint32_t nd_ = 31u - (uint32_t)__clz((int)(d | 2u));
                         uint32_t dcode = (nd_ << 1) | ((d >> (nd_ - 1u)) & 1u);
                         dcode = d < 2u ? d : dcode;
-                        atomicAdd(&S.lfreq[warp][mt ? 257u + lcode : (sv & 0xFFu)], 1u);
+                        atomicAdd(&S.lfreq[warp][li], 1u);
                         if (mt) atomicAdd(&S.dfreq[warp][dcode], 1u);
                     }
                 }
