@@ -622,8 +622,10 @@ static int zs_deflate_launch_slice(zscgpu_engine *e, const ZsSlice &sl, uint32_t
     ZS_CUDA_CHECK(cudaMemcpyAsync(e->h_ret + sl.stream0, e->d_ret + sl.stream0, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
     ZS_CUDA_CHECK(cudaMemcpyAsync(e->h_produced + sl.stream0, e->d_produced + sl.stream0, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, st));
     ZS_CUDA_CHECK(cudaMemcpyAsync(e->h_check + sl.stream0, e->d_check + sl.stream0, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, st));
-    e->launches = 8;   /* adler, lz, block stage (histogram / tree merges / codes), stored-run merge, offset, encode */
-    e->launches_total += 8;
+    /* adler, lz, block stage (histogram / tree merges / codes), stored-run merge, offset (two launches for one large stream:
+       zs_huff_launch), encode */
+    e->launches = 8 + ((n == 1 && nb >= 16384u) ? 1 : 0);
+    e->launches_total += (uint64_t)e->launches;
     return ZSCGPU_OK;
 }
 static int zs_deflate_launch_all(zscgpu_engine *e)
