@@ -112,6 +112,54 @@ __device__ __forceinline__ int zb_lengths_warp(uint32_t f, int n, int maxbits, u
     return max_code;
 }
 
+/* Sorts key[0, m), m <= 128 * EPT, ascending into key[] (padded with 0xFFFFFFFF to a multiple of four); A: 128 * EPT
+ * words of shared scratch.  Thread t of warp w holds the elements w * 32 * EPT + q * 32 + lane, q < EPT. */
+template <int EPT>
+__device__ __forceinline__ void zb_sort_keys(uint32_t *A, uint32_t *key, int m, uint32_t tid)
+{
+    static_assert(ZB_THREADS == 128, "four warps");
+    constexpr uint32_t N = 128u * EPT;
+    const uint32_t lane = tid & 31, base = (tid >> 5) * 32u * EPT + lane;
+    uint32_t x[EPT];
+#pragma unroll
+    for (int q = 0; q < EPT; q++) { const uint32_t i = base + 32u * q; x[q] = (int)i < m ? key[i] : 0xFFFFFFFFu; }
+#pragma unroll
+    for (uint32_t kk = 2; kk <= N; kk <<= 1) {
+#pragma unroll
+        for (uint32_t j = kk >> 1; j > 0; j >>= 1) {
+            if (j >= 32u * EPT) {                            /* the partner is in another warp */
+                __syncthreads();
+#pragma unroll
+                for (int q = 0; q < EPT; q++) A[base + 32u * q] = x[q];
+                __syncthreads();
+#pragma unroll
+                for (int q = 0; q < EPT; q++) {
+                    const uint32_t i = base + 32u * q, y = A[i ^ j];
+                    x[q] = (((i & j) == 0u) == ((i & kk) == 0u)) ? min(x[q], y) : max(x[q], y);
+                }
+            } else if (j >= 32u) {                           /* in another register of this thread */
+#pragma unroll
+                for (int q = 0; q < EPT; q++)
+                    if ((q & (int)(j >> 5)) == 0) {
+                        const int r = q | (int)(j >> 5);
+                        const uint32_t lo = min(x[q], x[r]), hi = max(x[q], x[r]);
+                        const bool up = ((base + 32u * q) & kk) == 0u;
+                        x[q] = up ? lo : hi; x[r] = up ? hi : lo;
+                    }
+            } else {                                         /* in another lane */
+#pragma unroll
+                for (int q = 0; q < EPT; q++) {
+                    const uint32_t i = base + 32u * q, y = __shfl_xor_sync(0xFFFFFFFFu, x[q], (int)j);
+                    x[q] = (((i & j) == 0u) == ((i & kk) == 0u)) ? min(x[q], y) : max(x[q], y);
+                }
+            }
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < EPT; q++) { const uint32_t i = base + 32u * q; if ((int)i < ((m + 3) & ~3)) key[i] = x[q]; }
+}
+
 /* The serial recipe of zh_build_block (huff_build.h) spread over the CTA: key collection, sort, leaf depths,
  * costs, canonical codes and the header bit string run on all threads; the distance tree and the 19-symbol
  * code-length tree are built by one warp each (zb_lengths_warp).  The two-queue merge of the literal/length tree — an inherently serial
@@ -208,25 +256,12 @@ zs_block_kernel(const ZsChunk *__restrict__ chunks, const uint32_t *__restrict__
         X.dlen[lane] = (uint8_t)dl;
         if (lane == 0) X.max_d = md;
     }
-    /* ---- bitonic sort of the keys (unique) on all threads, in a power-of-two array padded with 0xFFFFFFFF (a rank sort —
-            every key against every other — was 41 % of this kernel's instructions) ---- */
-    {
-        uint32_t *A = S.sc.w;                               /* 2 * ZH_LCODES_PAD words, free until the merge starts */
-        static_assert(2 * ZH_LCODES_PAD >= 512 && ZH_LCODES <= 512, "the sort array holds 512 keys");
-        const uint32_t N = m <= 128 ? 128u : m <= 256 ? 256u : 512u;
-        for (uint32_t i = tid; i < N; i += ZB_THREADS) A[i] = (int)i < m ? S.sc.key[i] : 0xFFFFFFFFu;
-        __syncthreads();
-        for (uint32_t kk = 2; kk <= N; kk <<= 1)
-            for (uint32_t j = kk >> 1; j > 0; j >>= 1) {
-                for (uint32_t p = tid; p < (N >> 1); p += ZB_THREADS) {
-                    const uint32_t i = ((p & ~(j - 1u)) << 1) | (p & (j - 1u)), l = i | j;
-                    const uint32_t x = A[i], y = A[l];
-                    if ((x > y) == ((i & kk) == 0u)) { A[i] = y; A[l] = x; }
-                }
-                __syncthreads();
-            }
-        for (int i = (int)tid; i < ((m + 3) & ~3); i += ZB_THREADS) S.sc.key[i] = A[i];     /* the pad to a multiple of 4 is 0xFFFFFFFF */
-    }
+    /* ---- bitonic sort of the keys (unique) on all threads, 128 * EPT of them padded with 0xFFFFFFFF, in registers:
+            strides below 32 by shuffles, strides inside a thread by register swaps, only the strides across warps through
+            shared memory (3 of the 45 steps of 512 keys) ---- */
+    if (m <= 128) zb_sort_keys<1>(S.sc.w, S.sc.key, m, tid);
+    else if (m <= 256) zb_sort_keys<2>(S.sc.w, S.sc.key, m, tid);
+    else zb_sort_keys<4>(S.sc.w, S.sc.key, m, tid);
     __syncthreads();
     /* ---- the hand-over (the distance tree, a serial job of one thread, is built in zs_merge_kernel where every
        lane has one to build; in here it kept 127 threads waiting for 37 % of the kernel's time) ---- */
