@@ -1,4 +1,4 @@
-"""zscgpu_compress_host end to end (1 GiB, level 1, 256 KiB sections), wave sizes swept via ZSC_B200_WAVE_ROUNDS."""
+"""zscgpu_compress_host end to end (1 GiB, level 1, 256 KiB sections), sections per wave swept via ZSC_B200_WAVE_SECS (a tuning build: tools/build_variant.sh NAME -DZSC_TUNING)."""
 import os, sys, time, ctypes as C, zlib
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -11,8 +11,8 @@ dest = np.empty(n + (n >> 3), np.uint8)
 E.L.zscgpu_host_register(x.ctypes.data, x.nbytes); E.L.zscgpu_host_register(dest.ctypes.data, dest.nbytes)
 p = DeflateParams(262144, 1, 0, 1, 15, 0); r = Result()
 ref = None
-for rounds in (sys.argv[1].split(",") if len(sys.argv) > 1 else ["1", "2", "3"]):
-    os.environ["ZSC_B200_WAVE_ROUNDS"] = rounds
+for rounds in (sys.argv[1].split(",") if len(sys.argv) > 1 else ["296"]):
+    os.environ["ZSC_B200_WAVE_SECS"] = rounds
     ts = []
     for i in range(4):
         t0 = time.perf_counter()
@@ -24,5 +24,5 @@ for rounds in (sys.argv[1].split(",") if len(sys.argv) > 1 else ["1", "2", "3"])
         ref = (r.produced, h)
         ok = zlib.decompress(dest[:r.produced].tobytes()) == x.tobytes()
         print("inflates to the input:", ok, flush=True)
-    print("rounds", rounds, "ms", [round(t, 2) for t in ts], "GB/s", round(n / 1e6 / min(ts[1:]), 2), "produced", r.produced, "same bytes as first:", (r.produced, h) == ref, flush=True)
+    print("sections per wave", rounds, "ms", [round(t, 2) for t in ts], "GB/s", round(n / 1e6 / min(ts[1:]), 2), "produced", r.produced, "same bytes as first:", (r.produced, h) == ref, flush=True)
 E.close()

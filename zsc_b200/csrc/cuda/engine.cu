@@ -599,7 +599,8 @@ static int zs_deflate_launch_slice(zscgpu_engine *e, const ZsSlice &sl, uint32_t
     ZsAdlerAcc *adler = e->d_adler + sl.stream0;
     /* event slots 8..13 bracket the kernels of the last deflate launch (see zscgpu.h).  Measured and dropped: the
        adler32 pass or the block stage of one half on a side stream beside the LZ kernel — whatever runs beside that
-       kernel takes SM slots from it and the step stays within 0.1 ms of the plain sequence. */
+       kernel takes SM slots from it and the step stays within 0.1 ms of the plain sequence; the block stage and bit
+       packing of a wave on a high-priority stream of their own (a 1 GiB zscgpu_compress_host 25.4 -> 25.9 ms). */
     uint32_t *chunk_nsym = e->d_chunk_nsym + sl.chunk0, *blk_in_start = e->d_blk_in_start + sl.blk0 + (sl.blk0 ? 1 : 0);
     uint32_t *blk_chunk = e->d_blk_chunk + sl.blk0;
     zh_block *blocks = e->d_blocks + sl.blk0;
@@ -1143,6 +1144,9 @@ extern "C" int zscgpu_compress_host(zscgpu_engine *e, uint8_t *dest, uint32_t de
         const uint64_t round_secs = (2ull * (uint64_t)e->sms + cps - 1) / cps;       /* sections in one round of chunks (two CTAs per SM); two and three rounds per wave measured slower */
         const uint64_t k = ((64ull << 20) + round_secs * mbl - 1) / (round_secs * mbl);
         uint64_t W = k * round_secs * mbl;
+#ifdef ZSC_TUNING
+        if (getenv("ZSC_B200_WAVE_SECS")) W = (uint64_t)atoi(getenv("ZSC_B200_WAVE_SECS")) * mbl;   /* sections per wave (tools/prof_e2e2.py) */
+#endif
         uint64_t nw = ((uint64_t)src_len + W - 1) / W;
         if (nw > ZS_MAX_WAVES) { W = (((uint64_t)src_len + ZS_MAX_WAVES - 1) / ZS_MAX_WAVES + p->max_block_len - 1) / p->max_block_len * p->max_block_len; nw = ((uint64_t)src_len + W - 1) / W; }
         const uint64_t need = (uint64_t)src_len + ((uint64_t)src_len >> 3) + nw * (4096 + 64 + 8);
