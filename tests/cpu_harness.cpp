@@ -44,6 +44,25 @@ int h_inflate_spec(const uint8_t *in, uint32_t in_len, uint8_t *out, uint32_t ou
     res7[4] = r.data_errors; res7[5] = r.stored_check; res7[6] = r.have_check;
     return r.ret;
 }
+// zh_lengths itself (huff_build.h): the serial code-length build that the warp forms of deflate_huff.cu must equal
+int h_zh_lengths(const uint32_t *freq, int n, int maxbits, uint8_t *len_out)
+{
+    static zh_scratch sc;
+    return zh_lengths(freq, n, maxbits, len_out, &sc);
+}
+// leaf depths of the (unlimited) literal/length tree, by sorted leaf: what zs_merge_kernel hands to zs_block_kernel<1>
+int h_zh_leaf_depths(const uint32_t *freq, int n, uint8_t *depth_out)
+{
+    static zh_scratch sc;
+    int max_code;
+    const int m = zh_lengths_prepare(freq, n, &sc, &max_code);
+    zh_sort_keys(sc.key, m);
+    const int e = zh_merge(m, &sc);
+    sc.depth[e - 1] = 0;
+    for (int i = e - 2; i >= 0; i--) { int d = sc.depth[sc.parent[i]] + 1; sc.depth[i] = (uint8_t)(d > 250 ? 250 : d); }
+    for (int i = 0; i < m; i++) depth_out[i] = sc.depth[i];
+    return m;
+}
 void h_spec_stats(uint64_t *out8, int reset) { for (int i = 0; i < 16; i++) { out8[i] = zp_stat[i]; if (reset) zp_stat[i] = 0; } }
 
 // ---------------------------------------------------------------- LZ77 model (mirrors deflate_lz.cu)
