@@ -745,7 +745,7 @@ struct ZeSmem {
     uint32_t stage[ZE_STAGE_WORDS];
     uint32_t lcode[ZH_LCODES_PAD];
     uint32_t dcode[ZH_DCODES_PAD];
-    uint32_t lenmap[256];       /* (len code bits | extra << codelen) | nbits << 24 */
+    uint32_t tab[516];          /* code bits | count << 24 of: a literal byte [0, 256); a match length - 3 with its extra bits [256, 512); no symbol [512] */
     uint32_t wsum[2][ZE_THREADS / 32];
     uint32_t total_bits;
 };
@@ -762,23 +762,16 @@ __device__ __forceinline__ void ze_or_bits(uint32_t *stage, uint32_t pos, uint64
     if (sh + n > 32) atomicOr(&stage[w + 1], (uint32_t)(t >> 32));
 }
 
-/* code bits of one symbol, split in two parts of <= 20 and <= 28 bits */
-__device__ __forceinline__ void ze_sym_bits(const ZeSmem &S, uint32_t s, uint32_t &v0, uint32_t &n0, uint32_t &v1, uint32_t &n1)
+/* distance part of a match: code + extra bits (<= 28 bits) and their count */
+__device__ __forceinline__ void ze_dist_bits(const ZeSmem &S, uint32_t s, uint32_t &v1, uint32_t &n1)
 {
-    if (s & ZS_MATCH) {
-        uint32_t lm = S.lenmap[(s >> 16) & 0xFF];
-        v0 = lm & 0xFFFFFFu; n0 = lm >> 24;
-        uint32_t d = s & 0x7FFF;
-        uint32_t dc, eb, ev;
-        if (d < 4) { dc = d; eb = 0; ev = 0; }
-        else { uint32_t n = 31u - (uint32_t)__clz((int)d); dc = (n << 1) | ((d >> (n - 1)) & 1u); eb = n - 1; ev = d & ((1u << eb) - 1u); }
-        uint32_t e = S.dcode[dc];
-        uint32_t cl = e >> 16;
-        v1 = (e & 0xFFFFu) | (ev << cl); n1 = cl + eb;
-    } else {
-        uint32_t e = S.lcode[s & 0xFF];
-        v0 = e & 0xFFFFu; n0 = e >> 16; v1 = 0; n1 = 0;
-    }
+    const uint32_t d = s & 0x7FFF;
+    uint32_t dc, eb, ev;
+    if (d < 4) { dc = d; eb = 0; ev = 0; }
+    else { uint32_t n = 31u - (uint32_t)__clz((int)d); dc = (n << 1) | ((d >> (n - 1)) & 1u); eb = n - 1; ev = d & ((1u << eb) - 1u); }
+    const uint32_t e = S.dcode[dc];
+    const uint32_t cl = e >> 16;
+    v1 = (e & 0xFFFFu) | (ev << cl); n1 = cl + eb;
 }
 
 /* write one byte of the comp arena; words shared with neighbouring blocks go through atomics */
@@ -861,7 +854,10 @@ zs_encode_kernel(const zh_block *__restrict__ blocks, const uint32_t *__restrict
         uint32_t cl = e >> 16;
         uint32_t eb = (uint32_t)zh_extra_lbits(c);
         uint32_t ev = eb ? (lc & ((1u << eb) - 1u)) : 0u;
-        S.lenmap[lc] = ((e & 0xFFFFu) | (ev << cl)) | ((cl + eb) << 24);
+        S.tab[256 + lc] = ((e & 0xFFFFu) | (ev << cl)) | ((cl + eb) << 24);
+        const uint32_t el = S.lcode[lc];                   /* literal byte lc */
+        S.tab[lc] = (el & 0xFFFFu) | ((el >> 16) << 24);
+        if (tid == 0) S.tab[512] = 0;
     }
     /* stream header + block header bits */
     if (tid == 0 && pre_bits) ze_or_bits(S.stage, lbase, (uint32_t)P.zhdr, 16);
@@ -900,10 +896,13 @@ zs_encode_kernel(const zh_block *__restrict__ blocks, const uint32_t *__restrict
 #pragma unroll
             for (int i = 0; i < ZE_SUB; i++) {
                 const uint32_t sv = (i & 3) == 0 ? v[i >> 2].x : (i & 3) == 1 ? v[i >> 2].y : (i & 3) == 2 ? v[i >> 2].z : v[i >> 2].w;
-                uint32_t v0 = 0, n0 = 0, v1 = 0, n1 = 0;
-                if (s0 + i < nsym) ze_sym_bits(S, sv, v0, n0, v1, n1);
-                ca[i] = v0 | (n0 << 24); cb[i] = v1 | (1u << n1);
-                mybits += n0 + n1;
+                /* first part: one table for literals and match lengths, read by every lane; the distance part only by matches */
+                const bool ok = s0 + i < nsym, mt = ok && (sv & ZS_MATCH);
+                const uint32_t t = S.tab[!ok ? 512u : (sv & ZS_MATCH) ? 256u + ((sv >> 16) & 0xFFu) : (sv & 0xFFu)];
+                uint32_t c = 1u;
+                if (mt) { uint32_t v1, n1; ze_dist_bits(S, sv, v1, n1); c = v1 | (1u << n1); mybits += n1; }
+                ca[i] = t; cb[i] = c;
+                mybits += t >> 24;
             }
         }
         uint32_t inc = mybits;
